@@ -1,0 +1,178 @@
+"""Synthetic weights and batches for the LLaMA-VQA training step.
+
+No datasets, tokenizer model or LLaMA checkpoints are available offline, so every test and the
+benchmark run on synthetic inputs that imitate the reference's batch contract
+(`/root/reference/dataloader/__init__.py:28-90`, `dataloader/base_dataset.py:30-174`) and the token
+layout produced by `llama/tokenizer.py:44-211`.
+
+Two generators live here:
+
+* ``hash_normal`` – a pure integer-hash pseudo-normal generator (splitmix64 + Irwin-Hall). It is
+  bit-reproducible on every platform/torch version, which lets the golden fixtures under
+  ``tests/golden/`` store only *results* (losses, gradients) and regenerate the weights.
+* ``synthetic_batch`` – the NExT-QA / DramaQA / TVQA-shaped batch dict.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+_MASK64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15)) & _MASK64
+    z = x
+    z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & _MASK64
+    z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & _MASK64
+    return z ^ (z >> np.uint64(31))
+
+
+def hash_normal(shape, seed: int, std: float = 1.0, mean: float = 0.0) -> torch.Tensor:
+    """Approximately normal fp32 tensor from integer hashing only (exactly reproducible).
+
+    Sum of four 16-bit uniforms (Irwin-Hall, n=4) centred and scaled to unit variance; the result
+    is then rounded to bf16-representable values so that fp16, bf16 and fp32 consumers all see
+    *identical* numbers (values below 2^-13 in magnitude are flushed to zero to stay inside fp16's
+    normal range)."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    with np.errstate(over="ignore"):
+        idx = np.arange(n, dtype=np.uint64) + (np.uint64(seed) << np.uint64(32))
+        h = _splitmix64(idx)
+    s = np.zeros(n, dtype=np.int64)
+    for k in range(4):
+        s += ((h >> np.uint64(16 * k)) & np.uint64(0xFFFF)).astype(np.int64)
+    # each uniform: mean 32767.5, var (65536^2-1)/12 ; sum of 4
+    z = (s.astype(np.float64) - 4 * 32767.5) / math.sqrt(4 * (65536.0 ** 2 - 1) / 12.0)
+    t = torch.from_numpy((z * std + mean).astype(np.float32)).reshape(shape)
+    t = t.to(torch.bfloat16).to(torch.float32)
+    t[t.abs() < 2.0 ** -13] = 0.0
+    return t
+
+
+def synthetic_state_dict(params, seed: int = 0, max_feats: int = 10, bias: float = 3.5,
+                         video_dim: int = 768) -> Dict[str, torch.Tensor]:
+    """Random-init state dict with the reference's parameter names (`llama/model.py:190-248`,
+    SURVEY.md §8(b)). Frozen ≥2-D weights ~ N(0, 0.02²); norm weights 1+N(0, 0.1²); adapter and
+    temporal embeddings N(0,1); gate1 ~ N(0, 0.5²) (NOT zero: the reference's zero init makes every
+    adapter gradient identically zero, SURVEY.md §7 'Hard parts'); gate2 = -bias + N(0, 0.1²)."""
+    d, L, H, V = params.dim, params.n_layers, params.n_heads, params.vocab_size
+    hid = ffn_hidden_dim(d, params.multiple_of)
+    sd: Dict[str, torch.Tensor] = {}
+    k = [seed * 1000 + 1]
+
+    def nxt():
+        k[0] += 1
+        return k[0]
+
+    sd["tok_embeddings.weight"] = hash_normal((V, d), nxt(), 0.02)
+    sd["output.weight"] = hash_normal((V, d), nxt(), 0.02)
+    sd["norm.weight"] = hash_normal((d,), nxt(), 0.1, 1.0)
+    for i in range(L):
+        p = f"layers.{i}."
+        for nm in ("wq", "wk", "wv", "wo"):
+            sd[p + f"attention.{nm}.weight"] = hash_normal((d, d), nxt(), 0.02)
+        sd[p + "feed_forward.w1.weight"] = hash_normal((hid, d), nxt(), 0.02)
+        sd[p + "feed_forward.w2.weight"] = hash_normal((d, hid), nxt(), 0.02)
+        sd[p + "feed_forward.w3.weight"] = hash_normal((hid, d), nxt(), 0.02)
+        sd[p + "attention_norm.weight"] = hash_normal((d,), nxt(), 0.1, 1.0)
+        sd[p + "ffn_norm.weight"] = hash_normal((d,), nxt(), 0.1, 1.0)
+        sd[p + "attention.gate1"] = hash_normal((1, H, 1, 1), nxt(), 0.5)
+        sd[p + "attention.gate2"] = hash_normal((1, H, 1, 1), nxt(), 0.1, -bias)
+    sd["adapter_query.weight"] = hash_normal((params.adapter_len * params.adapter_layer, d), nxt(), 1.0)
+    sd["visual_proj.weight"] = hash_normal((d, video_dim), nxt(), 1.0 / math.sqrt(video_dim))
+    sd["temporal_emb.weight"] = hash_normal((max_feats, d), nxt(), 1.0)
+    return sd
+
+
+def ffn_hidden_dim(dim: int, multiple_of: int) -> int:
+    """SwiGLU hidden size rule of `llama/model.py:134-135` applied to hidden_dim=4*dim (`:179`)."""
+    hidden = int(2 * (4 * dim) / 3)
+    return multiple_of * ((hidden + multiple_of - 1) // multiple_of)
+
+
+def synthetic_batch(bsz: int, seqlen: int, vocab: int, max_feats: int = 10, seed: int = 0,
+                    video_start: int = 18, n_options: int = 1, video_dim: int = 768,
+                    full_length: bool = False, vaq_label_span=(10, 25),
+                    generator_device: str = "cpu") -> Dict:
+    """Batch dict with the contract of `dataloader/__init__.py:28-90` (CPU tensors).
+
+    VQA/VAQ: ``[BOS, instr…] ‖ F video slots ‖ nl ‖ text ‖ EOS ‖ pad(0)`` with the video block at
+    ``video_start``; VQA labels = last 4 real tokens, VAQ labels = last U[span] real tokens, 0 =
+    ignore (`base_dataset.py:65-77`). QAV: video slots at ``[len-F-1, len-1)``, label 0..F-1 there
+    and -1 elsewhere, ``video_index = arange(prefix, prefix+F)`` (`base_dataset.py:80-91,120`).
+    ``n_options > 1`` produces the validation layout: per sample ``n_options`` sequences identical
+    except for the answer span (`llama/tokenizer.py:69-90`), plus ``answer`` in [0, n_options).
+    """
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    F = max_feats
+    assert seqlen >= video_start + F + 8, "sequence too short for the synthetic layout"
+    lo = max(video_start + F + 7, int(0.7 * seqlen))
+    ids = {k: torch.zeros(bsz, n_options, seqlen, dtype=torch.int64) for k in ("vqa", "vaq", "qav")}
+    labels = {"vqa": torch.zeros(bsz, n_options, seqlen, dtype=torch.int64),
+              "vaq": torch.zeros(bsz, n_options, seqlen, dtype=torch.int64),
+              "qav": torch.full((bsz, n_options, seqlen), -1, dtype=torch.int64)}
+    label_mask = {k: torch.zeros(bsz, n_options, seqlen) for k in ("vqa", "vaq", "qav")}
+    qav_index = torch.zeros(bsz, F, dtype=torch.int64)
+    qav_prefix, vqa_prefix, vaq_prefix = [], [], []
+    for b in range(bsz):
+        ln = seqlen if full_length else int(torch.randint(lo, seqlen + 1, (1,), generator=g))
+        base = torch.randint(3, vocab, (seqlen,), generator=g)
+        base[0] = 1                      # BOS
+        base[ln - 1] = 2                 # EOS
+        base[ln:] = 0                    # pad -> 0 (`base_dataset.py:99-104`)
+        # VQA: answer span = last 4 real tokens ("(X)" + EOS, `tokenizer.py:69`)
+        for o in range(n_options):
+            t = base.clone()
+            t[video_start:video_start + F] = 0          # video placeholders (-2 -> 0)
+            if n_options > 1:                           # options differ only in the answer span
+                t[ln - 4:ln - 1] = torch.randint(3, vocab, (3,), generator=g)
+            ids["vqa"][b, o] = t
+            labels["vqa"][b, o, ln - 4:ln] = t[ln - 4:ln]
+            label_mask["vqa"][b, o, ln - 4:ln] = 1
+        vqa_prefix.append(ln - 4)
+        # VAQ: question span = last U[span] real tokens
+        nq = int(torch.randint(vaq_label_span[0], vaq_label_span[1] + 1, (1,), generator=g))
+        nq = min(nq, ln - (video_start + F + 2))
+        t = torch.randint(3, vocab, (seqlen,), generator=g)
+        t[0] = 1; t[ln - 1] = 2; t[ln:] = 0
+        t[video_start:video_start + F] = 0
+        for o in range(n_options):
+            ids["vaq"][b, o] = t
+            labels["vaq"][b, o, ln - nq:ln] = t[ln - nq:ln]
+            label_mask["vaq"][b, o, ln - nq:ln] = 1
+        vaq_prefix.append(ln - nq)
+        # QAV: video slots just before the final token
+        t = torch.randint(3, vocab, (seqlen,), generator=g)
+        t[0] = 1; t[ln - 1] = 2; t[ln:] = 0
+        p = ln - F - 1
+        t[p:p + F] = 0
+        for o in range(n_options):
+            ids["qav"][b, o] = t
+            labels["qav"][b, o, p:p + F] = torch.arange(F)
+            label_mask["qav"][b, o, p] = 1
+        qav_index[b] = torch.arange(p, p + F)
+        qav_prefix.append(p)
+    video = torch.randn(bsz, F, video_dim, generator=g)
+    data = {
+        "video": video,
+        "video_len": torch.full((bsz,), F, dtype=torch.long),
+        "text_id": ids,
+        "label": labels,
+        "video_start": {"vqa": [video_start] * bsz, "vaq": [video_start] * bsz, "qav": qav_prefix},
+        "video_index": {"vqa": torch.stack([torch.arange(p, p + F) for p in vqa_prefix]),
+                        "vaq": torch.stack([torch.arange(p, p + F) for p in vaq_prefix]),
+                        "qav": qav_index},
+        "label_mask": label_mask,
+        "prefix_index": {"vqa": vqa_prefix, "vaq": vaq_prefix, "qav": qav_prefix},
+        "answer": torch.randint(0, max(n_options, 1), (bsz,), generator=g),
+        "qtype": torch.zeros(bsz, dtype=torch.long),
+        "vid": [f"synthetic{b}" for b in range(bsz)],
+        "qid": [f"q{b}" for b in range(bsz)],
+        "text": [{} for _ in range(bsz)],
+    }
+    return data
