@@ -1,0 +1,121 @@
+"""ctypes binding of the C ABI declared in include/fvqa.h (libfvqa.so, built in-tree).
+
+There is NO CPU fallback: if the library is missing, does not export a symbol the header declares,
+or `fvqa_init()` fails (no sm_100 GPU), the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfvqa.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fvqa.h")
+
+_p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+# name -> argtypes (all functions return int unless listed in _RESTYPES)
+_SIGNATURES = {
+    "fvqa_abi_version": [],
+    "fvqa_last_error": [],
+    "fvqa_init": [],
+    "fvqa_rmsnorm_fwd": [_p, _p, _p, _p, _i, _i, _f, _p],
+    "fvqa_rmsnorm_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "fvqa_rmsnorm_gather_fwd": [_p, _p, _p, _p, _p, _i, _i, _f, _p],
+    "fvqa_rmsnorm_scatter_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "fvqa_swiglu_fwd": [_p, _p, _i, _i, _p],
+    "fvqa_swiglu_bwd": [_p, _p, _p, _i, _i, _p],
+    "fvqa_gemm_bf16_nt": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "fvqa_attn_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fvqa_attn_bwd_ws_bytes": [_i, _i, _i, _i, _i],
+    "fvqa_attn_bwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
+    "fvqa_visual_proj_fwd": [_p, _p, _p, _i, _i, _i, _p],
+    "fvqa_visual_proj_bwd": [_p, _p, _p, _i, _i, _i, _p],
+    "fvqa_build_h0_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "fvqa_build_h0_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fvqa_video_grad_finish": [_p, _p, _p, _i, _i, _i, _p],
+    "fvqa_ce_fwd": [_p, _i, _p, _p, _p, _i, _i, _p],
+    "fvqa_ce_bwd": [_p, _i, _p, _p, _p, _f, _p, _i, _i, _i, _p],
+    "fvqa_sum_scale": [_p, _i, _f, _p, _p],
+    "fvqa_qav_loss_fwd": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
+    "fvqa_qav_loss_bwd": [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p],
+    "fvqa_scatter_rows": [_p, _p, _p, _i, _p],
+    "fvqa_option_score": [_p, _p, _p, _i, _i, _i, _p],
+    "fvqa_f32_to_bf16": [_p, _p, _i64, _p],
+}
+_RESTYPES = {"fvqa_last_error": C.c_char_p, "fvqa_attn_bwd_ws_bytes": _i64}
+
+_lib: Optional[C.CDLL] = None
+_initialised = False
+
+
+class FvqaError(RuntimeError):
+    pass
+
+
+def header_symbols() -> list:
+    """Every function the public header declares (used by the symbol-export test)."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"\b(fvqa_[a-z0-9_]+)\s*\(", text)))
+
+
+def load(build_if_missing: bool = False) -> C.CDLL:
+    """dlopen libfvqa.so and declare signatures. Does not touch the GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing:
+            from . import build as _build
+            _build.build()
+        else:
+            raise FvqaError(f"{LIB_PATH} not found: run `python -m flipped_vqa_b200.build` "
+                            "(there is no CPU/PyTorch fallback for the training step)")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in _SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise FvqaError(f"libfvqa.so does not export {name}") from e
+        fn.argtypes = args
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.fvqa_abi_version() != 1:
+        raise FvqaError("libfvqa.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def lib() -> C.CDLL:
+    """Library handle with the GPU side initialised (raises without an sm_100 device)."""
+    global _initialised
+    l = load()
+    if not _initialised:
+        if not torch.cuda.is_available():
+            raise FvqaError("flipped_vqa_b200 needs a CUDA (sm_100a) device; no CPU path exists")
+        torch.cuda.init()
+        torch.zeros(1, device="cuda")          # make sure the primary context is current
+        rc = l.fvqa_init()
+        if rc != 0:
+            raise FvqaError(f"fvqa_init failed: {l.fvqa_last_error().decode()}")
+        _initialised = True
+    return l
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        raise FvqaError(f"{what} failed ({rc}): {load().fvqa_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream

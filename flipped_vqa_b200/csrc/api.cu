@@ -1,0 +1,46 @@
+// C-ABI plumbing: error reporting, one-time initialisation.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace fvqa {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return FVQA_ERR_CUDA;
+  }
+  return FVQA_OK;
+}
+
+int gemm_init();
+int attn_init();
+
+}  // namespace fvqa
+
+extern "C" int fvqa_abi_version(void) { return FVQA_ABI_VERSION; }
+extern "C" const char* fvqa_last_error(void) { return fvqa::g_err; }
+
+extern "C" int fvqa_init(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    fvqa::set_error("fvqa_init: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    return FVQA_ERR_CUDA;
+  }
+  int rc = fvqa::gemm_init();
+  if (rc) return rc;
+  return fvqa::attn_init();
+}

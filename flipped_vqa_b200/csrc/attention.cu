@@ -1,0 +1,774 @@
+// Fused causal attention forward / backward for the LLaMA-VQA step, with
+//   * RoPE (interleaved pairs, llama/model.py:61-67) applied when Q/K tiles are loaded, and the
+//     inverse rotation applied to dQ/dK before they are written (nothing rotated is ever stored);
+//   * the adapter-prompt branch: a SEPARATE softmax over the A adapter keys scaled by tanh(gate1)
+//     (model.py:99-115) whose keys/values are shared by every sequence;
+//   * the gate2 bias on text scores of rows >= vs+F, columns [vs, vs+F) (model.py:116-119), per
+//     sequence (vstart < 0 = no bias, the QAV stream).
+// Flash-style: scores/probabilities never leave the SM. Backward is two deterministic passes
+// (no atomics): pass A owns query rows (dQ, D, gate partials), pass B owns keys (dK, dV and the
+// adapter dK_a/dV_a partials); a tiny kernel reduces the per-CTA partials in a fixed order.
+//
+// Round-1 implementation: warp-level mma.sync.m16n8k16 bf16 tensor-core tiles fed from padded
+// shared memory through ldmatrix (attention is ~0.5 % of the step's FLOPs; the tcgen05 budget
+// went to the GEMM first).
+#include "common.cuh"
+
+namespace fvqa {
+
+constexpr int AT_THREADS = 128;
+constexpr int AT_BM = 64;   // query rows per CTA (4 warps x 16)
+constexpr int AT_BN = 64;   // keys per tile
+constexpr int AT_AP = 16;   // adapter keys padded to one MMA k-block
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+// ---------------------------------------------------------------------------------------------
+// mma.sync / ldmatrix helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// acc[NT][4] += A[16 x K] * B^T.  A: smem row-major rows a_row0..+16; B: smem stored [n][k], rows b_row0..+NT*8.
+template <int NT, int K, int LD>
+__device__ __forceinline__ void warp_mma_nt(float (&acc)[NT][4], uint32_t sA, int a_row0, uint32_t sB, int b_row0) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t a_addr = sA + static_cast<uint32_t>(((a_row0 + (lane & 15)) * LD + (lane >> 4) * 8) * 2);
+  const uint32_t b_addr = sB + static_cast<uint32_t>(((b_row0 + (lane & 7) + ((lane >> 4) << 3)) * LD + ((lane >> 3) & 1) * 8) * 2);
+#pragma unroll
+  for (int kb = 0; kb < K / 16; ++kb) {
+    uint32_t a[4];
+    ldsm_x4(a, a_addr + kb * 32);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4(b, b_addr + static_cast<uint32_t>(np * 16 * LD * 2 + kb * 32));
+      mma16816(acc[2 * np], a, b[0], b[1]);
+      mma16816(acc[2 * np + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// acc[NT][4] += Afrag * B.  Afrag: KB register k-blocks; B: smem stored [k][n], rows b_k0..+KB*16, cols b_n0..+NT*8.
+template <int NT, int KB, int LD>
+__device__ __forceinline__ void warp_mma_ra_t(float (&acc)[NT][4], const uint32_t (&a)[KB][4], uint32_t sB, int b_k0, int b_n0) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t b_addr = sB + static_cast<uint32_t>(((b_k0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + b_n0 + (lane >> 4) * 8) * 2);
+#pragma unroll
+  for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b[4];
+      ldsm_x4_t(b, b_addr + static_cast<uint32_t>((kb * 16 * LD + np * 16) * 2));
+      mma16816(acc[2 * np], a[kb], b[0], b[1]);
+      mma16816(acc[2 * np + 1], a[kb], b[2], b[3]);
+    }
+  }
+}
+
+// C fragments (two adjacent n-tiles) -> A fragment of one k-block.
+__device__ __forceinline__ void c_to_a(uint32_t (&a)[4], const float (&c0)[4], const float (&c1)[4]) {
+  a[0] = pack_bf16x2(c0[0], c0[1]);
+  a[1] = pack_bf16x2(c0[2], c0[3]);
+  a[2] = pack_bf16x2(c1[0], c1[1]);
+  a[3] = pack_bf16x2(c1[2], c1[3]);
+}
+
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+// reductions over the 8 lanes that share (lane & 3): i.e. over the M index of a C fragment column
+__device__ __forceinline__ float col_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+}
+__device__ __forceinline__ float col_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v + __shfl_xor_sync(0xffffffffu, v, 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile movers
+// ---------------------------------------------------------------------------------------------
+// Load ROWS x HD bf16 (row stride `stride` elements) starting at sequence position row0 into padded
+// smem; rows with position >= limit are zero-filled; optional RoPE at position = row index.
+template <int HD, int ROWS, bool ROPE>
+__device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ g, long stride, int row0, int limit,
+                                          const float* __restrict__ cosT, const float* __restrict__ sinT) {
+  constexpr int LD = HD + 8;
+  constexpr int VPR = HD / 8;
+  for (int idx = threadIdx.x; idx < ROWS * VPR; idx += AT_THREADS) {
+    const int r = idx / VPR, v = idx - r * VPR;
+    const int pos = row0 + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (pos < limit) {
+      val = __ldg(reinterpret_cast<const uint4*>(g + static_cast<long>(pos) * stride) + v);
+      if (ROPE) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(cosT + static_cast<long>(pos) * (HD / 2)) + v);
+        const float4 sn = __ldg(reinterpret_cast<const float4*>(sinT + static_cast<long>(pos) * (HD / 2)) + v);
+        float f[8];
+        unpack8(val, f);
+        const float cc[4] = {c.x, c.y, c.z, c.w}, ss[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float a = f[2 * i], b = f[2 * i + 1];
+          f[2 * i] = a * cc[i] - b * ss[i];
+          f[2 * i + 1] = a * ss[i] + b * cc[i];
+        }
+        val = pack8(f);
+      }
+    }
+    *reinterpret_cast<uint4*>(s + r * LD + v * 8) = val;
+  }
+}
+
+// Warp writes its 16 x HD fp32 C-fragment tile (optionally inverse-rotated, scaled) as bf16 through a
+// private smem staging area (16 rows, padded) to global rows row0+0..15 (< limit) with 16-byte stores.
+template <int HD, bool INV_ROPE>
+__device__ __forceinline__ void store_tile_warp(bf16* stage, float (&acc)[HD / 8][4], float scale, bf16* __restrict__ g, long stride,
+                                                int row0, int limit, const float* __restrict__ cosT, const float* __restrict__ sinT) {
+  constexpr int LD = HD + 8;
+  const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < HD / 8; ++nt) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      float a = acc[nt][2 * hh] * scale, b = acc[nt][2 * hh + 1] * scale;
+      const int r = gq + 8 * hh;
+      if (INV_ROPE) {
+        const int pos = row0 + r;
+        if (pos < limit) {
+          const float c = __ldg(cosT + static_cast<long>(pos) * (HD / 2) + nt * 4 + t);
+          const float sn = __ldg(sinT + static_cast<long>(pos) * (HD / 2) + nt * 4 + t);
+          const float ra = a * c + b * sn, rb = -a * sn + b * c;
+          a = ra; b = rb;
+        }
+      }
+      *reinterpret_cast<uint32_t*>(stage + r * LD + nt * 8 + 2 * t) = pack_bf16x2(a, b);
+    }
+  }
+  __syncwarp();
+  constexpr int VPR = HD / 8;
+  for (int idx = lane; idx < 16 * VPR; idx += 32) {
+    const int r = idx / VPR, v = idx - r * VPR;
+    if (row0 + r < limit)
+      *(reinterpret_cast<uint4*>(g + static_cast<long>(row0 + r) * stride) + v) = *reinterpret_cast<const uint4*>(stage + r * LD + v * 8);
+  }
+  __syncwarp();
+}
+
+struct AttnParams {
+  const bf16* qkv; const bf16* akv; int akv_ld;
+  const float* cosT; const float* sinT; const float* gate1; const float* gate2; const int32_t* vstart;
+  bf16* out; float* lse;            // fwd outputs / bwd inputs
+  const bf16* dout; bf16* dqkv;     // bwd
+  float* ws_dx; float* ws_gate; float* ws_akv;
+  int n_seq, S, H, A, F, qtiles;
+};
+
+// ---------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p) {
+  constexpr int LD = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem);
+  bf16* sK = sQ + AT_BM * LD;
+  bf16* sV = sK + AT_BN * LD;
+  bf16* sKa = sV + AT_BN * LD;
+  bf16* sVa = sKa + AT_AP * LD;
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int S = p.S, D = p.H * HD;
+  const long qkv_stride = 3L * D;
+  const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
+  const bf16* kbase = qbase + D;
+  const bf16* vbase = qbase + 2 * D;
+  const int r0 = qt * AT_BM;
+  const float scale2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
+  const int vs = p.vstart[n];
+  const float bias2 = (vs >= 0) ? p.gate2[h] * LOG2E : 0.f;
+  const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;   // rows >= this get the bias
+  const int bias_c0 = vs, bias_c1 = vs + p.F;                  // columns [c0, c1)
+
+  load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, r0, S, p.cosT, p.sinT);
+  load_tile<HD, AT_AP, false>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+  load_tile<HD, AT_AP, false>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int row_a = r0 + warp * 16 + gq;   // this thread's rows: row_a and row_a + 8
+  const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV), sKa_u = smem_u32(sKa), sVa_u = smem_u32(sVa);
+
+  for (int j = 0; j <= qt; ++j) {
+    __syncthreads();   // previous tile fully consumed (also orders the initial loads)
+    load_tile<HD, AT_BN, true>(sK, kbase, qkv_stride, j * AT_BN, S, p.cosT, p.sinT);
+    load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
+    __syncthreads();
+    float s[AT_BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < AT_BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+    warp_mma_nt<AT_BN / 8, HD, LD>(s, sQ_u, warp * 16, sK_u, 0);
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < AT_BN / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = row_a + 8 * (e >> 1);
+        const int col = j * AT_BN + nt * 8 + 2 * t + (e & 1);
+        float v = s[nt][e] * scale2;
+        if (row >= bias_row0 && col >= bias_c0 && col < bias_c1) v += bias2;
+        if (col > row) v = -INFINITY;
+        s[nt][e] = v;
+        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+      }
+    }
+    float alpha[2], m_new[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      m_new[hh] = fmaxf(m_run[hh], quad_max(mx[hh]));
+      alpha[hh] = (m_run[hh] == -INFINITY) ? 0.f : exp2f(m_run[hh] - m_new[hh]);
+      m_run[hh] = m_new[hh];
+      l_run[hh] *= alpha[hh];
+    }
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][0] *= alpha[0]; o[i][1] *= alpha[0]; o[i][2] *= alpha[1]; o[i][3] *= alpha[1]; }
+    uint32_t pf[AT_BN / 16][4];
+#pragma unroll
+    for (int nt = 0; nt < AT_BN / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pv = (m_new[e >> 1] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_new[e >> 1]);
+        s[nt][e] = pv;
+        l_run[e >> 1] += pv;
+      }
+    }
+#pragma unroll
+    for (int kb = 0; kb < AT_BN / 16; ++kb) c_to_a(pf[kb], s[2 * kb], s[2 * kb + 1]);
+    warp_mma_ra_t<HD / 8, AT_BN / 16, LD>(o, pf, sV_u, 0, 0);
+  }
+  float lse2[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const float l = quad_sum(l_run[hh]);
+    const float inv = (l > 0.f) ? 1.f / l : 0.f;
+    lse2[hh] = m_run[hh] + log2f(l);
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { o[i][2 * hh] *= inv; o[i][2 * hh + 1] *= inv; }
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int row = row_a + 8 * hh;
+      if (row < S) p.lse[(static_cast<long>(n) * p.H + h) * S + row] = lse2[hh] * LN2;
+    }
+  }
+  // ---- adapter branch: separate softmax over the A adapter keys, scaled by tanh(gate1) ----
+  {
+    float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    warp_mma_nt<2, HD, LD>(sa, sQ_u, warp * 16, sKa_u, 0);
+    const float tg = bf16_round(tanhf(p.gate1[h]));
+    float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + 2 * t + (e & 1);
+        sa[nt][e] = (key < p.A) ? sa[nt][e] * scale2 : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sa[nt][e]);
+      }
+    mx[0] = quad_max(mx[0]); mx[1] = quad_max(mx[1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sa[nt][e] = exp2f(sa[nt][e] - mx[e >> 1]);
+        sm[e >> 1] += sa[nt][e];
+      }
+    sm[0] = quad_sum(sm[0]); sm[1] = quad_sum(sm[1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sa[nt][e] = bf16_round(sa[nt][e] / sm[e >> 1]) * tg;   // (softmax.half() * tanh.half())
+    uint32_t pa[1][4];
+    c_to_a(pa[0], sa[0], sa[1]);
+    warp_mma_ra_t<HD / 8, 1, LD>(o, pa, sVa_u, 0, 0);
+  }
+  // each warp re-uses its own 16 rows of sQ as the staging area (only this warp ever read them)
+  __syncwarp();
+  store_tile_warp<HD, false>(sQ + warp * 16 * LD, o, 1.f, p.out + static_cast<long>(n) * S * D + h * HD, D, r0 + warp * 16, S, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward pass A: per (sequence, head, 64 query rows) -> dQ, D_x, gate1/gate2 partial sums
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParams p) {
+  constexpr int LD = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem);
+  bf16* sdO = sQ + AT_BM * LD;
+  bf16* sK = sdO + AT_BM * LD;
+  bf16* sV = sK + AT_BN * LD;
+  bf16* sKa = sV + AT_BN * LD;
+  bf16* sVa = sKa + AT_AP * LD;
+  float* sRed = reinterpret_cast<float*>(sVa + AT_AP * LD);   // [8] cross-warp gate partials
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int S = p.S, D = p.H * HD;
+  const long qkv_stride = 3L * D;
+  const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
+  const bf16* kbase = qbase + D;
+  const bf16* vbase = qbase + 2 * D;
+  const bf16* obase = p.out + static_cast<long>(n) * S * D + h * HD;
+  const bf16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
+  const int r0 = qt * AT_BM;
+  const float scale = rsqrtf(static_cast<float>(HD));
+  const float scale2 = scale * LOG2E;
+  const int vs = p.vstart[n];
+  const float bias2 = (vs >= 0) ? p.gate2[h] * LOG2E : 0.f;
+  const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;
+  const int bias_c0 = vs, bias_c1 = vs + p.F;
+  const float tg = tanhf(p.gate1[h]);
+
+  load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, r0, S, p.cosT, p.sinT);
+  load_tile<HD, AT_BM, false>(sdO, dobase, D, r0, S, nullptr, nullptr);
+  load_tile<HD, AT_AP, false>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+  load_tile<HD, AT_AP, false>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+  __syncthreads();
+  const uint32_t sQ_u = smem_u32(sQ), sdO_u = smem_u32(sdO), sK_u = smem_u32(sK), sV_u = smem_u32(sV),
+                 sKa_u = smem_u32(sKa), sVa_u = smem_u32(sVa);
+  const int row_a = r0 + warp * 16 + gq;
+
+  // D_total[row] = <dO[row], O[row]> for this thread's two rows (quad-cooperative: each lane of the quad
+  // takes a quarter of the head dimension).
+  float dtot[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int lr = warp * 16 + gq + 8 * hh;
+    const int row = r0 + lr;
+    float acc = 0.f;
+    if (row < S) {
+      const uint4* orow = reinterpret_cast<const uint4*>(obase + static_cast<long>(row) * D);
+#pragma unroll
+      for (int v = 0; v < HD / 32; ++v) {
+        const int vec = t * (HD / 32) + v;
+        float a[8], b[8];
+        unpack8(__ldg(orow + vec), a);
+        unpack8(*reinterpret_cast<const uint4*>(sdO + lr * LD + vec * 8), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc += a[e] * b[e];
+      }
+    }
+    dtot[hh] = quad_sum(acc);
+  }
+
+  float dq[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+  float g1_part = 0.f, g2_part = 0.f;
+  float dx[2];
+  // ---- adapter branch ----
+  {
+    float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float dpa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    warp_mma_nt<2, HD, LD>(sa, sQ_u, warp * 16, sKa_u, 0);
+    warp_mma_nt<2, HD, LD>(dpa, sdO_u, warp * 16, sVa_u, 0);     // dP_a' = dO V_a^T (without tanh(gate1))
+    float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f}, da[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + 2 * t + (e & 1);
+        sa[nt][e] = (key < p.A) ? sa[nt][e] * scale2 : -INFINITY;
+        mx[e >> 1] = fmaxf(mx[e >> 1], sa[nt][e]);
+      }
+    mx[0] = quad_max(mx[0]); mx[1] = quad_max(mx[1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sa[nt][e] = exp2f(sa[nt][e] - mx[e >> 1]);
+        sm[e >> 1] += sa[nt][e];
+      }
+    sm[0] = quad_sum(sm[0]); sm[1] = quad_sum(sm[1]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        sa[nt][e] /= sm[e >> 1];
+        da[e >> 1] += sa[nt][e] * dpa[nt][e];
+      }
+    da[0] = quad_sum(da[0]); da[1] = quad_sum(da[1]);            // D_a' = <dO, P_a V_a>
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const bool ok = (row_a + 8 * hh) < S;
+      if (ok && t == 0) g1_part += da[hh];
+      dx[hh] = dtot[hh] - tg * da[hh];                           // D of the text softmax
+      if (ok && t == 0) p.ws_dx[(static_cast<long>(n) * p.H + h) * (p.qtiles * AT_BM) + row_a + 8 * hh] = dx[hh];
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sa[nt][e] = tg * sa[nt][e] * (dpa[nt][e] - da[e >> 1]);   // dS_a
+    uint32_t dsa[1][4];
+    c_to_a(dsa[0], sa[0], sa[1]);
+    warp_mma_ra_t<HD / 8, 1, LD>(dq, dsa, sKa_u, 0, 0);
+  }
+  float lse2[2];
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int row = row_a + 8 * hh;
+    lse2[hh] = (row < S) ? p.lse[(static_cast<long>(n) * p.H + h) * S + row] * LOG2E : 0.f;
+  }
+  // ---- text keys ----
+  for (int j = 0; j <= qt; ++j) {
+    __syncthreads();
+    load_tile<HD, AT_BN, true>(sK, kbase, qkv_stride, j * AT_BN, S, p.cosT, p.sinT);
+    load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
+    __syncthreads();
+    float s[AT_BN / 8][4], dp[AT_BN / 8][4];
+#pragma unroll
+    for (int i = 0; i < AT_BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+    warp_mma_nt<AT_BN / 8, HD, LD>(s, sQ_u, warp * 16, sK_u, 0);
+    warp_mma_nt<AT_BN / 8, HD, LD>(dp, sdO_u, warp * 16, sV_u, 0);
+#pragma unroll
+    for (int nt = 0; nt < AT_BN / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = row_a + 8 * (e >> 1);
+        const int col = j * AT_BN + nt * 8 + 2 * t + (e & 1);
+        float v = s[nt][e] * scale2;
+        const bool biased = (row >= bias_row0 && col >= bias_c0 && col < bias_c1);
+        if (biased) v += bias2;
+        const float pv = (col > row || row >= S) ? 0.f : exp2f(v - lse2[e >> 1]);
+        const float ds = pv * (dp[nt][e] - dx[e >> 1]);
+        if (biased) g2_part += ds;
+        s[nt][e] = ds;
+      }
+    }
+    uint32_t dsf[AT_BN / 16][4];
+#pragma unroll
+    for (int kb = 0; kb < AT_BN / 16; ++kb) c_to_a(dsf[kb], s[2 * kb], s[2 * kb + 1]);
+    warp_mma_ra_t<HD / 8, AT_BN / 16, LD>(dq, dsf, sK_u, 0, 0);
+  }
+  // gate partial sums of this CTA (fixed reduction order)
+  g1_part = warp_sum(g1_part);
+  g2_part = warp_sum(g2_part);
+  if (lane == 0) { sRed[warp] = g1_part; sRed[4 + warp] = g2_part; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float* wsg = p.ws_gate + ((static_cast<long>(n) * p.H + h) * p.qtiles + qt) * 2;
+    wsg[0] = sRed[0] + sRed[1] + sRed[2] + sRed[3];
+    wsg[1] = sRed[4] + sRed[5] + sRed[6] + sRed[7];
+  }
+  // dQ = scale * (dS K), inverse-rotated; staged through this warp's rows of sQ
+  store_tile_warp<HD, true>(sQ + warp * 16 * LD, dq, scale, p.dqkv + static_cast<long>(n) * S * qkv_stride + h * HD, qkv_stride,
+                            r0 + warp * 16, S, p.cosT, p.sinT);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward pass B: per (sequence, head, 64 keys) -> dK, dV ; blockIdx.x == qtiles -> adapter keys
+// (transposed formulation: S^T = K Q^T so that P^T / dS^T come out as A-operand fragments)
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+  constexpr int LD = HD + 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  bf16* sK = reinterpret_cast<bf16*>(smem);
+  bf16* sV = sK + AT_BN * LD;
+  bf16* sQ = sV + AT_BN * LD;
+  bf16* sdO = sQ + AT_BM * LD;
+  float* sLse = reinterpret_cast<float*>(sdO + AT_BM * LD);   // [64]
+  float* sDx = sLse + AT_BM;                                  // [64]
+  const int jt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int S = p.S, D = p.H * HD;
+  const long qkv_stride = 3L * D;
+  const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
+  const bf16* kbase = qbase + D;
+  const bf16* vbase = qbase + 2 * D;
+  const bf16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
+  const float scale = rsqrtf(static_cast<float>(HD));
+  const float scale2 = scale * LOG2E;
+  const uint32_t sQ_u = smem_u32(sQ), sdO_u = smem_u32(sdO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  const long lse_base = (static_cast<long>(n) * p.H + h) * S;
+  const long dx_base = (static_cast<long>(n) * p.H + h) * (p.qtiles * AT_BM);
+
+  if (jt == p.qtiles) {
+    // ======================= adapter keys =======================
+    const float tg = tanhf(p.gate1[h]);
+    load_tile<HD, AT_AP, false>(sK, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+    load_tile<HD, AT_AP, false>(sV, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+    float dka[HD / 8][4], dva[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) { dka[i][0] = dka[i][1] = dka[i][2] = dka[i][3] = 0.f; dva[i][0] = dva[i][1] = dva[i][2] = dva[i][3] = 0.f; }
+    for (int i = 0; i < p.qtiles; ++i) {
+      __syncthreads();
+      load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, i * AT_BM, S, p.cosT, p.sinT);
+      load_tile<HD, AT_BM, false>(sdO, dobase, D, i * AT_BM, S, nullptr, nullptr);
+      __syncthreads();
+      // each warp takes 16 of the 64 query rows (they are the contraction dimension of dK_a / dV_a)
+      float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      float dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      warp_mma_nt<2, HD, LD>(st, sK_u, 0, sQ_u, warp * 16);      // S_a^T [keys x rows]
+      warp_mma_nt<2, HD, LD>(dpt, sV_u, 0, sdO_u, warp * 16);    // dP_a'^T
+      float mx[2][2], sm[2][2], da[2][2];                          // [n-tile][column parity]
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          // keys of this thread: gq (e = c) and gq + 8 (e = 2 + c)
+          float v0 = (gq < p.A) ? st[nt][c] * scale2 : -INFINITY;
+          float v1 = (gq + 8 < p.A) ? st[nt][2 + c] * scale2 : -INFINITY;
+          st[nt][c] = v0; st[nt][2 + c] = v1;
+          mx[nt][c] = col_max(fmaxf(v0, v1));
+        }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          st[nt][c] = exp2f(st[nt][c] - mx[nt][c]);
+          st[nt][2 + c] = exp2f(st[nt][2 + c] - mx[nt][c]);
+          sm[nt][c] = col_sum(st[nt][c] + st[nt][2 + c]);
+        }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int row = i * AT_BM + warp * 16 + nt * 8 + 2 * t + c;
+          const float inv = (row < S) ? 1.f / sm[nt][c] : 0.f;    // rows past the sequence contribute nothing
+          st[nt][c] *= inv; st[nt][2 + c] *= inv;
+          da[nt][c] = col_sum(st[nt][c] * dpt[nt][c] + st[nt][2 + c] * dpt[nt][2 + c]);
+        }
+      float pt[2][4], dst[2][4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          pt[nt][e] = tg * st[nt][e];                                         // (tanh(g1) P_a)^T
+          dst[nt][e] = tg * st[nt][e] * (dpt[nt][e] - da[nt][e & 1]);       // dS_a^T
+        }
+      uint32_t pf[1][4], df[1][4];
+      c_to_a(pf[0], pt[0], pt[1]);
+      c_to_a(df[0], dst[0], dst[1]);
+      warp_mma_ra_t<HD / 8, 1, LD>(dva, pf, sdO_u, warp * 16, 0);
+      warp_mma_ra_t<HD / 8, 1, LD>(dka, df, sQ_u, warp * 16, 0);
+    }
+    // cross-warp reduction in a fixed order through shared memory (fp32 [4][16][HD] fits in sQ+sdO)
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(sQ);
+    float* wsa = p.ws_akv + (static_cast<long>(n) * p.H + h) * 2 * AT_AP * HD;
+    auto reduce_out = [&](float (&acc)[HD / 8][4], float mul, int which) {
+#pragma unroll
+      for (int nt = 0; nt < HD / 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          red[(warp * AT_AP + gq + 8 * (e >> 1)) * HD + nt * 8 + 2 * t + (e & 1)] = acc[nt][e] * mul;
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < AT_AP * HD; idx += AT_THREADS)
+        wsa[which * AT_AP * HD + idx] = red[idx] + red[AT_AP * HD + idx] + red[2 * AT_AP * HD + idx] + red[3 * AT_AP * HD + idx];
+      __syncthreads();
+    };
+    reduce_out(dka, scale, 0);
+    reduce_out(dva, 1.f, 1);
+    return;
+  }
+
+  // ======================= text keys =======================
+  const int k0 = jt * AT_BN;
+  load_tile<HD, AT_BN, true>(sK, kbase, qkv_stride, k0, S, p.cosT, p.sinT);
+  load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, k0, S, nullptr, nullptr);
+  const int vs = p.vstart[n];
+  const float bias2 = (vs >= 0) ? p.gate2[h] * LOG2E : 0.f;
+  const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;
+  const int bias_c0 = vs, bias_c1 = vs + p.F;
+  float dk[HD / 8][4], dv[HD / 8][4];
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
+  const int key_a = k0 + warp * 16 + gq;   // this thread's keys: key_a, key_a + 8
+  for (int i = jt; i < p.qtiles; ++i) {
+    __syncthreads();
+    load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, i * AT_BM, S, p.cosT, p.sinT);
+    load_tile<HD, AT_BM, false>(sdO, dobase, D, i * AT_BM, S, nullptr, nullptr);
+    if (threadIdx.x < AT_BM) {
+      const int row = i * AT_BM + threadIdx.x;
+      sLse[threadIdx.x] = (row < S) ? p.lse[lse_base + row] * LOG2E : 0.f;
+      sDx[threadIdx.x] = (row < S) ? p.ws_dx[dx_base + row] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      float st[4][4], dpt[4][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { st[q][0] = st[q][1] = st[q][2] = st[q][3] = 0.f; dpt[q][0] = dpt[q][1] = dpt[q][2] = dpt[q][3] = 0.f; }
+      warp_mma_nt<4, HD, LD>(st, sK_u, warp * 16, sQ_u, half * 32);     // S^T [16 keys x 32 rows]
+      warp_mma_nt<4, HD, LD>(dpt, sV_u, warp * 16, sdO_u, half * 32);   // dP^T
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int key = key_a + 8 * (e >> 1);
+          const int lr = half * 32 + nt * 8 + 2 * t + (e & 1);
+          const int row = i * AT_BM + lr;
+          float v = st[nt][e] * scale2;
+          if (row >= bias_row0 && key >= bias_c0 && key < bias_c1) v += bias2;
+          const float pv = (key > row || row >= S) ? 0.f : exp2f(v - sLse[lr]);
+          st[nt][e] = pv;
+          dpt[nt][e] = pv * (dpt[nt][e] - sDx[lr]);
+        }
+      }
+      uint32_t pf[2][4], df[2][4];
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) { c_to_a(pf[kb], st[2 * kb], st[2 * kb + 1]); c_to_a(df[kb], dpt[2 * kb], dpt[2 * kb + 1]); }
+      warp_mma_ra_t<HD / 8, 2, LD>(dv, pf, sdO_u, half * 32, 0);
+      warp_mma_ra_t<HD / 8, 2, LD>(dk, df, sQ_u, half * 32, 0);
+    }
+  }
+  __syncthreads();   // everyone done with sQ/sdO before they become staging areas
+  bf16* dkbase = p.dqkv + static_cast<long>(n) * S * qkv_stride + D + h * HD;
+  store_tile_warp<HD, true>(sQ + warp * 16 * LD, dk, scale, dkbase, qkv_stride, k0 + warp * 16, S, p.cosT, p.sinT);
+  store_tile_warp<HD, false>(sdO + warp * 16 * LD, dv, 1.f, dkbase + D, qkv_stride, k0 + warp * 16, S, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-order reduction of the per-CTA partials
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __restrict__ ws_akv, const float* __restrict__ ws_gate,
+                                                              const float* __restrict__ gate1, float* __restrict__ dakv,
+                                                              float* __restrict__ dgate1, float* __restrict__ dgate2, int n_seq,
+                                                              int H, int hd, int A, int qtiles) {
+  const int h = blockIdx.x;
+  const int D = H * hd;
+  for (int idx = threadIdx.x; idx < 2 * A * hd; idx += blockDim.x) {
+    const int which = idx / (A * hd), rem = idx - which * A * hd, a = rem / hd, c = rem - a * hd;
+    float acc = 0.f;
+    for (int n = 0; n < n_seq; ++n) acc += ws_akv[((static_cast<long>(n) * H + h) * 2 + which) * AT_AP * hd + a * hd + c];
+    dakv[static_cast<long>(a) * 2 * D + which * D + h * hd + c] = acc;
+  }
+  if (threadIdx.x == 0) {
+    float g1 = 0.f, g2 = 0.f;
+    for (int n = 0; n < n_seq; ++n)
+      for (int q = 0; q < qtiles; ++q) {
+        const float* w = ws_gate + ((static_cast<long>(n) * H + h) * qtiles + q) * 2;
+        g1 += w[0];
+        g2 += w[1];
+      }
+    const float tg = tanhf(gate1[h]);
+    dgate1[h] = (1.f - tg * tg) * g1;
+    dgate2[h] = g2;
+  }
+}
+
+template <int HD> constexpr int fwd_smem() { return (AT_BM + 2 * AT_BN + 2 * AT_AP) * (HD + 8) * 2; }
+template <int HD> constexpr int dq_smem() { return (2 * AT_BM + 2 * AT_BN + 2 * AT_AP) * (HD + 8) * 2 + 64; }
+template <int HD> constexpr int dkv_smem() { return (2 * AT_BM + 2 * AT_BN) * (HD + 8) * 2 + 2 * AT_BM * 4; }
+
+int attn_init() {
+  cudaError_t e;
+#define FVQA_ATTR(fn, bytes)                                                                   \
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);            \
+  FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(attn): %s", cudaGetErrorString(e));
+  FVQA_ATTR(attn_fwd_kernel<64>, fwd_smem<64>())
+  FVQA_ATTR(attn_fwd_kernel<128>, fwd_smem<128>())
+  FVQA_ATTR(attn_bwd_dq_kernel<64>, dq_smem<64>())
+  FVQA_ATTR(attn_bwd_dq_kernel<128>, dq_smem<128>())
+  FVQA_ATTR(attn_bwd_dkv_kernel<64>, dkv_smem<64>())
+  FVQA_ATTR(attn_bwd_dkv_kernel<128>, dkv_smem<128>())
+#undef FVQA_ATTR
+  return FVQA_OK;
+}
+
+static int check_attn_args(int n_seq, int S, int H, int hd, int A, int akv_ld) {
+  FVQA_REQUIRE(hd == 64 || hd == 128, FVQA_ERR_UNSUPPORTED, "attention: head_dim %d not in {64,128}", hd);
+  FVQA_REQUIRE(A >= 1 && A <= AT_AP, FVQA_ERR_UNSUPPORTED, "attention: adapter_len %d not in [1,%d]", A, AT_AP);
+  FVQA_REQUIRE(n_seq > 0 && S > 0 && H > 0 && H <= 65535 && n_seq <= 65535, FVQA_ERR_INVALID_ARG, "attention: bad sizes n_seq=%d S=%d H=%d", n_seq, S, H);
+  FVQA_REQUIRE(akv_ld % 8 == 0 && akv_ld >= 2 * H * hd, FVQA_ERR_INVALID_ARG, "attention: akv_ld %d", akv_ld);
+  return FVQA_OK;
+}
+
+}  // namespace fvqa
+
+using namespace fvqa;
+
+extern "C" int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
+                             const float* gate1, const float* gate2, const int32_t* vstart, fvqa_bf16* out, float* lse, int n_seq,
+                             int S, int H, int hd, int A, int max_feats, void* stream) {
+  int rc = check_attn_args(n_seq, S, H, hd, A, akv_ld);
+  if (rc) return rc;
+  AttnParams p{};
+  p.qkv = reinterpret_cast<const bf16*>(qkv); p.akv = reinterpret_cast<const bf16*>(akv); p.akv_ld = akv_ld;
+  p.cosT = rope_cos; p.sinT = rope_sin; p.gate1 = gate1; p.gate2 = gate2; p.vstart = vstart;
+  p.out = reinterpret_cast<bf16*>(out); p.lse = lse;
+  p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qtiles = (S + AT_BM - 1) / AT_BM;
+  dim3 grid(p.qtiles, H, n_seq);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (hd == 64) attn_fwd_kernel<64><<<grid, AT_THREADS, fwd_smem<64>(), s>>>(p);
+  else attn_fwd_kernel<128><<<grid, AT_THREADS, fwd_smem<128>(), s>>>(p);
+  return check_launch("attn_fwd");
+}
+
+extern "C" int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A) {
+  (void)A;
+  const int64_t qtiles = (S + AT_BM - 1) / AT_BM;
+  const int64_t nh = static_cast<int64_t>(n_seq) * H;
+  return 4 * (nh * qtiles * AT_BM + nh * qtiles * 2 + nh * 2 * AT_AP * hd);
+}
+
+extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
+                             const float* gate1, const float* gate2, const int32_t* vstart, const fvqa_bf16* out, const float* lse,
+                             const fvqa_bf16* dout, fvqa_bf16* dqkv, float* dakv, float* dgate1, float* dgate2, void* ws, int n_seq,
+                             int S, int H, int hd, int A, int max_feats, void* stream) {
+  int rc = check_attn_args(n_seq, S, H, hd, A, akv_ld);
+  if (rc) return rc;
+  FVQA_REQUIRE(ws != nullptr, FVQA_ERR_INVALID_ARG, "attn_bwd: workspace is null");
+  AttnParams p{};
+  p.qkv = reinterpret_cast<const bf16*>(qkv); p.akv = reinterpret_cast<const bf16*>(akv); p.akv_ld = akv_ld;
+  p.cosT = rope_cos; p.sinT = rope_sin; p.gate1 = gate1; p.gate2 = gate2; p.vstart = vstart;
+  p.out = const_cast<bf16*>(reinterpret_cast<const bf16*>(out)); p.lse = const_cast<float*>(lse);
+  p.dout = reinterpret_cast<const bf16*>(dout); p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qtiles = (S + AT_BM - 1) / AT_BM;
+  const int64_t nh = static_cast<int64_t>(n_seq) * H;
+  p.ws_dx = reinterpret_cast<float*>(ws);
+  p.ws_gate = p.ws_dx + nh * p.qtiles * AT_BM;
+  p.ws_akv = p.ws_gate + nh * p.qtiles * 2;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  dim3 grid_a(p.qtiles, H, n_seq), grid_b(p.qtiles + 1, H, n_seq);
+  if (hd == 64) {
+    attn_bwd_dq_kernel<64><<<grid_a, AT_THREADS, dq_smem<64>(), s>>>(p);
+    rc = check_launch("attn_bwd_dq");
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<64><<<grid_b, AT_THREADS, dkv_smem<64>(), s>>>(p);
+  } else {
+    attn_bwd_dq_kernel<128><<<grid_a, AT_THREADS, dq_smem<128>(), s>>>(p);
+    rc = check_launch("attn_bwd_dq");
+    if (rc) return rc;
+    attn_bwd_dkv_kernel<128><<<grid_b, AT_THREADS, dkv_smem<128>(), s>>>(p);
+  }
+  rc = check_launch("attn_bwd_dkv");
+  if (rc) return rc;
+  attn_bwd_reduce_kernel<<<H, 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qtiles);
+  return check_launch("attn_bwd_reduce");
+}

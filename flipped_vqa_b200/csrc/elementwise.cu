@@ -1,0 +1,250 @@
+// HBM-bound row kernels: fused RMSNorm fwd/bwd (+gather/scatter variants), fused SwiGLU fwd/bwd.
+// Reference semantics: llama/model.py:31-42 (RMSNorm), :142 (SwiGLU). All I/O is bf16 with 16-byte
+// vector accesses; math in fp32. One CTA per row for the norms (row cached in registers), flat
+// grid-stride for SwiGLU.
+#include "common.cuh"
+
+namespace fvqa {
+
+constexpr int NORM_THREADS = 256;
+constexpr int NORM_MAXV = 4;  // vectors (8 bf16) per thread kept in registers -> dim <= 8192
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm forward.  y = bf16( bf16(x * rstd) * w )   (rounding point of model.py:41-42)
+// idx == nullptr: row r reads x[r]; otherwise row r reads x[idx[r]] (idx<0 -> zero row).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
+    const bf16* __restrict__ x, const int32_t* __restrict__ idx, const bf16* __restrict__ w,
+    bf16* __restrict__ y, float* __restrict__ rstd_out, int dim, float eps) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nvec = dim >> 3;
+  long src = row;
+  if (idx != nullptr) src = idx[row];
+  uint4* yrow = reinterpret_cast<uint4*>(y + static_cast<long>(row) * dim);
+  if (src < 0) {  // padding row
+    for (int v = threadIdx.x; v < nvec; v += NORM_THREADS) yrow[v] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0 && rstd_out) rstd_out[row] = 0.f;
+    return;
+  }
+  const uint4* xrow = reinterpret_cast<const uint4*>(x + src * dim);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  uint4 xr[NORM_MAXV];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nvec) {
+      xr[i] = __ldg(xrow + v);
+      float f[8];
+      unpack8(xr[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rstd = rsqrtf(ss / static_cast<float>(dim) + eps);
+  if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nvec) {
+      float f[8], g[8];
+      unpack8(xr[i], f);
+      unpack8(__ldg(wv + v), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] * rstd) * g[j];
+      yrow[v] = pack8(f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RMSNorm backward (dX only). With n = x*rstd, dn = dy*w:
+//   dx = rstd * (dn - n * mean(dn * n)) (+ dres)
+// scatter variant: output row = idx[r] (rows with idx<0 skipped), no residual.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const int32_t* __restrict__ idx,
+    const bf16* __restrict__ w, const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
+    bf16* __restrict__ dx, int dim) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int nvec = dim >> 3;
+  long src = row;
+  if (idx != nullptr) {
+    src = idx[row];
+    if (src < 0) return;
+  }
+  const uint4* dyrow = reinterpret_cast<const uint4*>(dy + static_cast<long>(row) * dim);
+  const uint4* xrow = reinterpret_cast<const uint4*>(x + src * dim);
+  const uint4* wv = reinterpret_cast<const uint4*>(w);
+  const float rstd = rstd_in[row];
+  uint4 xr[NORM_MAXV], dr[NORM_MAXV];
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nvec) {
+      xr[i] = __ldg(xrow + v);
+      dr[i] = __ldg(dyrow + v);
+      float fx[8], fd[8], fw[8];
+      unpack8(xr[i], fx);
+      unpack8(dr[i], fd);
+      unpack8(__ldg(wv + v), fw);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dot += fd[j] * fw[j] * fx[j] * rstd;
+    }
+  }
+  dot = block_sum(dot, red) / static_cast<float>(dim);
+  uint4* dxrow = reinterpret_cast<uint4*>(dx + src * dim);
+  const uint4* rrow = dres ? reinterpret_cast<const uint4*>(dres + src * dim) : nullptr;
+#pragma unroll
+  for (int i = 0; i < NORM_MAXV; ++i) {
+    const int v = threadIdx.x + i * NORM_THREADS;
+    if (v < nvec) {
+      float fx[8], fd[8], fw[8], o[8];
+      unpack8(xr[i], fx);
+      unpack8(dr[i], fd);
+      unpack8(__ldg(wv + v), fw);
+      float fr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (rrow) unpack8(__ldg(rrow + v), fr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fr[j] + rstd * (fd[j] * fw[j] - fx[j] * rstd * dot);
+      dxrow[v] = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SwiGLU. g = [rows, 2*hid] (a | b). fwd: c = bf16( bf16(silu(a)) * b ).
+// bwd: da = dc * b * s * (1 + a * (1 - s)), db = dc * silu(a), s = sigmoid(a).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ c,
+                                                          long rows, int hid) {
+  const int hv = hid >> 3;
+  const long total = rows * hv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / hv;
+    const int v = static_cast<int>(i - r * hv);
+    const uint4* grow = reinterpret_cast<const uint4*>(g + r * 2 * hid);
+    float a[8], b[8], o[8];
+    unpack8(__ldg(grow + v), a);
+    unpack8(__ldg(grow + hv + v), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = a[j] / (1.f + __expf(-a[j]));
+      o[j] = bf16_round(s) * b[j];
+    }
+    reinterpret_cast<uint4*>(c + r * hid)[v] = pack8(o);
+  }
+}
+
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dc, const bf16* __restrict__ g,
+                                                          bf16* __restrict__ dg, long rows, int hid) {
+  const int hv = hid >> 3;
+  const long total = rows * hv;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / hv;
+    const int v = static_cast<int>(i - r * hv);
+    const uint4* grow = reinterpret_cast<const uint4*>(g + r * 2 * hid);
+    float a[8], b[8], d[8], da[8], db[8];
+    unpack8(__ldg(grow + v), a);
+    unpack8(__ldg(grow + hv + v), b);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(dc + r * hid) + v), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = 1.f / (1.f + __expf(-a[j]));
+      da[j] = d[j] * b[j] * s * (1.f + a[j] * (1.f - s));
+      db[j] = d[j] * a[j] * s;
+    }
+    uint4* orow = reinterpret_cast<uint4*>(dg + r * 2 * hid);
+    orow[v] = pack8(da);
+    orow[hv + v] = pack8(db);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+static int elementwise_grid(long work_items, int threads) {
+  long blocks = (work_items + threads - 1) / threads;
+  const long cap = 148L * 8;  // 8 resident CTAs of 256 threads per SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace fvqa
+
+using namespace fvqa;
+
+extern "C" int fvqa_rmsnorm_fwd(const fvqa_bf16* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd, int rows,
+                                int dim, float eps, void* stream) {
+  FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED,
+               "rmsnorm: dim %d must be a multiple of 8 and <= %d", dim, 8 * NORM_THREADS * NORM_MAXV);
+  if (rows <= 0) return FVQA_OK;
+  rmsnorm_fwd_kernel<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), nullptr, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
+  return check_launch("rmsnorm_fwd");
+}
+
+extern "C" int fvqa_rmsnorm_gather_fwd(const fvqa_bf16* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
+                                       float* rstd, int rows_out, int dim, float eps, void* stream) {
+  FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_gather: bad dim %d", dim);
+  FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_gather: idx is null");
+  if (rows_out <= 0) return FVQA_OK;
+  rmsnorm_fwd_kernel<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(x), idx, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
+  return check_launch("rmsnorm_gather_fwd");
+}
+
+extern "C" int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const fvqa_bf16* w, const float* rstd,
+                                const fvqa_bf16* dres, fvqa_bf16* dx, int rows, int dim, void* stream) {
+  FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_bwd: bad dim %d", dim);
+  if (rows <= 0) return FVQA_OK;
+  rmsnorm_bwd_kernel<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), nullptr, reinterpret_cast<const bf16*>(w), rstd,
+      reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dim);
+  return check_launch("rmsnorm_bwd");
+}
+
+extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const int32_t* idx, const fvqa_bf16* w,
+                                        const float* rstd, fvqa_bf16* dx, int rows_out, int dim, void* stream) {
+  FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_scatter_bwd: bad dim %d", dim);
+  FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_scatter_bwd: idx is null");
+  if (rows_out <= 0) return FVQA_OK;
+  rmsnorm_bwd_kernel<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), idx, reinterpret_cast<const bf16*>(w), rstd, nullptr,
+      reinterpret_cast<bf16*>(dx), dim);
+  return check_launch("rmsnorm_scatter_bwd");
+}
+
+extern "C" int fvqa_swiglu_fwd(const fvqa_bf16* g, fvqa_bf16* c, int rows, int hid, void* stream) {
+  FVQA_REQUIRE(hid % 8 == 0, FVQA_ERR_UNSUPPORTED, "swiglu: hid %d must be a multiple of 8", hid);
+  if (rows <= 0) return FVQA_OK;
+  const long items = static_cast<long>(rows) * (hid >> 3);
+  swiglu_fwd_kernel<<<elementwise_grid(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(c), rows, hid);
+  return check_launch("swiglu_fwd");
+}
+
+extern "C" int fvqa_swiglu_bwd(const fvqa_bf16* dc, const fvqa_bf16* g, fvqa_bf16* dg, int rows, int hid, void* stream) {
+  FVQA_REQUIRE(hid % 8 == 0, FVQA_ERR_UNSUPPORTED, "swiglu: hid %d must be a multiple of 8", hid);
+  if (rows <= 0) return FVQA_OK;
+  const long items = static_cast<long>(rows) * (hid >> 3);
+  swiglu_bwd_kernel<<<elementwise_grid(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const bf16*>(dc), reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(dg), rows, hid);
+  return check_launch("swiglu_bwd");
+}
+
+extern "C" int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, void* stream) {
+  if (n <= 0) return FVQA_OK;
+  f32_to_bf16_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  return check_launch("f32_to_bf16");
+}

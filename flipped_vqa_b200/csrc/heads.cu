@@ -1,0 +1,269 @@
+// Loss heads: vocabulary cross-entropy over labelled rows (fwd/bwd), QAV video-feature
+// reconstruction loss (fwd/bwd), per-token loss scatter and multiple-choice option scoring.
+// Reference: llama/model.py:347-361, llama/model_my_original_mod.py:375-377, engine.py:88-93.
+#include "common.cuh"
+
+namespace fvqa {
+
+constexpr int CE_THREADS = 512;
+constexpr int QAV_MAXF = 16;
+
+// row_loss = logsumexp(logits[row]) - logits[row, target]; one CTA per row, online max/sum.
+__global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restrict__ logits, int ld,
+                                                            const int32_t* __restrict__ target, float* __restrict__ row_loss,
+                                                            float* __restrict__ row_lse, int V) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int t = target[row];
+  if (t < 0) {
+    if (threadIdx.x == 0) { row_loss[row] = 0.f; row_lse[row] = 0.f; }
+    return;
+  }
+  const float* l = logits + static_cast<long>(row) * ld;
+  float m = -INFINITY, s = 0.f;
+  const int nv = V >> 2;
+  const float4* l4 = reinterpret_cast<const float4*>(l);
+  for (int i = threadIdx.x; i < nv; i += CE_THREADS) {
+    const float4 v = __ldg(l4 + i);
+    const float mx = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+    if (mx > m) { s *= __expf(m - mx); m = mx; }
+    s += __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+  }
+  for (int i = (nv << 2) + threadIdx.x; i < V; i += CE_THREADS) {
+    const float v = l[i];
+    if (v > m) { s *= __expf(m - v); m = v; }
+    s += __expf(v - m);
+  }
+  const float gm = block_max(m, red);
+  s = (m == -INFINITY) ? 0.f : s * __expf(m - gm);
+  const float gs = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    const float lse = gm + logf(gs);
+    row_lse[row] = lse;
+    row_loss[row] = lse - l[t];
+  }
+}
+
+// dlogits = (softmax - onehot) * gscale * inv_count  (bf16); padding rows are zero-filled.
+__global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restrict__ logits, int ld,
+                                                            const int32_t* __restrict__ target, const float* __restrict__ row_lse,
+                                                            const float* __restrict__ gscale, float inv_count,
+                                                            bf16* __restrict__ dlogits, int ldd, int V) {
+  const int row = blockIdx.x;
+  const int t = target[row];
+  bf16* d = dlogits + static_cast<long>(row) * ldd;
+  const int nv = V >> 3;
+  if (t < 0) {
+    for (int i = threadIdx.x; i < nv; i += CE_THREADS) reinterpret_cast<uint4*>(d)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += CE_THREADS) d[i] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float* l = logits + static_cast<long>(row) * ld;
+  const float lse = row_lse[row];
+  const float sc = gscale[0] * inv_count;
+  for (int i = threadIdx.x; i < nv; i += CE_THREADS) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(l) + 2 * i);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(l) + 2 * i + 1);
+    float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = (__expf(o[j] - lse) - ((i * 8 + j) == t ? 1.f : 0.f)) * sc;
+    reinterpret_cast<uint4*>(d)[i] = pack8(o);
+  }
+  for (int i = (nv << 3) + threadIdx.x; i < V; i += CE_THREADS)
+    d[i] = __float2bfloat16_rn((__expf(l[i] - lse) - (i == t ? 1.f : 0.f)) * sc);
+}
+
+// Deterministic single-CTA reduction: out[0] = scale * sum(v[0..rows)).
+__global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict__ v, int rows, float scale, float* __restrict__ out) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < rows; i += 256) s += v[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+// QAV forward: one CTA per gathered row.
+__global__ void __launch_bounds__(256) qav_fwd_kernel(const bf16* __restrict__ hn, const float* __restrict__ vf32,
+                                                      const int32_t* __restrict__ row_video, const int32_t* __restrict__ target,
+                                                      float inv_tau, float* __restrict__ row_loss, float* __restrict__ prob,
+                                                      int dim, int F) {
+  __shared__ float red[32];
+  __shared__ float logit[QAV_MAXF];
+  const int row = blockIdx.x;
+  const int b = row_video[row];
+  if (b < 0) {
+    if (threadIdx.x == 0) row_loss[row] = 0.f;
+    if (threadIdx.x < F) prob[row * F + threadIdx.x] = 0.f;
+    return;
+  }
+  float acc[QAV_MAXF];
+#pragma unroll
+  for (int j = 0; j < QAV_MAXF; ++j) acc[j] = 0.f;
+  const bf16* h = hn + static_cast<long>(row) * dim;
+  const float* vb = vf32 + static_cast<long>(b) * F * dim;
+  for (int c = threadIdx.x; c < dim; c += 256) {
+    const float x = __bfloat162float(h[c]);
+#pragma unroll
+    for (int j = 0; j < QAV_MAXF; ++j)
+      if (j < F) acc[j] += x * __ldg(vb + static_cast<long>(j) * dim + c);
+  }
+#pragma unroll
+  for (int j = 0; j < QAV_MAXF; ++j) {
+    if (j < F) {
+      const float s = block_sum(acc[j], red);
+      if (threadIdx.x == 0) logit[j] = s * inv_tau;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = -INFINITY;
+    for (int j = 0; j < F; ++j) m = fmaxf(m, logit[j]);
+    float s = 0.f;
+    for (int j = 0; j < F; ++j) s += expf(logit[j] - m);
+    const float lse = m + logf(s);
+    for (int j = 0; j < F; ++j) prob[row * F + j] = expf(logit[j] - lse);
+    row_loss[row] = lse - logit[target[row]];
+  }
+}
+
+// dhn[row] = sum_j dlogit[row,j] * vf32[b,j,:]   (one CTA per row)
+__global__ void __launch_bounds__(256) qav_bwd_dh_kernel(const float* __restrict__ vf32, const int32_t* __restrict__ row_video,
+                                                         const int32_t* __restrict__ target, const float* __restrict__ prob,
+                                                         const float* __restrict__ gscale, float coef, bf16* __restrict__ dhn,
+                                                         int dim, int F) {
+  const int row = blockIdx.x;
+  const int b = row_video[row];
+  bf16* o = dhn + static_cast<long>(row) * dim;
+  if (b < 0) {
+    for (int c = threadIdx.x; c < dim; c += 256) o[c] = __float2bfloat16_rn(0.f);
+    return;
+  }
+  const float sc = gscale[0] * coef;
+  float dl[QAV_MAXF];
+#pragma unroll
+  for (int j = 0; j < QAV_MAXF; ++j) dl[j] = (j < F) ? (prob[row * F + j] - (j == target[row] ? 1.f : 0.f)) * sc : 0.f;
+  const float* vb = vf32 + static_cast<long>(b) * F * dim;
+  for (int c = threadIdx.x; c < dim; c += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < QAV_MAXF; ++j)
+      if (j < F) a += dl[j] * __ldg(vb + static_cast<long>(j) * dim + c);
+    o[c] = __float2bfloat16_rn(a);
+  }
+}
+
+// dvf_qav[b,j,:] = sum_{rows of sample b} dlogit[row,j] * hn[row,:]   (one CTA per (b,j); fixed order)
+__global__ void __launch_bounds__(256) qav_bwd_dv_kernel(const bf16* __restrict__ hn, const int32_t* __restrict__ row_video,
+                                                         const int32_t* __restrict__ target, const float* __restrict__ prob,
+                                                         const float* __restrict__ gscale, float coef, float* __restrict__ dvf,
+                                                         int rows, int dim, int F) {
+  const int b = blockIdx.x / F, j = blockIdx.x - b * F;
+  const float sc = gscale[0] * coef;
+  for (int c = threadIdx.x; c < dim; c += 256) {
+    float a = 0.f;
+    for (int r = 0; r < rows; ++r) {
+      if (row_video[r] != b) continue;
+      const float dl = (prob[r * F + j] - (j == target[r] ? 1.f : 0.f)) * sc;
+      a += dl * __bfloat162float(hn[static_cast<long>(r) * dim + c]);
+    }
+    dvf[(static_cast<long>(b) * F + j) * dim + c] = a;
+  }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ v, const int32_t* __restrict__ idx, float* __restrict__ dst, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows && idx[i] >= 0) dst[idx[i]] = v[i];
+}
+
+// engine.py:88-93: count = (loss != 0).sum(-1); prediction = (loss.sum(-1) / count).argmin(-1)
+__global__ void option_score_kernel(const float* __restrict__ tok, int32_t* __restrict__ pred, float* __restrict__ mean_loss,
+                                    int n_items, int n_opt, int len) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_items) return;
+  int best = 0;
+  float bestv = 0.f;
+  bool have = false, nan_hit = false;
+  for (int o = 0; o < n_opt; ++o) {
+    const float* t = tok + (static_cast<long>(i) * n_opt + o) * len;
+    float s = 0.f;
+    int cnt = 0;
+    for (int k = 0; k < len; ++k) {
+      s += t[k];
+      cnt += (t[k] != 0.f);
+    }
+    const float m = s / static_cast<float>(cnt);
+    if (mean_loss) mean_loss[i * n_opt + o] = m;
+    if (nan_hit) continue;
+    if (m != m) { best = o; nan_hit = true; continue; }  // torch.argmin propagates NaN
+    if (!have || m < bestv) { best = o; bestv = m; have = true; }
+  }
+  pred[i] = best;
+}
+
+}  // namespace fvqa
+
+using namespace fvqa;
+
+extern "C" int fvqa_ce_fwd(const float* logits, int ld, const int32_t* target, float* row_loss, float* row_lse, int rows, int V,
+                           void* stream) {
+  FVQA_REQUIRE(ld % 4 == 0, FVQA_ERR_UNSUPPORTED, "ce_fwd: ld %d must be a multiple of 4", ld);
+  if (rows <= 0) return FVQA_OK;
+  ce_fwd_kernel<<<rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, row_loss, row_lse, V);
+  return check_launch("ce_fwd");
+}
+
+extern "C" int fvqa_ce_bwd(const float* logits, int ld, const int32_t* target, const float* row_lse, const float* gscale_dev,
+                           float inv_count, fvqa_bf16* dlogits, int ldd, int rows, int V, void* stream) {
+  FVQA_REQUIRE(ld % 4 == 0 && ldd % 8 == 0, FVQA_ERR_UNSUPPORTED, "ce_bwd: ld %d / ldd %d alignment", ld, ldd);
+  if (rows <= 0) return FVQA_OK;
+  ce_bwd_kernel<<<rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, row_lse, gscale_dev, inv_count,
+                                                                             reinterpret_cast<bf16*>(dlogits), ldd, V);
+  return check_launch("ce_bwd");
+}
+
+extern "C" int fvqa_sum_scale(const float* v, int rows, float scale, float* out, void* stream) {
+  sum_scale_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, rows, scale, out);
+  return check_launch("sum_scale");
+}
+
+extern "C" int fvqa_qav_loss_fwd(const fvqa_bf16* hn, const float* vf32, const int32_t* row_video, const int32_t* target, float tau,
+                                 float* row_loss, float* prob, int rows, int dim, int max_feats, void* stream) {
+  FVQA_REQUIRE(max_feats <= QAV_MAXF, FVQA_ERR_UNSUPPORTED, "qav_loss: max_feats %d > %d", max_feats, QAV_MAXF);
+  if (rows <= 0) return FVQA_OK;
+  qav_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(hn), vf32, row_video, target,
+                                                                       1.f / tau, row_loss, prob, dim, max_feats);
+  return check_launch("qav_loss_fwd");
+}
+
+extern "C" int fvqa_qav_loss_bwd(const fvqa_bf16* hn, const float* vf32, const int32_t* row_video, const int32_t* target,
+                                 const float* prob, const float* gscale_dev, float inv_count, float tau, fvqa_bf16* dhn,
+                                 float* dvf_qav, int rows, int n_video, int dim, int max_feats, void* stream) {
+  FVQA_REQUIRE(max_feats <= QAV_MAXF, FVQA_ERR_UNSUPPORTED, "qav_loss: max_feats %d > %d", max_feats, QAV_MAXF);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float coef = inv_count / tau;
+  if (rows > 0) {
+    qav_bwd_dh_kernel<<<rows, 256, 0, s>>>(vf32, row_video, target, prob, gscale_dev, coef, reinterpret_cast<bf16*>(dhn), dim, max_feats);
+    int rc = check_launch("qav_loss_bwd(dh)");
+    if (rc) return rc;
+  }
+  if (n_video * max_feats > 0) {
+    qav_bwd_dv_kernel<<<n_video * max_feats, 256, 0, s>>>(reinterpret_cast<const bf16*>(hn), row_video, target, prob, gscale_dev,
+                                                           coef, dvf_qav, rows, dim, max_feats);
+    return check_launch("qav_loss_bwd(dv)");
+  }
+  return FVQA_OK;
+}
+
+extern "C" int fvqa_scatter_rows(const float* row_val, const int32_t* dst_index, float* dst, int rows, void* stream) {
+  if (rows <= 0) return FVQA_OK;
+  scatter_rows_kernel<<<(rows + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(row_val, dst_index, dst, rows);
+  return check_launch("scatter_rows");
+}
+
+extern "C" int fvqa_option_score(const float* token_loss, int32_t* prediction, float* mean_loss, int n_items, int n_opt, int len,
+                                 void* stream) {
+  if (n_items <= 0) return FVQA_OK;
+  option_score_kernel<<<(n_items + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(token_loss, prediction, mean_loss, n_items,
+                                                                                            n_opt, len);
+  return check_launch("option_score");
+}

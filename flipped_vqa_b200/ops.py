@@ -1,0 +1,221 @@
+"""Tensor-level wrappers around the C ABI (include/fvqa.h). PyTorch only supplies device memory
+and the current stream; every computation happens in libfvqa.so. Outputs may be passed in
+(pre-allocated workspace) or are allocated with torch.empty."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+BF16 = torch.bfloat16
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous cuda {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}"
+
+
+# ------------------------------------------------------------------ RMSNorm
+def rmsnorm_fwd(x, w, eps: float, y=None, rstd=None):
+    _chk(x, BF16, "x"); _chk(w, BF16, "w")
+    rows, dim = x.shape
+    y = torch.empty_like(x) if y is None else y
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if rstd is None else rstd
+    check(_lib.lib().fvqa_rmsnorm_fwd(ptr(x), ptr(w), ptr(y), ptr(rstd), rows, dim, eps, stream()), "rmsnorm_fwd")
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None):
+    _chk(dy, BF16, "dy"); _chk(x, BF16, "x")
+    rows, dim = x.shape
+    dx = torch.empty_like(x) if dx is None else dx
+    check(_lib.lib().fvqa_rmsnorm_bwd(ptr(dy), ptr(x), ptr(w), ptr(rstd), ptr(dres), ptr(dx), rows, dim, stream()), "rmsnorm_bwd")
+    return dx
+
+
+def rmsnorm_gather_fwd(x, idx, w, eps: float, y=None, rstd=None):
+    _chk(x, BF16, "x"); _chk(idx, torch.int32, "idx")
+    rows, dim = idx.numel(), x.shape[-1]
+    y = torch.empty(rows, dim, dtype=BF16, device=x.device) if y is None else y
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if rstd is None else rstd
+    check(_lib.lib().fvqa_rmsnorm_gather_fwd(ptr(x), ptr(idx), ptr(w), ptr(y), ptr(rstd), rows, dim, eps, stream()), "rmsnorm_gather_fwd")
+    return y, rstd
+
+
+def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx):
+    rows, dim = idx.numel(), x.shape[-1]
+    check(_lib.lib().fvqa_rmsnorm_scatter_bwd(ptr(dy), ptr(x), ptr(idx), ptr(w), ptr(rstd), ptr(dx), rows, dim, stream()), "rmsnorm_scatter_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------ SwiGLU
+def swiglu_fwd(g, c=None):
+    _chk(g, BF16, "g")
+    rows, two_hid = g.shape
+    hid = two_hid // 2
+    c = torch.empty(rows, hid, dtype=BF16, device=g.device) if c is None else c
+    check(_lib.lib().fvqa_swiglu_fwd(ptr(g), ptr(c), rows, hid, stream()), "swiglu_fwd")
+    return c
+
+
+def swiglu_bwd(dc, g, dg=None):
+    _chk(dc, BF16, "dc"); _chk(g, BF16, "g")
+    rows, hid = dc.shape
+    dg = torch.empty_like(g) if dg is None else dg
+    check(_lib.lib().fvqa_swiglu_bwd(ptr(dc), ptr(g), ptr(dg), rows, hid, stream()), "swiglu_bwd")
+    return dg
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+            out_fp32: bool = False, M: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[N,K]^T (+ residual). a/b may be row-strided views (last dim contiguous)."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    Mfull, K = a.shape
+    M = Mfull if M is None else M
+    N, Kb = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else BF16, device=a.device)
+    assert out.stride(-1) == 1 and out.dtype == (torch.float32 if out_fp32 else BF16)
+    ldr = residual.stride(0) if residual is not None else 0
+    check(_lib.lib().fvqa_gemm_bf16_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), ptr(residual), ldr,
+                                       M, N, K, 1 if out_fp32 else 0, stream()), "gemm_bf16_nt")
+    return out
+
+
+# ------------------------------------------------------------------ attention
+def attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F, out=None, lse=None):
+    _chk(qkv, BF16, "qkv"); _chk(vstart, torch.int32, "vstart")
+    assert akv.dtype == BF16 and akv.stride(-1) == 1
+    out = torch.empty(n_seq * S, H * hd, dtype=BF16, device=qkv.device) if out is None else out
+    lse = torch.empty(n_seq, H, S, dtype=torch.float32, device=qkv.device) if lse is None else lse
+    check(_lib.lib().fvqa_attn_fwd(ptr(qkv), ptr(akv), akv.stride(0), ptr(cos), ptr(sin), ptr(gate1), ptr(gate2), ptr(vstart),
+                                   ptr(out), ptr(lse), n_seq, S, H, hd, A, F, stream()), "attn_fwd")
+    return out, lse
+
+
+def attn_bwd_ws_bytes(n_seq, S, H, hd, A) -> int:
+    return int(_lib.load().fvqa_attn_bwd_ws_bytes(n_seq, S, H, hd, A))
+
+
+def attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F,
+             dqkv=None, dakv=None, dgate1=None, dgate2=None, ws=None):
+    dev = qkv.device
+    dqkv = torch.empty_like(qkv) if dqkv is None else dqkv
+    dakv = torch.empty(A, 2 * H * hd, dtype=torch.float32, device=dev) if dakv is None else dakv
+    dgate1 = torch.empty(H, dtype=torch.float32, device=dev) if dgate1 is None else dgate1
+    dgate2 = torch.empty(H, dtype=torch.float32, device=dev) if dgate2 is None else dgate2
+    if ws is None:
+        ws = torch.empty(attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
+    check(_lib.lib().fvqa_attn_bwd(ptr(qkv), ptr(akv), akv.stride(0), ptr(cos), ptr(sin), ptr(gate1), ptr(gate2), ptr(vstart),
+                                   ptr(out), ptr(lse), ptr(dout), ptr(dqkv), ptr(dakv), ptr(dgate1), ptr(dgate2), ptr(ws),
+                                   n_seq, S, H, hd, A, F, stream()), "attn_bwd")
+    return dqkv, dakv, dgate1, dgate2
+
+
+# ------------------------------------------------------------------ input side
+def visual_proj_fwd(video2d, wv, out=None):
+    _chk(video2d, torch.float32, "video"); _chk(wv, torch.float32, "wv")
+    rows, vdim = video2d.shape
+    dim = wv.shape[0]
+    out = torch.empty(rows, dim, dtype=torch.float32, device=wv.device) if out is None else out
+    check(_lib.lib().fvqa_visual_proj_fwd(ptr(video2d), ptr(wv), ptr(out), rows, dim, vdim, stream()), "visual_proj_fwd")
+    return out
+
+
+def visual_proj_bwd(dvf2d, video2d, dwv=None):
+    rows, vdim = video2d.shape
+    dim = dvf2d.shape[1]
+    dwv = torch.empty(dim, vdim, dtype=torch.float32, device=dvf2d.device) if dwv is None else dwv
+    check(_lib.lib().fvqa_visual_proj_bwd(ptr(dvf2d), ptr(video2d), ptr(dwv), rows, dim, vdim, stream()), "visual_proj_bwd")
+    return dwv
+
+
+def build_h0_fwd(tok_emb, ids, labels, vstart, seq_video, qav_index, vf32, temporal, n_seq, S, F, h0=None):
+    dim = tok_emb.shape[1]
+    h0 = torch.empty(n_seq * S, dim, dtype=BF16, device=tok_emb.device) if h0 is None else h0
+    check(_lib.lib().fvqa_build_h0_fwd(ptr(tok_emb), ptr(ids), ptr(labels), ptr(vstart), ptr(seq_video), ptr(qav_index), ptr(vf32),
+                                       ptr(temporal), ptr(h0), n_seq, S, dim, F, stream()), "build_h0_fwd")
+    return h0
+
+
+def build_h0_bwd(dh0, vstart, seq_video, qav_index, n_seq, n_video, S, F, dvf=None):
+    dim = dh0.shape[1]
+    dvf = torch.empty(n_video * F, dim, dtype=torch.float32, device=dh0.device) if dvf is None else dvf
+    check(_lib.lib().fvqa_build_h0_bwd(ptr(dh0), ptr(vstart), ptr(seq_video), ptr(qav_index), ptr(dvf), n_seq, n_video, S, dim, F, stream()), "build_h0_bwd")
+    return dvf
+
+
+def video_grad_finish(dvf, dvf_qav, n_video, F, dtemporal=None):
+    dim = dvf.shape[1]
+    dtemporal = torch.empty(F, dim, dtype=torch.float32, device=dvf.device) if dtemporal is None else dtemporal
+    check(_lib.lib().fvqa_video_grad_finish(ptr(dvf), ptr(dvf_qav), ptr(dtemporal), n_video, dim, F, stream()), "video_grad_finish")
+    return dtemporal
+
+
+# ------------------------------------------------------------------ heads
+def ce_fwd(logits, target, row_loss=None, row_lse=None):
+    _chk(target, torch.int32, "target")
+    assert logits.dtype == torch.float32 and logits.stride(-1) == 1
+    rows, V = target.numel(), logits.shape[1]
+    dev = logits.device
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if row_loss is None else row_loss
+    row_lse = torch.empty(rows, dtype=torch.float32, device=dev) if row_lse is None else row_lse
+    check(_lib.lib().fvqa_ce_fwd(ptr(logits), logits.stride(0), ptr(target), ptr(row_loss), ptr(row_lse), rows, V, stream()), "ce_fwd")
+    return row_loss, row_lse
+
+
+def ce_bwd(logits, target, row_lse, gscale, inv_count: float, dlogits=None):
+    rows, V = target.numel(), logits.shape[1]
+    dlogits = torch.empty(rows, V, dtype=BF16, device=logits.device) if dlogits is None else dlogits
+    check(_lib.lib().fvqa_ce_bwd(ptr(logits), logits.stride(0), ptr(target), ptr(row_lse), ptr(gscale), inv_count, ptr(dlogits),
+                                 dlogits.stride(0), rows, V, stream()), "ce_bwd")
+    return dlogits
+
+
+def sum_scale(v, rows: int, scale: float, out):
+    check(_lib.lib().fvqa_sum_scale(ptr(v), rows, scale, ptr(out), stream()), "sum_scale")
+    return out
+
+
+def qav_loss_fwd(hn, vf32, row_video, target, tau: float, F: int, row_loss=None, prob=None):
+    rows, dim = hn.shape
+    dev = hn.device
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev) if row_loss is None else row_loss
+    prob = torch.empty(rows, F, dtype=torch.float32, device=dev) if prob is None else prob
+    check(_lib.lib().fvqa_qav_loss_fwd(ptr(hn), ptr(vf32), ptr(row_video), ptr(target), tau, ptr(row_loss), ptr(prob), rows, dim, F, stream()), "qav_loss_fwd")
+    return row_loss, prob
+
+
+def qav_loss_bwd(hn, vf32, row_video, target, prob, gscale, inv_count: float, tau: float, n_video: int, F: int, dhn=None, dvf_qav=None):
+    rows, dim = hn.shape
+    dev = hn.device
+    dhn = torch.empty_like(hn) if dhn is None else dhn
+    dvf_qav = torch.empty(n_video * F, dim, dtype=torch.float32, device=dev) if dvf_qav is None else dvf_qav
+    check(_lib.lib().fvqa_qav_loss_bwd(ptr(hn), ptr(vf32), ptr(row_video), ptr(target), ptr(prob), ptr(gscale), inv_count, tau,
+                                       ptr(dhn), ptr(dvf_qav), rows, n_video, dim, F, stream()), "qav_loss_bwd")
+    return dhn, dvf_qav
+
+
+def scatter_rows(row_val, dst_index, dst):
+    check(_lib.lib().fvqa_scatter_rows(ptr(row_val), ptr(dst_index), ptr(dst), dst_index.numel(), stream()), "scatter_rows")
+    return dst
+
+
+def option_score(token_loss: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    _chk(token_loss, torch.float32, "token_loss")
+    n_items, n_opt, ln = token_loss.shape
+    pred = torch.empty(n_items, dtype=torch.int32, device=token_loss.device)
+    mean = torch.empty(n_items, n_opt, dtype=torch.float32, device=token_loss.device)
+    check(_lib.lib().fvqa_option_score(ptr(token_loss), ptr(pred), ptr(mean), n_items, n_opt, ln, stream()), "option_score")
+    return pred, mean
+
+
+def f32_to_bf16(src, dst=None):
+    _chk(src, torch.float32, "src")
+    dst = torch.empty(src.shape, dtype=BF16, device=src.device) if dst is None else dst
+    check(_lib.lib().fvqa_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream()), "f32_to_bf16")
+    return dst

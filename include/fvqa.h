@@ -1,0 +1,154 @@
+/* flipped-vqa-b200 — C ABI of the LLaMA-VQA training-step kernels (sm_100a).
+ *
+ * The reference (inesriahi/Flipped-VQA) has no FFI layer: its boundary is the Python class API of
+ * llama/model.py. This header is the boundary OUR Python host binds (flipped_vqa_b200/_lib.py,
+ * ctypes): one entry point per fused region of the reference's hot path, forward and backward.
+ * Each entry point cites the reference lines it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory
+ *    (no hidden cudaMalloc, no host synchronisation inside any call);
+ *  - `stream` is a cudaStream_t / CUstream passed as void*;
+ *  - bf16 tensors are `uint16_t`-sized elements (__nv_bfloat16), row-major, leading dimension in
+ *    ELEMENTS; "tokens" are the rows of all objective streams concatenated:
+ *    sequence n = stream * B + b, token row = n * S + position;
+ *  - return value: 0 = ok, <0 = FVQA_ERR_*; fvqa_last_error() returns a thread-local message.
+ */
+#ifndef FVQA_H_
+#define FVQA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FVQA_ABI_VERSION 1
+
+#define FVQA_OK 0
+#define FVQA_ERR_INVALID_ARG (-1)
+#define FVQA_ERR_CUDA (-2)
+#define FVQA_ERR_UNSUPPORTED (-3)
+
+typedef uint16_t fvqa_bf16;
+
+int fvqa_abi_version(void);
+const char* fvqa_last_error(void);
+/* One-time per-process setup (kernel attributes, driver entry points). Idempotent. */
+int fvqa_init(void);
+
+/* ---- RMSNorm (llama/model.py:31-42). y = bf16( bf16(x * rstd) * w ); rstd saved in fp32. -------- */
+int fvqa_rmsnorm_fwd(const fvqa_bf16* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd,
+                     int rows, int dim, float eps, void* stream);
+/* dX only (weight is frozen). dx = (dres ? dres : 0) + d rmsnorm(x)/dx . dy */
+int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const fvqa_bf16* w, const float* rstd,
+                     const fvqa_bf16* dres, fvqa_bf16* dx, int rows, int dim, void* stream);
+/* Final norm applied only to the gathered rows `idx[i]` (>=0) of x; rows with idx<0 give zeros.
+ * (llama/model.py:347,352,358 restricted to the positions the losses read.) */
+int fvqa_rmsnorm_gather_fwd(const fvqa_bf16* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
+                            float* rstd, int rows_out, int dim, float eps, void* stream);
+/* dx[idx[i]] += rmsnorm backward of row i (dx must be zero-initialised by the caller; each source
+ * row may appear at most once per call). */
+int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const int32_t* idx,
+                             const fvqa_bf16* w, const float* rstd, fvqa_bf16* dx,
+                             int rows_out, int dim, void* stream);
+
+/* ---- SwiGLU (llama/model.py:142). g = [rows, 2*hid] holding a=W1x | b=W3x; c = silu(a)*b. -------- */
+int fvqa_swiglu_fwd(const fvqa_bf16* g, fvqa_bf16* c, int rows, int hid, void* stream);
+int fvqa_swiglu_bwd(const fvqa_bf16* dc, const fvqa_bf16* g, fvqa_bf16* dg, int rows, int hid, void* stream);
+
+/* ---- bf16 GEMM on tcgen05/TMEM fed by TMA (replaces every frozen nn.Linear: llama/model.py:89,
+ *      99-100,128,142,348,354 and their dX-only backward). C[M,N] = A[M,K] * B[N,K]^T (+ R[M,N]).
+ *      A, B bf16 K-contiguous; fp32 accumulation in TMEM. out_fp32 != 0 -> C is float, else bf16.
+ *      R (optional residual, bf16, leading dimension ldr) is added before the final rounding.
+ *      Requirements: K % 64 == 0, N % 8 == 0, lda/ldb/ldc/ldr % 8 == 0, 16-byte aligned pointers. */
+int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, void* C, int ldc,
+                      const fvqa_bf16* R, int ldr, int M, int N, int K, int out_fp32, void* stream);
+
+/* ---- fused attention (llama/model.py:61-67 RoPE, :87-126 attention incl. adapter branch). --------
+ * qkv  [n_seq*S, 3*H*hd] bf16, PRE-RoPE (q | k | v); RoPE (interleaved pairs) is applied on load.
+ * akv  [>=A rows, ld akv_ld] bf16: adapter keys (cols 0..H*hd) | adapter values (cols H*hd..2*H*hd),
+ *      no RoPE (model.py:99-100), shared by every sequence.
+ * rope [S, hd/2] fp32 cos and sin tables (model.py:45-50).
+ * gate1/gate2 [H] fp32 (model.py:84-85). vstart[n_seq] int32: video_start of the sequence, or -1
+ * for "no bias" sequences (QAV, model.py:121-122). max_feats = F.
+ * out  [n_seq*S, H*hd] bf16 = tanh(gate1)*softmax(q ka^T/sqrt(hd)) va + softmax(q k^T/sqrt(hd)+causal+bias) v
+ * lse  [n_seq, H, S] fp32 log-sum-exp of the text softmax (saved for backward).
+ * hd in {64, 128}; A <= 16. */
+int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos,
+                  const float* rope_sin, const float* gate1, const float* gate2, const int32_t* vstart,
+                  fvqa_bf16* out, float* lse, int n_seq, int S, int H, int hd, int A, int max_feats,
+                  void* stream);
+/* Backward. dqkv [n_seq*S, 3*H*hd] bf16 receives dq|dk|dv with the inverse RoPE already applied.
+ * Per-CTA partials of the shared-parameter gradients go to `ws` (size from fvqa_attn_bwd_ws_bytes)
+ * and are reduced deterministically into dakv [A, 2*H*hd] fp32 (dK_a | dV_a), dgate1[H], dgate2[H]
+ * (fp32; ACCUMULATED into, so the caller zero-initialises per step / layer as needed). */
+int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A);
+int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos,
+                  const float* rope_sin, const float* gate1, const float* gate2, const int32_t* vstart,
+                  const fvqa_bf16* out, const float* lse, const fvqa_bf16* dout, fvqa_bf16* dqkv,
+                  float* dakv, float* dgate1, float* dgate2, void* ws, int n_seq, int S, int H, int hd,
+                  int A, int max_feats, void* stream);
+
+/* ---- input embedding + video injection (llama/model.py:286-336). ---------------------------------
+ * vproj: vf32[B*F, d] = video[B*F, vdim] * Wv[d, vdim]^T in fp32 (model.py:322). */
+int fvqa_visual_proj_fwd(const float* video, const float* wv, float* vf32, int rows, int dim, int vdim, void* stream);
+/* dWv[d, vdim] += dvf[rows, d]^T * video[rows, vdim] (fp32, accumulated). */
+int fvqa_visual_proj_bwd(const float* dvf, const float* video, float* dwv, int rows, int dim, int vdim, void* stream);
+/* h0[n*S+p, :] for every sequence n:
+ *   mode vstart[n] >= 0 (VQA/VAQ): tok_emb[ids] except positions [vs, vs+F) <- bf16(vf32[vid[n],f] + temporal[f])
+ *   mode vstart[n] <  0 (QAV):     tok_emb[ids] * (labels[n,p] < 0), then += bf16(vf32+temporal) at qav_index[vid[n], f]
+ * ids/labels [n_seq, S] int32; seq_video[n] = video sample of sequence n; qav_index [B, F] int32. */
+int fvqa_build_h0_fwd(const fvqa_bf16* tok_emb, const int32_t* ids, const int32_t* labels,
+                      const int32_t* vstart, const int32_t* seq_video, const int32_t* qav_index,
+                      const float* vf32, const float* temporal, fvqa_bf16* h0,
+                      int n_seq, int S, int dim, int max_feats, void* stream);
+/* dvf[B, F, d] (fp32) = sum over sequences of dh0 at the video slots. Overwrites dvf. */
+int fvqa_build_h0_bwd(const fvqa_bf16* dh0, const int32_t* vstart, const int32_t* seq_video,
+                      const int32_t* qav_index, float* dvf, int n_seq, int n_video, int S, int dim,
+                      int max_feats, void* stream);
+/* dtemporal[F, d] += sum_b dvf[b]; dvf_total[b] = dvf[b] + dvf_qav[b] (in place into dvf). */
+int fvqa_video_grad_finish(float* dvf, const float* dvf_qav, float* dtemporal, int n_video, int dim,
+                           int max_feats, void* stream);
+
+/* ---- vocabulary cross-entropy over labelled rows (llama/model.py:348-356, ignore_index=0). -------
+ * logits [rows, V] fp32 (row stride ld), target[rows] int32 (<0 = padding row).
+ * row_loss[rows] = lse - logit[target] (0 for padding rows); row_lse saved for backward. */
+int fvqa_ce_fwd(const float* logits, int ld, const int32_t* target, float* row_loss, float* row_lse,
+                int rows, int V, void* stream);
+/* dlogits[rows, V] bf16 = (softmax - onehot) * (*gscale_dev) * inv_count; padding rows -> 0. */
+int fvqa_ce_bwd(const float* logits, int ld, const int32_t* target, const float* row_lse,
+                const float* gscale_dev, float inv_count, fvqa_bf16* dlogits, int ldd, int rows, int V,
+                void* stream);
+/* out[0] = sum(row_loss[0..rows)) * scale  (deterministic single-block reduction). */
+int fvqa_sum_scale(const float* v, int rows, float scale, float* out, void* stream);
+
+/* ---- QAV video-feature reconstruction loss (llama/model.py:358-361, ignore_index=-1). -------------
+ * hn [rows, d] bf16 = final-normed hidden rows (gathered), row_video[rows] = video sample (<0 pad),
+ * target[rows] in [0,F). logits[j] = <hn[i], vf32[row_video[i], j]> / tau. prob [rows, F] saved. */
+int fvqa_qav_loss_fwd(const fvqa_bf16* hn, const float* vf32, const int32_t* row_video,
+                      const int32_t* target, float tau, float* row_loss, float* prob, int rows, int dim,
+                      int max_feats, void* stream);
+/* dhn [rows, d] bf16 and dvf_qav [n_video, F, d] fp32 (overwritten; deterministic per-sample order). */
+int fvqa_qav_loss_bwd(const fvqa_bf16* hn, const float* vf32, const int32_t* row_video,
+                      const int32_t* target, const float* prob, const float* gscale_dev, float inv_count,
+                      float tau, fvqa_bf16* dhn, float* dvf_qav, int rows, int n_video, int dim,
+                      int max_feats, void* stream);
+
+/* ---- multiple-choice option scoring (llama/model_my_original_mod.py:375-377 + engine.py:88-93). ---
+ * token_loss [n_items, n_opt, S-1] fp32 -> prediction[i] = argmin_o( sum / count(loss != 0) ). */
+int fvqa_scatter_rows(const float* row_val, const int32_t* dst_index, float* dst, int rows, void* stream);
+int fvqa_option_score(const float* token_loss, int32_t* prediction, float* mean_loss, int n_items,
+                      int n_opt, int len, void* stream);
+
+/* ---- small utilities --------------------------------------------------------------------------- */
+int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, void* stream);
+/* dst[rows, cols] (fp32) += a[rows, K] * bT[cols, K]^T where a is fp32 and bT is bf16 (K-contiguous):
+ * used for d adapter = dK_a * Wk + dV_a * Wv with the transposed frozen weights. */
+int fvqa_small_gemm_f32_bf16(const float* a, int lda, const fvqa_bf16* bT, int ldb, float* dst, int ldd,
+                             int rows, int cols, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVQA_H_ */

@@ -52,28 +52,24 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return out.to(x.dtype)
 
 
-def attention(x, wq, wk, wv, wo, gate1, gate2, adapter, cos, sin, n_heads: int,
-              video_start: Optional[int], max_feats: int) -> torch.Tensor:
-    """`llama/model.py:87-128`. x [B,S,d]; adapter [A,d] (no RoPE on adapter keys, `:99-100`);
-    separate softmax over the A adapter keys scaled by tanh(gate1) (`:115`); gate2 added to text
-    scores of rows >= vs+F, columns vs..vs+F (`:116-119`) for VQA/VAQ; QAV passes video_start=None
-    (`:121-122`)."""
-    B, S, d = x.shape
-    hd = d // n_heads
-    dt = x.dtype
-    q = (x @ wq.t()).view(B, S, n_heads, hd)
-    k = (x @ wk.t()).view(B, S, n_heads, hd)
-    v = (x @ wv.t()).view(B, S, n_heads, hd)
+def attention_core(q, k, v, ak, av, gate1, gate2, cos, sin, video_start: Optional[int], max_feats: int) -> torch.Tensor:
+    """`llama/model.py:96-126` after the projections. q,k,v [B,S,H,hd] (pre-RoPE); ak,av [A,H,hd]
+    adapter keys/values (no RoPE, shared over the batch, `:99-100`). Returns [B,S,H*hd].
+    Separate softmax over the A adapter keys scaled by tanh(gate1) (`:115`); gate2 added to text
+    scores of rows >= vs+F, columns vs..vs+F (`:116-119`); video_start=None (QAV) -> plain softmax
+    in the activation dtype (`:121-122`)."""
+    B, S, H, hd = q.shape
+    dt = q.dtype
+    A = ak.shape[0]
     q, k = apply_rope(q, cos[:S], sin[:S]), apply_rope(k, cos[:S], sin[:S])
-    A = adapter.shape[0]
-    ak = (adapter @ wk.t()).view(1, A, n_heads, hd).expand(B, -1, -1, -1)
-    av = (adapter @ wv.t()).view(1, A, n_heads, hd).expand(B, -1, -1, -1)
-    q = q.transpose(1, 2)                                   # [B,H,S,hd]
-    keys = torch.cat([ak, k], dim=1).transpose(1, 2)        # [B,H,A+S,hd]
-    vals = torch.cat([av, v], dim=1).transpose(1, 2)
+    akb = ak[None].expand(B, -1, -1, -1)
+    avb = av[None].expand(B, -1, -1, -1)
+    q = q.transpose(1, 2)                                    # [B,H,S,hd]
+    keys = torch.cat([akb, k], dim=1).transpose(1, 2)        # [B,H,A+S,hd]
+    vals = torch.cat([avb, v], dim=1).transpose(1, 2)
     scores = (q @ keys.transpose(2, 3)) / math.sqrt(hd)
-    causal = torch.triu(torch.full((S, S), float("-inf"), device=x.device), diagonal=1).to(dt)
-    mask = torch.cat([torch.zeros(S, A, device=x.device, dtype=dt), causal], dim=-1)
+    causal = torch.triu(torch.full((S, S), float("-inf"), device=q.device), diagonal=1).to(dt)
+    mask = torch.cat([torch.zeros(S, A, device=q.device, dtype=dt), causal], dim=-1)
     scores = scores + mask[None, None]
     p_adapter = F.softmax(scores[..., :A].float(), dim=-1).to(dt) * gate1.tanh().to(dt)
     text = scores[..., A:]
@@ -83,9 +79,23 @@ def attention(x, wq, wk, wv, wo, gate1, gate2, adapter, cos, sin, n_heads: int,
         text[:, :, vs + Fv:, vs:vs + Fv] = text[:, :, vs + Fv:, vs:vs + Fv] + gate2.to(dt)
         p_text = F.softmax(text.float(), dim=-1).to(dt)
     else:
-        p_text = F.softmax(text, dim=-1)                    # QAV: softmax in the activation dtype
-    out = torch.cat([p_adapter, p_text], dim=-1) @ vals     # [B,H,S,hd]
-    out = out.transpose(1, 2).contiguous().view(B, S, d)
+        p_text = F.softmax(text, dim=-1)                     # QAV: softmax in the activation dtype
+    out = torch.cat([p_adapter, p_text], dim=-1) @ vals      # [B,H,S,hd]
+    return out.transpose(1, 2).contiguous().view(B, S, H * hd)
+
+
+def attention(x, wq, wk, wv, wo, gate1, gate2, adapter, cos, sin, n_heads: int,
+              video_start: Optional[int], max_feats: int) -> torch.Tensor:
+    """`llama/model.py:87-128`. x [B,S,d]; adapter [A,d]."""
+    B, S, d = x.shape
+    hd = d // n_heads
+    q = (x @ wq.t()).view(B, S, n_heads, hd)
+    k = (x @ wk.t()).view(B, S, n_heads, hd)
+    v = (x @ wv.t()).view(B, S, n_heads, hd)
+    A = adapter.shape[0]
+    ak = (adapter @ wk.t()).view(A, n_heads, hd)
+    av = (adapter @ wv.t()).view(A, n_heads, hd)
+    out = attention_core(q, k, v, ak, av, gate1, gate2, cos, sin, video_start, max_feats)
     return out @ wo.t()
 
 

@@ -1,0 +1,298 @@
+"""Parity of every CUDA kernel (called through the C ABI) against the oracle's PyTorch restatement
+of the same reference op, on seeded inputs. bf16 I/O, fp32 math: tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import llama_vqa_oracle as O  # noqa: E402  (checker only)
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def bf16_randn(*shape, std=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * std).to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------ RMSNorm / SwiGLU
+@pytest.mark.parametrize("rows,dim", [(7, 256), (1024, 4096), (33, 5120)])
+def test_rmsnorm_fwd_bwd(fvqa_lib, rows, dim):
+    from flipped_vqa_b200 import ops
+    x = bf16_randn(rows, dim, seed=1)
+    w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(torch.bfloat16)
+    dy = bf16_randn(rows, dim, seed=2)
+    res = bf16_randn(rows, dim, seed=3)
+    y, rstd = ops.rmsnorm_fwd(x, w, 1e-6)
+    xr = x.float().requires_grad_(True)
+    yr = O.rmsnorm(xr, w.float(), 1e-6)
+    # bit-level agreement is not expected (two bf16 roundings); 1 bf16 ulp ~ 0.4 %
+    assert relerr(y, yr) < 4e-3
+    (yr * dy.float()).sum().backward()
+    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres=res)
+    assert relerr(dx, xr.grad + res.float()) < 4e-3
+    dx2 = ops.rmsnorm_bwd(dy, x, w, rstd)
+    assert relerr(dx2, xr.grad) < 4e-3
+
+
+def test_rmsnorm_gather_scatter(fvqa_lib):
+    from flipped_vqa_b200 import ops
+    rows, dim = 300, 512
+    x = bf16_randn(rows, dim, seed=4)
+    w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(torch.bfloat16)
+    idx = torch.tensor([5, 17, -1, 299, 0, -1, 42], dtype=torch.int32, device="cuda")
+    y, rstd = ops.rmsnorm_gather_fwd(x, idx, w, 1e-6)
+    valid = idx >= 0
+    yr = O.rmsnorm(x[idx[valid].long()].float(), w.float(), 1e-6)
+    assert relerr(y[valid], yr) < 4e-3
+    assert float(y[~valid].float().abs().max()) == 0.0
+    dy = bf16_randn(idx.numel(), dim, seed=5)
+    dx = torch.zeros_like(x)
+    ops.rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx)
+    xr = x.float().requires_grad_(True)
+    (O.rmsnorm(xr[idx[valid].long()], w.float(), 1e-6) * dy[valid].float()).sum().backward()
+    assert relerr(dx, xr.grad) < 4e-3
+
+
+@pytest.mark.parametrize("rows,hid", [(5, 768), (1024, 11008)])
+def test_swiglu(fvqa_lib, rows, hid):
+    from flipped_vqa_b200 import ops
+    g = bf16_randn(rows, 2 * hid, seed=6)
+    dc = bf16_randn(rows, hid, seed=7)
+    c = ops.swiglu_fwd(g)
+    gr = g.float().requires_grad_(True)
+    cr = O.swiglu(gr[:, :hid], gr[:, hid:])
+    assert relerr(c, cr) < 4e-3
+    (cr * dc.float()).sum().backward()
+    dg = ops.swiglu_bwd(dc, g)
+    assert relerr(dg, gr.grad) < 4e-3
+
+
+# ------------------------------------------------------------------ tcgen05 GEMM
+GEMM_SHAPES = [
+    (128, 256, 64), (128, 128, 128), (256, 512, 256), (200, 384, 128), (10, 256, 512),
+    (384, 1536, 256), (1024, 4096, 4096), (3072, 11008, 4096), (3072, 4096, 11008), (96, 32000, 4096),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_nt(fvqa_lib, M, N, K):
+    from flipped_vqa_b200 import ops
+    a = bf16_randn(M, K, seed=10)
+    b = bf16_randn(N, K, std=0.05, seed=11)
+    ref = a.float() @ b.float().t()
+    c = ops.gemm_nt(a, b)
+    assert relerr(c, ref) < 5e-3, f"bf16 out relerr {relerr(c, ref)}"
+    c32 = ops.gemm_nt(a, b, out_fp32=True)
+    assert relerr(c32, ref) < 2e-4, f"fp32 out relerr {relerr(c32, ref)}"
+    r = bf16_randn(M, N, seed=12)
+    cr = ops.gemm_nt(a, b, residual=r)
+    assert relerr(cr, ref + r.float()) < 5e-3
+
+
+def test_gemm_strided_views(fvqa_lib):
+    """Sub-blocks of larger matrices (used for Wk|Wv of the fused QKV weight and its transpose)."""
+    from flipped_vqa_b200 import ops
+    d = 256
+    a_full = bf16_randn(16, 2 * d, seed=13)
+    wT = bf16_randn(d, 3 * d, std=0.05, seed=14)          # [d, 3d] ; use columns d..3d  -> B[N=d, K=2d], ldb=3d
+    b = wT[:, d:]
+    ref = a_full[:10].float() @ b.float().t()
+    out = ops.gemm_nt(a_full, b, out_fp32=True, M=10)
+    assert out.shape == (10, d)
+    assert relerr(out, ref) < 2e-4
+    w = bf16_randn(3 * d, d, std=0.05, seed=15)           # rows d..3d of [3d, d]
+    x = bf16_randn(10, d, seed=16)
+    out2 = ops.gemm_nt(x, w[d:])
+    assert relerr(out2, x.float() @ w[d:].float().t()) < 5e-3
+
+
+def test_gemm_rejects_bad_shapes(fvqa_lib):
+    from flipped_vqa_b200 import ops, _lib
+    a = bf16_randn(128, 72)
+    b = bf16_randn(128, 72)
+    with pytest.raises(_lib.FvqaError):
+        ops.gemm_nt(a, b)           # K not a multiple of 64
+
+
+# ------------------------------------------------------------------ attention
+def _attn_case(n_seq, S, H, hd, A, F, vstarts, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    D = H * hd
+    qkv = (torch.randn(n_seq * S, 3 * D, device="cuda", generator=g)).to(torch.bfloat16)
+    akv = (torch.randn(16, 2 * D, device="cuda", generator=g)).to(torch.bfloat16)
+    akv[A:] = 0
+    gate1 = torch.randn(H, device="cuda", generator=g) * 0.5
+    gate2 = -3.5 + 0.1 * torch.randn(H, device="cuda", generator=g)
+    cos, sin = O.rope_table(hd, S)
+    cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    vstart = torch.tensor(vstarts, dtype=torch.int32, device="cuda")
+    dout = (torch.randn(n_seq * S, D, device="cuda", generator=g)).to(torch.bfloat16)
+    return qkv, akv, gate1, gate2, cos, sin, vstart, dout
+
+
+def _attn_ref(qkv, akv, gate1, gate2, cos, sin, vstarts, dout, n_seq, S, H, hd, A, F):
+    D = H * hd
+    qkv_r = qkv.float().requires_grad_(True)
+    akv_r = akv[:A].float().requires_grad_(True)
+    g1 = gate1.clone().requires_grad_(True)
+    g2 = gate2.clone().requires_grad_(True)
+    outs = []
+    x = qkv_r.view(n_seq, S, 3, H, hd)
+    ak = akv_r[:, :D].view(A, H, hd)
+    av = akv_r[:, D:].view(A, H, hd)
+    for n in range(n_seq):
+        vs = vstarts[n]
+        o = O.attention_core(x[n:n + 1, :, 0], x[n:n + 1, :, 1], x[n:n + 1, :, 2], ak, av, g1.view(1, H, 1, 1), g2.view(1, H, 1, 1),
+                             cos, sin, None if vs < 0 else vs, F)
+        outs.append(o)
+    out = torch.cat(outs, 0).view(n_seq * S, D)
+    (out * dout.float()).sum().backward()
+    return out.detach(), qkv_r.grad, akv_r.grad, g1.grad, g2.grad
+
+
+@pytest.mark.parametrize("n_seq,S,H,hd,vstarts", [
+    (3, 48, 2, 64, [12, 12, -1]),
+    (3, 128, 2, 128, [18, -1, 18]),
+    (2, 200, 3, 128, [18, -1]),
+    (2, 130, 2, 64, [100, -1]),
+])
+def test_attention_fwd_bwd(fvqa_lib, n_seq, S, H, hd, vstarts):
+    from flipped_vqa_b200 import ops
+    A, F = 10, 10
+    qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, vstarts, seed=20)
+    out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
+    ref_out, ref_dqkv, ref_dakv, ref_dg1, ref_dg2 = _attn_ref(qkv, akv, gate1, gate2, cos, sin, vstarts, dout, n_seq, S, H, hd, A, F)
+    assert relerr(out, ref_out) < 1e-2, f"out {relerr(out, ref_out)}"
+    dqkv, dakv, dg1, dg2 = ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
+    D = H * hd
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        e = relerr(dqkv[:, sl], ref_dqkv[:, sl])
+        assert e < 2e-2, f"{name} relerr {e}"
+    assert relerr(dakv, ref_dakv) < 2e-2, f"dakv {relerr(dakv, ref_dakv)}"
+    assert relerr(dg1, ref_dg1) < 2e-2, f"dgate1 {relerr(dg1, ref_dg1)} {dg1} {ref_dg1}"
+    assert relerr(dg2, ref_dg2) < 2e-2, f"dgate2 {relerr(dg2, ref_dg2)} {dg2} {ref_dg2}"
+
+
+def test_attention_deterministic(fvqa_lib):
+    from flipped_vqa_b200 import ops
+    n_seq, S, H, hd, A, F = 3, 128, 2, 128, 10, 10
+    qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, [18, 18, -1], seed=21)
+    out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
+    r1 = ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
+    r2 = ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
+    for a, b in zip(r1, r2):
+        assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ input side + heads
+def test_visual_proj_and_h0(fvqa_lib):
+    from flipped_vqa_b200 import ops
+    B, F, d, V, S, vdim = 3, 10, 256, 500, 40, 768
+    g = torch.Generator(device="cuda").manual_seed(30)
+    video = torch.randn(B * F, vdim, device="cuda", generator=g)
+    wv = torch.randn(d, vdim, device="cuda", generator=g) / math.sqrt(vdim)
+    temporal = torch.randn(F, d, device="cuda", generator=g)
+    vf = ops.visual_proj_fwd(video, wv)
+    assert relerr(vf, video @ wv.t()) < 1e-5
+    dvf_in = torch.randn(B * F, d, device="cuda", generator=g)
+    dwv = ops.visual_proj_bwd(dvf_in, video)
+    assert relerr(dwv, dvf_in.t() @ video) < 1e-5
+    emb = bf16_randn(V, d, seed=31)
+    n_seq = 3 * B
+    ids = torch.randint(0, V, (n_seq, S), device="cuda", generator=g, dtype=torch.int32)
+    labels = torch.zeros(n_seq, S, dtype=torch.int32, device="cuda")
+    qav_index = torch.stack([torch.arange(p, p + F) for p in (20, 25, 29)]).to(torch.int32).cuda()
+    labels[2 * B:] = -1
+    for b in range(B):
+        labels[2 * B + b, qav_index[b].long()] = torch.arange(F, dtype=torch.int32, device="cuda")
+    vstart = torch.tensor([12] * (2 * B) + [-1] * B, dtype=torch.int32, device="cuda")
+    seq_video = torch.tensor(list(range(B)) * 3, dtype=torch.int32, device="cuda")
+    h0 = ops.build_h0_fwd(emb, ids, labels, vstart, seq_video, qav_index, vf, temporal, n_seq, S, F)
+    # reference (llama/model.py:324-336)
+    video_feature = (vf.view(B, F, d) + temporal[None]).to(torch.bfloat16)
+    ref = emb[ids.long()].clone()
+    ref[:2 * B, 12:12 + F] = video_feature.repeat(2, 1, 1)
+    q = ref[2 * B:] * (~(labels[2 * B:] >= 0))[..., None]
+    q = q.scatter_add(1, qav_index.long()[..., None].expand(-1, -1, d), video_feature)
+    ref[2 * B:] = q
+    assert torch.equal(h0.view(n_seq, S, d), ref)
+    dh0 = bf16_randn(n_seq * S, d, seed=32)
+    dvf = ops.build_h0_bwd(dh0, vstart, seq_video, qav_index, n_seq, B, S, F)
+    dh = dh0.float().view(n_seq, S, d)
+    ref_dvf = dh[:B, 12:12 + F] + dh[B:2 * B, 12:12 + F] + torch.gather(dh[2 * B:], 1, qav_index.long()[..., None].expand(-1, -1, d))
+    assert relerr(dvf, ref_dvf.reshape(B * F, d)) < 1e-6
+    dq = torch.randn(B * F, d, device="cuda", generator=g)
+    dvf_copy = dvf.clone()
+    dtemp = ops.video_grad_finish(dvf, dq, B, F)
+    assert relerr(dtemp, dvf_copy.view(B, F, d).sum(0)) < 1e-6
+    assert relerr(dvf, dvf_copy + dq) < 1e-6
+
+
+def test_ce_fwd_bwd(fvqa_lib):
+    from flipped_vqa_b200 import ops
+    rows, V = 37, 32000
+    g = torch.Generator(device="cuda").manual_seed(40)
+    logits = torch.randn(rows, V, device="cuda", generator=g) * 3
+    target = torch.randint(1, V, (rows,), device="cuda", generator=g, dtype=torch.int32)
+    target[5] = -1
+    target[20] = -1
+    row_loss, row_lse = ops.ce_fwd(logits, target)
+    valid = target >= 0
+    lr = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr[valid], target[valid].long(), reduction="none")
+    assert relerr(row_loss[valid], ref) < 1e-5
+    assert float(row_loss[~valid].abs().max()) == 0.0
+    n = int(valid.sum())
+    out = torch.zeros(1, device="cuda")
+    ops.sum_scale(row_loss, rows, 1.0 / n, out)
+    assert abs(float(out) - float(ref.mean())) < 1e-4
+    gs = torch.tensor([2.5], device="cuda")
+    dl = ops.ce_bwd(logits, target, row_lse, gs, 1.0 / n)
+    (ref.mean() * 2.5).backward()
+    assert relerr(dl[valid], lr.grad[valid]) < 5e-3
+    assert float(dl[~valid].float().abs().max()) == 0.0
+
+
+def test_qav_loss(fvqa_lib):
+    from flipped_vqa_b200 import ops
+    B, F, d, tau = 4, 10, 512, 100.0
+    g = torch.Generator(device="cuda").manual_seed(41)
+    rows = B * F + 3
+    hn = bf16_randn(rows, d, seed=42)
+    vf = torch.randn(B * F, d, device="cuda", generator=g)
+    row_video = torch.tensor([b for b in range(B) for _ in range(F)] + [-1, -1, -1], dtype=torch.int32, device="cuda")
+    target = torch.tensor(list(range(F)) * B + [0, 0, 0], dtype=torch.int32, device="cuda")
+    row_loss, prob = ops.qav_loss_fwd(hn, vf, row_video, target, tau, F)
+    hr = hn.float().requires_grad_(True)
+    vr = vf.clone().requires_grad_(True)
+    valid = row_video >= 0
+    logits = torch.einsum("rd,rfd->rf", hr[valid], vr.view(B, F, d)[row_video[valid].long()]) / tau
+    ref = torch.nn.functional.cross_entropy(logits, target[valid].long(), reduction="none")
+    assert relerr(row_loss[valid], ref) < 1e-5
+    gs = torch.tensor([0.7], device="cuda")
+    n = int(valid.sum())
+    dhn, dvfq = ops.qav_loss_bwd(hn, vf, row_video, target, prob, gs, 1.0 / n, tau, B, F)
+    (ref.mean() * 0.7).backward()
+    assert relerr(dhn[valid], hr.grad[valid]) < 5e-3
+    assert relerr(dvfq, vr.grad) < 1e-5
+
+
+def test_option_score(fvqa_lib):
+    from flipped_vqa_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(43)
+    tok = torch.zeros(6, 5, 47, device="cuda")
+    tok[:, :, 40:44] = torch.rand(6, 5, 4, device="cuda", generator=g) * 5
+    tok[2, 3, 41] = 0.0      # an exactly-zero labelled loss is NOT counted (engine.py:88 quirk)
+    pred, mean = ops.option_score(tok)
+    ref = O.option_predict(tok)
+    assert torch.equal(pred.long(), ref)
+    vals = torch.tensor([1.0, 2.0, 3.0], device="cuda")
+    dst = torch.zeros(10, device="cuda")
+    ops.scatter_rows(vals, torch.tensor([7, -1, 2], dtype=torch.int32, device="cuda"), dst)
+    assert dst.tolist() == [0, 0, 3.0, 0, 0, 0, 0, 1.0, 0, 0]
