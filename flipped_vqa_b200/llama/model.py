@@ -1,0 +1,317 @@
+"""LLaMA-VQA model with the reference's Python surface, running on the B200 kernels.
+
+Drop-in for `/root/reference/llama/model.py`: same `ModelArgs`, same `Transformer(params, args)`
+constructor attributes, same parameter / state-dict names (so `llama_vqa.py`'s freeze rule and
+`util/misc.py`'s trainable-only checkpoints keep working), same `forward(data, inference=False)`
+contract returning `(vqa_loss, vaq_loss, qav_loss)` (`model.py:250-365`) or, with
+``inference=True``, the per-token option losses `[bsz, n_options, S-1]` of
+`llama/model_my_original_mod.py:375-377,506`.
+
+Underneath, nothing of the reference's op sequence is kept: the three objective streams are
+concatenated into one token matrix, every frozen Linear is the tcgen05 GEMM, attention / norms /
+SwiGLU / heads are the fused kernels of libfvqa.so, and backward is hand-written (dX-only through
+the frozen base). The nn.Module tree below is only a *named parameter container*.
+There is no CPU path: calling forward without an sm_100 GPU raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from ..step import BatchPlan, GradBuffers, LayerWeights, StepEngine
+from ..synthetic import ffn_hidden_dim
+from .tokenizer import Tokenizer
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class ModelArgs:
+    """Same fields and defaults as `llama/model.py:17-29` (max_feats / bias are injected by
+    Transformer.__init__, `:193-194`)."""
+    dim: int = 512
+    n_layers: int = 8
+    n_heads: int = 8
+    vocab_size: int = -1
+    multiple_of: int = 256
+    norm_eps: float = 1e-5
+
+    max_batch_size: int = 32
+    max_seq_len: int = 2048
+    adapter_len: int = 10
+    adapter_layer: int = 30
+
+
+class _FrozenLinear(nn.Module):
+    """Named holder of a frozen [out, in] weight (a view into the packed device layout)."""
+
+    def __init__(self, weight_view: torch.Tensor):
+        super().__init__()
+        self.weight = nn.Parameter(weight_view, requires_grad=False)
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim: int, eps: float, device, dtype):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim, device=device, dtype=dtype), requires_grad=False)
+
+
+class Attention(nn.Module):
+    """Parameter names of `llama/model.py:71-85`: wq/wk/wv/wo (frozen) + gate1 (zeros) and
+    gate2 (-bias) [1,H,1,1] fp32 trainables. The reference's dead KV caches are not allocated."""
+
+    def __init__(self, wqkv: torch.Tensor, wo: torch.Tensor, n_heads: int, bias: float, device):
+        super().__init__()
+        d = wo.shape[0]
+        self.wq = _FrozenLinear(wqkv[0:d])
+        self.wk = _FrozenLinear(wqkv[d:2 * d])
+        self.wv = _FrozenLinear(wqkv[2 * d:3 * d])
+        self.wo = _FrozenLinear(wo)
+        self.gate1 = nn.Parameter(torch.zeros(1, n_heads, 1, 1, device=device))
+        self.gate2 = nn.Parameter(torch.ones(1, n_heads, 1, 1, device=device) * -bias)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, w13: torch.Tensor, w2: torch.Tensor):
+        super().__init__()
+        hid = w2.shape[1]
+        self.w1 = _FrozenLinear(w13[0:hid])
+        self.w2 = _FrozenLinear(w2)
+        self.w3 = _FrozenLinear(w13[hid:2 * hid])
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, layer_id: int, args: ModelArgs, hidden: int, device, dtype, init_std: float):
+        super().__init__()
+        d = args.dim
+        self.layer_id = layer_id
+        # packed device layout: one GEMM for Wq|Wk|Wv, one for W1|W3
+        self._wqkv = torch.empty(3 * d, d, device=device, dtype=dtype).normal_(0, init_std)
+        self._wo = torch.empty(d, d, device=device, dtype=dtype).normal_(0, init_std)
+        self._w13 = torch.empty(2 * hidden, d, device=device, dtype=dtype).normal_(0, init_std)
+        self._w2 = torch.empty(d, hidden, device=device, dtype=dtype).normal_(0, init_std)
+        self.attention = Attention(self._wqkv, self._wo, args.n_heads, args.bias, device)
+        self.feed_forward = FeedForward(self._w13, self._w2)
+        self.attention_norm = RMSNorm(d, args.norm_eps, device, dtype)
+        self.ffn_norm = RMSNorm(d, args.norm_eps, device, dtype)
+
+
+class _Embedding(nn.Module):
+    def __init__(self, n: int, dim: int, device, dtype, requires_grad: bool, std: float = 1.0):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n, dim, device=device, dtype=dtype).normal_(0, std), requires_grad=requires_grad)
+
+
+class _TrainableLinear(nn.Module):
+    def __init__(self, in_f: int, out_f: int, device):
+        super().__init__()
+        bound = 1.0 / math.sqrt(in_f)                      # nn.Linear default init
+        self.weight = nn.Parameter(torch.empty(out_f, in_f, device=device).uniform_(-bound, bound))
+
+
+class _StepFn(torch.autograd.Function):
+    """The whole training step as ONE autograd node: forward = fused kernels (+ saved activations),
+    backward = hand-written dX-only pass. Upstream gradients (e.g. GradScaler's scale,
+    `util/misc.py:260`) are honoured: every loss-gradient kernel multiplies by grad_output."""
+
+    @staticmethod
+    def forward(ctx, model, plan, n_run, *trainables):
+        adapter_w, visual_w, temporal_w = trainables[:3]
+        gate1 = [g.view(-1) for g in trainables[3:3 + n_run]]
+        gate2 = [g.view(-1) for g in trainables[3 + n_run:3 + 2 * n_run]]
+        losses, sv = model._engine.forward(plan, model._run_weights, model.tok_embeddings.weight, model.output.weight,
+                                           model.norm.weight, adapter_w, visual_w, temporal_w, gate1, gate2, save=True)
+        ctx.model, ctx.sv, ctx.n_run = model, sv, n_run
+        ctx.gates = (gate1, gate2)
+        ctx.streams = list(plan.streams)
+        return tuple(losses[k] for k in plan.streams)
+
+    @staticmethod
+    def backward(ctx, *grad_out):
+        model, sv, n_run = ctx.model, ctx.sv, ctx.n_run
+        dev = model._engine.device
+        gscale = torch.zeros(3, dtype=torch.float32, device=dev)
+        for k, g in zip(ctx.streams, grad_out):
+            if g is not None:
+                gscale[{"vqa": 0, "vaq": 1, "qav": 2}[k]] = g.float()
+        gb = model._grad_buffers
+        sync = model.grad_sync
+        model._engine.backward(sv, gscale, model._run_weights, model._output_t, model.norm.weight, ctx.gates[0], ctx.gates[1], gb,
+                               on_layer_done=(sync.layer_done if sync is not None else None))
+        if sync is not None:
+            sync.finish()
+        flat = gb.flat.clone()                              # autograd may keep what we return: never alias the work buffer
+        view = lambda k, shape: flat[gb.offsets[k]:gb.offsets[k] + gb.sizes[k]].view(shape)
+        H = model.params.n_heads
+        out = [None, None, None, view("adapter", gb.adapter.shape), view("visual", gb.visual.shape), view("temporal", gb.temporal.shape)]
+        g1, g2 = view("gate1", gb.gate1.shape), view("gate2", gb.gate2.shape)
+        out += [g1[l].view(1, H, 1, 1) for l in range(n_run)]
+        out += [g2[l].view(1, H, 1, 1) for l in range(n_run)]
+        ctx.sv = None
+        return tuple(out)
+
+
+class Transformer(nn.Module):
+    def __init__(self, params: ModelArgs, args, tokenizer=None, device=None, init_std: float = 0.02):
+        super().__init__()
+        params.max_feats = args.max_feats                  # `model.py:193-194`
+        params.bias = args.bias
+        self.args = args
+        self.params = params
+        self.vocab_size = params.vocab_size
+        self.n_layers = params.n_layers
+        self.max_feats = args.max_feats
+        if getattr(args, "audio", False):
+            raise NotImplementedError("audio fusion variants (`model.py:209-227,306-322`) are outside the accelerated path "
+                                      "(SURVEY.md §8(f) rank 4); use the reference for --audio runs")
+        self.tokenizer = tokenizer if tokenizer is not None else Tokenizer(model_path=f"{args.llama_model_path}./tokenizer.model", args=args)
+        self.eos_id = self.tokenizer.eos_id
+        self.answer_token_id = self.tokenizer.a_token_id
+        self.q_token_id = self.tokenizer.q_token_id
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self._device = torch.device(device)
+        dt = BF16
+        d = params.dim
+        self.hidden_dim = ffn_hidden_dim(d, params.multiple_of)
+        self.video_dim = 768
+
+        self.tok_embeddings = _Embedding(params.vocab_size, d, device, dt, requires_grad=False, std=init_std)
+        self.adapter_query = _Embedding(params.adapter_len * params.adapter_layer, d, device, torch.float32, requires_grad=True)
+        self.visual_proj = _TrainableLinear(self.video_dim, d, device)
+        self.temporal_emb = _Embedding(self.max_feats, d, device, torch.float32, requires_grad=True)
+        self.adapter_len = params.adapter_len
+        self.adapter_layer = params.adapter_layer
+        self.layers = nn.ModuleList([TransformerBlock(i, params, self.hidden_dim, device, dt, init_std) for i in range(params.n_layers)])
+        self.norm = RMSNorm(d, params.norm_eps, device, dt)
+        self.output = _FrozenLinear(torch.empty(params.vocab_size, d, device=device, dtype=dt).normal_(0, init_std))
+        self.tau = args.tau
+
+        self.grad_sync = None                               # set by flipped_vqa_b200.dp.DataParallel
+        self._engine: Optional[StepEngine] = None
+        self._run_weights: Optional[List[LayerWeights]] = None
+        self._output_t = None
+        self._grad_buffers: Optional[GradBuffers] = None
+        self._pack_token = None
+        self.last_plan: Optional[BatchPlan] = None
+
+    # ------------------------------------------------------------------ weight layout
+    def run_layers(self):
+        """Only the last `adapter_layer` layers run (`model.py:338`)."""
+        return list(self.layers[-1 * self.adapter_layer:])
+
+    def _token(self):
+        ps = [self.layers[0].attention.wq.weight, self.layers[-1].feed_forward.w2.weight, self.output.weight, self.tok_embeddings.weight]
+        return tuple((p.data_ptr(), p._version, p.dtype, str(p.device)) for p in ps)
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._pack_token = None                             # .to()/.cuda()/.half() replace parameter storage
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        res = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._pack_token = None
+        return res
+
+    def repack(self):
+        """(Re)build the packed / transposed frozen-weight layout from the named parameters and apply
+        the dtype contract of `llama_vqa.py:71-76` on the device (frozen bf16, trainables fp32)."""
+        dev = self._device
+        if dev.type != "cuda":
+            raise RuntimeError("flipped_vqa_b200 runs only on a CUDA sm_100a device (no CPU path)")
+        d, hid = self.params.dim, self.hidden_dim
+        for name, p in self.named_parameters():
+            trainable = any(s in name for s in ("gate", "adapter", "temporal_emb", "visual_proj"))
+            want = torch.float32 if trainable else BF16
+            if p.dtype != want or p.device != dev:
+                p.data = p.data.to(device=dev, dtype=want)
+        for blk in self.layers:
+            at, ff = blk.attention, blk.feed_forward
+            if not (at.wq.weight.data_ptr() == blk._wqkv.data_ptr() and blk._wqkv.device == dev and blk._wqkv.dtype == BF16
+                    and at.wk.weight.data_ptr() == blk._wqkv[d:].data_ptr() and at.wv.weight.data_ptr() == blk._wqkv[2 * d:].data_ptr()):
+                blk._wqkv = torch.cat([at.wq.weight.data, at.wk.weight.data, at.wv.weight.data], 0).contiguous()
+                at.wq.weight.data, at.wk.weight.data, at.wv.weight.data = blk._wqkv[0:d], blk._wqkv[d:2 * d], blk._wqkv[2 * d:]
+            if not (ff.w1.weight.data_ptr() == blk._w13.data_ptr() and blk._w13.device == dev and blk._w13.dtype == BF16
+                    and ff.w3.weight.data_ptr() == blk._w13[hid:].data_ptr()):
+                blk._w13 = torch.cat([ff.w1.weight.data, ff.w3.weight.data], 0).contiguous()
+                ff.w1.weight.data, ff.w3.weight.data = blk._w13[0:hid], blk._w13[hid:]
+            blk._wo = at.wo.weight.data
+            blk._w2 = ff.w2.weight.data
+        run = []
+        for blk in self.run_layers():
+            run.append(LayerWeights(
+                wqkv=blk._wqkv, wqkv_t=blk._wqkv.t().contiguous(), wo=blk._wo, wo_t=blk._wo.t().contiguous(),
+                w13=blk._w13, w13_t=blk._w13.t().contiguous(), w2=blk._w2, w2_t=blk._w2.t().contiguous(),
+                attn_norm=blk.attention_norm.weight.data, ffn_norm=blk.ffn_norm.weight.data))
+        self._run_weights = run
+        self._output_t = self.output.weight.data.t().contiguous()
+        if self._engine is None:
+            self._engine = StepEngine(d, self.params.n_heads, hid, self.params.vocab_size, self.adapter_len, self.max_feats,
+                                      self.params.norm_eps, self.tau, self.params.max_seq_len, dev)
+        n_run = len(run)
+        self._grad_buffers = GradBuffers(n_run, self.adapter_len, d, self.params.n_heads, self.video_dim, self.max_feats, dev)
+        self._pack_token = self._token()
+
+    def _ensure_packed(self):
+        if self._pack_token is None or self._pack_token != self._token():
+            self.repack()
+
+    def trainable_parameters(self):
+        n_run = len(self.run_layers())
+        ps = [self.adapter_query.weight, self.visual_proj.weight, self.temporal_emb.weight]
+        ps += [blk.attention.gate1 for blk in self.run_layers()]
+        ps += [blk.attention.gate2 for blk in self.run_layers()]
+        return ps, n_run
+
+    # ------------------------------------------------------------------ forward
+    def streams(self):
+        return ["vqa"] + (["vaq"] if self.args.vaq else []) + (["qav"] if self.args.qav else [])
+
+    def forward(self, data, inference: bool = False):
+        if inference:
+            return self.inference(data)
+        self._ensure_packed()
+        dev = self._device
+        plan = BatchPlan(data, self.streams(), self.max_feats).to_device(dev)
+        self.last_plan = plan
+        trainables, n_run = self.trainable_parameters()
+        if torch.is_grad_enabled() and any(p.requires_grad for p in trainables):
+            outs = _StepFn.apply(self, plan, n_run, *trainables)
+            losses = dict(zip(plan.streams, outs))
+        else:
+            g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]
+            g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
+            losses, _ = self._engine.forward(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
+                                             self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
+                                             g1, g2, save=False)
+        zero = lambda: torch.tensor([0], device=dev)        # disabled objectives, `model.py:302`
+        return losses["vqa"], losses.get("vaq", zero()), losses.get("qav", zero())
+
+    @torch.no_grad()
+    def inference(self, data):
+        """Loss-based option scoring: VQA stream only over bsz*n_options sequences
+        (`model_my_original_mod.py:281,332-333,348-360,375-377,506`)."""
+        self._ensure_packed()
+        dev = self._device
+        plan = BatchPlan(data, ["vqa"], self.max_feats, inference=True).to_device(dev)
+        self.last_plan = plan
+        trainables, n_run = self.trainable_parameters()
+        g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]
+        g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
+        tok, _ = self._engine.forward(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
+                                      self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
+                                      g1, g2, save=False, token_losses=True)
+        return tok
+
+    @staticmethod
+    def predict_options(token_losses: torch.Tensor) -> torch.Tensor:
+        """`engine.py:88-93` as one kernel: argmin over options of sum / count(loss != 0)."""
+        from .. import ops
+        pred, _ = ops.option_score(token_losses.contiguous())
+        return pred.long()

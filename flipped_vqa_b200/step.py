@@ -1,0 +1,324 @@
+"""Host-side orchestration of one LLaMA-VQA step on the CUDA kernels (no torch math on the hot path).
+
+`BatchPlan`   – turns the reference's batch dict (`dataloader/__init__.py:28-90`) into flat int32
+                arrays: concatenated objective streams, labelled-row lists for the fused heads.
+`PackedWeights` – the frozen base in its B200 layout: Wq|Wk|Wv and W1|W3 concatenated so each is one
+                GEMM, plus load-time TRANSPOSED copies so the dX-only backward is the same K-major
+                tcgen05 GEMM (HBM is plentiful: 2x13.5 GB for 7B of 180 GB).
+`StepEngine`  – workspace + forward / backward kernel sequences (`llama/model.py:286-361` forward;
+                backward derived in SURVEY.md §8(a) addendum: dX only through the frozen base,
+                weight gradients only for adapter prompts, gates, visual_proj, temporal_emb).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+I32 = torch.int32
+
+
+# ------------------------------------------------------------------------------------------------
+# batch -> flat device arrays
+# ------------------------------------------------------------------------------------------------
+class BatchPlan:
+    """Host-side (CPU) preparation of one batch. Everything the kernels need is packed into ONE
+    pinned int32 buffer (one H2D copy) plus the fp32 video features."""
+
+    def __init__(self, data: Dict, streams: List[str], max_feats: int, inference: bool = False):
+        F = max_feats
+        ids = {k: _cpu(data["text_id"][k]) for k in streams}
+        lab = {k: _cpu(data["label"][k]) for k in streams}
+        B, n_opt, S = ids[streams[0]].shape
+        self.B, self.n_opt, self.S, self.F = B, n_opt, S, F
+        self.streams = streams
+        per = B * n_opt                       # sequences per stream
+        self.n_seq = per * len(streams)
+        self.T = self.n_seq * S
+        self.n_video = B
+        ids_all = torch.cat([ids[k].reshape(per, S) for k in streams], 0).to(I32)
+        labels_all = torch.zeros(self.n_seq, S, dtype=I32)
+        vstart = torch.empty(self.n_seq, dtype=I32)
+        seq_video = (torch.arange(per) // n_opt).repeat(len(streams)).to(I32)
+        # the reference reads video_start of sample 0 only (`llama/model.py:264`)
+        for si, k in enumerate(streams):
+            vstart[si * per:(si + 1) * per] = -1 if k == "qav" else int(data["video_start"][k][0])
+        qav_index = torch.zeros(B, F, dtype=I32)
+        self.ce_counts: Dict[str, int] = {}
+        ce_rows, ce_tgt, ce_dst = [], [], []
+        self.q_count = 0
+        q_rows = q_tgt = q_vid = torch.zeros(0, dtype=I32)
+        for si, k in enumerate(streams):
+            l2 = lab[k].reshape(per, S)
+            if k == "qav":
+                labels_all[si * per:(si + 1) * per] = l2.to(I32)
+                qav_index = _cpu(data["video_index"]["qav"]).reshape(B, F).to(I32)
+                nz = (l2[:, 1:] >= 0).nonzero()                       # ignore_index=-1 (`model.py:235`)
+                q_rows = ((si * per + nz[:, 0]) * S + nz[:, 1]).to(I32)
+                q_tgt = l2[:, 1:][nz[:, 0], nz[:, 1]].to(I32)
+                q_vid = (nz[:, 0] // n_opt).to(I32)
+                self.q_count = int(nz.shape[0])
+            else:
+                nz = (l2[:, 1:] != 0).nonzero()                       # ignore_index=0 (`model.py:233-234`)
+                ce_rows.append(((si * per + nz[:, 0]) * S + nz[:, 1]).to(I32))
+                ce_tgt.append(l2[:, 1:][nz[:, 0], nz[:, 1]].to(I32))
+                ce_dst.append((nz[:, 0] * (S - 1) + nz[:, 1]).to(I32))   # index into [B, n_opt, S-1]
+                self.ce_counts[k] = int(nz.shape[0])
+        self.ce_total = sum(self.ce_counts.values())
+        ce_rows = torch.cat(ce_rows) if ce_rows else torch.zeros(0, dtype=I32)
+        ce_tgt = torch.cat(ce_tgt) if ce_tgt else torch.zeros(0, dtype=I32)
+        ce_dst = torch.cat(ce_dst) if ce_dst else torch.zeros(0, dtype=I32)
+        parts = [ids_all.flatten(), labels_all.flatten(), vstart, seq_video, qav_index.flatten(),
+                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid]
+        sizes = [p.numel() for p in parts]
+        total = sum(sizes)
+        host = torch.empty(max(total, 1), dtype=I32, pin_memory=torch.cuda.is_available())
+        off = 0
+        self._slices = []
+        for p, n in zip(parts, sizes):
+            host[off:off + n] = p
+            self._slices.append((off, n))
+            off += n
+        self.host_ints = host
+        video = _cpu(data["video"]).reshape(B * F, -1).float().contiguous()
+        self.host_video = video.pin_memory() if torch.cuda.is_available() else video
+        self.h2d_bytes = host.numel() * 4 + video.numel() * 4
+
+    def to_device(self, device):
+        dev = self.host_ints.to(device, non_blocking=True)
+        names = ["ids", "labels", "vstart", "seq_video", "qav_index", "ce_rows", "ce_tgt", "ce_dst", "q_rows", "q_tgt", "q_vid"]
+        for nm, (off, n) in zip(names, self._slices):
+            setattr(self, nm, dev[off:off + n])
+        self.video = self.host_video.to(device, non_blocking=True)
+        return self
+
+
+def _cpu(t):
+    return t.detach().cpu() if isinstance(t, torch.Tensor) else torch.as_tensor(t)
+
+
+# ------------------------------------------------------------------------------------------------
+# frozen weights in their B200 layout
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class LayerWeights:
+    wqkv: torch.Tensor      # [3d, d]   rows: Wq | Wk | Wv
+    wqkv_t: torch.Tensor    # [d, 3d]
+    wo: torch.Tensor        # [d, d]
+    wo_t: torch.Tensor
+    w13: torch.Tensor       # [2*hid, d] rows: W1 | W3
+    w13_t: torch.Tensor     # [d, 2*hid]
+    w2: torch.Tensor        # [d, hid]
+    w2_t: torch.Tensor      # [hid, d]
+    attn_norm: torch.Tensor
+    ffn_norm: torch.Tensor
+
+
+# ------------------------------------------------------------------------------------------------
+# the step
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SavedStep:
+    plan: BatchPlan
+    x: List[torch.Tensor] = field(default_factory=list)      # layer inputs  (L+1 entries; last = final hidden)
+    qkv: List[torch.Tensor] = field(default_factory=list)
+    akv: List[torch.Tensor] = field(default_factory=list)
+    o: List[torch.Tensor] = field(default_factory=list)
+    lse: List[torch.Tensor] = field(default_factory=list)
+    h: List[torch.Tensor] = field(default_factory=list)
+    g: List[torch.Tensor] = field(default_factory=list)
+    rstd1: List[torch.Tensor] = field(default_factory=list)
+    rstd2: List[torch.Tensor] = field(default_factory=list)
+    vf32: Optional[torch.Tensor] = None
+    ce: Optional[dict] = None
+    qav: Optional[dict] = None
+
+
+class StepEngine:
+    """Runs the kernels. Stateless w.r.t. parameters: callers pass the packed frozen weights and the
+    current trainable tensors each step."""
+
+    def __init__(self, dim, n_heads, hidden, vocab, adapter_len, max_feats, norm_eps, tau, max_seq_len, device):
+        self.d, self.H, self.hid, self.V = dim, n_heads, hidden, vocab
+        self.hd = dim // n_heads
+        self.A, self.F, self.eps, self.tau = adapter_len, max_feats, norm_eps, tau
+        self.device = device
+        # RoPE table `llama/model.py:45-50,245`: resident on the device (the reference re-uploads it every step)
+        inv = 1.0 / (10000.0 ** (torch.arange(0, self.hd, 2)[: self.hd // 2].float() / self.hd))
+        ang = torch.outer(torch.arange(max_seq_len * 2).float(), inv)
+        self.cos = torch.cos(ang).to(device).contiguous()
+        self.sin = torch.sin(ang).to(device).contiguous()
+        self._attn_ws = None
+
+    # -------------------------------------------------------------------------------- forward
+    def forward(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
+                gate1: List[torch.Tensor], gate2: List[torch.Tensor], save: bool, token_losses: bool = False):
+        """Returns (losses dict of 0-dim fp32 device tensors | per-token loss tensor, SavedStep|None)."""
+        d, H, hd, hid, A, F, S = self.d, self.H, self.hd, self.hid, self.A, self.F, plan.S
+        T, n_seq, dev = plan.T, plan.n_seq, self.device
+        sv = SavedStep(plan) if save else None
+        L = len(layers)
+        # --- inputs (`model.py:286-336`)
+        vf32 = ops.visual_proj_fwd(plan.video, visual_w)                           # [B*F, d] fp32
+        x = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w,
+                             n_seq, S, F)
+        adapter_bf16 = ops.f32_to_bf16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
+        xn = torch.empty(T, d, dtype=BF16, device=dev)
+        c = torch.empty(T, hid, dtype=BF16, device=dev)
+        qkv_b = o_b = g_b = None
+        for l, w in enumerate(layers):
+            _, rstd1 = ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
+            qkv = ops.gemm_nt(xn, w.wqkv, out=None if save else qkv_b)
+            akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])          # adapter K|V, no RoPE (`model.py:99-100`)
+            o, lse = ops.attn_fwd(qkv, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F,
+                                  out=None if save else o_b)
+            h = ops.gemm_nt(o, w.wo, residual=x)                                   # h = x + attn  (`model.py:185`)
+            _, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
+            g = ops.gemm_nt(xn, w.w13, out=None if save else g_b)
+            ops.swiglu_fwd(g, c)
+            x_next = ops.gemm_nt(c, w.w2, residual=h)                              # out = h + ffn (`model.py:186`)
+            if save:
+                sv.x.append(x); sv.qkv.append(qkv); sv.akv.append(akv); sv.o.append(o); sv.lse.append(lse)
+                sv.h.append(h); sv.g.append(g); sv.rstd1.append(rstd1); sv.rstd2.append(rstd2)
+            else:
+                qkv_b, o_b, g_b = qkv, o, g
+            x = x_next
+        if save:
+            sv.x.append(x)
+            sv.vf32 = vf32
+        # --- heads
+        losses = {}
+        if plan.ce_total > 0:
+            hn, rstd = ops.rmsnorm_gather_fwd(x, plan.ce_rows, norm_w, self.eps)     # final norm on labelled rows only
+            logits = ops.gemm_nt(hn, out_w, out_fp32=True)                          # [rows, V] fp32, never [B*S, V]
+            row_loss, row_lse = ops.ce_fwd(logits, plan.ce_tgt)
+            if token_losses:
+                tl = torch.zeros(plan.B * plan.n_opt * (S - 1), dtype=torch.float32, device=dev)
+                ops.scatter_rows(row_loss, plan.ce_dst, tl)
+                return tl.view(plan.B, plan.n_opt, S - 1), None
+            off = 0
+            for k in plan.streams:
+                if k == "qav":
+                    continue
+                n = plan.ce_counts[k]
+                out = torch.empty((), dtype=torch.float32, device=dev)
+                if n > 0:
+                    ops.sum_scale(row_loss[off:off + n], n, 1.0 / n, out)           # mean over ALL labelled tokens of the batch
+                else:
+                    out.fill_(float("nan"))
+                losses[k] = out
+                off += n
+            if save:
+                sv.ce = dict(hn=hn, rstd=rstd, logits=logits, row_lse=row_lse)
+        else:
+            if token_losses:
+                return torch.zeros(plan.B, plan.n_opt, S - 1, dtype=torch.float32, device=dev), None
+            for k in plan.streams:
+                if k != "qav":
+                    losses[k] = torch.full((), float("nan"), dtype=torch.float32, device=dev)
+        if "qav" in plan.streams:
+            out = torch.empty((), dtype=torch.float32, device=dev)
+            if plan.q_count > 0:
+                hnq, rstdq = ops.rmsnorm_gather_fwd(x, plan.q_rows, norm_w, self.eps)
+                row_loss, prob = ops.qav_loss_fwd(hnq, vf32, plan.q_vid, plan.q_tgt, self.tau, F)
+                ops.sum_scale(row_loss, plan.q_count, 1.0 / plan.q_count, out)
+                if save:
+                    sv.qav = dict(hn=hnq, rstd=rstdq, prob=prob)
+            else:
+                out.fill_(float("nan"))
+            losses["qav"] = out
+        return losses, sv
+
+    # -------------------------------------------------------------------------------- backward
+    def backward(self, sv: SavedStep, gscale: torch.Tensor, layers: List[LayerWeights], out_w_t, norm_w, gate1, gate2,
+                 grads: "GradBuffers", on_layer_done=None):
+        """gscale: fp32 device tensor [3] = upstream gradients of (vqa, vaq, qav) losses.
+        Fills `grads` (fp32): adapter [L*A, d], gate1/gate2 [L, H], visual [d, vdim], temporal [F, d]."""
+        plan = sv.plan
+        d, H, hd, hid, A, F, S = self.d, self.H, self.hd, self.hid, self.A, self.F, plan.S
+        T, n_seq, dev = plan.T, plan.n_seq, self.device
+        L = len(layers)
+        x_final = sv.x[L]
+        dx = torch.zeros(T, d, dtype=BF16, device=dev)
+        gidx = {"vqa": 0, "vaq": 1, "qav": 2}
+        # --- heads backward
+        if sv.ce is not None:
+            ce = sv.ce
+            dlogits = torch.empty(plan.ce_total, self.V, dtype=BF16, device=dev)
+            off = 0
+            for k in plan.streams:
+                if k == "qav":
+                    continue
+                n = plan.ce_counts[k]
+                if n > 0:
+                    ops.ce_bwd(ce["logits"][off:off + n], plan.ce_tgt[off:off + n], ce["row_lse"][off:off + n],
+                               gscale[gidx[k]:gidx[k] + 1], 1.0 / n, dlogits=dlogits[off:off + n])
+                off += n
+            dhn = ops.gemm_nt(dlogits, out_w_t)                                     # dH = dlogits . W_out
+            ops.rmsnorm_scatter_bwd(dhn, x_final, plan.ce_rows, norm_w, ce["rstd"], dx)
+        dvf_qav = None
+        if sv.qav is not None:
+            q = sv.qav
+            dhnq, dvf_qav = ops.qav_loss_bwd(q["hn"], sv.vf32, plan.q_vid, plan.q_tgt, q["prob"], gscale[2:3],
+                                             1.0 / plan.q_count, self.tau, plan.n_video, F)
+            ops.rmsnorm_scatter_bwd(dhnq, x_final, plan.q_rows, norm_w, q["rstd"], dx)
+        # --- layers, last to first
+        if self._attn_ws is None or self._attn_ws.numel() < ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A):
+            self._attn_ws = torch.empty(ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
+        dc = torch.empty(T, hid, dtype=BF16, device=dev)
+        dg = torch.empty(T, 2 * hid, dtype=BF16, device=dev)
+        dtmp = torch.empty(T, d, dtype=BF16, device=dev)
+        dh = torch.empty(T, d, dtype=BF16, device=dev)
+        dqkv = torch.empty(T, 3 * d, dtype=BF16, device=dev)
+        dakv = torch.empty(A, 2 * d, dtype=torch.float32, device=dev)
+        dakv_bf = torch.empty(A, 2 * d, dtype=BF16, device=dev)
+        dx_next = torch.empty(T, d, dtype=BF16, device=dev)
+        for l in range(L - 1, -1, -1):
+            w = layers[l]
+            ops.gemm_nt(dx, w.w2_t, out=dc)                                        # d(silu(a)*b) = dout . W2
+            ops.swiglu_bwd(dc, sv.g[l], dg)
+            ops.gemm_nt(dg, w.w13_t, out=dtmp)                                     # d(ffn_norm out) = [da|db] . [W1;W3]
+            ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh)
+            ops.gemm_nt(dh, w.wo_t, out=dtmp)                                      # d(attn out) = dh . Wo
+            ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dtmp,
+                         n_seq, S, H, hd, A, F, dqkv=dqkv, dakv=dakv, dgate1=grads.gate1[l], dgate2=grads.gate2[l], ws=self._attn_ws)
+            ops.gemm_nt(dqkv, w.wqkv_t, out=dtmp)                                  # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
+            ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next)
+            # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l)
+            ops.f32_to_bf16(dakv, dakv_bf)
+            ops.gemm_nt(dakv_bf, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
+            dx, dx_next = dx_next, dx
+            if on_layer_done is not None:
+                on_layer_done(l)
+        # --- input side (`model.py:322-336` backward)
+        dvf = ops.build_h0_bwd(dx, plan.vstart, plan.seq_video, plan.qav_index, n_seq, plan.n_video, S, F)
+        ops.video_grad_finish(dvf, dvf_qav, plan.n_video, F, dtemporal=grads.temporal)
+        ops.visual_proj_bwd(dvf, plan.video, dwv=grads.visual)
+        return grads
+
+
+class GradBuffers:
+    """One flat fp32 buffer for every trainable gradient, laid out so that the part that is final
+    early in backward (adapter prompts, last layer first) is contiguous and the late part
+    (gates, visual_proj, temporal_emb) is one contiguous tail -> few, large all-reduce messages."""
+
+    def __init__(self, n_layers_run: int, A: int, d: int, H: int, vdim: int, F: int, device):
+        self.sizes = dict(adapter=n_layers_run * A * d, gate1=n_layers_run * H, gate2=n_layers_run * H, visual=d * vdim, temporal=F * d)
+        total = sum(self.sizes.values())
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        off = 0
+        self.offsets = {}
+        for k, n in self.sizes.items():
+            self.offsets[k] = off
+            off += n
+        v = lambda k: self.flat[self.offsets[k]:self.offsets[k] + self.sizes[k]]
+        self.adapter = v("adapter").view(n_layers_run * A, d)
+        self.gate1 = v("gate1").view(n_layers_run, H)
+        self.gate2 = v("gate2").view(n_layers_run, H)
+        self.visual = v("visual").view(d, vdim)
+        self.temporal = v("temporal").view(F, d)
+        self.late_offset = self.offsets["gate1"]

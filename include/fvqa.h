@@ -81,8 +81,8 @@ int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const 
                   void* stream);
 /* Backward. dqkv [n_seq*S, 3*H*hd] bf16 receives dq|dk|dv with the inverse RoPE already applied.
  * Per-CTA partials of the shared-parameter gradients go to `ws` (size from fvqa_attn_bwd_ws_bytes)
- * and are reduced deterministically into dakv [A, 2*H*hd] fp32 (dK_a | dV_a), dgate1[H], dgate2[H]
- * (fp32; ACCUMULATED into, so the caller zero-initialises per step / layer as needed). */
+ * and are reduced in a fixed order into dakv [A, 2*H*hd] fp32 (dK_a | dV_a), dgate1[H], dgate2[H]
+ * (fp32, overwritten). */
 int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A);
 int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos,
                   const float* rope_sin, const float* gate1, const float* gate2, const int32_t* vstart,
@@ -93,7 +93,7 @@ int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const 
 /* ---- input embedding + video injection (llama/model.py:286-336). ---------------------------------
  * vproj: vf32[B*F, d] = video[B*F, vdim] * Wv[d, vdim]^T in fp32 (model.py:322). */
 int fvqa_visual_proj_fwd(const float* video, const float* wv, float* vf32, int rows, int dim, int vdim, void* stream);
-/* dWv[d, vdim] += dvf[rows, d]^T * video[rows, vdim] (fp32, accumulated). */
+/* dWv[d, vdim] = dvf[rows, d]^T * video[rows, vdim] (fp32, overwritten). */
 int fvqa_visual_proj_bwd(const float* dvf, const float* video, float* dwv, int rows, int dim, int vdim, void* stream);
 /* h0[n*S+p, :] for every sequence n:
  *   mode vstart[n] >= 0 (VQA/VAQ): tok_emb[ids] except positions [vs, vs+F) <- bf16(vf32[vid[n],f] + temporal[f])
@@ -107,7 +107,7 @@ int fvqa_build_h0_fwd(const fvqa_bf16* tok_emb, const int32_t* ids, const int32_
 int fvqa_build_h0_bwd(const fvqa_bf16* dh0, const int32_t* vstart, const int32_t* seq_video,
                       const int32_t* qav_index, float* dvf, int n_seq, int n_video, int S, int dim,
                       int max_feats, void* stream);
-/* dtemporal[F, d] += sum_b dvf[b]; dvf_total[b] = dvf[b] + dvf_qav[b] (in place into dvf). */
+/* dtemporal[F, d] = sum_b dvf[b] (overwritten); then dvf[b] += dvf_qav[b] in place (dvf_qav may be NULL). */
 int fvqa_video_grad_finish(float* dvf, const float* dvf_qav, float* dtemporal, int n_video, int dim,
                            int max_feats, void* stream);
 
@@ -143,10 +143,6 @@ int fvqa_option_score(const float* token_loss, int32_t* prediction, float* mean_
 
 /* ---- small utilities --------------------------------------------------------------------------- */
 int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, void* stream);
-/* dst[rows, cols] (fp32) += a[rows, K] * bT[cols, K]^T where a is fp32 and bT is bf16 (K-contiguous):
- * used for d adapter = dK_a * Wk + dV_a * Wv with the transposed frozen weights. */
-int fvqa_small_gemm_f32_bf16(const float* a, int lda, const fvqa_bf16* bT, int ldb, float* dst, int ldd,
-                             int rows, int cols, int K, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,123 @@
+"""CPU: host-side logic of the drop-in boundary — parameter names / freeze rule, batch planning,
+LR schedule, gradient-bucket layout. No kernels are launched."""
+import math
+
+import pytest
+import torch
+
+from tests.util_parity import GOLDEN, golden_inputs, make_args
+
+
+def _model():
+    from flipped_vqa_b200.llama import ModelArgs, SyntheticTokenizer, Transformer
+    return Transformer(ModelArgs(**GOLDEN), make_args(), tokenizer=SyntheticTokenizer(GOLDEN["vocab_size"]), device="cpu")
+
+
+def test_parameter_names_match_reference_state_dict():
+    m = _model()
+    names = dict(m.named_parameters())
+    d, hid = GOLDEN["dim"], 384
+    expect = {"tok_embeddings.weight": (256, d), "output.weight": (256, d), "norm.weight": (d,),
+              "adapter_query.weight": (GOLDEN["adapter_len"] * GOLDEN["adapter_layer"], d),
+              "visual_proj.weight": (d, 768), "temporal_emb.weight": (10, d)}
+    for i in range(GOLDEN["n_layers"]):
+        p = f"layers.{i}."
+        for w in ("wq", "wk", "wv", "wo"):
+            expect[p + f"attention.{w}.weight"] = (d, d)
+        expect[p + "attention.gate1"] = (1, 2, 1, 1)
+        expect[p + "attention.gate2"] = (1, 2, 1, 1)
+        expect[p + "feed_forward.w1.weight"] = (hid, d)
+        expect[p + "feed_forward.w2.weight"] = (d, hid)
+        expect[p + "feed_forward.w3.weight"] = (hid, d)
+        expect[p + "attention_norm.weight"] = (d,)
+        expect[p + "ffn_norm.weight"] = (d,)
+    assert set(names) == set(expect)
+    for n, s in expect.items():
+        assert tuple(names[n].shape) == s, n
+    assert set(m.state_dict()) == set(expect)
+
+
+def test_freeze_rule_matches_llama_vqa():
+    """llama_vqa.py:71-76: trainable <=> name contains gate/adapter/temporal_emb/visual_proj, fp32; rest frozen."""
+    m = _model()
+    for n, p in m.named_parameters():
+        trainable = any(s in n for s in ("gate", "adapter", "temporal_emb", "visual_proj"))
+        assert p.requires_grad == trainable, n
+        assert p.dtype == (torch.float32 if trainable else torch.bfloat16), n
+    assert float(m.layers[0].attention.gate1.abs().sum()) == 0.0                       # zero-init (model.py:84)
+    assert torch.allclose(m.layers[0].attention.gate2, torch.full((1, 2, 1, 1), -3.5))  # -bias (model.py:85)
+
+
+def test_load_state_dict_fills_packed_views():
+    from flipped_vqa_b200.synthetic import synthetic_state_dict
+    from types import SimpleNamespace
+    m = _model()
+    sd = synthetic_state_dict(SimpleNamespace(**GOLDEN), seed=1)
+    m.load_state_dict(sd)
+    d = GOLDEN["dim"]
+    blk = m.layers[1]
+    assert torch.equal(blk._wqkv[d:2 * d].float(), sd["layers.1.attention.wk.weight"])
+    assert torch.equal(blk._w13[384:].float(), sd["layers.1.feed_forward.w3.weight"])
+    assert m._pack_token is None            # transposed copies are rebuilt lazily on the next forward
+
+
+def test_audio_variants_are_rejected():
+    from flipped_vqa_b200.llama import ModelArgs, SyntheticTokenizer, Transformer
+    a = make_args()
+    a.audio = True
+    with pytest.raises(NotImplementedError):
+        Transformer(ModelArgs(**GOLDEN), a, tokenizer=SyntheticTokenizer(256), device="cpu")
+
+
+def test_batch_plan_rows_and_targets():
+    from flipped_vqa_b200.step import BatchPlan
+    params, sd, data = golden_inputs()
+    plan = BatchPlan(data, ["vqa", "vaq", "qav"], 10)
+    B, S = 3, 48
+    assert (plan.n_seq, plan.T) == (9, 9 * S)
+    names = ["ids", "labels", "vstart", "seq_video", "qav_index", "ce_rows", "ce_tgt", "ce_dst", "q_rows", "q_tgt", "q_vid"]
+    arr = {n: plan.host_ints[o:o + k] for n, (o, k) in zip(names, plan._slices)}
+    assert arr["vstart"].tolist() == [12] * 6 + [-1] * 3
+    assert arr["seq_video"].tolist() == [0, 1, 2] * 3
+    # labelled rows: position p predicts label[p+1] (model.py:278 shift), ignore_index 0
+    lab = data["label"]["vqa"].reshape(B, S)
+    n_vqa = int((lab[:, 1:] != 0).sum())
+    assert plan.ce_counts["vqa"] == n_vqa == 12
+    rows = arr["ce_rows"][:n_vqa].long()
+    assert torch.equal(arr["ce_tgt"][:n_vqa].long(), lab.flatten()[rows + 1])
+    # QAV rows precede each video slot; targets 0..F-1; ignore_index -1
+    assert plan.q_count == 30
+    assert arr["q_tgt"].tolist() == list(range(10)) * 3
+    ql = data["label"]["qav"].reshape(B, S)
+    qrows = arr["q_rows"].long() - 6 * S
+    assert torch.equal(ql.flatten()[qrows + 1], arr["q_tgt"].long())
+
+
+def test_batch_plan_option_layout():
+    from flipped_vqa_b200.step import BatchPlan
+    params, sd, data = golden_inputs(5)
+    plan = BatchPlan(data, ["vqa"], 10, inference=True)
+    assert plan.n_seq == 15 and plan.n_opt == 5
+    names = ["ids", "labels", "vstart", "seq_video"]
+    arr = {n: plan.host_ints[o:o + k] for n, (o, k) in zip(names, plan._slices)}
+    assert arr["seq_video"].tolist() == [0] * 5 + [1] * 5 + [2] * 5      # video repeated per option (model_my_original_mod.py:332-333)
+
+
+def test_lr_schedule_matches_reference_formula():
+    from flipped_vqa_b200.util import lr_sched
+    from types import SimpleNamespace
+    opt = SimpleNamespace(param_groups=[{"lr": 0.0}, {"lr": 0.0, "lr_scale": 0.5}])
+    a = SimpleNamespace(lr=0.09, min_lr=0.0, warmup_epochs=2, epochs=5)
+    assert lr_sched.adjust_learning_rate(opt, 1.0, a) == pytest.approx(0.045)
+    assert opt.param_groups[1]["lr"] == pytest.approx(0.0225)
+    lr = lr_sched.adjust_learning_rate(opt, 3.5, a)
+    assert lr == pytest.approx(0.09 * 0.5 * (1 + math.cos(math.pi * 1.5 / 3)))
+
+
+def test_grad_buffer_layout():
+    from flipped_vqa_b200.step import GradBuffers
+    gb = GradBuffers(32, 10, 4096, 32, 768, 10, "cpu")
+    assert gb.flat.numel() == 4499456             # 7B trainables = 4 499 456 fp32 = 18.0 MB
+    assert gb.late_offset == 32 * 10 * 4096
+    gb.adapter[5, 7] = 3.0
+    assert float(gb.flat[5 * 4096 + 7]) == 3.0

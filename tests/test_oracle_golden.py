@@ -1,0 +1,64 @@
+"""CPU: the oracle (oracle/llama_vqa_oracle.py) against the golden vectors produced by running the
+UNMODIFIED reference (oracle/make_golden.py -> tests/golden/*.npz). fp32 vs fp32: tight tolerances."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import llama_vqa_oracle as O
+from tests.util_parity import GOLDEN_DIR, GOLDEN_RUN, golden_inputs, rel_l2
+
+
+def test_oracle_training_step_matches_reference():
+    g = np.load(os.path.join(GOLDEN_DIR, "train_small.npz"))
+    params, sd, data = golden_inputs()
+    st = O.prepare_state(sd)
+    losses = O.forward_losses(st, params, data, max_feats=GOLDEN_RUN["max_feats"], tau=GOLDEN_RUN["tau"])
+    sum(losses).backward()
+    np.testing.assert_allclose([float(l.detach()) for l in losses], g["gold/loss"], rtol=2e-6)
+    n = 0
+    for key in g.files:
+        if key.startswith("gold/grad/"):
+            name = key[len("gold/grad/"):]
+            assert rel_l2(st[name].grad, g[key]) < 1e-5, name
+            n += 1
+    assert n == 7
+    # skipped leading layer (adapter_layer < n_layers, model.py:338): no gradient in the reference either
+    assert st["layers.0.attention.gate1"].grad is None and "gold/grad/layers.0.attention.gate1" not in g.files
+
+
+def test_reference_fp16_distance_from_gold_is_within_stated_tolerances():
+    """Attribution aid: the reference's own fp16 run sits well inside the parity tolerances."""
+    g = np.load(os.path.join(GOLDEN_DIR, "train_small.npz"))
+    assert np.all(np.abs(g["fp16/loss"] - g["gold/loss"]) / g["gold/loss"] < 1e-2)
+    for key in g.files:
+        if key.startswith("gold/grad/"):
+            assert rel_l2(g["fp16/" + key[5:]], g[key]) < 2e-2, key
+
+
+def test_oracle_option_scoring_matches_reference():
+    g = np.load(os.path.join(GOLDEN_DIR, "options_small.npz"))
+    params, sd, data = golden_inputs(5)
+    st = O.prepare_state(sd, requires_grad=False)
+    with torch.no_grad():
+        tok = O.option_token_losses(st, params, data, max_feats=GOLDEN_RUN["max_feats"])
+    np.testing.assert_allclose(tok.numpy(), g["gold/token_losses"], atol=2e-5)
+    assert O.option_predict(tok).tolist() == g["gold/prediction"].tolist()
+
+
+def test_oracle_without_vaq_qav_returns_zero_placeholders():
+    params, sd, data = golden_inputs()
+    st = O.prepare_state(sd, requires_grad=False)
+    vqa, vaq, qav = O.forward_losses(st, params, data, vaq=False, qav=False)
+    assert vaq.tolist() == [0] and qav.tolist() == [0] and float(vqa) > 0
+
+
+def test_hash_weights_are_reproducible():
+    from flipped_vqa_b200.synthetic import hash_normal
+    t = hash_normal((4, 5), seed=123, std=0.02)
+    assert t.shape == (4, 5)
+    # pinned values: integer hashing only, must never change across platforms / versions
+    assert torch.equal(t, hash_normal((4, 5), seed=123, std=0.02))
+    assert abs(float(hash_normal((200000,), seed=1).std()) - 1.0) < 0.01
+    assert torch.equal(t, t.to(torch.bfloat16).float())           # bf16-representable
+    assert torch.equal(t, t.to(torch.float16).float())            # and fp16-representable
