@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the LLaMA-VQA training step (BASELINE.json metric: 7B NExT-QA train samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 7b-nextqa] [--impl ours|reference]
+
+One JSON line on stdout (rank 0). A "step" = forward + hand-written backward + gradient all-reduce
+(N>1) + AdamW update on the trainables, on a synthetic NExT-QA-shaped batch (B=8, S=128, F=10,
+--vaq --qav) with random-init LLaMA-7B-shaped weights.
+  value : whole-job samples/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e   : same metric through the public API `model(data)` with HOST batch tensors: host planning,
+          pinned H2D copy and a D2H read of the loss inside the timed region
+  roofline     : tcgen05 GEMM launches sampled with CUDA events inside the timed region
+  cpu_baseline : the oracle (CPU port of the reference's step) on a bounded 7B-shaped slice
+`--impl reference` times that CPU port with all host threads (the reference itself is pure PyTorch
+and /root/reference does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    "7b-nextqa": dict(dim=4096, n_layers=32, n_heads=32, vocab_size=32000, multiple_of=256, adapter_layer=32, bsz=8, seqlen=128),
+    "7b-dramaqa": dict(dim=4096, n_layers=32, n_heads=32, vocab_size=32000, multiple_of=256, adapter_layer=32, bsz=2, seqlen=384),
+    "7b-tvqa": dict(dim=4096, n_layers=32, n_heads=32, vocab_size=32000, multiple_of=256, adapter_layer=32, bsz=1, seqlen=650),
+    "13b-nextqa": dict(dim=5120, n_layers=40, n_heads=40, vocab_size=32000, multiple_of=256, adapter_layer=40, bsz=8, seqlen=128),
+    "tiny": dict(dim=256, n_layers=4, n_heads=4, vocab_size=512, multiple_of=256, adapter_layer=4, bsz=8, seqlen=128),
+}
+WORKLOAD_NAMES = {
+    "7b-nextqa": "LLaMA-7B NExT-QA-shaped max_seq_len=128 bs=8 max_feats=10 --vaq --qav",
+    "7b-dramaqa": "LLaMA-7B DramaQA-shaped max_seq_len=384 bs=2 --vaq --qav",
+    "7b-tvqa": "LLaMA-7B TVQA-shaped max_seq_len=650 bs=1 --sub --vaq --qav",
+    "13b-nextqa": "LLaMA-13B NExT-QA-shaped max_seq_len=128 bs=8 --vaq --qav adapter_layer=40",
+    "tiny": "tiny random-init LLaMA-VQA dim=256 4 layers",
+}
+MAX_FEATS, ADAPTER_LEN, BIAS, TAU = 10, 10, 3.5, 100.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")   # B200_PROFILING.md
+
+
+def flops_per_step(cfg, n_labelled):
+    """F_step = 3*(2*body + 3.5*attn) + 2*sum(head) + small; heads counted on the
+    labelled rows actually evaluated (never count work not done)."""
+    d, L, V, B, S = cfg["dim"], cfg["adapter_layer"], cfg["vocab_size"], cfg["bsz"], cfg["seqlen"]
+    from flipped_vqa_b200.synthetic import ffn_hidden_dim
+    hid = ffn_hidden_dim(d, cfg["multiple_of"])
+    T = B * S
+    body = L * 2 * T * (4 * d * d + 3 * d * hid)
+    attn = L * 4 * B * d * (S * (S + 1) / 2 + S * ADAPTER_LEN)
+    head = 2 * n_labelled * d * V
+    small = L * 2 * ADAPTER_LEN * 2 * d * d + 2 * B * MAX_FEATS * 768 * d
+    return 3 * (2 * body + 3.5 * attn) + 2 * head + small
+
+
+def make_args():
+    return argparse.Namespace(max_feats=MAX_FEATS, bias=BIAS, tau=TAU, llama_model_path="x/", audio=False, audio_only=False,
+                              audio_merge="none", debug=False, vaq=True, qav=True, is_generation_task=False)
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_slice_seconds(cfg, n_layers, bsz, threads):
+    """fwd+bwd of the ORACLE (CPU port of the reference's step, fp32) on a 7B-shaped slice with
+    `n_layers` layers and batch `bsz`."""
+    from oracle import llama_vqa_oracle as O
+    from flipped_vqa_b200.synthetic import ffn_hidden_dim, synthetic_batch
+    torch.set_num_threads(threads)
+    d, V, H, S = cfg["dim"], cfg["vocab_size"], cfg["n_heads"], cfg["seqlen"]
+    hid = ffn_hidden_dim(d, cfg["multiple_of"])
+    g = torch.Generator().manual_seed(0)
+    r = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    sd = {"tok_embeddings.weight": r(V, d), "output.weight": r(V, d), "norm.weight": torch.ones(d),
+          "adapter_query.weight": r(ADAPTER_LEN * n_layers, d, std=1.0), "visual_proj.weight": r(d, 768, std=0.03),
+          "temporal_emb.weight": r(MAX_FEATS, d, std=1.0)}
+    for i in range(n_layers):
+        p = f"layers.{i}."
+        for nm in ("wq", "wk", "wv", "wo"):
+            sd[p + f"attention.{nm}.weight"] = r(d, d)
+        sd[p + "feed_forward.w1.weight"] = r(hid, d)
+        sd[p + "feed_forward.w2.weight"] = r(d, hid)
+        sd[p + "feed_forward.w3.weight"] = r(hid, d)
+        sd[p + "attention_norm.weight"] = torch.ones(d)
+        sd[p + "ffn_norm.weight"] = torch.ones(d)
+        sd[p + "attention.gate1"] = r(1, H, 1, 1, std=0.5)
+        sd[p + "attention.gate2"] = torch.full((1, H, 1, 1), -BIAS)
+    params = SimpleNamespace(dim=d, n_layers=n_layers, n_heads=H, vocab_size=V, norm_eps=1e-6, max_seq_len=S,
+                             adapter_len=ADAPTER_LEN, adapter_layer=n_layers)
+    st = O.prepare_state(sd)
+    data = synthetic_batch(bsz, S, V, max_feats=MAX_FEATS, seed=1)
+    t0 = time.perf_counter()
+    losses = O.forward_losses(st, params, data, max_feats=MAX_FEATS, tau=TAU)
+    sum(losses).backward()
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, budget_s=25.0):
+    """Bounded CPU sample: 1-layer and 2-layer 7B-shaped slices -> per-layer and fixed cost ->
+    extrapolated full-depth step time (clearly labelled)."""
+    threads = os.cpu_count() or 1
+    B = cfg["bsz"]
+    t1 = cpu_slice_seconds(cfg, 1, B, threads)
+    if t1 * 3 > budget_s:          # too slow for a second, deeper slice: single-slice estimate
+        t_layer, t_fixed, how = t1, 0.0, "1-layer slice x L (upper bound: head counted per layer)"
+    else:
+        t2 = cpu_slice_seconds(cfg, 2, B, threads)
+        t_layer = max(t2 - t1, 1e-6)
+        t_fixed = max(t1 - t_layer, 0.0)
+        how = "1- and 2-layer slices -> fixed + L x per-layer"
+    L = cfg["adapter_layer"]
+    t_full = t_fixed + L * t_layer
+    return dict(value=B / t_full, unit="samples/s", cores=threads, kind="port",
+                sample=f"oracle fp32 fwd+bwd, {WORKLOAD_NAMES.get(cfg['name'], cfg['name'])} shapes, {how}; extrapolated to {L} layers "
+                       f"(t_layer={t_layer:.2f}s t_fixed={t_fixed:.2f}s)")
+
+
+def run_reference_arm(a):
+    """`--impl reference`: the reference's step is pure PyTorch with no native path; on this box it is
+    represented by the oracle port on the host cores (bounded 1-layer 7B-shaped slice per step)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(CONFIGS[a.config], name=a.config)
+    threads = os.cpu_count() or 1
+    B, L = cfg["bsz"], cfg["adapter_layer"]
+    t1 = cpu_slice_seconds(cfg, 1, B, threads)                      # also serves as warm-up
+    Bs = B
+    while Bs > 1 and (a.steps + a.warmup) * t1 * Bs / B > 150.0:    # keep the whole arm within minutes
+        Bs //= 2
+    if t1 * 3 < 40.0:
+        t2 = cpu_slice_seconds(cfg, 2, B, threads)
+        t_layer0 = max(t2 - t1, 1e-6)
+        fixed_frac = max(t1 - t_layer0, 0.0) / t1
+    else:
+        fixed_frac = 0.0
+    for _ in range(max(a.warmup - 1, 0)):
+        cpu_slice_seconds(cfg, 1, Bs, threads)
+    times = [cpu_slice_seconds(cfg, 1, Bs, threads) for _ in range(a.steps)]
+    t = sum(times) / len(times)
+    t_fixed = fixed_frac * t
+    t_full = t_fixed + L * (t - t_fixed)
+    value = Bs / t_full
+    line = {"impl": "reference", "metric": "7B NExT-QA train samples/s" if a.config == "7b-nextqa" else f"{a.config} train samples/s",
+            "value": value, "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t_full * 1e3 * (B / Bs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD_NAMES[a.config]},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                             "sample": f"oracle (CPU port of llama/model.py step) fp32 fwd+bwd; each timed step = 1-layer 7B-shaped slice at "
+                                       f"batch {Bs}; extrapolated: fixed {fixed_frac:.2f} of slice + {L} x per-layer"},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="7b-nextqa", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-layers", type=int, default=2, help="layers whose GEMM launches are event-timed inside the timed region")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+
+    import torch.distributed as dist
+    from flipped_vqa_b200 import ops
+    from flipped_vqa_b200.dp import DataParallel
+    from flipped_vqa_b200.llama import ModelArgs, SyntheticTokenizer, Transformer
+    from flipped_vqa_b200.synthetic import synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(CONFIGS[a.config], name=a.config)
+    B, S = cfg["bsz"], cfg["seqlen"]
+
+    torch.manual_seed(0)                                       # same frozen base on every rank
+    params = ModelArgs(dim=cfg["dim"], n_layers=cfg["n_layers"], n_heads=cfg["n_heads"], vocab_size=cfg["vocab_size"],
+                       multiple_of=cfg["multiple_of"], norm_eps=1e-6, max_batch_size=32, max_seq_len=S,
+                       adapter_len=ADAPTER_LEN, adapter_layer=cfg["adapter_layer"])
+    model = Transformer(params, make_args(), tokenizer=SyntheticTokenizer(cfg["vocab_size"]), device=dev)
+    with torch.no_grad():                                      # zero-init gate1 would make every adapter gradient 0
+        for blk in model.layers:
+            blk.attention.gate1.normal_(0, 0.5)
+    model.repack()
+    net = DataParallel(model) if world > 1 else model
+    trainables = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(trainables, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+
+    batches = [synthetic_batch(B, S, cfg["vocab_size"], max_feats=MAX_FEATS, seed=1000 * rank + i) for i in range(4)]
+    plans = [model.plan_batch(b) for b in batches]
+    torch.cuda.synchronize()
+    n_lab = sum(p.ce_total for p in plans) / len(plans)
+    step_flops = flops_per_step(cfg, n_lab)
+
+    def step_resident(i):
+        vqa, vaq, qav = net.forward_plan(plans[i % len(plans)])
+        (vqa + vaq + qav).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+
+    def step_e2e(i):
+        vqa, vaq, qav = net(batches[i % len(batches)])
+        loss = vqa + vaq + qav
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item()                                      # D2H read of the step's result
+
+    def timed(fn, steps, sample_gemm=False):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        if sample_gemm:
+            ops.GEMM_TIMER = ops.GemmTimer()
+        launches0 = ops.LAUNCHES
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        launches = ops.LAUNCHES - launches0
+        clocks = sampler.stop()
+        timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks, (timer.summary() if timer is not None else None)
+
+    L = cfg["adapter_layer"]
+    model._engine.sample_layers = tuple(sorted({0, L - 1} if a.sample_layers >= 2 else {L - 1})) if a.sample_layers > 0 else ()
+    for i in range(a.warmup):
+        step_resident(i)
+    ms, launches, clocks, gemm = timed(step_resident, a.steps, sample_gemm=a.sample_layers > 0)
+    ms_per_step = ms / a.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e, _, clocks_e, _ = timed(step_e2e, a.steps)
+    e2e_value = world * B / (ms_e / a.steps * 1e-3)
+
+    peaks = measured_peaks()
+    if rank == 0:
+        line = {
+            "metric": "7B NExT-QA train samples/s" if a.config == "7b-nextqa" else f"{a.config} train samples/s",
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[a.config], "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}",
+                       "l2": "working set (2 x 13.5 GB frozen weights + 9 GB saved activations per step) >> 126 MB L2; no explicit flush",
+                       "objectives": "vqa+vaq+qav", "optimizer": "AdamW(fused) on 4.5M trainables", "flops_per_step": step_flops,
+                       "labelled_rows_per_step": n_lab},
+            "tensor_util": {"value": step_flops / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops"],
+                            "achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12, "peak_tflops": peaks["bf16_tflops"],
+                            "peak_sustained_tflops": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": plans[0].h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e / a.steps, "clocks": clocks_e},
+            "gpu_launches": launches,
+        }
+        if gemm is not None:
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_nt_kernel (tcgen05)", "achieved": gemm["tflops"],
+                                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm["tflops"] / peaks["bf16_tflops_sustained"],
+                                "frac_of_burst_peak": gemm["tflops"] / peaks["bf16_tflops"], "peak_kind": f"{peaks['source']} sustained (kernel timed inside a long step)",
+                                "traffic": None, "launches_sampled": gemm["launches"], "avg_launch_ms": gemm["avg_ms"],
+                                "avg_flops_per_launch": gemm["avg_flops"], "sampled_layers": list(model._engine.sample_layers),
+                                "gemm_share_of_step": None}
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(cfg)
+            except Exception as e:  # the baseline is informative; never lose the GPU numbers over it
+                line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

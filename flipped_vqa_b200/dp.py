@@ -1,0 +1,84 @@
+"""Data-parallel training across the GPUs of one box (replaces `train.py:115-117` DDP + the implicit
+reducer all-reduce).
+
+The batch shards by sample, every rank holds the frozen base, and the ONLY exchange is the all-reduce
+(mean) of the trainable gradients: 4 499 456 fp32 = 18 MB for 7B. `GradSync` issues it from inside
+the hand-written backward, on NCCL's stream, overlapped with the remaining layers:
+  * adapter-prompt gradient rows become final layer by layer (last layer first) -> reduced in chunks
+    of `chunk_layers` layers while backward continues;
+  * gates + visual_proj + temporal_emb are one contiguous tail of the flat buffer, final only after
+    layer 0 -> one message at the end.
+Like the reference's DDP (no `no_sync()` under accum_iter, `engine.py:37-41`) the reduce runs on every
+micro-step; averaging per micro-step then accumulating equals accumulating then averaging.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradSync:
+    def __init__(self, grad_buffers, n_layers_run: int, adapter_len: int, dim: int, group=None, chunk_layers: int = 8):
+        self.gb = grad_buffers
+        self.L, self.A, self.d = n_layers_run, adapter_len, dim
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.chunk = max(1, chunk_layers)
+        self.works: List = []
+        self.messages = 0
+
+    def _reduce(self, t: torch.Tensor):
+        self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self.messages += 1
+
+    def layer_done(self, l: int):
+        """Called by the backward pass right after layer l's adapter gradient rows were written."""
+        if self.world == 1:
+            return
+        if l % self.chunk == 0:                                   # layers [l, min(l+chunk, L)) are final
+            hi = min(l + self.chunk, self.L)
+            self._reduce(self.gb.flat[l * self.A * self.d: hi * self.A * self.d])
+
+    def finish(self):
+        """Late message (gates, visual_proj, temporal_emb), wait for everything, turn the sum into a mean."""
+        if self.world == 1:
+            return
+        self._reduce(self.gb.flat[self.gb.late_offset:])
+        for w in self.works:
+            w.wait()                                              # stream-level wait for NCCL, not a host sync
+        self.works = []
+        self.gb.flat.mul_(1.0 / self.world)
+
+
+class DataParallel(torch.nn.Module):
+    """`model = DataParallel(model)`; exposes `.module` like torch's DDP so `train.py:117`,
+    `util/misc.py:297-317` keep working. Broadcasts the trainable parameters from rank 0 once (C2)."""
+
+    def __init__(self, module, group=None, chunk_layers: int = 8, broadcast: bool = True):
+        super().__init__()
+        self.module = module
+        self.group = group
+        self.chunk_layers = chunk_layers
+        if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
+            for p in module.parameters():
+                if p.requires_grad:
+                    dist.broadcast(p.data, src=0, group=group)
+
+    def _attach(self):
+        m = self.module
+        m._ensure_packed()
+        if m.grad_sync is None or m.grad_sync.gb is not m._grad_buffers:
+            m.grad_sync = GradSync(m._grad_buffers, len(m.run_layers()), m.adapter_len, m.params.dim, self.group, self.chunk_layers)
+
+    def forward(self, data, inference: bool = False):
+        self._attach()
+        return self.module(data, inference=inference)
+
+    def forward_plan(self, plan):
+        self._attach()
+        return self.module.forward_plan(plan)
+
+    def plan_batch(self, data, inference: bool = False):
+        return self.module.plan_batch(data, inference)

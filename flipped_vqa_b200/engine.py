@@ -1,0 +1,73 @@
+"""Train / validation loops with the contracts of `/root/reference/engine.py:10-56` and `:59-145`
+(loss-argmin branch, `:87-93,123-129`): same arguments, same returned `{meter: global_avg}` dict.
+
+Host trimming relative to the reference (SURVEY.md §7 stage 7): the four `.item()` calls plus the
+`cuda.synchronize()` per step (`engine.py:28-31,43`) become ONE device->host read of a 4-float tensor."""
+from __future__ import annotations
+
+import math
+import sys
+from typing import Iterable
+
+import torch
+
+from .util import lr_sched, misc
+
+
+def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torch.optim.Optimizer, epoch: int, loss_scaler, args=None):
+    model.train(True)
+    metric_logger = misc.MetricLogger(delimiter="  ")
+    metric_logger.add_meter("lr", misc.SmoothedValue(window_size=1, fmt="{value:.6f}"))
+    header = "Epoch: [{}]".format(epoch)
+    print_freq = max(int(len(data_loader) / 4), 1)
+    accum_iter = args.accum_iter
+    optimizer.zero_grad()
+    for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
+        if data_iter_step % accum_iter == 0:
+            lr_sched.adjust_learning_rate(optimizer, data_iter_step / len(data_loader) + epoch, args)
+        vqa_loss, vaq_loss, qav_loss = model(data)
+        loss = vqa_loss + vaq_loss + qav_loss
+        update = (data_iter_step + 1) % accum_iter == 0
+        loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update)
+        if update:
+            optimizer.zero_grad()
+        # one D2H read for all four logged values (also the step's only host sync)
+        vals = torch.stack([loss.detach().float().reshape(()), vqa_loss.detach().float().reshape(()),
+                            vaq_loss.detach().float().reshape(()), qav_loss.detach().float().reshape(())]).tolist()
+        loss_value = vals[0]
+        if not math.isfinite(loss_value):
+            print("Loss is {}, stopping training".format(loss_value))
+            sys.exit(1)
+        metric_logger.update(loss=loss_value, vqa_loss=vals[1], vaq_loss=vals[2], qav_loss=vals[3])
+        metric_logger.update(lr=optimizer.param_groups[0]["lr"])
+        if getattr(args, "debug", False):
+            break
+    metric_logger.synchronize_between_processes()
+    print("Averaged stats:", metric_logger)
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}
+
+
+def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torch.optim.Optimizer, epoch: int, args=None):
+    """Loss-based multiple-choice accuracy (`engine.py:87-93,123-129`): the model returns per-token option
+    losses; prediction = argmin over options of sum / count(loss != 0), done by one kernel."""
+    model.eval()
+    metric_logger = misc.MetricLogger(delimiter="  ")
+    metric_logger.add_meter("lr", misc.SmoothedValue(window_size=1, fmt="{value:.6f}"))
+    header = "Epoch: [{}]".format(epoch)
+    print_freq = max(int(len(data_loader) / 4), 1)
+    inner = model.module if hasattr(model, "module") else model
+    for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
+        answer = data["answer"]
+        bsz = answer.shape[0]
+        with torch.no_grad():
+            individual_losses = model(data, inference=True)
+            prediction = inner.predict_options(individual_losses)
+        eval_exact_match = answer.to(prediction.device) == prediction
+        acc = eval_exact_match.sum().item() / bsz
+        metric_logger.update(lr=optimizer.param_groups[0]["lr"] if optimizer is not None else 0.0)
+        metric_logger.update(n=bsz, acc=acc)
+        if getattr(args, "debug", False):
+            break
+    metric_logger.synchronize_between_processes()
+    print("Averaged stats:", metric_logger)
+    return {k: meter.global_avg for k, meter in metric_logger.meters.items()}

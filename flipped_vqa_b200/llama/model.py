@@ -22,7 +22,7 @@ from typing import List, Optional
 import torch
 from torch import nn
 
-from ..step import BatchPlan, GradBuffers, LayerWeights, StepEngine
+from ..step import BatchPlan, GradBuffers, LayerWeights, PinnedPool, StepEngine
 from ..synthetic import ffn_hidden_dim
 from .tokenizer import Tokenizer
 
@@ -199,6 +199,7 @@ class Transformer(nn.Module):
         self._grad_buffers: Optional[GradBuffers] = None
         self._pack_token = None
         self.last_plan: Optional[BatchPlan] = None
+        self._pinned: Optional[PinnedPool] = None
 
     # ------------------------------------------------------------------ weight layout
     def run_layers(self):
@@ -273,12 +274,24 @@ class Transformer(nn.Module):
     def streams(self):
         return ["vqa"] + (["vaq"] if self.args.vaq else []) + (["qav"] if self.args.qav else [])
 
+    def plan_batch(self, data, inference: bool = False) -> BatchPlan:
+        """Host side of a step: flatten the batch dict (`dataloader/__init__.py:28-90`) into the int32
+        arrays the kernels read and start the (single) async H2D copy from pinned memory."""
+        if self._pinned is None:
+            self._pinned = PinnedPool()
+        streams = ["vqa"] if inference else self.streams()
+        return BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned).to_device(self._device)
+
     def forward(self, data, inference: bool = False):
         if inference:
             return self.inference(data)
         self._ensure_packed()
+        return self.forward_plan(self.plan_batch(data))
+
+    def forward_plan(self, plan: BatchPlan):
+        """The device side of the training step for an already device-resident batch plan."""
+        self._ensure_packed()
         dev = self._device
-        plan = BatchPlan(data, self.streams(), self.max_feats).to_device(dev)
         self.last_plan = plan
         trainables, n_run = self.trainable_parameters()
         if torch.is_grad_enabled() and any(p.requires_grad for p in trainables):
@@ -299,7 +312,7 @@ class Transformer(nn.Module):
         (`model_my_original_mod.py:281,332-333,348-360,375-377,506`)."""
         self._ensure_packed()
         dev = self._device
-        plan = BatchPlan(data, ["vqa"], self.max_feats, inference=True).to_device(dev)
+        plan = self.plan_batch(data, inference=True)
         self.last_plan = plan
         trainables, n_run = self.trainable_parameters()
         g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]

@@ -8,9 +8,45 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream
+from ._lib import check as _check_rc, ptr, stream
 
 BF16 = torch.bfloat16
+
+# kernels launched through the C ABI since import (bench.py reports the count inside its timed region)
+LAUNCHES = 0
+
+
+class GemmTimer:
+    """Optional CUDA-event timing of individual GEMM launches on the launching stream (bench.py's
+    roofline leg). `active` is toggled by the caller to sample a subset of launches."""
+
+    def __init__(self):
+        self.active = False
+        self.records = []          # (start_event, end_event, flops)
+
+    def summary(self):
+        if not self.records:
+            return None
+        ms = [a.elapsed_time(b) for a, b, _ in self.records]
+        fl = [f for _, _, f in self.records]
+        return dict(launches=len(ms), total_ms=sum(ms), total_flops=sum(fl), avg_ms=sum(ms) / len(ms),
+                    avg_flops=sum(fl) / len(fl), tflops=sum(fl) / (sum(ms) * 1e-3) / 1e12)
+
+
+GEMM_TIMER: Optional[GemmTimer] = None
+
+
+def _count(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+_KERNELS_PER_CALL = {"attn_bwd": 3, "qav_loss_bwd": 2}
+
+
+def check(rc: int, what: str):
+    _check_rc(rc, what)
+    _count(_KERNELS_PER_CALL.get(what, 1))
 
 
 def _chk(t: torch.Tensor, dtype, name: str):
@@ -81,8 +117,15 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else BF16, device=a.device)
     assert out.stride(-1) == 1 and out.dtype == (torch.float32 if out_fp32 else BF16)
     ldr = residual.stride(0) if residual is not None else 0
+    tm = GEMM_TIMER
+    if tm is not None and tm.active:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(_lib.lib().fvqa_gemm_bf16_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), ptr(residual), ldr,
                                        M, N, K, 1 if out_fp32 else 0, stream()), "gemm_bf16_nt")
+    if tm is not None and tm.active:
+        e1.record()
+        tm.records.append((e0, e1, 2.0 * M * N * K))
     return out
 
 

@@ -1,0 +1,199 @@
+"""The parts of `/root/reference/util/misc.py` that sit on the training step's path, same call
+signatures: `NativeScalerWithGradNormCount` (`:253-279`), `get_grad_norm_` (`:282-294`),
+`init_distributed_mode` (`:220-250`), trainable-only checkpoints (`:297-336`), plus a compact metric
+logger with the `global_avg` contract `engine.py:54-56` returns."""
+from __future__ import annotations
+
+import datetime
+import os
+import time
+from collections import defaultdict, deque
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+
+
+class SmoothedValue:
+    def __init__(self, window_size=20, fmt=None):
+        self.deque = deque(maxlen=window_size)
+        self.total, self.count = 0.0, 0
+        self.fmt = fmt or "{median:.4f} ({global_avg:.4f})"
+
+    def update(self, value, n=1):
+        self.deque.append(value)
+        self.count += n
+        self.total += value * n
+
+    def synchronize_between_processes(self):
+        if not is_dist_avail_and_initialized():
+            return
+        dev = "cuda" if torch.cuda.is_available() and dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([self.count, self.total], dtype=torch.float64, device=dev)
+        dist.barrier()
+        dist.all_reduce(t)
+        self.count, self.total = int(t[0].item()), float(t[1].item())
+
+    @property
+    def median(self):
+        d = sorted(self.deque)
+        return d[len(d) // 2] if d else 0.0
+
+    @property
+    def avg(self):
+        return sum(self.deque) / max(len(self.deque), 1)
+
+    @property
+    def global_avg(self):
+        return self.total / max(self.count, 1)
+
+    @property
+    def value(self):
+        return self.deque[-1] if self.deque else 0.0
+
+    def __str__(self):
+        return self.fmt.format(median=self.median, avg=self.avg, global_avg=self.global_avg, value=self.value)
+
+
+class MetricLogger:
+    def __init__(self, delimiter="\t"):
+        self.meters = defaultdict(SmoothedValue)
+        self.delimiter = delimiter
+
+    def update(self, n=1, **kwargs):
+        for k, v in kwargs.items():
+            if v is None:
+                continue
+            if isinstance(v, torch.Tensor):
+                v = v.item()
+            self.meters[k].update(float(v), n=n)
+
+    def add_meter(self, name, meter):
+        self.meters[name] = meter
+
+    def synchronize_between_processes(self):
+        for m in self.meters.values():
+            m.synchronize_between_processes()
+
+    def __str__(self):
+        return self.delimiter.join(f"{k}: {m}" for k, m in self.meters.items())
+
+    def log_every(self, iterable, print_freq, header=None):
+        header = header or ""
+        start = time.time()
+        n = len(iterable) if hasattr(iterable, "__len__") else -1
+        for i, obj in enumerate(iterable):
+            yield obj
+            if print_freq and (i % print_freq == 0 or i == n - 1):
+                print(f"{header} [{i}/{n}] {self}  elapsed {datetime.timedelta(seconds=int(time.time() - start))}")
+
+
+def is_dist_avail_and_initialized():
+    return dist.is_available() and dist.is_initialized()
+
+
+def get_world_size():
+    return dist.get_world_size() if is_dist_avail_and_initialized() else 1
+
+
+def get_rank():
+    return dist.get_rank() if is_dist_avail_and_initialized() else 0
+
+
+def is_main_process():
+    return get_rank() == 0
+
+
+def save_on_master(*args, **kwargs):
+    if is_main_process():
+        torch.save(*args, **kwargs)
+
+
+def init_distributed_mode(args):
+    """One process per GPU from torchrun's env (`util/misc.py:230-233`); NCCL over NVLink 5."""
+    if "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+        args.rank = int(os.environ["RANK"])
+        args.world_size = int(os.environ["WORLD_SIZE"])
+        args.gpu = int(os.environ.get("LOCAL_RANK", 0))
+    else:
+        print("Not using distributed mode")
+        args.distributed = False
+        return
+    args.distributed = True
+    torch.cuda.set_device(args.gpu)
+    args.dist_backend = "nccl"
+    dist.init_process_group(backend=args.dist_backend, init_method=getattr(args, "dist_url", "env://"),
+                            world_size=args.world_size, rank=args.rank)
+
+
+class NativeScalerWithGradNormCount:
+    """Same call path as `util/misc.py:253-279`. bf16 needs no loss scaling, so the GradScaler is
+    disabled by default (scale = 1, no inf-check host sync); `enabled=True` keeps the fp16-style
+    scaling path alive — the step's backward multiplies by the incoming scaled gradient."""
+    state_dict_key = "amp_scaler"
+
+    def __init__(self, enabled: bool = False):
+        self._scaler = torch.amp.GradScaler("cuda", enabled=enabled)
+
+    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+        self._scaler.scale(loss).backward(create_graph=create_graph)
+        if update_grad:
+            self._scaler.unscale_(optimizer)
+            if clip_grad is not None:
+                assert parameters is not None
+                norm = torch.nn.utils.clip_grad_norm_(parameters, clip_grad)
+            else:
+                norm = get_grad_norm_(parameters)
+            self._scaler.step(optimizer)
+            self._scaler.update()
+        else:
+            norm = None
+        return norm
+
+    def state_dict(self):
+        return self._scaler.state_dict()
+
+    def load_state_dict(self, state_dict):
+        self._scaler.load_state_dict(state_dict)
+
+
+def get_grad_norm_(parameters, norm_type: float = 2.0) -> torch.Tensor:
+    """L2 norm over parameters that have a gradient (`util/misc.py:282-294`), as one foreach op; stays on
+    the device (no host sync)."""
+    if isinstance(parameters, torch.Tensor):
+        parameters = [parameters]
+    grads = [p.grad.detach() for p in parameters if p.grad is not None]
+    if not grads:
+        return torch.tensor(0.0)
+    if norm_type == float("inf"):
+        return torch.stack([g.abs().max() for g in grads]).max()
+    return torch.linalg.vector_norm(torch.stack(torch._foreach_norm(grads, norm_type)), norm_type)
+
+
+def trainable_state(model_without_ddp):
+    """`util/misc.py:303-306`: only parameters whose name matches the trainable rule are checkpointed."""
+    return {n: p for n, p in model_without_ddp.named_parameters()
+            if any(s in n for s in ("gate", "adapter", "temporal_emb", "visual_proj"))}
+
+
+def save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler, name):
+    """Same file layout as `util/misc.py:297-317` (checkpoint_<name>.pth with model/optimizer/epoch/scaler/args)."""
+    output_dir = Path(args.output_dir)
+    to_save = {"model": {k: v.detach().clone() for k, v in trainable_state(model_without_ddp).items()},
+               "optimizer": optimizer.state_dict(), "epoch": epoch,
+               "scaler": loss_scaler.state_dict() if loss_scaler is not None else None, "args": args}
+    save_on_master(to_save, output_dir / f"checkpoint_{name}.pth")
+
+
+def load_model(args, model_without_ddp, optimizer, loss_scaler):
+    """`util/misc.py:323-336`: resume trainables (strict=False), optimizer, scaler, start_epoch."""
+    if not getattr(args, "resume", ""):
+        return
+    checkpoint = torch.load(args.resume, map_location="cpu", weights_only=False)
+    model_without_ddp.load_state_dict(checkpoint["model"], strict=False)
+    print(f"Resume checkpoint {args.resume}")
+    if "optimizer" in checkpoint and "epoch" in checkpoint:
+        optimizer.load_state_dict(checkpoint["optimizer"])
+        args.start_epoch = checkpoint["epoch"] + 1
+        if loss_scaler is not None and checkpoint.get("scaler") is not None:
+            loss_scaler.load_state_dict(checkpoint["scaler"])

@@ -97,14 +97,33 @@ def _compare_with_oracle(params_dict, run, args, seed, loss_tol=LOSS_RTOL, grad_
     model = build_product_model(params_dict, sd, args)
     losses = _run_product(model, data)
     ref_losses, ref_grads = _oracle_on_gpu(params_dict, sd, data, args)
-    n_streams = 1 + int(args.vaq) + int(args.qav)
-    for a, b in list(zip(losses, ref_losses))[:n_streams]:
-        assert abs(a - b) / abs(b) < loss_tol, f"loss {a} vs oracle {b}"
+    enabled = [True, bool(args.vaq), bool(args.qav)]
+    for name, on, a, b in zip(("vqa", "vaq", "qav"), enabled, losses, ref_losses):
+        if on:
+            assert abs(a - b) / abs(b) < loss_tol, f"{name} loss {a} vs oracle {b}"
+        else:
+            assert a == 0.0 and b == 0.0, name        # `model.py:302` placeholder tensor([0])
     grads = product_grads(model)
     assert set(grads) == set(ref_grads)
+    _check_grads(grads, ref_grads, grad_tol)
+
+
+def _check_grads(grads, ref_grads, grad_tol=GRAD_RTOL):
+    """2e-2 relative L2 per trainable tensor. The per-layer gates are [1,H,1,1] (2..40 numbers, each a
+    cancellation-heavy sum over every token): for them the 2e-2 bound is applied to the stacked
+    gate1 / gate2 vectors over all layers, with a 6e-2 bound per layer — the reference's OWN code run
+    in bf16 shows 4.2e-2 on a single layer's gate1 for the S=650 case ('Parity')."""
+    for group in ("gate1", "gate2"):
+        names = sorted(n for n in ref_grads if n.endswith(group))
+        if names:
+            a = torch.cat([grads[n].flatten() for n in names])
+            b = torch.cat([ref_grads[n].flatten() for n in names])
+            e = rel_l2(a, b)
+            assert e < grad_tol, f"grad {group} (stacked over {len(names)} layers): rel L2 {e}"
     for n in ref_grads:
         e = rel_l2(grads[n], ref_grads[n])
-        assert e < grad_tol, f"grad {n}: rel L2 {e}"
+        tol = 3 * grad_tol if "gate" in n else grad_tol
+        assert e < tol, f"grad {n}: rel L2 {e}"
 
 
 def test_tiny_config_vs_oracle(fvqa_lib):
