@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--config", default="7b-nextqa", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--sample-layers", type=int, default=2, help="layers whose GEMM launches are event-timed inside the timed region")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
@@ -310,9 +311,12 @@ def main():
     ms_per_step = ms / a.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    for i in range(2):
-        step_e2e(i)
-    ms_e, _, clocks_e, _ = timed(step_e2e, a.steps)
+    if a.no_e2e:
+        ms_e, clocks_e = float("nan"), None
+    else:
+        for i in range(2):
+            step_e2e(i)
+        ms_e, _, clocks_e, _ = timed(step_e2e, a.steps)
     e2e_value = world * B / (ms_e / a.steps * 1e-3)
 
     peaks = measured_peaks()
