@@ -24,12 +24,13 @@ _SIGNATURES = {
     "fvqa_last_error": [],
     "fvqa_init": [],
     "fvqa_rmsnorm_fwd": [_p, _p, _p, _p, _i, _i, _f, _p],
-    "fvqa_rmsnorm_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "fvqa_rmsnorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fvqa_rmsnorm_gather_fwd": [_p, _p, _p, _p, _p, _i, _i, _f, _p],
-    "fvqa_rmsnorm_scatter_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _p],
+    "fvqa_rmsnorm_scatter_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fvqa_swiglu_fwd": [_p, _p, _i, _i, _p],
     "fvqa_swiglu_bwd": [_p, _p, _p, _i, _i, _p],
     "fvqa_gemm_bf16_nt": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "fvqa_gemm_bf16_nt_rope": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p],
     "fvqa_attn_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fvqa_attn_bwd_ws_bytes": [_i, _i, _i, _i, _i],
     "fvqa_attn_bwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

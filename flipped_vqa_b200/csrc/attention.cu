@@ -1,6 +1,7 @@
 // Fused causal attention forward / backward for the LLaMA-VQA step, with
-//   * RoPE (interleaved pairs, llama/model.py:61-67) applied when Q/K tiles are loaded, and the
-//     inverse rotation applied to dQ/dK before they are written (nothing rotated is ever stored);
+//   * RoPE (interleaved pairs, llama/model.py:61-67): q/k arrive already rotated (the rotation is
+//     folded into the QKV GEMM epilogue); the INVERSE rotation is applied here to dQ/dK in registers
+//     before they are written, so the dX GEMM consumes gradients of the un-rotated projections;
 //   * the adapter-prompt branch: a SEPARATE softmax over the A adapter keys scaled by tanh(gate1)
 //     (model.py:99-115) whose keys/values are shared by every sequence;
 //   * the gate2 bias on text scores of rows >= vs+F, columns [vs, vs+F) (model.py:116-119), per
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
   const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;   // rows >= this get the bias
   const int bias_c0 = vs, bias_c1 = vs + p.F;                  // columns [c0, c1)
 
-  load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, r0, S, p.cosT, p.sinT);
+  load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, r0, S, nullptr, nullptr);
   load_tile<HD, AT_AP, false>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
   load_tile<HD, AT_AP, false>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
 
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
 
   for (int j = 0; j <= qt; ++j) {
     __syncthreads();   // previous tile fully consumed (also orders the initial loads)
-    load_tile<HD, AT_BN, true>(sK, kbase, qkv_stride, j * AT_BN, S, p.cosT, p.sinT);
+    load_tile<HD, AT_BN, false>(sK, kbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
     load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
     __syncthreads();
     float s[AT_BN / 8][4];
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
   {
     float sa[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     warp_mma_nt<2, HD, LD>(sa, sQ_u, warp * 16, sKa_u, 0);
-    const float tg = bf16_round(tanhf(p.gate1[h]));
+    const float tg = tanhf(p.gate1[h]);
     float mx[2] = {-INFINITY, -INFINITY}, sm[2] = {0.f, 0.f};
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) sa[nt][e] = bf16_round(sa[nt][e] / sm[e >> 1]) * tg;   // (softmax.half() * tanh.half())
+      for (int e = 0; e < 4; ++e) sa[nt][e] = sa[nt][e] / sm[e >> 1] * tg;               // softmax * tanh(gate1)
     uint32_t pa[1][4];
     c_to_a(pa[0], sa[0], sa[1]);
     warp_mma_ra_t<HD / 8, 1, LD>(o, pa, sVa_u, 0, 0);
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
   const int bias_c0 = vs, bias_c1 = vs + p.F;
   const float tg = tanhf(p.gate1[h]);
 
-  load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, r0, S, p.cosT, p.sinT);
+  load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, r0, S, nullptr, nullptr);
   load_tile<HD, AT_BM, false>(sdO, dobase, D, r0, S, nullptr, nullptr);
   load_tile<HD, AT_AP, false>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
   load_tile<HD, AT_AP, false>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
@@ -446,7 +447,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
   // ---- text keys ----
   for (int j = 0; j <= qt; ++j) {
     __syncthreads();
-    load_tile<HD, AT_BN, true>(sK, kbase, qkv_stride, j * AT_BN, S, p.cosT, p.sinT);
+    load_tile<HD, AT_BN, false>(sK, kbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
     load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
     __syncthreads();
     float s[AT_BN / 8][4], dp[AT_BN / 8][4];
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
     for (int i = 0; i < HD / 8; ++i) { dka[i][0] = dka[i][1] = dka[i][2] = dka[i][3] = 0.f; dva[i][0] = dva[i][1] = dva[i][2] = dva[i][3] = 0.f; }
     for (int i = 0; i < p.qtiles; ++i) {
       __syncthreads();
-      load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, i * AT_BM, S, p.cosT, p.sinT);
+      load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, i * AT_BM, S, nullptr, nullptr);
       load_tile<HD, AT_BM, false>(sdO, dobase, D, i * AT_BM, S, nullptr, nullptr);
       __syncthreads();
       // each warp takes 16 of the 64 query rows (they are the contraction dimension of dK_a / dV_a)
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
 
   // ======================= text keys =======================
   const int k0 = jt * AT_BN;
-  load_tile<HD, AT_BN, true>(sK, kbase, qkv_stride, k0, S, p.cosT, p.sinT);
+  load_tile<HD, AT_BN, false>(sK, kbase, qkv_stride, k0, S, nullptr, nullptr);
   load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, k0, S, nullptr, nullptr);
   const int vs = p.vstart[n];
   const float bias2 = (vs >= 0) ? p.gate2[h] * LOG2E : 0.f;
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
   const int key_a = k0 + warp * 16 + gq;   // this thread's keys: key_a, key_a + 8
   for (int i = jt; i < p.qtiles; ++i) {
     __syncthreads();
-    load_tile<HD, AT_BM, true>(sQ, qbase, qkv_stride, i * AT_BM, S, p.cosT, p.sinT);
+    load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, i * AT_BM, S, nullptr, nullptr);
     load_tile<HD, AT_BM, false>(sdO, dobase, D, i * AT_BM, S, nullptr, nullptr);
     if (threadIdx.x < AT_BM) {
       const int row = i * AT_BM + threadIdx.x;
@@ -656,26 +657,45 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
 // ---------------------------------------------------------------------------------------------
 // fixed-order reduction of the per-CTA partials
 // ---------------------------------------------------------------------------------------------
+// grid (H, A + 1): blocks (h, a < A) reduce adapter row a of head h over the sequences (independent
+// loads, fixed summation order); block (h, A) reduces the gate partials of head h.
 __global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __restrict__ ws_akv, const float* __restrict__ ws_gate,
                                                               const float* __restrict__ gate1, float* __restrict__ dakv,
                                                               float* __restrict__ dgate1, float* __restrict__ dgate2, int n_seq,
                                                               int H, int hd, int A, int qtiles) {
-  const int h = blockIdx.x;
+  __shared__ float red[32];
+  const int h = blockIdx.x, a = blockIdx.y;
   const int D = H * hd;
-  for (int idx = threadIdx.x; idx < 2 * A * hd; idx += blockDim.x) {
-    const int which = idx / (A * hd), rem = idx - which * A * hd, a = rem / hd, c = rem - a * hd;
-    float acc = 0.f;
-    for (int n = 0; n < n_seq; ++n) acc += ws_akv[((static_cast<long>(n) * H + h) * 2 + which) * AT_AP * hd + a * hd + c];
-    dakv[static_cast<long>(a) * 2 * D + which * D + h * hd + c] = acc;
-  }
-  if (threadIdx.x == 0) {
-    float g1 = 0.f, g2 = 0.f;
-    for (int n = 0; n < n_seq; ++n)
-      for (int q = 0; q < qtiles; ++q) {
-        const float* w = ws_gate + ((static_cast<long>(n) * H + h) * qtiles + q) * 2;
-        g1 += w[0];
-        g2 += w[1];
+  if (a < A) {
+    for (int idx = threadIdx.x; idx < 2 * hd; idx += blockDim.x) {
+      const int which = idx / hd, c = idx - which * hd;
+      const float* src = ws_akv + (static_cast<long>(h) * 2 + which) * AT_AP * hd + a * hd + c;
+      const long stride = static_cast<long>(H) * 2 * AT_AP * hd;
+      float acc = 0.f;
+      int n = 0;
+      for (; n + 8 <= n_seq; n += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (n + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += v[u];
       }
+      for (; n < n_seq; ++n) acc += __ldg(src + n * stride);
+      dakv[static_cast<long>(a) * 2 * D + which * D + h * hd + c] = acc;
+    }
+    return;
+  }
+  float g1 = 0.f, g2 = 0.f;
+  const int total = n_seq * qtiles;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int n = i / qtiles, q = i - n * qtiles;
+    const float* w = ws_gate + ((static_cast<long>(n) * H + h) * qtiles + q) * 2;
+    g1 += w[0];
+    g2 += w[1];
+  }
+  g1 = block_sum(g1, red);       // fixed tree order -> deterministic
+  g2 = block_sum(g2, red);
+  if (threadIdx.x == 0) {
     const float tg = tanhf(gate1[h]);
     dgate1[h] = (1.f - tg * tg) * g1;
     dgate2[h] = g2;
@@ -769,6 +789,6 @@ extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   }
   rc = check_launch("attn_bwd_dkv");
   if (rc) return rc;
-  attn_bwd_reduce_kernel<<<H, 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qtiles);
+  attn_bwd_reduce_kernel<<<dim3(H, A + 1), 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qtiles);
   return check_launch("attn_bwd_reduce");
 }

@@ -1,20 +1,30 @@
 // HBM-bound row kernels: fused RMSNorm fwd/bwd (+gather/scatter variants), fused SwiGLU fwd/bwd.
-// Reference semantics: llama/model.py:31-42 (RMSNorm), :142 (SwiGLU). All I/O is bf16 with 16-byte
-// vector accesses; math in fp32. One CTA per row for the norms (row cached in registers), flat
+// Reference semantics: llama/model.py:31-42 (RMSNorm), :142 (SwiGLU). The residual stream (and its
+// gradient) is fp32, GEMM operands are bf16; 16-byte vector accesses; math in fp32. One CTA per row for the norms (row cached in registers), flat
 // grid-stride for SwiGLU.
 #include "common.cuh"
 
 namespace fvqa {
 
 constexpr int NORM_THREADS = 256;
-constexpr int NORM_MAXV = 4;  // vectors (8 bf16) per thread kept in registers -> dim <= 8192
+constexpr int NORM_MAXV = 4;  // vectors (8 elements) per thread kept in registers -> dim <= 8192
+
+__device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8f(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
 
 // ---------------------------------------------------------------------------------------------
-// RMSNorm forward.  y = bf16( bf16(x * rstd) * w )   (rounding point of model.py:41-42)
+// RMSNorm forward on the fp32 residual stream:  y = bf16(x * rstd * w)
 // idx == nullptr: row r reads x[r]; otherwise row r reads x[idx[r]] (idx<0 -> zero row).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
-    const bf16* __restrict__ x, const int32_t* __restrict__ idx, const bf16* __restrict__ w,
+    const float* __restrict__ x, const int32_t* __restrict__ idx, const bf16* __restrict__ w,
     bf16* __restrict__ y, float* __restrict__ rstd_out, int dim, float eps) {
   __shared__ float red[32];
   const int row = blockIdx.x;
@@ -27,19 +37,17 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
     if (threadIdx.x == 0 && rstd_out) rstd_out[row] = 0.f;
     return;
   }
-  const uint4* xrow = reinterpret_cast<const uint4*>(x + src * dim);
+  const float* xrow = x + src * dim;
   const uint4* wv = reinterpret_cast<const uint4*>(w);
-  uint4 xr[NORM_MAXV];
+  float xr[NORM_MAXV][8];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
-      xr[i] = __ldg(xrow + v);
-      float f[8];
-      unpack8(xr[i], f);
+      load8f(xrow + v * 8, xr[i]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      for (int j = 0; j < 8; ++j) ss += xr[i][j] * xr[i][j];
     }
   }
   ss = block_sum(ss, red);
@@ -49,25 +57,24 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
   for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
-      float f[8], g[8];
-      unpack8(xr[i], f);
+      float g[8], o[8];
       unpack8(__ldg(wv + v), g);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = bf16_round(f[j] * rstd) * g[j];
-      yrow[v] = pack8(f);
+      for (int j = 0; j < 8; ++j) o[j] = xr[i][j] * rstd * g[j];
+      yrow[v] = pack8(o);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // RMSNorm backward (dX only). With n = x*rstd, dn = dy*w:
-//   dx = rstd * (dn - n * mean(dn * n)) (+ dres)
+//   dx = rstd * (dn - n * mean(dn * n)) (+ dres)      fp32 out (+ optional bf16 copy: next GEMM operand)
 // scatter variant: output row = idx[r] (rows with idx<0 skipped), no residual.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
-    const bf16* __restrict__ dy, const bf16* __restrict__ x, const int32_t* __restrict__ idx,
-    const bf16* __restrict__ w, const float* __restrict__ rstd_in, const bf16* __restrict__ dres,
-    bf16* __restrict__ dx, int dim) {
+    const bf16* __restrict__ dy, const float* __restrict__ x, const int32_t* __restrict__ idx,
+    const bf16* __restrict__ w, const float* __restrict__ rstd_in, const float* __restrict__ dres,
+    float* __restrict__ dx, bf16* __restrict__ dx_bf16, int dim) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int nvec = dim >> 3;
@@ -77,47 +84,46 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
     if (src < 0) return;
   }
   const uint4* dyrow = reinterpret_cast<const uint4*>(dy + static_cast<long>(row) * dim);
-  const uint4* xrow = reinterpret_cast<const uint4*>(x + src * dim);
+  const float* xrow = x + src * dim;
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   const float rstd = rstd_in[row];
-  uint4 xr[NORM_MAXV], dr[NORM_MAXV];
+  float xr[NORM_MAXV][8], dn[NORM_MAXV][8];
   float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
-      xr[i] = __ldg(xrow + v);
-      dr[i] = __ldg(dyrow + v);
-      float fx[8], fd[8], fw[8];
-      unpack8(xr[i], fx);
-      unpack8(dr[i], fd);
+      load8f(xrow + v * 8, xr[i]);
+      float fd[8], fw[8];
+      unpack8(__ldg(dyrow + v), fd);
       unpack8(__ldg(wv + v), fw);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dot += fd[j] * fw[j] * fx[j] * rstd;
+      for (int j = 0; j < 8; ++j) {
+        dn[i][j] = fd[j] * fw[j];
+        dot += dn[i][j] * xr[i][j] * rstd;
+      }
     }
   }
   dot = block_sum(dot, red) / static_cast<float>(dim);
-  uint4* dxrow = reinterpret_cast<uint4*>(dx + src * dim);
-  const uint4* rrow = dres ? reinterpret_cast<const uint4*>(dres + src * dim) : nullptr;
+  float* dxrow = dx + src * dim;
+  const float* rrow = dres ? dres + src * dim : nullptr;
 #pragma unroll
   for (int i = 0; i < NORM_MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
-      float fx[8], fd[8], fw[8], o[8];
-      unpack8(xr[i], fx);
-      unpack8(dr[i], fd);
-      unpack8(__ldg(wv + v), fw);
+      float o[8];
       float fr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (rrow) unpack8(__ldg(rrow + v), fr);
+      if (rrow) load8f(rrow + v * 8, fr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fr[j] + rstd * (fd[j] * fw[j] - fx[j] * rstd * dot);
-      dxrow[v] = pack8(o);
+      for (int j = 0; j < 8; ++j) o[j] = fr[j] + rstd * (dn[i][j] - xr[i][j] * rstd * dot);
+      store8f(dxrow + v * 8, o);
+      if (dx_bf16) reinterpret_cast<uint4*>(dx_bf16 + src * dim)[v] = pack8(o);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// SwiGLU. g = [rows, 2*hid] (a | b). fwd: c = bf16( bf16(silu(a)) * b ).
+// SwiGLU. g = [rows, 2*hid] (a | b). fwd: c = bf16( silu(a) * b ).
 // bwd: da = dc * b * s * (1 + a * (1 - s)), db = dc * silu(a), s = sigmoid(a).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ c,
@@ -135,7 +141,7 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float s = a[j] / (1.f + __expf(-a[j]));
-      o[j] = bf16_round(s) * b[j];
+      o[j] = s * b[j];
     }
     reinterpret_cast<uint4*>(c + r * hid)[v] = pack8(o);
   }
@@ -184,44 +190,44 @@ static int elementwise_grid(long work_items, int threads) {
 
 using namespace fvqa;
 
-extern "C" int fvqa_rmsnorm_fwd(const fvqa_bf16* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd, int rows,
+extern "C" int fvqa_rmsnorm_fwd(const float* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd, int rows,
                                 int dim, float eps, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED,
                "rmsnorm: dim %d must be a multiple of 8 and <= %d", dim, 8 * NORM_THREADS * NORM_MAXV);
   if (rows <= 0) return FVQA_OK;
   rmsnorm_fwd_kernel<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(x), nullptr, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
+      x, nullptr, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_fwd");
 }
 
-extern "C" int fvqa_rmsnorm_gather_fwd(const fvqa_bf16* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
+extern "C" int fvqa_rmsnorm_gather_fwd(const float* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
                                        float* rstd, int rows_out, int dim, float eps, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_gather: bad dim %d", dim);
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_gather: idx is null");
   if (rows_out <= 0) return FVQA_OK;
   rmsnorm_fwd_kernel<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(x), idx, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
+      x, idx, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_gather_fwd");
 }
 
-extern "C" int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const fvqa_bf16* w, const float* rstd,
-                                const fvqa_bf16* dres, fvqa_bf16* dx, int rows, int dim, void* stream) {
+extern "C" int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const float* x, const fvqa_bf16* w, const float* rstd,
+                                const float* dres, float* dx, fvqa_bf16* dx_bf16, int rows, int dim, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_bwd: bad dim %d", dim);
   if (rows <= 0) return FVQA_OK;
   rmsnorm_bwd_kernel<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), nullptr, reinterpret_cast<const bf16*>(w), rstd,
-      reinterpret_cast<const bf16*>(dres), reinterpret_cast<bf16*>(dx), dim);
+      reinterpret_cast<const bf16*>(dy), x, nullptr, reinterpret_cast<const bf16*>(w), rstd, dres, dx,
+      reinterpret_cast<bf16*>(dx_bf16), dim);
   return check_launch("rmsnorm_bwd");
 }
 
-extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const int32_t* idx, const fvqa_bf16* w,
-                                        const float* rstd, fvqa_bf16* dx, int rows_out, int dim, void* stream) {
+extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const float* x, const int32_t* idx, const fvqa_bf16* w,
+                                        const float* rstd, float* dx, fvqa_bf16* dx_bf16, int rows_out, int dim, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_scatter_bwd: bad dim %d", dim);
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_scatter_bwd: idx is null");
   if (rows_out <= 0) return FVQA_OK;
   rmsnorm_bwd_kernel<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), idx, reinterpret_cast<const bf16*>(w), rstd, nullptr,
-      reinterpret_cast<bf16*>(dx), dim);
+      reinterpret_cast<const bf16*>(dy), x, idx, reinterpret_cast<const bf16*>(w), rstd, nullptr, dx,
+      reinterpret_cast<bf16*>(dx_bf16), dim);
   return check_launch("rmsnorm_scatter_bwd");
 }
 

@@ -61,18 +61,22 @@ __global__ void __launch_bounds__(VP_THREADS) visual_proj_bwd_kernel(const float
   }
 }
 
-// One CTA per token row.
+// One CTA per token row; output is the fp32 residual stream (values are bf16-representable).
 __global__ void __launch_bounds__(256) build_h0_fwd_kernel(
     const bf16* __restrict__ tok_emb, const int32_t* __restrict__ ids, const int32_t* __restrict__ labels,
     const int32_t* __restrict__ vstart, const int32_t* __restrict__ seq_video, const int32_t* __restrict__ qav_index,
-    const float* __restrict__ vf32, const float* __restrict__ temporal, bf16* __restrict__ h0, int S, int dim, int F) {
+    const float* __restrict__ vf32, const float* __restrict__ temporal, float* __restrict__ h0, int S, int dim, int F) {
   const int row = blockIdx.x;
   const int n = row / S, p = row - n * S;
   const int vs = vstart[n];
   const int b = seq_video[n];
   const int nvec = dim >> 3;
   const uint4* erow = reinterpret_cast<const uint4*>(tok_emb + static_cast<long>(ids[row]) * dim);
-  uint4* orow = reinterpret_cast<uint4*>(h0 + static_cast<long>(row) * dim);
+  float4* orow = reinterpret_cast<float4*>(h0 + static_cast<long>(row) * dim);
+  auto put = [&](int v, const float (&o)[8]) {
+    orow[2 * v] = make_float4(o[0], o[1], o[2], o[3]);
+    orow[2 * v + 1] = make_float4(o[4], o[5], o[6], o[7]);
+  };
   if (vs >= 0) {
     if (p >= vs && p < vs + F) {  // h[:, vs:vs+F] = (vf + temporal).half()   (model.py:324-332)
       const int f = p - vs;
@@ -81,11 +85,15 @@ __global__ void __launch_bounds__(256) build_h0_fwd_kernel(
       for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = vrow[v * 8 + j] + trow[v * 8 + j];
-        orow[v] = pack8(o);
+        for (int j = 0; j < 8; ++j) o[j] = bf16_round(vrow[v * 8 + j] + trow[v * 8 + j]);
+        put(v, o);
       }
     } else {
-      for (int v = threadIdx.x; v < nvec; v += blockDim.x) orow[v] = __ldg(erow + v);
+      for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float o[8];
+        unpack8(__ldg(erow + v), o);
+        put(v, o);
+      }
     }
   } else {
     // QAV: h = emb * ~(label >= 0); h.scatter_add_(1, index, video_feature)   (model.py:335-336)
@@ -98,44 +106,35 @@ __global__ void __launch_bounds__(256) build_h0_fwd_kernel(
       } else {
         unpack8(__ldg(erow + v), o);
       }
-      bool touched = false;
       for (int f = 0; f < F; ++f) {
         if (qav_index[b * F + f] == p) {
           const float* vrow = vf32 + (static_cast<long>(b) * F + f) * dim;
           const float* trow = temporal + static_cast<long>(f) * dim;
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = bf16_round(o[j] + bf16_round(vrow[v * 8 + j] + trow[v * 8 + j]));
-          touched = true;
         }
       }
-      (void)touched;
-      orow[v] = pack8(o);
+      put(v, o);
     }
   }
 }
 
 // One CTA per (video sample b, frame f): dvf[b,f,:] = sum over sequences of dh0 at that frame's slot.
-__global__ void __launch_bounds__(256) build_h0_bwd_kernel(const bf16* __restrict__ dh0, const int32_t* __restrict__ vstart,
+__global__ void __launch_bounds__(256) build_h0_bwd_kernel(const float* __restrict__ dh0, const int32_t* __restrict__ vstart,
                                                             const int32_t* __restrict__ seq_video,
                                                             const int32_t* __restrict__ qav_index, float* __restrict__ dvf,
                                                             int n_seq, int S, int dim, int F) {
   const int b = blockIdx.x / F, f = blockIdx.x - b * F;
-  const int nvec = dim >> 3;
-  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float acc = 0.f;
     for (int n = 0; n < n_seq; ++n) {
       if (seq_video[n] != b) continue;
       const int vs = vstart[n];
       const int pos = vs >= 0 ? vs + f : qav_index[b * F + f];
       if (pos < 0 || pos >= S) continue;
-      float g[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(dh0 + (static_cast<long>(n) * S + pos) * dim) + v), g);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+      acc += __ldg(dh0 + (static_cast<long>(n) * S + pos) * dim + c);
     }
-    float* o = dvf + (static_cast<long>(b) * F + f) * dim + v * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = acc[j];
+    dvf[(static_cast<long>(b) * F + f) * dim + c] = acc;
   }
 }
 
@@ -174,21 +173,20 @@ extern "C" int fvqa_visual_proj_bwd(const float* dvf, const float* video, float*
 
 extern "C" int fvqa_build_h0_fwd(const fvqa_bf16* tok_emb, const int32_t* ids, const int32_t* labels, const int32_t* vstart,
                                  const int32_t* seq_video, const int32_t* qav_index, const float* vf32, const float* temporal,
-                                 fvqa_bf16* h0, int n_seq, int S, int dim, int max_feats, void* stream) {
+                                 float* h0, int n_seq, int S, int dim, int max_feats, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0, FVQA_ERR_UNSUPPORTED, "build_h0: dim %d must be a multiple of 8", dim);
   if (n_seq * S <= 0) return FVQA_OK;
   build_h0_fwd_kernel<<<n_seq * S, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(tok_emb), ids, labels, vstart, seq_video, qav_index, vf32, temporal,
-      reinterpret_cast<bf16*>(h0), S, dim, max_feats);
+      reinterpret_cast<const bf16*>(tok_emb), ids, labels, vstart, seq_video, qav_index, vf32, temporal, h0, S, dim, max_feats);
   return check_launch("build_h0_fwd");
 }
 
-extern "C" int fvqa_build_h0_bwd(const fvqa_bf16* dh0, const int32_t* vstart, const int32_t* seq_video, const int32_t* qav_index,
+extern "C" int fvqa_build_h0_bwd(const float* dh0, const int32_t* vstart, const int32_t* seq_video, const int32_t* qav_index,
                                  float* dvf, int n_seq, int n_video, int S, int dim, int max_feats, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0, FVQA_ERR_UNSUPPORTED, "build_h0_bwd: dim %d must be a multiple of 8", dim);
   if (n_video * max_feats <= 0) return FVQA_OK;
   build_h0_bwd_kernel<<<n_video * max_feats, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dh0), vstart, seq_video, qav_index, dvf, n_seq, S, dim, max_feats);
+      dh0, vstart, seq_video, qav_index, dvf, n_seq, S, dim, max_feats);
   return check_launch("build_h0_bwd");
 }
 

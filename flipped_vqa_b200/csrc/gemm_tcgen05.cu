@@ -34,10 +34,21 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // +1024 manual alignment
 };
 
-template <int BN, bool OUT_F32>
+// Epilogue extras. ROPE (QKV projection only): columns < rope_cols hold q|k heads of width hd; the
+// interleaved pairs (2i, 2i+1) of row r are rotated by angle[pos = r % S][i] (llama/model.py:61-67)
+// while the fp32 accumulator is still in registers, so attention never sees un-rotated q/k.
+struct GemmEpi {
+  const void* R;      // residual, same dtype as the output (nullptr = none)
+  int ldr;
+  const float* cosT;  // [S, hd/2]
+  const float* sinT;
+  int rope_cols, hd, S;
+};
+
+template <int BN, bool OUT_F32, bool ROPE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    void* __restrict__ Cout, const bf16* __restrict__ R, int M, int N, int K, int ldc, int ldr) {
+                    void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -155,30 +166,50 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (row_ok && col0 < N) {
           if constexpr (OUT_F32) {
             float* crow = reinterpret_cast<float*>(Cout) + static_cast<long>(row) * ldc + col0;
+            const float* rrow = epi.R ? reinterpret_cast<const float*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               if (col0 + j * 4 < N) {
                 float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                if (R != nullptr) {
-                  const uint2 rr = *reinterpret_cast<const uint2*>(R + static_cast<long>(row) * ldr + col0 + j * 4);
-                  const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y);
-                  o.x += r0.x; o.y += r0.y; o.z += r1.x; o.w += r1.y;
+                if (rrow != nullptr) {
+                  const float4 rr = *reinterpret_cast<const float4*>(rrow + j * 4);
+                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                 }
                 *reinterpret_cast<float4*>(crow + j * 4) = o;
               }
             }
           } else {
             bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
+            const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
+            if constexpr (ROPE) {
+              if (col0 < epi.rope_cols) {
+                const int pos = row % epi.S;
+                const int i0 = (col0 % epi.hd) >> 1;
+                const float4* c4 = reinterpret_cast<const float4*>(epi.cosT + static_cast<long>(pos) * (epi.hd >> 1) + i0);
+                const float4* s4 = reinterpret_cast<const float4*>(epi.sinT + static_cast<long>(pos) * (epi.hd >> 1) + i0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 cc = __ldg(c4 + q), ss = __ldg(s4 + q);
+                  const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float a = __uint_as_float(v[8 * q + 2 * e]), b = __uint_as_float(v[8 * q + 2 * e + 1]);
+                    v[8 * q + 2 * e] = __float_as_uint(a * cv[e] - b * sv[e]);
+                    v[8 * q + 2 * e + 1] = __float_as_uint(a * sv[e] + b * cv[e]);
+                  }
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (col0 + j * 8 < N) {
                 float f[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-                if (R != nullptr) {
+                if (rrow != nullptr) {
                   float r[8];
-                  unpack8(*reinterpret_cast<const uint4*>(R + static_cast<long>(row) * ldr + col0 + j * 8), r);
+                  unpack8(*reinterpret_cast<const uint4*>(rrow + j * 8), r);
 #pragma unroll
                   for (int e = 0; e < 8; ++e) f[e] += r[e];
                 }
@@ -248,14 +279,16 @@ int gemm_init() {
   FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
   FVQA_REQUIRE(prop.major == 10, FVQA_ERR_UNSUPPORTED, "this library only runs on sm_100 (found sm_%d%d)", prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
-#define FVQA_SET_SMEM(BN, F32)                                                                          \
-  e = cudaFuncSetAttribute(gemm_bf16_nt_kernel<BN, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                           GemmCfg<BN>::kSmemBytes);                                                    \
+#define FVQA_SET_SMEM(BN, F32, ROPE)                                                                          \
+  e = cudaFuncSetAttribute(gemm_bf16_nt_kernel<BN, F32, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                           GemmCfg<BN>::kSmemBytes);                                                          \
   FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
-  FVQA_SET_SMEM(256, false)
-  FVQA_SET_SMEM(256, true)
-  FVQA_SET_SMEM(128, false)
-  FVQA_SET_SMEM(128, true)
+  FVQA_SET_SMEM(256, false, false)
+  FVQA_SET_SMEM(256, true, false)
+  FVQA_SET_SMEM(128, false, false)
+  FVQA_SET_SMEM(128, true, false)
+  FVQA_SET_SMEM(256, false, true)
+  FVQA_SET_SMEM(128, false, true)
 #undef FVQA_SET_SMEM
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return FVQA_OK;
@@ -285,8 +318,8 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
   return FVQA_OK;
 }
 
-template <int BN, bool OUT_F32>
-static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const bf16* R, int ldr, int M,
+template <int BN, bool OUT_F32, bool ROPE>
+static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
                        int N, int K, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc = get_tmap(A, M, K, lda, GEMM_BM, &ta);
@@ -295,16 +328,11 @@ static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, 
   if (rc) return rc;
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_nt_kernel<BN, OUT_F32><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, C, R, M, N, K, ldc, ldr);
+  gemm_bf16_nt_kernel<BN, OUT_F32, ROPE><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, C, epi, M, N, K, ldc);
   return check_launch("gemm_bf16_nt");
 }
 
-}  // namespace fvqa
-
-using namespace fvqa;
-
-extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, void* C, int ldc,
-                                 const fvqa_bf16* R, int ldr, int M, int N, int K, int out_fp32, void* stream) {
+static int check_gemm_args(const void* A, int lda, const void* B, int ldb, const void* C, int ldc, const void* R, int ldr, int M, int N, int K) {
   FVQA_REQUIRE(g_encode != nullptr, FVQA_ERR_INVALID_ARG, "fvqa_init() has not been called");
   FVQA_REQUIRE(M > 0 && N > 0 && K > 0, FVQA_ERR_INVALID_ARG, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
   FVQA_REQUIRE(K % GEMM_BK == 0, FVQA_ERR_UNSUPPORTED, "gemm: K=%d must be a multiple of %d", K, GEMM_BK);
@@ -314,22 +342,52 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
   FVQA_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(R) & 15) == 0,
                FVQA_ERR_INVALID_ARG, "gemm: pointers must be 16-byte aligned");
+  return FVQA_OK;
+}
+
+// Tile choice: 128x256 unless N is small or the 128x128 tiling fills the SM waves clearly better.
+static bool prefer_bn128(int M, int N) {
+  const int tm = (M + GEMM_BM - 1) / GEMM_BM;
+  auto eff = [&](int bn) {
+    const long tn = (N + bn - 1) / bn;
+    const long tiles = static_cast<long>(tm) * tn;
+    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+    return (static_cast<double>(tiles) / (static_cast<double>(waves) * g_num_sms)) * (static_cast<double>(N) / (tn * bn));
+  };
+  return (N <= 128) || (eff(128) > eff(256) + 0.08);
+}
+
+}  // namespace fvqa
+
+using namespace fvqa;
+
+extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, void* C, int ldc,
+                                 const void* R, int ldr, int M, int N, int K, int out_fp32, void* stream) {
+  int rc = check_gemm_args(A, lda, B, ldb, C, ldc, R, ldr, M, N, K);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bf16* a = reinterpret_cast<const bf16*>(A);
   const bf16* b = reinterpret_cast<const bf16*>(B);
-  const bf16* r = reinterpret_cast<const bf16*>(R);
-  // Tile choice: 128x256 unless N is small or the 128x128 tiling fills the SM waves better.
-  const int tm = (M + GEMM_BM - 1) / GEMM_BM;
-  auto waves_eff = [&](int bn) {
-    const long tiles = static_cast<long>(tm) * ((N + bn - 1) / bn);
-    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-    return static_cast<double>(tiles) * bn / (static_cast<double>(waves) * g_num_sms * bn) * (static_cast<double>(N) / (((N + bn - 1) / bn) * bn));
-  };
-  const bool use128 = (N <= 128) || (waves_eff(128) > waves_eff(256) + 0.08);
-  if (use128) {
-    return out_fp32 ? launch_gemm<128, true>(a, lda, b, ldb, C, ldc, r, ldr, M, N, K, s)
-                    : launch_gemm<128, false>(a, lda, b, ldb, C, ldc, r, ldr, M, N, K, s);
+  GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1};
+  if (prefer_bn128(M, N)) {
+    return out_fp32 ? launch_gemm<128, true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s)
+                    : launch_gemm<128, false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   }
-  return out_fp32 ? launch_gemm<256, true>(a, lda, b, ldb, C, ldc, r, ldr, M, N, K, s)
-                  : launch_gemm<256, false>(a, lda, b, ldb, C, ldc, r, ldr, M, N, K, s);
+  return out_fp32 ? launch_gemm<256, true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s)
+                  : launch_gemm<256, false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
+}
+
+extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N,
+                                      int K, const float* rope_cos, const float* rope_sin, int rope_cols, int hd, int S,
+                                      void* stream) {
+  int rc = check_gemm_args(A, lda, B, ldb, C, ldc, nullptr, 0, M, N, K);
+  if (rc) return rc;
+  FVQA_REQUIRE((hd == 64 || hd == 128) && rope_cols % hd == 0 && rope_cols <= N && S > 0 && rope_cos && rope_sin,
+               FVQA_ERR_INVALID_ARG, "gemm_rope: bad rope arguments (hd=%d rope_cols=%d S=%d)", hd, rope_cols, S);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bf16* a = reinterpret_cast<const bf16*>(A);
+  const bf16* b = reinterpret_cast<const bf16*>(B);
+  GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S};
+  if (prefer_bn128(M, N)) return launch_gemm<128, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
+  return launch_gemm<256, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
 }

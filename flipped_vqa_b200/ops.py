@@ -53,26 +53,30 @@ def _chk(t: torch.Tensor, dtype, name: str):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous cuda {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}"
 
 
-# ------------------------------------------------------------------ RMSNorm
+# ------------------------------------------------------------------ RMSNorm (fp32 residual stream in, bf16 GEMM operand out)
+F32 = torch.float32
+
+
 def rmsnorm_fwd(x, w, eps: float, y=None, rstd=None):
-    _chk(x, BF16, "x"); _chk(w, BF16, "w")
+    _chk(x, F32, "x"); _chk(w, BF16, "w")
     rows, dim = x.shape
-    y = torch.empty_like(x) if y is None else y
+    y = torch.empty(rows, dim, dtype=BF16, device=x.device) if y is None else y
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if rstd is None else rstd
     check(_lib.lib().fvqa_rmsnorm_fwd(ptr(x), ptr(w), ptr(y), ptr(rstd), rows, dim, eps, stream()), "rmsnorm_fwd")
     return y, rstd
 
 
-def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None):
-    _chk(dy, BF16, "dy"); _chk(x, BF16, "x")
+def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None, dx_bf16=None):
+    """Returns (dx fp32, dx_bf16). dx = dres + rmsnorm'(x).dy"""
+    _chk(dy, BF16, "dy"); _chk(x, F32, "x")
     rows, dim = x.shape
-    dx = torch.empty_like(x) if dx is None else dx
-    check(_lib.lib().fvqa_rmsnorm_bwd(ptr(dy), ptr(x), ptr(w), ptr(rstd), ptr(dres), ptr(dx), rows, dim, stream()), "rmsnorm_bwd")
-    return dx
+    dx = torch.empty(rows, dim, dtype=F32, device=x.device) if dx is None else dx
+    check(_lib.lib().fvqa_rmsnorm_bwd(ptr(dy), ptr(x), ptr(w), ptr(rstd), ptr(dres), ptr(dx), ptr(dx_bf16), rows, dim, stream()), "rmsnorm_bwd")
+    return dx, dx_bf16
 
 
 def rmsnorm_gather_fwd(x, idx, w, eps: float, y=None, rstd=None):
-    _chk(x, BF16, "x"); _chk(idx, torch.int32, "idx")
+    _chk(x, F32, "x"); _chk(idx, torch.int32, "idx")
     rows, dim = idx.numel(), x.shape[-1]
     y = torch.empty(rows, dim, dtype=BF16, device=x.device) if y is None else y
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if rstd is None else rstd
@@ -80,9 +84,9 @@ def rmsnorm_gather_fwd(x, idx, w, eps: float, y=None, rstd=None):
     return y, rstd
 
 
-def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx):
+def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dx_bf16=None):
     rows, dim = idx.numel(), x.shape[-1]
-    check(_lib.lib().fvqa_rmsnorm_scatter_bwd(ptr(dy), ptr(x), ptr(idx), ptr(w), ptr(rstd), ptr(dx), rows, dim, stream()), "rmsnorm_scatter_bwd")
+    check(_lib.lib().fvqa_rmsnorm_scatter_bwd(ptr(dy), ptr(x), ptr(idx), ptr(w), ptr(rstd), ptr(dx), ptr(dx_bf16), rows, dim, stream()), "rmsnorm_scatter_bwd")
     return dx
 
 
@@ -116,6 +120,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else BF16, device=a.device)
     assert out.stride(-1) == 1 and out.dtype == (torch.float32 if out_fp32 else BF16)
+    assert residual is None or (residual.dtype == out.dtype and residual.stride(-1) == 1)
     ldr = residual.stride(0) if residual is not None else 0
     tm = GEMM_TIMER
     if tm is not None and tm.active:
@@ -123,6 +128,24 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         e0.record()
     check(_lib.lib().fvqa_gemm_bf16_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), ptr(residual), ldr,
                                        M, N, K, 1 if out_fp32 else 0, stream()), "gemm_bf16_nt")
+    if tm is not None and tm.active:
+        e1.record()
+        tm.records.append((e0, e1, 2.0 * M * N * K))
+    return out
+
+
+def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """QKV projection with RoPE applied to the q|k columns in the GEMM epilogue (bf16 out)."""
+    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty(M, N, dtype=BF16, device=a.device) if out is None else out
+    tm = GEMM_TIMER
+    if tm is not None and tm.active:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.lib().fvqa_gemm_bf16_nt_rope(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
+                                            ptr(cos), ptr(sin), rope_cols, hd, S, stream()), "gemm_bf16_nt_rope")
     if tm is not None and tm.active:
         e1.record()
         tm.records.append((e0, e1, 2.0 * M * N * K))
@@ -179,7 +202,7 @@ def visual_proj_bwd(dvf2d, video2d, dwv=None):
 
 def build_h0_fwd(tok_emb, ids, labels, vstart, seq_video, qav_index, vf32, temporal, n_seq, S, F, h0=None):
     dim = tok_emb.shape[1]
-    h0 = torch.empty(n_seq * S, dim, dtype=BF16, device=tok_emb.device) if h0 is None else h0
+    h0 = torch.empty(n_seq * S, dim, dtype=torch.float32, device=tok_emb.device) if h0 is None else h0
     check(_lib.lib().fvqa_build_h0_fwd(ptr(tok_emb), ptr(ids), ptr(labels), ptr(vstart), ptr(seq_video), ptr(qav_index), ptr(vf32),
                                        ptr(temporal), ptr(h0), n_seq, S, dim, F, stream()), "build_h0_fwd")
     return h0

@@ -212,15 +212,16 @@ class StepEngine:
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
             _, rstd1 = ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
-            qkv = ops.gemm_nt(xn, w.wqkv, out=None if save else qkv_b)
+            # Wq|Wk|Wv in one GEMM, RoPE applied to q|k in its epilogue (`model.py:89,96`)
+            qkv = ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=None if save else qkv_b)
             akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])          # adapter K|V, no RoPE (`model.py:99-100`)
             o, lse = ops.attn_fwd(qkv, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F,
                                   out=None if save else o_b)
-            h = ops.gemm_nt(o, w.wo, residual=x)                                   # h = x + attn  (`model.py:185`)
+            h = ops.gemm_nt(o, w.wo, residual=x, out_fp32=True)                    # h = x + attn  (`model.py:185`), fp32 stream
             _, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
             g = ops.gemm_nt(xn, w.w13, out=None if save else g_b)
             ops.swiglu_fwd(g, c)
-            x_next = ops.gemm_nt(c, w.w2, residual=h)                              # out = h + ffn (`model.py:186`)
+            x_next = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)               # out = h + ffn (`model.py:186`)
             if save:
                 sv.x.append(x); sv.qkv.append(qkv); sv.akv.append(akv); sv.o.append(o); sv.lse.append(lse)
                 sv.h.append(h); sv.g.append(g); sv.rstd1.append(rstd1); sv.rstd2.append(rstd2)
@@ -285,7 +286,9 @@ class StepEngine:
         T, n_seq, dev = plan.T, plan.n_seq, self.device
         L = len(layers)
         x_final = sv.x[L]
-        dx = torch.zeros(T, d, dtype=BF16, device=dev)
+        # gradient of the residual stream: fp32 master + bf16 copy (A operand of the next dX GEMM)
+        dx = torch.zeros(T, d, dtype=torch.float32, device=dev)
+        dx_bf = torch.zeros(T, d, dtype=BF16, device=dev)
         gidx = {"vqa": 0, "vaq": 1, "qav": 2}
         # --- heads backward
         if sv.ce is not None:
@@ -301,41 +304,44 @@ class StepEngine:
                                gscale[gidx[k]:gidx[k] + 1], 1.0 / n, dlogits=dlogits[off:off + n])
                 off += n
             dhn = ops.gemm_nt(dlogits, out_w_t)                                     # dH = dlogits . W_out
-            ops.rmsnorm_scatter_bwd(dhn, x_final, plan.ce_rows, norm_w, ce["rstd"], dx)
+            ops.rmsnorm_scatter_bwd(dhn, x_final, plan.ce_rows, norm_w, ce["rstd"], dx, dx_bf)
         dvf_qav = None
         if sv.qav is not None:
             q = sv.qav
             dhnq, dvf_qav = ops.qav_loss_bwd(q["hn"], sv.vf32, plan.q_vid, plan.q_tgt, q["prob"], gscale[2:3],
                                              1.0 / plan.q_count, self.tau, plan.n_video, F)
-            ops.rmsnorm_scatter_bwd(dhnq, x_final, plan.q_rows, norm_w, q["rstd"], dx)
+            ops.rmsnorm_scatter_bwd(dhnq, x_final, plan.q_rows, norm_w, q["rstd"], dx, dx_bf)
         # --- layers, last to first
         if self._attn_ws is None or self._attn_ws.numel() < ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A):
             self._attn_ws = torch.empty(ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
         dc = torch.empty(T, hid, dtype=BF16, device=dev)
         dg = torch.empty(T, 2 * hid, dtype=BF16, device=dev)
         dtmp = torch.empty(T, d, dtype=BF16, device=dev)
-        dh = torch.empty(T, d, dtype=BF16, device=dev)
+        dh = torch.empty(T, d, dtype=torch.float32, device=dev)
+        dh_bf = torch.empty(T, d, dtype=BF16, device=dev)
         dqkv = torch.empty(T, 3 * d, dtype=BF16, device=dev)
         dakv = torch.empty(A, 2 * d, dtype=torch.float32, device=dev)
         dakv_bf = torch.empty(A, 2 * d, dtype=BF16, device=dev)
-        dx_next = torch.empty(T, d, dtype=BF16, device=dev)
+        dx_next = torch.empty(T, d, dtype=torch.float32, device=dev)
+        dx_next_bf = torch.empty(T, d, dtype=BF16, device=dev)
         for l in range(L - 1, -1, -1):
             w = layers[l]
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
-            ops.gemm_nt(dx, w.w2_t, out=dc)                                        # d(silu(a)*b) = dout . W2
+            ops.gemm_nt(dx_bf, w.w2_t, out=dc)                                     # d(silu(a)*b) = dout . W2
             ops.swiglu_bwd(dc, sv.g[l], dg)
             ops.gemm_nt(dg, w.w13_t, out=dtmp)                                     # d(ffn_norm out) = [da|db] . [W1;W3]
-            ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh)
-            ops.gemm_nt(dh, w.wo_t, out=dtmp)                                      # d(attn out) = dh . Wo
+            ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_bf16=dh_bf)
+            ops.gemm_nt(dh_bf, w.wo_t, out=dtmp)                                   # d(attn out) = dh . Wo
             ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dtmp,
                          n_seq, S, H, hd, A, F, dqkv=dqkv, dakv=dakv, dgate1=grads.gate1[l], dgate2=grads.gate2[l], ws=self._attn_ws)
             ops.gemm_nt(dqkv, w.wqkv_t, out=dtmp)                                  # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
-            ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next)
+            ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next, dx_bf16=dx_next_bf)
             # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l)
             ops.f32_to_bf16(dakv, dakv_bf)
             ops.gemm_nt(dakv_bf, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
             dx, dx_next = dx_next, dx
+            dx_bf, dx_next_bf = dx_next_bf, dx_bf
             if on_layer_done is not None:
                 on_layer_done(l)
         if ops.GEMM_TIMER is not None:

@@ -37,20 +37,21 @@ const char* fvqa_last_error(void);
 /* One-time per-process setup (kernel attributes, driver entry points). Idempotent. */
 int fvqa_init(void);
 
-/* ---- RMSNorm (llama/model.py:31-42). y = bf16( bf16(x * rstd) * w ); rstd saved in fp32. -------- */
-int fvqa_rmsnorm_fwd(const fvqa_bf16* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd,
+/* ---- RMSNorm (llama/model.py:31-42) on the fp32 residual stream. y = bf16(x * rstd * w); rstd saved. -- */
+int fvqa_rmsnorm_fwd(const float* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd,
                      int rows, int dim, float eps, void* stream);
-/* dX only (weight is frozen). dx = (dres ? dres : 0) + d rmsnorm(x)/dx . dy */
-int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const fvqa_bf16* w, const float* rstd,
-                     const fvqa_bf16* dres, fvqa_bf16* dx, int rows, int dim, void* stream);
+/* dX only (weight is frozen). dx = (dres ? dres : 0) + d rmsnorm(x)/dx . dy   (fp32);
+ * dx_bf16 (optional) receives the same values rounded to bf16 = A operand of the next GEMM. */
+int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const float* x, const fvqa_bf16* w, const float* rstd,
+                     const float* dres, float* dx, fvqa_bf16* dx_bf16, int rows, int dim, void* stream);
 /* Final norm applied only to the gathered rows `idx[i]` (>=0) of x; rows with idx<0 give zeros.
  * (llama/model.py:347,352,358 restricted to the positions the losses read.) */
-int fvqa_rmsnorm_gather_fwd(const fvqa_bf16* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
+int fvqa_rmsnorm_gather_fwd(const float* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
                             float* rstd, int rows_out, int dim, float eps, void* stream);
-/* dx[idx[i]] += rmsnorm backward of row i (dx must be zero-initialised by the caller; each source
+/* dx[idx[i]] = rmsnorm backward of row i (dx / dx_bf16 zero-initialised by the caller; each source
  * row may appear at most once per call). */
-int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const fvqa_bf16* x, const int32_t* idx,
-                             const fvqa_bf16* w, const float* rstd, fvqa_bf16* dx,
+int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const float* x, const int32_t* idx,
+                             const fvqa_bf16* w, const float* rstd, float* dx, fvqa_bf16* dx_bf16,
                              int rows_out, int dim, void* stream);
 
 /* ---- SwiGLU (llama/model.py:142). g = [rows, 2*hid] holding a=W1x | b=W3x; c = silu(a)*b. -------- */
@@ -60,16 +61,23 @@ int fvqa_swiglu_bwd(const fvqa_bf16* dc, const fvqa_bf16* g, fvqa_bf16* dg, int 
 /* ---- bf16 GEMM on tcgen05/TMEM fed by TMA (replaces every frozen nn.Linear: llama/model.py:89,
  *      99-100,128,142,348,354 and their dX-only backward). C[M,N] = A[M,K] * B[N,K]^T (+ R[M,N]).
  *      A, B bf16 K-contiguous; fp32 accumulation in TMEM. out_fp32 != 0 -> C is float, else bf16.
- *      R (optional residual, bf16, leading dimension ldr) is added before the final rounding.
+ *      R (optional residual, SAME dtype as C, leading dimension ldr) is added in fp32 before the store:
+ *      with out_fp32 this is the fp32 residual stream  h = x + attn,  out = h + ffn (model.py:185-186).
  *      Requirements: K % 64 == 0, N % 8 == 0, lda/ldb/ldc/ldr % 8 == 0, 16-byte aligned pointers. */
 int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, void* C, int ldc,
-                      const fvqa_bf16* R, int ldr, int M, int N, int K, int out_fp32, void* stream);
+                      const void* R, int ldr, int M, int N, int K, int out_fp32, void* stream);
+/* Same GEMM (bf16 out) with RoPE folded into the epilogue for the fused Wq|Wk|Wv projection
+ * (llama/model.py:89 + :61-67): columns [0, rope_cols) are q|k heads of width hd whose interleaved
+ * pairs are rotated by the angle of position (row % S); rope_cos/rope_sin are [>=S, hd/2] fp32. */
+int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc,
+                           int M, int N, int K, const float* rope_cos, const float* rope_sin,
+                           int rope_cols, int hd, int S, void* stream);
 
 /* ---- fused attention (llama/model.py:61-67 RoPE, :87-126 attention incl. adapter branch). --------
- * qkv  [n_seq*S, 3*H*hd] bf16, PRE-RoPE (q | k | v); RoPE (interleaved pairs) is applied on load.
+ * qkv  [n_seq*S, 3*H*hd] bf16 (q | k | v) with q,k ALREADY rotated (fvqa_gemm_bf16_nt_rope).
  * akv  [>=A rows, ld akv_ld] bf16: adapter keys (cols 0..H*hd) | adapter values (cols H*hd..2*H*hd),
  *      no RoPE (model.py:99-100), shared by every sequence.
- * rope [S, hd/2] fp32 cos and sin tables (model.py:45-50).
+ * rope [S, hd/2] fp32 cos and sin tables (model.py:45-50); used by backward for the inverse rotation.
  * gate1/gate2 [H] fp32 (model.py:84-85). vstart[n_seq] int32: video_start of the sequence, or -1
  * for "no bias" sequences (QAV, model.py:121-122). max_feats = F.
  * out  [n_seq*S, H*hd] bf16 = tanh(gate1)*softmax(q ka^T/sqrt(hd)) va + softmax(q k^T/sqrt(hd)+causal+bias) v
@@ -98,13 +106,14 @@ int fvqa_visual_proj_bwd(const float* dvf, const float* video, float* dwv, int r
 /* h0[n*S+p, :] for every sequence n:
  *   mode vstart[n] >= 0 (VQA/VAQ): tok_emb[ids] except positions [vs, vs+F) <- bf16(vf32[vid[n],f] + temporal[f])
  *   mode vstart[n] <  0 (QAV):     tok_emb[ids] * (labels[n,p] < 0), then += bf16(vf32+temporal) at qav_index[vid[n], f]
- * ids/labels [n_seq, S] int32; seq_video[n] = video sample of sequence n; qav_index [B, F] int32. */
+ * ids/labels [n_seq, S] int32; seq_video[n] = video sample of sequence n; qav_index [B, F] int32.
+ * h0 is the fp32 residual stream (values are bf16-representable: embeddings / bf16(vf+temporal)). */
 int fvqa_build_h0_fwd(const fvqa_bf16* tok_emb, const int32_t* ids, const int32_t* labels,
                       const int32_t* vstart, const int32_t* seq_video, const int32_t* qav_index,
-                      const float* vf32, const float* temporal, fvqa_bf16* h0,
+                      const float* vf32, const float* temporal, float* h0,
                       int n_seq, int S, int dim, int max_feats, void* stream);
 /* dvf[B, F, d] (fp32) = sum over sequences of dh0 at the video slots. Overwrites dvf. */
-int fvqa_build_h0_bwd(const fvqa_bf16* dh0, const int32_t* vstart, const int32_t* seq_video,
+int fvqa_build_h0_bwd(const float* dh0, const int32_t* vstart, const int32_t* seq_video,
                       const int32_t* qav_index, float* dvf, int n_seq, int n_video, int S, int dim,
                       int max_feats, void* stream);
 /* dtemporal[F, d] = sum_b dvf[b] (overwritten); then dvf[b] += dvf_qav[b] in place (dvf_qav may be NULL). */

@@ -23,40 +23,44 @@ def bf16_randn(*shape, std=1.0, seed=0):
 # ------------------------------------------------------------------ RMSNorm / SwiGLU
 @pytest.mark.parametrize("rows,dim", [(7, 256), (1024, 4096), (33, 5120)])
 def test_rmsnorm_fwd_bwd(fvqa_lib, rows, dim):
+    """fp32 residual stream in, bf16 GEMM operand out; backward returns fp32 dx (+ bf16 copy)."""
     from flipped_vqa_b200 import ops
-    x = bf16_randn(rows, dim, seed=1)
+    x = bf16_randn(rows, dim, seed=1).float() + 1e-3 * torch.randn(rows, dim, device="cuda")
     w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(torch.bfloat16)
     dy = bf16_randn(rows, dim, seed=2)
-    res = bf16_randn(rows, dim, seed=3)
+    res = torch.randn(rows, dim, device="cuda")
     y, rstd = ops.rmsnorm_fwd(x, w, 1e-6)
-    xr = x.float().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
     yr = O.rmsnorm(xr, w.float(), 1e-6)
-    # bit-level agreement is not expected (two bf16 roundings); 1 bf16 ulp ~ 0.4 %
-    assert relerr(y, yr) < 4e-3
+    assert relerr(y, yr) < 3e-3                 # one bf16 rounding of the output
     (yr * dy.float()).sum().backward()
-    dx = ops.rmsnorm_bwd(dy, x, w, rstd, dres=res)
-    assert relerr(dx, xr.grad + res.float()) < 4e-3
-    dx2 = ops.rmsnorm_bwd(dy, x, w, rstd)
-    assert relerr(dx2, xr.grad) < 4e-3
+    dxb = torch.empty(rows, dim, dtype=torch.bfloat16, device="cuda")
+    dx, _ = ops.rmsnorm_bwd(dy, x, w, rstd, dres=res, dx_bf16=dxb)
+    assert relerr(dx, xr.grad + res) < 1e-5
+    assert relerr(dxb, xr.grad + res) < 3e-3
+    dx2, _ = ops.rmsnorm_bwd(dy, x, w, rstd)
+    assert relerr(dx2, xr.grad) < 1e-5
 
 
 def test_rmsnorm_gather_scatter(fvqa_lib):
     from flipped_vqa_b200 import ops
     rows, dim = 300, 512
-    x = bf16_randn(rows, dim, seed=4)
+    x = torch.randn(rows, dim, device="cuda")
     w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(torch.bfloat16)
     idx = torch.tensor([5, 17, -1, 299, 0, -1, 42], dtype=torch.int32, device="cuda")
     y, rstd = ops.rmsnorm_gather_fwd(x, idx, w, 1e-6)
     valid = idx >= 0
-    yr = O.rmsnorm(x[idx[valid].long()].float(), w.float(), 1e-6)
-    assert relerr(y[valid], yr) < 4e-3
+    yr = O.rmsnorm(x[idx[valid].long()], w.float(), 1e-6)
+    assert relerr(y[valid], yr) < 3e-3
     assert float(y[~valid].float().abs().max()) == 0.0
     dy = bf16_randn(idx.numel(), dim, seed=5)
     dx = torch.zeros_like(x)
-    ops.rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx)
-    xr = x.float().requires_grad_(True)
+    dxb = torch.zeros(rows, dim, dtype=torch.bfloat16, device="cuda")
+    ops.rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dxb)
+    xr = x.clone().requires_grad_(True)
     (O.rmsnorm(xr[idx[valid].long()], w.float(), 1e-6) * dy[valid].float()).sum().backward()
-    assert relerr(dx, xr.grad) < 4e-3
+    assert relerr(dx, xr.grad) < 1e-5
+    assert relerr(dxb, xr.grad) < 3e-3
 
 
 @pytest.mark.parametrize("rows,hid", [(5, 768), (1024, 11008)])
@@ -67,7 +71,7 @@ def test_swiglu(fvqa_lib, rows, hid):
     c = ops.swiglu_fwd(g)
     gr = g.float().requires_grad_(True)
     cr = O.swiglu(gr[:, :hid], gr[:, hid:])
-    assert relerr(c, cr) < 4e-3
+    assert relerr(c, cr) < 3e-3
     (cr * dc.float()).sum().backward()
     dg = ops.swiglu_bwd(dc, g)
     assert relerr(dg, gr.grad) < 4e-3
@@ -93,6 +97,27 @@ def test_gemm_nt(fvqa_lib, M, N, K):
     r = bf16_randn(M, N, seed=12)
     cr = ops.gemm_nt(a, b, residual=r)
     assert relerr(cr, ref + r.float()) < 5e-3
+    r32 = torch.randn(M, N, device="cuda")            # fp32 residual stream (h = x + attn, out = h + ffn)
+    cr32 = ops.gemm_nt(a, b, residual=r32, out_fp32=True)
+    assert relerr(cr32, ref + r32) < 2e-4
+
+
+@pytest.mark.parametrize("S,H,hd,B", [(48, 2, 64, 3), (128, 4, 128, 2)])
+def test_gemm_rope_epilogue(fvqa_lib, S, H, hd, B):
+    """QKV projection with RoPE folded into the epilogue == plain projection followed by the oracle's
+    apply_rope on the q|k parts (llama/model.py:61-67,89-96)."""
+    from flipped_vqa_b200 import ops
+    d = H * hd
+    x = bf16_randn(B * S, d, seed=17)
+    w = bf16_randn(3 * d, d, std=0.05, seed=18)
+    cos, sin = O.rope_table(hd, S)
+    cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    out = ops.gemm_nt_rope(x, w, cos, sin, 2 * d, hd, S)
+    ref = (x.float() @ w.float().t()).view(B, S, 3, H, hd)
+    q = O.apply_rope(ref[:, :, 0], cos, sin)
+    k = O.apply_rope(ref[:, :, 1], cos, sin)
+    ref = torch.stack([q, k, ref[:, :, 2]], dim=2).reshape(B * S, 3 * d)
+    assert relerr(out, ref) < 5e-3
 
 
 def test_gemm_strided_views(fvqa_lib):
@@ -136,6 +161,13 @@ def _attn_case(n_seq, S, H, hd, A, F, vstarts, seed):
     return qkv, akv, gate1, gate2, cos, sin, vstart, dout
 
 
+def _rotate_qk(qkv, cos, sin, n_seq, S, H, hd):
+    x = qkv.float().view(n_seq, S, 3, H, hd)
+    q = O.apply_rope(x[:, :, 0], cos, sin)
+    k = O.apply_rope(x[:, :, 1], cos, sin)
+    return torch.stack([q, k, x[:, :, 2]], dim=2).reshape(n_seq * S, 3 * H * hd).to(torch.bfloat16).contiguous()
+
+
 def _attn_ref(qkv, akv, gate1, gate2, cos, sin, vstarts, dout, n_seq, S, H, hd, A, F):
     D = H * hd
     qkv_r = qkv.float().requires_grad_(True)
@@ -166,11 +198,12 @@ def test_attention_fwd_bwd(fvqa_lib, n_seq, S, H, hd, vstarts):
     from flipped_vqa_b200 import ops
     A, F = 10, 10
     qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, vstarts, seed=20)
-    out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
+    qkv_rot = _rotate_qk(qkv, cos, sin, n_seq, S, H, hd)          # the kernel receives rotated q|k (GEMM epilogue)
+    out, lse = ops.attn_fwd(qkv_rot, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
     ref_out, ref_dqkv, ref_dakv, ref_dg1, ref_dg2 = _attn_ref(qkv, akv, gate1, gate2, cos, sin, vstarts, dout, n_seq, S, H, hd, A, F)
     assert relerr(out, ref_out) < 1e-2, f"out {relerr(out, ref_out)}"
-    dqkv, dakv, dg1, dg2 = ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
-    D = H * hd
+    dqkv, dakv, dg1, dg2 = ops.attn_bwd(qkv_rot, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
+    D = H * hd                                                   # dq|dk come back inverse-rotated: gradients of the raw projections
     for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
         e = relerr(dqkv[:, sl], ref_dqkv[:, sl])
         assert e < 2e-2, f"{name} relerr {e}"
@@ -183,6 +216,7 @@ def test_attention_deterministic(fvqa_lib):
     from flipped_vqa_b200 import ops
     n_seq, S, H, hd, A, F = 3, 128, 2, 128, 10, 10
     qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, [18, 18, -1], seed=21)
+    qkv = _rotate_qk(qkv, cos, sin, n_seq, S, H, hd)
     out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
     r1 = ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
     r2 = ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
@@ -221,10 +255,10 @@ def test_visual_proj_and_h0(fvqa_lib):
     q = ref[2 * B:] * (~(labels[2 * B:] >= 0))[..., None]
     q = q.scatter_add(1, qav_index.long()[..., None].expand(-1, -1, d), video_feature)
     ref[2 * B:] = q
-    assert torch.equal(h0.view(n_seq, S, d), ref)
-    dh0 = bf16_randn(n_seq * S, d, seed=32)
+    assert h0.dtype == torch.float32 and torch.equal(h0.view(n_seq, S, d), ref.float())
+    dh0 = torch.randn(n_seq * S, d, device="cuda", generator=g)
     dvf = ops.build_h0_bwd(dh0, vstart, seq_video, qav_index, n_seq, B, S, F)
-    dh = dh0.float().view(n_seq, S, d)
+    dh = dh0.view(n_seq, S, d)
     ref_dvf = dh[:B, 12:12 + F] + dh[B:2 * B, 12:12 + F] + torch.gather(dh[2 * B:], 1, qav_index.long()[..., None].expand(-1, -1, d))
     assert relerr(dvf, ref_dvf.reshape(B * F, d)) < 1e-6
     dq = torch.randn(B * F, d, device="cuda", generator=g)
