@@ -11,15 +11,14 @@
 // adapter dK_a/dV_a partials); a tiny kernel reduces the per-CTA partials in a fixed order.
 //
 // Round-1 implementation: warp-level mma.sync.m16n8k16 bf16 tensor-core tiles fed from padded
-// shared memory through ldmatrix (attention is ~0.5 % of the step's FLOPs; the tcgen05 budget
-// went to the GEMM first).
+// shared memory through ldmatrix; 8-warp CTAs own 128 query rows (or 128 keys) and stream the other
+// operand in 64-row tiles through a cp.async double buffer (attention is ~0.5 % of the step's FLOPs;
+// the tcgen05 budget went to the GEMM first).
 #include "common.cuh"
 
 namespace fvqa {
 
-constexpr int AT_THREADS = 128;
-constexpr int AT_BM = 64;   // query rows per CTA (4 warps x 16)
-constexpr int AT_BN = 64;   // keys per tile
+constexpr int AT_THREADS = 256;
 constexpr int AT_AP = 16;   // adapter keys padded to one MMA k-block
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -177,98 +176,146 @@ __device__ __forceinline__ void store_tile_warp(bf16* stage, float (&acc)[HD / 8
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------------------------
+// asynchronous tile loads (cp.async, 16 B per request; rows past `limit` are zero-filled)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int HD, int ROWS, int NT>
+__device__ __forceinline__ void load_tile_async(bf16* s, const bf16* __restrict__ g, long stride, int row0, int limit) {
+  constexpr int LD = HD + 8;
+  constexpr int VPR = HD / 8;
+  const uint32_t sbase = smem_u32(s);
+#pragma unroll
+  for (int idx = threadIdx.x; idx < ROWS * VPR; idx += NT) {
+    const int r = idx / VPR, v = idx - r * VPR;
+    const int pos = row0 + r;
+    const bool ok = pos < limit;
+    cp_async16(sbase + static_cast<uint32_t>((r * LD + v * 8) * 2), g + static_cast<long>(ok ? pos : 0) * stride + v * 8, ok);
+  }
+}
+
 struct AttnParams {
   const bf16* qkv; const bf16* akv; int akv_ld;
   const float* cosT; const float* sinT; const float* gate1; const float* gate2; const int32_t* vstart;
   bf16* out; float* lse;            // fwd outputs / bwd inputs
   const bf16* dout; bf16* dqkv;     // bwd
   float* ws_dx; float* ws_gate; float* ws_akv;
-  int n_seq, S, H, A, F, qtiles;
+  int n_seq, S, H, A, F, qblocks;   // qblocks = ceil(S / 128)
 };
 
+constexpr int AT_NT = 256;        // threads per CTA (8 warps)
+constexpr int AT_QB = 128;        // query rows (pass A / fwd) or keys (pass B) owned by a CTA
+constexpr int AT_T = 64;          // streamed tile (keys in fwd / pass A, query rows in pass B)
+
 // ---------------------------------------------------------------------------------------------
-// forward
+// forward: CTA = (128 query rows, head, sequence); K/V tiles of 64 keys double-buffered
 // ---------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_NT) attn_fwd_kernel(const AttnParams p) {
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sK = sQ + AT_BM * LD;
-  bf16* sV = sK + AT_BN * LD;
-  bf16* sKa = sV + AT_BN * LD;
+  bf16* sK = sQ + AT_QB * LD;            // [2][64][LD]
+  bf16* sV = sK + 2 * AT_T * LD;         // [2][64][LD]
+  bf16* sKa = sV + 2 * AT_T * LD;
   bf16* sVa = sKa + AT_AP * LD;
-  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = p.S, D = p.H * HD;
   const long qkv_stride = 3L * D;
   const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
   const bf16* kbase = qbase + D;
   const bf16* vbase = qbase + 2 * D;
-  const int r0 = qt * AT_BM;
+  const int r0 = qb * AT_QB;
   const float scale2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
   const int vs = p.vstart[n];
   const float bias2 = (vs >= 0) ? p.gate2[h] * LOG2E : 0.f;
   const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;   // rows >= this get the bias
   const int bias_c0 = vs, bias_c1 = vs + p.F;                  // columns [c0, c1)
+  const int last_key = min(S, r0 + AT_QB) - 1;                 // causal: keys beyond the block's last row are never needed
+  const int n_tiles = last_key / AT_T + 1;
 
-  load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, r0, S, nullptr, nullptr);
-  load_tile<HD, AT_AP, false>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
-  load_tile<HD, AT_AP, false>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+  load_tile_async<HD, AT_QB, AT_NT>(sQ, qbase, qkv_stride, r0, S);
+  load_tile_async<HD, AT_AP, AT_NT>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A);
+  load_tile_async<HD, AT_AP, AT_NT>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A);
+  load_tile_async<HD, AT_T, AT_NT>(sK, kbase, qkv_stride, 0, S);
+  load_tile_async<HD, AT_T, AT_NT>(sV, vbase, qkv_stride, 0, S);
+  cp_async_commit();
+  if (n_tiles > 1) {
+    load_tile_async<HD, AT_T, AT_NT>(sK + AT_T * LD, kbase, qkv_stride, AT_T, S);
+    load_tile_async<HD, AT_T, AT_NT>(sV + AT_T * LD, vbase, qkv_stride, AT_T, S);
+  }
+  cp_async_commit();
 
   float o[HD / 8][4];
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const int row_a = r0 + warp * 16 + gq;   // this thread's rows: row_a and row_a + 8
+  const int warp_last_row = r0 + warp * 16 + 15;
   const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV), sKa_u = smem_u32(sKa), sVa_u = smem_u32(sVa);
 
-  for (int j = 0; j <= qt; ++j) {
-    __syncthreads();   // previous tile fully consumed (also orders the initial loads)
-    load_tile<HD, AT_BN, false>(sK, kbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
-    load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
+  for (int j = 0; j < n_tiles; ++j) {
+    cp_async_wait<1>();
     __syncthreads();
-    float s[AT_BN / 8][4];
+    const uint32_t kb_u = sK_u + static_cast<uint32_t>((j & 1) * AT_T * LD * 2);
+    const uint32_t vb_u = sV_u + static_cast<uint32_t>((j & 1) * AT_T * LD * 2);
+    if (j * AT_T <= warp_last_row) {       // warp-uniform causal skip
+      float s[AT_T / 8][4];
 #pragma unroll
-    for (int i = 0; i < AT_BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
-    warp_mma_nt<AT_BN / 8, HD, LD>(s, sQ_u, warp * 16, sK_u, 0);
-    float mx[2] = {-INFINITY, -INFINITY};
+      for (int i = 0; i < AT_T / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+      warp_mma_nt<AT_T / 8, HD, LD>(s, sQ_u, warp * 16, kb_u, 0);
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < AT_BN / 8; ++nt) {
+      for (int nt = 0; nt < AT_T / 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int row = row_a + 8 * (e >> 1);
-        const int col = j * AT_BN + nt * 8 + 2 * t + (e & 1);
-        float v = s[nt][e] * scale2;
-        if (row >= bias_row0 && col >= bias_c0 && col < bias_c1) v += bias2;
-        if (col > row) v = -INFINITY;
-        s[nt][e] = v;
-        mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        for (int e = 0; e < 4; ++e) {
+          const int row = row_a + 8 * (e >> 1);
+          const int col = j * AT_T + nt * 8 + 2 * t + (e & 1);
+          float v = s[nt][e] * scale2;
+          if (row >= bias_row0 && col >= bias_c0 && col < bias_c1) v += bias2;
+          if (col > row) v = -INFINITY;
+          s[nt][e] = v;
+          mx[e >> 1] = fmaxf(mx[e >> 1], v);
+        }
       }
-    }
-    float alpha[2], m_new[2];
+      float alpha[2], m_new[2];
 #pragma unroll
-    for (int hh = 0; hh < 2; ++hh) {
-      m_new[hh] = fmaxf(m_run[hh], quad_max(mx[hh]));
-      alpha[hh] = (m_run[hh] == -INFINITY) ? 0.f : exp2f(m_run[hh] - m_new[hh]);
-      m_run[hh] = m_new[hh];
-      l_run[hh] *= alpha[hh];
-    }
-#pragma unroll
-    for (int i = 0; i < HD / 8; ++i) { o[i][0] *= alpha[0]; o[i][1] *= alpha[0]; o[i][2] *= alpha[1]; o[i][3] *= alpha[1]; }
-    uint32_t pf[AT_BN / 16][4];
-#pragma unroll
-    for (int nt = 0; nt < AT_BN / 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float pv = (m_new[e >> 1] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_new[e >> 1]);
-        s[nt][e] = pv;
-        l_run[e >> 1] += pv;
+      for (int hh = 0; hh < 2; ++hh) {
+        m_new[hh] = fmaxf(m_run[hh], quad_max(mx[hh]));
+        alpha[hh] = (m_run[hh] == -INFINITY) ? 0.f : exp2f(m_run[hh] - m_new[hh]);
+        m_run[hh] = m_new[hh];
+        l_run[hh] *= alpha[hh];
       }
-    }
 #pragma unroll
-    for (int kb = 0; kb < AT_BN / 16; ++kb) c_to_a(pf[kb], s[2 * kb], s[2 * kb + 1]);
-    warp_mma_ra_t<HD / 8, AT_BN / 16, LD>(o, pf, sV_u, 0, 0);
+      for (int i = 0; i < HD / 8; ++i) { o[i][0] *= alpha[0]; o[i][1] *= alpha[0]; o[i][2] *= alpha[1]; o[i][3] *= alpha[1]; }
+      uint32_t pf[AT_T / 16][4];
+#pragma unroll
+      for (int nt = 0; nt < AT_T / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pv = (m_new[e >> 1] == -INFINITY) ? 0.f : exp2f(s[nt][e] - m_new[e >> 1]);
+          s[nt][e] = pv;
+          l_run[e >> 1] += pv;
+        }
+      }
+#pragma unroll
+      for (int kb = 0; kb < AT_T / 16; ++kb) c_to_a(pf[kb], s[2 * kb], s[2 * kb + 1]);
+      warp_mma_ra_t<HD / 8, AT_T / 16, LD>(o, pf, vb_u, 0, 0);
+    }
+    __syncthreads();                         // everyone done with buffer j&1 before it is refilled
+    if (j + 2 < n_tiles) {
+      load_tile_async<HD, AT_T, AT_NT>(sK + (j & 1) * AT_T * LD, kbase, qkv_stride, (j + 2) * AT_T, S);
+      load_tile_async<HD, AT_T, AT_NT>(sV + (j & 1) * AT_T * LD, vbase, qkv_stride, (j + 2) * AT_T, S);
+    }
+    cp_async_commit();
   }
   float lse2[2];
 #pragma unroll
@@ -323,20 +370,21 @@ __global__ void __launch_bounds__(AT_THREADS) attn_fwd_kernel(const AttnParams p
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward pass A: per (sequence, head, 64 query rows) -> dQ, D_x, gate1/gate2 partial sums
+// backward pass A: CTA = (128 query rows, head, sequence) -> dQ, D_x, gate1/gate2 partial sums
 // ---------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_NT) attn_bwd_dq_kernel(const AttnParams p) {
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem[];
   bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sdO = sQ + AT_BM * LD;
-  bf16* sK = sdO + AT_BM * LD;
-  bf16* sV = sK + AT_BN * LD;
-  bf16* sKa = sV + AT_BN * LD;
+  bf16* sdO = sQ + AT_QB * LD;
+  bf16* sO = sdO + AT_QB * LD;
+  bf16* sK = sO + AT_QB * LD;             // [2][64][LD]
+  bf16* sV = sK + 2 * AT_T * LD;          // [2][64][LD]
+  bf16* sKa = sV + 2 * AT_T * LD;
   bf16* sVa = sKa + AT_AP * LD;
-  float* sRed = reinterpret_cast<float*>(sVa + AT_AP * LD);   // [8] cross-warp gate partials
-  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  float* sRed = reinterpret_cast<float*>(sVa + AT_AP * LD);   // [16] cross-warp gate partials
+  const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = p.S, D = p.H * HD;
   const long qkv_stride = 3L * D;
@@ -345,7 +393,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
   const bf16* vbase = qbase + 2 * D;
   const bf16* obase = p.out + static_cast<long>(n) * S * D + h * HD;
   const bf16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
-  const int r0 = qt * AT_BM;
+  const int r0 = qb * AT_QB;
   const float scale = rsqrtf(static_cast<float>(HD));
   const float scale2 = scale * LOG2E;
   const int vs = p.vstart[n];
@@ -353,35 +401,43 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
   const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;
   const int bias_c0 = vs, bias_c1 = vs + p.F;
   const float tg = tanhf(p.gate1[h]);
+  const int last_key = min(S, r0 + AT_QB) - 1;
+  const int n_tiles = last_key / AT_T + 1;
 
-  load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, r0, S, nullptr, nullptr);
-  load_tile<HD, AT_BM, false>(sdO, dobase, D, r0, S, nullptr, nullptr);
-  load_tile<HD, AT_AP, false>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
-  load_tile<HD, AT_AP, false>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+  load_tile_async<HD, AT_QB, AT_NT>(sQ, qbase, qkv_stride, r0, S);
+  load_tile_async<HD, AT_QB, AT_NT>(sdO, dobase, D, r0, S);
+  load_tile_async<HD, AT_QB, AT_NT>(sO, obase, D, r0, S);
+  load_tile_async<HD, AT_AP, AT_NT>(sKa, p.akv + h * HD, p.akv_ld, 0, p.A);
+  load_tile_async<HD, AT_AP, AT_NT>(sVa, p.akv + D + h * HD, p.akv_ld, 0, p.A);
+  load_tile_async<HD, AT_T, AT_NT>(sK, kbase, qkv_stride, 0, S);
+  load_tile_async<HD, AT_T, AT_NT>(sV, vbase, qkv_stride, 0, S);
+  cp_async_commit();
+  if (n_tiles > 1) {
+    load_tile_async<HD, AT_T, AT_NT>(sK + AT_T * LD, kbase, qkv_stride, AT_T, S);
+    load_tile_async<HD, AT_T, AT_NT>(sV + AT_T * LD, vbase, qkv_stride, AT_T, S);
+  }
+  cp_async_commit();
+  cp_async_wait<1>();
   __syncthreads();
   const uint32_t sQ_u = smem_u32(sQ), sdO_u = smem_u32(sdO), sK_u = smem_u32(sK), sV_u = smem_u32(sV),
                  sKa_u = smem_u32(sKa), sVa_u = smem_u32(sVa);
   const int row_a = r0 + warp * 16 + gq;
+  const int warp_last_row = r0 + warp * 16 + 15;
 
-  // D_total[row] = <dO[row], O[row]> for this thread's two rows (quad-cooperative: each lane of the quad
-  // takes a quarter of the head dimension).
+  // D_total[row] = <dO[row], O[row]> for this thread's two rows (each lane of the quad takes a quarter of hd)
   float dtot[2];
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     const int lr = warp * 16 + gq + 8 * hh;
-    const int row = r0 + lr;
     float acc = 0.f;
-    if (row < S) {
-      const uint4* orow = reinterpret_cast<const uint4*>(obase + static_cast<long>(row) * D);
 #pragma unroll
-      for (int v = 0; v < HD / 32; ++v) {
-        const int vec = t * (HD / 32) + v;
-        float a[8], b[8];
-        unpack8(__ldg(orow + vec), a);
-        unpack8(*reinterpret_cast<const uint4*>(sdO + lr * LD + vec * 8), b);
+    for (int v = 0; v < HD / 32; ++v) {
+      const int vec = t * (HD / 32) + v;
+      float a[8], b[8];
+      unpack8(*reinterpret_cast<const uint4*>(sO + lr * LD + vec * 8), a);
+      unpack8(*reinterpret_cast<const uint4*>(sdO + lr * LD + vec * 8), b);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc += a[e] * b[e];
-      }
+      for (int e = 0; e < 8; ++e) acc += a[e] * b[e];
     }
     dtot[hh] = quad_sum(acc);
   }
@@ -428,7 +484,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
       const bool ok = (row_a + 8 * hh) < S;
       if (ok && t == 0) g1_part += da[hh];
       dx[hh] = dtot[hh] - tg * da[hh];                           // D of the text softmax
-      if (ok && t == 0) p.ws_dx[(static_cast<long>(n) * p.H + h) * (p.qtiles * AT_BM) + row_a + 8 * hh] = dx[hh];
+      if (ok && t == 0) p.ws_dx[(static_cast<long>(n) * p.H + h) * (p.qblocks * AT_QB) + row_a + 8 * hh] = dx[hh];
     }
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
@@ -445,45 +501,58 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
     lse2[hh] = (row < S) ? p.lse[(static_cast<long>(n) * p.H + h) * S + row] * LOG2E : 0.f;
   }
   // ---- text keys ----
-  for (int j = 0; j <= qt; ++j) {
-    __syncthreads();
-    load_tile<HD, AT_BN, false>(sK, kbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
-    load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, j * AT_BN, S, nullptr, nullptr);
-    __syncthreads();
-    float s[AT_BN / 8][4], dp[AT_BN / 8][4];
-#pragma unroll
-    for (int i = 0; i < AT_BN / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
-    warp_mma_nt<AT_BN / 8, HD, LD>(s, sQ_u, warp * 16, sK_u, 0);
-    warp_mma_nt<AT_BN / 8, HD, LD>(dp, sdO_u, warp * 16, sV_u, 0);
-#pragma unroll
-    for (int nt = 0; nt < AT_BN / 8; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int row = row_a + 8 * (e >> 1);
-        const int col = j * AT_BN + nt * 8 + 2 * t + (e & 1);
-        float v = s[nt][e] * scale2;
-        const bool biased = (row >= bias_row0 && col >= bias_c0 && col < bias_c1);
-        if (biased) v += bias2;
-        const float pv = (col > row || row >= S) ? 0.f : exp2f(v - lse2[e >> 1]);
-        const float ds = pv * (dp[nt][e] - dx[e >> 1]);
-        if (biased) g2_part += ds;
-        s[nt][e] = ds;
-      }
+  for (int j = 0; j < n_tiles; ++j) {
+    if (j > 0) {
+      cp_async_wait<1>();
+      __syncthreads();
     }
-    uint32_t dsf[AT_BN / 16][4];
+    const uint32_t kb_u = sK_u + static_cast<uint32_t>((j & 1) * AT_T * LD * 2);
+    const uint32_t vb_u = sV_u + static_cast<uint32_t>((j & 1) * AT_T * LD * 2);
+    if (j * AT_T <= warp_last_row) {
+      float s[AT_T / 8][4], dp[AT_T / 8][4];
 #pragma unroll
-    for (int kb = 0; kb < AT_BN / 16; ++kb) c_to_a(dsf[kb], s[2 * kb], s[2 * kb + 1]);
-    warp_mma_ra_t<HD / 8, AT_BN / 16, LD>(dq, dsf, sK_u, 0, 0);
+      for (int i = 0; i < AT_T / 8; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f; }
+      warp_mma_nt<AT_T / 8, HD, LD>(s, sQ_u, warp * 16, kb_u, 0);
+      warp_mma_nt<AT_T / 8, HD, LD>(dp, sdO_u, warp * 16, vb_u, 0);
+#pragma unroll
+      for (int nt = 0; nt < AT_T / 8; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int row = row_a + 8 * (e >> 1);
+          const int col = j * AT_T + nt * 8 + 2 * t + (e & 1);
+          float v = s[nt][e] * scale2;
+          const bool biased = (row >= bias_row0 && col >= bias_c0 && col < bias_c1);
+          if (biased) v += bias2;
+          const float pv = (col > row || row >= S) ? 0.f : exp2f(v - lse2[e >> 1]);
+          const float ds = pv * (dp[nt][e] - dx[e >> 1]);
+          if (biased) g2_part += ds;
+          s[nt][e] = ds;
+        }
+      }
+      uint32_t dsf[AT_T / 16][4];
+#pragma unroll
+      for (int kb = 0; kb < AT_T / 16; ++kb) c_to_a(dsf[kb], s[2 * kb], s[2 * kb + 1]);
+      warp_mma_ra_t<HD / 8, AT_T / 16, LD>(dq, dsf, kb_u, 0, 0);
+    }
+    __syncthreads();
+    if (j + 2 < n_tiles) {
+      load_tile_async<HD, AT_T, AT_NT>(sK + (j & 1) * AT_T * LD, kbase, qkv_stride, (j + 2) * AT_T, S);
+      load_tile_async<HD, AT_T, AT_NT>(sV + (j & 1) * AT_T * LD, vbase, qkv_stride, (j + 2) * AT_T, S);
+    }
+    cp_async_commit();
   }
   // gate partial sums of this CTA (fixed reduction order)
   g1_part = warp_sum(g1_part);
   g2_part = warp_sum(g2_part);
-  if (lane == 0) { sRed[warp] = g1_part; sRed[4 + warp] = g2_part; }
+  if (lane == 0) { sRed[warp] = g1_part; sRed[8 + warp] = g2_part; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float* wsg = p.ws_gate + ((static_cast<long>(n) * p.H + h) * p.qtiles + qt) * 2;
-    wsg[0] = sRed[0] + sRed[1] + sRed[2] + sRed[3];
-    wsg[1] = sRed[4] + sRed[5] + sRed[6] + sRed[7];
+    float* wsg = p.ws_gate + ((static_cast<long>(n) * p.H + h) * p.qblocks + qb) * 2;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += sRed[w]; b += sRed[8 + w]; }
+    wsg[0] = a;
+    wsg[1] = b;
   }
   // dQ = scale * (dS K), inverse-rotated; staged through this warp's rows of sQ
   store_tile_warp<HD, true>(sQ + warp * 16 * LD, dq, scale, p.dqkv + static_cast<long>(n) * S * qkv_stride + h * HD, qkv_stride,
@@ -491,20 +560,21 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dq_kernel(const AttnParam
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward pass B: per (sequence, head, 64 keys) -> dK, dV ; blockIdx.x == qtiles -> adapter keys
-// (transposed formulation: S^T = K Q^T so that P^T / dS^T come out as A-operand fragments)
+// backward pass B: CTA = (128 keys, head, sequence) -> dK, dV ; blockIdx.x == qblocks -> adapter keys
+// (transposed formulation: S^T = K Q^T so that P^T / dS^T come out as A-operand fragments);
+// Q / dO tiles of 64 rows double-buffered.
 // ---------------------------------------------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(AT_NT) attn_bwd_dkv_kernel(const AttnParams p) {
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem[];
-  bf16* sK = reinterpret_cast<bf16*>(smem);
-  bf16* sV = sK + AT_BN * LD;
-  bf16* sQ = sV + AT_BN * LD;
-  bf16* sdO = sQ + AT_BM * LD;
-  float* sLse = reinterpret_cast<float*>(sdO + AT_BM * LD);   // [64]
-  float* sDx = sLse + AT_BM;                                  // [64]
-  const int jt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  bf16* sK = reinterpret_cast<bf16*>(smem);   // [128][LD]
+  bf16* sV = sK + AT_QB * LD;                 // [128][LD]
+  bf16* sQ = sV + AT_QB * LD;                 // [2][64][LD]
+  bf16* sdO = sQ + 2 * AT_T * LD;             // [2][64][LD]
+  float* sLse = reinterpret_cast<float*>(sdO + 2 * AT_T * LD);   // [2][64]
+  float* sDx = sLse + 2 * AT_T;                                  // [2][64]
+  const int kb_idx = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = p.S, D = p.H * HD;
   const long qkv_stride = 3L * D;
@@ -516,26 +586,29 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
   const float scale2 = scale * LOG2E;
   const uint32_t sQ_u = smem_u32(sQ), sdO_u = smem_u32(sdO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
   const long lse_base = (static_cast<long>(n) * p.H + h) * S;
-  const long dx_base = (static_cast<long>(n) * p.H + h) * (p.qtiles * AT_BM);
+  const long dx_base = (static_cast<long>(n) * p.H + h) * (p.qblocks * AT_QB);
 
-  if (jt == p.qtiles) {
+  if (kb_idx == p.qblocks) {
     // ======================= adapter keys =======================
+    // smem use here: sK region = Q block (128 rows), sV region = dO block, sQ[0..16) = K_a, sdO[0..16) = V_a
     const float tg = tanhf(p.gate1[h]);
-    load_tile<HD, AT_AP, false>(sK, p.akv + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
-    load_tile<HD, AT_AP, false>(sV, p.akv + D + h * HD, p.akv_ld, 0, p.A, nullptr, nullptr);
+    load_tile_async<HD, AT_AP, AT_NT>(sQ, p.akv + h * HD, p.akv_ld, 0, p.A);
+    load_tile_async<HD, AT_AP, AT_NT>(sdO, p.akv + D + h * HD, p.akv_ld, 0, p.A);
     float dka[HD / 8][4], dva[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) { dka[i][0] = dka[i][1] = dka[i][2] = dka[i][3] = 0.f; dva[i][0] = dva[i][1] = dva[i][2] = dva[i][3] = 0.f; }
-    for (int i = 0; i < p.qtiles; ++i) {
+    for (int i = 0; i < p.qblocks; ++i) {
       __syncthreads();
-      load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, i * AT_BM, S, nullptr, nullptr);
-      load_tile<HD, AT_BM, false>(sdO, dobase, D, i * AT_BM, S, nullptr, nullptr);
+      load_tile_async<HD, AT_QB, AT_NT>(sK, qbase, qkv_stride, i * AT_QB, S);
+      load_tile_async<HD, AT_QB, AT_NT>(sV, dobase, D, i * AT_QB, S);
+      cp_async_commit();
+      cp_async_wait<0>();
       __syncthreads();
-      // each warp takes 16 of the 64 query rows (they are the contraction dimension of dK_a / dV_a)
+      // each warp takes 16 of the 128 query rows (they are the contraction dimension of dK_a / dV_a)
       float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      warp_mma_nt<2, HD, LD>(st, sK_u, 0, sQ_u, warp * 16);      // S_a^T [keys x rows]
-      warp_mma_nt<2, HD, LD>(dpt, sV_u, 0, sdO_u, warp * 16);    // dP_a'^T
+      warp_mma_nt<2, HD, LD>(st, sQ_u, 0, sK_u, warp * 16);      // S_a^T [keys x rows]
+      warp_mma_nt<2, HD, LD>(dpt, sdO_u, 0, sV_u, warp * 16);    // dP_a'^T
       float mx[2][2], sm[2][2], da[2][2];                          // [n-tile][column parity]
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -559,7 +632,7 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int row = i * AT_BM + warp * 16 + nt * 8 + 2 * t + c;
+          const int row = i * AT_QB + warp * 16 + nt * 8 + 2 * t + c;
           const float inv = (row < S) ? 1.f / sm[nt][c] : 0.f;    // rows past the sequence contribute nothing
           st[nt][c] *= inv; st[nt][2 + c] *= inv;
           da[nt][c] = col_sum(st[nt][c] * dpt[nt][c] + st[nt][2 + c] * dpt[nt][2 + c]);
@@ -575,12 +648,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
       uint32_t pf[1][4], df[1][4];
       c_to_a(pf[0], pt[0], pt[1]);
       c_to_a(df[0], dst[0], dst[1]);
-      warp_mma_ra_t<HD / 8, 1, LD>(dva, pf, sdO_u, warp * 16, 0);
-      warp_mma_ra_t<HD / 8, 1, LD>(dka, df, sQ_u, warp * 16, 0);
+      warp_mma_ra_t<HD / 8, 1, LD>(dva, pf, sV_u, warp * 16, 0);
+      warp_mma_ra_t<HD / 8, 1, LD>(dka, df, sK_u, warp * 16, 0);
     }
-    // cross-warp reduction in a fixed order through shared memory (fp32 [4][16][HD] fits in sQ+sdO)
+    // cross-warp reduction in a fixed order through shared memory (fp32 [8][16][HD] fits in sK+sV)
     __syncthreads();
-    float* red = reinterpret_cast<float*>(sQ);
+    float* red = reinterpret_cast<float*>(sK);
     float* wsa = p.ws_akv + (static_cast<long>(n) * p.H + h) * 2 * AT_AP * HD;
     auto reduce_out = [&](float (&acc)[HD / 8][4], float mul, int which) {
 #pragma unroll
@@ -589,8 +662,12 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
         for (int e = 0; e < 4; ++e)
           red[(warp * AT_AP + gq + 8 * (e >> 1)) * HD + nt * 8 + 2 * t + (e & 1)] = acc[nt][e] * mul;
       __syncthreads();
-      for (int idx = threadIdx.x; idx < AT_AP * HD; idx += AT_THREADS)
-        wsa[which * AT_AP * HD + idx] = red[idx] + red[AT_AP * HD + idx] + red[2 * AT_AP * HD + idx] + red[3 * AT_AP * HD + idx];
+      for (int idx = threadIdx.x; idx < AT_AP * HD; idx += AT_NT) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a += red[w * AT_AP * HD + idx];
+        wsa[which * AT_AP * HD + idx] = a;
+      }
       __syncthreads();
     };
     reduce_out(dka, scale, 0);
@@ -599,9 +676,24 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
   }
 
   // ======================= text keys =======================
-  const int k0 = jt * AT_BN;
-  load_tile<HD, AT_BN, false>(sK, kbase, qkv_stride, k0, S, nullptr, nullptr);
-  load_tile<HD, AT_BN, false>(sV, vbase, qkv_stride, k0, S, nullptr, nullptr);
+  const int k0 = kb_idx * AT_QB;
+  const int n_qt = (S + AT_T - 1) / AT_T;          // 64-row query tiles in the sequence
+  const int i0 = k0 / AT_T;                        // first query tile that can see these keys
+  auto load_q_tile = [&](int i, int buf) {
+    load_tile_async<HD, AT_T, AT_NT>(sQ + buf * AT_T * LD, qbase, qkv_stride, i * AT_T, S);
+    load_tile_async<HD, AT_T, AT_NT>(sdO + buf * AT_T * LD, dobase, D, i * AT_T, S);
+    if (threadIdx.x < AT_T) {
+      const int row = i * AT_T + threadIdx.x;
+      sLse[buf * AT_T + threadIdx.x] = (row < S) ? p.lse[lse_base + row] * LOG2E : 0.f;
+      sDx[buf * AT_T + threadIdx.x] = (row < S) ? p.ws_dx[dx_base + row] : 0.f;
+    }
+  };
+  load_tile_async<HD, AT_QB, AT_NT>(sK, kbase, qkv_stride, k0, S);
+  load_tile_async<HD, AT_QB, AT_NT>(sV, vbase, qkv_stride, k0, S);
+  load_q_tile(i0, 0);
+  cp_async_commit();
+  if (i0 + 1 < n_qt) load_q_tile(i0 + 1, 1);
+  cp_async_commit();
   const int vs = p.vstart[n];
   const float bias2 = (vs >= 0) ? p.gate2[h] * LOG2E : 0.f;
   const int bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;
@@ -610,53 +702,54 @@ __global__ void __launch_bounds__(AT_THREADS) attn_bwd_dkv_kernel(const AttnPara
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) { dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f; dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f; }
   const int key_a = k0 + warp * 16 + gq;   // this thread's keys: key_a, key_a + 8
-  for (int i = jt; i < p.qtiles; ++i) {
+  const int warp_first_key = k0 + warp * 16;
+  for (int i = i0; i < n_qt; ++i) {
+    const int buf = (i - i0) & 1;
+    cp_async_wait<1>();
     __syncthreads();
-    load_tile<HD, AT_BM, false>(sQ, qbase, qkv_stride, i * AT_BM, S, nullptr, nullptr);
-    load_tile<HD, AT_BM, false>(sdO, dobase, D, i * AT_BM, S, nullptr, nullptr);
-    if (threadIdx.x < AT_BM) {
-      const int row = i * AT_BM + threadIdx.x;
-      sLse[threadIdx.x] = (row < S) ? p.lse[lse_base + row] * LOG2E : 0.f;
-      sDx[threadIdx.x] = (row < S) ? p.ws_dx[dx_base + row] : 0.f;
-    }
-    __syncthreads();
+    if (i * AT_T + AT_T - 1 >= warp_first_key) {    // warp-uniform causal skip
+      const uint32_t qb_u = sQ_u + static_cast<uint32_t>(buf * AT_T * LD * 2);
+      const uint32_t dob_u = sdO_u + static_cast<uint32_t>(buf * AT_T * LD * 2);
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      float st[4][4], dpt[4][4];
+      for (int half = 0; half < 2; ++half) {
+        float st[4][4], dpt[4][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { st[q][0] = st[q][1] = st[q][2] = st[q][3] = 0.f; dpt[q][0] = dpt[q][1] = dpt[q][2] = dpt[q][3] = 0.f; }
-      warp_mma_nt<4, HD, LD>(st, sK_u, warp * 16, sQ_u, half * 32);     // S^T [16 keys x 32 rows]
-      warp_mma_nt<4, HD, LD>(dpt, sV_u, warp * 16, sdO_u, half * 32);   // dP^T
+        for (int q = 0; q < 4; ++q) { st[q][0] = st[q][1] = st[q][2] = st[q][3] = 0.f; dpt[q][0] = dpt[q][1] = dpt[q][2] = dpt[q][3] = 0.f; }
+        warp_mma_nt<4, HD, LD>(st, sK_u, warp * 16, qb_u, half * 32);     // S^T [16 keys x 32 rows]
+        warp_mma_nt<4, HD, LD>(dpt, sV_u, warp * 16, dob_u, half * 32);   // dP^T
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
+        for (int nt = 0; nt < 4; ++nt) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int key = key_a + 8 * (e >> 1);
-          const int lr = half * 32 + nt * 8 + 2 * t + (e & 1);
-          const int row = i * AT_BM + lr;
-          float v = st[nt][e] * scale2;
-          if (row >= bias_row0 && key >= bias_c0 && key < bias_c1) v += bias2;
-          const float pv = (key > row || row >= S) ? 0.f : exp2f(v - sLse[lr]);
-          st[nt][e] = pv;
-          dpt[nt][e] = pv * (dpt[nt][e] - sDx[lr]);
+          for (int e = 0; e < 4; ++e) {
+            const int key = key_a + 8 * (e >> 1);
+            const int lr = half * 32 + nt * 8 + 2 * t + (e & 1);
+            const int row = i * AT_T + lr;
+            float v = st[nt][e] * scale2;
+            if (row >= bias_row0 && key >= bias_c0 && key < bias_c1) v += bias2;
+            const float pv = (key > row || row >= S) ? 0.f : exp2f(v - sLse[buf * AT_T + lr]);
+            st[nt][e] = pv;
+            dpt[nt][e] = pv * (dpt[nt][e] - sDx[buf * AT_T + lr]);
+          }
         }
-      }
-      uint32_t pf[2][4], df[2][4];
+        uint32_t pf[2][4], df[2][4];
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) { c_to_a(pf[kb], st[2 * kb], st[2 * kb + 1]); c_to_a(df[kb], dpt[2 * kb], dpt[2 * kb + 1]); }
-      warp_mma_ra_t<HD / 8, 2, LD>(dv, pf, sdO_u, half * 32, 0);
-      warp_mma_ra_t<HD / 8, 2, LD>(dk, df, sQ_u, half * 32, 0);
+        for (int kb = 0; kb < 2; ++kb) { c_to_a(pf[kb], st[2 * kb], st[2 * kb + 1]); c_to_a(df[kb], dpt[2 * kb], dpt[2 * kb + 1]); }
+        warp_mma_ra_t<HD / 8, 2, LD>(dv, pf, dob_u, half * 32, 0);
+        warp_mma_ra_t<HD / 8, 2, LD>(dk, df, qb_u, half * 32, 0);
+      }
     }
+    __syncthreads();
+    if (i + 2 < n_qt) load_q_tile(i + 2, buf);
+    cp_async_commit();
   }
+  cp_async_wait<0>();
   __syncthreads();   // everyone done with sQ/sdO before they become staging areas
+  // 8 warps x 16 rows = 128 staging rows: sQ (2 x 64 rows) for dK, sdO for dV
   bf16* dkbase = p.dqkv + static_cast<long>(n) * S * qkv_stride + D + h * HD;
   store_tile_warp<HD, true>(sQ + warp * 16 * LD, dk, scale, dkbase, qkv_stride, k0 + warp * 16, S, p.cosT, p.sinT);
   store_tile_warp<HD, false>(sdO + warp * 16 * LD, dv, 1.f, dkbase + D, qkv_stride, k0 + warp * 16, S, nullptr, nullptr);
 }
 
-// ---------------------------------------------------------------------------------------------
-// fixed-order reduction of the per-CTA partials
-// ---------------------------------------------------------------------------------------------
 // grid (H, A + 1): blocks (h, a < A) reduce adapter row a of head h over the sequences (independent
 // loads, fixed summation order); block (h, A) reduces the gate partials of head h.
 __global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __restrict__ ws_akv, const float* __restrict__ ws_gate,
@@ -702,9 +795,9 @@ __global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __res
   }
 }
 
-template <int HD> constexpr int fwd_smem() { return (AT_BM + 2 * AT_BN + 2 * AT_AP) * (HD + 8) * 2; }
-template <int HD> constexpr int dq_smem() { return (2 * AT_BM + 2 * AT_BN + 2 * AT_AP) * (HD + 8) * 2 + 64; }
-template <int HD> constexpr int dkv_smem() { return (2 * AT_BM + 2 * AT_BN) * (HD + 8) * 2 + 2 * AT_BM * 4; }
+template <int HD> constexpr int fwd_smem() { return (AT_QB + 4 * AT_T + 2 * AT_AP) * (HD + 8) * 2; }
+template <int HD> constexpr int dq_smem() { return (3 * AT_QB + 4 * AT_T + 2 * AT_AP) * (HD + 8) * 2 + 128; }
+template <int HD> constexpr int dkv_smem() { return (2 * AT_QB + 4 * AT_T) * (HD + 8) * 2 + 4 * AT_T * 4; }
 
 int attn_init() {
   cudaError_t e;
@@ -742,19 +835,19 @@ extern "C" int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   p.qkv = reinterpret_cast<const bf16*>(qkv); p.akv = reinterpret_cast<const bf16*>(akv); p.akv_ld = akv_ld;
   p.cosT = rope_cos; p.sinT = rope_sin; p.gate1 = gate1; p.gate2 = gate2; p.vstart = vstart;
   p.out = reinterpret_cast<bf16*>(out); p.lse = lse;
-  p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qtiles = (S + AT_BM - 1) / AT_BM;
-  dim3 grid(p.qtiles, H, n_seq);
+  p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qblocks = (S + AT_QB - 1) / AT_QB;
+  dim3 grid(p.qblocks, H, n_seq);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (hd == 64) attn_fwd_kernel<64><<<grid, AT_THREADS, fwd_smem<64>(), s>>>(p);
-  else attn_fwd_kernel<128><<<grid, AT_THREADS, fwd_smem<128>(), s>>>(p);
+  if (hd == 64) attn_fwd_kernel<64><<<grid, AT_NT, fwd_smem<64>(), s>>>(p);
+  else attn_fwd_kernel<128><<<grid, AT_NT, fwd_smem<128>(), s>>>(p);
   return check_launch("attn_fwd");
 }
 
 extern "C" int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A) {
   (void)A;
-  const int64_t qtiles = (S + AT_BM - 1) / AT_BM;
+  const int64_t qblocks = (S + AT_QB - 1) / AT_QB;
   const int64_t nh = static_cast<int64_t>(n_seq) * H;
-  return 4 * (nh * qtiles * AT_BM + nh * qtiles * 2 + nh * 2 * AT_AP * hd);
+  return 4 * (nh * qblocks * AT_QB + nh * qblocks * 2 + nh * 2 * AT_AP * hd);
 }
 
 extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
@@ -769,26 +862,26 @@ extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   p.cosT = rope_cos; p.sinT = rope_sin; p.gate1 = gate1; p.gate2 = gate2; p.vstart = vstart;
   p.out = const_cast<bf16*>(reinterpret_cast<const bf16*>(out)); p.lse = const_cast<float*>(lse);
   p.dout = reinterpret_cast<const bf16*>(dout); p.dqkv = reinterpret_cast<bf16*>(dqkv);
-  p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qtiles = (S + AT_BM - 1) / AT_BM;
+  p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qblocks = (S + AT_QB - 1) / AT_QB;
   const int64_t nh = static_cast<int64_t>(n_seq) * H;
   p.ws_dx = reinterpret_cast<float*>(ws);
-  p.ws_gate = p.ws_dx + nh * p.qtiles * AT_BM;
-  p.ws_akv = p.ws_gate + nh * p.qtiles * 2;
+  p.ws_gate = p.ws_dx + nh * p.qblocks * AT_QB;
+  p.ws_akv = p.ws_gate + nh * p.qblocks * 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  dim3 grid_a(p.qtiles, H, n_seq), grid_b(p.qtiles + 1, H, n_seq);
+  dim3 grid_a(p.qblocks, H, n_seq), grid_b(p.qblocks + 1, H, n_seq);
   if (hd == 64) {
-    attn_bwd_dq_kernel<64><<<grid_a, AT_THREADS, dq_smem<64>(), s>>>(p);
+    attn_bwd_dq_kernel<64><<<grid_a, AT_NT, dq_smem<64>(), s>>>(p);
     rc = check_launch("attn_bwd_dq");
     if (rc) return rc;
-    attn_bwd_dkv_kernel<64><<<grid_b, AT_THREADS, dkv_smem<64>(), s>>>(p);
+    attn_bwd_dkv_kernel<64><<<grid_b, AT_NT, dkv_smem<64>(), s>>>(p);
   } else {
-    attn_bwd_dq_kernel<128><<<grid_a, AT_THREADS, dq_smem<128>(), s>>>(p);
+    attn_bwd_dq_kernel<128><<<grid_a, AT_NT, dq_smem<128>(), s>>>(p);
     rc = check_launch("attn_bwd_dq");
     if (rc) return rc;
-    attn_bwd_dkv_kernel<128><<<grid_b, AT_THREADS, dkv_smem<128>(), s>>>(p);
+    attn_bwd_dkv_kernel<128><<<grid_b, AT_NT, dkv_smem<128>(), s>>>(p);
   }
   rc = check_launch("attn_bwd_dkv");
   if (rc) return rc;
-  attn_bwd_reduce_kernel<<<dim3(H, A + 1), 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qtiles);
+  attn_bwd_reduce_kernel<<<dim3(H, A + 1), 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qblocks);
   return check_launch("attn_bwd_reduce");
 }

@@ -1,0 +1,47 @@
+"""GPU micro-benchmark of the attention kernels and one GEMM at 7B NExT-QA shapes (ncu target)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from flipped_vqa_b200 import ops, _lib
+from oracle import llama_vqa_oracle as O
+
+def main():
+    _lib.lib()
+    n_seq, S, H, hd, A, F = 24, 128, 32, 128, 10, 10
+    if len(sys.argv) > 2:
+        n_seq, S = int(sys.argv[1]), int(sys.argv[2])
+    D = H * hd
+    g = torch.Generator(device="cuda").manual_seed(0)
+    qkv = torch.randn(n_seq * S, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
+    akv = torch.randn(A, 2 * D, device="cuda", generator=g).to(torch.bfloat16)
+    gate1 = torch.randn(H, device="cuda", generator=g) * 0.5
+    gate2 = torch.full((H,), -3.5, device="cuda")
+    cos, sin = O.rope_table(hd, S); cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    vstart = torch.tensor([18] * (2 * n_seq // 3) + [-1] * (n_seq - 2 * n_seq // 3), dtype=torch.int32, device="cuda")
+    dout = torch.randn(n_seq * S, D, device="cuda", generator=g).to(torch.bfloat16)
+    a = torch.randn(n_seq * S, 4096, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(11008, 4096, device="cuda", generator=g) * 0.02).to(torch.bfloat16)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    def run():
+        out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
+        ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
+        ops.gemm_nt(a, w)
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    tot = [0.0] * 4
+    for _ in range(10):
+        flush.zero_()
+        ev[0].record()
+        out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
+        ev[1].record()
+        ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
+        ev[2].record()
+        ops.gemm_nt(a, w)
+        ev[3].record()
+        torch.cuda.synchronize()
+        for i in range(3): tot[i] += ev[i].elapsed_time(ev[i + 1])
+    print(f"attn fwd {tot[0] / 10 * 1e3:.1f} us | attn bwd (3 kernels) {tot[1] / 10 * 1e3:.1f} us | gemm 3072x11008x4096 {tot[2] / 10 * 1e3:.1f} us")
+
+if __name__ == "__main__":
+    main()
