@@ -14,12 +14,12 @@
 // shared memory through ldmatrix; 8-warp CTAs own 128 query rows (or 128 keys) and stream the other
 // operand in 64-row tiles through a cp.async double buffer (attention is ~0.5 % of the step's FLOPs;
 // the tcgen05 budget went to the GEMM first).
+#include "attention.h"
 #include "common.cuh"
 
 namespace fvqa {
 
 constexpr int AT_THREADS = 256;
-constexpr int AT_AP = 16;   // adapter keys padded to one MMA k-block
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -200,15 +200,6 @@ __device__ __forceinline__ void load_tile_async(bf16* s, const bf16* __restrict_
     cp_async16(sbase + static_cast<uint32_t>((r * LD + v * 8) * 2), g + static_cast<long>(ok ? pos : 0) * stride + v * 8, ok);
   }
 }
-
-struct AttnParams {
-  const bf16* qkv; const bf16* akv; int akv_ld;
-  const float* cosT; const float* sinT; const float* gate1; const float* gate2; const int32_t* vstart;
-  bf16* out; float* lse;            // fwd outputs / bwd inputs
-  const bf16* dout; bf16* dqkv;     // bwd
-  float* ws_dx; float* ws_gate; float* ws_akv;
-  int n_seq, S, H, A, F, qblocks;   // qblocks = ceil(S / 128)
-};
 
 constexpr int AT_NT = 256;        // threads per CTA (8 warps)
 constexpr int AT_QB = 128;        // query rows (pass A / fwd) or keys (pass B) owned by a CTA
@@ -811,7 +802,7 @@ int attn_init() {
   FVQA_ATTR(attn_bwd_dkv_kernel<64>, dkv_smem<64>())
   FVQA_ATTR(attn_bwd_dkv_kernel<128>, dkv_smem<128>())
 #undef FVQA_ATTR
-  return FVQA_OK;
+  return attn_tc_init();
 }
 
 static int check_attn_args(int n_seq, int S, int H, int hd, int A, int akv_ld) {
@@ -838,6 +829,7 @@ extern "C" int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qblocks = (S + AT_QB - 1) / AT_QB;
   dim3 grid(p.qblocks, H, n_seq);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (attn_tc_supported(S, hd, A)) return attn_fwd_tc(p, s);
   if (hd == 64) attn_fwd_kernel<64><<<grid, AT_NT, fwd_smem<64>(), s>>>(p);
   else attn_fwd_kernel<128><<<grid, AT_NT, fwd_smem<128>(), s>>>(p);
   return check_launch("attn_fwd");
@@ -869,7 +861,10 @@ extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   p.ws_akv = p.ws_gate + nh * p.qblocks * 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid_a(p.qblocks, H, n_seq), grid_b(p.qblocks + 1, H, n_seq);
-  if (hd == 64) {
+  if (attn_tc_supported(S, hd, A)) {
+    rc = attn_bwd_tc(p, s);
+    if (rc) return rc;
+  } else if (hd == 64) {
     attn_bwd_dq_kernel<64><<<grid_a, AT_NT, dq_smem<64>(), s>>>(p);
     rc = check_launch("attn_bwd_dq");
     if (rc) return rc;

@@ -15,6 +15,7 @@
 #include <unordered_map>
 
 #include "common.cuh"
+#include "tmap.h"
 
 namespace fvqa {
 
@@ -44,6 +45,66 @@ struct GemmEpi {
   const float* sinT;
   int rope_cols, hd, S;
 };
+
+// One epilogue chunk: NC (32 or 16) consecutive fp32 accumulator columns of one output row held in
+// registers -> optional RoPE rotation / residual add -> global store (bf16 or fp32).
+template <int NC, bool OUT_F32, bool ROPE>
+__device__ __forceinline__ void epilogue_store(uint32_t (&v)[32], void* __restrict__ Cout, const GemmEpi& epi, int row, int col0,
+                                               int N, int ldc) {
+  if constexpr (OUT_F32) {
+    float* crow = reinterpret_cast<float*>(Cout) + static_cast<long>(row) * ldc + col0;
+    const float* rrow = epi.R ? reinterpret_cast<const float*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
+#pragma unroll
+    for (int j = 0; j < NC / 4; ++j) {
+      if (col0 + j * 4 < N) {
+        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        if (rrow != nullptr) {
+          const float4 rr = *reinterpret_cast<const float4*>(rrow + j * 4);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        *reinterpret_cast<float4*>(crow + j * 4) = o;
+      }
+    }
+  } else {
+    bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
+    const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
+    if constexpr (ROPE) {
+      const int pos = row % epi.S;
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {
+        const int col = col0 + 8 * q;                 // 8-column groups never straddle a head (hd % 8 == 0)
+        if (col < epi.rope_cols) {
+          const long ti = static_cast<long>(pos) * (epi.hd >> 1) + ((col % epi.hd) >> 1);
+          const float4 cc = __ldg(reinterpret_cast<const float4*>(epi.cosT + ti));
+          const float4 ss = __ldg(reinterpret_cast<const float4*>(epi.sinT + ti));
+          const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(v[8 * q + 2 * e]), b = __uint_as_float(v[8 * q + 2 * e + 1]);
+            v[8 * q + 2 * e] = __float_as_uint(a * cv[e] - b * sv[e]);
+            v[8 * q + 2 * e + 1] = __float_as_uint(a * sv[e] + b * cv[e]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NC / 8; ++j) {
+      if (col0 + j * 8 < N) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+        if (rrow != nullptr) {
+          float r[8];
+          unpack8(*reinterpret_cast<const uint4*>(rrow + j * 8), r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += r[e];
+        }
+        *reinterpret_cast<uint4*>(crow + j * 8) = pack8(f);
+      }
+    }
+  }
+}
 
 template <int BN, bool OUT_F32, bool ROPE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -163,61 +224,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tmem_ld_32x32(taddr, v);
         tmem_ld_wait();
         const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) {
-          if constexpr (OUT_F32) {
-            float* crow = reinterpret_cast<float*>(Cout) + static_cast<long>(row) * ldc + col0;
-            const float* rrow = epi.R ? reinterpret_cast<const float*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (col0 + j * 4 < N) {
-                float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                if (rrow != nullptr) {
-                  const float4 rr = *reinterpret_cast<const float4*>(rrow + j * 4);
-                  o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-                }
-                *reinterpret_cast<float4*>(crow + j * 4) = o;
-              }
-            }
-          } else {
-            bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
-            const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
-            if constexpr (ROPE) {
-              if (col0 < epi.rope_cols) {
-                const int pos = row % epi.S;
-                const int i0 = (col0 % epi.hd) >> 1;
-                const float4* c4 = reinterpret_cast<const float4*>(epi.cosT + static_cast<long>(pos) * (epi.hd >> 1) + i0);
-                const float4* s4 = reinterpret_cast<const float4*>(epi.sinT + static_cast<long>(pos) * (epi.hd >> 1) + i0);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 cc = __ldg(c4 + q), ss = __ldg(s4 + q);
-                  const float cv[4] = {cc.x, cc.y, cc.z, cc.w}, sv[4] = {ss.x, ss.y, ss.z, ss.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float a = __uint_as_float(v[8 * q + 2 * e]), b = __uint_as_float(v[8 * q + 2 * e + 1]);
-                    v[8 * q + 2 * e] = __float_as_uint(a * cv[e] - b * sv[e]);
-                    v[8 * q + 2 * e + 1] = __float_as_uint(a * sv[e] + b * cv[e]);
-                  }
-                }
-              }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (col0 + j * 8 < N) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-                if (rrow != nullptr) {
-                  float r[8];
-                  unpack8(*reinterpret_cast<const uint4*>(rrow + j * 8), r);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) f[e] += r[e];
-                }
-                *reinterpret_cast<uint4*>(crow + j * 8) = pack8(f);
-              }
-            }
-          }
-        }
+        if (row_ok && col0 < N) epilogue_store<32, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
       }
       tc_fence_before();
       __syncwarp();
@@ -235,6 +242,167 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2): a cluster of two CTAs on the two SMs of one TPC owns a 256 x BN
+// output tile. Each CTA stages ITS 128 rows of A and ITS BN/2 rows of B per k-block (32 KB at
+// BN = 256 instead of the 48 KB of the single-CTA tile -> deeper TMA ring, 1/3 less L2->smem
+// traffic per FLOP); the leader CTA's elected thread issues tcgen05.mma.cta_group::2 (UMMA
+// 256 x BN x 16) which reads both CTAs' shared memory and writes 128 accumulator rows into each
+// CTA's TMEM. BN is a RUNTIME multiple of 16 in [64, 256], chosen per problem so that the 74 pairs
+// finish their last wave together (N = 4096 outputs: 256 -> 2.6 waves, 176 -> 3.9 waves).
+// Barriers: full[s] lives in the leader (both CTAs' TMA bytes are credited to it), empty[s] and
+// tmem_full[a] exist in both CTAs and are signalled by multicast tcgen05.commit, tmem_empty[a]
+// lives in the leader and collects the 8 epilogue warps of the pair.
+// ---------------------------------------------------------------------------------------------
+constexpr int PAIR_MAX_STAGES = 8;
+constexpr int PAIR_BAR_BYTES = 256;
+constexpr int PAIR_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
+
+__host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GEMM_BK * 2 + (bn / 2) * GEMM_BK * 2; }
+
+template <bool OUT_F32, bool ROPE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int stage_bytes = pair_stage_bytes(BN);
+  const uint32_t bar_base = smem_base + stages * stage_bytes;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (PAIR_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * PAIR_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * PAIR_MAX_STAGES + 2 + a); };
+  const uint32_t holder = bar_base + 8u * (2 * PAIR_MAX_STAGES + 4);
+  volatile uint32_t* holder_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (holder - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int tiles_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = K / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_pair(holder, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();               // barrier inits + TMEM allocation visible to both CTAs
+  tc_fence_after();
+  const uint32_t tmem_base = *holder_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int m0 = (tile % tiles_m) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
+        const int n0 = (tile / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + GEMM_BM * GEMM_BK * 2;
+          const uint32_t lfull = mapa_shared(full_bar(stage), 0);
+          if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * stage_bytes);
+          tma_load_2d_pair(sa, &tmap_a, lfull, kb * GEMM_BK, m0);
+          tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          const uint32_t sb = sa + GEMM_BM * GEMM_BK * 2;
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
+            umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(empty_bar(stage));
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_pair(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: own 128 rows, all BN columns) =====================
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int n32 = BN >> 5;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      const int m0 = (tile % tiles_m) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
+      const int n0 = (tile / tiles_m) * BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
+#pragma unroll 1
+      for (int c = 0; c < n32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        const int col0 = n0 + c * 32;
+        if (row_ok && col0 < N) epilogue_store<32, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
+      }
+      if (BN & 16) {
+        uint32_t v[32];
+        tmem_ld_32x16(tbase + static_cast<uint32_t>(n32 * 32), v);
+        tmem_ld_wait();
+        const int col0 = n0 + n32 * 32;
+        if (row_ok && col0 < N) epilogue_store<16, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();               // the peer's shared memory / TMEM stay alive until every MMA has retired
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: tensor-map cache + launch
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -247,8 +415,9 @@ static std::mutex g_mu;
 struct MapKey {
   const void* ptr;
   int rows, cols, ld, box_rows;
+  int seq_len = 0;             // > 0: 3-D map (cols, seq_len, rows / seq_len)
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && seq_len == o.seq_len;
   }
 };
 struct MapKeyHash {
@@ -258,10 +427,13 @@ struct MapKeyHash {
     h ^= (static_cast<size_t>(k.cols) * 0xC2B2AE3D27D4EB4Full) + (h << 6) + (h >> 2);
     h ^= (static_cast<size_t>(k.ld) * 0x165667B19E3779F9ull) + (h << 6) + (h >> 2);
     h ^= static_cast<size_t>(k.box_rows) + (h << 6) + (h >> 2);
+    h ^= (static_cast<size_t>(k.seq_len) * 0x27D4EB2F165667C5ull) + (h << 6) + (h >> 2);
     return h;
   }
 };
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+int num_sms() { return g_num_sms; }
 
 int gemm_init() {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -290,11 +462,19 @@ int gemm_init() {
   FVQA_SET_SMEM(256, false, true)
   FVQA_SET_SMEM(128, false, true)
 #undef FVQA_SET_SMEM
+#define FVQA_SET_PAIR(F32, ROPE)                                                                                   \
+  e = cudaFuncSetAttribute(gemm_bf16_nt_pair_kernel<F32, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                           PAIR_SMEM_LIMIT);                                                                       \
+  FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm pair): %s", cudaGetErrorString(e));
+  FVQA_SET_PAIR(false, false)
+  FVQA_SET_PAIR(true, false)
+  FVQA_SET_PAIR(false, true)
+#undef FVQA_SET_PAIR
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return FVQA_OK;
 }
 
-static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
   MapKey key{ptr, rows, cols, ld, box_rows};
   std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_maps.find(key);
@@ -318,6 +498,33 @@ static int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, C
   return FVQA_OK;
 }
 
+// 3-D view of a token-major matrix: (column, position in sequence, sequence). Boxes are 64 columns x
+// box_rows positions of ONE sequence: positions >= seq_len are out of bounds (zero-filled on load, dropped
+// on store), so a 128-row box never touches the next sequence when seq_len < 128.
+int get_tmap_seq(const void* ptr, int n_seq, int seq_len, int cols, int ld, int box_rows, CUtensorMap* out) {
+  MapKey key{ptr, n_seq * seq_len, cols, ld, box_rows, seq_len};
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) {
+    *out = it->second;
+    return FVQA_OK;
+  }
+  CUtensorMap m;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(seq_len), static_cast<cuuint64_t>(n_seq)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * static_cast<cuuint64_t>(seq_len)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FVQA_REQUIRE(r == CUDA_SUCCESS, FVQA_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p n_seq=%d S=%d cols=%d ld=%d",
+               static_cast<int>(r), ptr, n_seq, seq_len, cols, ld);
+  if (g_maps.size() > 8192) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return FVQA_OK;
+}
+
 template <int BN, bool OUT_F32, bool ROPE>
 static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
                        int N, int K, cudaStream_t stream) {
@@ -330,6 +537,58 @@ static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, 
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   gemm_bf16_nt_kernel<BN, OUT_F32, ROPE><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, C, epi, M, N, K, ldc);
   return check_launch("gemm_bf16_nt");
+}
+
+// ---- CTA-pair path ---------------------------------------------------------------------------
+static int g_force_bn = 0;        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
+
+// Output-tile width for the pair kernel: maximise wave efficiency x per-tile efficiency. The per-tile
+// factors are MEASURED (B200, 3072 x 22016 x 4096, tools/gemm_diag.py): the UMMA 256 x N x 16 issue time
+// barely shrinks with N, so narrow tiles only pay when they remove most of a wave.
+static int choose_pair_bn(int M, int N) {
+  static const int kBn[] = {256, 240, 224, 208, 192, 176, 160, 144, 128};
+  static const double kTileEff[] = {1.0, 0.964, 0.872, 0.82, 0.778, 0.675, 0.62, 0.56, 0.50};
+  const int pairs = g_num_sms / 2;
+  const long tm = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  int best = 256;
+  double best_score = -1.0;
+  for (int i = 0; i < 9; ++i) {
+    const int bn = kBn[i];
+    const long tn = (N + bn - 1) / bn;
+    const long tiles = tm * tn;
+    const long waves = (tiles + pairs - 1) / pairs;
+    const double eff = (static_cast<double>(M) * N) / (static_cast<double>(waves) * pairs * 2 * GEMM_BM * bn);
+    const double score = eff * kTileEff[i];
+    if (score > best_score + 0.01) { best_score = score; best = bn; }
+  }
+  return best;
+}
+
+template <bool OUT_F32, bool ROPE>
+static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
+                            int N, int K, int bn, cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc = get_tmap(A, M, K, lda, GEMM_BM, &ta);
+  if (rc) return rc;
+  rc = get_tmap(B, N, K, ldb, bn / 2, &tb);
+  if (rc) return rc;
+  const int stage_bytes = pair_stage_bytes(bn);
+  int stages = (PAIR_SMEM_LIMIT - 1024 - PAIR_BAR_BYTES) / stage_bytes;
+  if (stages > PAIR_MAX_STAGES) stages = PAIR_MAX_STAGES;
+  const int smem = stages * stage_bytes + PAIR_BAR_BYTES + 1024;
+  const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + bn - 1) / bn);
+  const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+  gemm_bf16_nt_pair_kernel<OUT_F32, ROPE><<<2 * pairs, GEMM_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages);
+  return check_launch("gemm_bf16_nt_pair");
+}
+
+// M > 128 rows: CTA-pair kernel; tiny-M problems (adapter prompts, a handful of labelled rows) stay on
+// the single-CTA kernel.
+static bool use_pair(int M, int N) { return g_force_bn >= 0 && M > GEMM_BM && N >= 64; }
+static int pair_bn(int M, int N) {
+  if (g_force_bn > 0) return g_force_bn;
+  if (N < 128) return ((N + 15) / 16) * 16 < 64 ? 64 : ((N + 15) / 16) * 16;
+  return choose_pair_bn(M, N);
 }
 
 static int check_gemm_args(const void* A, int lda, const void* B, int ldb, const void* C, int ldc, const void* R, int ldr, int M, int N, int K) {
@@ -369,6 +628,11 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
   const bf16* a = reinterpret_cast<const bf16*>(A);
   const bf16* b = reinterpret_cast<const bf16*>(B);
   GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1};
+  if (use_pair(M, N)) {
+    const int bn = pair_bn(M, N);
+    return out_fp32 ? launch_gemm_pair<true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s)
+                    : launch_gemm_pair<false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s);
+  }
   if (prefer_bn128(M, N)) {
     return out_fp32 ? launch_gemm<128, true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s)
                     : launch_gemm<128, false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
@@ -388,6 +652,15 @@ extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf
   const bf16* a = reinterpret_cast<const bf16*>(A);
   const bf16* b = reinterpret_cast<const bf16*>(B);
   GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S};
+  if (use_pair(M, N)) return launch_gemm_pair<false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, pair_bn(M, N), s);
   if (prefer_bn128(M, N)) return launch_gemm<128, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   return launch_gemm<256, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
+}
+
+/* Test / tuning hook: force the CTA-pair tile width (multiple of 16 in [64,256]); 0 restores the
+ * heuristic, -1 forces the single-CTA kernel. Returns the previous setting. */
+extern "C" int fvqa_gemm_debug_force_bn(int bn) {
+  const int prev = g_force_bn;
+  if (bn == 0 || bn == -1 || (bn >= 64 && bn <= 256 && bn % 16 == 0)) g_force_bn = bn;
+  return prev;
 }

@@ -36,6 +36,46 @@ class GemmTimer:
 GEMM_TIMER: Optional[GemmTimer] = None
 
 
+class OpTimer:
+    """Optional CUDA-event timing of EVERY op wrapper below (tools/step_breakdown.py): per-op in-step device time
+    including the launch gap before it. Off (None) on the product path."""
+
+    def __init__(self):
+        self.records = []          # (name, start_event, end_event)
+
+    def summary(self):
+        agg = {}
+        for name, a, b in self.records:
+            t = agg.setdefault(name, [0, 0.0])
+            t[0] += 1
+            t[1] += a.elapsed_time(b)
+        return agg
+
+
+OP_TIMER: Optional[OpTimer] = None
+
+
+def _timed(fn):
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        tm = OP_TIMER
+        if tm is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a, **k)
+        e1.record()
+        name = fn.__name__
+        if name == "gemm_nt":
+            M = k.get("M") or a[0].shape[0]
+            name = f"gemm_nt[{M}x{a[1].shape[0]}x{a[0].shape[1]}]"
+        tm.records.append((name, e0, e1))
+        return out
+    return wrapper
+
+
 def _count(n: int = 1):
     global LAUNCHES
     LAUNCHES += n
@@ -57,6 +97,7 @@ def _chk(t: torch.Tensor, dtype, name: str):
 F32 = torch.float32
 
 
+@_timed
 def rmsnorm_fwd(x, w, eps: float, y=None, rstd=None):
     _chk(x, F32, "x"); _chk(w, BF16, "w")
     rows, dim = x.shape
@@ -66,6 +107,7 @@ def rmsnorm_fwd(x, w, eps: float, y=None, rstd=None):
     return y, rstd
 
 
+@_timed
 def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None, dx_bf16=None):
     """Returns (dx fp32, dx_bf16). dx = dres + rmsnorm'(x).dy"""
     _chk(dy, BF16, "dy"); _chk(x, F32, "x")
@@ -75,6 +117,7 @@ def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None, dx_bf16=None):
     return dx, dx_bf16
 
 
+@_timed
 def rmsnorm_gather_fwd(x, idx, w, eps: float, y=None, rstd=None):
     _chk(x, F32, "x"); _chk(idx, torch.int32, "idx")
     rows, dim = idx.numel(), x.shape[-1]
@@ -84,6 +127,7 @@ def rmsnorm_gather_fwd(x, idx, w, eps: float, y=None, rstd=None):
     return y, rstd
 
 
+@_timed
 def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dx_bf16=None):
     rows, dim = idx.numel(), x.shape[-1]
     check(_lib.lib().fvqa_rmsnorm_scatter_bwd(ptr(dy), ptr(x), ptr(idx), ptr(w), ptr(rstd), ptr(dx), ptr(dx_bf16), rows, dim, stream()), "rmsnorm_scatter_bwd")
@@ -91,6 +135,7 @@ def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dx_bf16=None):
 
 
 # ------------------------------------------------------------------ SwiGLU
+@_timed
 def swiglu_fwd(g, c=None):
     _chk(g, BF16, "g")
     rows, two_hid = g.shape
@@ -100,6 +145,7 @@ def swiglu_fwd(g, c=None):
     return c
 
 
+@_timed
 def swiglu_bwd(dc, g, dg=None):
     _chk(dc, BF16, "dc"); _chk(g, BF16, "g")
     rows, hid = dc.shape
@@ -109,6 +155,7 @@ def swiglu_bwd(dc, g, dg=None):
 
 
 # ------------------------------------------------------------------ GEMM
+@_timed
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
             out_fp32: bool = False, M: Optional[int] = None) -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[N,K]^T (+ residual). a/b may be row-strided views (last dim contiguous)."""
@@ -134,6 +181,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     return out
 
 
+@_timed
 def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """QKV projection with RoPE applied to the q|k columns in the GEMM epilogue (bf16 out)."""
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
@@ -153,6 +201,7 @@ def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd:
 
 
 # ------------------------------------------------------------------ attention
+@_timed
 def attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F, out=None, lse=None):
     _chk(qkv, BF16, "qkv"); _chk(vstart, torch.int32, "vstart")
     assert akv.dtype == BF16 and akv.stride(-1) == 1
@@ -167,6 +216,7 @@ def attn_bwd_ws_bytes(n_seq, S, H, hd, A) -> int:
     return int(_lib.load().fvqa_attn_bwd_ws_bytes(n_seq, S, H, hd, A))
 
 
+@_timed
 def attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F,
              dqkv=None, dakv=None, dgate1=None, dgate2=None, ws=None):
     dev = qkv.device
@@ -183,6 +233,7 @@ def attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S,
 
 
 # ------------------------------------------------------------------ input side
+@_timed
 def visual_proj_fwd(video2d, wv, out=None):
     _chk(video2d, torch.float32, "video"); _chk(wv, torch.float32, "wv")
     rows, vdim = video2d.shape
@@ -192,6 +243,7 @@ def visual_proj_fwd(video2d, wv, out=None):
     return out
 
 
+@_timed
 def visual_proj_bwd(dvf2d, video2d, dwv=None):
     rows, vdim = video2d.shape
     dim = dvf2d.shape[1]
@@ -200,6 +252,7 @@ def visual_proj_bwd(dvf2d, video2d, dwv=None):
     return dwv
 
 
+@_timed
 def build_h0_fwd(tok_emb, ids, labels, vstart, seq_video, qav_index, vf32, temporal, n_seq, S, F, h0=None):
     dim = tok_emb.shape[1]
     h0 = torch.empty(n_seq * S, dim, dtype=torch.float32, device=tok_emb.device) if h0 is None else h0
@@ -208,6 +261,7 @@ def build_h0_fwd(tok_emb, ids, labels, vstart, seq_video, qav_index, vf32, tempo
     return h0
 
 
+@_timed
 def build_h0_bwd(dh0, vstart, seq_video, qav_index, n_seq, n_video, S, F, dvf=None):
     dim = dh0.shape[1]
     dvf = torch.empty(n_video * F, dim, dtype=torch.float32, device=dh0.device) if dvf is None else dvf
@@ -215,6 +269,7 @@ def build_h0_bwd(dh0, vstart, seq_video, qav_index, n_seq, n_video, S, F, dvf=No
     return dvf
 
 
+@_timed
 def video_grad_finish(dvf, dvf_qav, n_video, F, dtemporal=None):
     dim = dvf.shape[1]
     dtemporal = torch.empty(F, dim, dtype=torch.float32, device=dvf.device) if dtemporal is None else dtemporal
@@ -223,6 +278,7 @@ def video_grad_finish(dvf, dvf_qav, n_video, F, dtemporal=None):
 
 
 # ------------------------------------------------------------------ heads
+@_timed
 def ce_fwd(logits, target, row_loss=None, row_lse=None):
     _chk(target, torch.int32, "target")
     assert logits.dtype == torch.float32 and logits.stride(-1) == 1
@@ -234,6 +290,7 @@ def ce_fwd(logits, target, row_loss=None, row_lse=None):
     return row_loss, row_lse
 
 
+@_timed
 def ce_bwd(logits, target, row_lse, gscale, inv_count: float, dlogits=None):
     rows, V = target.numel(), logits.shape[1]
     dlogits = torch.empty(rows, V, dtype=BF16, device=logits.device) if dlogits is None else dlogits
@@ -242,11 +299,13 @@ def ce_bwd(logits, target, row_lse, gscale, inv_count: float, dlogits=None):
     return dlogits
 
 
+@_timed
 def sum_scale(v, rows: int, scale: float, out):
     check(_lib.lib().fvqa_sum_scale(ptr(v), rows, scale, ptr(out), stream()), "sum_scale")
     return out
 
 
+@_timed
 def qav_loss_fwd(hn, vf32, row_video, target, tau: float, F: int, row_loss=None, prob=None):
     rows, dim = hn.shape
     dev = hn.device
@@ -256,6 +315,7 @@ def qav_loss_fwd(hn, vf32, row_video, target, tau: float, F: int, row_loss=None,
     return row_loss, prob
 
 
+@_timed
 def qav_loss_bwd(hn, vf32, row_video, target, prob, gscale, inv_count: float, tau: float, n_video: int, F: int, dhn=None, dvf_qav=None):
     rows, dim = hn.shape
     dev = hn.device
@@ -266,11 +326,13 @@ def qav_loss_bwd(hn, vf32, row_video, target, prob, gscale, inv_count: float, ta
     return dhn, dvf_qav
 
 
+@_timed
 def scatter_rows(row_val, dst_index, dst):
     check(_lib.lib().fvqa_scatter_rows(ptr(row_val), ptr(dst_index), ptr(dst), dst_index.numel(), stream()), "scatter_rows")
     return dst
 
 
+@_timed
 def option_score(token_loss: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     _chk(token_loss, torch.float32, "token_loss")
     n_items, n_opt, ln = token_loss.shape
@@ -280,6 +342,7 @@ def option_score(token_loss: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return pred, mean
 
 
+@_timed
 def f32_to_bf16(src, dst=None):
     _chk(src, torch.float32, "src")
     dst = torch.empty(src.shape, dtype=BF16, device=src.device) if dst is None else dst

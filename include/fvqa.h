@@ -73,6 +73,10 @@ int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int 
                            int M, int N, int K, const float* rope_cos, const float* rope_sin,
                            int rope_cols, int hd, int S, void* stream);
 
+/* Test / tuning hook for the GEMM tile choice: bn = multiple of 16 in [64,256] forces that CTA-pair
+ * tile width, 0 restores the heuristic, -1 forces the single-CTA kernel. Returns the previous value. */
+int fvqa_gemm_debug_force_bn(int bn);
+
 /* ---- fused attention (llama/model.py:61-67 RoPE, :87-126 attention incl. adapter branch). --------
  * qkv  [n_seq*S, 3*H*hd] bf16 (q | k | v) with q,k ALREADY rotated (fvqa_gemm_bf16_nt_rope).
  * akv  [>=A rows, ld akv_ld] bf16: adapter keys (cols 0..H*hd) | adapter values (cols H*hd..2*H*hd),
@@ -91,6 +95,8 @@ int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const 
  * Per-CTA partials of the shared-parameter gradients go to `ws` (size from fvqa_attn_bwd_ws_bytes)
  * and are reduced in a fixed order into dakv [A, 2*H*hd] fp32 (dK_a | dV_a), dgate1[H], dgate2[H]
  * (fp32, overwritten). */
+/* Test hook: 0 forces the mma.sync kernels, 1 (default) lets S <= 128, hd = 128 take the tcgen05 path. */
+int fvqa_attn_debug_use_tc(int on);
 int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A);
 int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos,
                   const float* rope_sin, const float* gate1, const float* gate2, const int32_t* vstart,

@@ -102,6 +102,26 @@ def test_gemm_nt(fvqa_lib, M, N, K):
     assert relerr(cr32, ref + r32) < 2e-4
 
 
+@pytest.mark.parametrize("bn", [-1, 64, 128, 144, 176, 208, 240, 256])
+def test_gemm_pair_tile_widths(fvqa_lib, bn):
+    """The CTA-pair (cta_group::2) kernel for every runtime tile width (and the single-CTA kernel, bn=-1)
+    on ragged shapes: M not a multiple of 256 (peer CTA partly / fully out of range), N not a multiple of bn."""
+    from flipped_vqa_b200 import ops
+    for (M, N, K) in [(200, 384, 128), (384, 1536, 256), (650, 1000, 192), (129, 72, 64)]:
+        a = bf16_randn(M, K, seed=20)
+        b = bf16_randn(N, K, std=0.05, seed=21)
+        r32 = torch.randn(M, N, device="cuda")
+        ref = a.float() @ b.float().t()
+        prev = fvqa_lib.fvqa_gemm_debug_force_bn(bn)
+        try:
+            c32 = ops.gemm_nt(a, b, residual=r32, out_fp32=True)
+            c16 = ops.gemm_nt(a, b)
+        finally:
+            fvqa_lib.fvqa_gemm_debug_force_bn(prev)
+        assert relerr(c32, ref + r32) < 2e-4, (M, N, K, bn)
+        assert relerr(c16, ref) < 5e-3, (M, N, K, bn)
+
+
 @pytest.mark.parametrize("S,H,hd,B", [(48, 2, 64, 3), (128, 4, 128, 2)])
 def test_gemm_rope_epilogue(fvqa_lib, S, H, hd, B):
     """QKV projection with RoPE folded into the epilogue == plain projection followed by the oracle's

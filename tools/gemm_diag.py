@@ -1,55 +1,82 @@
-"""GPU diagnostic for the tcgen05 GEMM: error structure per shape + quick timing (not a test)."""
-import sys, os, time
+"""GPU diagnostic for the tcgen05 GEMMs (not a test): correctness of the CTA-pair kernel for every tile
+width, then timing of the 7B/13B layer shapes per tile width against the heuristic's choice, the
+single-CTA kernel and cuBLAS (torch.matmul)."""
+import os
+import sys
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from flipped_vqa_b200 import ops, _lib
+from flipped_vqa_b200 import _lib, ops
+
+
+def force(bn):
+    return _lib.lib().fvqa_gemm_debug_force_bn(bn)
+
+
+def check(M, N, K, bn, out_fp32=True, residual=False):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    ref = a.float() @ b.float().t()
+    r = torch.randn(M, N, device="cuda") if residual else None
+    if residual:
+        ref = ref + r
+    force(bn)
+    try:
+        c = ops.gemm_nt(a, b, out_fp32=out_fp32, residual=(r if out_fp32 or r is None else r.to(torch.bfloat16)))
+        torch.cuda.synchronize()
+    finally:
+        force(0)
+    rel = float((c.float() - ref).norm() / ref.norm())
+    return rel, int(torch.isnan(c.float()).sum())
+
+
+def time_gemm(fn, iters=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
 
 def main():
     _lib.lib()
-    torch.manual_seed(0)
-    for (M, N, K) in [(128, 256, 64), (128, 256, 128), (128, 256, 256), (128, 128, 64), (256, 512, 256), (200, 384, 128), (3072, 4096, 4096)]:
-        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-        b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
-        ref = a.float() @ b.float().t()
-        try:
-            c = ops.gemm_nt(a, b, out_fp32=True)
-            torch.cuda.synchronize()
-        except Exception as e:
-            print("GEMM", M, N, K, "EXC", e); continue
-        err = (c - ref).abs()
-        rel = float((c - ref).norm() / ref.norm())
-        print(f"GEMM {M}x{N}x{K}: relerr {rel:.3e} maxabs {float(err.max()):.3e} nan {int(torch.isnan(c).sum())}")
-        if rel > 1e-3:
-            bad = err > (1e-2 * ref.abs().max())
-            rows = bad.any(1).nonzero().flatten()
-            cols = bad.any(0).nonzero().flatten()
-            print("  bad rows:", rows[:16].tolist(), "... n=", rows.numel(), " bad cols:", cols[:16].tolist(), "... n=", cols.numel())
-            print("  c[0,:8]", c[0, :8].tolist()); print("  r[0,:8]", ref[0, :8].tolist())
-            # is it a K-permutation problem? compare with partial-K references
-            for kk in range(64, K + 1, 64):
-                rk = a[:, :kk].float() @ b[:, :kk].float().t()
-                print(f"   vs K[:{kk}] relerr {float((c - rk).norm() / rk.norm()):.3e}")
-                if kk >= 256: break
-    # timing
-    for (M, N, K) in [(3072, 12288, 4096), (3072, 4096, 4096), (3072, 22016, 4096), (3072, 4096, 11008), (3072, 11008, 4096), (3072, 4096, 22016), (3072, 4096, 12288)]:
-        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-        b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
-        c = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        for _ in range(3): ops.gemm_nt(a, b, out=c)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10): ops.gemm_nt(a, b, out=c)
-        e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        for _ in range(3): torch.matmul(a, b.t(), out=c)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(10): torch.matmul(a, b.t(), out=c)
-        e1.record(); torch.cuda.synchronize()
-        ms2 = e0.elapsed_time(e1) / 10
-        fl = 2.0 * M * N * K
-        print(f"TIME {M}x{N}x{K}: ours {ms:.3f} ms {fl / ms / 1e9:.0f} TFLOP/s | cublas {ms2:.3f} ms {fl / ms2 / 1e9:.0f} TFLOP/s")
+    mode = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if mode in ("all", "check"):
+        bad = 0
+        for (M, N, K) in [(256, 256, 64), (256, 512, 256), (200, 384, 128), (384, 1536, 256), (1950, 4096, 512), (3072, 4096, 4096), (180, 32000, 256)]:
+            for bn in (-1, 64, 128, 144, 176, 192, 240, 256):
+                if bn > 0 and M <= 128:
+                    continue
+                rel, nan = check(M, N, K, bn, out_fp32=True, residual=(bn in (176, 256)))
+                tol = 2e-4
+                flag = "" if (rel < tol and nan == 0) else "   <<<<<< BAD"
+                bad += bool(flag)
+                print(f"CHECK {M}x{N}x{K} bn={bn:4d}: relerr {rel:.3e} nan {nan}{flag}", flush=True)
+        print("check failures:", bad, flush=True)
+    if mode in ("all", "time"):
+        shapes = [(3072, 12288, 4096), (3072, 4096, 4096), (3072, 22016, 4096), (3072, 4096, 11008), (3072, 11008, 4096),
+                  (3072, 4096, 22016), (3072, 4096, 12288), (3072, 5120, 5120), (3072, 5120, 13824), (2304, 4096, 11008), (1950, 4096, 11008)]
+        for (M, N, K) in shapes:
+            a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+            b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+            c = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            fl = 2.0 * M * N * K
+            res = []
+            for bn in (0, -1, 256, 240, 224, 208, 192, 176, 144, 128):
+                force(bn)
+                ms = time_gemm(lambda: ops.gemm_nt(a, b, out=c))
+                res.append((bn, fl / ms / 1e9))
+            force(0)
+            ms2 = time_gemm(lambda: torch.matmul(a, b.t(), out=c))
+            txt = " ".join(f"{('auto' if bn == 0 else '1cta' if bn < 0 else bn)}:{tf:.0f}" for bn, tf in res)
+            print(f"TIME {M}x{N}x{K}: {txt} | cublas {fl / ms2 / 1e9:.0f}  (TFLOP/s)", flush=True)
+
 
 if __name__ == "__main__":
     main()

@@ -13,7 +13,7 @@ fi
 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
 cat $OUT/bench_$TAG.json
 python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --sample-layers 0 > $OUT/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fvqa -s 2090 -c 700 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(attn|gemm|rmsnorm|swiglu|build_h0|ce_|qav|sum_scale|f32_to|video|visual|scatter|option)" -s 2090 -c 700 --csv \
     --log-file $OUT/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --sample-layers 0 > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?"
 python tools/attn_bench.py > $OUT/attn_bench_$TAG.log 2>&1 &&
