@@ -1,0 +1,98 @@
+// Skinny GEMM  C[M,N] = A[M,K] * B[N,K]^T  for M <= 16: the adapter-prompt projections
+//   akv_l      = adapter_l[A=10, d] . [Wk;Wv]_l^T                    (llama/model.py:99-100)
+//   d adapter_l = dK_a . Wk + dV_a . Wv  = dakv[10, 2d] . Wkv_t^T     (its backward; SURVEY.md 8(a) addendum)
+// These read a 67 MB weight block for 0.7 GFLOP: HBM/L2-bound, and a 128-row tcgen05 tile would waste
+// 92 % of every MMA and serialise 64-128 k-blocks per CTA. Here a CTA of 8 warps owns 8*NT output columns;
+// warp w streams K-slice w of the weight rows with 16-byte loads straight into mma.sync.m16n8k16
+// B fragments (the k index inside each 32-element chunk is permuted identically for A and B, which a
+// contraction does not see), and the 8 partial tiles are summed in shared memory in a fixed order.
+#include "common.cuh"
+
+namespace fvqa {
+
+namespace {
+
+__device__ __forceinline__ void mma16816_sk(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int SK_WARPS = 8;
+constexpr int SK_THREADS = SK_WARPS * 32;
+
+}  // namespace
+
+template <int NT, bool OUT_F32>
+__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const bf16* __restrict__ A, int lda, const bf16* __restrict__ B, int ldb,
+                                                                 void* __restrict__ C, int ldc, int M, int N, int K) {
+  __shared__ float red[SK_WARPS][16][8 * NT + 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = blockIdx.x * 8 * NT;
+  const int kslice = K / SK_WARPS;                     // multiple of 32 (checked by the launcher)
+  const int k_begin = warp * kslice;
+  const bool row_lo = g < M, row_hi = g + 8 < M;
+  const uint4* a_lo = reinterpret_cast<const uint4*>(A + static_cast<long>(row_lo ? g : 0) * lda + k_begin + 8 * t);
+  const uint4* a_hi = reinterpret_cast<const uint4*>(A + static_cast<long>(row_hi ? g + 8 : 0) * lda + k_begin + 8 * t);
+  const uint4* b_ptr[NT];
+  bool b_ok[NT];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int col = n0 + j * 8 + g;
+    b_ok[j] = col < N;
+    b_ptr[j] = reinterpret_cast<const uint4*>(B + static_cast<long>(b_ok[j] ? col : 0) * ldb + k_begin + 8 * t);
+  }
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const int chunks = kslice / 32;                      // 32 k per chunk = 4 uint4 per row
+#pragma unroll 8
+  for (int c = 0; c < chunks; ++c) {
+    const uint4 al = row_lo ? __ldg(a_lo + 4 * c) : zero;
+    const uint4 ah = row_hi ? __ldg(a_hi + 4 * c) : zero;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      const uint4 b = b_ok[j] ? __ldg(b_ptr[j] + 4 * c) : zero;
+      mma16816_sk(acc[j], al.x, ah.x, al.y, ah.y, b.x, b.y);
+      mma16816_sk(acc[j], al.z, ah.z, al.w, ah.w, b.z, b.w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    red[warp][g][j * 8 + 2 * t] = acc[j][0];
+    red[warp][g][j * 8 + 2 * t + 1] = acc[j][1];
+    red[warp][g + 8][j * 8 + 2 * t] = acc[j][2];
+    red[warp][g + 8][j * 8 + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 16 * 8 * NT; idx += SK_THREADS) {
+    const int r = idx / (8 * NT), cc = idx - r * (8 * NT);
+    if (r < M && n0 + cc < N) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < SK_WARPS; ++w) s += red[w][r][cc];
+      if constexpr (OUT_F32) reinterpret_cast<float*>(C)[static_cast<long>(r) * ldc + n0 + cc] = s;
+      else reinterpret_cast<bf16*>(C)[static_cast<long>(r) * ldc + n0 + cc] = __float2bfloat16_rn(s);
+    }
+  }
+}
+
+bool gemm_skinny_supported(int M, int K, const void* R) { return M <= 16 && R == nullptr && K % (SK_WARPS * 32) == 0; }
+
+int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
+                cudaStream_t stream) {
+  // widest column block that still gives every SM ~2 CTAs
+  const int nt = (N / 32 >= 2 * num_sms) ? 4 : (N / 16 >= 2 * num_sms ? 2 : 1);
+  const int cols = 8 * nt;
+  const dim3 grid((N + cols - 1) / cols);
+#define FVQA_SK(NT_)                                                                                                   \
+  if (out_fp32) gemm_skinny_kernel<NT_, true><<<grid, SK_THREADS, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K);        \
+  else gemm_skinny_kernel<NT_, false><<<grid, SK_THREADS, 0, stream>>>(A, lda, B, ldb, C, ldc, M, N, K);
+  if (nt == 4) { FVQA_SK(4) } else if (nt == 2) { FVQA_SK(2) } else { FVQA_SK(1) }
+#undef FVQA_SK
+  return check_launch("gemm_skinny");
+}
+
+}  // namespace fvqa

@@ -44,7 +44,12 @@ struct GemmEpi {
   const float* cosT;  // [S, hd/2]
   const float* sinT;
   int rope_cols, hd, S;
+  // SwiGLU-fused epilogues of the CTA-pair kernel (EPI_SWIGLU_FWD / EPI_SWIGLU_BWD)
+  void* aux;          // FWD: c = silu(a) * b output [M, hid];  BWD: g = [a | b] input [M, 2*hid]
+  int ld_aux, hid;
 };
+
+enum { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_SWIGLU_FWD = 2, EPI_SWIGLU_BWD = 3 };
 
 // One epilogue chunk: NC (32 or 16) consecutive fp32 accumulator columns of one output row held in
 // registers -> optional RoPE rotation / residual add -> global store (bf16 or fp32).
@@ -259,7 +264,7 @@ constexpr int PAIR_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
 __host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GEMM_BK * 2 + (bn / 2) * GEMM_BK * 2; }
 
-template <bool OUT_F32, bool ROPE>
+template <bool OUT_F32, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages) {
@@ -278,8 +283,11 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  constexpr bool ROPE = (EPI == EPI_ROPE);
   const int tiles_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-  const int tiles_n = (N + BN - 1) / BN;
+  // EPI_SWIGLU_FWD: B = [W1; W3] (2*hid rows); tile tn pairs W1 rows [128 tn, +128) (CTA 0's half of B)
+  // with W3 rows [128 tn, +128) (CTA 1's half) so that a row's a- and b-values meet in one accumulator.
+  const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = K / GEMM_BK;
 
@@ -314,7 +322,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
         const int m0 = (tile % tiles_m) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
-        const int n0 = (tile / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
+        const int n0 = (EPI == EPI_SWIGLU_FWD) ? (tile / tiles_m) * 128 + static_cast<int>(rank) * epi.hid
+                                               : (tile / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * stage_bytes;
@@ -372,20 +381,89 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      if constexpr (EPI == EPI_SWIGLU_FWD) {
+        // columns [0,128) = a = W1 x, [128,256) = b = W3 x of hidden units [128 tn, +128): write g = [a | b] (bf16,
+        // saved for backward) and c = silu(a) * b computed from the ROUNDED a, b (bit-identical to swiglu_fwd_kernel)
+        const int hcol = (tile / tiles_m) * 128;
 #pragma unroll 1
-      for (int c = 0; c < n32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
-        tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < N) epilogue_store<32, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
-      }
-      if (BN & 16) {
-        uint32_t v[32];
-        tmem_ld_32x16(tbase + static_cast<uint32_t>(n32 * 32), v);
-        tmem_ld_wait();
-        const int col0 = n0 + n32 * 32;
-        if (row_ok && col0 < N) epilogue_store<16, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
+        for (int c = 0; c < 4; ++c) {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), va);
+          tmem_ld_32x32(tbase + static_cast<uint32_t>(128 + c * 32), vb);
+          tmem_ld_wait();
+          if (row_ok) {
+            bf16* grow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + hcol + c * 32;
+            bf16* crow = reinterpret_cast<bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + hcol + c * 32;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float fa[8], fb[8], o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { fa[e] = __uint_as_float(va[q * 8 + e]); fb[e] = __uint_as_float(vb[q * 8 + e]); }
+              const uint4 pa = pack8(fa), pb = pack8(fb);
+              unpack8(pa, fa);
+              unpack8(pb, fb);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = fa[e] / (1.f + __expf(-fa[e])) * fb[e];
+              *reinterpret_cast<uint4*>(grow + q * 8) = pa;
+              *reinterpret_cast<uint4*>(grow + epi.hid + q * 8) = pb;
+              *reinterpret_cast<uint4*>(crow + q * 8) = pack8(o);
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_SWIGLU_BWD) {
+        // accumulator = dc = d(silu(a) * b) for hidden units [n0, n0 + BN): read g = [a | b], write
+        // dg = [dc b s (1 + a (1 - s)) | dc a s] (bit-identical to swiglu_bwd_kernel on the bf16-rounded dc)
+#pragma unroll 1
+        for (int c = 0; c < n32; ++c) {
+          const int col0 = n0 + c * 32;
+          uint4 ga[4], gb[4];
+          const bool ok = row_ok && col0 < N;
+          if (ok) {
+            const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + col0);
+            const uint4* gr2 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + epi.hid + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { ga[q] = __ldg(gr + q); gb[q] = __ldg(gr2 + q); }
+          }
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          if (ok) {
+            bf16* drow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float a[8], b[8], d[8], da[8], db[8];
+              unpack8(ga[q], a);
+              unpack8(gb[q], b);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) d[e] = __uint_as_float(v[q * 8 + e]);
+              unpack8(pack8(d), d);                                   // dc as the unfused path sees it (bf16)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float sg = 1.f / (1.f + __expf(-a[e]));
+                da[e] = d[e] * b[e] * sg * (1.f + a[e] * (1.f - sg));
+                db[e] = d[e] * a[e] * sg;
+              }
+              *reinterpret_cast<uint4*>(drow + q * 8) = pack8(da);
+              *reinterpret_cast<uint4*>(drow + epi.hid + q * 8) = pack8(db);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < n32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          const int col0 = n0 + c * 32;
+          if (row_ok && col0 < N) epilogue_store<32, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
+        }
+        if (BN & 16) {
+          uint32_t v[32];
+          tmem_ld_32x16(tbase + static_cast<uint32_t>(n32 * 32), v);
+          tmem_ld_wait();
+          const int col0 = n0 + n32 * 32;
+          if (row_ok && col0 < N) epilogue_store<16, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -462,13 +540,15 @@ int gemm_init() {
   FVQA_SET_SMEM(256, false, true)
   FVQA_SET_SMEM(128, false, true)
 #undef FVQA_SET_SMEM
-#define FVQA_SET_PAIR(F32, ROPE)                                                                                   \
-  e = cudaFuncSetAttribute(gemm_bf16_nt_pair_kernel<F32, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+#define FVQA_SET_PAIR(F32, EPI)                                                                                   \
+  e = cudaFuncSetAttribute(gemm_bf16_nt_pair_kernel<F32, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                            PAIR_SMEM_LIMIT);                                                                       \
   FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm pair): %s", cudaGetErrorString(e));
-  FVQA_SET_PAIR(false, false)
-  FVQA_SET_PAIR(true, false)
-  FVQA_SET_PAIR(false, true)
+  FVQA_SET_PAIR(false, EPI_PLAIN)
+  FVQA_SET_PAIR(true, EPI_PLAIN)
+  FVQA_SET_PAIR(false, EPI_ROPE)
+  FVQA_SET_PAIR(false, EPI_SWIGLU_FWD)
+  FVQA_SET_PAIR(false, EPI_SWIGLU_BWD)
 #undef FVQA_SET_PAIR
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return FVQA_OK;
@@ -539,6 +619,11 @@ static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, 
   return check_launch("gemm_bf16_nt");
 }
 
+// M <= 16 (adapter-prompt projections): gemm_skinny.cu
+bool gemm_skinny_supported(int M, int K, const void* R);
+int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
+                cudaStream_t stream);
+
 // ---- CTA-pair path ---------------------------------------------------------------------------
 static int g_force_bn = 0;        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
 
@@ -564,7 +649,7 @@ static int choose_pair_bn(int M, int N) {
   return best;
 }
 
-template <bool OUT_F32, bool ROPE>
+template <bool OUT_F32, int EPI>
 static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
                             int N, int K, int bn, cudaStream_t stream) {
   CUtensorMap ta, tb;
@@ -576,9 +661,10 @@ static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void
   int stages = (PAIR_SMEM_LIMIT - 1024 - PAIR_BAR_BYTES) / stage_bytes;
   if (stages > PAIR_MAX_STAGES) stages = PAIR_MAX_STAGES;
   const int smem = stages * stage_bytes + PAIR_BAR_BYTES + 1024;
-  const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * ((N + bn - 1) / bn);
+  const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + bn - 1) / bn;
+  const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tiles_n;
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_bf16_nt_pair_kernel<OUT_F32, ROPE><<<2 * pairs, GEMM_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages);
+  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, GEMM_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages);
   return check_launch("gemm_bf16_nt_pair");
 }
 
@@ -627,11 +713,12 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bf16* a = reinterpret_cast<const bf16*>(A);
   const bf16* b = reinterpret_cast<const bf16*>(B);
-  GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1};
+  GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1, nullptr, 0, 0};
+  if (g_force_bn == 0 && gemm_skinny_supported(M, K, R)) return gemm_skinny(a, lda, b, ldb, C, ldc, M, N, K, out_fp32, g_num_sms, s);
   if (use_pair(M, N)) {
     const int bn = pair_bn(M, N);
-    return out_fp32 ? launch_gemm_pair<true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s)
-                    : launch_gemm_pair<false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s);
+    return out_fp32 ? launch_gemm_pair<true, EPI_PLAIN>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s)
+                    : launch_gemm_pair<false, EPI_PLAIN>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s);
   }
   if (prefer_bn128(M, N)) {
     return out_fp32 ? launch_gemm<128, true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s)
@@ -651,8 +738,8 @@ extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bf16* a = reinterpret_cast<const bf16*>(A);
   const bf16* b = reinterpret_cast<const bf16*>(B);
-  GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S};
-  if (use_pair(M, N)) return launch_gemm_pair<false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, pair_bn(M, N), s);
+  GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S, nullptr, 0, 0};
+  if (use_pair(M, N)) return launch_gemm_pair<false, EPI_ROPE>(a, lda, b, ldb, C, ldc, epi, M, N, K, pair_bn(M, N), s);
   if (prefer_bn128(M, N)) return launch_gemm<128, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   return launch_gemm<256, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
 }
@@ -663,4 +750,30 @@ extern "C" int fvqa_gemm_debug_force_bn(int bn) {
   const int prev = g_force_bn;
   if (bn == 0 || bn == -1 || (bn >= 64 && bn <= 256 && bn % 16 == 0)) g_force_bn = bn;
   return prev;
+}
+
+/* W1|W3 projection with SwiGLU in the epilogue (llama/model.py:142): g[M, 2*hid] = x W13^T (bf16, saved for
+ * backward) and c[M, hid] = silu(g[:, :hid]) * g[:, hid:] in one pass. W13 = [W1; W3] is [2*hid, K]. */
+extern "C" int fvqa_gemm_swiglu_fwd(const fvqa_bf16* X, int ldx, const fvqa_bf16* W13, int ldw, fvqa_bf16* G, int ldg, fvqa_bf16* Cc,
+                                    int ldcc, int M, int hid, int K, void* stream) {
+  int rc = check_gemm_args(X, ldx, W13, ldw, G, ldg, nullptr, 0, M, 2 * hid, K);
+  if (rc) return rc;
+  FVQA_REQUIRE(hid % 128 == 0 && ldcc % 8 == 0 && ldcc >= hid && Cc != nullptr && (reinterpret_cast<uintptr_t>(Cc) & 15) == 0,
+               FVQA_ERR_UNSUPPORTED, "gemm_swiglu_fwd: hid=%d must be a multiple of 128 (ldc=%d)", hid, ldcc);
+  GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, Cc, ldcc, hid};
+  return launch_gemm_pair<false, EPI_SWIGLU_FWD>(reinterpret_cast<const bf16*>(X), ldx, reinterpret_cast<const bf16*>(W13), ldw, G, ldg, epi,
+                                                 M, 2 * hid, K, 256, static_cast<cudaStream_t>(stream));
+}
+
+/* Backward of the above through W2 and the SwiGLU: dg[M, 2*hid] = swiglu'(g) . (dY W2t^T) where the
+ * intermediate dc = dY W2t^T [M, hid] never leaves the SM. W2t is [hid, K] (the transposed w2). */
+extern "C" int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int ldw, const fvqa_bf16* G, int ldg,
+                                    fvqa_bf16* dG, int lddg, int M, int hid, int K, void* stream) {
+  int rc = check_gemm_args(dY, ldy, W2t, ldw, dG, lddg, nullptr, 0, M, hid, K);
+  if (rc) return rc;
+  FVQA_REQUIRE(hid % 32 == 0 && ldg % 8 == 0 && ldg >= 2 * hid && lddg >= 2 * hid && G != nullptr && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+               FVQA_ERR_UNSUPPORTED, "gemm_swiglu_bwd: hid=%d must be a multiple of 32 (ldg=%d lddg=%d)", hid, ldg, lddg);
+  GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, const_cast<fvqa_bf16*>(G), ldg, hid};
+  return launch_gemm_pair<false, EPI_SWIGLU_BWD>(reinterpret_cast<const bf16*>(dY), ldy, reinterpret_cast<const bf16*>(W2t), ldw, dG, lddg, epi,
+                                                 M, hid, K, 256, static_cast<cudaStream_t>(stream));
 }

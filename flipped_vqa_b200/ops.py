@@ -200,6 +200,51 @@ def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd:
     return out
 
 
+@_timed
+def gemm_swiglu_fwd(x: torch.Tensor, w13: torch.Tensor, g: Optional[torch.Tensor] = None, c: Optional[torch.Tensor] = None):
+    """g = x @ [W1;W3]^T (saved for backward) and c = silu(g[:, :hid]) * g[:, hid:] with the SwiGLU in the GEMM epilogue
+    (`llama/model.py:142`). Falls back to GEMM + swiglu kernel when hid is not a multiple of 128. Returns (g, c)."""
+    M, K = x.shape
+    hid = w13.shape[0] // 2
+    g = torch.empty(M, 2 * hid, dtype=BF16, device=x.device) if g is None else g
+    c = torch.empty(M, hid, dtype=BF16, device=x.device) if c is None else c
+    if hid % 128 != 0:
+        gemm_nt(x, w13, out=g)
+        swiglu_fwd(g, c)
+        return g, c
+    tm = GEMM_TIMER
+    if tm is not None and tm.active:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.lib().fvqa_gemm_swiglu_fwd(ptr(x), x.stride(0), ptr(w13), w13.stride(0), ptr(g), g.stride(0), ptr(c), c.stride(0),
+                                          M, hid, K, stream()), "gemm_swiglu_fwd")
+    if tm is not None and tm.active:
+        e1.record()
+        tm.records.append((e0, e1, 2.0 * M * 2 * hid * K))
+    return g, c
+
+
+@_timed
+def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Optional[torch.Tensor] = None):
+    """dg = swiglu'(g) . (dy @ W2t^T): backward through w2 and the SwiGLU in one GEMM (dc never materialised)."""
+    M, K = dy.shape
+    hid = w2t.shape[0]
+    dg = torch.empty(M, 2 * hid, dtype=BF16, device=dy.device) if dg is None else dg
+    if hid % 32 != 0:
+        dc = gemm_nt(dy, w2t)
+        return swiglu_bwd(dc, g, dg)
+    tm = GEMM_TIMER
+    if tm is not None and tm.active:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.lib().fvqa_gemm_swiglu_bwd(ptr(dy), dy.stride(0), ptr(w2t), w2t.stride(0), ptr(g), g.stride(0), ptr(dg), dg.stride(0),
+                                          M, hid, K, stream()), "gemm_swiglu_bwd")
+    if tm is not None and tm.active:
+        e1.record()
+        tm.records.append((e0, e1, 2.0 * M * hid * K))
+    return dg
+
+
 # ------------------------------------------------------------------ attention
 @_timed
 def attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F, out=None, lse=None):

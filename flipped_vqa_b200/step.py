@@ -219,8 +219,7 @@ class StepEngine:
                                   out=None if save else o_b)
             h = ops.gemm_nt(o, w.wo, residual=x, out_fp32=True)                    # h = x + attn  (`model.py:185`), fp32 stream
             _, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
-            g = ops.gemm_nt(xn, w.w13, out=None if save else g_b)
-            ops.swiglu_fwd(g, c)
+            g, _ = ops.gemm_swiglu_fwd(xn, w.w13, g=None if save else g_b, c=c)      # W1|W3 GEMM, SwiGLU in its epilogue
             x_next = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)               # out = h + ffn (`model.py:186`)
             if save:
                 sv.x.append(x); sv.qkv.append(qkv); sv.akv.append(akv); sv.o.append(o); sv.lse.append(lse)
@@ -314,7 +313,6 @@ class StepEngine:
         # --- layers, last to first
         if self._attn_ws is None or self._attn_ws.numel() < ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A):
             self._attn_ws = torch.empty(ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
-        dc = torch.empty(T, hid, dtype=BF16, device=dev)
         dg = torch.empty(T, 2 * hid, dtype=BF16, device=dev)
         dtmp = torch.empty(T, d, dtype=BF16, device=dev)
         dh = torch.empty(T, d, dtype=torch.float32, device=dev)
@@ -328,8 +326,7 @@ class StepEngine:
             w = layers[l]
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
-            ops.gemm_nt(dx_bf, w.w2_t, out=dc)                                     # d(silu(a)*b) = dout . W2
-            ops.swiglu_bwd(dc, sv.g[l], dg)
+            ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l], dg=dg)                     # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
             ops.gemm_nt(dg, w.w13_t, out=dtmp)                                     # d(ffn_norm out) = [da|db] . [W1;W3]
             ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_bf16=dh_bf)
             ops.gemm_nt(dh_bf, w.wo_t, out=dtmp)                                   # d(attn out) = dh . Wo

@@ -73,6 +73,16 @@ int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int 
                            int M, int N, int K, const float* rope_cos, const float* rope_sin,
                            int rope_cols, int hd, int S, void* stream);
 
+/* SwiGLU fused into the GEMM epilogues (llama/model.py:142 `w2(silu(w1 x) * w3 x)` and its backward):
+ *  fwd: G[M, 2*hid] = X[M,K] * W13[2*hid, K]^T (bf16, saved for backward; W13 = [W1; W3]) and
+ *       C[M, hid] = silu(G[:, :hid]) * G[:, hid:], bit-identical to fvqa_gemm_bf16_nt + fvqa_swiglu_fwd. hid % 128 == 0.
+ *  bwd: dG[M, 2*hid] = swiglu'(G) applied to dc = dY[M,K] * W2t[hid, K]^T; dc never reaches HBM;
+ *       bit-identical to fvqa_gemm_bf16_nt + fvqa_swiglu_bwd. hid % 32 == 0. */
+int fvqa_gemm_swiglu_fwd(const fvqa_bf16* X, int ldx, const fvqa_bf16* W13, int ldw, fvqa_bf16* G, int ldg,
+                         fvqa_bf16* C, int ldc, int M, int hid, int K, void* stream);
+int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int ldw, const fvqa_bf16* G, int ldg,
+                         fvqa_bf16* dG, int lddg, int M, int hid, int K, void* stream);
+
 /* Test / tuning hook for the GEMM tile choice: bn = multiple of 16 in [64,256] forces that CTA-pair
  * tile width, 0 restores the heuristic, -1 forces the single-CTA kernel. Returns the previous value. */
 int fvqa_gemm_debug_force_bn(int bn);

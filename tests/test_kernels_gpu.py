@@ -122,6 +122,28 @@ def test_gemm_pair_tile_widths(fvqa_lib, bn):
         assert relerr(c16, ref) < 5e-3, (M, N, K, bn)
 
 
+@pytest.mark.parametrize("M,hid,K", [(200, 384, 128), (1024, 768, 256), (3072, 11008, 4096)])
+def test_gemm_swiglu_fused_matches_unfused(fvqa_lib, M, hid, K):
+    """SwiGLU fused into the W1|W3 GEMM epilogue (fwd) and into the W2^T GEMM epilogue (bwd) must be
+    BIT-identical to GEMM + swiglu kernel (llama/model.py:142), and close to an fp32 restatement."""
+    from flipped_vqa_b200 import ops
+    x = bf16_randn(M, K, seed=30)
+    w13 = bf16_randn(2 * hid, K, std=0.05, seed=31)
+    g_ref = ops.gemm_nt(x, w13)
+    c_ref = ops.swiglu_fwd(g_ref)
+    g, c = ops.gemm_swiglu_fwd(x, w13)
+    assert torch.equal(g, g_ref) and torch.equal(c, c_ref)
+    gf = x.float() @ w13.float().t()
+    assert relerr(c, torch.nn.functional.silu(gf[:, :hid]) * gf[:, hid:]) < 1e-2
+    d = 4 * K if K <= 256 else K
+    dy = bf16_randn(M, d, seed=32)
+    w2t = bf16_randn(hid, d, std=0.05, seed=33)
+    dc_ref = ops.gemm_nt(dy, w2t)
+    dg_ref = ops.swiglu_bwd(dc_ref, g_ref)
+    dg = ops.gemm_swiglu_bwd(dy, w2t, g_ref)
+    assert torch.equal(dg, dg_ref)
+
+
 @pytest.mark.parametrize("S,H,hd,B", [(48, 2, 64, 3), (128, 4, 128, 2)])
 def test_gemm_rope_epilogue(fvqa_lib, S, H, hd, B):
     """QKV projection with RoPE folded into the epilogue == plain projection followed by the oracle's

@@ -78,5 +78,26 @@ def main():
             print(f"TIME {M}x{N}x{K}: {txt} | cublas {fl / ms2 / 1e9:.0f}  (TFLOP/s)", flush=True)
 
 
+def skinny():
+    d = 4096
+    for (M, N, K, f32, ldb) in [(10, 2 * d, d, False, d), (10, d, 2 * d, True, 3 * d), (10, 2 * 5120, 5120, False, 5120)]:
+        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+        wfull = (torch.randn(N, ldb, device="cuda") * 0.05).to(torch.bfloat16)
+        b = wfull[:, ldb - K:]
+        ref = a.float() @ b.float().t()
+        res = {}
+        for bn in (0, -1):
+            force(bn)
+            c = ops.gemm_nt(a, b, out_fp32=f32)
+            torch.cuda.synchronize()
+            rel = float((c.float() - ref).norm() / ref.norm())
+            ms = time_gemm(lambda: ops.gemm_nt(a, b, out_fp32=f32), iters=50)
+            res[bn] = (rel, ms)
+        force(0)
+        print(f"SKINNY {M}x{N}x{K} ldb={ldb}: skinny rel {res[0][0]:.2e} {res[0][1] * 1e3:.1f} us | tcgen05 1cta rel {res[-1][0]:.2e} {res[-1][1] * 1e3:.1f} us", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "skinny":
+        _lib.lib(); skinny(); sys.exit(0)
     main()
