@@ -55,6 +55,15 @@ def measured_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")   # B200_PROFILING.md
 
 
+def gemm_traffic():
+    """Per-launch DRAM traffic of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def flops_per_step(cfg, n_labelled):
     """F_step = 3*(2*body + 3.5*attn) + 2*sum(head) + small; heads counted on the
     labelled rows actually evaluated (never count work not done)."""
@@ -339,12 +348,15 @@ def main():
             "gpu_launches": launches,
         }
         if gemm is not None:
-            line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_nt_kernel (tcgen05)", "achieved": gemm["tflops"],
+            tr = gemm_traffic() if a.config == "7b-nextqa" else None
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_nt_pair_kernel (tcgen05.mma.cta_group::2, TMA, TMEM)", "achieved": gemm["tflops"],
                                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm["tflops"] / peaks["bf16_tflops_sustained"],
                                 "frac_of_burst_peak": gemm["tflops"] / peaks["bf16_tflops"], "peak_kind": f"{peaks['source']} sustained (kernel timed inside a long step)",
-                                "traffic": None, "launches_sampled": gemm["launches"], "avg_launch_ms": gemm["avg_ms"],
+                                "traffic": (tr["avg_dram_bytes_per_launch"] if tr else None),
+                                "traffic_note": (tr["note"] if tr else "no ncu capture for this config"),
+                                "launches_sampled": gemm["launches"], "avg_launch_ms": gemm["avg_ms"],
                                 "avg_flops_per_launch": gemm["avg_flops"], "sampled_layers": list(model._engine.sample_layers),
-                                "gemm_share_of_step": None}
+                                "gemm_share_of_step": gemm["total_ms"] / len(model._engine.sample_layers) * L / (ms_per_step * a.steps)}
         if world == 1 and not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(cfg)

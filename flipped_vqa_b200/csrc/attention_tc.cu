@@ -640,6 +640,9 @@ int attn_bwd_tc(const AttnParams& p, cudaStream_t stream) {
 
 }  // namespace fvqa
 
+/* 1 if fvqa_attn_fwd / fvqa_attn_bwd take the tcgen05 path for this shape (bwd then launches 2 kernels, else 3). */
+extern "C" int fvqa_attn_uses_tc(int S, int hd, int A) { return fvqa::attn_tc_supported(S, hd, A) ? 1 : 0; }
+
 /* Test hook: 0 forces the mma.sync attention kernels, 1 (default) lets S <= 128 / hd = 128 shapes take the
  * tcgen05 path. Returns the previous setting. */
 extern "C" int fvqa_attn_debug_use_tc(int on) {

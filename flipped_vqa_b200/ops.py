@@ -81,7 +81,7 @@ def _count(n: int = 1):
     LAUNCHES += n
 
 
-_KERNELS_PER_CALL = {"attn_bwd": 3, "qav_loss_bwd": 2}
+_KERNELS_PER_CALL = {"attn_bwd": 3, "attn_bwd_tc": 2, "qav_loss_bwd": 2}
 
 
 def check(rc: int, what: str):
@@ -273,7 +273,8 @@ def attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S,
         ws = torch.empty(attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
     check(_lib.lib().fvqa_attn_bwd(ptr(qkv), ptr(akv), akv.stride(0), ptr(cos), ptr(sin), ptr(gate1), ptr(gate2), ptr(vstart),
                                    ptr(out), ptr(lse), ptr(dout), ptr(dqkv), ptr(dakv), ptr(dgate1), ptr(dgate2), ptr(ws),
-                                   n_seq, S, H, hd, A, F, stream()), "attn_bwd")
+                                   n_seq, S, H, hd, A, F, stream()),
+          "attn_bwd_tc" if _lib.lib().fvqa_attn_uses_tc(S, hd, A) else "attn_bwd")
     return dqkv, dakv, dgate1, dgate2
 
 

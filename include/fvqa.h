@@ -107,6 +107,8 @@ int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const 
  * (fp32, overwritten). */
 /* Test hook: 0 forces the mma.sync kernels, 1 (default) lets S <= 128, hd = 128 take the tcgen05 path. */
 int fvqa_attn_debug_use_tc(int on);
+/* 1 if this shape takes the tcgen05 attention path (backward = 2 kernel launches instead of 3). */
+int fvqa_attn_uses_tc(int S, int hd, int A);
 int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A);
 int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos,
                   const float* rope_sin, const float* gate1, const float* gate2, const int32_t* vstart,

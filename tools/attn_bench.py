@@ -22,7 +22,13 @@ def main():
     a = torch.randn(n_seq * S, 4096, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(11008, 4096, device="cuda", generator=g) * 0.02).to(torch.bfloat16)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    xr = torch.randn(n_seq * S, 4096, device="cuda", generator=g)
+    wn = torch.ones(4096, device="cuda", dtype=torch.bfloat16)
+    rstd = torch.rand(n_seq * S, device="cuda", generator=g) + 0.5
+    dres = torch.randn(n_seq * S, 4096, device="cuda", generator=g)
+    dxo = torch.empty_like(xr); dxb = torch.empty(n_seq * S, 4096, device="cuda", dtype=torch.bfloat16)
     def run():
+        ops.rmsnorm_bwd(a, xr, wn, rstd, dres=dres, dx=dxo, dx_bf16=dxb)
         out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
         ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F)
         ops.gemm_nt(a, w)
