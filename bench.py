@@ -182,7 +182,7 @@ def cpu_baseline(cfg, budget_s=25.0):
                        f"(t_layer={t_layer:.2f}s t_fixed={t_fixed:.2f}s)")
 
 
-def run_reference_arm(a):
+def run_reference_arm(a, guard):
     """`--impl reference`: the reference's step is pure PyTorch with no native path; on this box it is
     represented by the oracle port on the host cores (bounded 1-layer 7B-shaped slice per step)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -216,11 +216,26 @@ def run_reference_arm(a):
                              "sample": f"oracle (CPU port of llama/model.py step) fp32 fwd+bwd; each timed step = 1-layer 7B-shaped slice at "
                                        f"batch {Bs}; extrapolated: fixed {fixed_frac:.2f} of slice + {L} x per-layer"},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    guard.emit(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------
+class _StdoutGuard:
+    """Everything any library prints to fd 1 while the bench runs (e.g. NCCL's version banner) goes to stderr;
+    `emit()` writes the ONE JSON line to the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main():
+    guard = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -233,7 +248,7 @@ def main():
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
-        run_reference_arm(a)
+        run_reference_arm(a, guard)
         return
 
     import torch.distributed as dist
@@ -362,7 +377,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(cfg)
             except Exception as e:  # the baseline is informative; never lose the GPU numbers over it
                 line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
-        print(json.dumps(line), flush=True)
+        guard.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
