@@ -267,7 +267,7 @@ __host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GE
 template <bool OUT_F32, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages) {
+                         void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages, int l2_hints) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int stage_bytes = pair_stage_bytes(BN);
@@ -330,8 +330,13 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t sb = sa + GEMM_BM * GEMM_BK * 2;
           const uint32_t lfull = mapa_shared(full_bar(stage), 0);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * stage_bytes);
-          tma_load_2d_pair(sa, &tmap_a, lfull, kb * GEMM_BK, m0);
-          tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+          if (l2_hints) {      // weights stream through once per wave; the activation operand is re-read by every tile column
+            tma_load_2d_pair_hint(sa, &tmap_a, lfull, kb * GEMM_BK, m0, L2_EVICT_LAST);
+            tma_load_2d_pair_hint(sb, &tmap_b, lfull, kb * GEMM_BK, n0, L2_EVICT_FIRST);
+          } else {
+            tma_load_2d_pair(sa, &tmap_a, lfull, kb * GEMM_BK, m0);
+            tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -625,6 +630,7 @@ int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc
                 cudaStream_t stream);
 
 // ---- CTA-pair path ---------------------------------------------------------------------------
+static int g_l2_hints = 0;         // test hook (fvqa_gemm_debug_l2_hints)
 static int g_force_bn = 0;        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
 
 // Output-tile width for the pair kernel: maximise wave efficiency x per-tile efficiency. The per-tile
@@ -667,7 +673,7 @@ static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void
   const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + bn - 1) / bn;
   const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tiles_n;
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, GEMM_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages);
+  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, GEMM_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints);
   return check_launch("gemm_bf16_nt_pair");
 }
 
@@ -779,4 +785,11 @@ extern "C" int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf1
   GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, const_cast<fvqa_bf16*>(G), ldg, hid};
   return launch_gemm_pair<false, EPI_SWIGLU_BWD>(reinterpret_cast<const bf16*>(dY), ldy, reinterpret_cast<const bf16*>(W2t), ldw, dG, lddg, epi,
                                                  M, hid, K, 256, static_cast<cudaStream_t>(stream));
+}
+
+/* Tuning hook: 1 = TMA loads of the CTA-pair kernel carry L2 eviction hints (A evict_last, B evict_first). */
+extern "C" int fvqa_gemm_debug_l2_hints(int on) {
+  const int prev = g_l2_hints;
+  g_l2_hints = on;
+  return prev;
 }

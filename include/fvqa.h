@@ -86,6 +86,8 @@ int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int
 /* Test / tuning hook for the GEMM tile choice: bn = multiple of 16 in [64,256] forces that CTA-pair
  * tile width, 0 restores the heuristic, -1 forces the single-CTA kernel. Returns the previous value. */
 int fvqa_gemm_debug_force_bn(int bn);
+/* Tuning hook: 1 = the CTA-pair kernel's TMA loads carry L2 eviction hints (A evict_last, B evict_first). */
+int fvqa_gemm_debug_l2_hints(int on);
 
 /* ---- fused attention (llama/model.py:61-67 RoPE, :87-126 attention incl. adapter branch). --------
  * qkv  [n_seq*S, 3*H*hd] bf16 (q | k | v) with q,k ALREADY rotated (fvqa_gemm_bf16_nt_rope).

@@ -1,4 +1,4 @@
-"""GPU diagnostic: per-parameter parity report of the CUDA path vs the fp32 oracle (run on the GPU)
+"""GPU diagnostic (checker, lives under tests/ because it runs the oracle): per-parameter parity report of the CUDA path vs the fp32 oracle (run on the GPU)
 at a chosen depth of 7B-shaped layers. Not a test; prints a table."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

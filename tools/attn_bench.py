@@ -3,7 +3,6 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import ops, _lib
-from oracle import llama_vqa_oracle as O
 
 def main():
     _lib.lib()
@@ -16,7 +15,8 @@ def main():
     akv = torch.randn(A, 2 * D, device="cuda", generator=g).to(torch.bfloat16)
     gate1 = torch.randn(H, device="cuda", generator=g) * 0.5
     gate2 = torch.full((H,), -3.5, device="cuda")
-    cos, sin = O.rope_table(hd, S); cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    ang = torch.outer(torch.arange(S).float(), 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd)))
+    cos, sin = torch.cos(ang), torch.sin(ang); cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
     vstart = torch.tensor([18] * (2 * n_seq // 3) + [-1] * (n_seq - 2 * n_seq // 3), dtype=torch.int32, device="cuda")
     dout = torch.randn(n_seq * S, D, device="cuda", generator=g).to(torch.bfloat16)
     a = torch.randn(n_seq * S, 4096, device="cuda", generator=g).to(torch.bfloat16)

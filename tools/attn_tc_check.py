@@ -4,7 +4,6 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import ops, _lib
-from oracle import llama_vqa_oracle as O
 
 
 def case(n_seq, S, H, A=10, F=10, seed=0):
@@ -15,7 +14,8 @@ def case(n_seq, S, H, A=10, F=10, seed=0):
     akv = torch.randn(A, 2 * D, device="cuda", generator=g).to(torch.bfloat16)
     gate1 = torch.randn(H, device="cuda", generator=g) * 0.5
     gate2 = torch.full((H,), -3.5, device="cuda") + 0.1 * torch.randn(H, device="cuda", generator=g)
-    cos, sin = O.rope_table(hd, S)
+    ang = torch.outer(torch.arange(S).float(), 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd)))
+    cos, sin = torch.cos(ang), torch.sin(ang)
     cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
     vs = [min(18, max(S - 12, 0)) if i % 3 != 2 else -1 for i in range(n_seq)]
     vstart = torch.tensor(vs, dtype=torch.int32, device="cuda")
