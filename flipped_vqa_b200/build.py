@@ -16,8 +16,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libfvqa.so")
-SOURCES = ["api.cu", "elementwise.cu", "embed.cu", "heads.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tmap.h"), os.path.join(CSRC, "attention.h"),
+SOURCES = ["api.cu", "elementwise.cu", "embed.cu", "heads.cu", "gemm_tcgen05.cu", "gemm_skinny.cu", "attention.cu", "attention_tc.cu", "attention_tc_long.cu"]
+HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tmap.h"), os.path.join(CSRC, "attention.h"), os.path.join(CSRC, "attention_tc.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "fvqa.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -746,7 +746,7 @@ __global__ void __launch_bounds__(AT_NT) attn_bwd_dkv_kernel(const AttnParams p)
 __global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __restrict__ ws_akv, const float* __restrict__ ws_gate,
                                                               const float* __restrict__ gate1, float* __restrict__ dakv,
                                                               float* __restrict__ dgate1, float* __restrict__ dgate2, int n_seq,
-                                                              int H, int hd, int A, int qtiles) {
+                                                              int H, int hd, int A, int qtiles, int n_akv) {
   __shared__ float red[32];
   const int h = blockIdx.x, a = blockIdx.y;
   const int D = H * hd;
@@ -757,14 +757,14 @@ __global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __res
       const long stride = static_cast<long>(H) * 2 * AT_AP * hd;
       float acc = 0.f;
       int n = 0;
-      for (; n + 8 <= n_seq; n += 8) {
+      for (; n + 8 <= n_akv; n += 8) {
         float v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (n + u) * stride);
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += v[u];
       }
-      for (; n < n_seq; ++n) acc += __ldg(src + n * stride);
+      for (; n < n_akv; ++n) acc += __ldg(src + n * stride);
       dakv[static_cast<long>(a) * 2 * D + which * D + h * hd + c] = acc;
     }
     return;
@@ -802,7 +802,9 @@ int attn_init() {
   FVQA_ATTR(attn_bwd_dkv_kernel<64>, dkv_smem<64>())
   FVQA_ATTR(attn_bwd_dkv_kernel<128>, dkv_smem<128>())
 #undef FVQA_ATTR
-  return attn_tc_init();
+  int rc = attn_tc_init();
+  if (rc) return rc;
+  return attn_tcl_init();
 }
 
 static int check_attn_args(int n_seq, int S, int H, int hd, int A, int akv_ld) {
@@ -830,6 +832,7 @@ extern "C" int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   dim3 grid(p.qblocks, H, n_seq);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (attn_tc_supported(S, hd, A)) return attn_fwd_tc(p, s);
+  if (attn_tcl_supported(S, hd, A)) return attn_fwd_tcl(p, s);
   if (hd == 64) attn_fwd_kernel<64><<<grid, AT_NT, fwd_smem<64>(), s>>>(p);
   else attn_fwd_kernel<128><<<grid, AT_NT, fwd_smem<128>(), s>>>(p);
   return check_launch("attn_fwd");
@@ -839,7 +842,7 @@ extern "C" int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A
   (void)A;
   const int64_t qblocks = (S + AT_QB - 1) / AT_QB;
   const int64_t nh = static_cast<int64_t>(n_seq) * H;
-  return 4 * (nh * qblocks * AT_QB + nh * qblocks * 2 + nh * 2 * AT_AP * hd);
+  return 4 * (nh * qblocks * AT_QB + nh * qblocks * 2 + nh * qblocks * 2 * AT_AP * hd);   // D | gate partials | adapter partials
 }
 
 extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
@@ -861,9 +864,14 @@ extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   p.ws_akv = p.ws_gate + nh * p.qblocks * 2;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   dim3 grid_a(p.qblocks, H, n_seq), grid_b(p.qblocks + 1, H, n_seq);
+  int n_akv = n_seq;                     // groups of adapter partials the reduce kernel sums
   if (attn_tc_supported(S, hd, A)) {
     rc = attn_bwd_tc(p, s);
     if (rc) return rc;
+  } else if (attn_tcl_supported(S, hd, A)) {
+    rc = attn_bwd_tcl(p, s);
+    if (rc) return rc;
+    n_akv = n_seq * p.qblocks;           // one group per (sequence, query tile)
   } else if (hd == 64) {
     attn_bwd_dq_kernel<64><<<grid_a, AT_NT, dq_smem<64>(), s>>>(p);
     rc = check_launch("attn_bwd_dq");
@@ -877,6 +885,6 @@ extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv
   }
   rc = check_launch("attn_bwd_dkv");
   if (rc) return rc;
-  attn_bwd_reduce_kernel<<<dim3(H, A + 1), 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qblocks);
+  attn_bwd_reduce_kernel<<<dim3(H, A + 1), 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qblocks, n_akv);
   return check_launch("attn_bwd_reduce");
 }

@@ -24,5 +24,10 @@ bool attn_tc_supported(int S, int hd, int A);
 int attn_tc_init();
 int attn_fwd_tc(const AttnParams& p, cudaStream_t stream);
 int attn_bwd_tc(const AttnParams& p, cudaStream_t stream);
+// tiled tcgen05 path for S > 128, hd = 128 (attention_tc_long.cu)
+bool attn_tcl_supported(int S, int hd, int A);
+int attn_tcl_init();
+int attn_fwd_tcl(const AttnParams& p, cudaStream_t stream);
+int attn_bwd_tcl(const AttnParams& p, cudaStream_t stream);   // dq + dkv kernels; caller runs the reduce kernel
 
 }  // namespace fvqa

@@ -11,51 +11,12 @@
 // Shared-memory operand layouts: everything TMA loads is the 128-byte-swizzled [rows][64 elem] box.
 // Used K-major when the contraction runs along the 64-element rows (Q, K, Ka, P) and MN-major when it
 // runs along the box rows (V, Va as B of P.V: N = head dim contiguous, K = keys).
-#include "attention.h"
-#include "common.cuh"
+#include "attention_tc.cuh"
 #include "tmap.h"
-
-#include <cuda_fp16.h>
 
 namespace fvqa {
 
 namespace {
-
-constexpr int TC_THREADS = 128;
-constexpr float TC_LOG2E = 1.4426950408889634f;
-constexpr float TC_LN2 = 0.6931471805599453f;
-
-// MN-major, 128-byte swizzle: 64 MN-elements per 128-byte row, 8-row (K) groups 1024 B apart (SBO),
-// 64-element MN blocks `lbo_bytes` apart.
-__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-// No swizzle ("interleave"): 8 x 16-byte core matrices (128 B contiguous).
-//   K-major : core matrices along K are lbo apart, 8-row groups along M/N are sbo apart.
-//   MN-major: 8-element chunks along M/N are sbo apart, 8-row groups along K are lbo apart.
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  return d;
-}
-__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-
-// byte offset of the 16-byte chunk `c16` (0..7) of row r inside a K-major SW128 [rows][64] block
-__device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
-  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
-}
 
 // ---- forward shared-memory map (bytes from the 1024-aligned base) ----
 constexpr int F_SQ = 0;               // [2][128][64] bf16; O staging for the TMA store at the end
@@ -596,6 +557,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 static int g_use_tc = 1;
 
 bool attn_tc_supported(int S, int hd, int A) { return g_use_tc != 0 && hd == 128 && S <= 128 && A <= AT_AP; }
+bool attn_tcl_supported(int S, int hd, int A) { return g_use_tc != 0 && hd == 128 && S > 128 && A <= AT_AP; }
 
 int attn_tc_init() {
   cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);

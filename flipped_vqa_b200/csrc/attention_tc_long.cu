@@ -1,0 +1,698 @@
+// tcgen05 / TMEM attention for sequences longer than one 128-row tile (DramaQA-shaped S = 384, TVQA-shaped
+// S = 650), head_dim = 128. Same operand layouts and per-row softmax code as attention_tc.cu, tiled:
+//
+//   forward   : CTA = (128-query tile i, head, sequence), 2 CTAs/SM. Two passes over the key tiles j <= i:
+//               pass 1 UMMA S = Q K_j^T -> running row max / sum (no rescaling of O is ever needed);
+//               pass 2 UMMA S again -> P = exp2(S - m) / l -> smem -> UMMA O += P V_j (TMEM accumulate).
+//               QK^T twice is cheap (attention is latency / HBM-bound), K tiles come back from L2.
+//   backward A: CTA = (query tile i, ...): D = <dO, O> from TMA-staged tiles, adapter softmax backward,
+//               loop j <= i: S, dP -> dS -> UMMA dQ += dS K_j; writes dQ (inverse RoPE), D, gate partials and the
+//               per-tile adapter partials dKa^T, dVa^T.
+//   backward B: CTA = (key tile j, ...): loop i >= j: S, dP -> P, dS -> UMMA dV += P^T dO_i, dK += dS^T Q_i
+//               (TMEM accumulators live across the loop); writes dK (inverse RoPE), dV.
+// Two deterministic passes, no atomics; partials are reduced in a fixed order by attn_bwd_reduce_kernel.
+#include "attention_tc.cuh"
+#include "tmap.h"
+
+namespace fvqa {
+
+namespace {
+
+// masked / biased log2-domain score of element (row_g, col_g)
+struct ScoreCtx {
+  float scale2, bias2;
+  int bias_row0, bias_c0, bias_c1;   // rows >= bias_row0, cols in [c0, c1) get bias2
+};
+__device__ __forceinline__ ScoreCtx make_score_ctx(const AttnParams& p, int n, int h) {
+  ScoreCtx c;
+  c.scale2 = rsqrtf(128.f) * TC_LOG2E;
+  const int vs = p.vstart[n];
+  c.bias2 = (vs >= 0) ? p.gate2[h] * TC_LOG2E : 0.f;
+  c.bias_row0 = (vs >= 0) ? vs + p.F : 0x7fffffff;
+  c.bias_c0 = vs;
+  c.bias_c1 = vs + p.F;
+  return c;
+}
+
+// ---- forward smem map: identical to the S <= 128 kernel ----
+constexpr int LF_SQ = 0, LF_SK = 32768, LF_SV = 65536, LF_SKA = 98304, LF_SVA = 102400, LF_SPA = 106496, LF_BAR = 110592;
+constexpr int LF_SMEM = LF_BAR + 64 + 1024;
+
+}  // namespace
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
+                    const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_q = sbase + LF_BAR, bar_k = bar_q + 8, bar_v = bar_q + 16, bar_s = bar_q + 24, bar_o = bar_q + 32, holder = bar_q + 40;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qi = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);   // longest key loops are scheduled first
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int S = p.S, D = p.H * 128;
+  const int row0 = qi * 128, row_g = row0 + tid;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(holder, 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + LF_BAR + 40);
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const int c = h * 128;
+  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0), id_o = idesc_bf16(128, 128, 0, 1);
+  auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_akv); tma_prefetch_desc(&tm_out);
+    mbar_arrive_expect_tx(bar_q, 32768 + 8192);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_3d(sbase + LF_SQ + kb * 16384, &tm_qkv, bar_q, c + kb * 64, row0, n);
+      tma_load_2d(sbase + LF_SKA + kb * 2048, &tm_akv, bar_q, c + kb * 64, 0);
+      tma_load_2d(sbase + LF_SVA + kb * 2048, &tm_akv, bar_q, D + c + kb * 64, 0);
+    }
+  }
+  const ScoreCtx sc = make_score_ctx(p, n, h);
+  const bool row_biased = row_g >= sc.bias_row0;
+  uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_o = 0;     // mbarrier phase parities (uniform across threads)
+  float m_run = -INFINITY, l_run = 0.f;
+
+  // one S = Q K_j^T into TMEM columns [0,128) (+ S_a at [128,144) when with_adapter)
+  auto issue_s = [&](int j, bool with_adapter) {
+    mbar_arrive_expect_tx(bar_k, 32768);
+    tma_load_3d(sbase + LF_SK, &tm_qkv, bar_k, D + c, j * 128, n);
+    tma_load_3d(sbase + LF_SK + 16384, &tm_qkv, bar_k, D + c + 64, j * 128, n);
+    if (with_adapter) { mbar_wait(bar_q, 0); }
+    mbar_wait(bar_k, ph_k);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      umma_bf16_ss(tmem, kdesc(LF_SQ, 16384, ks), kdesc(LF_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+      if (with_adapter) umma_bf16_ss(tmem + 128, kdesc(LF_SQ, 16384, ks), kdesc(LF_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_s);
+  };
+
+  // ---------------- pass 1: row max / sum over all key tiles ----------------
+  for (int j = 0; j <= qi; ++j) {
+    if (tid == 0) issue_s(j, j == 0);
+    __syncwarp();
+    mbar_wait(bar_s, ph_s);
+    tc_fence_after();
+    const int nch = (j == qi) ? warp + 1 : 4;            // diagonal tile: chunks beyond the warp's last row are masked
+    for (int ch = 0; ch < nch; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32(tlane + static_cast<uint32_t>(ch * 32), v);
+      tmem_ld_wait();
+      float x[32], mx = m_run;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int col_g = j * 128 + ch * 32 + e;
+        float t = __uint_as_float(v[e]) * sc.scale2;
+        if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
+        if (col_g > row_g) t = -INFINITY;
+        x[e] = t;
+        mx = fmaxf(mx, t);
+      }
+      float add = 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) add += exp2f(x[e] - mx);
+      l_run = l_run * exp2f(m_run - mx) + add;           // m_run = -inf, l_run = 0 on the first chunk: 0 * 0 + add
+      m_run = mx;
+    }
+    if (j == 0) {
+      // adapter branch (independent of the key tiles): separate softmax x tanh(gate1) -> P_a operand
+      uint32_t v[32];
+      tmem_ld_32x16(tlane + 128u, v);
+      tmem_ld_wait();
+      const float tg = tanhf(p.gate1[h]);
+      float sa[16], ma = -INFINITY, la = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        sa[e] = (e < p.A) ? __uint_as_float(v[e]) * sc.scale2 : -INFINITY;
+        ma = fmaxf(ma, sa[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { sa[e] = exp2f(sa[e] - ma); la += sa[e]; }
+      const float ia = tg / la;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = sa[cc * 8 + e] * ia;
+        *reinterpret_cast<uint4*>(sgen + LF_SPA + (tid >> 3) * 256 + cc * 128 + (tid & 7) * 16) = pack8(f);
+      }
+    }
+    ph_k ^= 1u; ph_s ^= 1u;
+    tc_fence_before();
+    __syncthreads();                                    // everyone has read S before the next UMMA overwrites it
+    tc_fence_after();
+  }
+  const float inv_l = 1.f / l_run;
+  if (row_g < S) p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] = (m_run + log2f(l_run)) * TC_LN2;
+
+  // ---------------- pass 2: P = exp2(S - m) / l, O += P V_j ----------------
+  for (int j = 0; j <= qi; ++j) {
+    if (tid == 0) {
+      if (j > 0) { mbar_wait(bar_o, ph_o); }            // previous P.V has finished reading P (K's buffer) and V
+      mbar_arrive_expect_tx(bar_v, 32768);
+      tma_load_3d(sbase + LF_SV, &tm_qkv, bar_v, 2 * D + c, j * 128, n);
+      tma_load_3d(sbase + LF_SV + 16384, &tm_qkv, bar_v, 2 * D + c + 64, j * 128, n);
+      issue_s(j, false);
+    }
+    __syncwarp();
+    if (j > 0) ph_o ^= (tid == 0) ? 1u : 0u;
+    mbar_wait(bar_s, ph_s);
+    tc_fence_after();
+    const int nch = (j == qi) ? warp + 1 : 4;
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < nch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tlane + static_cast<uint32_t>(ch * 32), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col_g = j * 128 + ch * 32 + q * 8 + e;
+            float t = __uint_as_float(v[q * 8 + e]) * sc.scale2;
+            if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
+            f[e] = (col_g > row_g) ? 0.f : exp2f(t - m_run) * inv_l;
+          }
+          *reinterpret_cast<uint4*>(sgen + LF_SK + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(sgen + LF_SK + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    ph_k ^= 1u; ph_s ^= 1u;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mbar_wait(bar_v, ph_v);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_bf16_ss(tmem + 128, kdesc(LF_SK, 16384, ks), desc_mn_sw128(sbase + LF_SV + ks * 2048, 16384), id_o, (j > 0 || ks > 0) ? 1u : 0u);
+      if (j == qi) umma_bf16_ss(tmem + 128, desc_nosw(sbase + LF_SPA, 128, 256), desc_mn_sw128(sbase + LF_SVA, 2048), id_o, 1u);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    ph_v ^= 1u;
+  }
+  // all threads: wait for the last P.V (tid 0 has consumed the earlier phases of bar_o itself)
+  {
+    const uint32_t last = static_cast<uint32_t>(qi) & 1u;   // bar_o completes once per tile: phase of completion #qi
+    mbar_wait(bar_o, last);
+  }
+  tc_fence_after();
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(tlane + 128u + static_cast<uint32_t>(ch * 32), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+      *reinterpret_cast<uint4*>(sgen + LF_SQ + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&tm_out, sbase + LF_SQ, c, row0, n);
+    tma_store_3d(&tm_out, sbase + LF_SQ + 16384, c + 64, row0, n);
+    tma_store_commit();
+    tma_store_wait_read();
+  }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward A: query tile owner -> dQ, D, gate partials, adapter partials
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int A_SQ = 0, A_SDO = 32768, A_SK = 65536, A_SV = 98304, A_SDS = 131072;   // A_SDS first holds the O tile
+constexpr int A_SKA = 163840, A_SVA = 167936, A_SPA = 172032, A_SDSA = 176128, A_ROPE = 180224, A_BAR = 212992;
+constexpr int A_RED = A_BAR + 64;
+constexpr int A_SMEM = A_BAR + 128 + 1024;
+}  // namespace
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
+                       const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_o,
+                       const __grid_constant__ CUtensorMap tm_dqkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_q = sbase + A_BAR, bar_kv = bar_q + 8, bar_m1 = bar_q + 16, bar_m2 = bar_q + 24, bar_ma = bar_q + 32, holder = bar_q + 40;
+  float* sred = reinterpret_cast<float*>(sgen + A_RED);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qi = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);   // longest key loops are scheduled first
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int S = p.S, D = p.H * 128;
+  const int row0 = qi * 128, row_g = row0 + tid;
+  const bool row_ok = row_g < S;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1); mbar_init(bar_ma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(holder, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + A_BAR + 40);
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_SA = 384, T_DPA = 400, T_DKA = 416;   // dVa^T at T_DKA + 16
+  const int c = h * 128;
+  auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
+  auto mndesc = [&](int off, int lbo, int ks) { return desc_mn_sw128(sbase + off + ks * 2048, lbo); };
+  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0), id_q = idesc_bf16(128, 128, 0, 1),
+                     id_at = idesc_bf16(128, 16, 1, 1);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_akv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_dqkv);
+    mbar_arrive_expect_tx(bar_q, 3 * 32768 + 8192);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_3d(sbase + A_SQ + kb * 16384, &tm_qkv, bar_q, c + kb * 64, row0, n);
+      tma_load_3d(sbase + A_SDO + kb * 16384, &tm_do, bar_q, c + kb * 64, row0, n);
+      tma_load_3d(sbase + A_SDS + kb * 16384, &tm_o, bar_q, c + kb * 64, row0, n);
+      tma_load_2d(sbase + A_SKA + kb * 2048, &tm_akv, bar_q, c + kb * 64, 0);
+      tma_load_2d(sbase + A_SVA + kb * 2048, &tm_akv, bar_q, D + c + kb * 64, 0);
+    }
+  }
+  __syncwarp();
+  stage_rope_table(sgen + A_ROPE, p.cosT, p.sinT, row0, S, tid, TC_THREADS);
+  if (tid == 0) {
+    mbar_wait(bar_q, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      umma_bf16_ss(tmem + T_SA, kdesc(A_SQ, 16384, ks), kdesc(A_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+      umma_bf16_ss(tmem + T_DPA, kdesc(A_SDO, 16384, ks), kdesc(A_SVA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(bar_ma);
+  }
+  __syncwarp();
+  mbar_wait(bar_q, 0);
+  // D_total = <dO, O> of this row from the staged tiles
+  float dtot = 0.f;
+#pragma unroll 4
+  for (int c16 = 0; c16 < 16; ++c16) {
+    float a[8], b[8];
+    const uint32_t off = static_cast<uint32_t>((c16 >> 3) * 16384) + sw128_off(tid, c16 & 7);
+    unpack8(*reinterpret_cast<const uint4*>(sgen + A_SDS + off), a);
+    unpack8(*reinterpret_cast<const uint4*>(sgen + A_SDO + off), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dtot += a[e] * b[e];
+  }
+  const ScoreCtx sc = make_score_ctx(p, n, h);
+  const bool row_biased = row_g >= sc.bias_row0;
+  const float scale = rsqrtf(128.f);
+  const float tg = tanhf(p.gate1[h]);
+  const float lse2 = row_ok ? p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] * TC_LOG2E : 0.f;
+  float g1_part = 0.f, g2_part = 0.f, dx;
+  mbar_wait(bar_ma, 0);
+  tc_fence_after();
+  {
+    uint32_t v[32], w[32];
+    tmem_ld_32x16(tlane + T_SA, v);
+    tmem_ld_32x16(tlane + T_DPA, w);
+    tmem_ld_wait();
+    float sa[16], ma = -INFINITY, la = 0.f, da = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      sa[e] = (e < p.A) ? __uint_as_float(v[e]) * sc.scale2 : -INFINITY;
+      ma = fmaxf(ma, sa[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { sa[e] = exp2f(sa[e] - ma); la += sa[e]; }
+    const float ia = row_ok ? 1.f / la : 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { sa[e] *= ia; da += sa[e] * __uint_as_float(w[e]); }
+    g1_part = da;
+    dx = dtot - tg * da;
+    if (row_ok) p.ws_dx[(static_cast<long>(n) * p.H + h) * (p.qblocks * 128) + row_g] = dx;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      float fp[8], fd[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float pa = sa[cc * 8 + e];
+        fp[e] = tg * pa;
+        fd[e] = tg * pa * (__uint_as_float(w[cc * 8 + e]) - da) * scale;
+      }
+      const int off = (tid >> 3) * 256 + cc * 128 + (tid & 7) * 16;
+      *reinterpret_cast<uint4*>(sgen + A_SPA + off) = pack8(fp);
+      *reinterpret_cast<uint4*>(sgen + A_SDSA + off) = pack8(fd);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();                                       // O tile fully consumed: its buffer becomes dS
+  tc_fence_after();
+
+  uint32_t ph_kv = 0, ph_m1 = 0, ph_m2 = 0;
+  for (int j = 0; j <= qi; ++j) {
+    if (tid == 0) {
+      if (j > 0) mbar_wait(bar_m2, ph_m2 ^ 1u);          // previous dQ UMMA done with K's buffer (parity of completion j-1)
+      mbar_arrive_expect_tx(bar_kv, 65536);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_3d(sbase + A_SK + kb * 16384, &tm_qkv, bar_kv, D + c + kb * 64, j * 128, n);
+        tma_load_3d(sbase + A_SV + kb * 16384, &tm_qkv, bar_kv, 2 * D + c + kb * 64, j * 128, n);
+      }
+      mbar_wait(bar_kv, ph_kv);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        umma_bf16_ss(tmem + T_S, kdesc(A_SQ, 16384, ks), kdesc(A_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_bf16_ss(tmem + T_DP, kdesc(A_SDO, 16384, ks), kdesc(A_SV, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_m1);
+    }
+    __syncwarp();
+    mbar_wait(bar_m1, ph_m1);
+    if (j > 0) mbar_wait(bar_m2, ph_m2 ^ 1u);            // dS buffer free again
+    tc_fence_after();
+    const int nch = (j == qi) ? warp + 1 : 4;
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < nch) {
+        uint32_t v[32], w[32];
+        tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
+        tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(ch * 32), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float fd[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col_g = j * 128 + ch * 32 + q * 8 + e;
+            float t = __uint_as_float(v[q * 8 + e]) * sc.scale2;
+            const bool biased = row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1;
+            if (biased) t += sc.bias2;
+            const float pv = (col_g > row_g || !row_ok) ? 0.f : exp2f(t - lse2);
+            const float ds = pv * (__uint_as_float(w[q * 8 + e]) - dx);
+            if (biased) g2_part += ds;
+            fd[e] = ds * scale;
+          }
+          *reinterpret_cast<uint4*>(sgen + A_SDS + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(fd);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(sgen + A_SDS + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_bf16_ss(tmem + T_DQ, kdesc(A_SDS, 16384, ks), mndesc(A_SK, 16384, ks), id_q, (j > 0 || ks > 0) ? 1u : 0u);
+      if (j == qi) {
+        umma_bf16_ss(tmem + T_DQ, desc_nosw(sbase + A_SDSA, 128, 256), desc_mn_sw128(sbase + A_SKA, 2048), id_q, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          umma_bf16_ss(tmem + T_DKA, mndesc(A_SQ, 16384, ks), desc_nosw(sbase + A_SDSA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
+          umma_bf16_ss(tmem + T_DKA + 16, mndesc(A_SDO, 16384, ks), desc_nosw(sbase + A_SPA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_m2);
+    }
+    __syncwarp();
+    ph_kv ^= 1u; ph_m1 ^= 1u; ph_m2 ^= 1u;
+  }
+  g1_part = warp_sum(g1_part);
+  g2_part = warp_sum(g2_part);
+  if (lane == 0) { sred[warp] = g1_part; sred[4 + warp] = g2_part; }
+  __syncthreads();
+  if (tid == 0) {
+    float* wsg = p.ws_gate + ((static_cast<long>(n) * p.H + h) * p.qblocks + qi) * 2;
+    wsg[0] = (sred[0] + sred[1]) + (sred[2] + sred[3]);
+    wsg[1] = (sred[4] + sred[5]) + (sred[6] + sred[7]);
+  }
+  mbar_wait(bar_m2, ph_m2 ^ 1u);                         // last completion
+  tc_fence_after();
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(tlane + T_DQ + static_cast<uint32_t>(ch * 32), v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+      inv_rope8(f, sgen + A_ROPE, tid, ch * 4 + q);
+      *reinterpret_cast<uint4*>(sgen + A_SK + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+    }
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_3d(&tm_dqkv, sbase + A_SK, c, row0, n);
+    tma_store_3d(&tm_dqkv, sbase + A_SK + 16384, c + 64, row0, n);
+    tma_store_commit();
+  }
+  {
+    uint32_t v[32];
+    tmem_ld_32x32(tlane + T_DKA, v);                     // [416,432) dKa^T, [432,448) dVa^T; thread = head-dim index
+    tmem_ld_wait();
+    float* wsa = p.ws_akv + ((static_cast<long>(n) * p.qblocks + qi) * p.H + h) * 2 * AT_AP * 128;
+#pragma unroll
+    for (int a = 0; a < AT_AP; ++a) {
+      wsa[a * 128 + tid] = __uint_as_float(v[a]);
+      wsa[AT_AP * 128 + a * 128 + tid] = __uint_as_float(v[16 + a]);
+    }
+  }
+  if (tid == 0) tma_store_wait_read();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward B: key tile owner -> dK, dV
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int K_SK = 0, K_SV = 32768, K_SQ = 65536, K_SDO = 98304, K_SP = 131072, K_SDS = 163840, K_ROPE = 196608, K_BAR = 229376;
+constexpr int K_SMEM = K_BAR + 64 + 1024;
+}  // namespace
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const __grid_constant__ CUtensorMap tm_dqkv, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const uint32_t bar_kv = sbase + K_BAR, bar_q = bar_kv + 8, bar_m1 = bar_kv + 16, bar_m2 = bar_kv + 24, holder = bar_kv + 32;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int kj = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int S = p.S, D = p.H * 128;
+  const int key0 = kj * 128;
+  const int qtiles = p.qblocks;
+
+  if (tid == 0) {
+    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { tmem_alloc(holder, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + K_BAR + 32);
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 384;
+  const int c = h * 128;
+  auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
+  auto mndesc = [&](int off, int lbo, int ks) { return desc_mn_sw128(sbase + off + ks * 2048, lbo); };
+  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_tt = idesc_bf16(128, 128, 1, 1);
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_dqkv);
+    mbar_arrive_expect_tx(bar_kv, 65536);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_3d(sbase + K_SK + kb * 16384, &tm_qkv, bar_kv, D + c + kb * 64, key0, n);
+      tma_load_3d(sbase + K_SV + kb * 16384, &tm_qkv, bar_kv, 2 * D + c + kb * 64, key0, n);
+    }
+  }
+  __syncwarp();
+  stage_rope_table(sgen + K_ROPE, p.cosT, p.sinT, key0, S, tid, TC_THREADS);
+  const ScoreCtx sc = make_score_ctx(p, n, h);
+  const float scale = rsqrtf(128.f);
+  uint32_t ph_q = 0, ph_m1 = 0, ph_m2 = 0;
+  for (int qi = kj; qi < qtiles; ++qi) {
+    const int row_g = qi * 128 + tid;
+    const bool row_ok = row_g < S;
+    if (tid == 0) {
+      if (qi > kj) mbar_wait(bar_m2, ph_m2 ^ 1u);        // previous dV/dK UMMAs done with Q, dO, P, dS
+      mbar_arrive_expect_tx(bar_q, 65536);
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_3d(sbase + K_SQ + kb * 16384, &tm_qkv, bar_q, c + kb * 64, qi * 128, n);
+        tma_load_3d(sbase + K_SDO + kb * 16384, &tm_do, bar_q, c + kb * 64, qi * 128, n);
+      }
+      if (qi == kj) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph_q);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        umma_bf16_ss(tmem + T_S, kdesc(K_SQ, 16384, ks), kdesc(K_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_bf16_ss(tmem + T_DP, kdesc(K_SDO, 16384, ks), kdesc(K_SV, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_m1);
+    }
+    __syncwarp();
+    const float lse2 = row_ok ? p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] * TC_LOG2E : 0.f;
+    const float dx = row_ok ? p.ws_dx[(static_cast<long>(n) * p.H + h) * (qtiles * 128) + row_g] : 0.f;
+    const bool row_biased = row_g >= sc.bias_row0;
+    mbar_wait(bar_m1, ph_m1);
+    if (qi > kj) mbar_wait(bar_m2, ph_m2 ^ 1u);
+    tc_fence_after();
+    const int nch = (qi == kj) ? warp + 1 : 4;
+    for (int ch = 0; ch < 4; ++ch) {
+      if (ch < nch) {
+        uint32_t v[32], w[32];
+        tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
+        tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(ch * 32), w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float fp[8], fd[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col_g = key0 + ch * 32 + q * 8 + e;
+            float t = __uint_as_float(v[q * 8 + e]) * sc.scale2;
+            if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
+            const float pv = (col_g > row_g || !row_ok) ? 0.f : exp2f(t - lse2);
+            fp[e] = pv;
+            fd[e] = pv * (__uint_as_float(w[q * 8 + e]) - dx) * scale;
+          }
+          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(tid, (ch & 1) * 4 + q);
+          *reinterpret_cast<uint4*>(sgen + K_SP + off) = pack8(fp);
+          *reinterpret_cast<uint4*>(sgen + K_SDS + off) = pack8(fd);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(tid, (ch & 1) * 4 + q);
+          *reinterpret_cast<uint4*>(sgen + K_SP + off) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sgen + K_SDS + off) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t accum = qi > kj ? 1u : 0u;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_bf16_ss(tmem + T_DV, mndesc(K_SP, 16384, ks), mndesc(K_SDO, 16384, ks), id_tt, (accum || ks > 0) ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        umma_bf16_ss(tmem + T_DK, mndesc(K_SDS, 16384, ks), mndesc(K_SQ, 16384, ks), id_tt, (accum || ks > 0) ? 1u : 0u);
+      umma_commit(bar_m2);
+    }
+    __syncwarp();
+    ph_q ^= 1u; ph_m1 ^= 1u; ph_m2 ^= 1u;
+  }
+  mbar_wait(bar_m2, ph_m2 ^ 1u);
+  tc_fence_after();
+#pragma unroll 1
+  for (int which = 1; which < 3; ++which) {              // 1: dK (inverse RoPE at the key positions), 2: dV
+    const uint32_t tcol = which == 1 ? T_DK : T_DV;
+    const int sdst = which == 1 ? K_SQ : K_SDO;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t v[32];
+      tmem_ld_32x32(tlane + tcol + static_cast<uint32_t>(ch * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+        if (which == 1) inv_rope8(f, sgen + K_ROPE, tid, ch * 4 + q);
+        *reinterpret_cast<uint4*>(sgen + sdst + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_3d(&tm_dqkv, sbase + sdst, which * D + c, key0, n);
+      tma_store_3d(&tm_dqkv, sbase + sdst + 16384, which * D + c + 64, key0, n);
+      tma_store_commit();
+    }
+  }
+  if (tid == 0) tma_store_wait_read();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------
+int attn_tcl_init() {
+  cudaError_t e = cudaFuncSetAttribute(attn_fwd_tcl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LF_SMEM);
+  FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(attn_fwd_tcl): %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(attn_bwd_tcl_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM);
+  FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(attn_bwd_tcl_dq): %s", cudaGetErrorString(e));
+  e = cudaFuncSetAttribute(attn_bwd_tcl_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K_SMEM);
+  FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(attn_bwd_tcl_dkv): %s", cudaGetErrorString(e));
+  return FVQA_OK;
+}
+
+int attn_fwd_tcl(const AttnParams& p, cudaStream_t stream) {
+  const int D = p.H * 128;
+  CUtensorMap tq, ta, to;
+  int rc = get_tmap_seq(p.qkv, p.n_seq, p.S, 3 * D, 3 * D, 128, &tq);
+  if (rc) return rc;
+  rc = get_tmap(p.akv, p.A, 2 * D, p.akv_ld, 16, &ta);
+  if (rc) return rc;
+  rc = get_tmap_seq(p.out, p.n_seq, p.S, D, D, 128, &to);
+  if (rc) return rc;
+  attn_fwd_tcl_kernel<<<dim3(p.qblocks, p.H, p.n_seq), TC_THREADS, LF_SMEM, stream>>>(tq, ta, to, p);
+  return check_launch("attn_fwd_tcl");
+}
+
+int attn_bwd_tcl(const AttnParams& p, cudaStream_t stream) {
+  const int D = p.H * 128;
+  CUtensorMap tq, ta, td, to, tg;
+  int rc = get_tmap_seq(p.qkv, p.n_seq, p.S, 3 * D, 3 * D, 128, &tq);
+  if (rc) return rc;
+  rc = get_tmap(p.akv, p.A, 2 * D, p.akv_ld, 16, &ta);
+  if (rc) return rc;
+  rc = get_tmap_seq(p.dout, p.n_seq, p.S, D, D, 128, &td);
+  if (rc) return rc;
+  rc = get_tmap_seq(p.out, p.n_seq, p.S, D, D, 128, &to);
+  if (rc) return rc;
+  rc = get_tmap_seq(p.dqkv, p.n_seq, p.S, 3 * D, 3 * D, 128, &tg);
+  if (rc) return rc;
+  const dim3 grid(p.qblocks, p.H, p.n_seq);
+  attn_bwd_tcl_dq_kernel<<<grid, TC_THREADS, A_SMEM, stream>>>(tq, ta, td, to, tg, p);
+  rc = check_launch("attn_bwd_tcl_dq");
+  if (rc) return rc;
+  attn_bwd_tcl_dkv_kernel<<<grid, TC_THREADS, K_SMEM, stream>>>(tq, td, tg, p);
+  return check_launch("attn_bwd_tcl_dkv");
+}
+
+}  // namespace fvqa

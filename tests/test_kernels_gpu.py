@@ -230,15 +230,30 @@ def _attn_ref(qkv, akv, gate1, gate2, cos, sin, vstarts, dout, n_seq, S, H, hd, 
     return out.detach(), qkv_r.grad, akv_r.grad, g1.grad, g2.grad
 
 
-@pytest.mark.parametrize("n_seq,S,H,hd,vstarts", [
-    (3, 48, 2, 64, [12, 12, -1]),
-    (3, 128, 2, 128, [18, -1, 18]),
-    (2, 200, 3, 128, [18, -1]),
-    (2, 130, 2, 64, [100, -1]),
+@pytest.mark.parametrize("n_seq,S,H,hd,vstarts,use_tc", [
+    (3, 48, 2, 64, [12, 12, -1], 1),          # hd 64: mma.sync kernels
+    (2, 130, 2, 64, [100, -1], 1),
+    (3, 128, 2, 128, [18, -1, 18], 1),        # tcgen05, one tile (7B / 13B NExT-QA shape)
+    (2, 100, 2, 128, [18, -1], 1),            # tcgen05, partial tile
+    (2, 200, 3, 128, [18, -1], 1),            # tcgen05 tiled (S > 128), ragged last tile
+    (2, 384, 2, 128, [18, -1], 1),            # DramaQA-shaped
+    (1, 650, 2, 128, [18], 1),                # TVQA-shaped
+    (3, 128, 2, 128, [18, -1, 18], 0),        # the same shapes on the mma.sync kernels (hook)
+    (2, 200, 3, 128, [18, -1], 0),
 ])
-def test_attention_fwd_bwd(fvqa_lib, n_seq, S, H, hd, vstarts):
+def test_attention_fwd_bwd(fvqa_lib, n_seq, S, H, hd, vstarts, use_tc):
     from flipped_vqa_b200 import ops
     A, F = 10, 10
+    prev = fvqa_lib.fvqa_attn_debug_use_tc(use_tc)
+    try:
+        assert fvqa_lib.fvqa_attn_uses_tc(S, hd, A) == (1 if (use_tc and hd == 128 and S <= 128) else 0)
+        _attention_fwd_bwd_case(n_seq, S, H, hd, vstarts, A, F)
+    finally:
+        fvqa_lib.fvqa_attn_debug_use_tc(prev)
+
+
+def _attention_fwd_bwd_case(n_seq, S, H, hd, vstarts, A, F):
+    from flipped_vqa_b200 import ops
     qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, vstarts, seed=20)
     qkv_rot = _rotate_qk(qkv, cos, sin, n_seq, S, H, hd)          # the kernel receives rotated q|k (GEMM epilogue)
     out, lse = ops.attn_fwd(qkv_rot, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)
@@ -254,9 +269,10 @@ def test_attention_fwd_bwd(fvqa_lib, n_seq, S, H, hd, vstarts):
     assert relerr(dg2, ref_dg2) < 2e-2, f"dgate2 {relerr(dg2, ref_dg2)} {dg2} {ref_dg2}"
 
 
-def test_attention_deterministic(fvqa_lib):
+@pytest.mark.parametrize("S", [128, 300])
+def test_attention_deterministic(fvqa_lib, S):
     from flipped_vqa_b200 import ops
-    n_seq, S, H, hd, A, F = 3, 128, 2, 128, 10, 10
+    n_seq, H, hd, A, F = 3, 2, 128, 10, 10
     qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, [18, 18, -1], seed=21)
     qkv = _rotate_qk(qkv, cos, sin, n_seq, S, H, hd)
     out, lse = ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F)

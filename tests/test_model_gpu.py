@@ -105,21 +105,37 @@ def _compare_with_oracle(params_dict, run, args, seed, loss_tol=LOSS_RTOL, grad_
             assert a == 0.0 and b == 0.0, name        # `model.py:302` placeholder tensor([0])
     grads = product_grads(model)
     assert set(grads) == set(ref_grads)
-    _check_grads(grads, ref_grads, grad_tol)
+
+    def bf16_reference_grads():
+        """The reference's op sequence under autograd in bf16 (same weights / inputs): the arithmetic noise floor."""
+        st = O.prepare_state(sd, frozen_dtype=torch.bfloat16, device="cuda")
+        ls = O.forward_losses(st, SimpleNamespace(**params_dict), data, max_feats=args.max_feats, tau=args.tau, vaq=args.vaq, qav=args.qav)
+        sum(l for l in ls if l.requires_grad).backward()
+        return {n: st[n].grad.detach().float().cpu() for n in O.trainable_names(st) if st[n].grad is not None}
+
+    _check_grads(grads, ref_grads, grad_tol, noise_floor=bf16_reference_grads)
 
 
-def _check_grads(grads, ref_grads, grad_tol=GRAD_RTOL):
+def _check_grads(grads, ref_grads, grad_tol=GRAD_RTOL, noise_floor=None):
     """2e-2 relative L2 per trainable tensor. The per-layer gates are [1,H,1,1] (2..40 numbers, each a
     cancellation-heavy sum over every token): for them the 2e-2 bound is applied to the stacked
-    gate1 / gate2 vectors over all layers, with a 6e-2 bound per layer — the reference's OWN code run
-    in bf16 shows 4.2e-2 on a single layer's gate1 for the S=650 case ('Parity')."""
+    gate1 / gate2 vectors over all layers, with a 6e-2 bound per layer. A stacked gate vector of a handful of
+    numbers can exceed 2e-2 from bf16 rounding alone (tests/gate_noise_probe.py: S=650, seed 13: the reference's
+    OWN op sequence in bf16 is 3.9e-2 from the fp32 oracle on gate1, seeds 14/15 are < 1e-2); when that happens
+    the bound becomes 'no worse than 1.25x the bf16 reference arithmetic', measured on the same inputs."""
+    floor = None
     for group in ("gate1", "gate2"):
         names = sorted(n for n in ref_grads if n.endswith(group))
         if names:
             a = torch.cat([grads[n].flatten() for n in names])
             b = torch.cat([ref_grads[n].flatten() for n in names])
             e = rel_l2(a, b)
-            assert e < grad_tol, f"grad {group} (stacked over {len(names)} layers): rel L2 {e}"
+            if e >= grad_tol and noise_floor is not None:
+                floor = noise_floor() if floor is None else floor
+                ef = rel_l2(torch.cat([floor[n].flatten() for n in names]), b)
+                assert e < 1.25 * ef, f"grad {group} (stacked over {len(names)} layers): rel L2 {e} vs bf16-reference noise floor {ef}"
+            else:
+                assert e < grad_tol, f"grad {group} (stacked over {len(names)} layers): rel L2 {e}"
     for n in ref_grads:
         e = rel_l2(grads[n], ref_grads[n])
         tol = 3 * grad_tol if "gate" in n else grad_tol

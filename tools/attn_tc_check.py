@@ -46,32 +46,35 @@ def rel(a, b):
 def main():
     bwd = "--fwd-only" not in sys.argv
     names = ["out", "lse", "dqkv", "dakv", "dgate1", "dgate2"]
-    for (n_seq, S, H) in [(3, 128, 2), (2, 48, 2), (5, 100, 3), (24, 128, 32)]:
+    long_mode = "--long" in sys.argv
+    shapes = [(2, 130, 2), (2, 200, 3), (2, 256, 2), (2, 384, 4), (3, 650, 32)] if long_mode else [(3, 128, 2), (2, 48, 2), (5, 100, 3), (24, 128, 32)]
+    for (n_seq, S, H) in shapes:
         c = case(n_seq, S, H)
         ref = run(c, False, bwd)
         got = run(c, True, bwd)
         txt = " ".join(f"{nm}:{rel(g, r):.2e}" for nm, g, r in zip(names, got, ref))
         nan = sum(int(torch.isnan(g.float()).sum()) for g in got)
         print(f"n_seq={n_seq} S={S} H={H}: tc vs mma.sync  {txt}  nan={nan}", flush=True)
-    c = case(24, 128, 32)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     lib = _lib.lib()
-    for tc in (0, 1):
-        lib.fvqa_attn_debug_use_tc(tc)
-        tf = tb = 0.0
-        for it in range(13):
-            flush.zero_()
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-            e[0].record()
-            out, lse = ops.attn_fwd(c["qkv"], c["akv"], c["cos"], c["sin"], c["gate1"], c["gate2"], c["vstart"], 24, 128, 32, 128, 10, 10)
-            e[1].record()
-            if bwd:
-                ops.attn_bwd(c["qkv"], c["akv"], c["cos"], c["sin"], c["gate1"], c["gate2"], c["vstart"], out, lse, c["dout"], 24, 128, 32, 128, 10, 10)
-            e[2].record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
-        print(f"tc={tc}: fwd {tf / 10 * 1e3:.1f} us  bwd {tb / 10 * 1e3:.1f} us", flush=True)
+    for (tn, tS) in ([(6, 384), (3, 650)] if long_mode else [(24, 128)]):
+      c = case(tn, tS, 32)
+      for tc in (0, 1):
+          lib.fvqa_attn_debug_use_tc(tc)
+          tf = tb = 0.0
+          for it in range(13):
+              flush.zero_()
+              e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+              e[0].record()
+              out, lse = ops.attn_fwd(c["qkv"], c["akv"], c["cos"], c["sin"], c["gate1"], c["gate2"], c["vstart"], tn, tS, 32, 128, 10, 10)
+              e[1].record()
+              if bwd:
+                  ops.attn_bwd(c["qkv"], c["akv"], c["cos"], c["sin"], c["gate1"], c["gate2"], c["vstart"], out, lse, c["dout"], tn, tS, 32, 128, 10, 10)
+              e[2].record()
+              torch.cuda.synchronize()
+              if it >= 3:
+                  tf += e[0].elapsed_time(e[1]); tb += e[1].elapsed_time(e[2])
+          print(f"n_seq={tn} S={tS} tc={tc}: fwd {tf / 10 * 1e3:.1f} us  bwd {tb / 10 * 1e3:.1f} us", flush=True)
     lib.fvqa_attn_debug_use_tc(1)
 
 
