@@ -169,3 +169,66 @@ def test_tvqa_shaped_long_sequence(fvqa_lib):
     pd = dict(dim=256, n_layers=2, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
               max_seq_len=650, adapter_len=10, adapter_layer=2)
     _compare_with_oracle(pd, dict(bsz=1, seqlen=650, full_length=True), make_args(), seed=13)
+
+
+def test_13b_shaped_two_layer_slice_vs_oracle(fvqa_lib):
+    """LLaMA-13B layer shapes (d 5120, 40 heads, hidden 13824, BASELINE.json configs[3]), B=8, S=128, 2 layers."""
+    pd = dict(dim=5120, n_layers=2, n_heads=40, vocab_size=32000, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=128, adapter_len=10, adapter_layer=2)
+    _compare_with_oracle(pd, dict(bsz=8, seqlen=128), make_args(), seed=17)
+
+
+@pytest.mark.parametrize("dim,heads", [(256, 4), (256, 2)])      # head_dim 64 (mma.sync) and 128 (tcgen05)
+def test_option_scoring_argmax_agreement(fvqa_lib, dim, heads):
+    """north_star: identical argmax answer choices on >= 99.5 % of synthetic items (loss-based scoring,
+    model_my_original_mod.py:375-377 + engine.py:88-93). 256 items x 5 options, 64 items per batch."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=dim, n_layers=4, n_heads=heads, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=64, adapter_len=10, adapter_layer=4)
+    args = make_args()
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=23, max_feats=args.max_feats, bias=args.bias)
+    model = build_product_model(pd, sd, args)
+    st = O.prepare_state(sd, frozen_dtype=torch.float32, device="cuda", requires_grad=False)
+    agree = total = 0
+    margins = []
+    for b in range(4):
+        data = synthetic_batch(64, 64, pd["vocab_size"], max_feats=args.max_feats, seed=100 + b, n_options=5)
+        tok = model(data, inference=True)
+        pred = model.predict_options(tok).cpu()
+        with torch.no_grad():
+            ref_tok = O.option_token_losses(st, SimpleNamespace(**pd), data, max_feats=args.max_feats)
+        ref_pred = O.option_predict(ref_tok).cpu()
+        agree += int((pred == ref_pred).sum())
+        total += pred.numel()
+        assert rel_l2(tok.cpu()[ref_tok.cpu() != 0], ref_tok.cpu()[ref_tok.cpu() != 0]) < LOSS_RTOL
+    assert total == 256 and agree / total >= 0.995, f"argmax agreement {agree}/{total}"
+
+
+def test_engine_train_and_val_epoch_drop_in(fvqa_lib):
+    """engine.train_one_epoch / val_one_epoch (engine.py:10-56, 59-145) drive the model exactly like the reference's
+    train.py: per-iteration LR schedule, loss_scaler(loss, optimizer, parameters=..., update_grad=...), accum_iter."""
+    import argparse
+    from flipped_vqa_b200 import engine
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    from flipped_vqa_b200.util import misc
+    pd = dict(dim=256, n_layers=2, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=64, adapter_len=10, adapter_layer=2)
+    margs = make_args()
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=29, max_feats=margs.max_feats, bias=margs.bias)
+    model = build_product_model(pd, sd, margs)
+    frozen_before = model.layers[0].attention.wq.weight.detach().clone()
+    adapter_before = model.adapter_query.weight.detach().clone()
+    train_batches = [synthetic_batch(4, 64, 512, max_feats=margs.max_feats, seed=200 + (i % 2)) for i in range(8)]
+    val_batches = [synthetic_batch(4, 64, 512, max_feats=margs.max_feats, seed=300 + i, n_options=5) for i in range(2)]
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+    targs = argparse.Namespace(accum_iter=2, lr=1e-3, min_lr=0.0, warmup_epochs=0, epochs=2, debug=False)
+    scaler = misc.NativeScalerWithGradNormCount()
+    s0 = engine.train_one_epoch(model, train_batches, opt, 0, scaler, args=targs)
+    s1 = engine.train_one_epoch(model, train_batches, opt, 1, scaler, args=targs)
+    for k in ("loss", "vqa_loss", "vaq_loss", "qav_loss", "lr"):
+        assert k in s0 and s0[k] == s0[k]                                   # present and not NaN
+    assert s1["loss"] < s0["loss"], (s0["loss"], s1["loss"])                # the trainables learn the repeated batches
+    assert torch.equal(model.layers[0].attention.wq.weight.detach(), frozen_before)      # frozen base untouched
+    assert not torch.equal(model.adapter_query.weight.detach(), adapter_before)
+    v = engine.val_one_epoch(model, val_batches, opt, 1, args=targs)
+    assert 0.0 <= v["acc"] <= 1.0
