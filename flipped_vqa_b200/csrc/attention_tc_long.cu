@@ -494,16 +494,18 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 namespace {
 constexpr int K_SK = 0, K_SV = 32768, K_SQ = 65536, K_SDO = 98304, K_SP = 131072, K_SDS = 163840, K_ROPE = 196608, K_BAR = 229376;
 constexpr int K_SMEM = K_BAR + 64 + 1024;
+constexpr int LB_THREADS = 256;
 }  // namespace
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// 256 threads: warps w and w + 4 share TMEM lane quadrant w & 3 (rows 32 (w & 3) ..) and split the 128 columns in halves.
+__global__ void __launch_bounds__(LB_THREADS, 1)
 attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_dqkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar_kv = sbase + K_BAR, bar_q = bar_kv + 8, bar_m1 = bar_kv + 16, bar_m2 = bar_kv + 24, holder = bar_kv + 32;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, half = tid >> 7, quad = warp & 3;
   const int kj = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int S = p.S, D = p.H * 128;
   const int key0 = kj * 128;
@@ -518,7 +520,7 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + K_BAR + 32);
-  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 384;
   const int c = h * 128;
   auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
@@ -535,12 +537,12 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     }
   }
   __syncwarp();
-  stage_rope_table(sgen + K_ROPE, p.cosT, p.sinT, key0, S, tid, TC_THREADS);
+  stage_rope_table(sgen + K_ROPE, p.cosT, p.sinT, key0, S, tid, LB_THREADS);
   const ScoreCtx sc = make_score_ctx(p, n, h);
   const float scale = rsqrtf(128.f);
   uint32_t ph_q = 0, ph_m1 = 0, ph_m2 = 0;
   for (int qi = kj; qi < qtiles; ++qi) {
-    const int row_g = qi * 128 + tid;
+    const int row_g = qi * 128 + r;
     const bool row_ok = row_g < S;
     if (tid == 0) {
       if (qi > kj) mbar_wait(bar_m2, ph_m2 ^ 1u);        // previous dV/dK UMMAs done with Q, dO, P, dS
@@ -567,8 +569,8 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     mbar_wait(bar_m1, ph_m1);
     if (qi > kj) mbar_wait(bar_m2, ph_m2 ^ 1u);
     tc_fence_after();
-    const int nch = (qi == kj) ? warp + 1 : 4;
-    for (int ch = 0; ch < 4; ++ch) {
+    const int nch = (qi == kj) ? quad + 1 : 4;
+    for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
       if (ch < nch) {
         uint32_t v[32], w[32];
         tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
@@ -586,14 +588,14 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             fp[e] = pv;
             fd[e] = pv * (__uint_as_float(w[q * 8 + e]) - dx) * scale;
           }
-          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(tid, (ch & 1) * 4 + q);
+          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(r, (ch & 1) * 4 + q);
           *reinterpret_cast<uint4*>(sgen + K_SP + off) = pack8(fp);
           *reinterpret_cast<uint4*>(sgen + K_SDS + off) = pack8(fd);
         }
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(tid, (ch & 1) * 4 + q);
+          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(r, (ch & 1) * 4 + q);
           *reinterpret_cast<uint4*>(sgen + K_SP + off) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(sgen + K_SDS + off) = make_uint4(0, 0, 0, 0);
         }
@@ -623,7 +625,7 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const uint32_t tcol = which == 1 ? T_DK : T_DV;
     const int sdst = which == 1 ? K_SQ : K_SDO;
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
       uint32_t v[32];
       tmem_ld_32x32(tlane + tcol + static_cast<uint32_t>(ch * 32), v);
       tmem_ld_wait();
@@ -632,8 +634,8 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
-        if (which == 1) inv_rope8(f, sgen + K_ROPE, tid, ch * 4 + q);
-        *reinterpret_cast<uint4*>(sgen + sdst + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+        if (which == 1) inv_rope8(f, sgen + K_ROPE, r, ch * 4 + q);
+        *reinterpret_cast<uint4*>(sgen + sdst + (ch >> 1) * 16384 + sw128_off(r, (ch & 1) * 4 + q)) = pack8(f);
       }
     }
     fence_proxy_async();
@@ -691,7 +693,7 @@ int attn_bwd_tcl(const AttnParams& p, cudaStream_t stream) {
   attn_bwd_tcl_dq_kernel<<<grid, TC_THREADS, A_SMEM, stream>>>(tq, ta, td, to, tg, p);
   rc = check_launch("attn_bwd_tcl_dq");
   if (rc) return rc;
-  attn_bwd_tcl_dkv_kernel<<<grid, TC_THREADS, K_SMEM, stream>>>(tq, td, tg, p);
+  attn_bwd_tcl_dkv_kernel<<<grid, LB_THREADS, K_SMEM, stream>>>(tq, td, tg, p);
   return check_launch("attn_bwd_tcl_dkv");
 }
 

@@ -388,3 +388,66 @@ def test_option_score(fvqa_lib):
     dst = torch.zeros(10, device="cuda")
     ops.scatter_rows(vals, torch.tensor([7, -1, 2], dtype=torch.int32, device="cuda"), dst)
     assert dst.tolist() == [0, 0, 3.0, 0, 0, 0, 0, 1.0, 0, 0]
+
+
+# ------------------------------------------------------------------ canaries (compute-sanitizer is not available on the pool)
+def _with_canary(shape, dtype, pad_elems=4096, value=7.0):
+    n = 1
+    for s in shape:
+        n *= s
+    buf = torch.full((n + 2 * pad_elems,), value, dtype=dtype, device="cuda")
+    return buf, buf[pad_elems:pad_elems + n].view(*shape)
+
+
+def _canary_intact(buf, n_inner, pad_elems=4096, value=7.0):
+    return bool((buf[:pad_elems] == value).all()) and bool((buf[pad_elems + n_inner:] == value).all())
+
+
+@pytest.mark.parametrize("n_seq,S,H", [(2, 100, 2), (3, 128, 2), (2, 200, 2), (1, 650, 2)])
+def test_attention_writes_stay_in_bounds(fvqa_lib, n_seq, S, H):
+    """Every output of the tcgen05 attention kernels (TMA stores clipped at the sequence end, per-row stores, workspace)
+    lands inside its buffer: ragged last tiles must not spill into the next sequence / past the allocation."""
+    from flipped_vqa_b200 import ops
+    hd, A, F = 128, 10, 10
+    D = H * hd
+    qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, [18] * n_seq, seed=40)
+    out_buf, out = _with_canary((n_seq * S, D), torch.bfloat16)
+    lse_buf, lse = _with_canary((n_seq, H, S), torch.float32)
+    ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F, out=out, lse=lse)
+    torch.cuda.synchronize()
+    assert _canary_intact(out_buf, out.numel()) and _canary_intact(lse_buf, lse.numel())
+    assert not bool((out == 7.0).all(dim=1).any()), "a row of the output was never written"
+    dq_buf, dqkv = _with_canary((n_seq * S, 3 * D), torch.bfloat16)
+    dakv_buf, dakv = _with_canary((A, 2 * D), torch.float32)
+    g1_buf, dg1 = _with_canary((H,), torch.float32)
+    g2_buf, dg2 = _with_canary((H,), torch.float32)
+    nbytes = ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A)
+    ws_buf, ws = _with_canary((nbytes,), torch.uint8, value=7)
+    ops.attn_bwd(qkv, akv, cos, sin, gate1, gate2, vstart, out, lse, dout, n_seq, S, H, hd, A, F,
+                 dqkv=dqkv, dakv=dakv, dgate1=dg1, dgate2=dg2, ws=ws)
+    torch.cuda.synchronize()
+    for buf, inner in ((dq_buf, dqkv), (dakv_buf, dakv), (g1_buf, dg1), (g2_buf, dg2)):
+        assert _canary_intact(buf, inner.numel())
+    assert _canary_intact(ws_buf, nbytes, value=7)
+    assert not bool((dqkv == 7.0).all(dim=1).any()), "a row of dqkv was never written"
+
+
+@pytest.mark.parametrize("M,N,K", [(200, 384, 128), (650, 1000, 192), (3072, 4096, 256)])
+def test_gemm_writes_stay_in_bounds(fvqa_lib, M, N, K):
+    from flipped_vqa_b200 import ops
+    a = bf16_randn(M, K, seed=41)
+    b = bf16_randn(N, K, std=0.05, seed=42)
+    for f32 in (False, True):
+        buf, c = _with_canary((M, N), torch.float32 if f32 else torch.bfloat16)
+        ops.gemm_nt(a, b, out=c, out_fp32=f32)
+        torch.cuda.synchronize()
+        assert _canary_intact(buf, c.numel())
+    if N % 256 == 0:
+        hid = N // 2
+        gbuf, g = _with_canary((M, N), torch.bfloat16)
+        cbuf, c = _with_canary((M, hid), torch.bfloat16)
+        ops.gemm_swiglu_fwd(a, b, g=g, c=c)
+        dbuf, dg = _with_canary((M, N), torch.bfloat16)
+        ops.gemm_swiglu_bwd(a, bf16_randn(hid, K, std=0.05, seed=43), g, dg=dg)
+        torch.cuda.synchronize()
+        assert _canary_intact(gbuf, g.numel()) and _canary_intact(cbuf, c.numel()) and _canary_intact(dbuf, dg.numel())
