@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int, period: float = 0.1):
         super().__init__(daemon=True)
         self.index, self.period = index, period
-        self.samples, self.reasons = [], set()
+        self.samples, self.power, self.reasons = [], [], set()
         self.max_mhz = None
         self._stop_evt = threading.Event()
         try:
@@ -111,6 +111,7 @@ class ClockSampler(threading.Thread):
         while not self._stop_evt.is_set():
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                 r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
@@ -124,7 +125,9 @@ class ClockSampler(threading.Thread):
         self._stop_evt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
-        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons))
+        pw = sorted(self.power)
+        return dict(sm_mhz=(s[len(s) // 2] if s else None), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                    power_w=(round(pw[len(pw) // 2], 1) if pw else None))
 
 
 # ---------------------------------------------------------------------------------------------------
