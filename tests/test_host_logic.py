@@ -121,3 +121,56 @@ def test_grad_buffer_layout():
     assert gb.late_offset == 32 * 10 * 4096
     gb.adapter[5, 7] = 3.0
     assert float(gb.flat[5 * 4096 + 7]) == 3.0
+
+
+def test_merge_shards_reassembles_model_parallel_checkpoint():
+    """llama_vqa.py:25-58: Meta's model-parallel shards are concatenated along their split dimension
+    (column-parallel wq/wk/wv/w1/w3/output on dim 0, row-parallel wo/w2/tok_embeddings on dim 1, norms replicated)."""
+    from types import SimpleNamespace
+    from flipped_vqa_b200.llama_vqa import merge_shards
+    from flipped_vqa_b200.synthetic import synthetic_state_dict
+    full = {k: v for k, v in synthetic_state_dict(SimpleNamespace(**GOLDEN), seed=2).items()
+            if not any(s in k for s in ("gate", "adapter", "temporal_emb", "visual_proj"))}
+    col = ("wq.weight", "wk.weight", "wv.weight", "w1.weight", "w3.weight", "output.weight")
+    row = ("wo.weight", "w2.weight", "tok_embeddings.weight")
+    shards = [{}, {}]
+    for k, v in full.items():
+        for r in range(2):
+            if k.endswith(col):
+                shards[r][k] = v.chunk(2, dim=0)[r].clone()
+            elif k.endswith(row):
+                shards[r][k] = v.chunk(2, dim=1)[r].clone()
+            else:
+                shards[r][k] = v.clone()
+    merged = merge_shards(shards, GOLDEN["n_layers"])
+    assert set(merged) == set(full)
+    for k in full:
+        assert torch.equal(merged[k], full[k]), k
+    assert merge_shards([full], GOLDEN["n_layers"]) is full
+
+
+def test_checkpoint_save_resume_roundtrip(tmp_path):
+    """util/misc.py:297-336: checkpoints hold only the trainables (+ optimizer, scaler, epoch, args) under the
+    reference's parameter names; resume restores them into a fresh model with strict=False."""
+    import argparse
+    from flipped_vqa_b200.util import misc
+    m = _model()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if p.requires_grad:
+                p.add_(torch.randn_like(p) * 0.1)
+    opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3)
+    args = argparse.Namespace(output_dir=str(tmp_path), resume="")
+    misc.save_model(args, 3, m, m, opt, misc.NativeScalerWithGradNormCount(), "best")
+    ck = torch.load(tmp_path / "checkpoint_best.pth", map_location="cpu", weights_only=False)
+    names = set(ck["model"])
+    assert names == {n for n, p in m.named_parameters() if p.requires_grad}          # trainables only, reference names
+    assert "adapter_query.weight" in names and "layers.1.attention.gate2" in names and not any("wq" in n for n in names)
+    m2 = _model()
+    opt2 = torch.optim.AdamW([p for p in m2.parameters() if p.requires_grad], lr=1e-3)
+    args.resume = str(tmp_path / "checkpoint_best.pth")
+    misc.load_model(args, m2, opt2, misc.NativeScalerWithGradNormCount())
+    assert args.start_epoch == 4
+    for (n, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
+        if a.requires_grad:
+            assert torch.equal(a, b), n
