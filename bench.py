@@ -64,9 +64,10 @@ def gemm_traffic():
     return None
 
 
-def flops_per_step(cfg, n_labelled):
+def flops_per_step(cfg, n_labelled, n_live=None):
     """F_step = 3*(2*body + 3.5*attn) + 2*sum(head) + small; heads counted on the
-    labelled rows actually evaluated (never count work not done)."""
+    labelled rows actually evaluated (never count work not done). `n_live`: rows the LAST layer's wo / FFN
+    actually process (only the rows the losses read); the rows it skips are subtracted, forward and backward."""
     d, L, V, B, S = cfg["dim"], cfg["adapter_layer"], cfg["vocab_size"], cfg["bsz"], cfg["seqlen"]
     from flipped_vqa_b200.synthetic import ffn_hidden_dim
     hid = ffn_hidden_dim(d, cfg["multiple_of"])
@@ -75,7 +76,10 @@ def flops_per_step(cfg, n_labelled):
     attn = L * 4 * B * d * (S * (S + 1) / 2 + S * ADAPTER_LEN)
     head = 2 * n_labelled * d * V
     small = L * 2 * ADAPTER_LEN * 2 * d * d + 2 * B * MAX_FEATS * 768 * d
-    return 3 * (2 * body + 3.5 * attn) + 2 * head + small
+    total = 3 * (2 * body + 3.5 * attn) + 2 * head + small
+    if n_live is not None:
+        total -= 2 * (3 * T - n_live) * 2 * (d * d + 3 * d * hid)
+    return total
 
 
 def make_args():
@@ -287,7 +291,8 @@ def main():
     plans = [model.plan_batch(b) for b in batches]
     torch.cuda.synchronize()
     n_lab = sum(p.ce_total for p in plans) / len(plans)
-    step_flops = flops_per_step(cfg, n_lab)
+    n_live = sum(p.n_live for p in plans) / len(plans)
+    step_flops = flops_per_step(cfg, n_lab, n_live if model._engine.prune_last_layer else None)
 
     def step_resident(i):
         vqa, vaq, qav = net.forward_plan(plans[i % len(plans)])
@@ -331,7 +336,7 @@ def main():
         return ms, launches, clocks, (timer.summary() if timer is not None else None)
 
     L = cfg["adapter_layer"]
-    model._engine.sample_layers = tuple(sorted({0, L - 1} if a.sample_layers >= 2 else {L - 1})) if a.sample_layers > 0 else ()
+    model._engine.sample_layers = tuple(sorted({0, L // 2} if a.sample_layers >= 2 else {L // 2})) if a.sample_layers > 0 else ()   # not the pruned last layer
     for i in range(a.warmup):
         step_resident(i)
     ms, launches, clocks, gemm = timed(step_resident, a.steps, sample_gemm=a.sample_layers > 0)
@@ -356,7 +361,8 @@ def main():
             "config": {"workload": WORKLOAD_NAMES[a.config], "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}",
                        "l2": "working set (2 x 13.5 GB frozen weights + 9 GB saved activations per step) >> 126 MB L2; no explicit flush",
                        "objectives": "vqa+vaq+qav", "optimizer": "AdamW(fused) on 4.5M trainables", "flops_per_step": step_flops,
-                       "labelled_rows_per_step": n_lab},
+                       "labelled_rows_per_step": n_lab,
+                       "last_layer_live_rows": (n_live if model._engine.prune_last_layer else None)},
             "tensor_util": {"value": step_flops / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops"],
                             "achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12, "peak_tflops": peaks["bf16_tflops"],
                             "peak_sustained_tflops": peaks["bf16_tflops_sustained"], "peak_source": peaks["source"]},

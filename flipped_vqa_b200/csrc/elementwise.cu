@@ -178,6 +178,21 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restri
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// dst[i, :] = src[idx[i], :] (GATHER) or dst[idx[i], :] = src[i, :] (!GATHER); rows of `vecs` 16-byte vectors
+template <bool GATHER>
+__global__ void __launch_bounds__(256) move_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx, uint4* __restrict__ dst,
+                                                        long rows, int vecs) {
+  const long total = rows * vecs;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / vecs;
+    const int v = static_cast<int>(i - r * vecs);
+    const long o = idx[r];
+    if (o < 0) continue;
+    if (GATHER) dst[r * vecs + v] = __ldg(src + o * vecs + v);
+    else dst[o * vecs + v] = __ldg(src + r * vecs + v);
+  }
+}
+
 static int elementwise_grid(long work_items, int threads) {
   long blocks = (work_items + threads - 1) / threads;
   const long cap = 148L * 8;  // 8 resident CTAs of 256 threads per SM
@@ -253,4 +268,22 @@ extern "C" int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, voi
   if (n <= 0) return FVQA_OK;
   f32_to_bf16_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
   return check_launch("f32_to_bf16");
+}
+
+extern "C" int fvqa_gather_rows(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream) {
+  FVQA_REQUIRE(row_bytes % 16 == 0, FVQA_ERR_UNSUPPORTED, "gather_rows: row_bytes %d must be a multiple of 16", row_bytes);
+  if (rows <= 0) return FVQA_OK;
+  const int vecs = row_bytes / 16;
+  move_rows_kernel<true><<<elementwise_grid(static_cast<long>(rows) * vecs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(src), idx, reinterpret_cast<uint4*>(dst), rows, vecs);
+  return check_launch("gather_rows");
+}
+
+extern "C" int fvqa_scatter_row_vectors(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream) {
+  FVQA_REQUIRE(row_bytes % 16 == 0, FVQA_ERR_UNSUPPORTED, "scatter_row_vectors: row_bytes %d must be a multiple of 16", row_bytes);
+  if (rows <= 0) return FVQA_OK;
+  const int vecs = row_bytes / 16;
+  move_rows_kernel<false><<<elementwise_grid(static_cast<long>(rows) * vecs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(src), idx, reinterpret_cast<uint4*>(dst), rows, vecs);
+  return check_launch("scatter_row_vectors");
 }

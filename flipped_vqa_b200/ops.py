@@ -394,3 +394,22 @@ def f32_to_bf16(src, dst=None):
     dst = torch.empty(src.shape, dtype=BF16, device=src.device) if dst is None else dst
     check(_lib.lib().fvqa_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream()), "f32_to_bf16")
     return dst
+
+
+@_timed
+def gather_rows(src: torch.Tensor, idx: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dst[i] = src[idx[i]] for 2-D contiguous src (any dtype whose rows are a multiple of 16 bytes)."""
+    assert src.is_contiguous() and idx.dtype == torch.int32
+    rows, row_bytes = idx.numel(), src.shape[1] * src.element_size()
+    dst = torch.empty(rows, src.shape[1], dtype=src.dtype, device=src.device) if dst is None else dst
+    check(_lib.lib().fvqa_gather_rows(ptr(src), ptr(idx), ptr(dst), rows, row_bytes, stream()), "gather_rows")
+    return dst
+
+
+@_timed
+def scatter_row_vectors(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor) -> torch.Tensor:
+    """dst[idx[i]] = src[i] (dst pre-initialised by the caller; indices unique)."""
+    assert src.is_contiguous() and dst.is_contiguous() and idx.dtype == torch.int32 and src.dtype == dst.dtype
+    rows, row_bytes = idx.numel(), src.shape[1] * src.element_size()
+    check(_lib.lib().fvqa_scatter_row_vectors(ptr(src), ptr(idx), ptr(dst), rows, row_bytes, stream()), "scatter_row_vectors")
+    return dst

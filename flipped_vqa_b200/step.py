@@ -72,8 +72,14 @@ class BatchPlan:
         ce_rows = torch.cat(ce_rows) if ce_rows else torch.zeros(0, dtype=I32)
         ce_tgt = torch.cat(ce_tgt) if ce_tgt else torch.zeros(0, dtype=I32)
         ce_dst = torch.cat(ce_dst) if ce_dst else torch.zeros(0, dtype=I32)
+        # rows whose final hidden state any loss reads: the LAST layer's wo / FFN only run on these (sorted, unique);
+        # ce_rows_c / q_rows_c index into that compact row set
+        live = torch.unique(torch.cat([ce_rows.long(), q_rows.long()]), sorted=True)
+        self.n_live = int(live.numel())
+        ce_rows_c = torch.searchsorted(live, ce_rows.long()).to(I32)
+        q_rows_c = torch.searchsorted(live, q_rows.long()).to(I32)
         parts = [ids_all.flatten(), labels_all.flatten(), vstart, seq_video, qav_index.flatten(),
-                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid]
+                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid, live.to(I32), ce_rows_c, q_rows_c]
         sizes = [p.numel() for p in parts]
         total = max(sum(sizes), 1)
         video = _cpu(data["video"]).reshape(B * F, -1).float()
@@ -94,7 +100,8 @@ class BatchPlan:
 
     def to_device(self, device):
         dev = self.host_ints.to(device, non_blocking=True)
-        names = ["ids", "labels", "vstart", "seq_video", "qav_index", "ce_rows", "ce_tgt", "ce_dst", "q_rows", "q_tgt", "q_vid"]
+        names = ["ids", "labels", "vstart", "seq_video", "qav_index", "ce_rows", "ce_tgt", "ce_dst", "q_rows", "q_tgt", "q_vid",
+                 "live_rows", "ce_rows_c", "q_rows_c"]
         for nm, (off, n) in zip(names, self._slices):
             setattr(self, nm, dev[off:off + n])
         self.video = self.host_video.to(device, non_blocking=True)
@@ -171,6 +178,7 @@ class SavedStep:
     rstd1: List[torch.Tensor] = field(default_factory=list)
     rstd2: List[torch.Tensor] = field(default_factory=list)
     vf32: Optional[torch.Tensor] = None
+    pruned: bool = False        # last layer ran on plan.live_rows only (h / g / rstd2 / final x of that layer are compact)
     ce: Optional[dict] = None
     qav: Optional[dict] = None
 
@@ -191,6 +199,9 @@ class StepEngine:
         self.sin = torch.sin(ang).to(device).contiguous()
         self._attn_ws = None
         self.sample_layers = ()      # layers whose GEMM launches bench.py's GemmTimer samples
+        # wo / FFN of the last layer only on the rows the losses read: -2.1 % FLOPs, but the M ~ 260 GEMMs fill 32-86 of the
+        # 74 CTA pairs and the step time does not move (76.00 vs 76.06 ms) -> off by default, kept + tested
+        self.prune_last_layer = False
 
     # -------------------------------------------------------------------------------- forward
     def forward(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
@@ -208,6 +219,10 @@ class StepEngine:
         xn = torch.empty(T, d, dtype=BF16, device=dev)
         c = torch.empty(T, hid, dtype=BF16, device=dev)
         qkv_b = o_b = g_b = None
+        # The last layer's wo / FFN outputs are read only at the rows the losses use (labelled positions): run them on
+        # those rows alone, exactly like the vocabulary projection (heads below). Everything upstream needs all rows (K/V).
+        prune = self.prune_last_layer and 0 < plan.n_live < T
+        ce_idx, q_idx = (plan.ce_rows_c, plan.q_rows_c) if prune else (plan.ce_rows, plan.q_rows)
         for l, w in enumerate(layers):
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
@@ -217,25 +232,34 @@ class StepEngine:
             akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])          # adapter K|V, no RoPE (`model.py:99-100`)
             o, lse = ops.attn_fwd(qkv, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F,
                                   out=None if save else o_b)
-            h = ops.gemm_nt(o, w.wo, residual=x, out_fp32=True)                    # h = x + attn  (`model.py:185`), fp32 stream
-            _, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
-            g, _ = ops.gemm_swiglu_fwd(xn, w.w13, g=None if save else g_b, c=c)      # W1|W3 GEMM, SwiGLU in its epilogue
-            x_next = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)               # out = h + ffn (`model.py:186`)
+            if prune and l == L - 1:
+                o_g = ops.gather_rows(o, plan.live_rows)
+                x_g = ops.gather_rows(x, plan.live_rows)
+                h = ops.gemm_nt(o_g, w.wo, residual=x_g, out_fp32=True)            # [n_live, d]
+                xn_g, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps)
+                g, c_g = ops.gemm_swiglu_fwd(xn_g, w.w13)
+                x_next = ops.gemm_nt(c_g, w.w2, residual=h, out_fp32=True)
+            else:
+                h = ops.gemm_nt(o, w.wo, residual=x, out_fp32=True)                # h = x + attn  (`model.py:185`), fp32 stream
+                _, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
+                g, _ = ops.gemm_swiglu_fwd(xn, w.w13, g=None if save else g_b, c=c)  # W1|W3 GEMM, SwiGLU in its epilogue
+                x_next = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)           # out = h + ffn (`model.py:186`)
             if save:
                 sv.x.append(x); sv.qkv.append(qkv); sv.akv.append(akv); sv.o.append(o); sv.lse.append(lse)
                 sv.h.append(h); sv.g.append(g); sv.rstd1.append(rstd1); sv.rstd2.append(rstd2)
-            else:
+            elif not (prune and l == L - 1):
                 qkv_b, o_b, g_b = qkv, o, g
             x = x_next
         if save:
             sv.x.append(x)
             sv.vf32 = vf32
+            sv.pruned = prune
         if ops.GEMM_TIMER is not None:
             ops.GEMM_TIMER.active = False
         # --- heads
         losses = {}
         if plan.ce_total > 0:
-            hn, rstd = ops.rmsnorm_gather_fwd(x, plan.ce_rows, norm_w, self.eps)     # final norm on labelled rows only
+            hn, rstd = ops.rmsnorm_gather_fwd(x, ce_idx, norm_w, self.eps)          # final norm on labelled rows only
             logits = ops.gemm_nt(hn, out_w, out_fp32=True)                          # [rows, V] fp32, never [B*S, V]
             row_loss, row_lse = ops.ce_fwd(logits, plan.ce_tgt)
             if token_losses:
@@ -265,7 +289,7 @@ class StepEngine:
         if "qav" in plan.streams:
             out = torch.empty((), dtype=torch.float32, device=dev)
             if plan.q_count > 0:
-                hnq, rstdq = ops.rmsnorm_gather_fwd(x, plan.q_rows, norm_w, self.eps)
+                hnq, rstdq = ops.rmsnorm_gather_fwd(x, q_idx, norm_w, self.eps)
                 row_loss, prob = ops.qav_loss_fwd(hnq, vf32, plan.q_vid, plan.q_tgt, self.tau, F)
                 ops.sum_scale(row_loss, plan.q_count, 1.0 / plan.q_count, out)
                 if save:
@@ -285,9 +309,12 @@ class StepEngine:
         T, n_seq, dev = plan.T, plan.n_seq, self.device
         L = len(layers)
         x_final = sv.x[L]
+        pruned = sv.pruned
+        R = plan.n_live if pruned else T                      # rows of the final hidden state that exist
+        ce_idx, q_idx = (plan.ce_rows_c, plan.q_rows_c) if pruned else (plan.ce_rows, plan.q_rows)
         # gradient of the residual stream: fp32 master + bf16 copy (A operand of the next dX GEMM)
-        dx = torch.zeros(T, d, dtype=torch.float32, device=dev)
-        dx_bf = torch.zeros(T, d, dtype=BF16, device=dev)
+        dx = torch.zeros(R, d, dtype=torch.float32, device=dev)
+        dx_bf = torch.zeros(R, d, dtype=BF16, device=dev)
         gidx = {"vqa": 0, "vaq": 1, "qav": 2}
         # --- heads backward
         if sv.ce is not None:
@@ -303,13 +330,13 @@ class StepEngine:
                                gscale[gidx[k]:gidx[k] + 1], 1.0 / n, dlogits=dlogits[off:off + n])
                 off += n
             dhn = ops.gemm_nt(dlogits, out_w_t)                                     # dH = dlogits . W_out
-            ops.rmsnorm_scatter_bwd(dhn, x_final, plan.ce_rows, norm_w, ce["rstd"], dx, dx_bf)
+            ops.rmsnorm_scatter_bwd(dhn, x_final, ce_idx, norm_w, ce["rstd"], dx, dx_bf)
         dvf_qav = None
         if sv.qav is not None:
             q = sv.qav
             dhnq, dvf_qav = ops.qav_loss_bwd(q["hn"], sv.vf32, plan.q_vid, plan.q_tgt, q["prob"], gscale[2:3],
                                              1.0 / plan.q_count, self.tau, plan.n_video, F)
-            ops.rmsnorm_scatter_bwd(dhnq, x_final, plan.q_rows, norm_w, q["rstd"], dx, dx_bf)
+            ops.rmsnorm_scatter_bwd(dhnq, x_final, q_idx, norm_w, q["rstd"], dx, dx_bf)
         # --- layers, last to first
         if self._attn_ws is None or self._attn_ws.numel() < ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A):
             self._attn_ws = torch.empty(ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
@@ -326,10 +353,24 @@ class StepEngine:
             w = layers[l]
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
-            ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l], dg=dg)                     # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
-            ops.gemm_nt(dg, w.w13_t, out=dtmp)                                     # d(ffn_norm out) = [da|db] . [W1;W3]
-            ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_bf16=dh_bf)
-            ops.gemm_nt(dh_bf, w.wo_t, out=dtmp)                                   # d(attn out) = dh . Wo
+            if pruned and l == L - 1:
+                # compact rows through the FFN and wo of the last layer, then scatter d(attn out) and dh back to all rows
+                dg_c = ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l])
+                dtmp_c = ops.gemm_nt(dg_c, w.w13_t)
+                dh_c, dh_c_bf = ops.rmsnorm_bwd(dtmp_c, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx,
+                                                dx_bf16=torch.empty(R, d, dtype=BF16, device=dev))
+                do_c = ops.gemm_nt(dh_c_bf, w.wo_t)
+                dtmp.zero_()
+                ops.scatter_row_vectors(do_c, plan.live_rows, dtmp)
+                dh.zero_()
+                ops.scatter_row_vectors(dh_c, plan.live_rows, dh)
+                dx = torch.empty(T, d, dtype=torch.float32, device=dev)           # full-size stream from here down
+                dx_bf = torch.empty(T, d, dtype=BF16, device=dev)
+            else:
+                ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l], dg=dg)                 # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
+                ops.gemm_nt(dg, w.w13_t, out=dtmp)                                 # d(ffn_norm out) = [da|db] . [W1;W3]
+                ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_bf16=dh_bf)
+                ops.gemm_nt(dh_bf, w.wo_t, out=dtmp)                               # d(attn out) = dh . Wo
             ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dtmp,
                          n_seq, S, H, hd, A, F, dqkv=dqkv, dakv=dakv, dgate1=grads.gate1[l], dgate2=grads.gate2[l], ws=self._attn_ws)
             ops.gemm_nt(dqkv, w.wqkv_t, out=dtmp)                                  # d(attn_norm out) = dqkv . [Wq;Wk;Wv]

@@ -170,6 +170,12 @@ int fvqa_scatter_rows(const float* row_val, const int32_t* dst_index, float* dst
 int fvqa_option_score(const float* token_loss, int32_t* prediction, float* mean_loss, int n_items,
                       int n_opt, int len, void* stream);
 
+/* ---- live-row pruning of the LAST layer: only the rows the losses read (labelled positions) go through
+ *      its wo / FFN GEMMs, like the vocabulary projection (llama/model.py:347-356 never needs the other rows' outputs).
+ *      dst[i, :] = src[idx[i], :]   and   dst[idx[i], :] = src[i, :]   for rows of row_bytes (multiple of 16); idx < 0 skipped. */
+int fvqa_gather_rows(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream);
+int fvqa_scatter_row_vectors(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream);
+
 /* ---- small utilities --------------------------------------------------------------------------- */
 int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, void* stream);
 

@@ -232,3 +232,35 @@ def test_engine_train_and_val_epoch_drop_in(fvqa_lib):
     assert not torch.equal(model.adapter_query.weight.detach(), adapter_before)
     v = engine.val_one_epoch(model, val_batches, opt, 1, args=targs)
     assert 0.0 <= v["acc"] <= 1.0
+
+
+def test_last_layer_live_row_pruning_is_equivalent(fvqa_lib):
+    """StepEngine.prune_last_layer: the last layer's wo / FFN run only on the rows the losses read. Same losses
+    (bit-identical: same rows, same kernels) and the same gradients up to the bf16 rounding of zero rows."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=128, adapter_len=10, adapter_layer=3)
+    args = make_args()
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=31, max_feats=args.max_feats, bias=args.bias)
+    data = synthetic_batch(4, 128, 512, max_feats=args.max_feats, seed=31)
+    res = []
+    for prune in (False, True):
+        model = build_product_model(pd, sd, args)
+        model._ensure_packed()
+        model._engine.prune_last_layer = prune
+        losses = _run_product(model, data)
+        res.append((losses, product_grads(model)))
+        if prune:
+            assert 0 < model.last_plan.n_live < model.last_plan.T
+    (l0, g0), (l1, g1) = res
+    assert l0 == l1
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) < 1e-3, n
+    tok = []
+    opt_data = synthetic_batch(4, 128, 512, max_feats=args.max_feats, seed=32, n_options=5)
+    for prune in (False, True):
+        model = build_product_model(pd, sd, args)
+        model._ensure_packed()
+        model._engine.prune_last_layer = prune
+        tok.append(model(opt_data, inference=True))
+    assert torch.equal(tok[0], tok[1])
