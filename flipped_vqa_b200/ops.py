@@ -34,6 +34,7 @@ class GemmTimer:
 
 
 GEMM_TIMER: Optional[GemmTimer] = None
+FUSE_SWIGLU = True      # A/B switch (tools/ab_step.py): False = plain GEMM + stand-alone SwiGLU kernels
 
 
 class OpTimer:
@@ -208,7 +209,7 @@ def gemm_swiglu_fwd(x: torch.Tensor, w13: torch.Tensor, g: Optional[torch.Tensor
     hid = w13.shape[0] // 2
     g = torch.empty(M, 2 * hid, dtype=BF16, device=x.device) if g is None else g
     c = torch.empty(M, hid, dtype=BF16, device=x.device) if c is None else c
-    if hid % 128 != 0:
+    if hid % 128 != 0 or not FUSE_SWIGLU:
         gemm_nt(x, w13, out=g)
         swiglu_fwd(g, c)
         return g, c
@@ -230,7 +231,7 @@ def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Op
     M, K = dy.shape
     hid = w2t.shape[0]
     dg = torch.empty(M, 2 * hid, dtype=BF16, device=dy.device) if dg is None else dg
-    if hid % 32 != 0:
+    if hid % 32 != 0 or not FUSE_SWIGLU:
         dc = gemm_nt(dy, w2t)
         return swiglu_bwd(dc, g, dg)
     tm = GEMM_TIMER

@@ -199,9 +199,9 @@ class StepEngine:
         self.sin = torch.sin(ang).to(device).contiguous()
         self._attn_ws = None
         self.sample_layers = ()      # layers whose GEMM launches bench.py's GemmTimer samples
-        # wo / FFN of the last layer only on the rows the losses read: -2.1 % FLOPs, but the M ~ 260 GEMMs fill 32-86 of the
-        # 74 CTA pairs and the step time does not move (76.00 vs 76.06 ms) -> off by default, kept + tested
-        self.prune_last_layer = False
+        # wo / FFN of the last layer only on the rows the losses read: -2.1 % FLOPs, -1.8 % step time in a same-box A/B
+        # (tools/ab_step.py); results identical (tests/test_model_gpu.py::test_last_layer_live_row_pruning_is_equivalent)
+        self.prune_last_layer = True
 
     # -------------------------------------------------------------------------------- forward
     def forward(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
