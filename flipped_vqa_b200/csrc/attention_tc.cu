@@ -138,13 +138,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
   }
   const float inv = 1.f / l;
-  // P (normalised, bf16) -> K's buffer as the K-major SW128 A operand of P.V
+  // P (normalised, bf16, two keys per 32-bit column) -> TMEM columns [0,64) over the consumed S: the A operand of P.V
+  // never touches shared memory
 #pragma unroll
-  for (int c16 = 0; c16 < 16; ++c16) {
-    float f[8];
+  for (int half = 0; half < 2; ++half) {
+    uint32_t pk[32];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = s[c16 * 8 + e] * inv;
-    *reinterpret_cast<uint4*>(sgen + F_SK + (c16 >> 3) * 16384 + sw128_off(r, c16 & 7)) = pack8(f);
+    for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(s[half * 64 + 2 * e] * inv, s[half * 64 + 2 * e + 1] * inv);
+    tmem_st_32x32(tlane + static_cast<uint32_t>(half * 32), pk);
   }
   // adapter branch: separate softmax over the A adapter keys, scaled by tanh(gate1)
   {
@@ -164,16 +165,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       la += sa[j];
     }
     const float ia = tg / la;
+    uint32_t pa[8];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = sa[c * 8 + e] * ia;
-      *reinterpret_cast<uint4*>(sgen + F_SPA + (r >> 3) * 256 + c * 128 + (r & 7) * 16) = pack8(f);
-    }
+    for (int e = 0; e < 8; ++e) pa[e] = pack_bf16x2(sa[2 * e] * ia, sa[2 * e + 1] * ia);
+    tmem_st_32x8(tlane + 64u, pa);                 // P_a -> TMEM columns [64,72)
   }
+  tmem_st_wait();
   if (r < S) p.lse[(static_cast<long>(n) * p.H + h) * S + r] = (mx + log2f(l)) * TC_LN2;
-  fence_proxy_async();            // generic-proxy smem writes -> visible to the UMMA (async proxy)
   tc_fence_before();
   __syncthreads();
 
@@ -183,12 +181,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tc_fence_after();
     constexpr uint32_t id_o = idesc_bf16(128, 128, 0, 1);
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint64_t a = umma_desc_k_sw128(sbase + F_SK + (ks >> 2) * 16384) + static_cast<uint64_t>(2 * (ks & 3));
-      const uint64_t b = desc_mn_sw128(sbase + F_SV + ks * 2048, 16384);
-      umma_bf16_ss(tmem + 128, a, b, id_o, ks > 0 ? 1u : 0u);      // O = P V (overwrites the consumed S_a columns)
-    }
-    umma_bf16_ss(tmem + 128, desc_nosw(sbase + F_SPA, 128, 256), desc_mn_sw128(sbase + F_SVA, 2048), id_o, 1u);   // += P_a Va
+    for (int ks = 0; ks < 8; ++ks)                                 // O = P V, A = P from TMEM (8 columns = 16 keys per step)
+      umma_bf16_ts(tmem + 128, tmem + static_cast<uint32_t>(ks * 8), desc_mn_sw128(sbase + F_SV + ks * 2048, 16384), id_o, ks > 0 ? 1u : 0u);
+    umma_bf16_ts(tmem + 128, tmem + 64u, desc_mn_sw128(sbase + F_SVA, 2048), id_o, 1u);   // += P_a Va
     umma_commit(bar_o);
   }
   __syncwarp();
