@@ -489,44 +489,64 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
-// backward B: key tile owner -> dK, dV
+// backward B: key tile owner -> dK, dV. Transposed formulation: S^T = K_j Q_i^T and dP^T = V_j dO_i^T put the KEYS on
+// the TMEM lanes, so P^T and dS^T are written back into TMEM (bf16, two rows per 32-bit column, in place over S^T /
+// dP^T) and feed dV += P^T dO_i, dK += dS^T Q_i as TMEM-resident A operands (TS-mode UMMA): no shared-memory round
+// trip, and the 64 KB that P / dS occupied become a second Q / dO buffer -> the TMA loads of tile i+1 overlap tile i.
 // ---------------------------------------------------------------------------------------------
 namespace {
-constexpr int K_SK = 0, K_SV = 32768, K_SQ = 65536, K_SDO = 98304, K_SP = 131072, K_SDS = 163840, K_ROPE = 196608, K_BAR = 229376;
+constexpr int K_SK = 0, K_SV = 32768;                 // resident key tile
+constexpr int K_BUF0 = 65536;                         // [2] x { Q_i 32 KB | dO_i 32 KB }; buffer 0 doubles as RoPE table / dK staging at the end
+constexpr int K_BUFSZ = 65536;
+constexpr int K_LSE = 196608;                         // [2][128] lse (log2 domain) | [2][128] D of the query tile
+constexpr int K_BAR = K_LSE + 2048;
 constexpr int K_SMEM = K_BAR + 64 + 1024;
 constexpr int LB_THREADS = 256;
 }  // namespace
 
-// 256 threads: warps w and w + 4 share TMEM lane quadrant w & 3 (rows 32 (w & 3) ..) and split the 128 columns in halves.
+// 256 threads: warps w and w + 4 share TMEM lane quadrant w & 3 (keys 32 (w & 3) ..) and split the 128 columns (query rows).
 __global__ void __launch_bounds__(LB_THREADS, 1)
 attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                         const __grid_constant__ CUtensorMap tm_dqkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar_kv = sbase + K_BAR, bar_q = bar_kv + 8, bar_m1 = bar_kv + 16, bar_m2 = bar_kv + 24, holder = bar_kv + 32;
+  const uint32_t bar_kv = sbase + K_BAR, bar_q0 = bar_kv + 8, bar_q1 = bar_kv + 16, bar_m1 = bar_kv + 24, bar_m2 = bar_kv + 32, holder = bar_kv + 40;
+  float* s_lse = reinterpret_cast<float*>(sgen + K_LSE);          // [2][128]
+  float* s_dx = s_lse + 256;                                       // [2][128]
   const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, half = tid >> 7, quad = warp & 3;
   const int kj = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int S = p.S, D = p.H * 128;
-  const int key0 = kj * 128;
+  const int key0 = kj * 128, key_g = key0 + r;
   const int qtiles = p.qblocks;
 
   if (tid == 0) {
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1);
+    mbar_init(bar_kv, 1); mbar_init(bar_q0, 1); mbar_init(bar_q1, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(holder, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + K_BAR + 32);
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + K_BAR + 40);
   const uint32_t tlane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
-  constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 384;
+  constexpr uint32_t T_ST = 0, T_DPT = 128, T_DV = 256, T_DK = 384;
   const int c = h * 128;
-  auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
-  auto mndesc = [&](int off, int lbo, int ks) { return desc_mn_sw128(sbase + off + ks * 2048, lbo); };
-  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_tt = idesc_bf16(128, 128, 1, 1);
+  auto kdesc = [&](int off, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * 16384) + static_cast<uint64_t>(2 * (ks & 3)); };
+  auto mndesc = [&](int off, int ks) { return desc_mn_sw128(sbase + off + ks * 2048, 16384); };
+  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_t = idesc_bf16(128, 128, 0, 1);
+  const long nh = static_cast<long>(n) * p.H + h;
 
+  auto load_q_tile = [&](int qi, int buf) {            // tid 0 only
+    const uint32_t bar = buf ? bar_q1 : bar_q0;
+    const int off = K_BUF0 + buf * K_BUFSZ;
+    mbar_arrive_expect_tx(bar, 65536);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_3d(sbase + off + kb * 16384, &tm_qkv, bar, c + kb * 64, qi * 128, n);
+      tma_load_3d(sbase + off + 32768 + kb * 16384, &tm_do, bar, c + kb * 64, qi * 128, n);
+    }
+  };
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_dqkv);
     mbar_arrive_expect_tx(bar_kv, 65536);
@@ -535,95 +555,123 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tma_load_3d(sbase + K_SK + kb * 16384, &tm_qkv, bar_kv, D + c + kb * 64, key0, n);
       tma_load_3d(sbase + K_SV + kb * 16384, &tm_qkv, bar_kv, 2 * D + c + kb * 64, key0, n);
     }
+    load_q_tile(kj, 0);
   }
-  __syncwarp();
-  stage_rope_table(sgen + K_ROPE, p.cosT, p.sinT, key0, S, tid, LB_THREADS);
   const ScoreCtx sc = make_score_ctx(p, n, h);
   const float scale = rsqrtf(128.f);
-  uint32_t ph_q = 0, ph_m1 = 0, ph_m2 = 0;
-  for (int qi = kj; qi < qtiles; ++qi) {
-    const int row_g = qi * 128 + r;
-    const bool row_ok = row_g < S;
+  const bool key_biased = key_g >= sc.bias_c0 && key_g < sc.bias_c1;
+  uint32_t ph_q[2] = {0, 0}, ph_m1 = 0, ph_m2 = 0;
+  int it = 0;
+  for (int qi = kj; qi < qtiles; ++qi, ++it) {
+    const int buf = it & 1;
+    const int qoff = K_BUF0 + buf * K_BUFSZ, dooff = qoff + 32768;
+    // lse / D of this query tile -> smem (threads 0..127: lse, 128..255: D)
+    {
+      const int row_g = qi * 128 + r;
+      // -lse (log2 domain; +inf-like for rows past the sequence so that P = 0 there) and D / sqrt(hd)
+      float v = half ? 0.f : -1e30f;
+      if (row_g < S) v = half ? p.ws_dx[nh * (qtiles * 128) + row_g] * scale : -p.lse[nh * S + row_g] * TC_LOG2E;
+      (half ? s_dx : s_lse)[buf * 128 + r] = v;
+    }
     if (tid == 0) {
-      if (qi > kj) mbar_wait(bar_m2, ph_m2 ^ 1u);        // previous dV/dK UMMAs done with Q, dO, P, dS
-      mbar_arrive_expect_tx(bar_q, 65536);
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-        tma_load_3d(sbase + K_SQ + kb * 16384, &tm_qkv, bar_q, c + kb * 64, qi * 128, n);
-        tma_load_3d(sbase + K_SDO + kb * 16384, &tm_do, bar_q, c + kb * 64, qi * 128, n);
-      }
-      if (qi == kj) mbar_wait(bar_kv, 0);
-      mbar_wait(bar_q, ph_q);
+      if (it > 0) mbar_wait(bar_m2, ph_m2 ^ 1u);         // UMMAs of tile it-1 are done with the other Q / dO buffer
+      if (qi + 1 < qtiles) load_q_tile(qi + 1, buf ^ 1);  // prefetch the next query tile
+      if (it == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(buf ? bar_q1 : bar_q0, ph_q[buf]);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        umma_bf16_ss(tmem + T_S, kdesc(K_SQ, 16384, ks), kdesc(K_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
-        umma_bf16_ss(tmem + T_DP, kdesc(K_SDO, 16384, ks), kdesc(K_SV, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_bf16_ss(tmem + T_ST, kdesc(K_SK, ks), kdesc(qoff, ks), id_s, ks > 0 ? 1u : 0u);      // S^T  = K_j Q_i^T
+        umma_bf16_ss(tmem + T_DPT, kdesc(K_SV, ks), kdesc(dooff, ks), id_s, ks > 0 ? 1u : 0u);    // dP^T = V_j dO_i^T
       }
       umma_commit(bar_m1);
     }
-    __syncwarp();
-    const float lse2 = row_ok ? p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] * TC_LOG2E : 0.f;
-    const float dx = row_ok ? p.ws_dx[(static_cast<long>(n) * p.H + h) * (qtiles * 128) + row_g] : 0.f;
-    const bool row_biased = row_g >= sc.bias_row0;
+    __syncthreads();                                      // lse / D staged; also orders tid 0's issue before the waits below
     mbar_wait(bar_m1, ph_m1);
-    if (qi > kj) mbar_wait(bar_m2, ph_m2 ^ 1u);
     tc_fence_after();
-    const int nch = (qi == kj) ? quad + 1 : 4;
-    for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-      if (ch < nch) {
-        uint32_t v[32], w[32];
-        tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
-        tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(ch * 32), w);
-        tmem_ld_wait();
+    // this thread: key key_g (lane), query rows [64 half, 64 half + 64) of the tile (columns)
+    uint32_t vs_[64], vd_[64];
+    const bool diag = (qi == kj);
+    // on the diagonal tile rows < 32 quad are all masked for this warp's keys: 32-row chunks c < quad are zero
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float fp[8], fd[8];
+    for (int cc = 0; cc < 2; ++cc) {
+      const int ch = 2 * half + cc;
+      uint32_t a[32], b[32];
+      tmem_ld_32x32(tlane + T_ST + static_cast<uint32_t>(ch * 32), a);
+      tmem_ld_32x32(tlane + T_DPT + static_cast<uint32_t>(ch * 32), b);
+      tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col_g = key0 + ch * 32 + q * 8 + e;
-            float t = __uint_as_float(v[q * 8 + e]) * sc.scale2;
-            if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
-            const float pv = (col_g > row_g || !row_ok) ? 0.f : exp2f(t - lse2);
-            fp[e] = pv;
-            fd[e] = pv * (__uint_as_float(w[q * 8 + e]) - dx) * scale;
+      for (int e = 0; e < 32; ++e) { vs_[cc * 32 + e] = a[e]; vd_[cc * 32 + e] = b[e]; }
+    }
+    tc_fence_before();
+    __syncthreads();                                      // both column halves of every lane are in registers: in-place overwrite is safe
+    tc_fence_after();
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int ch = 2 * half + cc;
+      uint32_t pp[16], dd[16];
+      if (!diag || ch >= quad) {
+        // gate2 bias: this key is a video column and the row is past the video block (uniform per 32-row chunk
+        // except for the one chunk that contains bias_row0)
+        const int row0_g = qi * 128 + ch * 32;
+        const float badd_all = (key_biased && row0_g >= sc.bias_row0) ? sc.bias2 : 0.f;
+        const bool bias_mixed = key_biased && row0_g < sc.bias_row0 && row0_g + 32 > sc.bias_row0;
+        const bool causal = diag && ch == quad;           // only the chunk on the diagonal needs the key > row test
+        const float4* l4 = reinterpret_cast<const float4*>(s_lse + buf * 128 + ch * 32);
+        const float4* d4 = reinterpret_cast<const float4*>(s_dx + buf * 128 + ch * 32);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 nl = l4[q4], dxs = d4[q4];          // broadcast reads: 4 rows at a time
+          const float nlv[4] = {nl.x, nl.y, nl.z, nl.w}, dxv[4] = {dxs.x, dxs.y, dxs.z, dxs.w};
+          float pv[4], ds[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = q4 * 4 + u;
+            float t = fmaf(__uint_as_float(vs_[cc * 32 + e]), sc.scale2, nlv[u] + badd_all);     // s * c - lse (+ bias)
+            if (bias_mixed && row0_g + e >= sc.bias_row0) t += sc.bias2;
+            float pe = exp2f(t);
+            if (causal && key_g > row0_g + e) pe = 0.f;
+            pv[u] = pe;
+            ds[u] = pe * fmaf(__uint_as_float(vd_[cc * 32 + e]), scale, -dxv[u]);                  // P (dP - D) / sqrt(hd)
           }
-          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(r, (ch & 1) * 4 + q);
-          *reinterpret_cast<uint4*>(sgen + K_SP + off) = pack8(fp);
-          *reinterpret_cast<uint4*>(sgen + K_SDS + off) = pack8(fd);
+          pp[q4 * 2] = pack_bf16x2(pv[0], pv[1]); pp[q4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
+          dd[q4 * 2] = pack_bf16x2(ds[0], ds[1]); dd[q4 * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t off = static_cast<uint32_t>((ch >> 1) * 16384) + sw128_off(r, (ch & 1) * 4 + q);
-          *reinterpret_cast<uint4*>(sgen + K_SP + off) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(sgen + K_SDS + off) = make_uint4(0, 0, 0, 0);
-        }
+        for (int e = 0; e < 16; ++e) { pp[e] = 0u; dd[e] = 0u; }
       }
+      // rows [32 ch, 32 ch + 32) -> packed columns [16 ch, 16 ch + 16)
+      tmem_st_32x16(tlane + T_ST + static_cast<uint32_t>(ch * 16), pp);
+      tmem_st_32x16(tlane + T_DPT + static_cast<uint32_t>(ch * 16), dd);
     }
-    fence_proxy_async();
+    tmem_st_wait();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t accum = qi > kj ? 1u : 0u;
+      const uint32_t accum = it > 0 ? 1u : 0u;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
-        umma_bf16_ss(tmem + T_DV, mndesc(K_SP, 16384, ks), mndesc(K_SDO, 16384, ks), id_tt, (accum || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < 8; ++ks)                      // dV[key][d] += sum_rows P^T[key][row] dO[row][d]
+        umma_bf16_ts(tmem + T_DV, tmem + T_ST + static_cast<uint32_t>(ks * 8), mndesc(dooff, ks), id_t, (accum || ks > 0) ? 1u : 0u);
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
-        umma_bf16_ss(tmem + T_DK, mndesc(K_SDS, 16384, ks), mndesc(K_SQ, 16384, ks), id_tt, (accum || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < 8; ++ks)                      // dK[key][d] += sum_rows dS^T[key][row] Q[row][d]
+        umma_bf16_ts(tmem + T_DK, tmem + T_DPT + static_cast<uint32_t>(ks * 8), mndesc(qoff, ks), id_t, (accum || ks > 0) ? 1u : 0u);
       umma_commit(bar_m2);
     }
     __syncwarp();
-    ph_q ^= 1u; ph_m1 ^= 1u; ph_m2 ^= 1u;
+    ph_q[buf] ^= 1u; ph_m1 ^= 1u; ph_m2 ^= 1u;
   }
   mbar_wait(bar_m2, ph_m2 ^ 1u);
   tc_fence_after();
+  // all shared memory is free now: RoPE table of the key positions -> buffer 1 (buffer 0 stages dK / dV)
+  uint8_t* s_rope = sgen + K_BUF0 + K_BUFSZ;
+  stage_rope_table(s_rope, p.cosT, p.sinT, key0, S, tid, LB_THREADS);
+  __syncthreads();
 #pragma unroll 1
   for (int which = 1; which < 3; ++which) {              // 1: dK (inverse RoPE at the key positions), 2: dV
     const uint32_t tcol = which == 1 ? T_DK : T_DV;
-    const int sdst = which == 1 ? K_SQ : K_SDO;
+    const int sdst = K_BUF0 + (which == 1 ? 0 : 32768);
 #pragma unroll
     for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
       uint32_t v[32];
@@ -634,7 +682,7 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
-        if (which == 1) inv_rope8(f, sgen + K_ROPE, r, ch * 4 + q);
+        if (which == 1) inv_rope8(f, s_rope, r, ch * 4 + q);
         *reinterpret_cast<uint4*>(sgen + sdst + (ch >> 1) * 16384 + sw128_off(r, (ch & 1) * 4 + q)) = pack8(f);
       }
     }
