@@ -43,6 +43,10 @@ constexpr int LF_SMEM = LF_BAR + 64 + 1024;
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
                     const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
+  // Single pass over the key tiles j <= i with an online softmax: S = Q K_j^T (UMMA) -> per-row p = exp2(s - m_ref)
+  // -> P (bf16) written back into TMEM over S -> O += P V_j (TS-mode UMMA, accumulator in TMEM). The reference maximum
+  // m_ref only moves when a tile's maximum exceeds it by more than 2^8 (then O and l are rescaled through TMEM), so
+  // rescaling is rare; the final O / l and the adapter term (tanh(g1) softmax_a, pre-multiplied by l) end the row.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -65,8 +69,18 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const int c = h * 128;
   constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0), id_o = idesc_bf16(128, 128, 0, 1);
+  constexpr uint32_t T_S = 0, T_O = 128, T_SA = 128;      // S_a sits in O's columns until the first P.V overwrites them
   auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
-
+  auto load_k = [&](int j) {
+    mbar_arrive_expect_tx(bar_k, 32768);
+    tma_load_3d(sbase + LF_SK, &tm_qkv, bar_k, D + c, j * 128, n);
+    tma_load_3d(sbase + LF_SK + 16384, &tm_qkv, bar_k, D + c + 64, j * 128, n);
+  };
+  auto load_v = [&](int j) {
+    mbar_arrive_expect_tx(bar_v, 32768);
+    tma_load_3d(sbase + LF_SV, &tm_qkv, bar_v, 2 * D + c, j * 128, n);
+    tma_load_3d(sbase + LF_SV + 16384, &tm_qkv, bar_v, 2 * D + c + 64, j * 128, n);
+  };
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_akv); tma_prefetch_desc(&tm_out);
     mbar_arrive_expect_tx(bar_q, 32768 + 8192);
@@ -76,125 +90,113 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tma_load_2d(sbase + LF_SKA + kb * 2048, &tm_akv, bar_q, c + kb * 64, 0);
       tma_load_2d(sbase + LF_SVA + kb * 2048, &tm_akv, bar_q, D + c + kb * 64, 0);
     }
+    load_k(0);
+    load_v(0);
   }
   const ScoreCtx sc = make_score_ctx(p, n, h);
   const bool row_biased = row_g >= sc.bias_row0;
-  uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_o = 0;     // mbarrier phase parities (uniform across threads)
-  float m_run = -INFINITY, l_run = 0.f;
+  uint32_t ph_k = 0, ph_v = 0, ph_s = 0, ph_o = 0;
+  float m_ref = -INFINITY, l_run = 0.f;
+  float pa_n[16];                                        // tanh(g1) * softmax over the adapter keys (fp32, row-local)
 
-  // one S = Q K_j^T into TMEM columns [0,128) (+ S_a at [128,144) when with_adapter)
-  auto issue_s = [&](int j, bool with_adapter) {
-    mbar_arrive_expect_tx(bar_k, 32768);
-    tma_load_3d(sbase + LF_SK, &tm_qkv, bar_k, D + c, j * 128, n);
-    tma_load_3d(sbase + LF_SK + 16384, &tm_qkv, bar_k, D + c + 64, j * 128, n);
-    if (with_adapter) { mbar_wait(bar_q, 0); }
-    mbar_wait(bar_k, ph_k);
-    tc_fence_after();
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      umma_bf16_ss(tmem, kdesc(LF_SQ, 16384, ks), kdesc(LF_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
-      if (with_adapter) umma_bf16_ss(tmem + 128, kdesc(LF_SQ, 16384, ks), kdesc(LF_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
-    }
-    umma_commit(bar_s);
-  };
-
-  // ---------------- pass 1: row max / sum over all key tiles ----------------
-  for (int j = 0; j <= qi; ++j) {
-    if (tid == 0) issue_s(j, j == 0);
-    __syncwarp();
-    mbar_wait(bar_s, ph_s);
-    tc_fence_after();
-    const int nch = (j == qi) ? warp + 1 : 4;            // diagonal tile: chunks beyond the warp's last row are masked
-    for (int ch = 0; ch < nch; ++ch) {
-      uint32_t v[32];
-      tmem_ld_32x32(tlane + static_cast<uint32_t>(ch * 32), v);
-      tmem_ld_wait();
-      float x[32], mx = m_run;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const int col_g = j * 128 + ch * 32 + e;
-        float t = __uint_as_float(v[e]) * sc.scale2;
-        if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
-        if (col_g > row_g) t = -INFINITY;
-        x[e] = t;
-        mx = fmaxf(mx, t);
-      }
-      float add = 0.f;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) add += exp2f(x[e] - mx);
-      l_run = l_run * exp2f(m_run - mx) + add;           // m_run = -inf, l_run = 0 on the first chunk: 0 * 0 + add
-      m_run = mx;
-    }
-    if (j == 0) {
-      // adapter branch (independent of the key tiles): separate softmax x tanh(gate1) -> P_a operand
-      uint32_t v[32];
-      tmem_ld_32x16(tlane + 128u, v);
-      tmem_ld_wait();
-      const float tg = tanhf(p.gate1[h]);
-      float sa[16], ma = -INFINITY, la = 0.f;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        sa[e] = (e < p.A) ? __uint_as_float(v[e]) * sc.scale2 : -INFINITY;
-        ma = fmaxf(ma, sa[e]);
-      }
-#pragma unroll
-      for (int e = 0; e < 16; ++e) { sa[e] = exp2f(sa[e] - ma); la += sa[e]; }
-      const float ia = tg / la;
-#pragma unroll
-      for (int cc = 0; cc < 2; ++cc) {
-        float f[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = sa[cc * 8 + e] * ia;
-        *reinterpret_cast<uint4*>(sgen + LF_SPA + (tid >> 3) * 256 + cc * 128 + (tid & 7) * 16) = pack8(f);
-      }
-    }
-    ph_k ^= 1u; ph_s ^= 1u;
-    tc_fence_before();
-    __syncthreads();                                    // everyone has read S before the next UMMA overwrites it
-    tc_fence_after();
-  }
-  const float inv_l = 1.f / l_run;
-  if (row_g < S) p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] = (m_run + log2f(l_run)) * TC_LN2;
-
-  // ---------------- pass 2: P = exp2(S - m) / l, O += P V_j ----------------
   for (int j = 0; j <= qi; ++j) {
     if (tid == 0) {
-      if (j > 0) { mbar_wait(bar_o, ph_o); }            // previous P.V has finished reading P (K's buffer) and V
-      mbar_arrive_expect_tx(bar_v, 32768);
-      tma_load_3d(sbase + LF_SV, &tm_qkv, bar_v, 2 * D + c, j * 128, n);
-      tma_load_3d(sbase + LF_SV + 16384, &tm_qkv, bar_v, 2 * D + c + 64, j * 128, n);
-      issue_s(j, false);
+      if (j == 0) mbar_wait(bar_q, 0);
+      mbar_wait(bar_k, ph_k);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        umma_bf16_ss(tmem + T_S, kdesc(LF_SQ, 16384, ks), kdesc(LF_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        if (j == 0) umma_bf16_ss(tmem + T_SA, kdesc(LF_SQ, 16384, ks), kdesc(LF_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+      }
+      umma_commit(bar_s);
     }
     __syncwarp();
-    if (j > 0) ph_o ^= (tid == 0) ? 1u : 0u;
     mbar_wait(bar_s, ph_s);
     tc_fence_after();
+    if (tid == 0 && j < qi) load_k(j + 1);                // K's buffer is free as soon as S is complete
+    if (j == 0) {
+      uint32_t v[32];
+      tmem_ld_32x16(tlane + T_SA, v);
+      tmem_ld_wait();
+      const float tg = tanhf(p.gate1[h]);
+      float ma = -INFINITY, la = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        pa_n[e] = (e < p.A) ? __uint_as_float(v[e]) * sc.scale2 : -INFINITY;
+        ma = fmaxf(ma, pa_n[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { pa_n[e] = exp2f(pa_n[e] - ma); la += pa_n[e]; }
+      const float ia = tg / la;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) pa_n[e] *= ia;
+    }
+    // scores of this tile (diagonal tile: 32-column chunks beyond the warp's last row are fully masked)
     const int nch = (j == qi) ? warp + 1 : 4;
+    float x[128];
+    float mx = -INFINITY;
+#pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
       if (ch < nch) {
         uint32_t v[32];
-        tmem_ld_32x32(tlane + static_cast<uint32_t>(ch * 32), v);
+        tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col_g = j * 128 + ch * 32 + q * 8 + e;
-            float t = __uint_as_float(v[q * 8 + e]) * sc.scale2;
-            if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
-            f[e] = (col_g > row_g) ? 0.f : exp2f(t - m_run) * inv_l;
-          }
-          *reinterpret_cast<uint4*>(sgen + LF_SK + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+        for (int e = 0; e < 32; ++e) {
+          const int col_g = j * 128 + ch * 32 + e;
+          float t = __uint_as_float(v[e]) * sc.scale2;
+          if (row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1) t += sc.bias2;
+          if (col_g > row_g) t = -INFINITY;
+          x[ch * 32 + e] = t;
+          mx = fmaxf(mx, t);
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(sgen + LF_SK + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < 32; ++e) x[ch * 32 + e] = -INFINITY;
       }
     }
+    // lazy rescale of the running state: only when this tile's maximum beats the reference by > 2^8 (warp-uniform
+    // decision: tcgen05.ld/st are warp-collective); the previous P.V has retired (S_j was issued after it completed)
+    const bool bump = mx > m_ref + 8.f;
+    if (__any_sync(0xffffffffu, bump)) {
+      const float m_new = bump ? mx : m_ref;
+      const float f = (m_ref == -INFINITY) ? 0.f : exp2f(m_ref - m_new);
+      if (j > 0) {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(tlane + T_O + static_cast<uint32_t>(ch * 32), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
+          tmem_st_32x32(tlane + T_O + static_cast<uint32_t>(ch * 32), v);
+        }
+      }
+      l_run *= f;
+      m_ref = m_new;
+    }
+    // P = exp2(x - m_ref) (bf16, two keys per column) -> TMEM columns [0,64) over the consumed S
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t pk[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const float p0 = exp2f(x[hf * 64 + 2 * e] - m_ref), p1 = exp2f(x[hf * 64 + 2 * e + 1] - m_ref);
+        l_run += p0 + p1;
+        pk[e] = pack_bf16x2(p0, p1);
+      }
+      tmem_st_32x32(tlane + T_S + static_cast<uint32_t>(hf * 32), pk);
+    }
+    if (j == qi) {
+      // adapter probabilities pre-multiplied by l so that the final O / l leaves tanh(g1) softmax_a . Va
+      uint32_t pa[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pa[e] = pack_bf16x2(pa_n[2 * e] * l_run, pa_n[2 * e + 1] * l_run);
+      tmem_st_32x8(tlane + T_S + 64u, pa);
+    }
+    tmem_st_wait();
     ph_k ^= 1u; ph_s ^= 1u;
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
@@ -203,29 +205,32 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
-        umma_bf16_ss(tmem + 128, kdesc(LF_SK, 16384, ks), desc_mn_sw128(sbase + LF_SV + ks * 2048, 16384), id_o, (j > 0 || ks > 0) ? 1u : 0u);
-      if (j == qi) umma_bf16_ss(tmem + 128, desc_nosw(sbase + LF_SPA, 128, 256), desc_mn_sw128(sbase + LF_SVA, 2048), id_o, 1u);
+        umma_bf16_ts(tmem + T_O, tmem + T_S + static_cast<uint32_t>(ks * 8), desc_mn_sw128(sbase + LF_SV + ks * 2048, 16384), id_o,
+                     (j > 0 || ks > 0) ? 1u : 0u);
+      if (j == qi) umma_bf16_ts(tmem + T_O, tmem + T_S + 64u, desc_mn_sw128(sbase + LF_SVA, 2048), id_o, 1u);
       umma_commit(bar_o);
+      // the next S overwrites P's columns and the next V load overwrites V: both wait for this P.V
+      mbar_wait(bar_o, ph_o);
+      if (j < qi) load_v(j + 1);
     }
     __syncwarp();
-    ph_v ^= 1u;
+    ph_v ^= 1u; ph_o ^= 1u;
   }
-  // all threads: wait for the last P.V (tid 0 has consumed the earlier phases of bar_o itself)
-  {
-    const uint32_t last = static_cast<uint32_t>(qi) & 1u;   // bar_o completes once per tile: phase of completion #qi
-    mbar_wait(bar_o, last);
-  }
+  // every thread: the last P.V (completion #qi of bar_o)
+  mbar_wait(bar_o, static_cast<uint32_t>(qi) & 1u);
   tc_fence_after();
+  const float inv_l = 1.f / l_run;
+  if (row_g < S) p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] = (m_ref + log2f(l_run)) * TC_LN2;
 #pragma unroll
   for (int ch = 0; ch < 4; ++ch) {
     uint32_t v[32];
-    tmem_ld_32x32(tlane + 128u + static_cast<uint32_t>(ch * 32), v);
+    tmem_ld_32x32(tlane + T_O + static_cast<uint32_t>(ch * 32), v);
     tmem_ld_wait();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float f[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) * inv_l;
       *reinterpret_cast<uint4*>(sgen + LF_SQ + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
     }
   }
