@@ -252,28 +252,33 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
 namespace {
 constexpr int A_SQ = 0, A_SDO = 32768, A_SK = 65536, A_SV = 98304, A_SDS = 131072;   // A_SDS first holds the O tile
 constexpr int A_SKA = 163840, A_SVA = 167936, A_SPA = 172032, A_SDSA = 176128, A_ROPE = 180224, A_BAR = 212992;
-constexpr int A_RED = A_BAR + 64;
-constexpr int A_SMEM = A_BAR + 128 + 1024;
+constexpr int A_RED = A_BAR + 64;                     // 32 floats: per-warp gate partials
+constexpr int A_ROW = A_BAR + 256;                    // [4][128] floats of per-row scratch
+constexpr int A_SMEM = A_ROW + 2048 + 1024;
+constexpr int LQ_THREADS = 512;
 }  // namespace
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// 512 threads: the four warps w, w+4, w+8, w+12 share TMEM lane quadrant w & 3 (query rows 32 (w & 3) ..) and take one
+// 32-column chunk each (part = tid / 128); with one warp per scheduler the row-wise math is pure exposed latency.
+__global__ void __launch_bounds__(LQ_THREADS, 1)
 attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
                        const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_o,
                        const __grid_constant__ CUtensorMap tm_dqkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  const uint32_t bar_q = sbase + A_BAR, bar_kv = bar_q + 8, bar_m1 = bar_q + 16, bar_m2 = bar_q + 24, bar_ma = bar_q + 32, holder = bar_q + 40;
+  const uint32_t bar_q = sbase + A_BAR, bar_kv0 = bar_q + 8, bar_m1 = bar_q + 16, bar_m2 = bar_q + 24, bar_ma = bar_q + 32, holder = bar_q + 40,
+                 bar_kv1 = bar_q + 48;
   float* sred = reinterpret_cast<float*>(sgen + A_RED);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 127, part = tid >> 7, quad = warp & 3;
   const int qi = static_cast<int>(gridDim.x) - 1 - static_cast<int>(blockIdx.x);   // longest key loops are scheduled first
   const int h = blockIdx.y, n = blockIdx.z;
   const int S = p.S, D = p.H * 128;
-  const int row0 = qi * 128, row_g = row0 + tid;
+  const int row0 = qi * 128, row_g = row0 + r;
   const bool row_ok = row_g < S;
 
   if (tid == 0) {
-    mbar_init(bar_q, 1); mbar_init(bar_kv, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1); mbar_init(bar_ma, 1);
+    mbar_init(bar_q, 1); mbar_init(bar_kv0, 1); mbar_init(bar_kv1, 1); mbar_init(bar_m1, 1); mbar_init(bar_m2, 1); mbar_init(bar_ma, 1);
     fence_mbar_init();
   }
   if (warp == 0) { tmem_alloc(holder, 512); tmem_relinquish(); }
@@ -281,7 +286,7 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + A_BAR + 40);
-  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   constexpr uint32_t T_S = 0, T_DP = 128, T_DQ = 256, T_SA = 384, T_DPA = 400, T_DKA = 416;   // dVa^T at T_DKA + 16
   const int c = h * 128;
   auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
@@ -289,6 +294,18 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0), id_q = idesc_bf16(128, 128, 0, 1),
                      id_at = idesc_bf16(128, 16, 1, 1);
 
+  // K/V tile buffers: 0 = (A_SK, A_SV); 1 = (A_SDS once the O tile has been consumed, A_ROPE)
+  auto koff = [&](int buf) { return buf ? A_SDS : A_SK; };
+  auto voff = [&](int buf) { return buf ? A_ROPE : A_SV; };
+  auto load_kv = [&](int j, int buf) {                  // tid 0 only
+    const uint32_t bar = buf ? bar_kv1 : bar_kv0;
+    mbar_arrive_expect_tx(bar, 65536);
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_3d(sbase + koff(buf) + kb * 16384, &tm_qkv, bar, D + c + kb * 64, j * 128, n);
+      tma_load_3d(sbase + voff(buf) + kb * 16384, &tm_qkv, bar, 2 * D + c + kb * 64, j * 128, n);
+    }
+  };
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv); tma_prefetch_desc(&tm_akv); tma_prefetch_desc(&tm_do); tma_prefetch_desc(&tm_o); tma_prefetch_desc(&tm_dqkv);
     mbar_arrive_expect_tx(bar_q, 3 * 32768 + 8192);
@@ -300,9 +317,9 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       tma_load_2d(sbase + A_SKA + kb * 2048, &tm_akv, bar_q, c + kb * 64, 0);
       tma_load_2d(sbase + A_SVA + kb * 2048, &tm_akv, bar_q, D + c + kb * 64, 0);
     }
+    load_kv(0, 0);
   }
   __syncwarp();
-  stage_rope_table(sgen + A_ROPE, p.cosT, p.sinT, row0, S, tid, TC_THREADS);
   if (tid == 0) {
     mbar_wait(bar_q, 0);
     tc_fence_after();
@@ -315,26 +332,34 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   }
   __syncwarp();
   mbar_wait(bar_q, 0);
-  // D_total = <dO, O> of this row from the staged tiles
-  float dtot = 0.f;
-#pragma unroll 4
-  for (int c16 = 0; c16 < 16; ++c16) {
-    float a[8], b[8];
-    const uint32_t off = static_cast<uint32_t>((c16 >> 3) * 16384) + sw128_off(tid, c16 & 7);
-    unpack8(*reinterpret_cast<const uint4*>(sgen + A_SDS + off), a);
-    unpack8(*reinterpret_cast<const uint4*>(sgen + A_SDO + off), b);
+  // D_total = <dO, O> of this row from the staged tiles: each of the 4 parts sums 4 of the 16 chunks
+  float* s_row = reinterpret_cast<float*>(sgen + A_ROW);          // [4][128] partial D | later [128] -lse, [128] D / sqrt(hd)
+  {
+    float dpart = 0.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dtot += a[e] * b[e];
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c16 = part * 4 + cc;
+      float a[8], b[8];
+      const uint32_t off = static_cast<uint32_t>((c16 >> 3) * 16384) + sw128_off(r, c16 & 7);
+      unpack8(*reinterpret_cast<const uint4*>(sgen + A_SDS + off), a);
+      unpack8(*reinterpret_cast<const uint4*>(sgen + A_SDO + off), b);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dpart += a[e] * b[e];
+    }
+    s_row[part * 128 + r] = dpart;
   }
+  __syncthreads();
   const ScoreCtx sc = make_score_ctx(p, n, h);
   const bool row_biased = row_g >= sc.bias_row0;
   const float scale = rsqrtf(128.f);
-  const float tg = tanhf(p.gate1[h]);
-  const float lse2 = row_ok ? p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] * TC_LOG2E : 0.f;
-  float g1_part = 0.f, g2_part = 0.f, dx;
+  float g1_part = 0.f, g2_part = 0.f;
   mbar_wait(bar_ma, 0);
   tc_fence_after();
-  {
+  float nlse_own = 0.f, dxs_own = 0.f;
+  if (part == 0) {                                        // adapter branch + row constants: one thread per row
+    const float dtot = (s_row[r] + s_row[128 + r]) + (s_row[256 + r] + s_row[384 + r]);
+    const float tg = tanhf(p.gate1[h]);
+    const float lse2 = row_ok ? p.lse[(static_cast<long>(n) * p.H + h) * S + row_g] * TC_LOG2E : 0.f;
     uint32_t v[32], w[32];
     tmem_ld_32x16(tlane + T_SA, v);
     tmem_ld_32x16(tlane + T_DPA, w);
@@ -351,7 +376,7 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
     for (int e = 0; e < 16; ++e) { sa[e] *= ia; da += sa[e] * __uint_as_float(w[e]); }
     g1_part = da;
-    dx = dtot - tg * da;
+    const float dx = dtot - tg * da;
     if (row_ok) p.ws_dx[(static_cast<long>(n) * p.H + h) * (p.qblocks * 128) + row_g] = dx;
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
@@ -362,75 +387,88 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         fp[e] = tg * pa;
         fd[e] = tg * pa * (__uint_as_float(w[cc * 8 + e]) - da) * scale;
       }
-      const int off = (tid >> 3) * 256 + cc * 128 + (tid & 7) * 16;
+      const int off = (r >> 3) * 256 + cc * 128 + (r & 7) * 16;
       *reinterpret_cast<uint4*>(sgen + A_SPA + off) = pack8(fp);
       *reinterpret_cast<uint4*>(sgen + A_SDSA + off) = pack8(fd);
     }
+    nlse_own = row_ok ? -lse2 : -1e30f;                   // p = exp2(s c + nlse); rows past the sequence give p = 0
+    dxs_own = dx * scale;                                 // ds = p (dp / sqrt(hd) - dxs)
   }
+  __syncthreads();                                        // partial D consumed
+  if (part == 0) { s_row[r] = nlse_own; s_row[128 + r] = dxs_own; }
   tc_fence_before();
   __syncthreads();                                       // O tile fully consumed: its buffer becomes dS
   tc_fence_after();
 
-  uint32_t ph_kv = 0, ph_m1 = 0, ph_m2 = 0;
+  const float nlse = s_row[r], dxs = s_row[128 + r];      // (written before the barrier above)
+  uint32_t ph_kv[2] = {0, 0}, ph_m1 = 0, ph_m2 = 0;
   for (int j = 0; j <= qi; ++j) {
+    const int buf = j & 1;
     if (tid == 0) {
-      if (j > 0) mbar_wait(bar_m2, ph_m2 ^ 1u);          // previous dQ UMMA done with K's buffer (parity of completion j-1)
-      mbar_arrive_expect_tx(bar_kv, 65536);
-#pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
-        tma_load_3d(sbase + A_SK + kb * 16384, &tm_qkv, bar_kv, D + c + kb * 64, j * 128, n);
-        tma_load_3d(sbase + A_SV + kb * 16384, &tm_qkv, bar_kv, 2 * D + c + kb * 64, j * 128, n);
-      }
-      mbar_wait(bar_kv, ph_kv);
+      if (j > 0) mbar_wait(bar_m2, ph_m2 ^ 1u);          // dQ UMMA of tile j-1 retired: its K buffer and the dS columns are free
+      if (j < qi) load_kv(j + 1, buf ^ 1);                // prefetch the next key tile
+      mbar_wait(buf ? bar_kv1 : bar_kv0, ph_kv[buf]);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        umma_bf16_ss(tmem + T_S, kdesc(A_SQ, 16384, ks), kdesc(A_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
-        umma_bf16_ss(tmem + T_DP, kdesc(A_SDO, 16384, ks), kdesc(A_SV, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_bf16_ss(tmem + T_S, kdesc(A_SQ, 16384, ks), kdesc(koff(buf), 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_bf16_ss(tmem + T_DP, kdesc(A_SDO, 16384, ks), kdesc(voff(buf), 16384, ks), id_s, ks > 0 ? 1u : 0u);
       }
       umma_commit(bar_m1);
     }
     __syncwarp();
     mbar_wait(bar_m1, ph_m1);
-    if (j > 0) mbar_wait(bar_m2, ph_m2 ^ 1u);            // dS buffer free again
     tc_fence_after();
-    const int nch = (j == qi) ? warp + 1 : 4;
-    for (int ch = 0; ch < 4; ++ch) {
-      if (ch < nch) {
-        uint32_t v[32], w[32];
-        tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
-        tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(ch * 32), w);
-        tmem_ld_wait();
+    // dS (bf16, two keys per 32-bit column) is written back IN PLACE over S: this thread owns chunk `part` (fp32 columns
+    // [32 part, +32) -> packed columns [16 part, +16)); all four parts read before anyone writes (barrier in between)
+    const int ch = part;
+    const bool live = (j < qi) || ch <= quad;              // diagonal tile: chunks beyond the warp's last row are masked
+    uint32_t v[32], w[32];
+    if (live) {
+      tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
+      tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(ch * 32), w);
+      tmem_ld_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    {
+      uint32_t dd[16];
+      if (live) {
+        const int col0_g = j * 128 + ch * 32;
+        const bool causal = (j == qi) && ch == quad;      // only the chunk on the diagonal needs the key > row test
+        const bool bias_any = row_biased && col0_g < sc.bias_c1 && col0_g + 32 > sc.bias_c0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float fd[8];
+        for (int e = 0; e < 32; e += 2) {
+          float ds[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int col_g = j * 128 + ch * 32 + q * 8 + e;
-            float t = __uint_as_float(v[q * 8 + e]) * sc.scale2;
-            const bool biased = row_biased && col_g >= sc.bias_c0 && col_g < sc.bias_c1;
+          for (int u = 0; u < 2; ++u) {
+            const int col_g = col0_g + e + u;
+            float t = fmaf(__uint_as_float(v[e + u]), sc.scale2, nlse);
+            const bool biased = bias_any && col_g >= sc.bias_c0 && col_g < sc.bias_c1;
             if (biased) t += sc.bias2;
-            const float pv = (col_g > row_g || !row_ok) ? 0.f : exp2f(t - lse2);
-            const float ds = pv * (__uint_as_float(w[q * 8 + e]) - dx);
-            if (biased) g2_part += ds;
-            fd[e] = ds * scale;
+            float pe = exp2f(t);
+            if (causal && col_g > row_g) pe = 0.f;
+            const float dse = pe * fmaf(__uint_as_float(w[e + u]), scale, -dxs);     // dS / sqrt(hd)
+            if (biased) g2_part += dse;
+            ds[u] = dse;
           }
-          *reinterpret_cast<uint4*>(sgen + A_SDS + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(fd);
+          dd[e >> 1] = pack_bf16x2(ds[0], ds[1]);
         }
       } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(sgen + A_SDS + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < 16; ++e) dd[e] = 0u;
       }
+      tmem_st_32x16(tlane + T_S + static_cast<uint32_t>(ch * 16), dd);
     }
-    fence_proxy_async();
+    tmem_st_wait();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks)
-        umma_bf16_ss(tmem + T_DQ, kdesc(A_SDS, 16384, ks), mndesc(A_SK, 16384, ks), id_q, (j > 0 || ks > 0) ? 1u : 0u);
+      for (int ks = 0; ks < 8; ++ks)                      // dQ[row][d] += sum_keys dS[row][key] K_j[key][d], A = dS from TMEM
+        umma_bf16_ts(tmem + T_DQ, tmem + T_S + static_cast<uint32_t>(ks * 8), mndesc(koff(buf), 16384, ks), id_q, (j > 0 || ks > 0) ? 1u : 0u);
       if (j == qi) {
         umma_bf16_ss(tmem + T_DQ, desc_nosw(sbase + A_SDSA, 128, 256), desc_mn_sw128(sbase + A_SKA, 2048), id_q, 1u);
 #pragma unroll
@@ -442,21 +480,27 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       umma_commit(bar_m2);
     }
     __syncwarp();
-    ph_kv ^= 1u; ph_m1 ^= 1u; ph_m2 ^= 1u;
+    ph_kv[buf] ^= 1u; ph_m1 ^= 1u; ph_m2 ^= 1u;
   }
+  g2_part *= 1.f / scale;                                 // the partial sums were taken on dS / sqrt(hd)
   g1_part = warp_sum(g1_part);
   g2_part = warp_sum(g2_part);
-  if (lane == 0) { sred[warp] = g1_part; sred[4 + warp] = g2_part; }
+  if (lane == 0) { sred[warp] = g1_part; sred[16 + warp] = g2_part; }
   __syncthreads();
   if (tid == 0) {
     float* wsg = p.ws_gate + ((static_cast<long>(n) * p.H + h) * p.qblocks + qi) * 2;
-    wsg[0] = (sred[0] + sred[1]) + (sred[2] + sred[3]);
-    wsg[1] = (sred[4] + sred[5]) + (sred[6] + sred[7]);
-  }
-  mbar_wait(bar_m2, ph_m2 ^ 1u);                         // last completion
-  tc_fence_after();
+    float a1 = 0.f, a2 = 0.f;
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
+    for (int w2 = 0; w2 < 16; ++w2) { a1 += sred[w2]; a2 += sred[16 + w2]; }     // fixed order
+    wsg[0] = a1;
+    wsg[1] = a2;
+  }
+  mbar_wait(bar_m2, ph_m2 ^ 1u);                         // last completion: every buffer is free
+  tc_fence_after();
+  stage_rope_table(sgen + A_SV, p.cosT, p.sinT, row0, S, tid, LQ_THREADS);
+  __syncthreads();
+  {
+    const int ch = part;
     uint32_t v[32];
     tmem_ld_32x32(tlane + T_DQ + static_cast<uint32_t>(ch * 32), v);
     tmem_ld_wait();
@@ -465,8 +509,8 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       float f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
-      inv_rope8(f, sgen + A_ROPE, tid, ch * 4 + q);
-      *reinterpret_cast<uint4*>(sgen + A_SK + (ch >> 1) * 16384 + sw128_off(tid, (ch & 1) * 4 + q)) = pack8(f);
+      inv_rope8(f, sgen + A_SV, r, ch * 4 + q);
+      *reinterpret_cast<uint4*>(sgen + A_SK + (ch >> 1) * 16384 + sw128_off(r, (ch & 1) * 4 + q)) = pack8(f);
     }
   }
   fence_proxy_async();
@@ -476,15 +520,15 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     tma_store_3d(&tm_dqkv, sbase + A_SK + 16384, c + 64, row0, n);
     tma_store_commit();
   }
-  {
+  if (part == 0) {
     uint32_t v[32];
     tmem_ld_32x32(tlane + T_DKA, v);                     // [416,432) dKa^T, [432,448) dVa^T; thread = head-dim index
     tmem_ld_wait();
     float* wsa = p.ws_akv + ((static_cast<long>(n) * p.qblocks + qi) * p.H + h) * 2 * AT_AP * 128;
 #pragma unroll
     for (int a = 0; a < AT_AP; ++a) {
-      wsa[a * 128 + tid] = __uint_as_float(v[a]);
-      wsa[AT_AP * 128 + a * 128 + tid] = __uint_as_float(v[16 + a]);
+      wsa[a * 128 + r] = __uint_as_float(v[a]);
+      wsa[AT_AP * 128 + a * 128 + r] = __uint_as_float(v[16 + a]);
     }
   }
   if (tid == 0) tma_store_wait_read();
@@ -743,7 +787,7 @@ int attn_bwd_tcl(const AttnParams& p, cudaStream_t stream) {
   rc = get_tmap_seq(p.dqkv, p.n_seq, p.S, 3 * D, 3 * D, 128, &tg);
   if (rc) return rc;
   const dim3 grid(p.qblocks, p.H, p.n_seq);
-  attn_bwd_tcl_dq_kernel<<<grid, TC_THREADS, A_SMEM, stream>>>(tq, ta, td, to, tg, p);
+  attn_bwd_tcl_dq_kernel<<<grid, LQ_THREADS, A_SMEM, stream>>>(tq, ta, td, to, tg, p);
   rc = check_launch("attn_bwd_tcl_dq");
   if (rc) return rc;
   attn_bwd_tcl_dkv_kernel<<<grid, LB_THREADS, K_SMEM, stream>>>(tq, td, tg, p);
