@@ -242,19 +242,25 @@ constexpr int B_SPA = 172032;          // tanh(g1) P_a, no swizzle (4 KB)
 constexpr int B_SDSA = 176128;         // dS_a, no swizzle (4 KB)
 constexpr int B_ROPE = 180224;         // [128 rows][16 chunks ^ (row & 7)][4 x half2(cos, sin)]  (32 KB)
 constexpr int B_BAR = 212992;
-constexpr int B_RED = B_BAR + 64;      // 8 floats
-constexpr int B_SMEM = B_BAR + 128 + 1024;
+constexpr int B_RED = B_BAR + 64;      // 32 floats
+constexpr int B_ROW = B_BAR + 256;     // [4][128] floats
+constexpr int B_SMEM = B_ROW + 2048 + 1024;
+constexpr int BW_THREADS = 512;
 }  // namespace
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// 512 threads: warps w, w+4, w+8, w+12 share TMEM lane quadrant w & 3 (rows 32 (w & 3) ..); thread = (row r, part):
+// part owns the 32-column chunk `part` of every 128-column matrix. With one warp per scheduler the row-wise math
+// was pure exposed latency (ncu: 36 K cycles per CTA).
+__global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
                    const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_dqkv, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar_a = sbase + B_BAR, bar_b = bar_a + 8, bar_m1 = bar_a + 16, bar_m2 = bar_a + 24, holder = bar_a + 32;
-  float* sred = reinterpret_cast<float*>(sgen + B_RED);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* sred = reinterpret_cast<float*>(sgen + B_RED);           // 32 floats: per-warp gate partials
+  float* s_row = reinterpret_cast<float*>(sgen + B_ROW);          // [4][128] per-row partial sums of D
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = tid & 127, part = tid >> 7, quad = warp & 3;
   const int h = blockIdx.x, n = blockIdx.y;
   const int S = p.S, D = p.H * 128;
 
@@ -303,20 +309,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   __syncwarp();
   // RoPE table of this sequence's positions -> smem as fp16 (cos, sin) pairs (coalesced; overlaps the TMA loads)
-  {
-    const int n4 = S * 16;                               // float4 groups (4 pairs each)
-    for (int idx = tid; idx < n4; idx += TC_THREADS) {
-      const float4 cc = __ldg(reinterpret_cast<const float4*>(p.cosT) + idx);
-      const float4 ss = __ldg(reinterpret_cast<const float4*>(p.sinT) + idx);
-      const int rr = idx >> 4, ch = idx & 15;
-      __half2 h0 = __floats2half2_rn(cc.x, ss.x), h1 = __floats2half2_rn(cc.y, ss.y);
-      __half2 h2 = __floats2half2_rn(cc.z, ss.z), h3 = __floats2half2_rn(cc.w, ss.w);
-      uint4 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-      *reinterpret_cast<uint4*>(sgen + B_ROPE + rr * 256 + ((ch ^ (rr & 7)) << 4)) = u;
-    }
-  }
+  stage_rope_table(sgen + B_ROPE, p.cosT, p.sinT, 0, S, tid, BW_THREADS);
   if (tid == 0) {
     constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0);
     mbar_wait(bar_a, 0);
@@ -337,24 +330,23 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
   __syncwarp();
 
-  const int r = tid;
   const bool row_ok = r < S;
-  const float lse2 = row_ok ? p.lse[(static_cast<long>(n) * p.H + h) * S + r] * TC_LOG2E : 0.f;
+  const float nlse = row_ok ? -p.lse[(static_cast<long>(n) * p.H + h) * S + r] * TC_LOG2E : -1e30f;   // rows past S: P = 0
   const float scale = rsqrtf(128.f);
   const float scale2 = scale * TC_LOG2E;
   const int vs = p.vstart[n];
   const float bias2 = (vs >= 0) ? p.gate2[h] * TC_LOG2E : 0.f;
   const bool row_biased = (vs >= 0) && (r >= vs + p.F);
   const int bias_c0 = vs, bias_c1 = vs + p.F;
-  const float tg = tanhf(p.gate1[h]);
-  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
 
   mbar_wait(bar_m1, 0);
   tc_fence_after();
 
   float g1_part = 0.f, g2_part = 0.f;
-  // ---------------- adapter branch ----------------
-  {
+  // ---------------- adapter branch (one thread per row) ----------------
+  if (part == 0) {
+    const float tg = tanhf(p.gate1[h]);
     uint32_t v[32], w[32];
     tmem_ld_32x16(tlane + T_SA, v);
     tmem_ld_32x16(tlane + T_DPA, w);
@@ -391,65 +383,63 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       *reinterpret_cast<uint4*>(sgen + B_SDSA + off) = pack8(fd);
     }
   }
-  // ---------------- text keys, pass 1: P (bf16, registers + smem) and D = sum_k P dP ----------------
-  uint4 pk[4][4];
-  float dx = 0.f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c <= warp) {                                   // warp-uniform causal skip
-      uint32_t v[32], w[32];
-      tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(c * 32), v);
-      tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(c * 32), w);
+  // ---------------- text keys: this thread's 32-key chunk. P -> smem (over V), D partial -> smem ----------------
+  const int ch = part;
+  const bool live = ch <= quad;                        // warp-uniform causal skip: chunks beyond the warp's last row are masked
+  float pf[32];
+  uint32_t w[32];                                      // dP chunk, kept for pass 2
+  {
+    float dpart = 0.f;
+    if (live) {
+      uint32_t v[32];
+      tmem_ld_32x32(tlane + T_S + static_cast<uint32_t>(ch * 32), v);
+      tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(ch * 32), w);
       tmem_ld_wait();
+      const bool causal = ch == quad;
+      const bool bias_any = row_biased && ch * 32 < bias_c1 && ch * 32 + 32 > bias_c0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float fp[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = q * 8 + e;
-          const int col = c * 32 + j;
-          float x = __uint_as_float(v[j]) * scale2;
-          if (row_biased && col >= bias_c0 && col < bias_c1) x += bias2;
-          const float pv = (col > r || !row_ok) ? 0.f : exp2f(x - lse2);
-          dx += pv * __uint_as_float(w[j]);
-          fp[e] = pv;
-        }
-        pk[c][q] = pack8(fp);
+      for (int e = 0; e < 32; ++e) {
+        const int col = ch * 32 + e;
+        float t = fmaf(__uint_as_float(v[e]), scale2, nlse);
+        if (bias_any && col >= bias_c0 && col < bias_c1) t += bias2;
+        float pe = exp2f(t);
+        if (causal && col > r) pe = 0.f;
+        pf[e] = pe;
+        dpart += pe * __uint_as_float(w[e]);
       }
     } else {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) pk[c][q] = make_uint4(0, 0, 0, 0);
+      for (int e = 0; e < 32; ++e) pf[e] = 0.f;
     }
+    s_row[part * 128 + r] = dpart;
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      *reinterpret_cast<uint4*>(sgen + B_SV + (c >> 1) * 16384 + sw128_off(r, (c & 1) * 4 + q)) = pk[c][q];
+    for (int q = 0; q < 4; ++q) {
+      float f8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f8[e] = pf[q * 8 + e];
+      *reinterpret_cast<uint4*>(sgen + B_SV + (ch >> 1) * 16384 + sw128_off(r, (ch & 1) * 4 + q)) = pack8(f8);
+    }
   }
-  // ---------------- pass 2: dS = P (dP - D) / sqrt(hd) ----------------
+  __syncthreads();
+  // ---------------- pass 2: dS = P (dP - D) / sqrt(hd), D = sum_k P dP (= <dO, O> minus the adapter part) ----------------
+  {
+    const float dxs = ((s_row[r] + s_row[128 + r]) + (s_row[256 + r] + s_row[384 + r])) * scale;
+    const bool bias_any = row_biased && ch * 32 < bias_c1 && ch * 32 + 32 > bias_c0;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c <= warp) {
-      uint32_t w[32];
-      tmem_ld_32x32(tlane + T_DP + static_cast<uint32_t>(c * 32), w);
-      tmem_ld_wait();
+    for (int q = 0; q < 4; ++q) {
+      float fd[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float fp[8], fd[8];
-        unpack8(pk[c][q], fp);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = q * 8 + e;
-          const int col = c * 32 + j;
-          const float ds = fp[e] * (__uint_as_float(w[j]) - dx);
-          if (row_biased && col >= bias_c0 && col < bias_c1) g2_part += ds;
-          fd[e] = ds * scale;
-        }
-        *reinterpret_cast<uint4*>(sgen + B_SDS + (c >> 1) * 16384 + sw128_off(r, (c & 1) * 4 + q)) = pack8(fd);
+      for (int e = 0; e < 8; ++e) {
+        const int j = q * 8 + e;
+        // P as the UMMA sees it (bf16), like the unfused formulation
+        const float pb = __bfloat162float(__float2bfloat16_rn(pf[j]));
+        const float ds = live ? pb * fmaf(__uint_as_float(w[j]), scale, -dxs) : 0.f;
+        if (bias_any && ch * 32 + j >= bias_c0 && ch * 32 + j < bias_c1) g2_part += ds;
+        fd[e] = ds;
       }
-    } else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(sgen + B_SDS + (c >> 1) * 16384 + sw128_off(r, (c & 1) * 4 + q)) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sgen + B_SDS + (ch >> 1) * 16384 + sw128_off(r, (ch & 1) * 4 + q)) = pack8(fd);
     }
+    g2_part *= 1.f / scale;                            // partial sums were taken on dS / sqrt(hd)
   }
   fence_proxy_async();
   tc_fence_before();
@@ -480,12 +470,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // gate partial sums of this (sequence, head) in a fixed order while the MMAs run
   g1_part = warp_sum(g1_part);
   g2_part = warp_sum(g2_part);
-  if (lane == 0) { sred[warp] = g1_part; sred[4 + warp] = g2_part; }
+  if (lane == 0) { sred[warp] = g1_part; sred[16 + warp] = g2_part; }
   __syncthreads();
   if (tid == 0) {
     float* wsg = p.ws_gate + (static_cast<long>(n) * p.H + h) * 2;
-    wsg[0] = (sred[0] + sred[1]) + (sred[2] + sred[3]);
-    wsg[1] = (sred[4] + sred[5]) + (sred[6] + sred[7]);
+    float a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 16; ++w2) { a1 += sred[w2]; a2 += sred[16 + w2]; }
+    wsg[0] = a1;
+    wsg[1] = a2;
   }
 
   mbar_wait(bar_m2, 0);
@@ -495,28 +488,17 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   for (int which = 0; which < 3; ++which) {            // 0: dQ (row = query), 1: dK (row = key), 2: dV
     const uint32_t tcol = which == 0 ? T_DQ : (which == 1 ? T_DK : T_DV);
     const int sdst = which == 0 ? B_SQ : (which == 1 ? B_SK : B_SV);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld_32x32(tlane + tcol + static_cast<uint32_t>(c * 32), v);
+      tmem_ld_32x32(tlane + tcol + static_cast<uint32_t>(ch * 32), v);
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float f[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]);
-        if (which < 2) {                                // rotate pair (2i, 2i+1) by -angle(pos = r, i)
-          const uint4 t = *reinterpret_cast<const uint4*>(sgen + B_ROPE + r * 256 + (((c * 4 + q) ^ (r & 7)) << 4));
-          const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&tw[e]));
-            const float a = f[2 * e], b = f[2 * e + 1];
-            f[2 * e] = a * cs.x + b * cs.y;
-            f[2 * e + 1] = -a * cs.y + b * cs.x;
-          }
-        }
-        *reinterpret_cast<uint4*>(sgen + sdst + (c >> 1) * 16384 + sw128_off(r, (c & 1) * 4 + q)) = pack8(f);
+        if (which < 2) inv_rope8(f, sgen + B_ROPE, r, ch * 4 + q);      // rotate pair (2i, 2i+1) by -angle(pos = r, i)
+        *reinterpret_cast<uint4*>(sgen + sdst + (ch >> 1) * 16384 + sw128_off(r, (ch & 1) * 4 + q)) = pack8(f);
       }
     }
     fence_proxy_async();
@@ -527,7 +509,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       tma_store_commit();
     }
   }
-  {
+  if (part == 0) {
     // adapter partials: thread = head-dim index d; columns [128,144) dKa^T, [144,160) dVa^T
     uint32_t v[32];
     tmem_ld_32x32(tlane + T_DKA, v);
@@ -591,7 +573,7 @@ int attn_bwd_tc(const AttnParams& p, cudaStream_t stream) {
   if (rc) return rc;
   rc = get_tmap_seq(p.dqkv, p.n_seq, p.S, 3 * D, 3 * D, 128, &tg);
   if (rc) return rc;
-  attn_bwd_tc_kernel<<<dim3(p.H, p.n_seq), TC_THREADS, B_SMEM, stream>>>(tq, ta, td, tg, p);
+  attn_bwd_tc_kernel<<<dim3(p.H, p.n_seq), BW_THREADS, B_SMEM, stream>>>(tq, ta, td, tg, p);
   return check_launch("attn_bwd_tc");
 }
 
