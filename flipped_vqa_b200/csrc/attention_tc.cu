@@ -26,18 +26,21 @@ constexpr int F_SKA = 98304;          // [2][16][64]
 constexpr int F_SVA = 102400;         // [2][16][64]
 constexpr int F_SPA = 106496;         // P_a: [16 row groups][2 k-chunks][8 rows][8] bf16, no swizzle (4 KB)
 constexpr int F_BAR = 110592;
-constexpr int F_SMEM = F_BAR + 64 + 1024;
+constexpr int F_ROW = F_BAR + 64;     // [4][128] floats: partial row max / sum
+constexpr int F_SMEM = F_ROW + 2048 + 1024;
+constexpr int FW_THREADS = 256;
 
 }  // namespace
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// 256 threads: warps w and w + 4 share TMEM lane quadrant w & 3 (rows) and split the 128 key columns in halves.
+__global__ void __launch_bounds__(FW_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
                    const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bar_qk = sbase + F_BAR, bar_v = bar_qk + 8, bar_s = bar_qk + 16, bar_o = bar_qk + 24, holder = bar_qk + 32;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, r = tid & 127, part = tid >> 7, quad = warp & 3;
   const int h = blockIdx.x, n = blockIdx.y;
   const int S = p.S, D = p.H * 128;
 
@@ -92,19 +95,21 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   mbar_wait(bar_s, 0);
   tc_fence_after();
 
-  // ---------------- softmax: thread = query row ----------------
-  const int r = tid;
-  const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+  // ---------------- softmax: thread = (query row r, column half `part`) ----------------
+  const uint32_t tlane = tmem + (static_cast<uint32_t>(quad * 32) << 16);
   const float scale2 = rsqrtf(128.f) * TC_LOG2E;
   const int vs = p.vstart[n];
   const float bias2 = (vs >= 0) ? p.gate2[h] * TC_LOG2E : 0.f;
   const bool row_biased = (vs >= 0) && (r >= vs + p.F);
   const int bias_c0 = vs, bias_c1 = vs + p.F;
-  float s[128];
+  float* s_max = reinterpret_cast<float*>(sgen + F_ROW);          // [2][128] partial row max | [2][128] partial row sum
+  float* s_sum = s_max + 256;
+  float s[64];
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c <= warp) {                                   // warp-uniform: chunks beyond the warp's last row are fully masked
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = 2 * part + cc;
+    if (c <= quad) {                                   // warp-uniform: chunks beyond the warp's last row are fully masked
       uint32_t v[32];
       tmem_ld_32x32(tlane + static_cast<uint32_t>(c * 32), v);
       tmem_ld_wait();
@@ -114,41 +119,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         float x = __uint_as_float(v[j]) * scale2;
         if (row_biased && col >= bias_c0 && col < bias_c1) x += bias2;
         if (col > r) x = -INFINITY;
-        s[col] = x;
+        s[cc * 32 + j] = x;
         mx = fmaxf(mx, x);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) s[c * 32 + j] = -INFINITY;
+      for (int j = 0; j < 32; ++j) s[cc * 32 + j] = -INFINITY;
     }
   }
-  float l = 0.f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    if (c <= warp) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float e = exp2f(s[c * 32 + j] - mx);
-        s[c * 32 + j] = e;
-        l += e;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) s[c * 32 + j] = 0.f;
-    }
-  }
-  const float inv = 1.f / l;
-  // P (normalised, bf16, two keys per 32-bit column) -> TMEM columns [0,64) over the consumed S: the A operand of P.V
-  // never touches shared memory
-#pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t pk[32];
-#pragma unroll
-    for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(s[half * 64 + 2 * e] * inv, s[half * 64 + 2 * e + 1] * inv);
-    tmem_st_32x32(tlane + static_cast<uint32_t>(half * 32), pk);
-  }
-  // adapter branch: separate softmax over the A adapter keys, scaled by tanh(gate1)
-  {
+  s_max[part * 128 + r] = mx;
+  // adapter branch (part 1 threads; part 0 always has live text chunks): separate softmax x tanh(gate1)
+  uint32_t pa[8];
+  if (part == 1) {
     uint32_t v[32];
     tmem_ld_32x16(tlane + 128u, v);
     tmem_ld_wait();
@@ -165,13 +147,34 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       la += sa[j];
     }
     const float ia = tg / la;
-    uint32_t pa[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) pa[e] = pack_bf16x2(sa[2 * e] * ia, sa[2 * e + 1] * ia);
-    tmem_st_32x8(tlane + 64u, pa);                 // P_a -> TMEM columns [64,72)
   }
+  tc_fence_before();
+  __syncthreads();                                     // every S / S_a value is in registers; partial maxima published
+  tc_fence_after();
+  mx = fmaxf(s_max[r], s_max[128 + r]);
+  float l = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) {
+    const float e = exp2f(s[j] - mx);                  // masked entries: exp2(-inf) = 0
+    s[j] = e;
+    l += e;
+  }
+  s_sum[part * 128 + r] = l;
+  __syncthreads();
+  l = s_sum[r] + s_sum[128 + r];
+  const float inv = 1.f / l;
+  // P (normalised, bf16, two keys per 32-bit column) -> TMEM columns [32 part, 32 part + 32) over the consumed S
+  {
+    uint32_t pk[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(s[2 * e] * inv, s[2 * e + 1] * inv);
+    tmem_st_32x32(tlane + static_cast<uint32_t>(part * 32), pk);
+  }
+  if (part == 1) tmem_st_32x8(tlane + 64u, pa);        // P_a -> TMEM columns [64,72)
   tmem_st_wait();
-  if (r < S) p.lse[(static_cast<long>(n) * p.H + h) * S + r] = (mx + log2f(l)) * TC_LN2;
+  if (part == 0 && r < S) p.lse[(static_cast<long>(n) * p.H + h) * S + r] = (mx + log2f(l)) * TC_LN2;
   tc_fence_before();
   __syncthreads();
 
@@ -191,7 +194,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   tc_fence_after();
   // O -> bf16 -> swizzled staging (Q's buffer: every MMA that read it has retired) -> TMA store
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 2 * part; c < 2 * part + 2; ++c) {
     uint32_t v[32];
     tmem_ld_32x32(tlane + 128u + static_cast<uint32_t>(c * 32), v);
     tmem_ld_wait();
@@ -558,7 +561,7 @@ int attn_fwd_tc(const AttnParams& p, cudaStream_t stream) {
   const int D = p.H * 128;
   rc = get_tmap_seq(p.out, p.n_seq, p.S, D, D, 128, &to);
   if (rc) return rc;
-  attn_fwd_tc_kernel<<<dim3(p.H, p.n_seq), TC_THREADS, F_SMEM, stream>>>(tq, ta, to, p);
+  attn_fwd_tc_kernel<<<dim3(p.H, p.n_seq), FW_THREADS, F_SMEM, stream>>>(tq, ta, to, p);
   return check_launch("attn_fwd_tc");
 }
 
