@@ -47,6 +47,7 @@ struct GemmEpi {
   // SwiGLU-fused epilogues of the CTA-pair kernel (EPI_SWIGLU_FWD / EPI_SWIGLU_BWD)
   void* aux;          // FWD: c = silu(a) * b output [M, hid];  BWD: g = [a | b] input [M, 2*hid]
   int ld_aux, hid;
+  const int32_t* pos_ids;  // ROPE only: position of each row (ragged / compacted token layouts); nullptr -> row % S
 };
 
 enum { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_SWIGLU_FWD = 2, EPI_SWIGLU_BWD = 3 };
@@ -75,7 +76,7 @@ __device__ __forceinline__ void epilogue_store(uint32_t (&v)[32], void* __restri
     bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
     const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
     if constexpr (ROPE) {
-      const int pos = row % epi.S;
+      const int pos = epi.pos_ids != nullptr ? __ldg(epi.pos_ids + row) : row % epi.S;
 #pragma unroll
       for (int q = 0; q < NC / 8; ++q) {
         const int col = col0 + 8 * q;                 // 8-column groups never straddle a head (hd % 8 == 0)
@@ -737,9 +738,9 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
                   : launch_gemm<256, false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
 }
 
-extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N,
-                                      int K, const float* rope_cos, const float* rope_sin, int rope_cols, int hd, int S,
-                                      void* stream) {
+static int gemm_rope_impl(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N, int K,
+                          const float* rope_cos, const float* rope_sin, int rope_cols, int hd, int S, const int32_t* pos_ids,
+                          void* stream) {
   int rc = check_gemm_args(A, lda, B, ldb, C, ldc, nullptr, 0, M, N, K);
   if (rc) return rc;
   FVQA_REQUIRE((hd == 64 || hd == 128) && rope_cols % hd == 0 && rope_cols <= N && S > 0 && rope_cos && rope_sin,
@@ -747,10 +748,24 @@ extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bf16* a = reinterpret_cast<const bf16*>(A);
   const bf16* b = reinterpret_cast<const bf16*>(B);
-  GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S, nullptr, 0, 0};
+  GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S, nullptr, 0, 0, pos_ids};
   if (use_pair(M, N)) return launch_gemm_pair<false, EPI_ROPE>(a, lda, b, ldb, C, ldc, epi, M, N, K, pair_bn(M, N), s);
   if (prefer_bn128(M, N)) return launch_gemm<128, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   return launch_gemm<256, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
+}
+
+extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N,
+                                      int K, const float* rope_cos, const float* rope_sin, int rope_cols, int hd, int S,
+                                      void* stream) {
+  return gemm_rope_impl(A, lda, B, ldb, C, ldc, M, N, K, rope_cos, rope_sin, rope_cols, hd, S, nullptr, stream);
+}
+
+/* Ragged / compacted token layouts (shared-prefix option scoring): row r is rotated by the angle of position pos_ids[r]. */
+extern "C" int fvqa_gemm_bf16_nt_rope_pos(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M,
+                                          int N, int K, const float* rope_cos, const float* rope_sin, int rope_cols, int hd,
+                                          const int32_t* pos_ids, void* stream) {
+  FVQA_REQUIRE(pos_ids != nullptr, FVQA_ERR_INVALID_ARG, "gemm_rope_pos: pos_ids is NULL");
+  return gemm_rope_impl(A, lda, B, ldb, C, ldc, M, N, K, rope_cos, rope_sin, rope_cols, hd, 1, pos_ids, stream);
 }
 
 /* Test / tuning hook: force the CTA-pair tile width (multiple of 16 in [64,256]); 0 restores the

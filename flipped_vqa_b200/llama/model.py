@@ -22,7 +22,7 @@ from typing import List, Optional
 import torch
 from torch import nn
 
-from ..step import BatchPlan, GradBuffers, LayerWeights, PinnedPool, StepEngine
+from ..step import BatchPlan, GradBuffers, LayerWeights, OptionPlan, PinnedPool, StepEngine
 from ..synthetic import ffn_hidden_dim
 from .tokenizer import Tokenizer
 
@@ -200,6 +200,7 @@ class Transformer(nn.Module):
         self._pack_token = None
         self.last_plan: Optional[BatchPlan] = None
         self._pinned: Optional[PinnedPool] = None
+        self.share_option_prefix = True                     # validation: shared-prefix option scoring (step.OptionPlan)
 
     # ------------------------------------------------------------------ weight layout
     def run_layers(self):
@@ -309,14 +310,22 @@ class Transformer(nn.Module):
     @torch.no_grad()
     def inference(self, data):
         """Loss-based option scoring: VQA stream only over bsz*n_options sequences
-        (`model_my_original_mod.py:281,332-333,348-360,375-377,506`)."""
+        (`model_my_original_mod.py:281,332-333,348-360,375-377,506`). With `share_option_prefix` (default) the
+        option-invariant prefix of each sample is evaluated once (`step.OptionPlan`); the per-token losses are the same."""
         self._ensure_packed()
-        dev = self._device
-        plan = self.plan_batch(data, inference=True)
-        self.last_plan = plan
         trainables, n_run = self.trainable_parameters()
         g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]
         g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
+        if self.share_option_prefix:
+            if self._pinned is None:
+                self._pinned = PinnedPool()
+            plan = OptionPlan(data, self.max_feats, pool=self._pinned).to_device(self._device)
+            self.last_plan = plan
+            return self._engine.forward_options(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
+                                                self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
+                                                g1, g2)
+        plan = self.plan_batch(data, inference=True)
+        self.last_plan = plan
         tok, _ = self._engine.forward(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
                                       self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
                                       g1, g2, save=False, token_losses=True)

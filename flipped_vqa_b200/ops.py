@@ -183,8 +183,10 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
 
 
 @_timed
-def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd: int, S: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """QKV projection with RoPE applied to the q|k columns in the GEMM epilogue (bf16 out)."""
+def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd: int, S: int, out: Optional[torch.Tensor] = None,
+                 pos_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """QKV projection with RoPE applied to the q|k columns in the GEMM epilogue (bf16 out). Position of row r is
+    r % S, or pos_ids[r] (int32) for ragged / compacted token layouts."""
     assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
     M, K = a.shape
     N = b.shape[0]
@@ -193,8 +195,14 @@ def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd:
     if tm is not None and tm.active:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(_lib.lib().fvqa_gemm_bf16_nt_rope(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
-                                            ptr(cos), ptr(sin), rope_cols, hd, S, stream()), "gemm_bf16_nt_rope")
+    if pos_ids is not None:
+        _chk(pos_ids, torch.int32, "pos_ids")
+        assert pos_ids.numel() >= M
+        check(_lib.lib().fvqa_gemm_bf16_nt_rope_pos(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
+                                                    ptr(cos), ptr(sin), rope_cols, hd, ptr(pos_ids), stream()), "gemm_bf16_nt_rope_pos")
+    else:
+        check(_lib.lib().fvqa_gemm_bf16_nt_rope(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
+                                                ptr(cos), ptr(sin), rope_cols, hd, S, stream()), "gemm_bf16_nt_rope")
     if tm is not None and tm.active:
         e1.record()
         tm.records.append((e0, e1, 2.0 * M * N * K))

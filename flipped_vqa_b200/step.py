@@ -110,6 +110,106 @@ class BatchPlan:
         return self
 
 
+class OptionPlan:
+    """Host-side plan of loss-based option scoring (`llama/model_my_original_mod.py:332-377`, `engine.py:87-93`) that
+    evaluates the OPTION-INVARIANT PREFIX of every sample once.
+
+    The n_opt sequences of a sample are identical up to the answer span, and under the causal mask the hidden state of
+    a position depends only on the tokens at and before it, so rows [0, P_b) of all options of sample b are the same
+    numbers; rows after the last labelled position E_b of a sample feed no loss at all. The layer GEMMs, norms and the
+    FFN therefore run on a COMPACT, ragged row set
+
+        [ prefix rows of sample 0 | ... | prefix rows of sample B-1 | suffix rows (b, o, P_b <= pos < E_b) ... ]
+
+    (T_c = sum_b P_b + n_opt * sum_b (E_b - P_b) instead of B * n_opt * S rows); only attention sees the full
+    [B * n_opt, S] layout, rebuilt per layer by a row gather of q|k|v. Results equal the dense evaluation's.
+      pos_ids[T_c]      position of each compact row (RoPE angle)
+      c2f[T_c]          full row (sequence * S + pos) that compact row r stands for (option 0 for prefix rows)
+      f2c[n_seq * S]    compact row holding full row's values, -1 for rows past E_b (never read: causal)
+    """
+
+    def __init__(self, data: Dict, max_feats: int, pool: "PinnedPool" = None):
+        ids = _cpu(data["text_id"]["vqa"]).long()
+        lab = _cpu(data["label"]["vqa"]).long()
+        B, n_opt, S = ids.shape
+        F = max_feats
+        self.B, self.n_opt, self.S, self.F = B, n_opt, S, F
+        self.streams = ["vqa"]
+        self.n_seq = B * n_opt
+        self.T = self.n_seq * S
+        self.n_video = B
+        neq = (ids != ids[:, :1]).any(1)                                     # [B, S] some option differs here
+        cp = torch.where(neq.any(1), neq.int().argmax(1), torch.full((B,), S))  # common-prefix length per sample
+        labelled = lab[:, :, 1:] != 0                                         # row t predicts token t+1 (`model.py:350`)
+        any_row = labelled.any(1)                                             # [B, S-1]
+        last = (S - 2) - any_row.flip(1).int().argmax(1)
+        E = torch.where(any_row.any(1), last + 1, torch.zeros(B, dtype=torch.long))   # rows needed: [0, E_b)
+        P = torch.minimum(cp, E)
+        self.prefix_len, self.end = P, E
+        pos = torch.arange(S).view(1, 1, S).expand(B, n_opt, S)
+        opt = torch.arange(n_opt).view(1, n_opt, 1).expand(B, n_opt, S)
+        Pb, Eb = P.view(B, 1, 1), E.view(B, 1, 1)
+        m_pre = ((opt == 0) & (pos < Pb)).reshape(-1)
+        m_suf = ((pos >= Pb) & (pos < Eb)).reshape(-1)
+        c2f = torch.cat([m_pre.nonzero().flatten(), m_suf.nonzero().flatten()])
+        self.n_prefix_rows = int(m_pre.sum())
+        self.T_c = int(c2f.numel())
+        pre_off = torch.cumsum(P, 0) - P                                      # first compact row of each sample's prefix
+        f2c = torch.full((self.T,), -1, dtype=torch.long)
+        in_pre = (pos < Pb).reshape(-1)
+        f2c[in_pre] = (pre_off.view(B, 1, 1) + pos).reshape(-1)[in_pre]
+        f2c[m_suf] = self.n_prefix_rows + torch.arange(int(m_suf.sum()))
+        pos_ids = pos.reshape(-1)[c2f]
+        nz = labelled.reshape(self.n_seq, S - 1).nonzero()
+        ce_full = nz[:, 0] * S + nz[:, 1]
+        ce_rows = f2c[ce_full]
+        assert bool((ce_rows >= 0).all())
+        ce_tgt = lab.reshape(self.n_seq, S)[:, 1:][nz[:, 0], nz[:, 1]]
+        ce_dst = nz[:, 0] * (S - 1) + nz[:, 1]
+        self.ce_total = int(nz.shape[0])
+        self.ce_counts = {"vqa": self.ce_total}
+        live = torch.unique(ce_rows, sorted=True)                             # last layer: wo / FFN on these only
+        self.n_live = int(live.numel())
+        ce_rows_c = torch.searchsorted(live, ce_rows)
+        vs = int(data["video_start"]["vqa"][0])                               # sample 0's, `model_my_original_mod.py:264`
+        vstart = torch.full((self.n_seq,), vs, dtype=I32)
+        seq_video = (torch.arange(self.n_seq) // n_opt).to(I32)
+        parts = [ids.reshape(-1), torch.zeros(self.T, dtype=I32), vstart, seq_video, torch.zeros(B * F, dtype=I32),
+                 pos_ids, c2f, f2c, ce_rows, ce_tgt, ce_dst, live, ce_rows_c]
+        self._names = ["ids", "labels", "vstart", "seq_video", "qav_index", "pos_ids", "c2f", "f2c", "ce_rows", "ce_tgt", "ce_dst",
+                       "live_rows", "ce_rows_c"]
+        sizes = [p.numel() for p in parts]
+        total = max(sum(sizes), 1)
+        video = _cpu(data["video"]).reshape(B * F, -1).float()
+        slot = pool.acquire(total, video.numel()) if pool is not None else None
+        if slot is not None:
+            host, hvideo = slot.ints[:total], slot.video[:video.numel()].view(video.shape)
+        else:
+            host, hvideo = torch.empty(total, dtype=I32), torch.empty(video.shape, dtype=torch.float32)
+        off = 0
+        self._slices = []
+        for p, n in zip(parts, sizes):
+            host[off:off + n] = p
+            self._slices.append((off, n))
+            off += n
+        hvideo.copy_(video)
+        self.host_ints, self.host_video, self._slot = host, hvideo, slot
+        self.h2d_bytes = host.numel() * 4 + video.numel() * 4
+
+    def host(self, name: str) -> torch.Tensor:
+        off, n = self._slices[self._names.index(name)]
+        return self.host_ints[off:off + n]
+
+    def to_device(self, device):
+        dev = self.host_ints.to(device, non_blocking=True)
+        for nm, (off, n) in zip(self._names, self._slices):
+            setattr(self, nm, dev[off:off + n])
+        self.video = self.host_video.to(device, non_blocking=True)
+        if self._slot is not None:
+            self._slot.event.record()
+        return self
+
+
 class PinnedPool:
     """Small ring of pinned host staging buffers for the per-step H2D copy (ids/labels/row lists in
     one int32 buffer + the fp32 video features). A slot is reused only after the CUDA event recorded
@@ -298,6 +398,59 @@ class StepEngine:
                 out.fill_(float("nan"))
             losses["qav"] = out
         return losses, sv
+
+    # -------------------------------------------------------------------------------- option scoring, shared prefix
+    def forward_options(self, plan: "OptionPlan", layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
+                        gate1: List[torch.Tensor], gate2: List[torch.Tensor]):
+        """Per-token VQA losses [B, n_opt, S-1] (`model_my_original_mod.py:375-377`) with the option-invariant prefix of
+        each sample evaluated once: every row-wise op (norms, the 7 frozen GEMMs per layer, SwiGLU, residuals) runs on
+        `plan`'s compact ragged rows; attention runs on the full [B * n_opt, S] layout rebuilt by a q|k|v row gather."""
+        d, H, hd, hid, A, F, S = self.d, self.H, self.hd, self.hid, self.A, self.F, plan.S
+        n_seq, dev, Tc = plan.n_seq, self.device, plan.T_c
+        tl = torch.zeros(plan.B * plan.n_opt * (S - 1), dtype=torch.float32, device=dev)
+        if plan.ce_total == 0 or Tc == 0:
+            return tl.view(plan.B, plan.n_opt, S - 1)
+        L = len(layers)
+        vf32 = ops.visual_proj_fwd(plan.video, visual_w)
+        x_full = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w,
+                                  n_seq, S, F)
+        x = ops.gather_rows(x_full, plan.c2f)                                       # [Tc, d] fp32 residual stream, compact
+        del x_full
+        adapter_bf16 = ops.f32_to_bf16(adapter_w)
+        xn = torch.empty(Tc, d, dtype=BF16, device=dev)
+        qkv_c = torch.empty(Tc, 3 * d, dtype=BF16, device=dev)
+        qkv_f = torch.zeros(plan.T, 3 * d, dtype=BF16, device=dev)                 # rows past E_b stay zero (finite V rows)
+        o_f = torch.empty(plan.T, d, dtype=BF16, device=dev)
+        lse = torch.empty(n_seq, H, S, dtype=torch.float32, device=dev)
+        o_c = torch.empty(Tc, d, dtype=BF16, device=dev)
+        g = torch.empty(Tc, 2 * hid, dtype=BF16, device=dev)
+        c = torch.empty(Tc, hid, dtype=BF16, device=dev)
+        prune = self.prune_last_layer and 0 < plan.n_live < Tc
+        ce_idx = plan.ce_rows_c if prune else plan.ce_rows
+        for l, w in enumerate(layers):
+            ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
+            ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_c, pos_ids=plan.pos_ids)
+            ops.gather_rows(qkv_c, plan.f2c, dst=qkv_f)                             # compact -> every option's sequence
+            akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])
+            ops.attn_fwd(qkv_f, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F, out=o_f, lse=lse)
+            if prune and l == L - 1:
+                o_g = ops.gather_rows(ops.gather_rows(o_f, plan.c2f, dst=o_c), plan.live_rows)
+                x_g = ops.gather_rows(x, plan.live_rows)
+                h = ops.gemm_nt(o_g, w.wo, residual=x_g, out_fp32=True)
+                xn_g, _ = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps)
+                _, c_g = ops.gemm_swiglu_fwd(xn_g, w.w13)
+                x = ops.gemm_nt(c_g, w.w2, residual=h, out_fp32=True)
+            else:
+                ops.gather_rows(o_f, plan.c2f, dst=o_c)
+                h = ops.gemm_nt(o_c, w.wo, residual=x, out_fp32=True)
+                ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
+                ops.gemm_swiglu_fwd(xn, w.w13, g=g, c=c)
+                x = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)
+        hn, _ = ops.rmsnorm_gather_fwd(x, ce_idx, norm_w, self.eps)
+        logits = ops.gemm_nt(hn, out_w, out_fp32=True)
+        row_loss, _ = ops.ce_fwd(logits, plan.ce_tgt)
+        ops.scatter_rows(row_loss, plan.ce_dst, tl)
+        return tl.view(plan.B, plan.n_opt, S - 1)
 
     # -------------------------------------------------------------------------------- backward
     def backward(self, sv: SavedStep, gscale: torch.Tensor, layers: List[LayerWeights], out_w_t, norm_w, gate1, gate2,

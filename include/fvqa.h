@@ -72,6 +72,12 @@ int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, 
 int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc,
                            int M, int N, int K, const float* rope_cos, const float* rope_sin,
                            int rope_cols, int hd, int S, void* stream);
+/* Same, for ragged / compacted token layouts (shared-prefix option scoring, llama/model_my_original_mod.py:332-377
+ * evaluated once per option-invariant prefix): row r is rotated by the angle of position pos_ids[r] (device int32 [M],
+ * each in [0, rows of the rope tables)). */
+int fvqa_gemm_bf16_nt_rope_pos(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc,
+                               int M, int N, int K, const float* rope_cos, const float* rope_sin,
+                               int rope_cols, int hd, const int32_t* pos_ids, void* stream);
 
 /* SwiGLU fused into the GEMM epilogues (llama/model.py:142 `w2(silu(w1 x) * w3 x)` and its backward):
  *  fwd: G[M, 2*hid] = X[M,K] * W13[2*hid, K]^T (bf16, saved for backward; W13 = [W1; W3]) and

@@ -103,6 +103,49 @@ def test_batch_plan_option_layout():
     assert arr["seq_video"].tolist() == [0] * 5 + [1] * 5 + [2] * 5      # video repeated per option (model_my_original_mod.py:332-333)
 
 
+def test_option_plan_shared_prefix_layout():
+    """step.OptionPlan: the compact ragged row set of shared-prefix option scoring. Every labelled row is present, every
+    present row is backed by a compact row with the SAME token history (so its hidden state is the same number), the
+    kept rows of a sequence are causally closed, and sequences without labels / with an early divergence are handled."""
+    from flipped_vqa_b200.step import OptionPlan
+    from flipped_vqa_b200.synthetic import synthetic_batch
+    for seed, n_opt in ((0, 1), (1, 5), (3, 5)):
+        data = synthetic_batch(4, 64, 512, seed=seed, n_options=n_opt)
+        if seed == 3:
+            data["label"]["vqa"][1] = 0                 # a sample no loss reads
+            data["text_id"]["vqa"][2, 3, 5] = 7         # options diverge at position 5
+        p = OptionPlan(data, 10)
+        ids, lab = data["text_id"]["vqa"], data["label"]["vqa"]
+        B, n, S = ids.shape
+        c2f, f2c, pos = p.host("c2f").long(), p.host("f2c").long(), p.host("pos_ids").long()
+        assert p.T_c == c2f.numel() < p.T
+        assert torch.equal(c2f % S, pos)
+        assert torch.equal(f2c[c2f], torch.arange(p.T_c))
+        for b in range(B):
+            for o in range(n):
+                present = f2c[(b * n + o) * S:(b * n + o + 1) * S] >= 0
+                k = int(present.sum())
+                assert bool(present[:k].all()) and not bool(present[k:].any())          # causally closed
+                assert k == int(p.end[b])
+                for t in range(k):
+                    src = int(c2f[f2c[(b * n + o) * S + t]])
+                    sb, so, sp = src // (n * S), (src // S) % n, src % S
+                    assert sb == b and sp == t and torch.equal(ids[b, so, :t + 1], ids[b, o, :t + 1])
+                labelled = (lab[b, o, 1:] != 0).nonzero().flatten()
+                assert bool((labelled < k).all())
+        # the CE row list: targets and destinations of every labelled (sequence, position) pair
+        nz = (lab.reshape(B * n, S)[:, 1:] != 0).nonzero()
+        assert p.ce_total == nz.shape[0]
+        assert torch.equal(p.host("ce_tgt").long(), lab.reshape(B * n, S)[:, 1:][nz[:, 0], nz[:, 1]])
+        assert torch.equal(p.host("ce_dst").long(), nz[:, 0] * (S - 1) + nz[:, 1])
+        assert torch.equal(c2f[p.host("ce_rows").long()] % S, nz[:, 1])
+        assert torch.equal(p.host("live_rows").long()[p.host("ce_rows_c").long()], p.host("ce_rows").long())
+        if seed == 3:
+            assert int(p.end[1]) == 0 and int(p.prefix_len[2]) == 5
+        if n_opt == 5 and seed == 1:
+            assert p.T_c < p.T // 4                     # 5 options cost about one sequence per sample
+
+
 def test_lr_schedule_matches_reference_formula():
     from flipped_vqa_b200.util import lr_sched
     from types import SimpleNamespace

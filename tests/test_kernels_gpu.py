@@ -162,6 +162,25 @@ def test_gemm_rope_epilogue(fvqa_lib, S, H, hd, B):
     assert relerr(out, ref) < 5e-3
 
 
+def test_gemm_rope_epilogue_position_table(fvqa_lib):
+    """fvqa_gemm_bf16_nt_rope_pos: the row's position comes from an int32 table (ragged / compacted token layouts of
+    shared-prefix option scoring). Must be bit-identical to the row % S variant on the same (row, position) pairs."""
+    from flipped_vqa_b200 import ops
+    S, H, hd, B = 128, 4, 128, 3
+    d = H * hd
+    x = bf16_randn(B * S, d, seed=27)
+    w = bf16_randn(3 * d, d, std=0.05, seed=28)
+    cos, sin = O.rope_table(hd, S)
+    cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    dense = ops.gemm_nt_rope(x, w, cos, sin, 2 * d, hd, S)
+    g = torch.Generator().manual_seed(5)
+    rows = torch.randperm(B * S, generator=g)[:301].sort().values                 # a ragged subset of the rows
+    pos = (rows % S).to(torch.int32).cuda()
+    xc = x[rows.cuda()].contiguous()
+    out = ops.gemm_nt_rope(xc, w, cos, sin, 2 * d, hd, S, pos_ids=pos)
+    assert torch.equal(out, dense[rows.cuda()])
+
+
 def test_gemm_strided_views(fvqa_lib):
     """Sub-blocks of larger matrices (used for Wk|Wv of the fused QKV weight and its transpose)."""
     from flipped_vqa_b200 import ops

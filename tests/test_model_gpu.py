@@ -264,3 +264,32 @@ def test_last_layer_live_row_pruning_is_equivalent(fvqa_lib):
         model._engine.prune_last_layer = prune
         tok.append(model(opt_data, inference=True))
     assert torch.equal(tok[0], tok[1])
+
+
+@pytest.mark.parametrize("dim,heads,S", [(256, 2, 128), (256, 4, 64), (256, 2, 200)])
+def test_shared_prefix_option_scoring_equals_dense(fvqa_lib, dim, heads, S):
+    """Validation path: evaluating the option-invariant prefix once (step.OptionPlan,
+    StepEngine.forward_options) gives the per-token losses of the dense [B * n_opt, S] evaluation
+    (model_my_original_mod.py:332-377) and the same predictions, on far fewer rows."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=dim, n_layers=3, n_heads=heads, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=S, adapter_len=10, adapter_layer=3)
+    args = make_args()
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=41, max_feats=args.max_feats, bias=args.bias)
+    model = build_product_model(pd, sd, args)
+    for seed, n_opt in ((50, 5), (51, 1), (52, 4)):
+        data = synthetic_batch(6, S, 512, max_feats=args.max_feats, seed=seed, n_options=n_opt)
+        if seed == 52:
+            data["label"]["vqa"][1] = 0                 # a sample without labels
+            data["text_id"]["vqa"][2, 3, 30] = 7        # an option that diverges early
+        model.share_option_prefix = True
+        tok_s = model(data, inference=True)
+        plan = model.last_plan
+        model.share_option_prefix = False
+        tok_d = model(data, inference=True)
+        assert tok_s.shape == tok_d.shape == (6, n_opt, S - 1)
+        assert torch.equal(tok_s != 0, tok_d != 0)
+        assert rel_l2(tok_s.cpu(), tok_d.cpu()) < 1e-4
+        assert torch.equal(model.predict_options(tok_s), model.predict_options(tok_d))
+        if n_opt == 5:
+            assert plan.T_c * 3 < plan.T

@@ -25,21 +25,28 @@ def main():
         tok = model(batches[i % 3], inference=True)
         return model.predict_options(tok).cpu()
 
-    for i in range(3):
-        step(i)
-    torch.cuda.synchronize()
-    n = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(n):
-        step(i)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
     d, L, S, hid = cfg["dim"], cfg["adapter_layer"], cfg["seqlen"], 11008 if cfg["dim"] == 4096 else 13824
-    T = bs * 5 * S
-    flops = L * 2 * T * (4 * d * d + 3 * d * hid) + L * 4 * bs * 5 * d * (S * (S + 1) / 2 + S * 10)
-    print(json.dumps({"task": "option scoring (validation)", "config": name, "items_per_step": bs, "options": 5, "ms_per_step": ms,
-                      "items_per_s": bs / (ms * 1e-3), "sequences_per_s": bs * 5 / (ms * 1e-3), "tflops": flops / (ms * 1e-3) / 1e12}))
+    out = {"task": "option scoring (validation)", "config": name, "items_per_step": bs, "options": 5}
+    preds = {}
+    for mode in ("dense", "shared_prefix"):
+        model.share_option_prefix = mode == "shared_prefix"
+        preds[mode] = [step(i).tolist() for i in range(3)]          # warm-up; also the agreement check
+        rows = model.last_plan.T_c if mode == "shared_prefix" else model.last_plan.T
+        torch.cuda.synchronize()
+        n = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step(i)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        # FLOPs actually executed: row-wise GEMMs on `rows`, attention on the full [bs*5, S] layout
+        flops = L * 2 * rows * (4 * d * d + 3 * d * hid) + L * 4 * bs * 5 * d * (S * (S + 1) / 2 + S * 10)
+        out[mode] = {"ms_per_step": ms, "items_per_s": bs / (ms * 1e-3), "sequences_per_s": bs * 5 / (ms * 1e-3),
+                     "gemm_rows_per_step": rows, "tflops_executed": flops / (ms * 1e-3) / 1e12}
+    out["predictions_agree"] = preds["dense"] == preds["shared_prefix"]
+    out["speedup"] = out["dense"]["ms_per_step"] / out["shared_prefix"]["ms_per_step"]
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":
