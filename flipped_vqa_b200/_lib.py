@@ -35,6 +35,7 @@ _SIGNATURES = {
     "fvqa_gemm_swiglu_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_debug_force_bn": [_i],
+    "fvqa_gemm_debug_epilogue_warps": [_i],
     "fvqa_gemm_debug_l2_hints": [_i],
     "fvqa_attn_debug_use_tc": [_i],
     "fvqa_attn_uses_tc": [_i, _i, _i],

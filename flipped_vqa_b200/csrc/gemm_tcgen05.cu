@@ -22,6 +22,7 @@ namespace fvqa {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 256;
+constexpr int PAIR_THREADS = 384;   // CTA-pair kernel: warps 0-3 TMA / MMA / TMEM alloc / idle, warps 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int GEMM_UMMA_K = 16;
 
 template <int BN>
@@ -266,7 +267,7 @@ constexpr int PAIR_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 __host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GEMM_BK * 2 + (bn / 2) * GEMM_BK * 2; }
 
 template <bool OUT_F32, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages, int l2_hints) {
   extern __shared__ uint8_t smem_raw[];
@@ -303,7 +304,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+      mbar_init(tempty_bar(a), 2 * ((blockDim.x >> 5) - 4));  // epilogue warps x 2 CTAs (only the leader's copy is used)
     }
     fence_mbar_init();
   }
@@ -375,15 +376,23 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs: own 128 rows, all BN columns) =====================
+    // The epilogue of a short-K tile (K = 4096: ~21 us of MMA) is a chain of dependent global loads (residual / cos,sin /
+    // g) and stores per chunk, which used to be LONGER than the main loop it should hide behind (Wo + residual: 114 us).
+    // The loads of chunk c+1 are therefore issued before chunk c is processed, and the first chunk's before the
+    // accumulator is even complete (88 us). A second warp per TMEM lane quadrant (384 threads, each warp half of the
+    // chunks; test hook) measured no better and 5 % worse for the SwiGLU-forward epilogue, so four warps stay the default.
     const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const bool split = blockDim.x > 256;                  // 384 threads: two epilogue warps per quadrant (test hook: 256 = one)
     int acc = 0;
     uint32_t acc_phase = 0;
     const int n32 = BN >> 5;
+    const int nch = n32 + ((BN & 16) ? 1 : 0);            // 32-column chunks incl. a 16-column tail
+    const int c_begin = (split && half) ? (nch + 1) >> 1 : 0;
+    const int c_end = (split && !half) ? (nch + 1) >> 1 : nch;
     for (int tile = pair; tile < num_tiles; tile += n_pairs) {
       const int m0 = (tile % tiles_m) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (tile / tiles_m) * BN;
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < M;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
@@ -391,8 +400,10 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // columns [0,128) = a = W1 x, [128,256) = b = W3 x of hidden units [128 tn, +128): write g = [a | b] (bf16,
         // saved for backward) and c = silu(a) * b computed from the ROUNDED a, b (bit-identical to swiglu_fwd_kernel)
         const int hcol = (tile / tiles_m) * 128;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = split ? 2 * half : 0; c < (split ? 2 * half + 2 : 4); ++c) {
           uint32_t va[32], vb[32];
           tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), va);
           tmem_ld_32x32(tbase + static_cast<uint32_t>(128 + c * 32), vb);
@@ -419,17 +430,28 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       } else if constexpr (EPI == EPI_SWIGLU_BWD) {
         // accumulator = dc = d(silu(a) * b) for hidden units [n0, n0 + BN): read g = [a | b], write
         // dg = [dc b s (1 + a (1 - s)) | dc a s] (bit-identical to swiglu_bwd_kernel on the bf16-rounded dc)
-#pragma unroll 1
-        for (int c = 0; c < n32; ++c) {
+        uint4 ga_n[4], gb_n[4];
+        auto load_g = [&](int c) {
           const int col0 = n0 + c * 32;
-          uint4 ga[4], gb[4];
-          const bool ok = row_ok && col0 < N;
-          if (ok) {
+          if (row_ok && col0 < N) {
             const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + col0);
             const uint4* gr2 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + epi.hid + col0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { ga[q] = __ldg(gr + q); gb[q] = __ldg(gr2 + q); }
+            for (int q = 0; q < 4; ++q) { ga_n[q] = __ldg(gr + q); gb_n[q] = __ldg(gr2 + q); }
           }
+        };
+        // (BN is a multiple of 32 here: hid % 32 == 0 and the launcher keeps 32 | BN for this epilogue)
+        if (c_begin < c_end) load_g(c_begin);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          const int col0 = n0 + c * 32;
+          uint4 ga[4], gb[4];
+          const bool ok = row_ok && col0 < N;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { ga[q] = ga_n[q]; gb[q] = gb_n[q]; }
+          if (c + 1 < c_end) load_g(c + 1);
           uint32_t v[32];
           tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
@@ -455,20 +477,100 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         }
       } else {
-#pragma unroll 1
-        for (int c = 0; c < n32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
-          tmem_ld_wait();
+        // aux = what the chunk needs from global memory besides the accumulator: the fp32 residual (8 x float4) or the
+        // RoPE cos | sin of the row's position (4 + 4 x float4); loaded one chunk ahead
+        constexpr bool PIPE = OUT_F32 || ROPE;
+        float4 aux_n[8];
+        const int pos = ROPE ? (epi.pos_ids != nullptr ? __ldg(epi.pos_ids + (row_ok ? row : 0)) : row % epi.S) : 0;
+        auto load_aux = [&](int c) {
           const int col0 = n0 + c * 32;
-          if (row_ok && col0 < N) epilogue_store<32, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
-        }
-        if (BN & 16) {
+          if (!(row_ok && col0 < N)) return;
+          if constexpr (OUT_F32) {
+            if (epi.R != nullptr) {
+              const float4* rr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(epi.R) + static_cast<long>(row) * epi.ldr + col0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col0 + 4 * j < N) aux_n[j] = rr[j];
+            }
+          } else if constexpr (ROPE) {
+            // 8-column groups never straddle a head or the q|k / v boundary (hd % 8 == 0, col % 8 == 0)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int col = col0 + 8 * q;
+              if (col < epi.rope_cols) {
+                const long ti = static_cast<long>(pos) * (epi.hd >> 1) + ((col % epi.hd) >> 1);
+                aux_n[q] = __ldg(reinterpret_cast<const float4*>(epi.cosT + ti));
+                aux_n[4 + q] = __ldg(reinterpret_cast<const float4*>(epi.sinT + ti));
+              }
+            }
+          }
+        };
+        if (PIPE && c_begin < c_end) load_aux(c_begin);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          const int col0 = n0 + c * 32;
+          const bool tail = c >= n32;                       // the 16-column tail chunk (BN & 16)
+          float4 aux[8];
+          if constexpr (PIPE) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) aux[j] = aux_n[j];
+            if (c + 1 < c_end) load_aux(c + 1);
+          }
           uint32_t v[32];
-          tmem_ld_32x16(tbase + static_cast<uint32_t>(n32 * 32), v);
+          if (tail) tmem_ld_32x16(tbase + static_cast<uint32_t>(c * 32), v);
+          else tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
-          const int col0 = n0 + n32 * 32;
-          if (row_ok && col0 < N) epilogue_store<16, OUT_F32, ROPE>(v, Cout, epi, row, col0, N, ldc);
+          const int ncol = tail ? 16 : 32;
+          if (!(row_ok && col0 < N)) {
+            // nothing to store for this lane / chunk
+          } else if constexpr (OUT_F32) {
+            float* crow = reinterpret_cast<float*>(Cout) + static_cast<long>(row) * ldc + col0;
+            const bool has_r = epi.R != nullptr;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (4 * j < ncol && col0 + 4 * j < N) {
+                float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                       __uint_as_float(v[4 * j + 3]));
+                if (has_r) { o.x += aux[j].x; o.y += aux[j].y; o.z += aux[j].z; o.w += aux[j].w; }
+                *reinterpret_cast<float4*>(crow + 4 * j) = o;
+              }
+            }
+          } else {
+            bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
+            const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
+            if constexpr (ROPE) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                if (col0 + 8 * q < epi.rope_cols) {
+                  const float cv[4] = {aux[q].x, aux[q].y, aux[q].z, aux[q].w};
+                  const float sv[4] = {aux[4 + q].x, aux[4 + q].y, aux[4 + q].z, aux[4 + q].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float a = __uint_as_float(v[8 * q + 2 * e]), b = __uint_as_float(v[8 * q + 2 * e + 1]);
+                    v[8 * q + 2 * e] = __float_as_uint(a * cv[e] - b * sv[e]);
+                    v[8 * q + 2 * e + 1] = __float_as_uint(a * sv[e] + b * cv[e]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (8 * j < ncol && col0 + 8 * j < N) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+                if (rrow != nullptr) {
+                  float r[8];
+                  unpack8(*reinterpret_cast<const uint4*>(rrow + 8 * j), r);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) f[e] += r[e];
+                }
+                *reinterpret_cast<uint4*>(crow + 8 * j) = pack8(f);
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -633,6 +735,7 @@ int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc
 // ---- CTA-pair path ---------------------------------------------------------------------------
 static int g_l2_hints = 0;         // test hook (fvqa_gemm_debug_l2_hints)
 static int g_force_bn = 0;        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
+static int g_pair_threads = GEMM_THREADS;   // test hook (fvqa_gemm_debug_epilogue_warps): 256 = 4 epilogue warps (default), 384 = 8
 
 // Output-tile width for the pair kernel: maximise wave efficiency x per-tile efficiency. The per-tile
 // factors are MEASURED (B200, 3072 x 22016 x 4096, tools/gemm_diag.py): the UMMA 256 x N x 16 issue time
@@ -674,7 +777,7 @@ static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void
   const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + bn - 1) / bn;
   const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tiles_n;
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, GEMM_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints);
+  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, g_pair_threads, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints);
   return check_launch("gemm_bf16_nt_pair");
 }
 
@@ -766,6 +869,14 @@ extern "C" int fvqa_gemm_bf16_nt_rope_pos(const fvqa_bf16* A, int lda, const fvq
                                           const int32_t* pos_ids, void* stream) {
   FVQA_REQUIRE(pos_ids != nullptr, FVQA_ERR_INVALID_ARG, "gemm_rope_pos: pos_ids is NULL");
   return gemm_rope_impl(A, lda, B, ldb, C, ldc, M, N, K, rope_cos, rope_sin, rope_cols, hd, 1, pos_ids, stream);
+}
+
+/* Test / tuning hook: epilogue warps per CTA of the CTA-pair kernel, 4 (default) or 8 (two per TMEM lane quadrant).
+ * Returns the previous value. */
+extern "C" int fvqa_gemm_debug_epilogue_warps(int n) {
+  const int prev = (g_pair_threads >> 5) - 4;
+  if (n == 4 || n == 8) g_pair_threads = (4 + n) * 32;
+  return prev;
 }
 
 /* Test / tuning hook: force the CTA-pair tile width (multiple of 16 in [64,256]); 0 restores the

@@ -92,6 +92,8 @@ int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int
 /* Test / tuning hook for the GEMM tile choice: bn = multiple of 16 in [64,256] forces that CTA-pair
  * tile width, 0 restores the heuristic, -1 forces the single-CTA kernel. Returns the previous value. */
 int fvqa_gemm_debug_force_bn(int bn);
+/* Test / tuning hook: epilogue warps per CTA of the CTA-pair kernel: 4 (default) or 8 (two per TMEM lane quadrant). */
+int fvqa_gemm_debug_epilogue_warps(int n);
 /* Tuning hook: 1 = the CTA-pair kernel's TMA loads carry L2 eviction hints (A evict_last, B evict_first). */
 int fvqa_gemm_debug_l2_hints(int on);
 

@@ -1,0 +1,69 @@
+"""Burst time of the eight GEMM launches of one 7B NExT-QA layer (forward + dX backward), each with the epilogue it
+has in the step, for 4 vs 8 epilogue warps in the CTA-pair kernel; cuBLAS (plain bf16 out) beside it."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from flipped_vqa_b200 import _lib, ops
+
+BF = torch.bfloat16
+
+
+def timeit(fn, n=30):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    time.sleep(0.5)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+def main():
+    lib = _lib.lib()
+    T, d, hid, S, hd = int(os.environ.get("ROWS", 3072)), 4096, 11008, 128, 128
+    dev = "cuda"
+    rn = lambda *s, std=1.0: (torch.randn(*s, device=dev) * std).to(BF)
+    x, xh = rn(T, d), rn(T, hid)
+    wqkv, wo, w13, w2 = rn(3 * d, d, std=.02), rn(d, d, std=.02), rn(2 * hid, d, std=.02), rn(d, hid, std=.02)
+    wqkv_t, w13_t, w2_t = rn(d, 3 * d, std=.02), rn(d, 2 * hid, std=.02), rn(hid, d, std=.02)
+    res = torch.randn(T, d, device=dev)
+    dqkv, dg = rn(T, 3 * d), rn(T, 2 * hid)
+    inv = 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd))
+    ang = torch.outer(torch.arange(2 * S).float(), inv)
+    cos, sin = torch.cos(ang).to(dev).contiguous(), torch.sin(ang).to(dev).contiguous()
+    o32 = torch.empty(T, d, device=dev)
+    o16 = torch.empty(T, d, device=dev, dtype=BF)
+    qkv = torch.empty(T, 3 * d, device=dev, dtype=BF)
+    g = rn(T, 2 * hid); c = torch.empty(T, hid, device=dev, dtype=BF); dgo = torch.empty(T, 2 * hid, device=dev, dtype=BF)
+    cases = [
+        ("qkv+rope      N=12288 K=4096 ", lambda: ops.gemm_nt_rope(x, wqkv, cos, sin, 2 * d, hd, S, out=qkv), 2. * T * 3 * d * d, (x, wqkv)),
+        ("wo f32+res    N=4096  K=4096 ", lambda: ops.gemm_nt(x, wo, out=o32, residual=res, out_fp32=True), 2. * T * d * d, (x, wo)),
+        ("w13+swiglu    N=22016 K=4096 ", lambda: ops.gemm_swiglu_fwd(x, w13, g=g, c=c), 2. * T * 2 * hid * d, (x, w13)),
+        ("w2 f32+res    N=4096  K=11008", lambda: ops.gemm_nt(xh, w2, out=o32, residual=res, out_fp32=True), 2. * T * d * hid, (xh, w2)),
+        ("w2t+swiglu'   N=11008 K=4096 ", lambda: ops.gemm_swiglu_bwd(x, w2_t, g, dg=dgo), 2. * T * hid * d, (x, w2_t)),
+        ("w13t dX       N=4096  K=22016", lambda: ops.gemm_nt(dg, w13_t, out=o16), 2. * T * d * 2 * hid, (dg, w13_t)),
+        ("wot dX        N=4096  K=4096 ", lambda: ops.gemm_nt(x, wo, out=o16), 2. * T * d * d, (x, wo)),
+        ("wqkvt dX      N=4096  K=12288", lambda: ops.gemm_nt(dqkv, wqkv_t, out=o16), 2. * T * d * 3 * d, (dqkv, wqkv_t)),
+    ]
+    tot = {4: 0.0, 8: 0.0, "cublas": 0.0}
+    for name, fn, fl, (a, b) in cases:
+        row = []
+        for nw in (4, 8):
+            lib.fvqa_gemm_debug_epilogue_warps(nw)
+            us = timeit(fn)
+            tot[nw] += us
+            row.append(f"{nw} warps {us:6.1f} us {fl / us / 1e6:5.0f} TF/s")
+        lib.fvqa_gemm_debug_epilogue_warps(8)
+        cb = torch.empty(a.shape[0], b.shape[0], device=dev, dtype=BF)
+        us = timeit(lambda: torch.matmul(a, b.t(), out=cb))
+        tot["cublas"] += us
+        row.append(f"cublas plain {us:6.1f} us {fl / us / 1e6:5.0f} TF/s")
+        print(name, " | ".join(row), flush=True)
+    print(f"layer total: 4 warps {tot[4]:.0f} us | 8 warps {tot[8]:.0f} us | cublas (no epilogue work) {tot['cublas']:.0f} us")
+
+
+if __name__ == "__main__":
+    main()
