@@ -1,5 +1,5 @@
 """Burst time of the eight GEMM launches of one 7B NExT-QA layer (forward + dX backward), each with the epilogue it
-has in the step (env STAGES=0,6,5 compares TMA ring depths, STREAMK=0/1); cuBLAS (plain bf16 out, no epilogue work) beside it."""
+has in the step; cuBLAS (plain bf16 out, no epilogue work) beside it."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -48,18 +48,12 @@ def main():
         ("wot dX        N=4096  K=4096 ", lambda: ops.gemm_nt(x, wo, out=o16), 2. * T * d * d, (x, wo)),
         ("wqkvt dX      N=4096  K=12288", lambda: ops.gemm_nt(dqkv, wqkv_t, out=o16), 2. * T * d * 3 * d, (dqkv, wqkv_t)),
     ]
-    variants = [int(v) for v in os.environ.get("STAGES", "0").split(",")]
-    lib.fvqa_gemm_debug_stream_k(int(os.environ.get("STREAMK", "1")))
-    tot = {v: 0.0 for v in variants}
-    tot["cublas"] = 0.0
+    tot = {"pair": 0.0, "cublas": 0.0}
     for name, fn, fl, (a, b) in cases:
         row = []
-        for nw in variants:
-            lib.fvqa_gemm_debug_max_stages(nw)
-            us = timeit(fn)
-            tot[nw] += us
-            row.append(f"stages<={nw} {us:6.1f} us {fl / us / 1e6:5.0f} TF/s")
-        lib.fvqa_gemm_debug_max_stages(0)
+        us = timeit(fn)
+        tot["pair"] += us
+        row.append(f"pair kernel {us:6.1f} us {fl / us / 1e6:5.0f} TF/s")
         cb = torch.empty(a.shape[0], b.shape[0], device=dev, dtype=BF)
         us = timeit(lambda: torch.matmul(a, b.t(), out=cb))
         tot["cublas"] += us
