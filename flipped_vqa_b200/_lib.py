@@ -57,6 +57,7 @@ _SIGNATURES = {
     "fvqa_f32_to_bf16": [_p, _p, _i64, _p],
     "fvqa_gather_rows": [_p, _p, _p, _i, _i, _p],
     "fvqa_scatter_row_vectors": [_p, _p, _p, _i, _i, _p],
+    "fvqa_expand_rows": [_p, _p, _p, _i, _i, _p],
 }
 _RESTYPES = {"fvqa_last_error": C.c_char_p, "fvqa_attn_bwd_ws_bytes": _i64}
 

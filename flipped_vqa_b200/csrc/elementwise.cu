@@ -193,6 +193,18 @@ __global__ void __launch_bounds__(256) move_rows_kernel(const uint4* __restrict_
   }
 }
 
+// dst[r] = idx[r] >= 0 ? src[idx[r]] : 0 — expands a compacted row set back to the full [n_seq * S] token layout
+__global__ void __launch_bounds__(256) expand_rows_kernel(const uint4* __restrict__ src, const int32_t* __restrict__ idx, uint4* __restrict__ dst,
+                                                          long rows, int vecs) {
+  const long total = rows * vecs;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / vecs;
+    const int v = static_cast<int>(i - r * vecs);
+    const long o = idx[r];
+    dst[i] = o >= 0 ? __ldg(src + o * vecs + v) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 static int elementwise_grid(long work_items, int threads) {
   long blocks = (work_items + threads - 1) / threads;
   const long cap = 148L * 8;  // 8 resident CTAs of 256 threads per SM
@@ -277,6 +289,15 @@ extern "C" int fvqa_gather_rows(const void* src, const int32_t* idx, void* dst, 
   move_rows_kernel<true><<<elementwise_grid(static_cast<long>(rows) * vecs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const uint4*>(src), idx, reinterpret_cast<uint4*>(dst), rows, vecs);
   return check_launch("gather_rows");
+}
+
+extern "C" int fvqa_expand_rows(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream) {
+  FVQA_REQUIRE(row_bytes % 16 == 0, FVQA_ERR_UNSUPPORTED, "expand_rows: row_bytes %d must be a multiple of 16", row_bytes);
+  if (rows <= 0) return FVQA_OK;
+  const int vecs = row_bytes / 16;
+  expand_rows_kernel<<<elementwise_grid(static_cast<long>(rows) * vecs, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint4*>(src), idx, reinterpret_cast<uint4*>(dst), rows, vecs);
+  return check_launch("expand_rows");
 }
 
 extern "C" int fvqa_scatter_row_vectors(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream) {

@@ -422,3 +422,14 @@ def scatter_row_vectors(src: torch.Tensor, idx: torch.Tensor, dst: torch.Tensor)
     rows, row_bytes = idx.numel(), src.shape[1] * src.element_size()
     check(_lib.lib().fvqa_scatter_row_vectors(ptr(src), ptr(idx), ptr(dst), rows, row_bytes, stream()), "scatter_row_vectors")
     return dst
+
+
+@_timed
+def expand_rows(src: torch.Tensor, idx: torch.Tensor, dst: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dst[r] = src[idx[r]] where idx[r] >= 0, zeros elsewhere (compact row set -> full [n_seq * S] token layout)."""
+    assert src.is_contiguous() and idx.dtype == torch.int32
+    rows, row_bytes = idx.numel(), src.shape[1] * src.element_size()
+    dst = torch.empty(rows, src.shape[1], dtype=src.dtype, device=src.device) if dst is None else dst
+    assert dst.is_contiguous() and dst.shape[0] == rows
+    check(_lib.lib().fvqa_expand_rows(ptr(src), ptr(idx), ptr(dst), rows, row_bytes, stream()), "expand_rows")
+    return dst

@@ -78,8 +78,23 @@ class BatchPlan:
         self.n_live = int(live.numel())
         ce_rows_c = torch.searchsorted(live, ce_rows.long()).to(I32)
         q_rows_c = torch.searchsorted(live, q_rows.long()).to(I32)
+        # padding-free row set: rows after the last loss-relevant position of a sequence cannot reach any loss through the
+        # causal mask (`model.py:298-299`), so the row-wise ops only need rows [0, end_n) of sequence n ("k" = kept rows).
+        loss_rows = torch.cat([ce_rows.long(), q_rows.long()])
+        end = torch.zeros(self.n_seq, dtype=torch.long)
+        if loss_rows.numel():
+            end.scatter_reduce_(0, loss_rows // S, loss_rows % S + 1, reduce="amax")
+        keep = (torch.arange(S).view(1, S) < end.view(-1, 1)).reshape(-1)
+        c2f = keep.nonzero().flatten()
+        self.T_c = int(c2f.numel())
+        f2c = torch.full((self.T,), -1, dtype=torch.long)
+        f2c[c2f] = torch.arange(self.T_c)
+        ce_rows_k, q_rows_k = f2c[ce_rows.long()], f2c[q_rows.long()]
+        live_k = torch.unique(torch.cat([ce_rows_k, q_rows_k]), sorted=True)
+        self.n_live_k = int(live_k.numel())
         parts = [ids_all.flatten(), labels_all.flatten(), vstart, seq_video, qav_index.flatten(),
-                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid, live.to(I32), ce_rows_c, q_rows_c]
+                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid, live.to(I32), ce_rows_c, q_rows_c,
+                 c2f % S, c2f, f2c, ce_rows_k, q_rows_k, live_k, torch.searchsorted(live_k, ce_rows_k), torch.searchsorted(live_k, q_rows_k)]
         sizes = [p.numel() for p in parts]
         total = max(sum(sizes), 1)
         video = _cpu(data["video"]).reshape(B * F, -1).float()
@@ -101,7 +116,8 @@ class BatchPlan:
     def to_device(self, device):
         dev = self.host_ints.to(device, non_blocking=True)
         names = ["ids", "labels", "vstart", "seq_video", "qav_index", "ce_rows", "ce_tgt", "ce_dst", "q_rows", "q_tgt", "q_vid",
-                 "live_rows", "ce_rows_c", "q_rows_c"]
+                 "live_rows", "ce_rows_c", "q_rows_c",
+                 "pos_ids", "c2f", "f2c", "ce_rows_k", "q_rows_k", "live_rows_k", "ce_rows_kc", "q_rows_kc"]
         for nm, (off, n) in zip(names, self._slices):
             setattr(self, nm, dev[off:off + n])
         self.video = self.host_video.to(device, non_blocking=True)
@@ -279,6 +295,7 @@ class SavedStep:
     rstd2: List[torch.Tensor] = field(default_factory=list)
     vf32: Optional[torch.Tensor] = None
     pruned: bool = False        # last layer ran on plan.live_rows only (h / g / rstd2 / final x of that layer are compact)
+    compact: bool = False       # row-wise tensors (x, h, g, rstd) hold the padding-free rows plan.c2f; qkv / o / lse are full
     ce: Optional[dict] = None
     qav: Optional[dict] = None
 
@@ -302,6 +319,12 @@ class StepEngine:
         # wo / FFN of the last layer only on the rows the losses read: -2.1 % FLOPs, -1.8 % step time in a same-box A/B
         # (tools/ab_step.py); results identical (tests/test_model_gpu.py::test_last_layer_live_row_pruning_is_equivalent)
         self.prune_last_layer = True
+        # padding-free rows (BatchPlan.c2f), opt-in: the row-wise ops skip the rows after each sequence's last loss-relevant
+        # position. Same losses and gradients (tests/test_model_gpu.py::test_padding_free_rows_are_equivalent); costs four row
+        # copies per layer around attention, so it is only used when it drops at least `skip_pad_min_saving` of the rows.
+        # Off by default: the default step computes the reference's row set (every position of every sequence).
+        self.skip_pad_rows = False
+        self.skip_pad_min_saving = 0.06
 
     # -------------------------------------------------------------------------------- forward
     def forward(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
@@ -315,26 +338,43 @@ class StepEngine:
         vf32 = ops.visual_proj_fwd(plan.video, visual_w)                           # [B*F, d] fp32
         x = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w,
                              n_seq, S, F)
+        # Row set of the row-wise ops: all T rows, or the padding-free compact rows (attention always sees all T rows)
+        compact = self.skip_pad_rows and 0 < plan.T_c <= (1.0 - self.skip_pad_min_saving) * T
+        R = plan.T_c if compact else T
+        if compact:
+            x = ops.gather_rows(x, plan.c2f)
+            ce_full, q_full, live_rows, ce_live, q_live, n_live = (plan.ce_rows_k, plan.q_rows_k, plan.live_rows_k, plan.ce_rows_kc,
+                                                                   plan.q_rows_kc, plan.n_live_k)
+        else:
+            ce_full, q_full, live_rows, ce_live, q_live, n_live = (plan.ce_rows, plan.q_rows, plan.live_rows, plan.ce_rows_c,
+                                                                   plan.q_rows_c, plan.n_live)
         adapter_bf16 = ops.f32_to_bf16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
-        xn = torch.empty(T, d, dtype=BF16, device=dev)
-        c = torch.empty(T, hid, dtype=BF16, device=dev)
+        xn = torch.empty(R, d, dtype=BF16, device=dev)
+        c = torch.empty(R, hid, dtype=BF16, device=dev)
         qkv_b = o_b = g_b = None
+        qkv_c = torch.empty(R, 3 * d, dtype=BF16, device=dev) if compact else None
+        o_c = torch.empty(R, d, dtype=BF16, device=dev) if compact else None
         # The last layer's wo / FFN outputs are read only at the rows the losses use (labelled positions): run them on
         # those rows alone, exactly like the vocabulary projection (heads below). Everything upstream needs all rows (K/V).
-        prune = self.prune_last_layer and 0 < plan.n_live < T
-        ce_idx, q_idx = (plan.ce_rows_c, plan.q_rows_c) if prune else (plan.ce_rows, plan.q_rows)
+        prune = self.prune_last_layer and 0 < n_live < R
+        ce_idx, q_idx = (ce_live, q_live) if prune else (ce_full, q_full)
         for l, w in enumerate(layers):
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
             _, rstd1 = ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
             # Wq|Wk|Wv in one GEMM, RoPE applied to q|k in its epilogue (`model.py:89,96`)
-            qkv = ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=None if save else qkv_b)
+            if compact:
+                ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_c, pos_ids=plan.pos_ids)
+                qkv = ops.expand_rows(qkv_c, plan.f2c, dst=None if save else qkv_b)  # full layout (zero rows past the end)
+            else:
+                qkv = ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=None if save else qkv_b)
             akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])          # adapter K|V, no RoPE (`model.py:99-100`)
-            o, lse = ops.attn_fwd(qkv, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F,
-                                  out=None if save else o_b)
+            o_full, lse = ops.attn_fwd(qkv, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F,
+                                       out=None if save else o_b)
+            o = ops.gather_rows(o_full, plan.c2f, dst=o_c) if compact else o_full
             if prune and l == L - 1:
-                o_g = ops.gather_rows(o, plan.live_rows)
-                x_g = ops.gather_rows(x, plan.live_rows)
+                o_g = ops.gather_rows(o, live_rows)
+                x_g = ops.gather_rows(x, live_rows)
                 h = ops.gemm_nt(o_g, w.wo, residual=x_g, out_fp32=True)            # [n_live, d]
                 xn_g, rstd2 = ops.rmsnorm_fwd(h, w.ffn_norm, self.eps)
                 g, c_g = ops.gemm_swiglu_fwd(xn_g, w.w13)
@@ -345,15 +385,16 @@ class StepEngine:
                 g, _ = ops.gemm_swiglu_fwd(xn, w.w13, g=None if save else g_b, c=c)  # W1|W3 GEMM, SwiGLU in its epilogue
                 x_next = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)           # out = h + ffn (`model.py:186`)
             if save:
-                sv.x.append(x); sv.qkv.append(qkv); sv.akv.append(akv); sv.o.append(o); sv.lse.append(lse)
+                sv.x.append(x); sv.qkv.append(qkv); sv.akv.append(akv); sv.o.append(o_full); sv.lse.append(lse)
                 sv.h.append(h); sv.g.append(g); sv.rstd1.append(rstd1); sv.rstd2.append(rstd2)
             elif not (prune and l == L - 1):
-                qkv_b, o_b, g_b = qkv, o, g
+                qkv_b, o_b, g_b = qkv, o_full, g
             x = x_next
         if save:
             sv.x.append(x)
             sv.vf32 = vf32
             sv.pruned = prune
+            sv.compact = compact
         if ops.GEMM_TIMER is not None:
             ops.GEMM_TIMER.active = False
         # --- heads
@@ -419,7 +460,7 @@ class StepEngine:
         adapter_bf16 = ops.f32_to_bf16(adapter_w)
         xn = torch.empty(Tc, d, dtype=BF16, device=dev)
         qkv_c = torch.empty(Tc, 3 * d, dtype=BF16, device=dev)
-        qkv_f = torch.zeros(plan.T, 3 * d, dtype=BF16, device=dev)                 # rows past E_b stay zero (finite V rows)
+        qkv_f = torch.empty(plan.T, 3 * d, dtype=BF16, device=dev)
         o_f = torch.empty(plan.T, d, dtype=BF16, device=dev)
         lse = torch.empty(n_seq, H, S, dtype=torch.float32, device=dev)
         o_c = torch.empty(Tc, d, dtype=BF16, device=dev)
@@ -430,7 +471,7 @@ class StepEngine:
         for l, w in enumerate(layers):
             ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
             ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_c, pos_ids=plan.pos_ids)
-            ops.gather_rows(qkv_c, plan.f2c, dst=qkv_f)                             # compact -> every option's sequence
+            ops.expand_rows(qkv_c, plan.f2c, dst=qkv_f)                             # compact -> every option's sequence, zero rows past E_b
             akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])
             ops.attn_fwd(qkv_f, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F, out=o_f, lse=lse)
             if prune and l == L - 1:
@@ -462,9 +503,16 @@ class StepEngine:
         T, n_seq, dev = plan.T, plan.n_seq, self.device
         L = len(layers)
         x_final = sv.x[L]
-        pruned = sv.pruned
-        R = plan.n_live if pruned else T                      # rows of the final hidden state that exist
-        ce_idx, q_idx = (plan.ce_rows_c, plan.q_rows_c) if pruned else (plan.ce_rows, plan.q_rows)
+        pruned, compact = sv.pruned, sv.compact
+        if compact:
+            ce_full, q_full, live_rows, ce_live, q_live, n_live = (plan.ce_rows_k, plan.q_rows_k, plan.live_rows_k, plan.ce_rows_kc,
+                                                                   plan.q_rows_kc, plan.n_live_k)
+        else:
+            ce_full, q_full, live_rows, ce_live, q_live, n_live = (plan.ce_rows, plan.q_rows, plan.live_rows, plan.ce_rows_c,
+                                                                   plan.q_rows_c, plan.n_live)
+        Tr = plan.T_c if compact else T                       # rows of the row-wise tensors
+        R = n_live if pruned else Tr                          # rows of the final hidden state that exist
+        ce_idx, q_idx = (ce_live, q_live) if pruned else (ce_full, q_full)
         # gradient of the residual stream: fp32 master + bf16 copy (A operand of the next dX GEMM)
         dx = torch.zeros(R, d, dtype=torch.float32, device=dev)
         dx_bf = torch.zeros(R, d, dtype=BF16, device=dev)
@@ -493,15 +541,17 @@ class StepEngine:
         # --- layers, last to first
         if self._attn_ws is None or self._attn_ws.numel() < ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A):
             self._attn_ws = torch.empty(ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
-        dg = torch.empty(T, 2 * hid, dtype=BF16, device=dev)
-        dtmp = torch.empty(T, d, dtype=BF16, device=dev)
-        dh = torch.empty(T, d, dtype=torch.float32, device=dev)
-        dh_bf = torch.empty(T, d, dtype=BF16, device=dev)
+        dg = torch.empty(Tr, 2 * hid, dtype=BF16, device=dev)
+        dtmp = torch.empty(Tr, d, dtype=BF16, device=dev)
+        dh = torch.empty(Tr, d, dtype=torch.float32, device=dev)
+        dh_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
         dqkv = torch.empty(T, 3 * d, dtype=BF16, device=dev)
         dakv = torch.empty(A, 2 * d, dtype=torch.float32, device=dev)
         dakv_bf = torch.empty(A, 2 * d, dtype=BF16, device=dev)
-        dx_next = torch.empty(T, d, dtype=torch.float32, device=dev)
-        dx_next_bf = torch.empty(T, d, dtype=BF16, device=dev)
+        dx_next = torch.empty(Tr, d, dtype=torch.float32, device=dev)
+        dx_next_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
+        do_full = torch.empty(T, d, dtype=BF16, device=dev) if compact else None
+        dqkv_c = torch.empty(Tr, 3 * d, dtype=BF16, device=dev) if compact else None
         for l in range(L - 1, -1, -1):
             w = layers[l]
             if ops.GEMM_TIMER is not None:
@@ -514,19 +564,22 @@ class StepEngine:
                                                 dx_bf16=torch.empty(R, d, dtype=BF16, device=dev))
                 do_c = ops.gemm_nt(dh_c_bf, w.wo_t)
                 dtmp.zero_()
-                ops.scatter_row_vectors(do_c, plan.live_rows, dtmp)
+                ops.scatter_row_vectors(do_c, live_rows, dtmp)
                 dh.zero_()
-                ops.scatter_row_vectors(dh_c, plan.live_rows, dh)
-                dx = torch.empty(T, d, dtype=torch.float32, device=dev)           # full-size stream from here down
-                dx_bf = torch.empty(T, d, dtype=BF16, device=dev)
+                ops.scatter_row_vectors(dh_c, live_rows, dh)
+                dx = torch.empty(Tr, d, dtype=torch.float32, device=dev)          # full-size stream from here down
+                dx_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
             else:
                 ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l], dg=dg)                 # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
                 ops.gemm_nt(dg, w.w13_t, out=dtmp)                                 # d(ffn_norm out) = [da|db] . [W1;W3]
                 ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_bf16=dh_bf)
                 ops.gemm_nt(dh_bf, w.wo_t, out=dtmp)                               # d(attn out) = dh . Wo
-            ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dtmp,
+            # attention sees the full layout: d(attn out) of the rows that were never computed is zero
+            dout = ops.expand_rows(dtmp, plan.f2c, dst=do_full) if compact else dtmp
+            ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dout,
                          n_seq, S, H, hd, A, F, dqkv=dqkv, dakv=dakv, dgate1=grads.gate1[l], dgate2=grads.gate2[l], ws=self._attn_ws)
-            ops.gemm_nt(dqkv, w.wqkv_t, out=dtmp)                                  # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
+            dqkv_r = ops.gather_rows(dqkv, plan.c2f, dst=dqkv_c) if compact else dqkv
+            ops.gemm_nt(dqkv_r, w.wqkv_t, out=dtmp)                                # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
             ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next, dx_bf16=dx_next_bf)
             # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l)
             ops.f32_to_bf16(dakv, dakv_bf)
@@ -538,6 +591,8 @@ class StepEngine:
         if ops.GEMM_TIMER is not None:
             ops.GEMM_TIMER.active = False
         # --- input side (`model.py:322-336` backward)
+        if compact:
+            dx = ops.expand_rows(dx, plan.f2c)                                     # [T, d] fp32, zero at the skipped rows
         dvf = ops.build_h0_bwd(dx, plan.vstart, plan.seq_video, plan.qav_index, n_seq, plan.n_video, S, F)
         ops.video_grad_finish(dvf, dvf_qav, plan.n_video, F, dtemporal=grads.temporal)
         ops.visual_proj_bwd(dvf, plan.video, dwv=grads.visual)

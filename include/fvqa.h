@@ -183,6 +183,11 @@ int fvqa_option_score(const float* token_loss, int32_t* prediction, float* mean_
  *      dst[i, :] = src[idx[i], :]   and   dst[idx[i], :] = src[i, :]   for rows of row_bytes (multiple of 16); idx < 0 skipped. */
 int fvqa_gather_rows(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream);
 int fvqa_scatter_row_vectors(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream);
+/* ---- padding-free row set: the row-wise ops (norms, frozen GEMMs, SwiGLU, residuals) of llama/model.py:172-187 only run on
+ *      the rows [0, last loss-relevant position] of each sequence (rows after it cannot influence any loss under the causal
+ *      mask of model.py:298-299); attention still sees the full [n_seq, S] layout. dst[r, :] = idx[r] >= 0 ? src[idx[r], :] : 0
+ *      rebuilds that layout (zero rows where nothing was computed) from the compact rows. */
+int fvqa_expand_rows(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream);
 
 /* ---- small utilities --------------------------------------------------------------------------- */
 int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, void* stream);

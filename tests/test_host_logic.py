@@ -93,6 +93,32 @@ def test_batch_plan_rows_and_targets():
     assert torch.equal(ql.flatten()[qrows + 1], arr["q_tgt"].long())
 
 
+def test_batch_plan_padding_free_rows():
+    """BatchPlan's compact row set: every sequence keeps exactly the rows [0, last loss-relevant position]; the loss row
+    lists re-indexed into it point at the same (sequence, position) pairs."""
+    from flipped_vqa_b200.step import BatchPlan
+    from flipped_vqa_b200.synthetic import synthetic_batch
+    data = synthetic_batch(4, 64, 512, seed=5)
+    data["label"]["vaq"][2] = 0
+    plan = BatchPlan(data, ["vqa", "vaq", "qav"], 10)
+    names = ["ids", "labels", "vstart", "seq_video", "qav_index", "ce_rows", "ce_tgt", "ce_dst", "q_rows", "q_tgt", "q_vid",
+             "live_rows", "ce_rows_c", "q_rows_c", "pos_ids", "c2f", "f2c", "ce_rows_k", "q_rows_k", "live_rows_k", "ce_rows_kc", "q_rows_kc"]
+    arr = {n: plan.host_ints[o:o + k].long() for n, (o, k) in zip(names, plan._slices)}
+    S, c2f, f2c = plan.S, arr["c2f"], arr["f2c"]
+    assert plan.T_c == c2f.numel() < plan.T
+    assert torch.equal(f2c[c2f], torch.arange(plan.T_c)) and torch.equal(arr["pos_ids"], c2f % S)
+    loss_rows = torch.cat([arr["ce_rows"], arr["q_rows"]])
+    for n in range(plan.n_seq):
+        kept = (f2c[n * S:(n + 1) * S] >= 0)
+        mine = loss_rows[(loss_rows // S) == n] % S
+        end = int(mine.max()) + 1 if mine.numel() else 0
+        assert int(kept.sum()) == end and bool(kept[:end].all())
+    assert int((f2c[(4 + 2) * S:(4 + 3) * S] >= 0).sum()) == 0          # the VAQ sequence without labels keeps no rows
+    assert torch.equal(c2f[arr["ce_rows_k"]], arr["ce_rows"]) and torch.equal(c2f[arr["q_rows_k"]], arr["q_rows"])
+    assert torch.equal(arr["live_rows_k"][arr["ce_rows_kc"]], arr["ce_rows_k"])
+    assert torch.equal(arr["live_rows_k"][arr["q_rows_kc"]], arr["q_rows_k"])
+
+
 def test_batch_plan_option_layout():
     from flipped_vqa_b200.step import BatchPlan
     params, sd, data = golden_inputs(5)

@@ -293,3 +293,40 @@ def test_shared_prefix_option_scoring_equals_dense(fvqa_lib, dim, heads, S):
         assert torch.equal(model.predict_options(tok_s), model.predict_options(tok_d))
         if n_opt == 5:
             assert plan.T_c * 3 < plan.T
+
+
+@pytest.mark.parametrize("vaq,qav", [(True, True), (False, False)])
+def test_padding_free_rows_are_equivalent(fvqa_lib, vaq, qav):
+    """StepEngine.skip_pad_rows: norms / frozen GEMMs / SwiGLU only on the rows up to each sequence's last loss-relevant
+    position (rows after it cannot reach a loss through the causal mask, model.py:298-299); attention on the full layout.
+    Losses must be identical and gradients equal up to summation order; option scoring (dense path) likewise."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=128, adapter_len=10, adapter_layer=3)
+    args = make_args()
+    args.vaq, args.qav = vaq, qav
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=61, max_feats=args.max_feats, bias=args.bias)
+    data = synthetic_batch(5, 128, 512, max_feats=args.max_feats, seed=62)
+    data["label"]["vqa"][3] = 0                               # a sequence no loss reads at all
+    res = []
+    for skip in (False, True):
+        model = build_product_model(pd, sd, args)
+        model._ensure_packed()
+        model._engine.skip_pad_rows = skip
+        losses = _run_product(model, data)
+        res.append((losses, product_grads(model)))
+        if skip:
+            assert 0 < model.last_plan.T_c < 0.95 * model.last_plan.T
+    (l0, g0), (l1, g1) = res
+    assert l0 == l1
+    for n in g0:
+        assert rel_l2(g1[n], g0[n]) < 1e-4, n
+    tok = []
+    opt_data = synthetic_batch(4, 128, 512, max_feats=args.max_feats, seed=63, n_options=5)
+    for skip in (False, True):
+        model = build_product_model(pd, sd, args)
+        model._ensure_packed()
+        model._engine.skip_pad_rows = skip
+        model.share_option_prefix = False
+        tok.append(model(opt_data, inference=True))
+    assert torch.equal(tok[0], tok[1])

@@ -13,7 +13,7 @@ if [ "${2:-}" != "skip_tests" ]; then
 fi
 python bench.py --steps 10 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench exit $?"
 cat $OUT/bench_$TAG.json
-BENCH1="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --sample-layers 0"
+BENCH1="python bench.py --steps 1 --warmup 3 --no-e2e --no-padfree --no-cpu-baseline --sample-layers 0"
 $BENCH1 > $OUT/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k "$KRE" -s 1250 -c 620 --csv \
     --log-file $OUT/launches_$TAG.csv $BENCH1 > $OUT/ncu_list_$TAG.log 2>&1
