@@ -7,7 +7,7 @@
 namespace fvqa {
 
 constexpr int NORM_THREADS = 256;
-constexpr int NORM_MAXV = 4;  // vectors (8 elements) per thread kept in registers -> dim <= 8192
+constexpr int NORM_MAXV = 4;  // vectors (8 elements) per thread kept in registers -> dim <= 8192 (kernels are instantiated for 2, 3, 4)
 
 __device__ __forceinline__ void load8f(const float* p, float (&f)[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -23,6 +23,7 @@ __device__ __forceinline__ void store8f(float* p, const float (&f)[8]) {
 // RMSNorm forward on the fp32 residual stream:  y = bf16(x * rstd * w)
 // idx == nullptr: row r reads x[r]; otherwise row r reads x[idx[r]] (idx<0 -> zero row).
 // ---------------------------------------------------------------------------------------------
+template <int MAXV>
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ idx, const bf16* __restrict__ w,
     bf16* __restrict__ y, float* __restrict__ rstd_out, int dim, float eps) {
@@ -39,10 +40,10 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
   }
   const float* xrow = x + src * dim;
   const uint4* wv = reinterpret_cast<const uint4*>(w);
-  float xr[NORM_MAXV][8];
+  float xr[MAXV][8];
   float ss = 0.f;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
+  for (int i = 0; i < MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
       load8f(xrow + v * 8, xr[i]);
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
   const float rstd = rsqrtf(ss / static_cast<float>(dim) + eps);
   if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
+  for (int i = 0; i < MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
       float g[8], o[8];
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
 //   dx = rstd * (dn - n * mean(dn * n)) (+ dres)      fp32 out (+ optional bf16 copy: next GEMM operand)
 // scatter variant: output row = idx[r] (rows with idx<0 skipped), no residual.
 // ---------------------------------------------------------------------------------------------
+template <int MAXV>
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
     const bf16* __restrict__ dy, const float* __restrict__ x, const int32_t* __restrict__ idx,
     const bf16* __restrict__ w, const float* __restrict__ rstd_in, const float* __restrict__ dres,
@@ -87,13 +89,20 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
   const float* xrow = x + src * dim;
   const uint4* wv = reinterpret_cast<const uint4*>(w);
   const float rstd = rstd_in[row];
-  float xr[NORM_MAXV][8], dn[NORM_MAXV][8];
+  float xr[MAXV][8], dn[MAXV][8], fr[MAXV][8];
   float dot = 0.f;
+  const float* rrow = dres ? dres + src * dim : nullptr;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
+  for (int i = 0; i < MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
       load8f(xrow + v * 8, xr[i]);
+      // the residual gradient is only needed after the row reduction: loading it here keeps ONE round trip to memory per row
+      if (rrow) load8f(rrow + v * 8, fr[i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fr[i][j] = 0.f;
+      }
       float fd[8], fw[8];
       unpack8(__ldg(dyrow + v), fd);
       unpack8(__ldg(wv + v), fw);
@@ -106,16 +115,13 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
   }
   dot = block_sum(dot, red) / static_cast<float>(dim);
   float* dxrow = dx + src * dim;
-  const float* rrow = dres ? dres + src * dim : nullptr;
 #pragma unroll
-  for (int i = 0; i < NORM_MAXV; ++i) {
+  for (int i = 0; i < MAXV; ++i) {
     const int v = threadIdx.x + i * NORM_THREADS;
     if (v < nvec) {
       float o[8];
-      float fr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (rrow) load8f(rrow + v * 8, fr);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fr[j] + rstd * (dn[i][j] - xr[i][j] * rstd * dot);
+      for (int j = 0; j < 8; ++j) o[j] = fr[i][j] + rstd * (dn[i][j] - xr[i][j] * rstd * dot);
       store8f(dxrow + v * 8, o);
       if (dx_bf16) reinterpret_cast<uint4*>(dx_bf16 + src * dim)[v] = pack8(o);
     }
@@ -205,6 +211,9 @@ __global__ void __launch_bounds__(256) expand_rows_kernel(const uint4* __restric
   }
 }
 
+// registers follow the row length: 2 vectors per thread up to dim 4096 (7B), 3 up to 6144 (13B), else 4
+#define FVQA_NORM_PICK(kernel, dim) ((dim) <= 8 * NORM_THREADS * 2 ? kernel<2> : (dim) <= 8 * NORM_THREADS * 3 ? kernel<3> : kernel<4>)
+
 static int elementwise_grid(long work_items, int threads) {
   long blocks = (work_items + threads - 1) / threads;
   const long cap = 148L * 8;  // 8 resident CTAs of 256 threads per SM
@@ -222,7 +231,8 @@ extern "C" int fvqa_rmsnorm_fwd(const float* x, const fvqa_bf16* w, fvqa_bf16* y
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED,
                "rmsnorm: dim %d must be a multiple of 8 and <= %d", dim, 8 * NORM_THREADS * NORM_MAXV);
   if (rows <= 0) return FVQA_OK;
-  rmsnorm_fwd_kernel<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kfn = FVQA_NORM_PICK(rmsnorm_fwd_kernel, dim);
+  kfn<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       x, nullptr, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_fwd");
 }
@@ -232,7 +242,8 @@ extern "C" int fvqa_rmsnorm_gather_fwd(const float* x, const int32_t* idx, const
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_gather: bad dim %d", dim);
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_gather: idx is null");
   if (rows_out <= 0) return FVQA_OK;
-  rmsnorm_fwd_kernel<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kfn = FVQA_NORM_PICK(rmsnorm_fwd_kernel, dim);
+  kfn<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       x, idx, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_gather_fwd");
 }
@@ -241,7 +252,8 @@ extern "C" int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const float* x, const fvqa_
                                 const float* dres, float* dx, fvqa_bf16* dx_bf16, int rows, int dim, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_bwd: bad dim %d", dim);
   if (rows <= 0) return FVQA_OK;
-  rmsnorm_bwd_kernel<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kfn = FVQA_NORM_PICK(rmsnorm_bwd_kernel, dim);
+  kfn<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(dy), x, nullptr, reinterpret_cast<const bf16*>(w), rstd, dres, dx,
       reinterpret_cast<bf16*>(dx_bf16), dim);
   return check_launch("rmsnorm_bwd");
@@ -252,7 +264,8 @@ extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const float* x, con
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_scatter_bwd: bad dim %d", dim);
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_scatter_bwd: idx is null");
   if (rows_out <= 0) return FVQA_OK;
-  rmsnorm_bwd_kernel<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+  auto kfn = FVQA_NORM_PICK(rmsnorm_bwd_kernel, dim);
+  kfn<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(dy), x, idx, reinterpret_cast<const bf16*>(w), rstd, nullptr, dx,
       reinterpret_cast<bf16*>(dx_bf16), dim);
   return check_launch("rmsnorm_scatter_bwd");
