@@ -25,7 +25,11 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: to
     for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         if data_iter_step % accum_iter == 0:
             lr_sched.adjust_learning_rate(optimizer, data_iter_step / len(data_loader) + epoch, args)
-        vqa_loss, vaq_loss, qav_loss = model(data)
+        if isinstance(data, tuple):                  # dataloader.PlannedLoader: (batch dict, device-resident plan)
+            data, plan = data
+            vqa_loss, vaq_loss, qav_loss = model.forward_plan(plan)
+        else:
+            vqa_loss, vaq_loss, qav_loss = model(data)
         loss = vqa_loss + vaq_loss + qav_loss
         update = (data_iter_step + 1) % accum_iter == 0
         loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update)
@@ -57,10 +61,13 @@ def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torc
     print_freq = max(int(len(data_loader) / 4), 1)
     inner = model.module if hasattr(model, "module") else model
     for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
+        plan = None
+        if isinstance(data, tuple):                  # dataloader.PlannedLoader(..., inference=True)
+            data, plan = data
         answer = data["answer"]
         bsz = answer.shape[0]
         with torch.no_grad():
-            individual_losses = model(data, inference=True)
+            individual_losses = inner.inference_plan(plan) if plan is not None else model(data, inference=True)
             prediction = inner.predict_options(individual_losses)
         eval_exact_match = answer.to(prediction.device) == prediction
         acc = eval_exact_match.sum().item() / bsz

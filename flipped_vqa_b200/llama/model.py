@@ -307,28 +307,33 @@ class Transformer(nn.Module):
         zero = lambda: torch.tensor([0], device=dev)        # disabled objectives, `model.py:302`
         return losses["vqa"], losses.get("vaq", zero()), losses.get("qav", zero())
 
+    def plan_options(self, data) -> OptionPlan:
+        """Host side of shared-prefix option scoring (`step.OptionPlan`) + its async H2D copy."""
+        if self._pinned is None:
+            self._pinned = PinnedPool()
+        return OptionPlan(data, self.max_feats, pool=self._pinned).to_device(self._device)
+
     @torch.no_grad()
     def inference(self, data):
         """Loss-based option scoring: VQA stream only over bsz*n_options sequences
         (`model_my_original_mod.py:281,332-333,348-360,375-377,506`). With `share_option_prefix` (default) the
         option-invariant prefix of each sample is evaluated once (`step.OptionPlan`); the per-token losses are the same."""
         self._ensure_packed()
+        return self.inference_plan(self.plan_options(data) if self.share_option_prefix else self.plan_batch(data, inference=True))
+
+    @torch.no_grad()
+    def inference_plan(self, plan):
+        """Device side of option scoring for an already device-resident `OptionPlan` (or dense inference `BatchPlan`)."""
+        self._ensure_packed()
+        self.last_plan = plan
         trainables, n_run = self.trainable_parameters()
         g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]
         g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
-        if self.share_option_prefix:
-            if self._pinned is None:
-                self._pinned = PinnedPool()
-            plan = OptionPlan(data, self.max_feats, pool=self._pinned).to_device(self._device)
-            self.last_plan = plan
-            return self._engine.forward_options(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
-                                                self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
-                                                g1, g2)
-        plan = self.plan_batch(data, inference=True)
-        self.last_plan = plan
-        tok, _ = self._engine.forward(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
-                                      self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
-                                      g1, g2, save=False, token_losses=True)
+        w = (self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data, self.norm.weight.data,
+             trainables[0].data, trainables[1].data, trainables[2].data, g1, g2)
+        if isinstance(plan, OptionPlan):
+            return self._engine.forward_options(plan, *w)
+        tok, _ = self._engine.forward(plan, *w, save=False, token_losses=True)
         return tok
 
     @staticmethod

@@ -1,17 +1,73 @@
-"""Tokenizer surface the model needs (`/root/reference/llama/tokenizer.py:14-42`).
+"""Tokenizer surface the model needs (`/root/reference/llama/tokenizer.py:14-42`) and the prompt builders of the
+three objectives (`encode_vqa` / `encode_vaq` / `encode_qav`, `tokenizer.py:44-211`).
 
-The reference's prompt builders (`encode_vqa/vaq/qav`, `:44-302`) are CPU data preparation and out
-of the accelerated path's scope; the model itself only reads
-`n_words`, `eos_id`, `a_token_id`, `q_token_id` (`llama/model.py:201-204`). With a real
-`tokenizer.model` this class wraps SentencePiece exactly like the reference; `SyntheticTokenizer`
-stands in when no tokenizer file exists (tests, benchmarks)."""
+The model itself only reads `n_words`, `eos_id`, `a_token_id`, `q_token_id` (`llama/model.py:201-204`). With a real
+`tokenizer.model` this class wraps SentencePiece exactly like the reference; `SyntheticTokenizer` stands in when no
+tokenizer file exists (tests, benchmarks). The prompt builders live in `PromptBuilder`, which only needs an object
+with `.encode(str) -> List[int]` as `sp_model`, so they are testable without a SentencePiece model file. The subtitle
+(`--sub`) builders of TVQA (`tokenizer.py:213-302`) are not mirrored."""
 from __future__ import annotations
 
 import os
 from typing import List
 
 
-class Tokenizer:
+class PromptBuilder:
+    """Token sequences of the three objectives. Layouts (F = max_feats video placeholders, id -2):
+
+      vqa : [bos] enc(instr 'Video:') | F x -2 | nl | enc(question [choices] 'Answer: The answer is ' <option>) eos
+      vaq : [bos] enc(instr 'Video:') | F x -2 | nl | enc([choices] answer-part <option> '\n' question) eos
+      qav : [bos] enc(instr question [choices] answer-part <option> '\nVideo:') | F x -2 | eos
+
+    `split == 'train'` builds ONE sequence (the correct option), otherwise one per option (`tokenizer.py:69-77`).
+    Multiple-choice runs (`args.is_generation_task` false) append `answer_mapping[k]` ('(A)' ...) and include the choices
+    text; generation-task runs append the option TEXT and omit the choices (`tokenizer.py:79-101,132-164,192-211`).
+    prefix_index = first position the loss reads: the 'Answer' piece + 5 (vqa), the 'Question' piece + 2 (vaq), the
+    'Video' piece + 2 (qav), located in the sequence of the correct option (vaq in generation mode: of option 0)."""
+
+    _INSTR = {"vqa": "Instruction: Predict the answer based on the video and question.\n",
+              "vaq": "Instruction: Predict the question based on the video and answer.\n",
+              "qav": "Instruction: Predict the video based on the question and answer.\n"}
+
+    def _gen(self) -> bool:
+        return bool(getattr(self.args, "is_generation_task", False))
+
+    def _option_strings(self, split, answer_mapping, answer, options):
+        pool = list(options) if self._gen() else list(answer_mapping.values())
+        if split == "train":
+            return [options[answer] if self._gen() else answer_mapping[answer]]
+        return pool
+
+    def _video_head(self, task: str):
+        head = [self.bos_id] + self.sp_model.encode(self._INSTR[task] + "Video:")
+        return head, len(head)
+
+    def encode_vqa(self, text=None, max_feats: int = 10, split: str = "train", answer_mapping=None, answer=None, options=None):
+        head, video_start = self._video_head("vqa")
+        stem = text["q_text"] + ("" if self._gen() else text["o_text"]) + text["a_text"]
+        seqs = [head + [-2] * max_feats + [self.nl_id] + self.sp_model.encode(stem + o) + [self.eos_id]
+                for o in self._option_strings(split, answer_mapping, answer, options)]
+        ref = seqs[0] if split == "train" else seqs[answer]
+        return seqs, ref.index(self.a_token_id) + 5, video_start
+
+    def encode_vaq(self, text=None, max_feats: int = 10, split: str = "train", answer_mapping=None, answer=None, options=None):
+        head, video_start = self._video_head("vaq")
+        q = text["q_text"].strip()
+        stem = ("\n" + text["a_text"]) if self._gen() else (text["o_text"] + text["a_text"])
+        seqs = [head + [-2] * max_feats + [self.nl_id] + self.sp_model.encode(stem + o + "\n" + q) + [self.eos_id]
+                for o in self._option_strings(split, answer_mapping, answer, options)]
+        ref = seqs[0] if (split == "train" or self._gen()) else seqs[answer]
+        return seqs, ref.index(self.q_token_id) + 2, video_start
+
+    def encode_qav(self, text=None, max_feats: int = 10, split: str = "train", answer_mapping=None, answer=None, options=None):
+        stem = self._INSTR["qav"] + text["q_text"] + ("" if self._gen() else text["o_text"]) + text["a_text"]
+        seqs = [[self.bos_id] + self.sp_model.encode(stem + o + "\n" + "Video:") + [-2] * max_feats + [self.eos_id]
+                for o in self._option_strings(split, answer_mapping, answer, options)]
+        ref = seqs[0] if split == "train" else seqs[answer]
+        return seqs, ref.index(self.v_token_id) + 2
+
+
+class Tokenizer(PromptBuilder):
     def __init__(self, model_path: str, args=None):
         self.args = args
         if not os.path.isfile(model_path):

@@ -121,9 +121,15 @@ class BatchPlan:
         for nm, (off, n) in zip(names, self._slices):
             setattr(self, nm, dev[off:off + n])
         self.video = self.host_video.to(device, non_blocking=True)
+        self._dev = dev
         if self._slot is not None:
             self._slot.event.record()          # the pinned slot may be rewritten once these copies are done
         return self
+
+    def record_stream(self, stream):
+        """The plan was copied on another stream (dataloader.PlannedLoader): tell the allocator who uses it."""
+        self._dev.record_stream(stream)
+        self.video.record_stream(stream)
 
 
 class OptionPlan:
@@ -221,9 +227,14 @@ class OptionPlan:
         for nm, (off, n) in zip(self._names, self._slices):
             setattr(self, nm, dev[off:off + n])
         self.video = self.host_video.to(device, non_blocking=True)
+        self._dev = dev
         if self._slot is not None:
             self._slot.event.record()
         return self
+
+    def record_stream(self, stream):
+        self._dev.record_stream(stream)
+        self.video.record_stream(stream)
 
 
 class PinnedPool:

@@ -176,3 +176,49 @@ def synthetic_batch(bsz: int, seqlen: int, vocab: int, max_feats: int = 10, seed
         "text": [{} for _ in range(bsz)],
     }
     return data
+
+
+class HashSentencePiece:
+    """Deterministic stand-in for `SentencePieceProcessor.encode` (no `tokenizer.model` exists offline): words and
+    punctuation marks hash to ids in [100, n_words); the pieces 'Video', 'Question', 'Answer' map to the ids the
+    reference hard-codes (`llama/tokenizer.py:28-31`) so the prompt builders can locate them."""
+
+    SPECIAL = {"Video": 15167, "Question": 16492, "Answer": 22550}
+
+    def __init__(self, n_words: int = 32000):
+        self.n_words = n_words
+
+    def encode(self, s: str):
+        import re
+        import zlib
+        out = []
+        for piece in re.findall(r"\w+|[^\w\s]|\n", s):
+            out.append(self.SPECIAL.get(piece, 100 + zlib.crc32(piece.encode()) % (self.n_words - 100)))
+        return out
+
+
+def hash_tokenizer(cls, n_words: int = 32000, is_generation_task: bool = False):
+    """Instance of a tokenizer class (ours or the reference's) wired to `HashSentencePiece` without a model file."""
+    import argparse
+    t = object.__new__(cls)
+    t.args = argparse.Namespace(is_generation_task=is_generation_task, debug=False)
+    t.sp_model = HashSentencePiece(n_words)
+    t.n_words, t.bos_id, t.eos_id, t.pad_id = n_words, 1, 2, -1
+    t.v_token_id, t.q_token_id, t.a_token_id, t.nl_id = 15167, 16492, 22550, 13
+    return t
+
+
+def synthetic_qa_texts(n: int, n_options: int = 5, seed: int = 0):
+    """NExT-QA-style prompt pieces (`dataloader/nextqa.py:24-39` layout) with random words."""
+    import random
+    rng = random.Random(seed)
+    words = ["man", "dog", "ball", "red", "jump", "why", "after", "child", "table", "run", "holding", "water", "car", "before", "smile"]
+    mapping = {i: f"({chr(65 + i)})" for i in range(n_options)}
+    out = []
+    for _ in range(n):
+        question = " ".join(rng.choice(words) for _ in range(rng.randint(4, 10))).capitalize() + "?"
+        options = [" ".join(rng.choice(words) for _ in range(rng.randint(1, 4))) for _ in range(n_options)]
+        o_text = "Choices: \n" + "".join(f"{mapping[i]} {options[i]}\n" for i in range(n_options))
+        out.append(dict(text={"q_text": f"Question: {question}\n", "o_text": o_text, "a_text": "Answer: The answer is ", "options": options},
+                        answer=rng.randrange(n_options), options=options))
+    return out, mapping

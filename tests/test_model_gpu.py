@@ -330,3 +330,34 @@ def test_padding_free_rows_are_equivalent(fvqa_lib, vaq, qav):
         model.share_option_prefix = False
         tok.append(model(opt_data, inference=True))
     assert torch.equal(tok[0], tok[1])
+
+
+def test_planned_loader_drives_train_and_val(fvqa_lib):
+    """dataloader.PlannedLoader: plans built and copied on a side stream ahead of the step give the same losses /
+    predictions as model(data), and engine.train_one_epoch / val_one_epoch accept its (data, plan) items."""
+    import argparse
+    from flipped_vqa_b200 import engine
+    from flipped_vqa_b200.dataloader import PlannedLoader
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    from flipped_vqa_b200.util import misc
+    pd = dict(dim=256, n_layers=2, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=64, adapter_len=10, adapter_layer=2)
+    margs = make_args()
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=71, max_feats=margs.max_feats, bias=margs.bias)
+    model = build_product_model(pd, sd, margs)
+    train = [synthetic_batch(4, 64, 512, max_feats=margs.max_feats, seed=400 + i) for i in range(6)]
+    val = [synthetic_batch(4, 64, 512, max_feats=margs.max_feats, seed=500 + i, n_options=5) for i in range(3)]
+    with torch.no_grad():
+        direct = [[float(x) for x in model(b)] for b in train]
+        planned = [[float(x) for x in model.forward_plan(p)] for _, p in PlannedLoader(train, model, depth=3)]
+        assert direct == planned
+        tok_d = [model(b, inference=True) for b in val]
+        tok_p = [model.inference_plan(p) for _, p in PlannedLoader(val, model, inference=True)]
+        for a, b in zip(tok_d, tok_p):
+            assert torch.equal(a, b)
+    opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.95), weight_decay=0.0)
+    targs = argparse.Namespace(accum_iter=1, lr=1e-3, min_lr=0.0, warmup_epochs=0, epochs=1, debug=False)
+    s0 = engine.train_one_epoch(model, PlannedLoader(train, model), opt, 0, misc.NativeScalerWithGradNormCount(), args=targs)
+    assert s0["loss"] == s0["loss"]
+    v = engine.val_one_epoch(model, PlannedLoader(val, model, inference=True), opt, 0, args=targs)
+    assert 0.0 <= v["acc"] <= 1.0
