@@ -53,6 +53,49 @@ def hash_normal(shape, seed: int, std: float = 1.0, mean: float = 0.0) -> torch.
     return t
 
 
+AUDIO_DIM = 1024        # ImageBind audio features (`dataloader/base_dataset.py:13`)
+
+
+def audio_mode(args) -> Optional[str]:
+    """The five input-fusion branches of `llama/model.py:209-227,306-322` as one tag:
+    None (video only) | 'audio_only' | 'concat' | 'sum' | 'attention'."""
+    if not getattr(args, "audio", False):
+        return None
+    if getattr(args, "audio_only", False):
+        return "audio_only"
+    m = getattr(args, "audio_merge", "none")
+    if m == "concat":
+        return "concat"
+    if m != "" and m in "sum":                     # the reference tests `audio_merge in 'sum'` (`model.py:215,313`)
+        return "sum"
+    if m == "attention":
+        return "attention"
+    return None
+
+
+def synthetic_audio_state(params, mode: str, seed: int = 0, video_dim: int = 768) -> Dict[str, torch.Tensor]:
+    """Extra / replaced parameters of an audio-fusion variant, reference names (`llama/model.py:209-227,145-150`)."""
+    d = params.dim
+    sd: Dict[str, torch.Tensor] = {}
+    k = seed * 1000 + 900
+    if mode in ("audio_only", "sum"):
+        sd["audio_proj.weight"] = hash_normal((d, AUDIO_DIM), k + 1, 1.0 / math.sqrt(AUDIO_DIM))
+    if mode == "attention":
+        sd["audio_proj.weight"] = hash_normal((video_dim, AUDIO_DIM), k + 1, 1.0 / math.sqrt(AUDIO_DIM))
+        for i, nm in enumerate(("query", "key", "value")):
+            sd[f"video_audio_cross_attn.{nm}.weight"] = hash_normal((video_dim, video_dim), k + 2 + 2 * i, 1.0 / math.sqrt(video_dim))
+            sd[f"video_audio_cross_attn.{nm}.bias"] = hash_normal((video_dim,), k + 3 + 2 * i, 0.05)
+    if mode == "concat":
+        sd["visual_proj.weight"] = hash_normal((d, video_dim + AUDIO_DIM), k + 8, 1.0 / math.sqrt(video_dim + AUDIO_DIM))
+    return sd
+
+
+def synthetic_audio(bsz: int, frames: int, seed: int = 0) -> torch.Tensor:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(77_000 + seed)
+    return torch.randn(bsz, frames, AUDIO_DIM, generator=g)
+
+
 def synthetic_state_dict(params, seed: int = 0, max_feats: int = 10, bias: float = 3.5,
                          video_dim: int = 768) -> Dict[str, torch.Tensor]:
     """Random-init state dict with the reference's parameter names (`llama/model.py:190-248`,

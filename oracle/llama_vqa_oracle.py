@@ -147,12 +147,32 @@ def _run_layers(h, sd, params, adapter, cos, sin, video_start, max_feats):
     return h
 
 
+def fused_video_feature(sd, data, audio_mode: Optional[str], dev, dt):
+    """`_video_feature` of the five input-fusion branches (`llama/model.py:306-322`; `CrossAttentionModule` `:145-169`)."""
+    video = data["video"].to(dev) if audio_mode != "audio_only" else None
+    audio = data["audio"].to(dev).to(dt) if audio_mode is not None else None          # `.cuda().half()`, `:258-261`
+    if audio_mode is None:
+        return video @ sd["visual_proj.weight"].t()                                   # fp32, `:322`
+    if audio_mode == "audio_only":
+        return audio @ sd["audio_proj.weight"].t()                                    # `:307`
+    if audio_mode == "concat":
+        return torch.cat([video, audio], dim=-1) @ sd["visual_proj.weight"].t()       # `:310-311`
+    if audio_mode == "sum":
+        return (audio @ sd["audio_proj.weight"].t()).to(dt) + (video @ sd["visual_proj.weight"].t()).to(dt)   # `:314`
+    if audio_mode == "attention":
+        af = (audio @ sd["audio_proj.weight"].t()).float()                            # [B, Fa, 768], `:317`, `:158`
+        lin = lambda n, x: x @ sd[f"video_audio_cross_attn.{n}.weight"].float().t() + sd[f"video_audio_cross_attn.{n}.bias"].float()
+        q, k, v = lin("query", video), lin("key", af), lin("value", af)
+        p = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(q.shape[-1]), dim=-1)  # `:165-168`
+        return ((p @ v) @ sd["visual_proj.weight"].t()).to(dt)                         # `:318-320`
+    raise ValueError(audio_mode)
+
+
 def forward_losses(sd, params, data, max_feats: int = 10, tau: float = 100.0,
-                   vaq: bool = True, qav: bool = True):
-    """`llama/model.py:250-365` (video-only branch). Returns (vqa_loss, vaq_loss, qav_loss)."""
+                   vaq: bool = True, qav: bool = True, audio_mode: Optional[str] = None):
+    """`llama/model.py:250-365`. Returns (vqa_loss, vaq_loss, qav_loss). `audio_mode`: see `fused_video_feature`."""
     dev = sd["tok_embeddings.weight"].device
     dt = sd["tok_embeddings.weight"].dtype
-    video = data["video"].to(dev)
     ids = {k: data["text_id"][k].to(dev) for k in ("vqa", "vaq", "qav")}
     lab = {k: data["label"][k].to(dev) for k in ("vqa", "vaq", "qav")}
     vs_vqa, vs_vaq = int(data["video_start"]["vqa"][0]), int(data["video_start"]["vaq"][0])  # sample 0 only, `:264`
@@ -171,7 +191,7 @@ def forward_losses(sd, params, data, max_feats: int = 10, tau: float = 100.0,
 
     emb = sd["tok_embeddings.weight"]
     adapter = sd["adapter_query.weight"].reshape(-1, params.adapter_len, d)       # `:304`
-    _video_feature = video @ sd["visual_proj.weight"].t()                         # fp32, `:322`
+    _video_feature = fused_video_feature(sd, data, audio_mode, dev, dt)            # `:306-322`
     video_feature = (_video_feature + sd["temporal_emb.weight"][None]).to(dt)     # `:324`
 
     def inject(idmat, vs):

@@ -23,7 +23,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict  # noqa: E402
+from flipped_vqa_b200.synthetic import synthetic_audio, synthetic_audio_state, synthetic_batch, synthetic_state_dict  # noqa: E402
 from oracle import ref_shims  # noqa: E402
 
 # The golden config: small enough for a <1 MB fixture, big enough for the CUDA path
@@ -59,6 +59,43 @@ def run_reference_train(dtype):
     return out
 
 
+AUDIO_MODES = ("audio_only", "concat", "sum", "attention")
+
+
+def golden_audio_inputs(mode: str):
+    """Golden inputs of an audio-fusion variant: the video-only inputs + the variant's parameters and audio features
+    ([B, F, 1024] frames; one ImageBind vector per sample for 'attention', `dataloader/nextqa.py:16-18`)."""
+    params, sd, data = golden_inputs()
+    sd = dict(sd)
+    if mode == "audio_only":
+        sd.pop("visual_proj.weight")
+    sd.update(synthetic_audio_state(params, mode, seed=GOLDEN_RUN["seed"]))
+    data = dict(data)
+    data["audio"] = synthetic_audio(GOLDEN_RUN["bsz"], 1 if mode == "attention" else GOLDEN_RUN["max_feats"], seed=GOLDEN_RUN["seed"])
+    if mode == "audio_only":
+        data.pop("video")
+    return params, sd, data
+
+
+def run_reference_audio(mode: str, dtype=torch.float32):
+    params, sd, data = golden_audio_inputs(mode)
+    mod = ref_shims.import_reference("model")
+    r = GOLDEN_RUN
+    args = ref_shims.reference_args(max_feats=r["max_feats"], bias=r["bias"], tau=r["tau"], audio_mode=mode)
+    model = ref_shims.build_reference_model(mod, GOLDEN, args, sd, dtype)
+    if mode == "attention":                       # `CrossAttentionModule(768).float()` (`model.py:227`) stays fp32 in every build
+        for n, p in model.video_audio_cross_attn.named_parameters():
+            p.data = sd["video_audio_cross_attn." + n].detach().clone().float()
+    with ref_shims.patched_torch(dtype):
+        vqa, vaq, qav = model(data)
+        (vqa + vaq + qav).backward()
+    out = {"loss": np.array([float(vqa.detach()), float(vaq.detach()), float(qav.detach())], dtype=np.float64)}
+    for n, p in model.named_parameters():
+        if p.requires_grad and p.grad is not None:
+            out["grad/" + n] = p.grad.detach().float().numpy()
+    return out
+
+
 def run_reference_options(dtype, n_options=5):
     params, sd, data = golden_inputs(n_options)
     mod = ref_shims.import_reference("model_my_original_mod")
@@ -88,9 +125,15 @@ def main():
         for k, v in run_reference_options(dt).items():
             op[f"{tag}/{k}"] = v
     np.savez_compressed(os.path.join(gdir, "options_small.npz"), **op)
+    au = {}
+    for mode in AUDIO_MODES:
+        for k, v in run_reference_audio(mode).items():
+            au[f"{mode}/gold/{k}"] = v
+        print(mode, "gold losses", au[f"{mode}/gold/loss"])
+    np.savez_compressed(os.path.join(gdir, "train_audio_small.npz"), **au)
     print("gold losses", tr["gold/loss"], "fp16 losses", tr["fp16/loss"])
     print("gold pred", op["gold/prediction"], "fp16 pred", op["fp16/prediction"])
-    for f in ("train_small.npz", "options_small.npz"):
+    for f in ("train_small.npz", "options_small.npz", "train_audio_small.npz"):
         print(f, os.path.getsize(os.path.join(gdir, f)), "bytes")
 
 

@@ -63,9 +63,12 @@ def import_reference(variant: str = "model"):
     return mod
 
 
-def reference_args(max_feats=10, bias=3.5, tau=100.0, vaq=True, qav=True):
+def reference_args(max_feats=10, bias=3.5, tau=100.0, vaq=True, qav=True, audio_mode=None):
+    """audio_mode: None | 'audio_only' | 'concat' | 'sum' | 'attention' -> the reference's --audio / --audio_only /
+    --audio_merge flags (`train.py`, `llama/model.py:209-227`)."""
     return argparse.Namespace(max_feats=max_feats, bias=bias, tau=tau, llama_model_path="x/",
-                              audio=False, audio_only=False, audio_merge="none", debug=False,
+                              audio=audio_mode is not None, audio_only=audio_mode == "audio_only",
+                              audio_merge=audio_mode if audio_mode in ("concat", "sum", "attention") else "none", debug=False,
                               vaq=vaq, qav=qav, is_generation_task=False)
 
 

@@ -6,7 +6,9 @@ import numpy as np
 import torch
 
 from oracle import llama_vqa_oracle as O
-from tests.util_parity import GOLDEN_DIR, GOLDEN_RUN, golden_inputs, rel_l2
+import pytest
+
+from tests.util_parity import AUDIO_MODES, GOLDEN_DIR, GOLDEN_RUN, golden_audio_inputs, golden_inputs, rel_l2
 
 
 def test_oracle_training_step_matches_reference():
@@ -25,6 +27,27 @@ def test_oracle_training_step_matches_reference():
     assert n == 7
     # skipped leading layer (adapter_layer < n_layers, model.py:338): no gradient in the reference either
     assert st["layers.0.attention.gate1"].grad is None and "gold/grad/layers.0.attention.gate1" not in g.files
+
+
+@pytest.mark.parametrize("mode", AUDIO_MODES)
+def test_oracle_audio_fusion_variants_match_reference(mode):
+    """The four audio-fusion branches of `llama/model.py:209-227,306-322` (audio only / concat / sum / cross-attention)."""
+    g = np.load(os.path.join(GOLDEN_DIR, "train_audio_small.npz"))
+    params, sd, data = golden_audio_inputs(mode)
+    st = O.prepare_state(sd)
+    losses = O.forward_losses(st, params, data, max_feats=GOLDEN_RUN["max_feats"], tau=GOLDEN_RUN["tau"], audio_mode=mode)
+    sum(losses).backward()
+    np.testing.assert_allclose([float(l.detach()) for l in losses], g[f"{mode}/gold/loss"], rtol=2e-6)
+    n = 0
+    for key in g.files:
+        if key.startswith(f"{mode}/gold/grad/"):
+            name = key[len(f"{mode}/gold/grad/"):]
+            assert rel_l2(st[name].grad, g[key]) < 1e-5, name
+            n += 1
+    assert n == (6 if mode == "audio_only" else 7)            # audio only has no visual_proj (`model.py:209-210`)
+    for name in st:
+        if name.startswith("audio_proj") or name.startswith("video_audio_cross_attn"):
+            assert not st[name].requires_grad                  # frozen by the substring rule (`llama_vqa.py:72`)
 
 
 def test_reference_fp16_distance_from_gold_is_within_stated_tolerances():

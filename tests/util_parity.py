@@ -29,9 +29,27 @@ def golden_inputs(n_options=1):
     return params, sd, data
 
 
-def make_args(max_feats=10, bias=3.5, tau=100.0, vaq=True, qav=True):
-    return argparse.Namespace(max_feats=max_feats, bias=bias, tau=tau, llama_model_path="x/", audio=False, audio_only=False,
-                              audio_merge="none", debug=False, vaq=vaq, qav=qav, is_generation_task=False)
+AUDIO_MODES = ("audio_only", "concat", "sum", "attention")
+
+
+def golden_audio_inputs(mode):
+    """must match oracle/make_golden.py::golden_audio_inputs"""
+    from flipped_vqa_b200.synthetic import synthetic_audio, synthetic_audio_state
+    params, sd, data = golden_inputs()
+    sd, data = dict(sd), dict(data)
+    if mode == "audio_only":
+        sd.pop("visual_proj.weight")
+        data.pop("video")
+    sd.update(synthetic_audio_state(params, mode, seed=GOLDEN_RUN["seed"]))
+    data["audio"] = synthetic_audio(GOLDEN_RUN["bsz"], 1 if mode == "attention" else GOLDEN_RUN["max_feats"], seed=GOLDEN_RUN["seed"])
+    return params, sd, data
+
+
+def make_args(max_feats=10, bias=3.5, tau=100.0, vaq=True, qav=True, audio_mode=None):
+    return argparse.Namespace(max_feats=max_feats, bias=bias, tau=tau, llama_model_path="x/", audio=audio_mode is not None,
+                              audio_only=audio_mode == "audio_only",
+                              audio_merge=audio_mode if audio_mode in ("concat", "sum", "attention") else "none",
+                              debug=False, vaq=vaq, qav=qav, is_generation_task=False)
 
 
 def build_product_model(params_dict, sd, args):
