@@ -44,6 +44,8 @@ _SIGNATURES = {
     "fvqa_attn_bwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fvqa_visual_proj_fwd": [_p, _p, _p, _i, _i, _i, _p],
     "fvqa_visual_proj_bwd": [_p, _p, _p, _i, _i, _i, _p],
+    "fvqa_linear_f32": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
+    "fvqa_cross_attn_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fvqa_build_h0_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fvqa_build_h0_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fvqa_video_grad_finish": [_p, _p, _p, _i, _i, _i, _p],

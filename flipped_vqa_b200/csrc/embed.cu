@@ -8,9 +8,11 @@ namespace fvqa {
 constexpr int VP_COLS = 8;      // output columns per CTA
 constexpr int VP_THREADS = 256;
 
-// vf32[r, c] = sum_k video[r, k] * wv[c, k]     (model.py:322, fp32 Linear without bias)
+// vf32[r, c] = sum_k video[r, k] * wv[c, k] (+ bias[c]) (+ add[r, c])     fp32 Linear: model.py:322 (visual_proj, no bias);
+// also the frozen audio projections / cross-attention q,k,v of the audio-fusion variants (model.py:307-320, :148-163)
 __global__ void __launch_bounds__(VP_THREADS) visual_proj_fwd_kernel(const float* __restrict__ video,
                                                                      const float* __restrict__ wv,
+                                                                     const float* __restrict__ bias, const float* __restrict__ add,
                                                                      float* __restrict__ vf, int rows, int dim, int vdim) {
   extern __shared__ float ws[];  // [VP_COLS][vdim]
   const int c0 = blockIdx.x * VP_COLS;
@@ -35,8 +37,46 @@ __global__ void __launch_bounds__(VP_THREADS) visual_proj_fwd_kernel(const float
     if (lane == 0) {
 #pragma unroll
       for (int j = 0; j < VP_COLS; ++j)
-        if (c0 + j < dim) vf[static_cast<long>(r) * dim + c0 + j] = acc[j];
+        if (c0 + j < dim) {
+          float o = acc[j];
+          if (bias != nullptr) o += bias[c0 + j];
+          if (add != nullptr) o += add[static_cast<long>(r) * dim + c0 + j];
+          vf[static_cast<long>(r) * dim + c0 + j] = o;
+        }
     }
+  }
+}
+
+// Cross-attention of the 'attention' audio-fusion variant (CrossAttentionModule.forward, model.py:153-169):
+// out[b, f, :] = softmax_j(<q[b, f], k[b, j]> / sqrt(D)) . v[b, j, :]   over the Fa audio tokens of sample b. One CTA per (b, f).
+constexpr int XA_MAX_TOKENS = 64;
+__global__ void __launch_bounds__(256) cross_attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                             const float* __restrict__ v, float* __restrict__ out, int F, int Fa, int D,
+                                                             float scale) {
+  __shared__ float red[32];
+  __shared__ float p[XA_MAX_TOKENS];
+  const int b = blockIdx.x / F;
+  const float* qrow = q + static_cast<long>(blockIdx.x) * D;
+  for (int j = 0; j < Fa; ++j) {
+    const float* krow = k + (static_cast<long>(b) * Fa + j) * D;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s += qrow[i] * krow[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) p[j] = s * scale;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float m = p[0];
+    for (int j = 1; j < Fa; ++j) m = fmaxf(m, p[j]);
+    float z = 0.f;
+    for (int j = 0; j < Fa; ++j) { p[j] = expf(p[j] - m); z += p[j]; }
+    for (int j = 0; j < Fa; ++j) p[j] /= z;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float o = 0.f;
+    for (int j = 0; j < Fa; ++j) o += p[j] * v[(static_cast<long>(b) * Fa + j) * D + i];
+    out[static_cast<long>(blockIdx.x) * D + i] = o;
   }
 }
 
@@ -158,12 +198,33 @@ __global__ void __launch_bounds__(256) video_grad_finish_kernel(float* __restric
 
 using namespace fvqa;
 
-extern "C" int fvqa_visual_proj_fwd(const float* video, const float* wv, float* vf32, int rows, int dim, int vdim, void* stream) {
+extern "C" int fvqa_linear_f32(const float* x, const float* w, const float* bias, const float* add, float* y, int rows, int dim,
+                               int in_dim, void* stream) {
   if (rows <= 0) return FVQA_OK;
-  const size_t smem = static_cast<size_t>(VP_COLS) * vdim * sizeof(float);
-  FVQA_REQUIRE(smem <= 48 * 1024, FVQA_ERR_UNSUPPORTED, "visual_proj: vdim %d too large", vdim);
-  visual_proj_fwd_kernel<<<(dim + VP_COLS - 1) / VP_COLS, VP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(video, wv, vf32, rows, dim, vdim);
-  return check_launch("visual_proj_fwd");
+  const size_t smem = static_cast<size_t>(VP_COLS) * in_dim * sizeof(float);
+  FVQA_REQUIRE(smem <= 96 * 1024, FVQA_ERR_UNSUPPORTED, "linear_f32: in_dim %d too large", in_dim);
+  static bool big_smem_enabled = false;       // 768 + 1024 concatenated features need 56 KB (> the 48 KB default)
+  if (smem > 48 * 1024 && !big_smem_enabled) {
+    const cudaError_t e = cudaFuncSetAttribute(visual_proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(visual_proj_fwd): %s", cudaGetErrorString(e));
+    big_smem_enabled = true;
+  }
+  visual_proj_fwd_kernel<<<(dim + VP_COLS - 1) / VP_COLS, VP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, add, y, rows,
+                                                                                                                dim, in_dim);
+  return check_launch("linear_f32");
+}
+
+extern "C" int fvqa_visual_proj_fwd(const float* video, const float* wv, float* vf32, int rows, int dim, int vdim, void* stream) {
+  return fvqa_linear_f32(video, wv, nullptr, nullptr, vf32, rows, dim, vdim, stream);
+}
+
+extern "C" int fvqa_cross_attn_fwd(const float* q, const float* k, const float* v, float* out, int n_samples, int frames, int tokens,
+                                   int dim, void* stream) {
+  FVQA_REQUIRE(tokens >= 1 && tokens <= XA_MAX_TOKENS, FVQA_ERR_UNSUPPORTED, "cross_attn: %d audio tokens (max %d)", tokens, XA_MAX_TOKENS);
+  if (n_samples * frames <= 0) return FVQA_OK;
+  cross_attn_fwd_kernel<<<n_samples * frames, 256, 0, static_cast<cudaStream_t>(stream)>>>(q, k, v, out, frames, tokens, dim,
+                                                                                            rsqrtf(static_cast<float>(dim)));
+  return check_launch("cross_attn_fwd");
 }
 
 extern "C" int fvqa_visual_proj_bwd(const float* dvf, const float* video, float* dwv, int rows, int dim, int vdim, void* stream) {

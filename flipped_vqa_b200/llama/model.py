@@ -23,7 +23,8 @@ import torch
 from torch import nn
 
 from ..step import BatchPlan, GradBuffers, LayerWeights, OptionPlan, PinnedPool, StepEngine
-from ..synthetic import ffn_hidden_dim
+from .. import ops
+from ..synthetic import AUDIO_DIM, audio_mode, ffn_hidden_dim
 from .tokenizer import Tokenizer
 
 BF16 = torch.bfloat16
@@ -114,6 +115,23 @@ class _TrainableLinear(nn.Module):
         self.weight = nn.Parameter(torch.empty(out_f, in_f, device=device).uniform_(-bound, bound))
 
 
+class _FrozenAffine(nn.Module):
+    def __init__(self, dim: int, device):
+        super().__init__()
+        bound = 1.0 / math.sqrt(dim)                        # nn.Linear default init
+        self.weight = nn.Parameter(torch.empty(dim, dim, device=device).uniform_(-bound, bound), requires_grad=False)
+        self.bias = nn.Parameter(torch.empty(dim, device=device).uniform_(-bound, bound), requires_grad=False)
+
+
+class _CrossAttention(nn.Module):
+    """Parameter container of `CrossAttentionModule` (`model.py:145-150`): query / key / value Linear(768, 768) with
+    bias, fp32 (`.float()`, `:227`), frozen by the substring rule. The math runs in `Transformer._fuse_inputs`."""
+
+    def __init__(self, dim: int, device):
+        super().__init__()
+        self.query, self.key, self.value = _FrozenAffine(dim, device), _FrozenAffine(dim, device), _FrozenAffine(dim, device)
+
+
 class _StepFn(torch.autograd.Function):
     """The whole training step as ONE autograd node: forward = fused kernels (+ saved activations),
     backward = hand-written dX-only pass. Upstream gradients (e.g. GradScaler's scale,
@@ -148,7 +166,8 @@ class _StepFn(torch.autograd.Function):
         flat = gb.flat.clone()                              # autograd may keep what we return: never alias the work buffer
         view = lambda k, shape: flat[gb.offsets[k]:gb.offsets[k] + gb.sizes[k]].view(shape)
         H = model.params.n_heads
-        out = [None, None, None, view("adapter", gb.adapter.shape), view("visual", gb.visual.shape), view("temporal", gb.temporal.shape)]
+        out = [None, None, None, view("adapter", gb.adapter.shape), view("visual", gb.visual.shape) if gb.sizes["visual"] else None,
+               view("temporal", gb.temporal.shape)]
         g1, g2 = view("gate1", gb.gate1.shape), view("gate2", gb.gate2.shape)
         out += [g1[l].view(1, H, 1, 1) for l in range(n_run)]
         out += [g2[l].view(1, H, 1, 1) for l in range(n_run)]
@@ -166,9 +185,8 @@ class Transformer(nn.Module):
         self.vocab_size = params.vocab_size
         self.n_layers = params.n_layers
         self.max_feats = args.max_feats
-        if getattr(args, "audio", False):
-            raise NotImplementedError("audio fusion variants (`model.py:209-227,306-322`) are outside the accelerated path "
-                                      "(SURVEY.md §8(f) rank 4); use the reference for --audio runs")
+        # input-fusion variant (`model.py:209-227,306-322`): None | 'audio_only' | 'concat' | 'sum' | 'attention'
+        self.audio_mode = audio_mode(args)
         self.tokenizer = tokenizer if tokenizer is not None else Tokenizer(model_path=f"{args.llama_model_path}./tokenizer.model", args=args)
         self.eos_id = self.tokenizer.eos_id
         self.answer_token_id = self.tokenizer.a_token_id
@@ -179,11 +197,21 @@ class Transformer(nn.Module):
         dt = BF16
         d = params.dim
         self.hidden_dim = ffn_hidden_dim(d, params.multiple_of)
-        self.video_dim = 768
+        self.feature_dim = 768                              # CLIP ViT-L/14 frame features
+        # input width of the TRAINABLE projection: video, [video | audio] (`model.py:213`) or none (`model.py:209-210`)
+        self.video_dim = {None: 768, "audio_only": 0, "concat": 768 + AUDIO_DIM, "sum": 768, "attention": 768}[self.audio_mode]
 
         self.tok_embeddings = _Embedding(params.vocab_size, d, device, dt, requires_grad=False, std=init_std)
         self.adapter_query = _Embedding(params.adapter_len * params.adapter_layer, d, device, torch.float32, requires_grad=True)
-        self.visual_proj = _TrainableLinear(self.video_dim, d, device)
+        if self.audio_mode != "audio_only":
+            self.visual_proj = _TrainableLinear(self.video_dim, d, device)
+        # frozen extras of the audio variants (the freeze rule `llama_vqa.py:72` does not match their names)
+        if self.audio_mode in ("audio_only", "sum"):
+            self.audio_proj = _FrozenLinear(torch.empty(d, AUDIO_DIM, device=device, dtype=dt).normal_(0, 1.0 / math.sqrt(AUDIO_DIM)))
+        elif self.audio_mode == "attention":
+            self.audio_proj = _FrozenLinear(torch.empty(self.feature_dim, AUDIO_DIM, device=device, dtype=dt).normal_(0, 1.0 / math.sqrt(AUDIO_DIM)))
+            self.video_audio_cross_attn = _CrossAttention(self.feature_dim, device)
+        self._audio_f32 = {}                                # fp32 compute copies of the frozen audio-side weights (repack)
         self.temporal_emb = _Embedding(self.max_feats, d, device, torch.float32, requires_grad=True)
         self.adapter_len = params.adapter_len
         self.adapter_layer = params.adapter_layer
@@ -230,7 +258,7 @@ class Transformer(nn.Module):
         d, hid = self.params.dim, self.hidden_dim
         for name, p in self.named_parameters():
             trainable = any(s in name for s in ("gate", "adapter", "temporal_emb", "visual_proj"))
-            want = torch.float32 if trainable else BF16
+            want = torch.float32 if (trainable or name.startswith("video_audio_cross_attn")) else BF16   # `.float()`, `model.py:227`
             if p.dtype != want or p.device != dev:
                 p.data = p.data.to(device=dev, dtype=want)
         for blk in self.layers:
@@ -253,6 +281,7 @@ class Transformer(nn.Module):
                 attn_norm=blk.attention_norm.weight.data, ffn_norm=blk.ffn_norm.weight.data))
         self._run_weights = run
         self._output_t = self.output.weight.data.t().contiguous()
+        self._audio_f32 = {"audio_proj": self.audio_proj.weight.data.float().contiguous()} if hasattr(self, "audio_proj") else {}
         if self._engine is None:
             self._engine = StepEngine(d, self.params.n_heads, hid, self.params.vocab_size, self.adapter_len, self.max_feats,
                                       self.params.norm_eps, self.tau, self.params.max_seq_len, dev)
@@ -266,7 +295,9 @@ class Transformer(nn.Module):
 
     def trainable_parameters(self):
         n_run = len(self.run_layers())
-        ps = [self.adapter_query.weight, self.visual_proj.weight, self.temporal_emb.weight]
+        # audio only: no trainable projection (`model.py:209-210`); the frozen audio_proj takes its place in the kernels
+        visual = self.visual_proj.weight if self.audio_mode != "audio_only" else self._audio_f32["audio_proj"]
+        ps = [self.adapter_query.weight, visual, self.temporal_emb.weight]
         ps += [blk.attention.gate1 for blk in self.run_layers()]
         ps += [blk.attention.gate2 for blk in self.run_layers()]
         return ps, n_run
@@ -281,7 +312,45 @@ class Transformer(nn.Module):
         if self._pinned is None:
             self._pinned = PinnedPool()
         streams = ["vqa"] if inference else self.streams()
-        return BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned).to_device(self._device)
+        data, post = self._fuse_inputs(data)
+        return post(BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned).to_device(self._device))
+
+    def _fuse_inputs(self, data):
+        """The input-fusion branches of `model.py:306-322` reduced to what the step kernels see: a feature matrix
+        `plan.video` [B*F, video_dim] for the (trainable) projection and an optional frozen additive term `plan.vf_extra`
+        [B*F, d]. Returns (batch dict whose 'video' is that feature matrix where the host can build it, fix-up run on the
+        device-resident plan)."""
+        mode = self.audio_mode
+        if mode is None:
+            return data, (lambda plan: plan)
+        self._ensure_packed()
+        dev, F = self._device, self.max_feats
+        audio = data["audio"].float()                       # `.cuda().half()` in the reference (`model.py:258-261`); kept fp32 here
+        B, Fa = audio.shape[0], audio.shape[1]
+        d2 = dict(data)
+        if mode == "audio_only":                            # `_video_feature = audio_proj(audio)`, `:307`
+            d2["video"] = audio
+            return d2, (lambda plan: plan)
+        if mode == "concat":                                # `visual_proj(cat([video, audio]))`, `:310-311`
+            d2["video"] = torch.cat([data["video"].float(), audio], dim=-1)
+            return d2, (lambda plan: plan)
+        audio_dev = audio.reshape(B * Fa, AUDIO_DIM).to(dev, non_blocking=True)
+        if mode == "sum":                                   # `audio_proj(audio) + visual_proj(video)`, `:314`
+
+            def post(plan):
+                plan.vf_extra = ops.linear_f32(audio_dev, self._audio_f32["audio_proj"])
+                return plan
+            return d2, post
+
+        def post(plan):                                     # 'attention', `:317-320` + CrossAttentionModule `:153-169`
+            ca = self.video_audio_cross_attn
+            af = ops.linear_f32(audio_dev, self._audio_f32["audio_proj"])                        # [B*Fa, 768]
+            q = ops.linear_f32(plan.video, ca.query.weight.data, bias=ca.query.bias.data)
+            k = ops.linear_f32(af, ca.key.weight.data, bias=ca.key.bias.data)
+            v = ops.linear_f32(af, ca.value.weight.data, bias=ca.value.bias.data)
+            plan.video = ops.cross_attn_fwd(q, k, v, B, F, Fa)                                   # input of visual_proj
+            return plan
+        return d2, post
 
     def forward(self, data, inference: bool = False):
         if inference:
@@ -311,7 +380,8 @@ class Transformer(nn.Module):
         """Host side of shared-prefix option scoring (`step.OptionPlan`) + its async H2D copy."""
         if self._pinned is None:
             self._pinned = PinnedPool()
-        return OptionPlan(data, self.max_feats, pool=self._pinned).to_device(self._device)
+        data, post = self._fuse_inputs(data)
+        return post(OptionPlan(data, self.max_feats, pool=self._pinned).to_device(self._device))
 
     @torch.no_grad()
     def inference(self, data):

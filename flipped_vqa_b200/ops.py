@@ -433,3 +433,24 @@ def expand_rows(src: torch.Tensor, idx: torch.Tensor, dst: Optional[torch.Tensor
     assert dst.is_contiguous() and dst.shape[0] == rows
     check(_lib.lib().fvqa_expand_rows(ptr(src), ptr(idx), ptr(dst), rows, row_bytes, stream()), "expand_rows")
     return dst
+
+
+@_timed
+def linear_f32(x2d, w, bias=None, add=None, out=None):
+    """fp32 y = x @ w.T (+ bias) (+ add): the small input-side Linears of the fusion variants (`llama/model.py:306-322`)."""
+    _chk(x2d, torch.float32, "x"); _chk(w, torch.float32, "w")
+    rows, in_dim = x2d.shape
+    dim = w.shape[0]
+    assert w.shape[1] == in_dim
+    out = torch.empty(rows, dim, dtype=torch.float32, device=w.device) if out is None else out
+    check(_lib.lib().fvqa_linear_f32(ptr(x2d), ptr(w), ptr(bias), ptr(add), ptr(out), rows, dim, in_dim, stream()), "linear_f32")
+    return out
+
+
+@_timed
+def cross_attn_fwd(q, k, v, n_samples: int, frames: int, tokens: int):
+    """`CrossAttentionModule.forward` after its Linears (`llama/model.py:161-169`): softmax(q k^T / sqrt(D)) v per sample."""
+    _chk(q, torch.float32, "q"); _chk(k, torch.float32, "k"); _chk(v, torch.float32, "v")
+    out = torch.empty_like(q)
+    check(_lib.lib().fvqa_cross_attn_fwd(ptr(q), ptr(k), ptr(v), ptr(out), n_samples, frames, tokens, q.shape[1], stream()), "cross_attn_fwd")
+    return out

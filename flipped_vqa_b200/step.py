@@ -346,7 +346,8 @@ class StepEngine:
         sv = SavedStep(plan) if save else None
         L = len(layers)
         # --- inputs (`model.py:286-336`)
-        vf32 = ops.visual_proj_fwd(plan.video, visual_w)                           # [B*F, d] fp32
+        # [B*F, d] fp32: visual_proj(features) (+ the frozen audio term of the 'sum' variant, `model.py:306-322`)
+        vf32 = ops.linear_f32(plan.video, visual_w, add=getattr(plan, "vf_extra", None))
         x = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w,
                              n_seq, S, F)
         # Row set of the row-wise ops: all T rows, or the padding-free compact rows (attention always sees all T rows)
@@ -463,7 +464,7 @@ class StepEngine:
         if plan.ce_total == 0 or Tc == 0:
             return tl.view(plan.B, plan.n_opt, S - 1)
         L = len(layers)
-        vf32 = ops.visual_proj_fwd(plan.video, visual_w)
+        vf32 = ops.linear_f32(plan.video, visual_w, add=getattr(plan, "vf_extra", None))
         x_full = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w,
                                   n_seq, S, F)
         x = ops.gather_rows(x_full, plan.c2f)                                       # [Tc, d] fp32 residual stream, compact
@@ -606,7 +607,8 @@ class StepEngine:
             dx = ops.expand_rows(dx, plan.f2c)                                     # [T, d] fp32, zero at the skipped rows
         dvf = ops.build_h0_bwd(dx, plan.vstart, plan.seq_video, plan.qav_index, n_seq, plan.n_video, S, F)
         ops.video_grad_finish(dvf, dvf_qav, plan.n_video, F, dtemporal=grads.temporal)
-        ops.visual_proj_bwd(dvf, plan.video, dwv=grads.visual)
+        if grads.sizes["visual"]:                              # audio only: the projection is frozen (`model.py:209-210`)
+            ops.visual_proj_bwd(dvf, plan.video, dwv=grads.visual)
         return grads
 
 

@@ -129,6 +129,17 @@ int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const 
 /* ---- input embedding + video injection (llama/model.py:286-336). ---------------------------------
  * vproj: vf32[B*F, d] = video[B*F, vdim] * Wv[d, vdim]^T in fp32 (model.py:322). */
 int fvqa_visual_proj_fwd(const float* video, const float* wv, float* vf32, int rows, int dim, int vdim, void* stream);
+/* Generic fp32 Linear y[rows, dim] = x[rows, in_dim] * w[dim, in_dim]^T (+ bias[dim]) (+ add[rows, dim]); bias / add may be
+ * NULL. Used for the input-fusion variants of llama/model.py:306-322: the concatenated [video | audio] projection (:310-311),
+ * the frozen audio projection (:307, :314 with add = nothing / sum of both projections) and the q / k / v Linears (with
+ * bias) of CrossAttentionModule (:148-163). */
+int fvqa_linear_f32(const float* x, const float* w, const float* bias, const float* add, float* y, int rows, int dim, int in_dim,
+                    void* stream);
+/* CrossAttentionModule.forward (llama/model.py:153-169) after its three Linears: out[b, f, :] =
+ * softmax_j(<q[b, f], k[b, j]> / sqrt(dim)) . v[b, j, :] over the `tokens` audio tokens of sample b (tokens <= 64).
+ * q, out [n_samples*frames, dim]; k, v [n_samples*tokens, dim]; fp32. Forward only: everything upstream of visual_proj is frozen. */
+int fvqa_cross_attn_fwd(const float* q, const float* k, const float* v, float* out, int n_samples, int frames, int tokens,
+                        int dim, void* stream);
 /* dWv[d, vdim] = dvf[rows, d]^T * video[rows, vdim] (fp32, overwritten). */
 int fvqa_visual_proj_bwd(const float* dvf, const float* video, float* dwv, int rows, int dim, int vdim, void* stream);
 /* h0[n*S+p, :] for every sequence n:

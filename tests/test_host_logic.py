@@ -61,12 +61,22 @@ def test_load_state_dict_fills_packed_views():
     assert m._pack_token is None            # transposed copies are rebuilt lazily on the next forward
 
 
-def test_audio_variants_are_rejected():
+@pytest.mark.parametrize("mode", ["audio_only", "concat", "sum", "attention"])
+def test_audio_variant_parameters_match_reference_names(mode):
+    """Input-fusion variants (`llama/model.py:209-227`): parameter names / shapes as in the reference, and only the names
+    the substring rule of `llama_vqa.py:72` matches are trainable (audio_proj and the cross-attention stay frozen)."""
     from flipped_vqa_b200.llama import ModelArgs, SyntheticTokenizer, Transformer
-    a = make_args()
-    a.audio = True
-    with pytest.raises(NotImplementedError):
-        Transformer(ModelArgs(**GOLDEN), a, tokenizer=SyntheticTokenizer(256), device="cpu")
+    from tests.util_parity import golden_audio_inputs
+    params, sd, data = golden_audio_inputs(mode)
+    m = Transformer(ModelArgs(**GOLDEN), make_args(audio_mode=mode), tokenizer=SyntheticTokenizer(256), device="cpu")
+    names = {n: tuple(p.shape) for n, p in m.named_parameters()}
+    assert set(names) == set(sd), set(names) ^ set(sd)
+    for n, t in sd.items():
+        assert names[n] == tuple(t.shape), n
+    for n, p in m.named_parameters():
+        assert p.requires_grad == any(s in n for s in ("gate", "adapter", "temporal_emb", "visual_proj")), n
+    assert ("visual_proj.weight" in names) == (mode != "audio_only")
+    assert m.video_dim == {"audio_only": 0, "concat": 768 + 1024, "sum": 768, "attention": 768}[mode]
 
 
 def test_batch_plan_rows_and_targets():

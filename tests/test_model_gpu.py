@@ -12,8 +12,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from oracle import llama_vqa_oracle as O  # noqa: E402  (checker only)
-from tests.util_parity import (GOLDEN, GOLDEN_DIR, GOLDEN_RUN, GRAD_RTOL, LOSS_RTOL, build_product_model, golden_inputs,  # noqa: E402
-                               make_args, product_grads, rel_l2)
+from tests.util_parity import (AUDIO_MODES, GOLDEN, GOLDEN_DIR, GOLDEN_RUN, GRAD_RTOL, LOSS_RTOL, build_product_model,  # noqa: E402
+                               golden_audio_inputs, golden_inputs, make_args, product_grads, rel_l2)
 
 
 def _run_product(model, data, scale=1.0):
@@ -361,3 +361,38 @@ def test_planned_loader_drives_train_and_val(fvqa_lib):
     assert s0["loss"] == s0["loss"]
     v = engine.val_one_epoch(model, PlannedLoader(val, model, inference=True), opt, 0, args=targs)
     assert 0.0 <= v["acc"] <= 1.0
+
+
+@pytest.mark.parametrize("mode", AUDIO_MODES)
+def test_audio_fusion_variants_match_reference_golden(fvqa_lib, mode):
+    """the input-fusion variants of llama/model.py:209-227,306-322 (audio only / concat / sum /
+    cross-attention) through the CUDA path against golden vectors from the unmodified reference."""
+    g = np.load(os.path.join(GOLDEN_DIR, "train_audio_small.npz"))
+    params, sd, data = golden_audio_inputs(mode)
+    r = GOLDEN_RUN
+    model = build_product_model(GOLDEN, sd, make_args(r["max_feats"], r["bias"], r["tau"], audio_mode=mode))
+    losses = _run_product(model, data)
+    ref = g[f"{mode}/gold/loss"]
+    for a, b in zip(losses, ref):
+        assert abs(a - b) / abs(b) < LOSS_RTOL, (losses, ref)
+    grads = product_grads(model)
+    pre = f"{mode}/gold/grad/"
+    ref_grads = {k[len(pre):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre)}
+    assert set(grads) == set(ref_grads) and len(grads) == (6 if mode == "audio_only" else 7)
+
+    def bf16_reference_grads():                   # the reference's op sequence in bf16 on the same inputs: the noise floor
+        st = O.prepare_state(sd, frozen_dtype=torch.bfloat16, device="cuda")
+        ls = O.forward_losses(st, params, data, max_feats=r["max_feats"], tau=r["tau"], audio_mode=mode)
+        sum(ls).backward()
+        return {n: st[n].grad.detach().float().cpu() for n in O.trainable_names(st) if st[n].grad is not None}
+
+    _check_grads(grads, ref_grads, noise_floor=bf16_reference_grads)      # 2e-2 (gates: stacked / 6e-2 per layer, see _check_grads)
+    # option scoring goes through the same fused inputs (`model.py:391-409`)
+    from flipped_vqa_b200.synthetic import synthetic_batch
+    opt = synthetic_batch(r["bsz"], r["seqlen"], GOLDEN["vocab_size"], max_feats=r["max_feats"], seed=9, video_start=r["video_start"], n_options=4)
+    opt["audio"] = data["audio"]
+    if mode == "audio_only":
+        opt.pop("video")
+    tok = model(opt, inference=True)
+    model.share_option_prefix = False
+    assert rel_l2(model(opt, inference=True), tok) < 1e-4
