@@ -33,6 +33,24 @@ class GradSync:
         self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         self.messages += 1
 
+    def warm_up(self, rounds: int = 3):
+        """Set-up, not a step: run the step's exact message pattern (chunk sizes, tail) on a scratch buffer so that NCCL's
+        lazily built channels / proxy connections exist before the first real backward (the first all-reduces of a size
+        class otherwise cost milliseconds on one rank and every other rank waits for it)."""
+        if self.world == 1:
+            return
+        scratch = torch.zeros_like(self.gb.flat)
+        for _ in range(rounds):
+            works = []
+            for l in range(self.L - 1, -1, -1):
+                if l % self.chunk == 0:
+                    hi = min(l + self.chunk, self.L)
+                    works.append(dist.all_reduce(scratch[l * self.A * self.d: hi * self.A * self.d], group=self.group, async_op=True))
+            works.append(dist.all_reduce(scratch[self.gb.late_offset:], group=self.group, async_op=True))
+            for w in works:
+                w.wait()
+        torch.cuda.synchronize()
+
     def layer_done(self, l: int):
         """Called by the backward pass right after layer l's adapter gradient rows were written."""
         if self.world == 1:
@@ -71,6 +89,8 @@ class DataParallel(torch.nn.Module):
         m._ensure_packed()
         if m.grad_sync is None or m.grad_sync.gb is not m._grad_buffers:
             m.grad_sync = GradSync(m._grad_buffers, len(m.run_layers()), m.adapter_len, m.params.dim, self.group, self.chunk_layers)
+            if m._grad_buffers.flat.is_cuda:
+                m.grad_sync.warm_up()
 
     def forward(self, data, inference: bool = False):
         self._attach()
