@@ -358,6 +358,8 @@ def main():
     if not a.no_padfree:
         model._engine.skip_pad_rows = True
         sampled_layers, model._engine.sample_layers = model._engine.sample_layers, ()
+        plans_dense, plans = plans, [model.plan_batch(b) for b in batches]      # with the padding-free row maps
+        torch.cuda.synchronize()
         for i in range(max(a.warmup, 3)):
             step_resident(i)
         ms_p, _, _, _ = timed(step_resident, a.steps)
@@ -365,6 +367,7 @@ def main():
         model._engine.sample_layers = sampled_layers
         rows_p = sum(p.T_c for p in plans) / len(plans)
         n_live_p = sum(p.n_live_k for p in plans) / len(plans)
+        plans = plans_dense
         fl_p = flops_per_step(cfg, n_lab, n_live_p if model._engine.prune_last_layer else None, rows=rows_p)
         padfree = {"value": world * B / (ms_p / a.steps * 1e-3), "unit": "samples/s", "ms_per_step": ms_p / a.steps,
                    "rows_per_step": rows_p, "rows_dense": 3 * B * S, "flops_per_step": fl_p,

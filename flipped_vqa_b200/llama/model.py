@@ -142,8 +142,9 @@ class _StepFn(torch.autograd.Function):
         adapter_w, visual_w, temporal_w = trainables[:3]
         gate1 = [g.view(-1) for g in trainables[3:3 + n_run]]
         gate2 = [g.view(-1) for g in trainables[3 + n_run:3 + 2 * n_run]]
+        akv_pre = model._take_adapter_kv()
         losses, sv = model._engine.forward(plan, model._run_weights, model.tok_embeddings.weight, model.output.weight,
-                                           model.norm.weight, adapter_w, visual_w, temporal_w, gate1, gate2, save=True)
+                                           model.norm.weight, adapter_w, visual_w, temporal_w, gate1, gate2, save=True, akv_pre=akv_pre)
         ctx.model, ctx.sv, ctx.n_run = model, sv, n_run
         ctx.gates = (gate1, gate2)
         ctx.streams = list(plan.streams)
@@ -229,6 +230,7 @@ class Transformer(nn.Module):
         self.last_plan: Optional[BatchPlan] = None
         self._pinned: Optional[PinnedPool] = None
         self.share_option_prefix = True                     # validation: shared-prefix option scoring (step.OptionPlan)
+        self._akv_pre = None                                # adapter K|V enqueued ahead of host planning (forward(data))
 
     # ------------------------------------------------------------------ weight layout
     def run_layers(self):
@@ -313,7 +315,8 @@ class Transformer(nn.Module):
             self._pinned = PinnedPool()
         streams = ["vqa"] if inference else self.streams()
         data, post = self._fuse_inputs(data)
-        return post(BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned).to_device(self._device))
+        compact = self._engine is not None and self._engine.skip_pad_rows        # padding-free row maps only when they are used
+        return post(BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned, compact=compact).to_device(self._device))
 
     def _fuse_inputs(self, data):
         """The input-fusion branches of `model.py:306-322` reduced to what the step kernels see: a feature matrix
@@ -356,7 +359,18 @@ class Transformer(nn.Module):
         if inference:
             return self.inference(data)
         self._ensure_packed()
+        self._prefetch_adapter_kv()                         # GPU work that does not need the batch, enqueued before host planning
         return self.forward_plan(self.plan_batch(data))
+
+    def _prefetch_adapter_kv(self):
+        w = self.adapter_query.weight
+        self._akv_pre = ((w.data_ptr(), w._version), self._engine.adapter_kv(self._run_weights, w.data))
+
+    def _take_adapter_kv(self):
+        """The prefetched adapter K|V if it was computed from the current adapter weights, else None (computed in-loop)."""
+        pre, self._akv_pre = self._akv_pre, None
+        w = self.adapter_query.weight
+        return pre[1] if pre is not None and pre[0] == (w.data_ptr(), w._version) else None
 
     def forward_plan(self, plan: BatchPlan):
         """The device side of the training step for an already device-resident batch plan."""
@@ -370,9 +384,10 @@ class Transformer(nn.Module):
         else:
             g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]
             g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
+            akv_pre = self._take_adapter_kv()
             losses, _ = self._engine.forward(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
                                              self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
-                                             g1, g2, save=False)
+                                             g1, g2, save=False, akv_pre=akv_pre)
         zero = lambda: torch.tensor([0], device=dev)        # disabled objectives, `model.py:302`
         return losses["vqa"], losses.get("vaq", zero()), losses.get("qav", zero())
 
@@ -389,6 +404,7 @@ class Transformer(nn.Module):
         (`model_my_original_mod.py:281,332-333,348-360,375-377,506`). With `share_option_prefix` (default) the
         option-invariant prefix of each sample is evaluated once (`step.OptionPlan`); the per-token losses are the same."""
         self._ensure_packed()
+        self._prefetch_adapter_kv()
         return self.inference_plan(self.plan_options(data) if self.share_option_prefix else self.plan_batch(data, inference=True))
 
     @torch.no_grad()
@@ -401,9 +417,10 @@ class Transformer(nn.Module):
         g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
         w = (self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data, self.norm.weight.data,
              trainables[0].data, trainables[1].data, trainables[2].data, g1, g2)
+        akv_pre = self._take_adapter_kv()
         if isinstance(plan, OptionPlan):
-            return self._engine.forward_options(plan, *w)
-        tok, _ = self._engine.forward(plan, *w, save=False, token_losses=True)
+            return self._engine.forward_options(plan, *w, akv_pre=akv_pre)
+        tok, _ = self._engine.forward(plan, *w, save=False, token_losses=True, akv_pre=akv_pre)
         return tok
 
     @staticmethod

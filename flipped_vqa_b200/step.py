@@ -29,7 +29,8 @@ class BatchPlan:
     """Host-side (CPU) preparation of one batch. Everything the kernels need is packed into ONE
     pinned int32 buffer (one H2D copy) plus the fp32 video features."""
 
-    def __init__(self, data: Dict, streams: List[str], max_feats: int, inference: bool = False, pool: "PinnedPool" = None):
+    def __init__(self, data: Dict, streams: List[str], max_feats: int, inference: bool = False, pool: "PinnedPool" = None,
+                 compact: bool = True):
         F = max_feats
         ids = {k: _cpu(data["text_id"][k]) for k in streams}
         lab = {k: _cpu(data["label"][k]) for k in streams}
@@ -78,23 +79,26 @@ class BatchPlan:
         self.n_live = int(live.numel())
         ce_rows_c = torch.searchsorted(live, ce_rows.long()).to(I32)
         q_rows_c = torch.searchsorted(live, q_rows.long()).to(I32)
-        # padding-free row set: rows after the last loss-relevant position of a sequence cannot reach any loss through the
-        # causal mask (`model.py:298-299`), so the row-wise ops only need rows [0, end_n) of sequence n ("k" = kept rows).
-        loss_rows = torch.cat([ce_rows.long(), q_rows.long()])
-        end = torch.zeros(self.n_seq, dtype=torch.long)
-        if loss_rows.numel():
-            end.scatter_reduce_(0, loss_rows // S, loss_rows % S + 1, reduce="amax")
-        keep = (torch.arange(S).view(1, S) < end.view(-1, 1)).reshape(-1)
-        c2f = keep.nonzero().flatten()
-        self.T_c = int(c2f.numel())
-        f2c = torch.full((self.T,), -1, dtype=torch.long)
-        f2c[c2f] = torch.arange(self.T_c)
-        ce_rows_k, q_rows_k = f2c[ce_rows.long()], f2c[q_rows.long()]
-        live_k = torch.unique(torch.cat([ce_rows_k, q_rows_k]), sorted=True)
-        self.n_live_k = int(live_k.numel())
         parts = [ids_all.flatten(), labels_all.flatten(), vstart, seq_video, qav_index.flatten(),
-                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid, live.to(I32), ce_rows_c, q_rows_c,
-                 c2f % S, c2f, f2c, ce_rows_k, q_rows_k, live_k, torch.searchsorted(live_k, ce_rows_k), torch.searchsorted(live_k, q_rows_k)]
+                 ce_rows, ce_tgt, ce_dst, q_rows, q_tgt, q_vid, live.to(I32), ce_rows_c, q_rows_c]
+        # padding-free row set (only built when the engine will use it: `StepEngine.skip_pad_rows`): rows after the last
+        # loss-relevant position of a sequence cannot reach any loss through the causal mask (`model.py:298-299`), so the
+        # row-wise ops only need rows [0, end_n) of sequence n ("k" = kept rows).
+        self.T_c = None
+        if compact:
+            loss_rows = torch.cat([ce_rows.long(), q_rows.long()])
+            end = torch.zeros(self.n_seq, dtype=torch.long)
+            if loss_rows.numel():
+                end.scatter_reduce_(0, loss_rows // S, loss_rows % S + 1, reduce="amax")
+            keep = (torch.arange(S).view(1, S) < end.view(-1, 1)).reshape(-1)
+            c2f = keep.nonzero().flatten()
+            self.T_c = int(c2f.numel())
+            f2c = torch.full((self.T,), -1, dtype=torch.long)
+            f2c[c2f] = torch.arange(self.T_c)
+            ce_rows_k, q_rows_k = f2c[ce_rows.long()], f2c[q_rows.long()]
+            live_k = torch.unique(torch.cat([ce_rows_k, q_rows_k]), sorted=True)
+            self.n_live_k = int(live_k.numel())
+            parts += [c2f % S, c2f, f2c, ce_rows_k, q_rows_k, live_k, torch.searchsorted(live_k, ce_rows_k), torch.searchsorted(live_k, q_rows_k)]
         sizes = [p.numel() for p in parts]
         total = max(sum(sizes), 1)
         video = _cpu(data["video"]).reshape(B * F, -1).float()
@@ -337,9 +341,19 @@ class StepEngine:
         self.skip_pad_rows = False
         self.skip_pad_min_saving = 0.06
 
+    # -------------------------------------------------------------------------------- batch-independent prologue
+    def adapter_kv(self, layers: List[LayerWeights], adapter_w):
+        """Adapter K|V of every layer, `wk/wv(adapter)` (`model.py:99-100`): the only part of the step that does not depend
+        on the batch. `Transformer.forward(data)` enqueues it BEFORE it builds the batch plan on the host, so the GPU has
+        ~1 ms of work while the host flattens ids / labels and starts the H2D copy (instead of idling after the previous
+        step's loss read). Same kernels and values as the in-loop computation."""
+        A, d = self.A, self.d
+        adapter_bf16 = ops.f32_to_bf16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
+        return [ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:]) for l, w in enumerate(layers)]
+
     # -------------------------------------------------------------------------------- forward
     def forward(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
-                gate1: List[torch.Tensor], gate2: List[torch.Tensor], save: bool, token_losses: bool = False):
+                gate1: List[torch.Tensor], gate2: List[torch.Tensor], save: bool, token_losses: bool = False, akv_pre=None):
         """Returns (losses dict of 0-dim fp32 device tensors | per-token loss tensor, SavedStep|None)."""
         d, H, hd, hid, A, F, S = self.d, self.H, self.hd, self.hid, self.A, self.F, plan.S
         T, n_seq, dev = plan.T, plan.n_seq, self.device
@@ -351,7 +365,7 @@ class StepEngine:
         x = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w,
                              n_seq, S, F)
         # Row set of the row-wise ops: all T rows, or the padding-free compact rows (attention always sees all T rows)
-        compact = self.skip_pad_rows and 0 < plan.T_c <= (1.0 - self.skip_pad_min_saving) * T
+        compact = self.skip_pad_rows and plan.T_c is not None and 0 < plan.T_c <= (1.0 - self.skip_pad_min_saving) * T
         R = plan.T_c if compact else T
         if compact:
             x = ops.gather_rows(x, plan.c2f)
@@ -360,7 +374,7 @@ class StepEngine:
         else:
             ce_full, q_full, live_rows, ce_live, q_live, n_live = (plan.ce_rows, plan.q_rows, plan.live_rows, plan.ce_rows_c,
                                                                    plan.q_rows_c, plan.n_live)
-        adapter_bf16 = ops.f32_to_bf16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
+        akv_all = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)   # adapter K|V, no RoPE (`model.py:99-100`)
         xn = torch.empty(R, d, dtype=BF16, device=dev)
         c = torch.empty(R, hid, dtype=BF16, device=dev)
         qkv_b = o_b = g_b = None
@@ -380,7 +394,7 @@ class StepEngine:
                 qkv = ops.expand_rows(qkv_c, plan.f2c, dst=None if save else qkv_b)  # full layout (zero rows past the end)
             else:
                 qkv = ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=None if save else qkv_b)
-            akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])          # adapter K|V, no RoPE (`model.py:99-100`)
+            akv = akv_all[l]
             o_full, lse = ops.attn_fwd(qkv, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F,
                                        out=None if save else o_b)
             o = ops.gather_rows(o_full, plan.c2f, dst=o_c) if compact else o_full
@@ -454,7 +468,7 @@ class StepEngine:
 
     # -------------------------------------------------------------------------------- option scoring, shared prefix
     def forward_options(self, plan: "OptionPlan", layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
-                        gate1: List[torch.Tensor], gate2: List[torch.Tensor]):
+                        gate1: List[torch.Tensor], gate2: List[torch.Tensor], akv_pre=None):
         """Per-token VQA losses [B, n_opt, S-1] (`model_my_original_mod.py:375-377`) with the option-invariant prefix of
         each sample evaluated once: every row-wise op (norms, the 7 frozen GEMMs per layer, SwiGLU, residuals) runs on
         `plan`'s compact ragged rows; attention runs on the full [B * n_opt, S] layout rebuilt by a q|k|v row gather."""
@@ -469,7 +483,7 @@ class StepEngine:
                                   n_seq, S, F)
         x = ops.gather_rows(x_full, plan.c2f)                                       # [Tc, d] fp32 residual stream, compact
         del x_full
-        adapter_bf16 = ops.f32_to_bf16(adapter_w)
+        akv_all = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)
         xn = torch.empty(Tc, d, dtype=BF16, device=dev)
         qkv_c = torch.empty(Tc, 3 * d, dtype=BF16, device=dev)
         qkv_f = torch.empty(plan.T, 3 * d, dtype=BF16, device=dev)
@@ -484,7 +498,7 @@ class StepEngine:
             ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
             ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_c, pos_ids=plan.pos_ids)
             ops.expand_rows(qkv_c, plan.f2c, dst=qkv_f)                             # compact -> every option's sequence, zero rows past E_b
-            akv = ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:])
+            akv = akv_all[l]
             ops.attn_fwd(qkv_f, akv, self.cos, self.sin, gate1[l], gate2[l], plan.vstart, n_seq, S, H, hd, A, F, out=o_f, lse=lse)
             if prune and l == L - 1:
                 o_g = ops.gather_rows(ops.gather_rows(o_f, plan.c2f, dst=o_c), plan.live_rows)
