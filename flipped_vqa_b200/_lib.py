@@ -32,6 +32,7 @@ _SIGNATURES = {
     "fvqa_gemm_bf16_nt": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
     "fvqa_gemm_bf16_nt_rope": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p],
     "fvqa_gemm_bf16_nt_rope_pos": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p],
+    "fvqa_gemm_skinny_grouped": [_p, _i64, _i, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_debug_force_bn": [_i],

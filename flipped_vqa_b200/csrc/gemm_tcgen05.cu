@@ -731,6 +731,8 @@ static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, 
 bool gemm_skinny_supported(int M, int K, const void* R);
 int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
                 cudaStream_t stream);
+int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, const bf16* const* Bptrs, int ldb, void* C, long strideC,
+                        int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream);
 
 // ---- CTA-pair path ---------------------------------------------------------------------------
 static int g_l2_hints = 0;         // test hook (fvqa_gemm_debug_l2_hints)
@@ -839,6 +841,21 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
   }
   return out_fp32 ? launch_gemm<256, true, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s)
                   : launch_gemm<256, false, false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
+}
+
+/* Grouped skinny GEMM (M <= 16): C_g[M,N] = A_g[M,K] * B_g[N,K]^T for g < groups in ONE launch; see include/fvqa.h. */
+extern "C" int fvqa_gemm_skinny_grouped(const fvqa_bf16* A, int64_t strideA, int lda, const void* const* B_ptrs_dev, int ldb, void* C,
+                                        int64_t strideC, int ldc, int M, int N, int K, int groups, int out_fp32, void* stream) {
+  FVQA_REQUIRE(g_encode != nullptr, FVQA_ERR_INVALID_ARG, "fvqa_init() has not been called");
+  FVQA_REQUIRE(M > 0 && M <= 16 && N > 0 && K > 0 && groups > 0 && groups <= 65535, FVQA_ERR_INVALID_ARG,
+               "gemm_skinny_grouped: M=%d (<= 16) N=%d K=%d groups=%d", M, N, K, groups);
+  FVQA_REQUIRE(gemm_skinny_supported(M, K, nullptr) && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && strideA % 8 == 0, FVQA_ERR_UNSUPPORTED,
+               "gemm_skinny_grouped: K=%d must be a multiple of 256, N / lda / ldb / strideA multiples of 8", K);
+  FVQA_REQUIRE(A != nullptr && B_ptrs_dev != nullptr && C != nullptr && lda >= K && ldb >= K && ldc >= N, FVQA_ERR_INVALID_ARG,
+               "gemm_skinny_grouped: null pointer or leading dimension too small");
+  return gemm_skinny_grouped(reinterpret_cast<const bf16*>(A), static_cast<long>(strideA), lda, nullptr,
+                             reinterpret_cast<const bf16* const*>(B_ptrs_dev), ldb, C, static_cast<long>(strideC), ldc, M, N, K, groups,
+                             out_fp32, g_num_sms, static_cast<cudaStream_t>(stream));
 }
 
 static int gemm_rope_impl(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N, int K,

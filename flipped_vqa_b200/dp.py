@@ -89,6 +89,7 @@ class DataParallel(torch.nn.Module):
         m._ensure_packed()
         if m.grad_sync is None or m.grad_sync.gb is not m._grad_buffers:
             m.grad_sync = GradSync(m._grad_buffers, len(m.run_layers()), m.adapter_len, m.params.dim, self.group, self.chunk_layers)
+            m._engine.adapter_grad_chunk = self.chunk_layers    # adapter gradient rows become final in the chunks GradSync reduces
             if m._grad_buffers.flat.is_cuda:
                 m.grad_sync.warm_up()
 

@@ -454,3 +454,15 @@ def cross_attn_fwd(q, k, v, n_samples: int, frames: int, tokens: int):
     out = torch.empty_like(q)
     check(_lib.lib().fvqa_cross_attn_fwd(ptr(q), ptr(k), ptr(v), ptr(out), n_samples, frames, tokens, q.shape[1], stream()), "cross_attn_fwd")
     return out
+
+
+@_timed
+def gemm_skinny_grouped(a: torch.Tensor, b_ptrs: torch.Tensor, ldb: int, N: int, out: torch.Tensor) -> torch.Tensor:
+    """out[g] = a[g] @ B_g^T for every group in one launch. a [G, M<=16, K] bf16 contiguous; b_ptrs int64 device tensor of G
+    weight-block pointers ([N, K] bf16 each, leading dimension ldb); out [G, M, N] bf16 or fp32 contiguous."""
+    _chk(a, BF16, "a"); _chk(b_ptrs, torch.int64, "b_ptrs")
+    G, M, K = a.shape
+    assert out.is_contiguous() and tuple(out.shape) == (G, M, N) and out.dtype in (BF16, torch.float32) and b_ptrs.numel() >= G
+    check(_lib.lib().fvqa_gemm_skinny_grouped(ptr(a), M * K, K, ptr(b_ptrs), ldb, ptr(out), M * N, N, M, N, K, G,
+                                              1 if out.dtype == torch.float32 else 0, stream()), "gemm_skinny_grouped")
+    return out

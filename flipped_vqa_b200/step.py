@@ -330,6 +330,8 @@ class StepEngine:
         self.cos = torch.cos(ang).to(device).contiguous()
         self.sin = torch.sin(ang).to(device).contiguous()
         self._attn_ws = None
+        self._tables = None
+        self.adapter_grad_chunk = 8  # layers per grouped d-adapter GEMM = layers per early all-reduce message (dp.GradSync)
         self.sample_layers = ()      # layers whose GEMM launches bench.py's GemmTimer samples
         # wo / FFN of the last layer only on the rows the losses read: -2.1 % FLOPs, -1.8 % step time in a same-box A/B
         # (tools/ab_step.py); results identical (tests/test_model_gpu.py::test_last_layer_live_row_pruning_is_equivalent)
@@ -347,9 +349,27 @@ class StepEngine:
         on the batch. `Transformer.forward(data)` enqueues it BEFORE it builds the batch plan on the host, so the GPU has
         ~1 ms of work while the host flattens ids / labels and starts the H2D copy (instead of idling after the previous
         step's loss read). Same kernels and values as the in-loop computation."""
-        A, d = self.A, self.d
+        A, d, L = self.A, self.d, len(layers)
         adapter_bf16 = ops.f32_to_bf16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
-        return [ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:]) for l, w in enumerate(layers)]
+        tables = self._weight_tables(layers)
+        if tables is None:                                                          # small / odd dims: one skinny GEMM per layer
+            return [ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:]) for l, w in enumerate(layers)]
+        akv_all = torch.empty(L, A, 2 * d, dtype=BF16, device=self.device)
+        ops.gemm_skinny_grouped(adapter_bf16.view(L, A, d), tables[0], d, 2 * d, akv_all)   # all layers, one launch (2.1 GB of Wk|Wv at 7B)
+        return [akv_all[l] for l in range(L)]
+
+    def _weight_tables(self, layers: List[LayerWeights]):
+        """Device pointer tables of the per-layer [Wk; Wv] blocks and their transposes for the grouped skinny GEMM
+        (None when the shape is outside its range). Cached per packed-weight list; the weights are frozen."""
+        if self.A > 16 or self.d % 256 != 0 or not layers:
+            return None
+        key = (id(layers), layers[0].wqkv.data_ptr(), layers[-1].wqkv_t.data_ptr())
+        if self._tables is None or self._tables[0] != key:
+            d = self.d
+            kv = torch.tensor([w.wqkv[d:].data_ptr() for w in layers], dtype=torch.int64, device=self.device)
+            kv_t = torch.tensor([w.wqkv_t[:, d:].data_ptr() for w in layers], dtype=torch.int64, device=self.device)
+            self._tables = (key, (kv, kv_t))
+        return self._tables[1]
 
     # -------------------------------------------------------------------------------- forward
     def forward(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
@@ -574,6 +594,8 @@ class StepEngine:
         dqkv = torch.empty(T, 3 * d, dtype=BF16, device=dev)
         dakv = torch.empty(A, 2 * d, dtype=torch.float32, device=dev)
         dakv_bf = torch.empty(A, 2 * d, dtype=BF16, device=dev)
+        tables, chunk = self._weight_tables(layers), max(1, self.adapter_grad_chunk)
+        dakv_bf_all = torch.empty(L, A, 2 * d, dtype=BF16, device=dev) if tables is not None else None
         dx_next = torch.empty(Tr, d, dtype=torch.float32, device=dev)
         dx_next_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
         do_full = torch.empty(T, d, dtype=BF16, device=dev) if compact else None
@@ -607,9 +629,16 @@ class StepEngine:
             dqkv_r = ops.gather_rows(dqkv, plan.c2f, dst=dqkv_c) if compact else dqkv
             ops.gemm_nt(dqkv_r, w.wqkv_t, out=dtmp)                                # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
             ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next, dx_bf16=dx_next_bf)
-            # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l)
-            ops.f32_to_bf16(dakv, dakv_bf)
-            ops.gemm_nt(dakv_bf, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
+            # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l): one grouped launch
+            # per chunk of layers (their rows then become final together, which is what dp.GradSync reduces early)
+            if tables is None:
+                ops.f32_to_bf16(dakv, dakv_bf)
+                ops.gemm_nt(dakv_bf, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
+            else:
+                ops.f32_to_bf16(dakv, dakv_bf_all[l])
+                if l % chunk == 0:
+                    hi = min(l + chunk, L)
+                    ops.gemm_skinny_grouped(dakv_bf_all[l:hi], tables[1][l:hi], 3 * d, d, grads.adapter.view(L, A, d)[l:hi])
             dx, dx_next = dx_next, dx
             dx_bf, dx_next_bf = dx_next_bf, dx_bf
             if on_layer_done is not None:

@@ -79,6 +79,14 @@ int fvqa_gemm_bf16_nt_rope_pos(const fvqa_bf16* A, int lda, const fvqa_bf16* B, 
                                int M, int N, int K, const float* rope_cos, const float* rope_sin,
                                int rope_cols, int hd, const int32_t* pos_ids, void* stream);
 
+/* Grouped skinny GEMM for the adapter-prompt projections of ALL layers in one launch (llama/model.py:99-100 `wk/wv(adapter)` and
+ * its backward d adapter = dK_a Wk + dV_a Wv): C_g[M,N] = A_g[M,K] * B_g[N,K]^T, g < groups, M <= 16, K % 256 == 0.
+ * A_g = A + g*strideA, C_g = C + g*strideC (strides in elements of the respective type); B_g = B_ptrs_dev[g], a DEVICE array of
+ * `groups` device pointers (the per-layer weight blocks are separate allocations), each with leading dimension ldb. HBM-bound:
+ * 2*N*K bytes per group. */
+int fvqa_gemm_skinny_grouped(const fvqa_bf16* A, int64_t strideA, int lda, const void* const* B_ptrs_dev, int ldb, void* C,
+                             int64_t strideC, int ldc, int M, int N, int K, int groups, int out_fp32, void* stream);
+
 /* SwiGLU fused into the GEMM epilogues (llama/model.py:142 `w2(silu(w1 x) * w3 x)` and its backward):
  *  fwd: G[M, 2*hid] = X[M,K] * W13[2*hid, K]^T (bf16, saved for backward; W13 = [W1; W3]) and
  *       C[M, hid] = silu(G[:, :hid]) * G[:, hid:], bit-identical to fvqa_gemm_bf16_nt + fvqa_swiglu_fwd. hid % 128 == 0.

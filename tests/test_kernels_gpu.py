@@ -102,6 +102,25 @@ def test_gemm_nt(fvqa_lib, M, N, K):
     assert relerr(cr32, ref + r32) < 2e-4
 
 
+@pytest.mark.parametrize("G,M,N,K,f32", [(5, 10, 512, 256, False), (32, 10, 1024, 512, False), (8, 10, 512, 1024, True), (3, 16, 264, 256, True)])
+def test_gemm_skinny_grouped(fvqa_lib, G, M, N, K, f32):
+    """One launch for the adapter projections of all layers: C_g = A_g B_g^T with the weight blocks B_g in separate
+    allocations (device pointer table) and strided views (ldb > K, as the [Wk; Wv] rows of the packed Wqkv^T)."""
+    from flipped_vqa_b200 import ops
+    a = bf16_randn(G * M, K, seed=70).view(G, M, K)
+    ldb = K + 64
+    blocks = [bf16_randn(N, ldb, std=0.05, seed=71 + g) for g in range(G)]
+    ptrs = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device="cuda")
+    out = torch.full((G + 1, M, N), 7.0, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    ops.gemm_skinny_grouped(a, ptrs, ldb, N, out[:G])
+    assert torch.all(out[G].float() == 7.0)
+    for g in range(G):
+        ref = a[g].float() @ blocks[g][:, :K].float().t()
+        assert relerr(out[g], ref) < (2e-4 if f32 else 5e-3), g
+        single = ops.gemm_nt(a[g], blocks[g][:, :K], out_fp32=f32)            # the per-layer launch it replaces
+        assert torch.equal(single, out[g]), g
+
+
 @pytest.mark.parametrize("bn", [-1, 64, 128, 144, 176, 208, 240, 256])
 def test_gemm_pair_tile_widths(fvqa_lib, bn):
     """The CTA-pair (cta_group::2) kernel for every runtime tile width (and the single-CTA kernel, bn=-1)
