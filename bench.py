@@ -400,7 +400,7 @@ def main():
         }
         if gemm is not None:
             tr = gemm_traffic() if a.config == "7b-nextqa" else None
-            line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_nt_pair_kernel (tcgen05.mma.cta_group::2, TMA, TMEM)", "achieved": gemm["tflops"],
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_nt_pair_kernel (tcgen05.mma.cta_group::2, TMA, TMEM; 2x2-cluster TMA-multicast variant on the N = 4096 GEMMs)", "achieved": gemm["tflops"],
                                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm["tflops"] / peaks["bf16_tflops_sustained"],
                                 "frac_of_burst_peak": gemm["tflops"] / peaks["bf16_tflops"], "peak_kind": f"{peaks['source']} sustained (kernel timed inside a long step)",
                                 "traffic": (tr["avg_dram_bytes_per_launch"] if tr else None),

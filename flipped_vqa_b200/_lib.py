@@ -36,6 +36,8 @@ _SIGNATURES = {
     "fvqa_gemm_swiglu_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_debug_force_bn": [_i],
+    "fvqa_gemm_debug_quad": [_i],
+    "fvqa_gemm_quad_clusters": [],
     "fvqa_gemm_debug_epilogue_warps": [_i],
     "fvqa_gemm_debug_l2_hints": [_i],
     "fvqa_attn_debug_use_tc": [_i],

@@ -287,6 +287,19 @@ __device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t ades
 }
 // arrives (once all previously issued MMAs of this thread completed) on the barrier at the same
 // offset in BOTH CTAs of the pair
+// multicast variant (cluster of two CTA pairs): the box lands at the same shared-memory offset in every CTA of `mask`; each
+// destination's bytes are credited to the barrier at the given offset in the LEADER (even-ranked) CTA of the destination's
+// pair (the address carries the leader's rank: peer bit cleared).
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t smem_dst, const void* tmap, uint32_t cluster_bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(cluster_bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair_mask(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");

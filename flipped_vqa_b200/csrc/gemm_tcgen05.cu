@@ -266,8 +266,14 @@ constexpr int PAIR_SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA
 
 __host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GEMM_BK * 2 + (bn / 2) * GEMM_BK * 2; }
 
-template <bool OUT_F32, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
+// QUAD: a cluster of TWO CTA pairs (4 CTAs) owns a 256 x 2 BN output block: both pairs work on the same 256 rows and on
+// adjacent column tiles, so CTA r and CTA r^2 need the same 128 x 64 A slice per k-block: each loads HALF of it (64 rows)
+// and TMA-multicasts it to both (-25 % L2 -> SM operand bytes; the pair kernel sits on the L2 throughput cap, and this is
+// what cuBLAS's 2x2-cluster kernels do on the N = 4096 shapes). A stage is free once BOTH pairs' MMAs have consumed it
+// (the partner pair writes into it), hence two arrivals on empty[s], committed to all four CTAs. Only 33 four-CTA
+// clusters fit the chip (132 of 148 SMs, profiles/r1_cluster_occupancy.txt).
+template <bool OUT_F32, int EPI, bool QUAD = false>
+__global__ void __cluster_dims__(QUAD ? 4 : 2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages, int l2_hints) {
   extern __shared__ uint8_t smem_raw[];
@@ -283,14 +289,19 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t crank = cluster_ctarank();           // rank in the cluster: 0..1, or 0..3 (QUAD)
+  const uint32_t rank = crank & 1u;                   // CTA within its pair; 0 = the pair's MMA leader
+  const uint32_t leader = crank & ~1u;                // cluster rank of this pair's leader
+  const int cq = QUAD ? static_cast<int>(crank >> 1) : 0;   // pair within the cluster
+  // scheduling unit: a pair and its tile, or (QUAD) a cluster and its two column-adjacent tiles
+  const int pair = QUAD ? blockIdx.x >> 2 : blockIdx.x >> 1, n_pairs = QUAD ? gridDim.x >> 2 : gridDim.x >> 1;
   constexpr bool ROPE = (EPI == EPI_ROPE);
   const int tiles_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
   // EPI_SWIGLU_FWD: B = [W1; W3] (2*hid rows); tile tn pairs W1 rows [128 tn, +128) (CTA 0's half of B)
   // with W3 rows [128 tn, +128) (CTA 1's half) so that a row's a- and b-values meet in one accumulator.
   const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + BN - 1) / BN;
-  const int num_tiles = tiles_m * tiles_n;
+  const int num_tiles = QUAD ? tiles_m * (tiles_n >> 1) : tiles_m * tiles_n;     // scheduling units (QUAD: tiles_n is even)
+  auto tile_of = [&](int unit) { return QUAD ? (unit % tiles_m) + tiles_m * (2 * (unit / tiles_m) + cq) : unit; };
   const int num_kb = K / GEMM_BK;
 
   if (warp == 0 && lane == 0) {
@@ -300,7 +311,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < stages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), QUAD ? 2 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -322,7 +333,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      for (int unit = pair; unit < num_tiles; unit += n_pairs) {
+        const int tile = tile_of(unit);
         const int m0 = (tile % tiles_m) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
         const int n0 = (EPI == EPI_SWIGLU_FWD) ? (tile / tiles_m) * 128 + static_cast<int>(rank) * epi.hid
                                                : (tile / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
@@ -330,9 +342,15 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + GEMM_BM * GEMM_BK * 2;
-          const uint32_t lfull = mapa_shared(full_bar(stage), 0);
+          const uint32_t lfull = mapa_shared(full_bar(stage), leader);
           if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2u * stage_bytes);
-          if (l2_hints) {      // weights stream through once per wave; the activation operand is re-read by every tile column
+          if constexpr (QUAD) {
+            // my half (64 rows) of the A slice I share with CTA crank ^ 2, multicast to both of us; B is this pair's own
+            constexpr uint32_t kHalf = (GEMM_BM / 2) * GEMM_BK * 2;
+            tma_load_2d_pair_mc(sa + cq * kHalf, &tmap_a, lfull, kb * GEMM_BK, m0 + cq * (GEMM_BM / 2),
+                                static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2u))));
+            tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+          } else if (l2_hints) {      // weights stream through once per wave; the activation operand is re-read by every tile column
             tma_load_2d_pair_hint(sa, &tmap_a, lfull, kb * GEMM_BK, m0, L2_EVICT_LAST);
             tma_load_2d_pair_hint(sb, &tmap_b, lfull, kb * GEMM_BK, n0, L2_EVICT_FIRST);
           } else {
@@ -351,7 +369,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      for (int unit = pair; unit < num_tiles; unit += n_pairs) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -367,10 +385,10 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                               (kb > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit_pair(empty_bar(stage));
+          umma_commit_pair_mask(empty_bar(stage), QUAD ? 0xF : 0x3);                       // QUAD: the partner pair writes into this stage too
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit_pair(tfull_bar(acc));
+        umma_commit_pair_mask(tfull_bar(acc), static_cast<uint16_t>(0x3u << leader));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -390,7 +408,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int nch = n32 + ((BN & 16) ? 1 : 0);            // 32-column chunks incl. a 16-column tail
     const int c_begin = (split && half) ? (nch + 1) >> 1 : 0;
     const int c_end = (split && !half) ? (nch + 1) >> 1 : nch;
-    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+    for (int unit = pair; unit < num_tiles; unit += n_pairs) {
+      const int tile = tile_of(unit);
       const int m0 = (tile % tiles_m) * (2 * GEMM_BM) + static_cast<int>(rank) * GEMM_BM;
       const int n0 = (tile / tiles_m) * BN;
       const int row = m0 + quad * 32 + lane;
@@ -575,7 +594,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), leader));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -596,6 +615,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
+static int g_quad_clusters = 0;   // co-resident 4-CTA clusters of the QUAD GEMM (33 on a B200: 132 of 148 SMs); 0 = unavailable
+static int g_quad_mode = 1;       // fvqa_gemm_debug_quad: 0 = never, 1 = heuristic (default), 2 = every eligible plain GEMM
 static std::mutex g_mu;
 
 struct MapKey {
@@ -658,6 +679,26 @@ int gemm_init() {
   FVQA_SET_PAIR(false, EPI_SWIGLU_FWD)
   FVQA_SET_PAIR(false, EPI_SWIGLU_BWD)
 #undef FVQA_SET_PAIR
+  // 2x2-cluster (QUAD) variants of the plain-epilogue kernel: opt-in shared memory, and how many 4-CTA clusters fit the chip
+  {
+    auto kq16 = gemm_bf16_nt_pair_kernel<false, EPI_PLAIN, true>;
+    auto kq32 = gemm_bf16_nt_pair_kernel<true, EPI_PLAIN, true>;
+    e = cudaFuncSetAttribute(kq16, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kq32, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
+    FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm quad): %s", cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * (g_num_sms / 4));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = PAIR_SMEM_LIMIT;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = 4; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kq16, &cfg) == cudaSuccess && n > 0) g_quad_clusters = n;
+    (void)cudaGetLastError();
+  }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return FVQA_OK;
 }
@@ -783,6 +824,39 @@ static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void
   return check_launch("gemm_bf16_nt_pair");
 }
 
+// 2x2-cluster multicast variant (plain epilogue, BN = 256, an even number of column tiles)
+template <bool OUT_F32>
+static int launch_gemm_quad(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M, int N, int K,
+                            cudaStream_t stream) {
+  constexpr int bn = 256;
+  CUtensorMap ta, tb;
+  int rc = get_tmap(A, M, K, lda, GEMM_BM / 2, &ta);          // 64-row boxes: each CTA loads half of the slice it shares
+  if (rc) return rc;
+  rc = get_tmap(B, N, K, ldb, bn / 2, &tb);
+  if (rc) return rc;
+  const int stage_bytes = pair_stage_bytes(bn);
+  int stages = (PAIR_SMEM_LIMIT - 1024 - PAIR_BAR_BYTES) / stage_bytes;
+  if (stages > PAIR_MAX_STAGES) stages = PAIR_MAX_STAGES;
+  const int smem = stages * stage_bytes + PAIR_BAR_BYTES + 1024;
+  const int units = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * (N / (2 * bn));
+  const int clusters = units < g_quad_clusters ? units : g_quad_clusters;
+  gemm_bf16_nt_pair_kernel<OUT_F32, EPI_PLAIN, true><<<4 * clusters, PAIR_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, 0);
+  return check_launch("gemm_bf16_nt_quad");
+}
+// Used when the pair schedule would end in a clearly partial wave and the cluster schedule does not (N = 4096 outputs of a
+// 3072-row step: 192 tiles on 74 pairs = 86 % vs 96 units on 33 clusters = 97 %): measured sustained +0.6 % (K = 11008) to
+// +2.5 % (K = 22016) over the pair kernel, -0.5 % step time; on shapes with full pair waves (N >= 11008) the 16 idle SMs of the
+// cluster schedule cost 4-5 % instead (profiles/r1_gemm_quad_cluster.txt).
+static bool use_quad(int M, int N) {
+  if (g_quad_mode == 0 || g_quad_clusters <= 0 || g_force_bn != 0 || M <= GEMM_BM || N % 512 != 0) return false;
+  if (g_quad_mode == 2) return true;
+  const long tm = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const long tiles = tm * (N / 256), units = tm * (N / 512), pairs = g_num_sms / 2;
+  const double eff_pair = static_cast<double>(tiles) / (static_cast<double>((tiles + pairs - 1) / pairs) * pairs);
+  const double eff_quad = static_cast<double>(units) / (static_cast<double>((units + g_quad_clusters - 1) / g_quad_clusters) * g_quad_clusters);
+  return eff_pair < 0.9 && eff_quad > eff_pair + 0.05;
+}
+
 // M > 128 rows: CTA-pair kernel; tiny-M problems (adapter prompts, a handful of labelled rows) stay on
 // the single-CTA kernel.
 static bool use_pair(int M, int N) { return g_force_bn >= 0 && M > GEMM_BM && N >= 64; }
@@ -830,6 +904,9 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
   const bf16* b = reinterpret_cast<const bf16*>(B);
   GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1, nullptr, 0, 0};
   if (g_force_bn == 0 && gemm_skinny_supported(M, K, R)) return gemm_skinny(a, lda, b, ldb, C, ldc, M, N, K, out_fp32, g_num_sms, s);
+  if (use_quad(M, N)) {
+    return out_fp32 ? launch_gemm_quad<true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s) : launch_gemm_quad<false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
+  }
   if (use_pair(M, N)) {
     const int bn = pair_bn(M, N);
     return out_fp32 ? launch_gemm_pair<true, EPI_PLAIN>(a, lda, b, ldb, C, ldc, epi, M, N, K, bn, s)
@@ -895,6 +972,16 @@ extern "C" int fvqa_gemm_debug_epilogue_warps(int n) {
   if (n == 4 || n == 8) g_pair_threads = (4 + n) * 32;
   return prev;
 }
+
+/* Test / tuning hook for the 2x2-cluster multicast kernel (plain epilogue, M > 128, N % 512 == 0): 0 = never, 1 = when the pair
+ * schedule would end in a partial wave (default), 2 = always when eligible. Returns the previous mode;
+ * fvqa_gemm_quad_clusters() = how many 4-CTA clusters fit the device (0 = variant unavailable). */
+extern "C" int fvqa_gemm_debug_quad(int mode) {
+  const int prev = g_quad_mode;
+  if (mode >= 0 && mode <= 2) g_quad_mode = mode;
+  return prev;
+}
+extern "C" int fvqa_gemm_quad_clusters(void) { return g_quad_clusters; }
 
 /* Test / tuning hook: force the CTA-pair tile width (multiple of 16 in [64,256]); 0 restores the
  * heuristic, -1 forces the single-CTA kernel. Returns the previous setting. */

@@ -97,6 +97,12 @@ int fvqa_gemm_swiglu_fwd(const fvqa_bf16* X, int ldx, const fvqa_bf16* W13, int 
 int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int ldw, const fvqa_bf16* G, int ldg,
                          fvqa_bf16* dG, int lddg, int M, int hid, int K, void* stream);
 
+/* 2x2-cluster variant of the GEMM (plain epilogue, M > 128, N % 512 == 0): clusters of TWO CTA pairs own 256 x 512 output blocks
+ * and TMA-multicast the A slice the pairs share (-25 % L2 -> SM operand bytes); same results bit for bit. Mode 0 = never,
+ * 1 (default) = when the CTA-pair schedule would end in a partial wave (the N = 4096 GEMMs of a 3072-row step), 2 = always when
+ * eligible. fvqa_gemm_quad_clusters() = co-resident 4-CTA clusters on this device (33 on a B200), 0 if unavailable. */
+int fvqa_gemm_debug_quad(int mode);
+int fvqa_gemm_quad_clusters(void);
 /* Test / tuning hook for the GEMM tile choice: bn = multiple of 16 in [64,256] forces that CTA-pair
  * tile width, 0 restores the heuristic, -1 forces the single-CTA kernel. Returns the previous value. */
 int fvqa_gemm_debug_force_bn(int bn);

@@ -121,6 +121,30 @@ def test_gemm_skinny_grouped(fvqa_lib, G, M, N, K, f32):
         assert torch.equal(single, out[g]), g
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 512, 64), (700, 1536, 384), (129, 512, 128), (3072, 4096, 4096), (2535, 4096, 1024)])
+def test_gemm_quad_cluster_multicast(fvqa_lib, M, N, K):
+    """2x2-cluster variant (two CTA pairs share an A slice through TMA multicast): bit-identical to the CTA-pair kernel —
+    same tiles, same k order — for bf16 and fp32 + residual outputs, ragged M included, nothing written out of bounds."""
+    from flipped_vqa_b200 import ops
+    if fvqa_lib.fvqa_gemm_quad_clusters() <= 0:
+        pytest.skip("no 4-CTA clusters on this device")
+    a = bf16_randn(M, K, seed=80)
+    b = bf16_randn(N, K, std=0.05, seed=81)
+    r32 = torch.randn(M, N, device="cuda")
+    prev = fvqa_lib.fvqa_gemm_debug_quad(0)
+    try:
+        p16, p32 = ops.gemm_nt(a, b), ops.gemm_nt(a, b, residual=r32, out_fp32=True)
+        fvqa_lib.fvqa_gemm_debug_quad(2)
+        guard = torch.full((M + 2, N), 7.0, device="cuda")
+        q32 = ops.gemm_nt(a, b, residual=r32, out_fp32=True, out=guard[1:M + 1])
+        q16 = ops.gemm_nt(a, b)
+    finally:
+        fvqa_lib.fvqa_gemm_debug_quad(prev)
+    assert torch.all(guard[0] == 7.0) and torch.all(guard[M + 1] == 7.0)
+    assert torch.equal(q16, p16) and torch.equal(q32, p32)
+    assert relerr(q32, a.float() @ b.float().t() + r32) < 2e-4
+
+
 @pytest.mark.parametrize("bn", [-1, 64, 128, 144, 176, 208, 240, 256])
 def test_gemm_pair_tile_widths(fvqa_lib, bn):
     """The CTA-pair (cta_group::2) kernel for every runtime tile width (and the single-CTA kernel, bn=-1)

@@ -33,7 +33,7 @@ def main():
     def reset():
         model._engine.prune_last_layer = False
         ops.FUSE_SWIGLU = True
-        lib.fvqa_attn_debug_use_tc(1); lib.fvqa_gemm_debug_force_bn(0); lib.fvqa_gemm_debug_l2_hints(0)
+        lib.fvqa_attn_debug_use_tc(1); lib.fvqa_gemm_debug_force_bn(0); lib.fvqa_gemm_debug_l2_hints(0); lib.fvqa_gemm_debug_quad(1)
 
     variants = {
         "default": lambda: None,
@@ -42,7 +42,12 @@ def main():
         "mma_sync_attention": lambda: lib.fvqa_attn_debug_use_tc(0),
         "bn240": lambda: lib.fvqa_gemm_debug_force_bn(240),
         "single_cta_gemm": lambda: lib.fvqa_gemm_debug_force_bn(-1),
+        "no_quad_cluster_gemm": lambda: lib.fvqa_gemm_debug_quad(1),
+        "quad_cluster_gemm_everywhere": lambda: lib.fvqa_gemm_debug_quad(2),
     }
+    only = os.environ.get("AB_VARIANTS")
+    if only:
+        variants = {k: v for k, v in variants.items() if k in only.split(",")}
     for i in range(10):
         step(i)
     torch.cuda.synchronize()

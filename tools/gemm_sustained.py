@@ -41,7 +41,10 @@ def sustained(fn, flops, secs=2.5):
 def main():
     pynvml.nvmlInit()
     lib = _lib.lib()
-    shapes = [(8192, 8192, 8192), (3072, 22016, 4096), (3072, 4096, 11008), (3072, 12288, 4096), (3072, 4096, 4096)]
+    lib.fvqa_gemm_debug_quad(0)                                  # "pair" below = the CTA-pair kernel
+    shapes = [(3072, 4096, 11008), (3072, 4096, 22016), (3072, 4096, 4096), (3072, 12288, 4096), (3072, 22016, 4096), (8192, 8192, 8192)]
+    if len(sys.argv) > 1:
+        shapes = shapes[:int(sys.argv[1])]
     for (M, N, K) in shapes:
         a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
         b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
@@ -51,6 +54,12 @@ def main():
         for name, fn in [("pair", lambda: ops.gemm_nt(a, b, out=c)), ("cublas", lambda: torch.matmul(a, b.t(), out=c))]:
             tf, pw, ck = sustained(fn, fl)
             res.append(f"{name}: {tf:6.0f} TF/s {pw:5.0f} W {ck:5.0f} MHz {pw / tf * 1e3:5.0f} mJ/TFLOP")
+            time.sleep(1.0)
+        if N % 512 == 0 and lib.fvqa_gemm_quad_clusters() > 0:
+            lib.fvqa_gemm_debug_quad(2)
+            tf, pw, ck = sustained(lambda: ops.gemm_nt(a, b, out=c), fl)
+            lib.fvqa_gemm_debug_quad(0)
+            res.append(f"quad: {tf:6.0f} TF/s {pw:5.0f} W {ck:5.0f} MHz {pw / tf * 1e3:5.0f} mJ/TFLOP")
             time.sleep(1.0)
         lib.fvqa_gemm_debug_force_bn(-1)
         tf, pw, ck = sustained(lambda: ops.gemm_nt(a, b, out=c), fl)
