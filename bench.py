@@ -17,6 +17,7 @@ and /root/reference does not exist on the GPU box).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -98,14 +99,24 @@ class ClockSampler(threading.Thread):
         self.samples, self.power, self.reasons = [], [], set()
         self.max_mhz = None
         self._stop_evt = threading.Event()
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
+        # NVML is initialised ONCE per process, before the warm-up steps: doing it here, between the warm-up and the timed
+        # region, left the GPU idle for ~0.2 s, after which it boosted past the power cap on the first timed step and was
+        # throttled hard on the second (one 94 ms step among 74 ms ones; visible in step_ms_rank0)
+        self.nv, self.h, self.max_mhz = ClockSampler._nvml(index)
+
+    _cache = {}
+
+    @staticmethod
+    def _nvml(index):
+        if index not in ClockSampler._cache:
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                h = pynvml.nvmlDeviceGetHandleByIndex(index)
+                ClockSampler._cache[index] = (pynvml, h, pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            except Exception:
+                ClockSampler._cache[index] = (None, None, None)
+        return ClockSampler._cache[index]
 
     def run(self):
         if self.nv is None:
@@ -310,7 +321,11 @@ def main():
         opt.zero_grad(set_to_none=True)
         return loss.item()                                      # D2H read of the step's result
 
+    step_ms = []        # per-step device times of the last timed() call on this rank (diagnostic: one-off stalls show up here)
+
     def timed(fn, steps, sample_gemm=False):
+        gc.collect()
+        gc.disable()                    # a generational GC pause on one rank stalls every rank at the next all-reduce
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -320,14 +335,19 @@ def main():
             ops.GEMM_TIMER = ops.GemmTimer()
         launches0 = ops.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
         for i in range(steps):
             fn(i)
+            marks[i].record()
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+        gc.enable()
         ms = e0.elapsed_time(e1)
+        step_ms.clear()
+        step_ms.extend(round(a.elapsed_time(b), 3) for a, b in zip([e0] + marks[:-1], marks))
         launches = ops.LAUNCHES - launches0
         clocks = sampler.stop()
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
@@ -339,10 +359,12 @@ def main():
 
     L = cfg["adapter_layer"]
     model._engine.sample_layers = tuple(sorted({0, L // 2} if a.sample_layers >= 2 else {L // 2})) if a.sample_layers > 0 else ()   # not the pruned last layer
+    ClockSampler._nvml(local)                                   # NVML set-up before the warm-up, not between warm-up and timing
     for i in range(a.warmup):
         step_resident(i)
     ms, launches, clocks, gemm = timed(step_resident, a.steps, sample_gemm=a.sample_layers > 0)
     ms_per_step = ms / a.steps
+    resident_step_ms = list(step_ms)
     value = world * B / (ms_per_step * 1e-3)
 
     if a.no_e2e:
@@ -396,6 +418,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": plans[0].h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e / a.steps, "clocks": clocks_e},
             "gpu_launches": launches,
+            "step_ms_rank0": resident_step_ms,
             "padding_free": padfree,
         }
         if gemm is not None:
