@@ -36,6 +36,7 @@ _SIGNATURES = {
     "fvqa_gemm_swiglu_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_debug_force_bn": [_i],
+    "fvqa_gemm_debug_skinny_nt": [_i],
     "fvqa_gemm_debug_quad": [_i],
     "fvqa_gemm_quad_clusters": [],
     "fvqa_gemm_debug_epilogue_warps": [_i],

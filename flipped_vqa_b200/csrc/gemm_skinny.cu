@@ -92,11 +92,15 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const bf16* __r
 
 bool gemm_skinny_supported(int M, int K, const void* R) { return M <= 16 && R == nullptr && K % (SK_WARPS * 32) == 0; }
 
+int g_skinny_force_nt = 0;   // tuning hook (fvqa_gemm_debug_skinny_nt): column blocks of 8 * nt per CTA; 0 = heuristic
+
 int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, const bf16* const* Bptrs, int ldb, void* C, long strideC,
                         int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream) {
-  // widest column block that still gives every SM ~2 CTAs
-  const long blocks32 = static_cast<long>(N / 32) * groups, blocks16 = static_cast<long>(N / 16) * groups;
-  const int nt = (blocks32 >= 2 * num_sms) ? 4 : (blocks16 >= 2 * num_sms ? 2 : 1);
+  // 16 columns per CTA when that still gives every SM ~2 CTAs, else 8. (32 columns per CTA cost registers / resident CTAs:
+  // measured 4.96 vs 5.38 TB/s on the 2.1 GB forward launch and 3.5 vs 4.3 TB/s on a backward chunk, tools/skinny_bench.py.)
+  const long blocks16 = static_cast<long>(N / 16) * groups;
+  int nt = blocks16 >= 2 * num_sms ? 2 : 1;
+  if (g_skinny_force_nt == 1 || g_skinny_force_nt == 2 || g_skinny_force_nt == 4) nt = g_skinny_force_nt;
   const int cols = 8 * nt;
   const dim3 grid((N + cols - 1) / cols, groups);
 #define FVQA_SK(NT_)                                                                                                                \

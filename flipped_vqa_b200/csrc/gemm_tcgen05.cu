@@ -774,6 +774,7 @@ int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc
                 cudaStream_t stream);
 int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, const bf16* const* Bptrs, int ldb, void* C, long strideC,
                         int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream);
+extern int g_skinny_force_nt;
 
 // ---- CTA-pair path ---------------------------------------------------------------------------
 static int g_l2_hints = 0;         // test hook (fvqa_gemm_debug_l2_hints)
@@ -982,6 +983,13 @@ extern "C" int fvqa_gemm_debug_quad(int mode) {
   return prev;
 }
 extern "C" int fvqa_gemm_quad_clusters(void) { return g_quad_clusters; }
+
+/* Tuning hook: the skinny (M <= 16) kernel's CTA covers 8 * nt output columns, nt in {1, 2, 4}; 0 restores the heuristic. */
+extern "C" int fvqa_gemm_debug_skinny_nt(int nt) {
+  const int prev = g_skinny_force_nt;
+  g_skinny_force_nt = nt;
+  return prev;
+}
 
 /* Test / tuning hook: force the CTA-pair tile width (multiple of 16 in [64,256]); 0 restores the
  * heuristic, -1 forces the single-CTA kernel. Returns the previous setting. */

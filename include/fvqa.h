@@ -103,6 +103,8 @@ int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int
  * eligible. fvqa_gemm_quad_clusters() = co-resident 4-CTA clusters on this device (33 on a B200), 0 if unavailable. */
 int fvqa_gemm_debug_quad(int mode);
 int fvqa_gemm_quad_clusters(void);
+/* Tuning hook: the skinny (M <= 16) kernel's CTA covers 8 * nt output columns, nt in {1, 2, 4}; 0 = heuristic. */
+int fvqa_gemm_debug_skinny_nt(int nt);
 /* Test / tuning hook for the GEMM tile choice: bn = multiple of 16 in [64,256] forces that CTA-pair
  * tile width, 0 restores the heuristic, -1 forces the single-CTA kernel. Returns the previous value. */
 int fvqa_gemm_debug_force_bn(int bn);
