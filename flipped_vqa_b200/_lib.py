@@ -41,6 +41,7 @@ _SIGNATURES = {
     "fvqa_gemm_quad_clusters": [],
     "fvqa_gemm_debug_epilogue_warps": [_i],
     "fvqa_gemm_debug_l2_hints": [_i],
+    "fvqa_gemm_debug_a_fp16": [_i],
     "fvqa_attn_debug_use_tc": [_i],
     "fvqa_attn_uses_tc": [_i, _i, _i],
     "fvqa_attn_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],

@@ -350,7 +350,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tma_load_2d_pair_mc(sa + cq * kHalf, &tmap_a, lfull, kb * GEMM_BK, m0 + cq * (GEMM_BM / 2),
                                 static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2u))));
             tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
-          } else if (l2_hints) {      // weights stream through once per wave; the activation operand is re-read by every tile column
+          } else if (l2_hints & 1) {      // weights stream through once per wave; the activation operand is re-read by every tile column
             tma_load_2d_pair_hint(sa, &tmap_a, lfull, kb * GEMM_BK, m0, L2_EVICT_LAST);
             tma_load_2d_pair_hint(sb, &tmap_b, lfull, kb * GEMM_BK, n0, L2_EVICT_FIRST);
           } else {
@@ -364,7 +364,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN);
+      // l2_hints bit 1 (probe, fvqa_gemm_debug_a_fp16): the A operand holds fp16 bits (mixed fp16 x bf16 kind::f16 MMA)
+      const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN) & ~((l2_hints & 2) ? (1u << 7) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -777,6 +778,7 @@ int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, con
 extern int g_skinny_force_nt;
 
 // ---- CTA-pair path ---------------------------------------------------------------------------
+static int g_a_fp16 = 0;           // probe (fvqa_gemm_debug_a_fp16)
 static int g_l2_hints = 0;         // test hook (fvqa_gemm_debug_l2_hints)
 static int g_force_bn = 0;        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
 static int g_pair_threads = GEMM_THREADS;   // test hook (fvqa_gemm_debug_epilogue_warps): 256 = 4 epilogue warps (default), 384 = 8
@@ -821,7 +823,7 @@ static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void
   const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + bn - 1) / bn;
   const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tiles_n;
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, g_pair_threads, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints);
+  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, g_pair_threads, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints | (g_a_fp16 << 1));
   return check_launch("gemm_bf16_nt_pair");
 }
 
@@ -1031,5 +1033,12 @@ extern "C" int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf1
 extern "C" int fvqa_gemm_debug_l2_hints(int on) {
   const int prev = g_l2_hints;
   g_l2_hints = on;
+  return prev;
+}
+
+/* Probe: 1 = the A operand of the CTA-pair kernel is read as fp16 (B stays bf16). */
+extern "C" int fvqa_gemm_debug_a_fp16(int on) {
+  const int prev = g_a_fp16;
+  g_a_fp16 = on ? 1 : 0;
   return prev;
 }

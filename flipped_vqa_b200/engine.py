@@ -37,16 +37,17 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: to
             vqa_loss, vaq_loss, qav_loss = model(data)
         loss = vqa_loss + vaq_loss + qav_loss
         update = (data_iter_step + 1) % accum_iter == 0
-        loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update)
-        if update:
-            optimizer.zero_grad()
-        # one D2H read for all four logged values (also the step's only host sync)
+        # one D2H read for all four logged values (also the step's only host sync), BEFORE backward / the optimizer step as in
+        # `engine.py:28-35`: a non-finite loss must never reach the trainables or the AdamW state
         vals = torch.stack([loss.detach().float().reshape(()), vqa_loss.detach().float().reshape(()),
                             vaq_loss.detach().float().reshape(()), qav_loss.detach().float().reshape(())]).tolist()
         loss_value = vals[0]
         if not math.isfinite(loss_value):
             print("Loss is {}, stopping training".format(loss_value))
             sys.exit(1)
+        loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update)
+        if update:
+            optimizer.zero_grad()
         metric_logger.update(loss=loss_value, vqa_loss=vals[1], vaq_loss=vals[2], qav_loss=vals[3])
         metric_logger.update(lr=optimizer.param_groups[0]["lr"])
         if getattr(args, "debug", False):
@@ -65,6 +66,8 @@ def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torc
     header = "Epoch: [{}]".format(epoch)
     print_freq = max(int(len(data_loader) / 4), 1)
     inner = model.module if hasattr(model, "module") else model
+    if getattr(args, "is_generation_task", False) and not hasattr(inner, "generate_answers"):
+        raise NotImplementedError("is_generation_task: this model has no generation evaluator (`engine.py:78-85,99-121`)")
     for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         plan = None
         if isinstance(data, tuple):                  # dataloader.PlannedLoader(..., inference=True)
@@ -74,8 +77,9 @@ def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torc
         with torch.no_grad():
             individual_losses = inner.inference_plan(plan) if plan is not None else model(data, inference=True)
             prediction = inner.predict_options(individual_losses)
-        eval_exact_match = answer.to(prediction.device) == prediction
+        eval_exact_match = (answer.to(prediction.device) == prediction).cpu()
         acc = eval_exact_match.sum().item() / bsz
+        misc.log_qtype(data, eval_exact_match, metric_logger, args)             # `engine.py:127`: val_<qtype> meters
         metric_logger.update(lr=optimizer.param_groups[0]["lr"] if optimizer is not None else 0.0)
         metric_logger.update(n=bsz, acc=acc)
         if getattr(args, "debug", False):

@@ -45,7 +45,7 @@ class SmoothedValue:
 
     @property
     def global_avg(self):
-        return self.total / max(self.count, 1)
+        return self.total / self.count if self.count else 0.0      # `util/misc.py:83-84` (a fractional weight is possible, see log_qtype)
 
     @property
     def value(self):
@@ -60,13 +60,15 @@ class MetricLogger:
         self.meters = defaultdict(SmoothedValue)
         self.delimiter = delimiter
 
-    def update(self, n=1, **kwargs):
-        for k, v in kwargs.items():
+    def update(self, count=1, **metrics):
+        """`util/misc.py:111-118`: the weight is the positional/keyword `count`; a keyword `n=` (as `engine.py:133-135` and the
+        per-question-type updates pass it) is therefore a METER called "n", exactly as in the reference."""
+        for k, v in metrics.items():
             if v is None:
                 continue
             if isinstance(v, torch.Tensor):
                 v = v.item()
-            self.meters[k].update(float(v), n=n)
+            self.meters[k].update(float(v), n=count)
 
     def add_meter(self, name, meter):
         self.meters[name] = meter
@@ -177,12 +179,13 @@ def trainable_state(model_without_ddp):
 
 
 def save_model(args, epoch, model, model_without_ddp, optimizer, loss_scaler, name):
-    """Same file layout as `util/misc.py:297-317` (checkpoint_<name>.pth with model/optimizer/epoch/scaler/args)."""
+    """Same file layout as `util/misc.py:297-317`: `<output_dir>/<name>.pth` (the reference's driver passes
+    name='checkpoint_best', `train.py:141`) holding model (trainables only) / optimizer / epoch / scaler / args."""
     output_dir = Path(args.output_dir)
     to_save = {"model": {k: v.detach().clone() for k, v in trainable_state(model_without_ddp).items()},
                "optimizer": optimizer.state_dict(), "epoch": epoch,
                "scaler": loss_scaler.state_dict() if loss_scaler is not None else None, "args": args}
-    save_on_master(to_save, output_dir / f"checkpoint_{name}.pth")
+    save_on_master(to_save, output_dir / f"{name}.pth")
 
 
 def load_model(args, model_without_ddp, optimizer, loss_scaler):
@@ -192,8 +195,80 @@ def load_model(args, model_without_ddp, optimizer, loss_scaler):
     checkpoint = torch.load(args.resume, map_location="cpu", weights_only=False)
     model_without_ddp.load_state_dict(checkpoint["model"], strict=False)
     print(f"Resume checkpoint {args.resume}")
-    if "optimizer" in checkpoint and "epoch" in checkpoint:
+    if "optimizer" in checkpoint and "epoch" in checkpoint and not getattr(args, "eval", False):   # `util/misc.py:331`
         optimizer.load_state_dict(checkpoint["optimizer"])
         args.start_epoch = checkpoint["epoch"] + 1
         if loss_scaler is not None and checkpoint.get("scaler") is not None:
             loss_scaler.load_state_dict(checkpoint["scaler"])
+
+
+# ------------------------------------------------------------------------------------------------
+# per-question-type accuracy meters of the validation loop (`util/misc.py:361-532`)
+# ------------------------------------------------------------------------------------------------
+_VALOR_TYPES = ("count", "temporal", "desc", "action", "loc", "rel_pos")
+_MUSIC_TYPES = ("Temporal", "Existential", "Comparative", "Location", "Counting")
+
+
+def get_qtype_mapping(dataset_name: str) -> dict:
+    """`util/misc.py:365-412`: question-type name -> id (0 is reserved for the total)."""
+    if dataset_name == "nextqa":
+        return {k: i + 1 for i, k in enumerate(("CH", "CW", "TN", "TC", "TP", "DL", "DC", "DO"))}
+    if dataset_name == "star":
+        return {k: i + 1 for i, k in enumerate(("In", "Seq", "Pre", "Feas"))}
+    if dataset_name == "valor32k":
+        m = {f"{t}_{mod}": 3 * i + j + 1 for i, t in enumerate(_VALOR_TYPES) for j, mod in enumerate(("visual", "audio", "both"))}
+        m.update(audio_both=19, audio_visual=20)
+        return m
+    if dataset_name == "musicavqa":
+        return {f"{mod}_{t}": 5 * i + j + 1 for i, mod in enumerate(("Audio", "Visual", "Audio-Visual")) for j, t in enumerate(_MUSIC_TYPES)}
+    return {}
+
+
+def _qtype_groups(dataset_name: str):
+    """(meter name, count-meter name, question-type ids) in the reference's update order (`util/misc.py:443-524`)."""
+    if dataset_name == "valor32k":
+        g = [("audio", [2, 5, 8, 11, 14, 17]), ("visual", [1, 4, 7, 10, 13, 16, 20]), ("both", [3, 6, 9, 12, 15, 18, 19])]
+        g += [(t, [3 * i + 1, 3 * i + 2, 3 * i + 3]) for i, t in enumerate(_VALOR_TYPES)] + [("audio_second", [19, 20])]
+        return g
+    if dataset_name == "musicavqa":
+        g = [("audio", [1, 2, 3, 4, 5]), ("visual", [6, 7, 8, 9, 10]), ("audio_visual", [11, 12, 13, 14, 15])]
+        return g + [(t.lower(), [j + 1, j + 6, j + 11]) for j, t in enumerate(_MUSIC_TYPES)]
+    return []
+
+
+def log_qtype(data, eval, metric_logger: MetricLogger, args):
+    """`util/misc.py:526-532` (+ `:414-524`): per-batch hit / count per question type -> the reference's meters (nextqa: C, T,
+    D, Total; star: In, Seq, Pre, Feas, Total; valor32k / musicavqa: one score meter and one `n_*` meter per group)."""
+    eps = 1e-10
+    dataset = getattr(args, "dataset", None)
+    qtype2id = get_qtype_mapping(dataset)
+    if not qtype2id:
+        return
+    freq = {i: [0.0, 0.0] for i in qtype2id.values()}
+    freq[0] = [0.0, 0.0]
+    hits = [float(v) for v in torch.as_tensor(eval).flatten().tolist()]
+    qts = [int(q) for q in torch.as_tensor(data["qtype"]).flatten().tolist()]
+    for qt, v in zip(qts, hits):
+        for key in (qt, 0):
+            freq[key][0] += v
+            freq[key][1] += 1
+    tot = lambda ids: (sum(freq[i][0] for i in ids), sum(freq[i][1] for i in ids))
+    ratio = lambda f: f[0] / f[1] if f[1] != 0 else 0.0                       # getCount, `:361-363`
+    if dataset == "nextqa":
+        for name, ids in (("C", (1, 2)), ("T", (3, 4, 5)), ("D", (6, 7, 8))):
+            s, c = tot(ids)
+            metric_logger.update(n=c + eps, **{name: s / (c + eps)})
+        metric_logger.update(n=freq[0][1] + eps, Total=ratio(freq[0]))
+    elif dataset == "star":
+        for i, name in enumerate(("In", "Seq", "Pre", "Feas")):
+            metric_logger.update(n=freq[i + 1][1] + eps, **{name: ratio(freq[i + 1])})
+        metric_logger.update(n=freq[0][1] + eps, Total=ratio(freq[0]))
+    else:
+        # one update(**...) call as in `util/misc.py:479-490`: for valor32k the score of the 'count' group is passed as `count=`, i.e.
+        # it binds to update()'s WEIGHT parameter (there is no 'count' meter and that batch's meters are weighted by it) - kept
+        upd = {}
+        for name, ids in _qtype_groups(dataset):
+            s, c = tot(ids)
+            upd["n_" + name] = c + eps
+            upd[name] = s / (c + eps)
+        metric_logger.update(**upd)

@@ -112,6 +112,8 @@ int fvqa_gemm_debug_force_bn(int bn);
 int fvqa_gemm_debug_epilogue_warps(int n);
 /* Tuning hook: 1 = the CTA-pair kernel's TMA loads carry L2 eviction hints (A evict_last, B evict_first). */
 int fvqa_gemm_debug_l2_hints(int on);
+/* Probe: 1 = the CTA-pair kernel reads its A operand as fp16 (B stays bf16): mixed-format kind::f16 MMA. */
+int fvqa_gemm_debug_a_fp16(int on);
 
 /* ---- fused attention (llama/model.py:61-67 RoPE, :87-126 attention incl. adapter branch). --------
  * qkv  [n_seq*S, 3*H*hd] bf16 (q | k | v) with q,k ALREADY rotated (fvqa_gemm_bf16_nt_rope).

@@ -240,7 +240,7 @@ def test_checkpoint_save_resume_roundtrip(tmp_path):
                 p.add_(torch.randn_like(p) * 0.1)
     opt = torch.optim.AdamW([p for p in m.parameters() if p.requires_grad], lr=1e-3)
     args = argparse.Namespace(output_dir=str(tmp_path), resume="")
-    misc.save_model(args, 3, m, m, opt, misc.NativeScalerWithGradNormCount(), "best")
+    misc.save_model(args, 3, m, m, opt, misc.NativeScalerWithGradNormCount(), "checkpoint_best")   # the name `train.py:141` passes
     ck = torch.load(tmp_path / "checkpoint_best.pth", map_location="cpu", weights_only=False)
     names = set(ck["model"])
     assert names == {n for n, p in m.named_parameters() if p.requires_grad}          # trainables only, reference names
@@ -253,3 +253,39 @@ def test_checkpoint_save_resume_roundtrip(tmp_path):
     for (n, a), (_, b) in zip(m.named_parameters(), m2.named_parameters()):
         if a.requires_grad:
             assert torch.equal(a, b), n
+    # `util/misc.py:331`: an --eval run restores the weights only (no optimizer state, start_epoch untouched)
+    m3 = _model()
+    opt3 = torch.optim.AdamW([p for p in m3.parameters() if p.requires_grad], lr=1e-3)
+    args3 = argparse.Namespace(output_dir=str(tmp_path), resume=args.resume, eval=True, start_epoch=0)
+    misc.load_model(args3, m3, opt3, misc.NativeScalerWithGradNormCount())
+    assert args3.start_epoch == 0 and not opt3.state_dict()["state"]
+    assert torch.equal(m3.adapter_query.weight, m.adapter_query.weight)
+
+
+def test_log_qtype_meters_match_reference_formulas():
+    """`util/misc.py:361-532`: per-question-type meters of the validation loop; MetricLogger.update(count=1, **metrics) keeps the
+    reference's quirk that a keyword n= is a meter named 'n'."""
+    import argparse
+    from flipped_vqa_b200.util import misc
+    ml = misc.MetricLogger()
+    data = {"qtype": torch.tensor([1, 2, 3, 6, 6, 8])}
+    hit = torch.tensor([True, False, True, True, False, True])
+    misc.log_qtype(data, hit, ml, argparse.Namespace(dataset="nextqa"))
+    eps = 1e-10
+    assert abs(ml.meters["C"].global_avg - 1 / (2 + eps)) < 1e-12
+    assert abs(ml.meters["T"].global_avg - 1 / (1 + eps)) < 1e-12
+    assert abs(ml.meters["D"].global_avg - 2 / (3 + eps)) < 1e-12
+    assert abs(ml.meters["Total"].global_avg - 4 / 6) < 1e-12
+    assert ml.meters["n"].count == 4                                   # four update(n=...) calls -> meter 'n'
+    ml.update(n=6, acc=0.5)
+    assert ml.meters["acc"].count == 1 and ml.meters["n"].count == 5
+    ml2 = misc.MetricLogger()
+    misc.log_qtype({"qtype": torch.tensor([1, 7, 12, 15])}, torch.tensor([1, 0, 1, 1]), ml2, argparse.Namespace(dataset="musicavqa"))
+    assert abs(ml2.meters["audio"].global_avg - 1 / (1 + eps)) < 1e-12 and abs(ml2.meters["visual"].global_avg) < 1e-12
+    assert abs(ml2.meters["audio_visual"].global_avg - 2 / (2 + eps)) < 1e-12
+    assert abs(ml2.meters["existential"].global_avg - 1 / (2 + eps)) < 1e-12 and abs(ml2.meters["counting"].global_avg - 1 / (1 + eps)) < 1e-12
+    assert misc.get_qtype_mapping("valor32k")["rel_pos_both"] == 18 and misc.get_qtype_mapping("star")["Feas"] == 4
+    assert misc.get_qtype_mapping("musicavqa")["Audio-Visual_Counting"] == 15 and misc.get_qtype_mapping("tvqa") == {}
+    ml3 = misc.MetricLogger()
+    misc.log_qtype(data, hit, ml3, argparse.Namespace(dataset="tvqa"))
+    assert not ml3.meters
