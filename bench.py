@@ -273,7 +273,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from flipped_vqa_b200 import ops
+    from flipped_vqa_b200 import _lib, ops
     from flipped_vqa_b200.dp import DataParallel
     from flipped_vqa_b200.llama import ModelArgs, SyntheticTokenizer, Transformer
     from flipped_vqa_b200.synthetic import synthetic_batch
@@ -405,8 +405,8 @@ def main():
             "metric": "7B NExT-QA train samples/s" if a.config == "7b-nextqa" else f"{a.config} train samples/s",
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[a.config], "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}",
+            "dtype": _lib.DTYPE_NAME, "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAMES[a.config], "operands": f"{_lib.DTYPE_NAME} weights / activations / gradients (tcgen05 kind::f16, fp32 accumulate), fp32 residual stream and trainables", "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}",
                        "l2": "working set (2 x 13.5 GB frozen weights + 9 GB saved activations per step) >> 126 MB L2; no explicit flush",
                        "objectives": "vqa+vaq+qav", "optimizer": "AdamW(fused) on 4.5M trainables", "flops_per_step": step_flops,
                        "labelled_rows_per_step": n_lab,
@@ -424,7 +424,7 @@ def main():
         }
         if gemm is not None:
             tr = gemm_traffic() if a.config == "7b-nextqa" else None
-            line["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_nt_pair_kernel (tcgen05.mma.cta_group::2, TMA, TMEM; 2x2-cluster TMA-multicast variant on the N = 4096 GEMMs)", "achieved": gemm["tflops"],
+            line["roofline"] = {"bound": "tensor", "kernel": "gemm_nt_pair_kernel (tcgen05.mma.cta_group::2, TMA, TMEM; 2x2-cluster TMA-multicast variant on the N = 4096 GEMMs)", "achieved": gemm["tflops"],
                                 "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm["tflops"] / peaks["bf16_tflops_sustained"],
                                 "frac_of_burst_peak": gemm["tflops"] / peaks["bf16_tflops"], "peak_kind": f"{peaks['source']} sustained (kernel timed inside a long step)",
                                 "traffic": (tr["avg_dram_bytes_per_launch"] if tr else None),

@@ -1,4 +1,9 @@
-"""ctypes binding of the C ABI declared in include/fvqa.h (libfvqa.so, built in-tree).
+"""ctypes binding of the C ABI declared in include/fvqa.h (+ the test hooks of include/fvqa_debug.h), built in-tree.
+
+The 16-bit tensor-core operand format is a property of the LIBRARY (tcgen05.mma rejects mixed fp16 x bf16 operands):
+`libfvqa.so` = fp16 (default: the reference's dtype, `llama_vqa.py:63`, and the format that meets the full-depth parity
+bound), `libfvqa_bf16.so` = bf16, selected with the environment variable FVQA_DTYPE=bf16 before the first import.
+`H16` is the matching torch dtype of every `fvqa_h16` tensor.
 
 There is NO CPU fallback: if the library is missing, does not export a symbol the header declares,
 or `fvqa_init()` fails (no sm_100 GPU), the product path raises.
@@ -13,14 +18,20 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfvqa.so")
+DTYPE_NAME = os.environ.get("FVQA_DTYPE", "fp16").lower()
+if DTYPE_NAME not in ("fp16", "bf16"):
+    raise ValueError(f"FVQA_DTYPE must be fp16 or bf16, got {DTYPE_NAME!r}")
+H16 = torch.float16 if DTYPE_NAME == "fp16" else torch.bfloat16
+LIB_PATH = os.path.join(_HERE, "libfvqa.so" if DTYPE_NAME == "fp16" else "libfvqa_bf16.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fvqa.h")
+DEBUG_HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "fvqa_debug.h")
 
 _p, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 # name -> argtypes (all functions return int unless listed in _RESTYPES)
 _SIGNATURES = {
     "fvqa_abi_version": [],
+    "fvqa_operand_dtype": [],
     "fvqa_last_error": [],
     "fvqa_init": [],
     "fvqa_rmsnorm_fwd": [_p, _p, _p, _p, _i, _i, _f, _p],
@@ -29,9 +40,9 @@ _SIGNATURES = {
     "fvqa_rmsnorm_scatter_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _p],
     "fvqa_swiglu_fwd": [_p, _p, _i, _i, _p],
     "fvqa_swiglu_bwd": [_p, _p, _p, _i, _i, _p],
-    "fvqa_gemm_bf16_nt": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
-    "fvqa_gemm_bf16_nt_rope": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p],
-    "fvqa_gemm_bf16_nt_rope_pos": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p],
+    "fvqa_gemm_nt": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _i, _p],
+    "fvqa_gemm_nt_rope": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p],
+    "fvqa_gemm_nt_rope_pos": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _p],
     "fvqa_gemm_skinny_grouped": [_p, _i64, _i, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
@@ -41,7 +52,7 @@ _SIGNATURES = {
     "fvqa_gemm_quad_clusters": [],
     "fvqa_gemm_debug_epilogue_warps": [_i],
     "fvqa_gemm_debug_l2_hints": [_i],
-    "fvqa_gemm_debug_a_fp16": [_i],
+    "fvqa_gemm_debug_mixed_a": [_i],
     "fvqa_attn_debug_use_tc": [_i],
     "fvqa_attn_uses_tc": [_i, _i, _i],
     "fvqa_attn_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
@@ -61,7 +72,9 @@ _SIGNATURES = {
     "fvqa_qav_loss_bwd": [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p],
     "fvqa_scatter_rows": [_p, _p, _p, _i, _p],
     "fvqa_option_score": [_p, _p, _p, _i, _i, _i, _p],
-    "fvqa_f32_to_bf16": [_p, _p, _i64, _p],
+    "fvqa_f32_to_h16": [_p, _p, _i64, _p],
+    "fvqa_grad_scale_prepare": [_p, _f, _p, _p, _p],
+    "fvqa_scale_f32": [_p, _p, _i64, _p],
     "fvqa_gather_rows": [_p, _p, _p, _i, _i, _p],
     "fvqa_scatter_row_vectors": [_p, _p, _p, _i, _i, _p],
     "fvqa_expand_rows": [_p, _p, _p, _i, _i, _p],
@@ -76,10 +89,12 @@ class FvqaError(RuntimeError):
     pass
 
 
-def header_symbols() -> list:
-    """Every function the public header declares (used by the symbol-export test)."""
-    with open(HEADER_PATH) as f:
-        text = f.read()
+def header_symbols(debug: bool = True) -> list:
+    """Every function the public header (and, with `debug`, the test-hook header) declares (symbol-export test)."""
+    text = ""
+    for path in (HEADER_PATH,) + ((DEBUG_HEADER_PATH,) if debug else ()):
+        with open(path) as f:
+            text += f.read()
     return sorted(set(re.findall(r"\b(fvqa_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -103,8 +118,10 @@ def load(build_if_missing: bool = False) -> C.CDLL:
             raise FvqaError(f"libfvqa.so does not export {name}") from e
         fn.argtypes = args
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.fvqa_abi_version() != 1:
-        raise FvqaError("libfvqa.so ABI version mismatch; rebuild")
+    if lib.fvqa_abi_version() != 2:
+        raise FvqaError(f"{LIB_PATH}: ABI version mismatch; rebuild")
+    if lib.fvqa_operand_dtype() != (0 if DTYPE_NAME == "fp16" else 1):
+        raise FvqaError(f"{LIB_PATH} was not built for {DTYPE_NAME} operands; rebuild")
     _lib = lib
     return lib
 

@@ -31,6 +31,7 @@ int attn_init();
 }  // namespace fvqa
 
 extern "C" int fvqa_abi_version(void) { return FVQA_ABI_VERSION; }
+extern "C" int fvqa_operand_dtype(void) { return FVQA_OPERAND_DTYPE; }
 extern "C" const char* fvqa_last_error(void) { return fvqa::g_err; }
 
 extern "C" int fvqa_init(void) {

@@ -10,7 +10,7 @@
 // (no atomics): pass A owns query rows (dQ, D, gate partials), pass B owns keys (dK, dV and the
 // adapter dK_a/dV_a partials); a tiny kernel reduces the per-CTA partials in a fixed order.
 //
-// Round-1 implementation: warp-level mma.sync.m16n8k16 bf16 tensor-core tiles fed from padded
+// Round-1 implementation: warp-level mma.sync.m16n8k16 h16 tensor-core tiles fed from padded
 // shared memory through ldmatrix; 8-warp CTAs own 128 query rows (or 128 keys) and stream the other
 // operand in 64-row tiles through a cp.async double buffer (attention is ~0.5 % of the step's FLOPs;
 // the tcgen05 budget went to the GEMM first).
@@ -28,7 +28,7 @@ constexpr float LN2 = 0.6931471805599453f;
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." FVQA_MMA_TYPE "." FVQA_MMA_TYPE ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -80,10 +80,10 @@ __device__ __forceinline__ void warp_mma_ra_t(float (&acc)[NT][4], const uint32_
 
 // C fragments (two adjacent n-tiles) -> A fragment of one k-block.
 __device__ __forceinline__ void c_to_a(uint32_t (&a)[4], const float (&c0)[4], const float (&c1)[4]) {
-  a[0] = pack_bf16x2(c0[0], c0[1]);
-  a[1] = pack_bf16x2(c0[2], c0[3]);
-  a[2] = pack_bf16x2(c1[0], c1[1]);
-  a[3] = pack_bf16x2(c1[2], c1[3]);
+  a[0] = pack_h16x2(c0[0], c0[1]);
+  a[1] = pack_h16x2(c0[2], c0[3]);
+  a[2] = pack_h16x2(c1[0], c1[1]);
+  a[3] = pack_h16x2(c1[2], c1[3]);
 }
 
 __device__ __forceinline__ float quad_max(float v) {
@@ -109,10 +109,10 @@ __device__ __forceinline__ float col_sum(float v) {
 // ---------------------------------------------------------------------------------------------
 // tile movers
 // ---------------------------------------------------------------------------------------------
-// Load ROWS x HD bf16 (row stride `stride` elements) starting at sequence position row0 into padded
+// Load ROWS x HD h16 (row stride `stride` elements) starting at sequence position row0 into padded
 // smem; rows with position >= limit are zero-filled; optional RoPE at position = row index.
 template <int HD, int ROWS, bool ROPE>
-__device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ g, long stride, int row0, int limit,
+__device__ __forceinline__ void load_tile(h16* s, const h16* __restrict__ g, long stride, int row0, int limit,
                                           const float* __restrict__ cosT, const float* __restrict__ sinT) {
   constexpr int LD = HD + 8;
   constexpr int VPR = HD / 8;
@@ -141,10 +141,10 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* __restrict__ g, l
   }
 }
 
-// Warp writes its 16 x HD fp32 C-fragment tile (optionally inverse-rotated, scaled) as bf16 through a
+// Warp writes its 16 x HD fp32 C-fragment tile (optionally inverse-rotated, scaled) as h16 through a
 // private smem staging area (16 rows, padded) to global rows row0+0..15 (< limit) with 16-byte stores.
 template <int HD, bool INV_ROPE>
-__device__ __forceinline__ void store_tile_warp(bf16* stage, float (&acc)[HD / 8][4], float scale, bf16* __restrict__ g, long stride,
+__device__ __forceinline__ void store_tile_warp(h16* stage, float (&acc)[HD / 8][4], float scale, h16* __restrict__ g, long stride,
                                                 int row0, int limit, const float* __restrict__ cosT, const float* __restrict__ sinT) {
   constexpr int LD = HD + 8;
   const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
@@ -163,7 +163,7 @@ __device__ __forceinline__ void store_tile_warp(bf16* stage, float (&acc)[HD / 8
           a = ra; b = rb;
         }
       }
-      *reinterpret_cast<uint32_t*>(stage + r * LD + nt * 8 + 2 * t) = pack_bf16x2(a, b);
+      *reinterpret_cast<uint32_t*>(stage + r * LD + nt * 8 + 2 * t) = pack_h16x2(a, b);
     }
   }
   __syncwarp();
@@ -188,7 +188,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int HD, int ROWS, int NT>
-__device__ __forceinline__ void load_tile_async(bf16* s, const bf16* __restrict__ g, long stride, int row0, int limit) {
+__device__ __forceinline__ void load_tile_async(h16* s, const h16* __restrict__ g, long stride, int row0, int limit) {
   constexpr int LD = HD + 8;
   constexpr int VPR = HD / 8;
   const uint32_t sbase = smem_u32(s);
@@ -212,18 +212,18 @@ template <int HD>
 __global__ void __launch_bounds__(AT_NT) attn_fwd_kernel(const AttnParams p) {
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sK = sQ + AT_QB * LD;            // [2][64][LD]
-  bf16* sV = sK + 2 * AT_T * LD;         // [2][64][LD]
-  bf16* sKa = sV + 2 * AT_T * LD;
-  bf16* sVa = sKa + AT_AP * LD;
+  h16* sQ = reinterpret_cast<h16*>(smem);
+  h16* sK = sQ + AT_QB * LD;            // [2][64][LD]
+  h16* sV = sK + 2 * AT_T * LD;         // [2][64][LD]
+  h16* sKa = sV + 2 * AT_T * LD;
+  h16* sVa = sKa + AT_AP * LD;
   const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = p.S, D = p.H * HD;
   const long qkv_stride = 3L * D;
-  const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
-  const bf16* kbase = qbase + D;
-  const bf16* vbase = qbase + 2 * D;
+  const h16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
+  const h16* kbase = qbase + D;
+  const h16* vbase = qbase + 2 * D;
   const int r0 = qb * AT_QB;
   const float scale2 = rsqrtf(static_cast<float>(HD)) * LOG2E;
   const int vs = p.vstart[n];
@@ -367,23 +367,23 @@ template <int HD>
 __global__ void __launch_bounds__(AT_NT) attn_bwd_dq_kernel(const AttnParams p) {
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem[];
-  bf16* sQ = reinterpret_cast<bf16*>(smem);
-  bf16* sdO = sQ + AT_QB * LD;
-  bf16* sO = sdO + AT_QB * LD;
-  bf16* sK = sO + AT_QB * LD;             // [2][64][LD]
-  bf16* sV = sK + 2 * AT_T * LD;          // [2][64][LD]
-  bf16* sKa = sV + 2 * AT_T * LD;
-  bf16* sVa = sKa + AT_AP * LD;
+  h16* sQ = reinterpret_cast<h16*>(smem);
+  h16* sdO = sQ + AT_QB * LD;
+  h16* sO = sdO + AT_QB * LD;
+  h16* sK = sO + AT_QB * LD;             // [2][64][LD]
+  h16* sV = sK + 2 * AT_T * LD;          // [2][64][LD]
+  h16* sKa = sV + 2 * AT_T * LD;
+  h16* sVa = sKa + AT_AP * LD;
   float* sRed = reinterpret_cast<float*>(sVa + AT_AP * LD);   // [16] cross-warp gate partials
   const int qb = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = p.S, D = p.H * HD;
   const long qkv_stride = 3L * D;
-  const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
-  const bf16* kbase = qbase + D;
-  const bf16* vbase = qbase + 2 * D;
-  const bf16* obase = p.out + static_cast<long>(n) * S * D + h * HD;
-  const bf16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
+  const h16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
+  const h16* kbase = qbase + D;
+  const h16* vbase = qbase + 2 * D;
+  const h16* obase = p.out + static_cast<long>(n) * S * D + h * HD;
+  const h16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
   const int r0 = qb * AT_QB;
   const float scale = rsqrtf(static_cast<float>(HD));
   const float scale2 = scale * LOG2E;
@@ -559,20 +559,20 @@ template <int HD>
 __global__ void __launch_bounds__(AT_NT) attn_bwd_dkv_kernel(const AttnParams p) {
   constexpr int LD = HD + 8;
   extern __shared__ __align__(16) uint8_t smem[];
-  bf16* sK = reinterpret_cast<bf16*>(smem);   // [128][LD]
-  bf16* sV = sK + AT_QB * LD;                 // [128][LD]
-  bf16* sQ = sV + AT_QB * LD;                 // [2][64][LD]
-  bf16* sdO = sQ + 2 * AT_T * LD;             // [2][64][LD]
+  h16* sK = reinterpret_cast<h16*>(smem);   // [128][LD]
+  h16* sV = sK + AT_QB * LD;                 // [128][LD]
+  h16* sQ = sV + AT_QB * LD;                 // [2][64][LD]
+  h16* sdO = sQ + 2 * AT_T * LD;             // [2][64][LD]
   float* sLse = reinterpret_cast<float*>(sdO + 2 * AT_T * LD);   // [2][64]
   float* sDx = sLse + 2 * AT_T;                                  // [2][64]
   const int kb_idx = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int S = p.S, D = p.H * HD;
   const long qkv_stride = 3L * D;
-  const bf16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
-  const bf16* kbase = qbase + D;
-  const bf16* vbase = qbase + 2 * D;
-  const bf16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
+  const h16* qbase = p.qkv + static_cast<long>(n) * S * qkv_stride + h * HD;
+  const h16* kbase = qbase + D;
+  const h16* vbase = qbase + 2 * D;
+  const h16* dobase = p.dout + static_cast<long>(n) * S * D + h * HD;
   const float scale = rsqrtf(static_cast<float>(HD));
   const float scale2 = scale * LOG2E;
   const uint32_t sQ_u = smem_u32(sQ), sdO_u = smem_u32(sdO), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(AT_NT) attn_bwd_dkv_kernel(const AttnParams p)
   cp_async_wait<0>();
   __syncthreads();   // everyone done with sQ/sdO before they become staging areas
   // 8 warps x 16 rows = 128 staging rows: sQ (2 x 64 rows) for dK, sdO for dV
-  bf16* dkbase = p.dqkv + static_cast<long>(n) * S * qkv_stride + D + h * HD;
+  h16* dkbase = p.dqkv + static_cast<long>(n) * S * qkv_stride + D + h * HD;
   store_tile_warp<HD, true>(sQ + warp * 16 * LD, dk, scale, dkbase, qkv_stride, k0 + warp * 16, S, p.cosT, p.sinT);
   store_tile_warp<HD, false>(sdO + warp * 16 * LD, dv, 1.f, dkbase + D, qkv_stride, k0 + warp * 16, S, nullptr, nullptr);
 }
@@ -819,15 +819,15 @@ static int check_attn_args(int n_seq, int S, int H, int hd, int A, int akv_ld) {
 
 using namespace fvqa;
 
-extern "C" int fvqa_attn_fwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
-                             const float* gate1, const float* gate2, const int32_t* vstart, fvqa_bf16* out, float* lse, int n_seq,
+extern "C" int fvqa_attn_fwd(const fvqa_h16* qkv, const fvqa_h16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
+                             const float* gate1, const float* gate2, const int32_t* vstart, fvqa_h16* out, float* lse, int n_seq,
                              int S, int H, int hd, int A, int max_feats, void* stream) {
   int rc = check_attn_args(n_seq, S, H, hd, A, akv_ld);
   if (rc) return rc;
   AttnParams p{};
-  p.qkv = reinterpret_cast<const bf16*>(qkv); p.akv = reinterpret_cast<const bf16*>(akv); p.akv_ld = akv_ld;
+  p.qkv = reinterpret_cast<const h16*>(qkv); p.akv = reinterpret_cast<const h16*>(akv); p.akv_ld = akv_ld;
   p.cosT = rope_cos; p.sinT = rope_sin; p.gate1 = gate1; p.gate2 = gate2; p.vstart = vstart;
-  p.out = reinterpret_cast<bf16*>(out); p.lse = lse;
+  p.out = reinterpret_cast<h16*>(out); p.lse = lse;
   p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qblocks = (S + AT_QB - 1) / AT_QB;
   dim3 grid(p.qblocks, H, n_seq);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -845,18 +845,18 @@ extern "C" int64_t fvqa_attn_bwd_ws_bytes(int n_seq, int S, int H, int hd, int A
   return 4 * (nh * qblocks * AT_QB + nh * qblocks * 2 + nh * qblocks * 2 * AT_AP * hd);   // D | gate partials | adapter partials
 }
 
-extern "C" int fvqa_attn_bwd(const fvqa_bf16* qkv, const fvqa_bf16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
-                             const float* gate1, const float* gate2, const int32_t* vstart, const fvqa_bf16* out, const float* lse,
-                             const fvqa_bf16* dout, fvqa_bf16* dqkv, float* dakv, float* dgate1, float* dgate2, void* ws, int n_seq,
+extern "C" int fvqa_attn_bwd(const fvqa_h16* qkv, const fvqa_h16* akv, int akv_ld, const float* rope_cos, const float* rope_sin,
+                             const float* gate1, const float* gate2, const int32_t* vstart, const fvqa_h16* out, const float* lse,
+                             const fvqa_h16* dout, fvqa_h16* dqkv, float* dakv, float* dgate1, float* dgate2, void* ws, int n_seq,
                              int S, int H, int hd, int A, int max_feats, void* stream) {
   int rc = check_attn_args(n_seq, S, H, hd, A, akv_ld);
   if (rc) return rc;
   FVQA_REQUIRE(ws != nullptr, FVQA_ERR_INVALID_ARG, "attn_bwd: workspace is null");
   AttnParams p{};
-  p.qkv = reinterpret_cast<const bf16*>(qkv); p.akv = reinterpret_cast<const bf16*>(akv); p.akv_ld = akv_ld;
+  p.qkv = reinterpret_cast<const h16*>(qkv); p.akv = reinterpret_cast<const h16*>(akv); p.akv_ld = akv_ld;
   p.cosT = rope_cos; p.sinT = rope_sin; p.gate1 = gate1; p.gate2 = gate2; p.vstart = vstart;
-  p.out = const_cast<bf16*>(reinterpret_cast<const bf16*>(out)); p.lse = const_cast<float*>(lse);
-  p.dout = reinterpret_cast<const bf16*>(dout); p.dqkv = reinterpret_cast<bf16*>(dqkv);
+  p.out = const_cast<h16*>(reinterpret_cast<const h16*>(out)); p.lse = const_cast<float*>(lse);
+  p.dout = reinterpret_cast<const h16*>(dout); p.dqkv = reinterpret_cast<h16*>(dqkv);
   p.n_seq = n_seq; p.S = S; p.H = H; p.A = A; p.F = max_feats; p.qblocks = (S + AT_QB - 1) / AT_QB;
   const int64_t nh = static_cast<int64_t>(n_seq) * H;
   p.ws_dx = reinterpret_cast<float*>(ws);

@@ -1,19 +1,20 @@
 // Shared declarations of the attention kernels (attention.cu: mma.sync path for any S / hd in {64,128};
 // attention_tc.cu: tcgen05/TMEM path for S <= 128, hd = 128).
 #pragma once
-#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "common.cuh"
 
 namespace fvqa {
 
 constexpr int AT_AP = 16;   // adapter keys padded to one MMA k-block
 
 struct AttnParams {
-  const __nv_bfloat16* qkv; const __nv_bfloat16* akv; int akv_ld;
+  const h16* qkv; const h16* akv; int akv_ld;
   const float* cosT; const float* sinT; const float* gate1; const float* gate2; const int32_t* vstart;
-  __nv_bfloat16* out; float* lse;                       // fwd outputs / bwd inputs
-  const __nv_bfloat16* dout; __nv_bfloat16* dqkv;       // bwd
+  h16* out; float* lse;                       // fwd outputs / bwd inputs
+  const h16* dout; h16* dqkv;       // bwd
   float* ws_dx; float* ws_gate; float* ws_akv;
   int n_seq, S, H, A, F, qblocks;                       // qblocks = ceil(S / 128)
 };

@@ -4,13 +4,16 @@
 //
 //   forward : TMA(Q,K,Ka | V,Va) -> UMMA S = Q K^T, S_a = Q Ka^T -> per-row softmax in registers
 //             (causal + gate2 block bias; separate adapter softmax x tanh(gate1), llama/model.py:111-122)
-//             -> P, P_a as bf16 UMMA operands in shared memory (P overwrites K) -> UMMA O = P V + P_a Va
-//             -> bf16 store. 2 CTAs per SM (110 KB smem, 256 TMEM columns each) overlap one unit's
+//             -> P, P_a as h16 UMMA operands in shared memory (P overwrites K) -> UMMA O = P V + P_a Va
+//             -> h16 store. 2 CTAs per SM (110 KB smem, 256 TMEM columns each) overlap one unit's
 //             loads with the other's math: at S = 128 attention is HBM-bound (65 FLOP/B), not tensor-bound.
 //
 // Shared-memory operand layouts: everything TMA loads is the 128-byte-swizzled [rows][64 elem] box.
 // Used K-major when the contraction runs along the 64-element rows (Q, K, Ka, P) and MN-major when it
 // runs along the box rows (V, Va as B of P.V: N = head dim contiguous, K = keys).
+#include <atomic>
+
+#include "../../include/fvqa_debug.h"
 #include "attention_tc.cuh"
 #include "tmap.h"
 
@@ -19,12 +22,12 @@ namespace fvqa {
 namespace {
 
 // ---- forward shared-memory map (bytes from the 1024-aligned base) ----
-constexpr int F_SQ = 0;               // [2][128][64] bf16; O staging for the TMA store at the end
+constexpr int F_SQ = 0;               // [2][128][64] h16; O staging for the TMA store at the end
 constexpr int F_SK = 32768;           // [2][128][64]; overwritten by P after S is complete
 constexpr int F_SV = 65536;           // [2][128][64]
 constexpr int F_SKA = 98304;          // [2][16][64]
 constexpr int F_SVA = 102400;         // [2][16][64]
-constexpr int F_SPA = 106496;         // P_a: [16 row groups][2 k-chunks][8 rows][8] bf16, no swizzle (4 KB)
+constexpr int F_SPA = 106496;         // P_a: [16 row groups][2 k-chunks][8 rows][8] h16, no swizzle (4 KB)
 constexpr int F_BAR = 110592;
 constexpr int F_ROW = F_BAR + 64;     // [4][128] floats: partial row max / sum
 constexpr int F_SMEM = F_ROW + 2048 + 1024;
@@ -80,14 +83,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     mbar_wait(bar_qk, 0);
     tc_fence_after();
-    constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0);
+    constexpr uint32_t id_s = idesc_h16(128, 128, 0, 0), id_a = idesc_h16(128, 16, 0, 0);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
       const uint64_t a = umma_desc_k_sw128(sbase + F_SQ + (ks >> 2) * 16384) + static_cast<uint64_t>(2 * (ks & 3));
       const uint64_t b = umma_desc_k_sw128(sbase + F_SK + (ks >> 2) * 16384) + static_cast<uint64_t>(2 * (ks & 3));
       const uint64_t ba = umma_desc_k_sw128(sbase + F_SKA + (ks >> 2) * 2048) + static_cast<uint64_t>(2 * (ks & 3));
-      umma_bf16_ss(tmem, a, b, id_s, ks > 0 ? 1u : 0u);            // S   -> columns [0,128)
-      umma_bf16_ss(tmem + 128, a, ba, id_a, ks > 0 ? 1u : 0u);     // S_a -> columns [128,144)
+      umma_h16_ss(tmem, a, b, id_s, ks > 0 ? 1u : 0u);            // S   -> columns [0,128)
+      umma_h16_ss(tmem + 128, a, ba, id_a, ks > 0 ? 1u : 0u);     // S_a -> columns [128,144)
     }
     umma_commit(bar_s);
   }
@@ -148,7 +151,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     }
     const float ia = tg / la;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) pa[e] = pack_bf16x2(sa[2 * e] * ia, sa[2 * e + 1] * ia);
+    for (int e = 0; e < 8; ++e) pa[e] = pack_h16x2(sa[2 * e] * ia, sa[2 * e + 1] * ia);
   }
   tc_fence_before();
   __syncthreads();                                     // every S / S_a value is in registers; partial maxima published
@@ -165,11 +168,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   __syncthreads();
   l = s_sum[r] + s_sum[128 + r];
   const float inv = 1.f / l;
-  // P (normalised, bf16, two keys per 32-bit column) -> TMEM columns [32 part, 32 part + 32) over the consumed S
+  // P (normalised, h16, two keys per 32-bit column) -> TMEM columns [32 part, 32 part + 32) over the consumed S
   {
     uint32_t pk[32];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) pk[e] = pack_bf16x2(s[2 * e] * inv, s[2 * e + 1] * inv);
+    for (int e = 0; e < 32; ++e) pk[e] = pack_h16x2(s[2 * e] * inv, s[2 * e + 1] * inv);
     tmem_st_32x32(tlane + static_cast<uint32_t>(part * 32), pk);
   }
   if (part == 1) tmem_st_32x8(tlane + 64u, pa);        // P_a -> TMEM columns [64,72)
@@ -182,17 +185,17 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tc_fence_after();
     mbar_wait(bar_v, 0);
     tc_fence_after();
-    constexpr uint32_t id_o = idesc_bf16(128, 128, 0, 1);
+    constexpr uint32_t id_o = idesc_h16(128, 128, 0, 1);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks)                                 // O = P V, A = P from TMEM (8 columns = 16 keys per step)
-      umma_bf16_ts(tmem + 128, tmem + static_cast<uint32_t>(ks * 8), desc_mn_sw128(sbase + F_SV + ks * 2048, 16384), id_o, ks > 0 ? 1u : 0u);
-    umma_bf16_ts(tmem + 128, tmem + 64u, desc_mn_sw128(sbase + F_SVA, 2048), id_o, 1u);   // += P_a Va
+      umma_h16_ts(tmem + 128, tmem + static_cast<uint32_t>(ks * 8), desc_mn_sw128(sbase + F_SV + ks * 2048, 16384), id_o, ks > 0 ? 1u : 0u);
+    umma_h16_ts(tmem + 128, tmem + 64u, desc_mn_sw128(sbase + F_SVA, 2048), id_o, 1u);   // += P_a Va
     umma_commit(bar_o);
   }
   __syncwarp();
   mbar_wait(bar_o, 0);
   tc_fence_after();
-  // O -> bf16 -> swizzled staging (Q's buffer: every MMA that read it has retired) -> TMA store
+  // O -> h16 -> swizzled staging (Q's buffer: every MMA that read it has retired) -> TMA store
 #pragma unroll
   for (int c = 2 * part; c < 2 * part + 2; ++c) {
     uint32_t v[32];
@@ -224,11 +227,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // backward: one CTA (128 threads, 1 per SM: 210 KB smem, all 512 TMEM columns) per (sequence, head).
 //   UMMA  S = Q K^T, S_a = Q Ka^T, dP = dO V^T, dP_a = dO Va^T          (TMEM)
-//   rows  pass 1: P = exp2(S - lse) (kept as packed bf16 in registers, also written over V as a UMMA operand),
+//   rows  pass 1: P = exp2(S - lse) (kept as packed h16 in registers, also written over V as a UMMA operand),
 //                 D = sum_k P dP  (= <dO, O> minus the adapter part: no O / dO reads from global memory);
 //         pass 2: dS = P (dP - D) / sqrt(hd) (+ gate2 partial); adapter softmax backward (gate1 partial);
 //   UMMA  dV = P^T dO, dK = dS^T Q, dQ = dS K + dS_a Ka, dKa^T = Q^T dS_a, dVa^T = dO^T (tanh(g1) P_a)
-//   rows  inverse RoPE on dQ / dK (fp16 cos|sin table staged in smem at kernel start), bf16 -> swizzled smem
+//   rows  inverse RoPE on dQ / dK (fp16 cos|sin table staged in smem at kernel start), h16 -> swizzled smem
 //         -> TMA stores; per-(sequence, head) adapter / gate partials to the workspace (reduced over sequences
 //         in a fixed order by attn_bwd_reduce_kernel -> deterministic).
 // Every [128][64]-element box is used K-major for one product and MN-major for another (same bytes).
@@ -314,20 +317,20 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   // RoPE table of this sequence's positions -> smem as fp16 (cos, sin) pairs (coalesced; overlaps the TMA loads)
   stage_rope_table(sgen + B_ROPE, p.cosT, p.sinT, 0, S, tid, BW_THREADS);
   if (tid == 0) {
-    constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0);
+    constexpr uint32_t id_s = idesc_h16(128, 128, 0, 0), id_a = idesc_h16(128, 16, 0, 0);
     mbar_wait(bar_a, 0);
     tc_fence_after();
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      umma_bf16_ss(tmem + T_S, kmaj(B_SQ, 16384, ks), kmaj(B_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
-      umma_bf16_ss(tmem + T_SA, kmaj(B_SQ, 16384, ks), kmaj(B_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_S, kmaj(B_SQ, 16384, ks), kmaj(B_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_SA, kmaj(B_SQ, 16384, ks), kmaj(B_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
     }
     mbar_wait(bar_b, 0);
     tc_fence_after();
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      umma_bf16_ss(tmem + T_DP, kmaj(B_SDO, 16384, ks), kmaj(B_SV, 16384, ks), id_s, ks > 0 ? 1u : 0u);
-      umma_bf16_ss(tmem + T_DPA, kmaj(B_SDO, 16384, ks), kmaj(B_SVA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DP, kmaj(B_SDO, 16384, ks), kmaj(B_SV, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DPA, kmaj(B_SDO, 16384, ks), kmaj(B_SVA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar_m1);
   }
@@ -434,8 +437,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int j = q * 8 + e;
-        // P as the UMMA sees it (bf16), like the unfused formulation
-        const float pb = __bfloat162float(__float2bfloat16_rn(pf[j]));
+        // P as the UMMA sees it (h16), like the unfused formulation
+        const float pb = h2f(f2h(pf[j]));
         const float ds = live ? pb * fmaf(__uint_as_float(w[j]), scale, -dxs) : 0.f;
         if (bias_any && ch * 32 + j >= bias_c0 && ch * 32 + j < bias_c1) g2_part += ds;
         fd[e] = ds;
@@ -450,21 +453,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   if (tid == 0) {
     tc_fence_after();
-    constexpr uint32_t id_tt = idesc_bf16(128, 128, 1, 1), id_q = idesc_bf16(128, 128, 0, 1), id_at = idesc_bf16(128, 16, 1, 1);
+    constexpr uint32_t id_tt = idesc_h16(128, 128, 1, 1), id_q = idesc_h16(128, 128, 0, 1), id_at = idesc_h16(128, 16, 1, 1);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks)      // dQ[row][d] = sum_keys dS[row][key] K[key][d]
-      umma_bf16_ss(tmem + T_DQ, kmaj(B_SDS, 16384, ks), mnmaj(B_SK, 16384, ks), id_q, ks > 0 ? 1u : 0u);
-    umma_bf16_ss(tmem + T_DQ, desc_nosw(sbase + B_SDSA, 128, 256), desc_mn_sw128(sbase + B_SKA, 2048), id_q, 1u);   // += dS_a Ka
+      umma_h16_ss(tmem + T_DQ, kmaj(B_SDS, 16384, ks), mnmaj(B_SK, 16384, ks), id_q, ks > 0 ? 1u : 0u);
+    umma_h16_ss(tmem + T_DQ, desc_nosw(sbase + B_SDSA, 128, 256), desc_mn_sw128(sbase + B_SKA, 2048), id_q, 1u);   // += dS_a Ka
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks)      // dK[key][d] = sum_rows dS[row][key] Q[row][d]
-      umma_bf16_ss(tmem + T_DK, mnmaj(B_SDS, 16384, ks), mnmaj(B_SQ, 16384, ks), id_tt, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DK, mnmaj(B_SDS, 16384, ks), mnmaj(B_SQ, 16384, ks), id_tt, ks > 0 ? 1u : 0u);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks)      // dV[key][d] = sum_rows P[row][key] dO[row][d]
-      umma_bf16_ss(tmem + T_DV, mnmaj(B_SV, 16384, ks), mnmaj(B_SDO, 16384, ks), id_tt, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DV, mnmaj(B_SV, 16384, ks), mnmaj(B_SDO, 16384, ks), id_tt, ks > 0 ? 1u : 0u);
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {    // dKa^T[d][a] = sum_rows Q[row][d] dS_a[row][a];  dVa^T[d][a] = sum_rows dO[row][d] (tg P_a)[row][a]
-      umma_bf16_ss(tmem + T_DKA, mnmaj(B_SQ, 16384, ks), desc_nosw(sbase + B_SDSA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
-      umma_bf16_ss(tmem + T_DKA + 16, mnmaj(B_SDO, 16384, ks), desc_nosw(sbase + B_SPA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DKA, mnmaj(B_SQ, 16384, ks), desc_nosw(sbase + B_SDSA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DKA + 16, mnmaj(B_SDO, 16384, ks), desc_nosw(sbase + B_SPA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar_m2);
   }
@@ -486,7 +489,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 
   mbar_wait(bar_m2, 0);
   tc_fence_after();
-  // ---------------- epilogue: TMEM -> (inverse RoPE) -> bf16 -> swizzled smem -> TMA store ----------------
+  // ---------------- epilogue: TMEM -> (inverse RoPE) -> h16 -> swizzled smem -> TMA store ----------------
 #pragma unroll 1
   for (int which = 0; which < 3; ++which) {            // 0: dQ (row = query), 1: dK (row = key), 2: dV
     const uint32_t tcol = which == 0 ? T_DQ : (which == 1 ? T_DK : T_DV);
@@ -534,7 +537,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
-static int g_use_tc = 1;
+static std::atomic<int> g_use_tc{1};   // test hook (fvqa_attn_debug_use_tc), process-wide
 
 bool attn_tc_supported(int S, int hd, int A) { return g_use_tc != 0 && hd == 128 && S <= 128 && A <= AT_AP; }
 bool attn_tcl_supported(int S, int hd, int A) { return g_use_tc != 0 && hd == 128 && S > 128 && A <= AT_AP; }

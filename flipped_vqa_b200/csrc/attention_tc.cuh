@@ -34,8 +34,8 @@ __device__ __forceinline__ uint64_t desc_nosw(uint32_t smem_addr, uint32_t lbo_b
   d |= static_cast<uint64_t>(1) << 46;
   return d;
 }
-__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
+__host__ __device__ constexpr uint32_t idesc_h16(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (FVQA_UMMA_FMT << 7) | (FVQA_UMMA_FMT << 10) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16) |
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_akv,
                     const __grid_constant__ CUtensorMap tm_out, const AttnParams p) {
   // Single pass over the key tiles j <= i with an online softmax: S = Q K_j^T (UMMA) -> per-row p = exp2(s - m_ref)
-  // -> P (bf16) written back into TMEM over S -> O += P V_j (TS-mode UMMA, accumulator in TMEM). The reference maximum
+  // -> P (h16) written back into TMEM over S -> O += P V_j (TS-mode UMMA, accumulator in TMEM). The reference maximum
   // m_ref only moves when a tile's maximum exceeds it by more than 2^8 (then O and l are rescaled through TMEM), so
   // rescaling is rare; the final O / l and the adapter term (tanh(g1) softmax_a, pre-multiplied by l) end the row.
   extern __shared__ uint8_t smem_raw[];
@@ -68,7 +68,7 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + LF_BAR + 40);
   const uint32_t tlane = tmem + (static_cast<uint32_t>(warp * 32) << 16);
   const int c = h * 128;
-  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0), id_o = idesc_bf16(128, 128, 0, 1);
+  constexpr uint32_t id_s = idesc_h16(128, 128, 0, 0), id_a = idesc_h16(128, 16, 0, 0), id_o = idesc_h16(128, 128, 0, 1);
   constexpr uint32_t T_S = 0, T_O = 128, T_SA = 128;      // S_a sits in O's columns until the first P.V overwrites them
   auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
   auto load_k = [&](int j) {
@@ -106,8 +106,8 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        umma_bf16_ss(tmem + T_S, kdesc(LF_SQ, 16384, ks), kdesc(LF_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
-        if (j == 0) umma_bf16_ss(tmem + T_SA, kdesc(LF_SQ, 16384, ks), kdesc(LF_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+        umma_h16_ss(tmem + T_S, kdesc(LF_SQ, 16384, ks), kdesc(LF_SK, 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        if (j == 0) umma_h16_ss(tmem + T_SA, kdesc(LF_SQ, 16384, ks), kdesc(LF_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
       }
       umma_commit(bar_s);
     }
@@ -176,7 +176,7 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       l_run *= f;
       m_ref = m_new;
     }
-    // P = exp2(x - m_ref) (bf16, two keys per column) -> TMEM columns [0,64) over the consumed S
+    // P = exp2(x - m_ref) (h16, two keys per column) -> TMEM columns [0,64) over the consumed S
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
       uint32_t pk[32];
@@ -184,7 +184,7 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       for (int e = 0; e < 32; ++e) {
         const float p0 = exp2f(x[hf * 64 + 2 * e] - m_ref), p1 = exp2f(x[hf * 64 + 2 * e + 1] - m_ref);
         l_run += p0 + p1;
-        pk[e] = pack_bf16x2(p0, p1);
+        pk[e] = pack_h16x2(p0, p1);
       }
       tmem_st_32x32(tlane + T_S + static_cast<uint32_t>(hf * 32), pk);
     }
@@ -192,7 +192,7 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       // adapter probabilities pre-multiplied by l so that the final O / l leaves tanh(g1) softmax_a . Va
       uint32_t pa[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) pa[e] = pack_bf16x2(pa_n[2 * e] * l_run, pa_n[2 * e + 1] * l_run);
+      for (int e = 0; e < 8; ++e) pa[e] = pack_h16x2(pa_n[2 * e] * l_run, pa_n[2 * e + 1] * l_run);
       tmem_st_32x8(tlane + T_S + 64u, pa);
     }
     tmem_st_wait();
@@ -205,9 +205,9 @@ attn_fwd_tcl_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_con
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)
-        umma_bf16_ts(tmem + T_O, tmem + T_S + static_cast<uint32_t>(ks * 8), desc_mn_sw128(sbase + LF_SV + ks * 2048, 16384), id_o,
+        umma_h16_ts(tmem + T_O, tmem + T_S + static_cast<uint32_t>(ks * 8), desc_mn_sw128(sbase + LF_SV + ks * 2048, 16384), id_o,
                      (j > 0 || ks > 0) ? 1u : 0u);
-      if (j == qi) umma_bf16_ts(tmem + T_O, tmem + T_S + 64u, desc_mn_sw128(sbase + LF_SVA, 2048), id_o, 1u);
+      if (j == qi) umma_h16_ts(tmem + T_O, tmem + T_S + 64u, desc_mn_sw128(sbase + LF_SVA, 2048), id_o, 1u);
       umma_commit(bar_o);
       // the next S overwrites P's columns and the next V load overwrites V: both wait for this P.V
       mbar_wait(bar_o, ph_o);
@@ -291,8 +291,8 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   const int c = h * 128;
   auto kdesc = [&](int off, int blk, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * blk) + static_cast<uint64_t>(2 * (ks & 3)); };
   auto mndesc = [&](int off, int lbo, int ks) { return desc_mn_sw128(sbase + off + ks * 2048, lbo); };
-  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_a = idesc_bf16(128, 16, 0, 0), id_q = idesc_bf16(128, 128, 0, 1),
-                     id_at = idesc_bf16(128, 16, 1, 1);
+  constexpr uint32_t id_s = idesc_h16(128, 128, 0, 0), id_a = idesc_h16(128, 16, 0, 0), id_q = idesc_h16(128, 128, 0, 1),
+                     id_at = idesc_h16(128, 16, 1, 1);
 
   // K/V tile buffers: 0 = (A_SK, A_SV); 1 = (A_SDS once the O tile has been consumed, A_ROPE)
   auto koff = [&](int buf) { return buf ? A_SDS : A_SK; };
@@ -325,8 +325,8 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     tc_fence_after();
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) {
-      umma_bf16_ss(tmem + T_SA, kdesc(A_SQ, 16384, ks), kdesc(A_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
-      umma_bf16_ss(tmem + T_DPA, kdesc(A_SDO, 16384, ks), kdesc(A_SVA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_SA, kdesc(A_SQ, 16384, ks), kdesc(A_SKA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
+      umma_h16_ss(tmem + T_DPA, kdesc(A_SDO, 16384, ks), kdesc(A_SVA, 2048, ks), id_a, ks > 0 ? 1u : 0u);
     }
     umma_commit(bar_ma);
   }
@@ -411,15 +411,15 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        umma_bf16_ss(tmem + T_S, kdesc(A_SQ, 16384, ks), kdesc(koff(buf), 16384, ks), id_s, ks > 0 ? 1u : 0u);
-        umma_bf16_ss(tmem + T_DP, kdesc(A_SDO, 16384, ks), kdesc(voff(buf), 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_h16_ss(tmem + T_S, kdesc(A_SQ, 16384, ks), kdesc(koff(buf), 16384, ks), id_s, ks > 0 ? 1u : 0u);
+        umma_h16_ss(tmem + T_DP, kdesc(A_SDO, 16384, ks), kdesc(voff(buf), 16384, ks), id_s, ks > 0 ? 1u : 0u);
       }
       umma_commit(bar_m1);
     }
     __syncwarp();
     mbar_wait(bar_m1, ph_m1);
     tc_fence_after();
-    // dS (bf16, two keys per 32-bit column) is written back IN PLACE over S: this thread owns chunk `part` (fp32 columns
+    // dS (h16, two keys per 32-bit column) is written back IN PLACE over S: this thread owns chunk `part` (fp32 columns
     // [32 part, +32) -> packed columns [16 part, +16)); all four parts read before anyone writes (barrier in between)
     const int ch = part;
     const bool live = (j < qi) || ch <= quad;              // diagonal tile: chunks beyond the warp's last row are masked
@@ -453,7 +453,7 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             if (biased) g2_part += dse;
             ds[u] = dse;
           }
-          dd[e >> 1] = pack_bf16x2(ds[0], ds[1]);
+          dd[e >> 1] = pack_h16x2(ds[0], ds[1]);
         }
       } else {
 #pragma unroll
@@ -468,13 +468,13 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)                      // dQ[row][d] += sum_keys dS[row][key] K_j[key][d], A = dS from TMEM
-        umma_bf16_ts(tmem + T_DQ, tmem + T_S + static_cast<uint32_t>(ks * 8), mndesc(koff(buf), 16384, ks), id_q, (j > 0 || ks > 0) ? 1u : 0u);
+        umma_h16_ts(tmem + T_DQ, tmem + T_S + static_cast<uint32_t>(ks * 8), mndesc(koff(buf), 16384, ks), id_q, (j > 0 || ks > 0) ? 1u : 0u);
       if (j == qi) {
-        umma_bf16_ss(tmem + T_DQ, desc_nosw(sbase + A_SDSA, 128, 256), desc_mn_sw128(sbase + A_SKA, 2048), id_q, 1u);
+        umma_h16_ss(tmem + T_DQ, desc_nosw(sbase + A_SDSA, 128, 256), desc_mn_sw128(sbase + A_SKA, 2048), id_q, 1u);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          umma_bf16_ss(tmem + T_DKA, mndesc(A_SQ, 16384, ks), desc_nosw(sbase + A_SDSA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
-          umma_bf16_ss(tmem + T_DKA + 16, mndesc(A_SDO, 16384, ks), desc_nosw(sbase + A_SPA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
+          umma_h16_ss(tmem + T_DKA, mndesc(A_SQ, 16384, ks), desc_nosw(sbase + A_SDSA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
+          umma_h16_ss(tmem + T_DKA + 16, mndesc(A_SDO, 16384, ks), desc_nosw(sbase + A_SPA + ks * 512, 256, 128), id_at, ks > 0 ? 1u : 0u);
         }
       }
       umma_commit(bar_m2);
@@ -539,7 +539,7 @@ attn_bwd_tcl_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 
 // ---------------------------------------------------------------------------------------------
 // backward B: key tile owner -> dK, dV. Transposed formulation: S^T = K_j Q_i^T and dP^T = V_j dO_i^T put the KEYS on
-// the TMEM lanes, so P^T and dS^T are written back into TMEM (bf16, two rows per 32-bit column, in place over S^T /
+// the TMEM lanes, so P^T and dS^T are written back into TMEM (h16, two rows per 32-bit column, in place over S^T /
 // dP^T) and feed dV += P^T dO_i, dK += dS^T Q_i as TMEM-resident A operands (TS-mode UMMA): no shared-memory round
 // trip, and the 64 KB that P / dS occupied become a second Q / dO buffer -> the TMA loads of tile i+1 overlap tile i.
 // ---------------------------------------------------------------------------------------------
@@ -583,7 +583,7 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   const int c = h * 128;
   auto kdesc = [&](int off, int ks) { return umma_desc_k_sw128(sbase + off + (ks >> 2) * 16384) + static_cast<uint64_t>(2 * (ks & 3)); };
   auto mndesc = [&](int off, int ks) { return desc_mn_sw128(sbase + off + ks * 2048, 16384); };
-  constexpr uint32_t id_s = idesc_bf16(128, 128, 0, 0), id_t = idesc_bf16(128, 128, 0, 1);
+  constexpr uint32_t id_s = idesc_h16(128, 128, 0, 0), id_t = idesc_h16(128, 128, 0, 1);
   const long nh = static_cast<long>(n) * p.H + h;
 
   auto load_q_tile = [&](int qi, int buf) {            // tid 0 only
@@ -630,8 +630,8 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        umma_bf16_ss(tmem + T_ST, kdesc(K_SK, ks), kdesc(qoff, ks), id_s, ks > 0 ? 1u : 0u);      // S^T  = K_j Q_i^T
-        umma_bf16_ss(tmem + T_DPT, kdesc(K_SV, ks), kdesc(dooff, ks), id_s, ks > 0 ? 1u : 0u);    // dP^T = V_j dO_i^T
+        umma_h16_ss(tmem + T_ST, kdesc(K_SK, ks), kdesc(qoff, ks), id_s, ks > 0 ? 1u : 0u);      // S^T  = K_j Q_i^T
+        umma_h16_ss(tmem + T_DPT, kdesc(K_SV, ks), kdesc(dooff, ks), id_s, ks > 0 ? 1u : 0u);    // dP^T = V_j dO_i^T
       }
       umma_commit(bar_m1);
     }
@@ -683,8 +683,8 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
             pv[u] = pe;
             ds[u] = pe * fmaf(__uint_as_float(vd_[cc * 32 + e]), scale, -dxv[u]);                  // P (dP - D) / sqrt(hd)
           }
-          pp[q4 * 2] = pack_bf16x2(pv[0], pv[1]); pp[q4 * 2 + 1] = pack_bf16x2(pv[2], pv[3]);
-          dd[q4 * 2] = pack_bf16x2(ds[0], ds[1]); dd[q4 * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+          pp[q4 * 2] = pack_h16x2(pv[0], pv[1]); pp[q4 * 2 + 1] = pack_h16x2(pv[2], pv[3]);
+          dd[q4 * 2] = pack_h16x2(ds[0], ds[1]); dd[q4 * 2 + 1] = pack_h16x2(ds[2], ds[3]);
         }
       } else {
 #pragma unroll
@@ -702,10 +702,10 @@ attn_bwd_tcl_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       const uint32_t accum = it > 0 ? 1u : 0u;
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)                      // dV[key][d] += sum_rows P^T[key][row] dO[row][d]
-        umma_bf16_ts(tmem + T_DV, tmem + T_ST + static_cast<uint32_t>(ks * 8), mndesc(dooff, ks), id_t, (accum || ks > 0) ? 1u : 0u);
+        umma_h16_ts(tmem + T_DV, tmem + T_ST + static_cast<uint32_t>(ks * 8), mndesc(dooff, ks), id_t, (accum || ks > 0) ? 1u : 0u);
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks)                      // dK[key][d] += sum_rows dS^T[key][row] Q[row][d]
-        umma_bf16_ts(tmem + T_DK, tmem + T_DPT + static_cast<uint32_t>(ks * 8), mndesc(qoff, ks), id_t, (accum || ks > 0) ? 1u : 0u);
+        umma_h16_ts(tmem + T_DK, tmem + T_DPT + static_cast<uint32_t>(ks * 8), mndesc(qoff, ks), id_t, (accum || ks > 0) ? 1u : 0u);
       umma_commit(bar_m2);
     }
     __syncwarp();

@@ -1,6 +1,8 @@
 // Shared device helpers for the flipped-vqa B200 kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -9,7 +11,36 @@
 
 namespace fvqa {
 
-typedef __nv_bfloat16 bf16;
+// ---------------------------------------------------------------------------------------------
+// The 16-bit operand format of this build ("h16"): every tensor-core operand - frozen weights, activations,
+// gradients - is fp16 (default) or, with -DFVQA_BF16, bf16. tcgen05.mma kind::f16 runs both at the same rate but
+// rejects mixed A/B formats (illegal instruction, tools/mixed_umma_probe.py), so the choice is per library.
+// fp16 is the reference's own dtype (llama_vqa.py:63) and the only one whose operand rounding keeps the
+// full-depth gradients within north_star's 2e-2 (profiles/r2_numerics_ablation.txt).
+// ---------------------------------------------------------------------------------------------
+#if defined(FVQA_BF16)
+typedef __nv_bfloat16 h16;
+typedef __nv_bfloat162 h162;
+#define FVQA_MMA_TYPE "bf16"
+#define FVQA_UMMA_FMT 1u
+#define FVQA_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define FVQA_OPERAND_DTYPE 1
+__device__ __forceinline__ h16 f2h(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float h2f(h16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ h162 f2h2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+__device__ __forceinline__ float2 h22f2(h162 v) { return __bfloat1622float2(v); }
+#else
+typedef __half h16;
+typedef __half2 h162;
+#define FVQA_MMA_TYPE "f16"
+#define FVQA_UMMA_FMT 0u
+#define FVQA_TMAP_DTYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define FVQA_OPERAND_DTYPE 0
+__device__ __forceinline__ h16 f2h(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float h2f(h16 x) { return __half2float(x); }
+__device__ __forceinline__ h162 f2h2(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+__device__ __forceinline__ float2 h22f2(h162 v) { return __half22float2(v); }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing (host)
@@ -28,24 +59,24 @@ int check_launch(const char* what);
 // ---------------------------------------------------------------------------------------------
 // small numeric helpers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float h16_round(float x) { return h2f(f2h(x)); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_h16x2(float lo, float hi) {
+  h162 v = f2h2(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+__device__ __forceinline__ float2 unpack_h16x2(uint32_t u) {
+  h162 v = *reinterpret_cast<h162*>(&u);
+  return h22f2(v);
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  float2 a = unpack_h16x2(u.x), b = unpack_h16x2(u.y), c = unpack_h16x2(u.z), d = unpack_h16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack_h16x2(f[0], f[1]); u.y = pack_h16x2(f[2], f[3]);
+  u.z = pack_h16x2(f[4], f[5]); u.w = pack_h16x2(f[6], f[7]);
   return u;
 }
 
@@ -164,8 +195,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; bf16 inputs, fp32 accumulate; one thread issues.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T ; h16 inputs, fp32 accumulate; one thread issues.
+__device__ __forceinline__ void umma_h16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -175,7 +206,7 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, ui
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]^T : A operand resident in TMEM (lane = M index, 16-bit elements packed two per
 // 32-bit column along K, K-major only).
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_h16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -277,7 +308,7 @@ __device__ __forceinline__ void tmem_relinquish_pair() {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_h16_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -315,7 +346,7 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
-// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B; 8-row
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 h16 = 128 B; 8-row
 // swizzle atoms 1024 B apart). Bit layout follows the sm_100 "SmemDescriptor" (start address,
 // LBO, SBO, version=1, layout_type=SWIZZLE_128B).
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
@@ -327,9 +358,9 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor: bf16 x bf16 -> fp32, A and B K-major, dense.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+// Instruction descriptor: h16 x h16 -> fp32 (a/b format fields: 0 = fp16, 1 = bf16), A and B K-major, dense.
+__host__ __device__ constexpr uint32_t umma_idesc_h16(int m, int n) {
+  return (1u << 4) | (FVQA_UMMA_FMT << 7) | (FVQA_UMMA_FMT << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 }  // namespace fvqa

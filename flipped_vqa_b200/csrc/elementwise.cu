@@ -1,6 +1,6 @@
 // HBM-bound row kernels: fused RMSNorm fwd/bwd (+gather/scatter variants), fused SwiGLU fwd/bwd.
 // Reference semantics: llama/model.py:31-42 (RMSNorm), :142 (SwiGLU). The residual stream (and its
-// gradient) is fp32, GEMM operands are bf16; 16-byte vector accesses; math in fp32. One CTA per row for the norms (row cached in registers), flat
+// gradient) is fp32, GEMM operands are h16; 16-byte vector accesses; math in fp32. One CTA per row for the norms (row cached in registers), flat
 // grid-stride for SwiGLU.
 #include "common.cuh"
 
@@ -20,13 +20,13 @@ __device__ __forceinline__ void store8f(float* p, const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// RMSNorm forward on the fp32 residual stream:  y = bf16(x * rstd * w)
+// RMSNorm forward on the fp32 residual stream:  y = h16(x * rstd * w)
 // idx == nullptr: row r reads x[r]; otherwise row r reads x[idx[r]] (idx<0 -> zero row).
 // ---------------------------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
-    const float* __restrict__ x, const int32_t* __restrict__ idx, const bf16* __restrict__ w,
-    bf16* __restrict__ y, float* __restrict__ rstd_out, int dim, float eps) {
+    const float* __restrict__ x, const int32_t* __restrict__ idx, const h16* __restrict__ w,
+    h16* __restrict__ y, float* __restrict__ rstd_out, int dim, float eps) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int nvec = dim >> 3;
@@ -69,14 +69,14 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
 
 // ---------------------------------------------------------------------------------------------
 // RMSNorm backward (dX only). With n = x*rstd, dn = dy*w:
-//   dx = rstd * (dn - n * mean(dn * n)) (+ dres)      fp32 out (+ optional bf16 copy: next GEMM operand)
+//   dx = rstd * (dn - n * mean(dn * n)) (+ dres)      fp32 out (+ optional h16 copy: next GEMM operand)
 // scatter variant: output row = idx[r] (rows with idx<0 skipped), no residual.
 // ---------------------------------------------------------------------------------------------
 template <int MAXV>
 __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
-    const bf16* __restrict__ dy, const float* __restrict__ x, const int32_t* __restrict__ idx,
-    const bf16* __restrict__ w, const float* __restrict__ rstd_in, const float* __restrict__ dres,
-    float* __restrict__ dx, bf16* __restrict__ dx_bf16, int dim) {
+    const h16* __restrict__ dy, const float* __restrict__ x, const int32_t* __restrict__ idx,
+    const h16* __restrict__ w, const float* __restrict__ rstd_in, const float* __restrict__ dres,
+    float* __restrict__ dx, h16* __restrict__ dx_h16, int dim) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int nvec = dim >> 3;
@@ -123,16 +123,16 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fr[i][j] + rstd * (dn[i][j] - xr[i][j] * rstd * dot);
       store8f(dxrow + v * 8, o);
-      if (dx_bf16) reinterpret_cast<uint4*>(dx_bf16 + src * dim)[v] = pack8(o);
+      if (dx_h16) reinterpret_cast<uint4*>(dx_h16 + src * dim)[v] = pack8(o);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// SwiGLU. g = [rows, 2*hid] (a | b). fwd: c = bf16( silu(a) * b ).
+// SwiGLU. g = [rows, 2*hid] (a | b). fwd: c = h16( silu(a) * b ).
 // bwd: da = dc * b * s * (1 + a * (1 - s)), db = dc * silu(a), s = sigmoid(a).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ g, bf16* __restrict__ c,
+__global__ void __launch_bounds__(256) swiglu_fwd_kernel(const h16* __restrict__ g, h16* __restrict__ c,
                                                           long rows, int hid) {
   const int hv = hid >> 3;
   const long total = rows * hv;
@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dc, const bf16* __restrict__ g,
-                                                          bf16* __restrict__ dg, long rows, int hid) {
+__global__ void __launch_bounds__(256) swiglu_bwd_kernel(const h16* __restrict__ dc, const h16* __restrict__ g,
+                                                          h16* __restrict__ dg, long rows, int hid) {
   const int hv = hid >> 3;
   const long total = rows * hv;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
@@ -178,10 +178,10 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
   }
 }
 
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long n) {
+__global__ void f32_to_h16_kernel(const float* __restrict__ src, h16* __restrict__ dst, long n) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x)
-    dst[i] = __float2bfloat16_rn(src[i]);
+    dst[i] = f2h(src[i]);
 }
 
 // dst[i, :] = src[idx[i], :] (GATHER) or dst[idx[i], :] = src[i, :] (!GATHER); rows of `vecs` 16-byte vectors
@@ -226,73 +226,73 @@ static int elementwise_grid(long work_items, int threads) {
 
 using namespace fvqa;
 
-extern "C" int fvqa_rmsnorm_fwd(const float* x, const fvqa_bf16* w, fvqa_bf16* y, float* rstd, int rows,
+extern "C" int fvqa_rmsnorm_fwd(const float* x, const fvqa_h16* w, fvqa_h16* y, float* rstd, int rows,
                                 int dim, float eps, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED,
                "rmsnorm: dim %d must be a multiple of 8 and <= %d", dim, 8 * NORM_THREADS * NORM_MAXV);
   if (rows <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_fwd_kernel, dim);
   kfn<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, nullptr, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
+      x, nullptr, reinterpret_cast<const h16*>(w), reinterpret_cast<h16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_fwd");
 }
 
-extern "C" int fvqa_rmsnorm_gather_fwd(const float* x, const int32_t* idx, const fvqa_bf16* w, fvqa_bf16* y,
+extern "C" int fvqa_rmsnorm_gather_fwd(const float* x, const int32_t* idx, const fvqa_h16* w, fvqa_h16* y,
                                        float* rstd, int rows_out, int dim, float eps, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_gather: bad dim %d", dim);
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_gather: idx is null");
   if (rows_out <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_fwd_kernel, dim);
   kfn<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, idx, reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(y), rstd, dim, eps);
+      x, idx, reinterpret_cast<const h16*>(w), reinterpret_cast<h16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_gather_fwd");
 }
 
-extern "C" int fvqa_rmsnorm_bwd(const fvqa_bf16* dy, const float* x, const fvqa_bf16* w, const float* rstd,
-                                const float* dres, float* dx, fvqa_bf16* dx_bf16, int rows, int dim, void* stream) {
+extern "C" int fvqa_rmsnorm_bwd(const fvqa_h16* dy, const float* x, const fvqa_h16* w, const float* rstd,
+                                const float* dres, float* dx, fvqa_h16* dx_h16, int rows, int dim, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_bwd: bad dim %d", dim);
   if (rows <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_bwd_kernel, dim);
   kfn<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dy), x, nullptr, reinterpret_cast<const bf16*>(w), rstd, dres, dx,
-      reinterpret_cast<bf16*>(dx_bf16), dim);
+      reinterpret_cast<const h16*>(dy), x, nullptr, reinterpret_cast<const h16*>(w), rstd, dres, dx,
+      reinterpret_cast<h16*>(dx_h16), dim);
   return check_launch("rmsnorm_bwd");
 }
 
-extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_bf16* dy, const float* x, const int32_t* idx, const fvqa_bf16* w,
-                                        const float* rstd, float* dx, fvqa_bf16* dx_bf16, int rows_out, int dim, void* stream) {
+extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_h16* dy, const float* x, const int32_t* idx, const fvqa_h16* w,
+                                        const float* rstd, float* dx, fvqa_h16* dx_h16, int rows_out, int dim, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_scatter_bwd: bad dim %d", dim);
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_scatter_bwd: idx is null");
   if (rows_out <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_bwd_kernel, dim);
   kfn<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dy), x, idx, reinterpret_cast<const bf16*>(w), rstd, nullptr, dx,
-      reinterpret_cast<bf16*>(dx_bf16), dim);
+      reinterpret_cast<const h16*>(dy), x, idx, reinterpret_cast<const h16*>(w), rstd, nullptr, dx,
+      reinterpret_cast<h16*>(dx_h16), dim);
   return check_launch("rmsnorm_scatter_bwd");
 }
 
-extern "C" int fvqa_swiglu_fwd(const fvqa_bf16* g, fvqa_bf16* c, int rows, int hid, void* stream) {
+extern "C" int fvqa_swiglu_fwd(const fvqa_h16* g, fvqa_h16* c, int rows, int hid, void* stream) {
   FVQA_REQUIRE(hid % 8 == 0, FVQA_ERR_UNSUPPORTED, "swiglu: hid %d must be a multiple of 8", hid);
   if (rows <= 0) return FVQA_OK;
   const long items = static_cast<long>(rows) * (hid >> 3);
   swiglu_fwd_kernel<<<elementwise_grid(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(c), rows, hid);
+      reinterpret_cast<const h16*>(g), reinterpret_cast<h16*>(c), rows, hid);
   return check_launch("swiglu_fwd");
 }
 
-extern "C" int fvqa_swiglu_bwd(const fvqa_bf16* dc, const fvqa_bf16* g, fvqa_bf16* dg, int rows, int hid, void* stream) {
+extern "C" int fvqa_swiglu_bwd(const fvqa_h16* dc, const fvqa_h16* g, fvqa_h16* dg, int rows, int hid, void* stream) {
   FVQA_REQUIRE(hid % 8 == 0, FVQA_ERR_UNSUPPORTED, "swiglu: hid %d must be a multiple of 8", hid);
   if (rows <= 0) return FVQA_OK;
   const long items = static_cast<long>(rows) * (hid >> 3);
   swiglu_bwd_kernel<<<elementwise_grid(items, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(dc), reinterpret_cast<const bf16*>(g), reinterpret_cast<bf16*>(dg), rows, hid);
+      reinterpret_cast<const h16*>(dc), reinterpret_cast<const h16*>(g), reinterpret_cast<h16*>(dg), rows, hid);
   return check_launch("swiglu_bwd");
 }
 
-extern "C" int fvqa_f32_to_bf16(const float* src, fvqa_bf16* dst, int64_t n, void* stream) {
+extern "C" int fvqa_f32_to_h16(const float* src, fvqa_h16* dst, int64_t n, void* stream) {
   if (n <= 0) return FVQA_OK;
-  f32_to_bf16_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
-  return check_launch("f32_to_bf16");
+  f32_to_h16_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<h16*>(dst), n);
+  return check_launch("f32_to_h16");
 }
 
 extern "C" int fvqa_gather_rows(const void* src, const int32_t* idx, void* dst, int rows, int row_bytes, void* stream) {

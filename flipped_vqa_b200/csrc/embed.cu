@@ -101,9 +101,9 @@ __global__ void __launch_bounds__(VP_THREADS) visual_proj_bwd_kernel(const float
   }
 }
 
-// One CTA per token row; output is the fp32 residual stream (values are bf16-representable).
+// One CTA per token row; output is the fp32 residual stream (values are h16-representable).
 __global__ void __launch_bounds__(256) build_h0_fwd_kernel(
-    const bf16* __restrict__ tok_emb, const int32_t* __restrict__ ids, const int32_t* __restrict__ labels,
+    const h16* __restrict__ tok_emb, const int32_t* __restrict__ ids, const int32_t* __restrict__ labels,
     const int32_t* __restrict__ vstart, const int32_t* __restrict__ seq_video, const int32_t* __restrict__ qav_index,
     const float* __restrict__ vf32, const float* __restrict__ temporal, float* __restrict__ h0, int S, int dim, int F) {
   const int row = blockIdx.x;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) build_h0_fwd_kernel(
       for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = bf16_round(vrow[v * 8 + j] + trow[v * 8 + j]);
+        for (int j = 0; j < 8; ++j) o[j] = h16_round(vrow[v * 8 + j] + trow[v * 8 + j]);
         put(v, o);
       }
     } else {
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) build_h0_fwd_kernel(
           const float* vrow = vf32 + (static_cast<long>(b) * F + f) * dim;
           const float* trow = temporal + static_cast<long>(f) * dim;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = bf16_round(o[j] + bf16_round(vrow[v * 8 + j] + trow[v * 8 + j]));
+          for (int j = 0; j < 8; ++j) o[j] = h16_round(o[j] + h16_round(vrow[v * 8 + j] + trow[v * 8 + j]));
         }
       }
       put(v, o);
@@ -232,13 +232,13 @@ extern "C" int fvqa_visual_proj_bwd(const float* dvf, const float* video, float*
   return check_launch("visual_proj_bwd");
 }
 
-extern "C" int fvqa_build_h0_fwd(const fvqa_bf16* tok_emb, const int32_t* ids, const int32_t* labels, const int32_t* vstart,
+extern "C" int fvqa_build_h0_fwd(const fvqa_h16* tok_emb, const int32_t* ids, const int32_t* labels, const int32_t* vstart,
                                  const int32_t* seq_video, const int32_t* qav_index, const float* vf32, const float* temporal,
                                  float* h0, int n_seq, int S, int dim, int max_feats, void* stream) {
   FVQA_REQUIRE(dim % 8 == 0, FVQA_ERR_UNSUPPORTED, "build_h0: dim %d must be a multiple of 8", dim);
   if (n_seq * S <= 0) return FVQA_OK;
   build_h0_fwd_kernel<<<n_seq * S, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const bf16*>(tok_emb), ids, labels, vstart, seq_video, qav_index, vf32, temporal, h0, S, dim, max_feats);
+      reinterpret_cast<const h16*>(tok_emb), ids, labels, vstart, seq_video, qav_index, vf32, temporal, h0, S, dim, max_feats);
   return check_launch("build_h0_fwd");
 }
 

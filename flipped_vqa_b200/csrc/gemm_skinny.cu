@@ -6,6 +6,8 @@
 // warp w streams K-slice w of the weight rows with 16-byte loads straight into mma.sync.m16n8k16
 // B fragments (the k index inside each 32-element chunk is permuted identically for A and B, which a
 // contraction does not see), and the 8 partial tiles are summed in shared memory in a fixed order.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace fvqa {
@@ -14,7 +16,7 @@ namespace {
 
 __device__ __forceinline__ void mma16816_sk(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." FVQA_MMA_TYPE "." FVQA_MMA_TYPE ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -28,8 +30,8 @@ constexpr int SK_THREADS = SK_WARPS * 32;
 // pointer table is given (the per-layer weight blocks live in separate allocations), else B. One launch then covers the
 // adapter projections of ALL layers (2.1 GB of weights at 7B) instead of 32 launches of 67 MB that are mostly ramp and tail.
 template <int NT, bool OUT_F32>
-__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const bf16* __restrict__ A, long strideA, int lda,
-                                                                 const bf16* __restrict__ B, const bf16* const* __restrict__ Bptrs, int ldb,
+__global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const h16* __restrict__ A, long strideA, int lda,
+                                                                 const h16* __restrict__ B, const h16* const* __restrict__ Bptrs, int ldb,
                                                                  void* __restrict__ C, long strideC, int ldc, int M, int N, int K) {
   __shared__ float red[SK_WARPS][16][8 * NT + 1];
   {
@@ -37,7 +39,7 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const bf16* __r
     A += grp * strideA;
     if (Bptrs != nullptr) B = Bptrs[grp];
     if constexpr (OUT_F32) C = reinterpret_cast<float*>(C) + grp * strideC;
-    else C = reinterpret_cast<bf16*>(C) + grp * strideC;
+    else C = reinterpret_cast<h16*>(C) + grp * strideC;
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int n0 = blockIdx.x * 8 * NT;
@@ -85,22 +87,22 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const bf16* __r
 #pragma unroll
       for (int w = 0; w < SK_WARPS; ++w) s += red[w][r][cc];
       if constexpr (OUT_F32) reinterpret_cast<float*>(C)[static_cast<long>(r) * ldc + n0 + cc] = s;
-      else reinterpret_cast<bf16*>(C)[static_cast<long>(r) * ldc + n0 + cc] = __float2bfloat16_rn(s);
+      else reinterpret_cast<h16*>(C)[static_cast<long>(r) * ldc + n0 + cc] = f2h(s);
     }
   }
 }
 
 bool gemm_skinny_supported(int M, int K, const void* R) { return M <= 16 && R == nullptr && K % (SK_WARPS * 32) == 0; }
 
-int g_skinny_force_nt = 0;   // tuning hook (fvqa_gemm_debug_skinny_nt): column blocks of 8 * nt per CTA; 0 = heuristic
+std::atomic<int> g_skinny_force_nt{0};   // tuning hook (fvqa_gemm_debug_skinny_nt): column blocks of 8 * nt per CTA; 0 = heuristic
 
-int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, const bf16* const* Bptrs, int ldb, void* C, long strideC,
+int gemm_skinny_grouped(const h16* A, long strideA, int lda, const h16* B, const h16* const* Bptrs, int ldb, void* C, long strideC,
                         int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream) {
   // 16 columns per CTA when that still gives every SM ~2 CTAs, else 8. (32 columns per CTA cost registers / resident CTAs:
   // measured 4.96 vs 5.38 TB/s on the 2.1 GB forward launch and 3.5 vs 4.3 TB/s on a backward chunk, tools/skinny_bench.py.)
   const long blocks16 = static_cast<long>(N / 16) * groups;
   int nt = blocks16 >= 2 * num_sms ? 2 : 1;
-  if (g_skinny_force_nt == 1 || g_skinny_force_nt == 2 || g_skinny_force_nt == 4) nt = g_skinny_force_nt;
+  if (g_skinny_force_nt == 1 || g_skinny_force_nt == 2 || g_skinny_force_nt == 4) nt = g_skinny_force_nt.load();
   const int cols = 8 * nt;
   const dim3 grid((N + cols - 1) / cols, groups);
 #define FVQA_SK(NT_)                                                                                                                \
@@ -111,7 +113,7 @@ int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, con
   return check_launch("gemm_skinny");
 }
 
-int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
+int gemm_skinny(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
                 cudaStream_t stream) {
   return gemm_skinny_grouped(A, 0, lda, B, nullptr, ldb, C, 0, ldc, M, N, K, 1, out_fp32, num_sms, stream);
 }

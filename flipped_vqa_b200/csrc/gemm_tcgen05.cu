@@ -1,26 +1,28 @@
-// bf16 GEMM  C[M,N] = A[M,K] * B[N,K]^T (+ R)  on the 5th-gen tensor cores (tcgen05.mma, accumulators
+// h16 GEMM  C[M,N] = A[M,K] * B[N,K]^T (+ R)  on the 5th-gen tensor cores (tcgen05.mma, accumulators
 // in TMEM), operands staged by TMA (128B swizzle) through a multi-stage mbarrier ring; persistent
 // CTAs, one per SM, warp-specialised:
 //   warp 0 : TMA producer (one elected thread)
 //   warp 1 : MMA issuer   (one elected thread)
 //   warp 2 : TMEM allocator / deallocator
-//   warps 4-7 : epilogue (TMEM -> registers -> bf16/fp32 -> global, optional residual add)
+//   warps 4-7 : epilogue (TMEM -> registers -> h16/fp32 -> global, optional residual add)
 // Two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // This kernel replaces every frozen nn.Linear of the reference (llama/model.py:89,99-100,128,142,
 // 348,354) and — with the load-time transposed weight copies — its dX-only backward.
 #include <cuda.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
+#include "../../include/fvqa_debug.h"
 #include "common.cuh"
 #include "tmap.h"
 
 namespace fvqa {
 
 constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;           // 64 bf16 = 128 B = one swizzle row
+constexpr int GEMM_BK = 64;           // 64 h16 = 128 B = one swizzle row
 constexpr int GEMM_THREADS = 256;
 constexpr int PAIR_THREADS = 384;   // CTA-pair kernel: warps 0-3 TMA / MMA / TMEM alloc / idle, warps 4-11 epilogue (two per TMEM lane quadrant)
 constexpr int GEMM_UMMA_K = 16;
@@ -54,7 +56,7 @@ struct GemmEpi {
 enum { EPI_PLAIN = 0, EPI_ROPE = 1, EPI_SWIGLU_FWD = 2, EPI_SWIGLU_BWD = 3 };
 
 // One epilogue chunk: NC (32 or 16) consecutive fp32 accumulator columns of one output row held in
-// registers -> optional RoPE rotation / residual add -> global store (bf16 or fp32).
+// registers -> optional RoPE rotation / residual add -> global store (h16 or fp32).
 template <int NC, bool OUT_F32, bool ROPE>
 __device__ __forceinline__ void epilogue_store(uint32_t (&v)[32], void* __restrict__ Cout, const GemmEpi& epi, int row, int col0,
                                                int N, int ldc) {
@@ -74,8 +76,8 @@ __device__ __forceinline__ void epilogue_store(uint32_t (&v)[32], void* __restri
       }
     }
   } else {
-    bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
-    const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
+    h16* crow = reinterpret_cast<h16*>(Cout) + static_cast<long>(row) * ldc + col0;
+    const h16* rrow = epi.R ? reinterpret_cast<const h16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
     if constexpr (ROPE) {
       const int pos = epi.pos_ids != nullptr ? __ldg(epi.pos_ids + row) : row % epi.S;
 #pragma unroll
@@ -115,7 +117,7 @@ __device__ __forceinline__ void epilogue_store(uint32_t (&v)[32], void* __restri
 
 template <int BN, bool OUT_F32, bool ROPE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -183,7 +185,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BM, BN);
+      constexpr uint32_t idesc = umma_idesc_h16(GEMM_BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -202,7 +204,7 @@ gemm_bf16_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
             // advance 16 elements (32 B) along K inside the swizzle row: +2 in 16-byte units
-            umma_bf16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+            umma_h16_ss(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                          (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(empty_bar(stage));               // smem slot reusable once these MMAs finish
@@ -274,7 +276,7 @@ __host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GE
 // clusters fit the chip (132 of 148 SMs, profiles/r1_cluster_occupancy.txt).
 template <bool OUT_F32, int EPI, bool QUAD = false>
 __global__ void __cluster_dims__(QUAD ? 4 : 2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
-gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages, int l2_hints) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -364,8 +366,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      // l2_hints bit 1 (probe, fvqa_gemm_debug_a_fp16): the A operand holds fp16 bits (mixed fp16 x bf16 kind::f16 MMA)
-      const uint32_t idesc = umma_idesc_bf16(2 * GEMM_BM, BN) & ~((l2_hints & 2) ? (1u << 7) : 0u);
+      // l2_hints bit 1 (probe, fvqa_debug_gemm_mixed_a): A is read in the OTHER 16-bit format than B (mixed fp16 x bf16 MMA)
+      const uint32_t idesc = umma_idesc_h16(2 * GEMM_BM, BN) ^ ((l2_hints & 2) ? (1u << 7) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -383,7 +385,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint64_t bdesc = umma_desc_k_sw128(sb);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-            umma_bf16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+            umma_h16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                               (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_pair_mask(empty_bar(stage), QUAD ? 0xF : 0x3);                       // QUAD: the partner pair writes into this stage too
@@ -417,7 +419,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const bool row_ok = row < M;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * 256);
       if constexpr (EPI == EPI_SWIGLU_FWD) {
-        // columns [0,128) = a = W1 x, [128,256) = b = W3 x of hidden units [128 tn, +128): write g = [a | b] (bf16,
+        // columns [0,128) = a = W1 x, [128,256) = b = W3 x of hidden units [128 tn, +128): write g = [a | b] (h16,
         // saved for backward) and c = silu(a) * b computed from the ROUNDED a, b (bit-identical to swiglu_fwd_kernel)
         const int hcol = (tile / tiles_m) * 128;
         mbar_wait(tfull_bar(acc), acc_phase);
@@ -429,8 +431,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tmem_ld_32x32(tbase + static_cast<uint32_t>(128 + c * 32), vb);
           tmem_ld_wait();
           if (row_ok) {
-            bf16* grow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + hcol + c * 32;
-            bf16* crow = reinterpret_cast<bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + hcol + c * 32;
+            h16* grow = reinterpret_cast<h16*>(Cout) + static_cast<long>(row) * ldc + hcol + c * 32;
+            h16* crow = reinterpret_cast<h16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + hcol + c * 32;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float fa[8], fb[8], o[8];
@@ -449,13 +451,13 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       } else if constexpr (EPI == EPI_SWIGLU_BWD) {
         // accumulator = dc = d(silu(a) * b) for hidden units [n0, n0 + BN): read g = [a | b], write
-        // dg = [dc b s (1 + a (1 - s)) | dc a s] (bit-identical to swiglu_bwd_kernel on the bf16-rounded dc)
+        // dg = [dc b s (1 + a (1 - s)) | dc a s] (bit-identical to swiglu_bwd_kernel on the h16-rounded dc)
         uint4 ga_n[4], gb_n[4];
         auto load_g = [&](int c) {
           const int col0 = n0 + c * 32;
           if (row_ok && col0 < N) {
-            const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + col0);
-            const uint4* gr2 = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + epi.hid + col0);
+            const uint4* gr = reinterpret_cast<const uint4*>(reinterpret_cast<const h16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + col0);
+            const uint4* gr2 = reinterpret_cast<const uint4*>(reinterpret_cast<const h16*>(epi.aux) + static_cast<long>(row) * epi.ld_aux + epi.hid + col0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) { ga_n[q] = __ldg(gr + q); gb_n[q] = __ldg(gr2 + q); }
           }
@@ -476,7 +478,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tmem_ld_32x32(tbase + static_cast<uint32_t>(c * 32), v);
           tmem_ld_wait();
           if (ok) {
-            bf16* drow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
+            h16* drow = reinterpret_cast<h16*>(Cout) + static_cast<long>(row) * ldc + col0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               float a[8], b[8], d[8], da[8], db[8];
@@ -484,7 +486,7 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               unpack8(gb[q], b);
 #pragma unroll
               for (int e = 0; e < 8; ++e) d[e] = __uint_as_float(v[q * 8 + e]);
-              unpack8(pack8(d), d);                                   // dc as the unfused path sees it (bf16)
+              unpack8(pack8(d), d);                                   // dc as the unfused path sees it (h16)
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float sg = 1.f / (1.f + __expf(-a[e]));
@@ -558,8 +560,8 @@ gemm_bf16_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
           } else {
-            bf16* crow = reinterpret_cast<bf16*>(Cout) + static_cast<long>(row) * ldc + col0;
-            const bf16* rrow = epi.R ? reinterpret_cast<const bf16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
+            h16* crow = reinterpret_cast<h16*>(Cout) + static_cast<long>(row) * ldc + col0;
+            const h16* rrow = epi.R ? reinterpret_cast<const h16*>(epi.R) + static_cast<long>(row) * epi.ldr + col0 : nullptr;
             if constexpr (ROPE) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -617,7 +619,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
 static int g_quad_clusters = 0;   // co-resident 4-CTA clusters of the QUAD GEMM (33 on a B200: 132 of 148 SMs); 0 = unavailable
-static int g_quad_mode = 1;       // fvqa_gemm_debug_quad: 0 = never, 1 = heuristic (default), 2 = every eligible plain GEMM
+static std::atomic<int> g_quad_mode{1};       // fvqa_gemm_debug_quad: 0 = never, 1 = heuristic (default), 2 = every eligible plain GEMM
 static std::mutex g_mu;
 
 struct MapKey {
@@ -639,7 +641,8 @@ struct MapKeyHash {
     return h;
   }
 };
-static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+// per host thread: launches take no lock (the library is re-entrant per device; each rank drives its GPU from one thread)
+static thread_local std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 int num_sms() { return g_num_sms; }
 
@@ -660,7 +663,7 @@ int gemm_init() {
   FVQA_REQUIRE(prop.major == 10, FVQA_ERR_UNSUPPORTED, "this library only runs on sm_100 (found sm_%d%d)", prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
 #define FVQA_SET_SMEM(BN, F32, ROPE)                                                                          \
-  e = cudaFuncSetAttribute(gemm_bf16_nt_kernel<BN, F32, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+  e = cudaFuncSetAttribute(gemm_nt_kernel<BN, F32, ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                            GemmCfg<BN>::kSmemBytes);                                                          \
   FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e));
   FVQA_SET_SMEM(256, false, false)
@@ -671,7 +674,7 @@ int gemm_init() {
   FVQA_SET_SMEM(128, false, true)
 #undef FVQA_SET_SMEM
 #define FVQA_SET_PAIR(F32, EPI)                                                                                   \
-  e = cudaFuncSetAttribute(gemm_bf16_nt_pair_kernel<F32, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+  e = cudaFuncSetAttribute(gemm_nt_pair_kernel<F32, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
                            PAIR_SMEM_LIMIT);                                                                       \
   FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm pair): %s", cudaGetErrorString(e));
   FVQA_SET_PAIR(false, EPI_PLAIN)
@@ -682,8 +685,8 @@ int gemm_init() {
 #undef FVQA_SET_PAIR
   // 2x2-cluster (QUAD) variants of the plain-epilogue kernel: opt-in shared memory, and how many 4-CTA clusters fit the chip
   {
-    auto kq16 = gemm_bf16_nt_pair_kernel<false, EPI_PLAIN, true>;
-    auto kq32 = gemm_bf16_nt_pair_kernel<true, EPI_PLAIN, true>;
+    auto kq16 = gemm_nt_pair_kernel<false, EPI_PLAIN, true>;
+    auto kq32 = gemm_nt_pair_kernel<true, EPI_PLAIN, true>;
     e = cudaFuncSetAttribute(kq16, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kq32, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
     FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm quad): %s", cudaGetErrorString(e));
@@ -706,7 +709,6 @@ int gemm_init() {
 
 int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
   MapKey key{ptr, rows, cols, ld, box_rows};
-  std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -717,7 +719,7 @@ int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensor
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   cuuint32_t box[2] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = g_encode(&m, FVQA_TMAP_DTYPE, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FVQA_REQUIRE(r == CUDA_SUCCESS, FVQA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) ptr=%p rows=%d cols=%d ld=%d box_rows=%d",
@@ -733,7 +735,6 @@ int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensor
 // on store), so a 128-row box never touches the next sequence when seq_len < 128.
 int get_tmap_seq(const void* ptr, int n_seq, int seq_len, int cols, int ld, int box_rows, CUtensorMap* out) {
   MapKey key{ptr, n_seq * seq_len, cols, ld, box_rows, seq_len};
-  std::lock_guard<std::mutex> lk(g_mu);
   auto it = g_maps.find(key);
   if (it != g_maps.end()) {
     *out = it->second;
@@ -744,7 +745,7 @@ int get_tmap_seq(const void* ptr, int n_seq, int seq_len, int cols, int ld, int 
   cuuint64_t gstride[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(ld) * 2 * static_cast<cuuint64_t>(seq_len)};
   cuuint32_t box[3] = {static_cast<cuuint32_t>(GEMM_BK), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+  CUresult r = g_encode(&m, FVQA_TMAP_DTYPE, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FVQA_REQUIRE(r == CUDA_SUCCESS, FVQA_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p n_seq=%d S=%d cols=%d ld=%d",
@@ -756,7 +757,7 @@ int get_tmap_seq(const void* ptr, int n_seq, int seq_len, int cols, int ld, int 
 }
 
 template <int BN, bool OUT_F32, bool ROPE>
-static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
+static int launch_gemm(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
                        int N, int K, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc = get_tmap(A, M, K, lda, GEMM_BM, &ta);
@@ -765,23 +766,23 @@ static int launch_gemm(const bf16* A, int lda, const bf16* B, int ldb, void* C, 
   if (rc) return rc;
   const int tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + BN - 1) / BN);
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_bf16_nt_kernel<BN, OUT_F32, ROPE><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, C, epi, M, N, K, ldc);
-  return check_launch("gemm_bf16_nt");
+  gemm_nt_kernel<BN, OUT_F32, ROPE><<<grid, GEMM_THREADS, GemmCfg<BN>::kSmemBytes, stream>>>(ta, tb, C, epi, M, N, K, ldc);
+  return check_launch("gemm_nt");
 }
 
 // M <= 16 (adapter-prompt projections): gemm_skinny.cu
 bool gemm_skinny_supported(int M, int K, const void* R);
-int gemm_skinny(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
+int gemm_skinny(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
                 cudaStream_t stream);
-int gemm_skinny_grouped(const bf16* A, long strideA, int lda, const bf16* B, const bf16* const* Bptrs, int ldb, void* C, long strideC,
+int gemm_skinny_grouped(const h16* A, long strideA, int lda, const h16* B, const h16* const* Bptrs, int ldb, void* C, long strideC,
                         int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream);
-extern int g_skinny_force_nt;
+extern std::atomic<int> g_skinny_force_nt;
 
 // ---- CTA-pair path ---------------------------------------------------------------------------
-static int g_a_fp16 = 0;           // probe (fvqa_gemm_debug_a_fp16)
-static int g_l2_hints = 0;         // test hook (fvqa_gemm_debug_l2_hints)
-static int g_force_bn = 0;        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
-static int g_pair_threads = GEMM_THREADS;   // test hook (fvqa_gemm_debug_epilogue_warps): 256 = 4 epilogue warps (default), 384 = 8
+static std::atomic<int> g_mixed_a{0};    // probe (fvqa_gemm_debug_mixed_a)
+static std::atomic<int> g_l2_hints{0};         // test hook (fvqa_gemm_debug_l2_hints)
+static std::atomic<int> g_force_bn{0};        // test hook (fvqa_gemm_debug_force_bn): 0 = heuristic, -1 = single-CTA kernel only
+static std::atomic<int> g_pair_threads{GEMM_THREADS};   // test hook (fvqa_gemm_debug_epilogue_warps): 256 = 4 epilogue warps (default), 384 = 8
 
 // Output-tile width for the pair kernel: maximise wave efficiency x per-tile efficiency. The per-tile
 // factors are MEASURED (B200, 3072 x 22016 x 4096, tools/gemm_diag.py): the UMMA 256 x N x 16 issue time
@@ -809,7 +810,7 @@ static int choose_pair_bn(int M, int N) {
 }
 
 template <bool OUT_F32, int EPI>
-static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
+static int launch_gemm_pair(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M,
                             int N, int K, int bn, cudaStream_t stream) {
   CUtensorMap ta, tb;
   int rc = get_tmap(A, M, K, lda, GEMM_BM, &ta);
@@ -823,13 +824,13 @@ static int launch_gemm_pair(const bf16* A, int lda, const bf16* B, int ldb, void
   const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + bn - 1) / bn;
   const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tiles_n;
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_bf16_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, g_pair_threads, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints | (g_a_fp16 << 1));
-  return check_launch("gemm_bf16_nt_pair");
+  gemm_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, g_pair_threads.load(), smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints | (g_mixed_a << 1));
+  return check_launch("gemm_nt_pair");
 }
 
 // 2x2-cluster multicast variant (plain epilogue, BN = 256, an even number of column tiles)
 template <bool OUT_F32>
-static int launch_gemm_quad(const bf16* A, int lda, const bf16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M, int N, int K,
+static int launch_gemm_quad(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M, int N, int K,
                             cudaStream_t stream) {
   constexpr int bn = 256;
   CUtensorMap ta, tb;
@@ -845,8 +846,8 @@ static int launch_gemm_quad(const bf16* A, int lda, const bf16* B, int ldb, void
   const int clusters = units < g_quad_clusters ? units : g_quad_clusters;
   // 384 threads = two epilogue warps per TMEM lane quadrant: neutral for the pair kernel, but with the multicast operand stream the
   // faster accumulator drain pays (K = 11008 burst 191.7 vs 199.0 us with four warps; in-step A/B -0.5 % vs 0.0 %)
-  gemm_bf16_nt_pair_kernel<OUT_F32, EPI_PLAIN, true><<<4 * clusters, PAIR_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, 0);
-  return check_launch("gemm_bf16_nt_quad");
+  gemm_nt_pair_kernel<OUT_F32, EPI_PLAIN, true><<<4 * clusters, PAIR_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, 0);
+  return check_launch("gemm_nt_quad");
 }
 // Used when the pair schedule would end in a clearly partial wave and the cluster schedule does not (N = 4096 outputs of a
 // 3072-row step: 192 tiles on 74 pairs = 86 % vs 96 units on 33 clusters = 97 %): measured sustained +0.6 % (K = 11008) to
@@ -866,7 +867,7 @@ static bool use_quad(int M, int N) {
 // the single-CTA kernel.
 static bool use_pair(int M, int N) { return g_force_bn >= 0 && M > GEMM_BM && N >= 64; }
 static int pair_bn(int M, int N) {
-  if (g_force_bn > 0) return g_force_bn;
+  if (g_force_bn > 0) return g_force_bn.load();
   if (N < 128) return ((N + 15) / 16) * 16 < 64 ? 64 : ((N + 15) / 16) * 16;
   return choose_pair_bn(M, N);
 }
@@ -900,13 +901,13 @@ static bool prefer_bn128(int M, int N) {
 
 using namespace fvqa;
 
-extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, void* C, int ldc,
+extern "C" int fvqa_gemm_nt(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb, void* C, int ldc,
                                  const void* R, int ldr, int M, int N, int K, int out_fp32, void* stream) {
   int rc = check_gemm_args(A, lda, B, ldb, C, ldc, R, ldr, M, N, K);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bf16* a = reinterpret_cast<const bf16*>(A);
-  const bf16* b = reinterpret_cast<const bf16*>(B);
+  const h16* a = reinterpret_cast<const h16*>(A);
+  const h16* b = reinterpret_cast<const h16*>(B);
   GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1, nullptr, 0, 0};
   if (g_force_bn == 0 && gemm_skinny_supported(M, K, R)) return gemm_skinny(a, lda, b, ldb, C, ldc, M, N, K, out_fp32, g_num_sms, s);
   if (use_quad(M, N)) {
@@ -926,7 +927,7 @@ extern "C" int fvqa_gemm_bf16_nt(const fvqa_bf16* A, int lda, const fvqa_bf16* B
 }
 
 /* Grouped skinny GEMM (M <= 16): C_g[M,N] = A_g[M,K] * B_g[N,K]^T for g < groups in ONE launch; see include/fvqa.h. */
-extern "C" int fvqa_gemm_skinny_grouped(const fvqa_bf16* A, int64_t strideA, int lda, const void* const* B_ptrs_dev, int ldb, void* C,
+extern "C" int fvqa_gemm_skinny_grouped(const fvqa_h16* A, int64_t strideA, int lda, const void* const* B_ptrs_dev, int ldb, void* C,
                                         int64_t strideC, int ldc, int M, int N, int K, int groups, int out_fp32, void* stream) {
   FVQA_REQUIRE(g_encode != nullptr, FVQA_ERR_INVALID_ARG, "fvqa_init() has not been called");
   FVQA_REQUIRE(M > 0 && M <= 16 && N > 0 && K > 0 && groups > 0 && groups <= 65535, FVQA_ERR_INVALID_ARG,
@@ -935,12 +936,12 @@ extern "C" int fvqa_gemm_skinny_grouped(const fvqa_bf16* A, int64_t strideA, int
                "gemm_skinny_grouped: K=%d must be a multiple of 256, N / lda / ldb / strideA multiples of 8", K);
   FVQA_REQUIRE(A != nullptr && B_ptrs_dev != nullptr && C != nullptr && lda >= K && ldb >= K && ldc >= N, FVQA_ERR_INVALID_ARG,
                "gemm_skinny_grouped: null pointer or leading dimension too small");
-  return gemm_skinny_grouped(reinterpret_cast<const bf16*>(A), static_cast<long>(strideA), lda, nullptr,
-                             reinterpret_cast<const bf16* const*>(B_ptrs_dev), ldb, C, static_cast<long>(strideC), ldc, M, N, K, groups,
+  return gemm_skinny_grouped(reinterpret_cast<const h16*>(A), static_cast<long>(strideA), lda, nullptr,
+                             reinterpret_cast<const h16* const*>(B_ptrs_dev), ldb, C, static_cast<long>(strideC), ldc, M, N, K, groups,
                              out_fp32, g_num_sms, static_cast<cudaStream_t>(stream));
 }
 
-static int gemm_rope_impl(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N, int K,
+static int gemm_rope_impl(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb, fvqa_h16* C, int ldc, int M, int N, int K,
                           const float* rope_cos, const float* rope_sin, int rope_cols, int hd, int S, const int32_t* pos_ids,
                           void* stream) {
   int rc = check_gemm_args(A, lda, B, ldb, C, ldc, nullptr, 0, M, N, K);
@@ -948,22 +949,22 @@ static int gemm_rope_impl(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int l
   FVQA_REQUIRE((hd == 64 || hd == 128) && rope_cols % hd == 0 && rope_cols <= N && S > 0 && rope_cos && rope_sin,
                FVQA_ERR_INVALID_ARG, "gemm_rope: bad rope arguments (hd=%d rope_cols=%d S=%d)", hd, rope_cols, S);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const bf16* a = reinterpret_cast<const bf16*>(A);
-  const bf16* b = reinterpret_cast<const bf16*>(B);
+  const h16* a = reinterpret_cast<const h16*>(A);
+  const h16* b = reinterpret_cast<const h16*>(B);
   GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S, nullptr, 0, 0, pos_ids};
   if (use_pair(M, N)) return launch_gemm_pair<false, EPI_ROPE>(a, lda, b, ldb, C, ldc, epi, M, N, K, pair_bn(M, N), s);
   if (prefer_bn128(M, N)) return launch_gemm<128, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   return launch_gemm<256, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
 }
 
-extern "C" int fvqa_gemm_bf16_nt_rope(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M, int N,
+extern "C" int fvqa_gemm_nt_rope(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb, fvqa_h16* C, int ldc, int M, int N,
                                       int K, const float* rope_cos, const float* rope_sin, int rope_cols, int hd, int S,
                                       void* stream) {
   return gemm_rope_impl(A, lda, B, ldb, C, ldc, M, N, K, rope_cos, rope_sin, rope_cols, hd, S, nullptr, stream);
 }
 
 /* Ragged / compacted token layouts (shared-prefix option scoring): row r is rotated by the angle of position pos_ids[r]. */
-extern "C" int fvqa_gemm_bf16_nt_rope_pos(const fvqa_bf16* A, int lda, const fvqa_bf16* B, int ldb, fvqa_bf16* C, int ldc, int M,
+extern "C" int fvqa_gemm_nt_rope_pos(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb, fvqa_h16* C, int ldc, int M,
                                           int N, int K, const float* rope_cos, const float* rope_sin, int rope_cols, int hd,
                                           const int32_t* pos_ids, void* stream) {
   FVQA_REQUIRE(pos_ids != nullptr, FVQA_ERR_INVALID_ARG, "gemm_rope_pos: pos_ids is NULL");
@@ -1003,29 +1004,29 @@ extern "C" int fvqa_gemm_debug_force_bn(int bn) {
   return prev;
 }
 
-/* W1|W3 projection with SwiGLU in the epilogue (llama/model.py:142): g[M, 2*hid] = x W13^T (bf16, saved for
+/* W1|W3 projection with SwiGLU in the epilogue (llama/model.py:142): g[M, 2*hid] = x W13^T (h16, saved for
  * backward) and c[M, hid] = silu(g[:, :hid]) * g[:, hid:] in one pass. W13 = [W1; W3] is [2*hid, K]. */
-extern "C" int fvqa_gemm_swiglu_fwd(const fvqa_bf16* X, int ldx, const fvqa_bf16* W13, int ldw, fvqa_bf16* G, int ldg, fvqa_bf16* Cc,
+extern "C" int fvqa_gemm_swiglu_fwd(const fvqa_h16* X, int ldx, const fvqa_h16* W13, int ldw, fvqa_h16* G, int ldg, fvqa_h16* Cc,
                                     int ldcc, int M, int hid, int K, void* stream) {
   int rc = check_gemm_args(X, ldx, W13, ldw, G, ldg, nullptr, 0, M, 2 * hid, K);
   if (rc) return rc;
   FVQA_REQUIRE(hid % 128 == 0 && ldcc % 8 == 0 && ldcc >= hid && Cc != nullptr && (reinterpret_cast<uintptr_t>(Cc) & 15) == 0,
                FVQA_ERR_UNSUPPORTED, "gemm_swiglu_fwd: hid=%d must be a multiple of 128 (ldc=%d)", hid, ldcc);
   GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, Cc, ldcc, hid};
-  return launch_gemm_pair<false, EPI_SWIGLU_FWD>(reinterpret_cast<const bf16*>(X), ldx, reinterpret_cast<const bf16*>(W13), ldw, G, ldg, epi,
+  return launch_gemm_pair<false, EPI_SWIGLU_FWD>(reinterpret_cast<const h16*>(X), ldx, reinterpret_cast<const h16*>(W13), ldw, G, ldg, epi,
                                                  M, 2 * hid, K, 256, static_cast<cudaStream_t>(stream));
 }
 
 /* Backward of the above through W2 and the SwiGLU: dg[M, 2*hid] = swiglu'(g) . (dY W2t^T) where the
  * intermediate dc = dY W2t^T [M, hid] never leaves the SM. W2t is [hid, K] (the transposed w2). */
-extern "C" int fvqa_gemm_swiglu_bwd(const fvqa_bf16* dY, int ldy, const fvqa_bf16* W2t, int ldw, const fvqa_bf16* G, int ldg,
-                                    fvqa_bf16* dG, int lddg, int M, int hid, int K, void* stream) {
+extern "C" int fvqa_gemm_swiglu_bwd(const fvqa_h16* dY, int ldy, const fvqa_h16* W2t, int ldw, const fvqa_h16* G, int ldg,
+                                    fvqa_h16* dG, int lddg, int M, int hid, int K, void* stream) {
   int rc = check_gemm_args(dY, ldy, W2t, ldw, dG, lddg, nullptr, 0, M, hid, K);
   if (rc) return rc;
   FVQA_REQUIRE(hid % 32 == 0 && ldg % 8 == 0 && ldg >= 2 * hid && lddg >= 2 * hid && G != nullptr && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
                FVQA_ERR_UNSUPPORTED, "gemm_swiglu_bwd: hid=%d must be a multiple of 32 (ldg=%d lddg=%d)", hid, ldg, lddg);
-  GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, const_cast<fvqa_bf16*>(G), ldg, hid};
-  return launch_gemm_pair<false, EPI_SWIGLU_BWD>(reinterpret_cast<const bf16*>(dY), ldy, reinterpret_cast<const bf16*>(W2t), ldw, dG, lddg, epi,
+  GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, const_cast<fvqa_h16*>(G), ldg, hid};
+  return launch_gemm_pair<false, EPI_SWIGLU_BWD>(reinterpret_cast<const h16*>(dY), ldy, reinterpret_cast<const h16*>(W2t), ldw, dG, lddg, epi,
                                                  M, hid, K, 256, static_cast<cudaStream_t>(stream));
 }
 
@@ -1036,9 +1037,9 @@ extern "C" int fvqa_gemm_debug_l2_hints(int on) {
   return prev;
 }
 
-/* Probe: 1 = the A operand of the CTA-pair kernel is read as fp16 (B stays bf16). */
-extern "C" int fvqa_gemm_debug_a_fp16(int on) {
-  const int prev = g_a_fp16;
-  g_a_fp16 = on ? 1 : 0;
+/* Probe: 1 = the A operand of the CTA-pair kernel is read in the other 16-bit format than B (see fvqa_debug.h). */
+extern "C" int fvqa_gemm_debug_mixed_a(int on) {
+  const int prev = g_mixed_a;
+  g_mixed_a = on ? 1 : 0;
   return prev;
 }

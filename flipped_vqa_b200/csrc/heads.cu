@@ -44,18 +44,18 @@ __global__ void __launch_bounds__(CE_THREADS) ce_fwd_kernel(const float* __restr
   }
 }
 
-// dlogits = (softmax - onehot) * gscale * inv_count  (bf16); padding rows are zero-filled.
+// dlogits = (softmax - onehot) * gscale * inv_count  (h16); padding rows are zero-filled.
 __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restrict__ logits, int ld,
                                                             const int32_t* __restrict__ target, const float* __restrict__ row_lse,
                                                             const float* __restrict__ gscale, float inv_count,
-                                                            bf16* __restrict__ dlogits, int ldd, int V) {
+                                                            h16* __restrict__ dlogits, int ldd, int V) {
   const int row = blockIdx.x;
   const int t = target[row];
-  bf16* d = dlogits + static_cast<long>(row) * ldd;
+  h16* d = dlogits + static_cast<long>(row) * ldd;
   const int nv = V >> 3;
   if (t < 0) {
     for (int i = threadIdx.x; i < nv; i += CE_THREADS) reinterpret_cast<uint4*>(d)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = (nv << 3) + threadIdx.x; i < V; i += CE_THREADS) d[i] = __float2bfloat16_rn(0.f);
+    for (int i = (nv << 3) + threadIdx.x; i < V; i += CE_THREADS) d[i] = f2h(0.f);
     return;
   }
   const float* l = logits + static_cast<long>(row) * ld;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(CE_THREADS) ce_bwd_kernel(const float* __restr
     reinterpret_cast<uint4*>(d)[i] = pack8(o);
   }
   for (int i = (nv << 3) + threadIdx.x; i < V; i += CE_THREADS)
-    d[i] = __float2bfloat16_rn((__expf(l[i] - lse) - (i == t ? 1.f : 0.f)) * sc);
+    d[i] = f2h((__expf(l[i] - lse) - (i == t ? 1.f : 0.f)) * sc);
 }
 
 // Deterministic single-CTA reduction: out[0] = scale * sum(v[0..rows)).
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) sum_scale_kernel(const float* __restrict_
 }
 
 // QAV forward: one CTA per gathered row.
-__global__ void __launch_bounds__(256) qav_fwd_kernel(const bf16* __restrict__ hn, const float* __restrict__ vf32,
+__global__ void __launch_bounds__(256) qav_fwd_kernel(const h16* __restrict__ hn, const float* __restrict__ vf32,
                                                       const int32_t* __restrict__ row_video, const int32_t* __restrict__ target,
                                                       float inv_tau, float* __restrict__ row_loss, float* __restrict__ prob,
                                                       int dim, int F) {
@@ -99,10 +99,10 @@ __global__ void __launch_bounds__(256) qav_fwd_kernel(const bf16* __restrict__ h
   float acc[QAV_MAXF];
 #pragma unroll
   for (int j = 0; j < QAV_MAXF; ++j) acc[j] = 0.f;
-  const bf16* h = hn + static_cast<long>(row) * dim;
+  const h16* h = hn + static_cast<long>(row) * dim;
   const float* vb = vf32 + static_cast<long>(b) * F * dim;
   for (int c = threadIdx.x; c < dim; c += 256) {
-    const float x = __bfloat162float(h[c]);
+    const float x = h2f(h[c]);
 #pragma unroll
     for (int j = 0; j < QAV_MAXF; ++j)
       if (j < F) acc[j] += x * __ldg(vb + static_cast<long>(j) * dim + c);
@@ -129,13 +129,13 @@ __global__ void __launch_bounds__(256) qav_fwd_kernel(const bf16* __restrict__ h
 // dhn[row] = sum_j dlogit[row,j] * vf32[b,j,:]   (one CTA per row)
 __global__ void __launch_bounds__(256) qav_bwd_dh_kernel(const float* __restrict__ vf32, const int32_t* __restrict__ row_video,
                                                          const int32_t* __restrict__ target, const float* __restrict__ prob,
-                                                         const float* __restrict__ gscale, float coef, bf16* __restrict__ dhn,
+                                                         const float* __restrict__ gscale, float coef, h16* __restrict__ dhn,
                                                          int dim, int F) {
   const int row = blockIdx.x;
   const int b = row_video[row];
-  bf16* o = dhn + static_cast<long>(row) * dim;
+  h16* o = dhn + static_cast<long>(row) * dim;
   if (b < 0) {
-    for (int c = threadIdx.x; c < dim; c += 256) o[c] = __float2bfloat16_rn(0.f);
+    for (int c = threadIdx.x; c < dim; c += 256) o[c] = f2h(0.f);
     return;
   }
   const float sc = gscale[0] * coef;
@@ -148,12 +148,12 @@ __global__ void __launch_bounds__(256) qav_bwd_dh_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < QAV_MAXF; ++j)
       if (j < F) a += dl[j] * __ldg(vb + static_cast<long>(j) * dim + c);
-    o[c] = __float2bfloat16_rn(a);
+    o[c] = f2h(a);
   }
 }
 
 // dvf_qav[b,j,:] = sum_{rows of sample b} dlogit[row,j] * hn[row,:]   (one CTA per (b,j); fixed order)
-__global__ void __launch_bounds__(256) qav_bwd_dv_kernel(const bf16* __restrict__ hn, const int32_t* __restrict__ row_video,
+__global__ void __launch_bounds__(256) qav_bwd_dv_kernel(const h16* __restrict__ hn, const int32_t* __restrict__ row_video,
                                                          const int32_t* __restrict__ target, const float* __restrict__ prob,
                                                          const float* __restrict__ gscale, float coef, float* __restrict__ dvf,
                                                          int rows, int dim, int F) {
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) qav_bwd_dv_kernel(const bf16* __restrict_
     for (int r = 0; r < rows; ++r) {
       if (row_video[r] != b) continue;
       const float dl = (prob[r * F + j] - (j == target[r] ? 1.f : 0.f)) * sc;
-      a += dl * __bfloat162float(hn[static_cast<long>(r) * dim + c]);
+      a += dl * h2f(hn[static_cast<long>(r) * dim + c]);
     }
     dvf[(static_cast<long>(b) * F + j) * dim + c] = a;
   }
@@ -213,11 +213,11 @@ extern "C" int fvqa_ce_fwd(const float* logits, int ld, const int32_t* target, f
 }
 
 extern "C" int fvqa_ce_bwd(const float* logits, int ld, const int32_t* target, const float* row_lse, const float* gscale_dev,
-                           float inv_count, fvqa_bf16* dlogits, int ldd, int rows, int V, void* stream) {
+                           float inv_count, fvqa_h16* dlogits, int ldd, int rows, int V, void* stream) {
   FVQA_REQUIRE(ld % 4 == 0 && ldd % 8 == 0, FVQA_ERR_UNSUPPORTED, "ce_bwd: ld %d / ldd %d alignment", ld, ldd);
   if (rows <= 0) return FVQA_OK;
   ce_bwd_kernel<<<rows, CE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, target, row_lse, gscale_dev, inv_count,
-                                                                             reinterpret_cast<bf16*>(dlogits), ldd, V);
+                                                                             reinterpret_cast<h16*>(dlogits), ldd, V);
   return check_launch("ce_bwd");
 }
 
@@ -226,32 +226,74 @@ extern "C" int fvqa_sum_scale(const float* v, int rows, float scale, float* out,
   return check_launch("sum_scale");
 }
 
-extern "C" int fvqa_qav_loss_fwd(const fvqa_bf16* hn, const float* vf32, const int32_t* row_video, const int32_t* target, float tau,
+extern "C" int fvqa_qav_loss_fwd(const fvqa_h16* hn, const float* vf32, const int32_t* row_video, const int32_t* target, float tau,
                                  float* row_loss, float* prob, int rows, int dim, int max_feats, void* stream) {
   FVQA_REQUIRE(max_feats <= QAV_MAXF, FVQA_ERR_UNSUPPORTED, "qav_loss: max_feats %d > %d", max_feats, QAV_MAXF);
   if (rows <= 0) return FVQA_OK;
-  qav_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(hn), vf32, row_video, target,
+  qav_fwd_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const h16*>(hn), vf32, row_video, target,
                                                                        1.f / tau, row_loss, prob, dim, max_feats);
   return check_launch("qav_loss_fwd");
 }
 
-extern "C" int fvqa_qav_loss_bwd(const fvqa_bf16* hn, const float* vf32, const int32_t* row_video, const int32_t* target,
-                                 const float* prob, const float* gscale_dev, float inv_count, float tau, fvqa_bf16* dhn,
+extern "C" int fvqa_qav_loss_bwd(const fvqa_h16* hn, const float* vf32, const int32_t* row_video, const int32_t* target,
+                                 const float* prob, const float* gscale_dev, float inv_count, float tau, fvqa_h16* dhn,
                                  float* dvf_qav, int rows, int n_video, int dim, int max_feats, void* stream) {
   FVQA_REQUIRE(max_feats <= QAV_MAXF, FVQA_ERR_UNSUPPORTED, "qav_loss: max_feats %d > %d", max_feats, QAV_MAXF);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const float coef = inv_count / tau;
   if (rows > 0) {
-    qav_bwd_dh_kernel<<<rows, 256, 0, s>>>(vf32, row_video, target, prob, gscale_dev, coef, reinterpret_cast<bf16*>(dhn), dim, max_feats);
+    qav_bwd_dh_kernel<<<rows, 256, 0, s>>>(vf32, row_video, target, prob, gscale_dev, coef, reinterpret_cast<h16*>(dhn), dim, max_feats);
     int rc = check_launch("qav_loss_bwd(dh)");
     if (rc) return rc;
   }
   if (n_video * max_feats > 0) {
-    qav_bwd_dv_kernel<<<n_video * max_feats, 256, 0, s>>>(reinterpret_cast<const bf16*>(hn), row_video, target, prob, gscale_dev,
+    qav_bwd_dv_kernel<<<n_video * max_feats, 256, 0, s>>>(reinterpret_cast<const h16*>(hn), row_video, target, prob, gscale_dev,
                                                            coef, dvf_qav, rows, dim, max_feats);
     return check_launch("qav_loss_bwd(dv)");
   }
   return FVQA_OK;
+}
+
+namespace fvqa {
+// One thread: k = 2^round(log2(target / max|g|)), gs_out = g * k, inv_k = 1 / k (see include/fvqa.h).
+__global__ void grad_scale_prepare_kernel(const float* __restrict__ g, float target, float* __restrict__ gs, float* __restrict__ inv_k) {
+  const float m = fmaxf(fabsf(g[0]), fmaxf(fabsf(g[1]), fabsf(g[2])));
+  float k = 1.f;
+  if (target > 0.f && m > 0.f && isfinite(m)) {
+    int e = static_cast<int>(rintf(log2f(target / m)));
+    e = max(-60, min(60, e));
+    k = exp2f(static_cast<float>(e));
+  }
+  gs[0] = g[0] * k; gs[1] = g[1] * k; gs[2] = g[2] * k;
+  inv_k[0] = 1.f / k;
+}
+__global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict__ factor, long n) {
+  const float f = __ldg(factor);
+  const long n4 = n >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+    x4[i] = v;
+  }
+  for (long i = (n4 << 2) + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) x[i] *= f;
+}
+}  // namespace fvqa
+
+extern "C" int fvqa_grad_scale_prepare(const float* gscale, float target, float* gs_out, float* inv_k, void* stream) {
+  FVQA_REQUIRE(gscale && gs_out && inv_k, FVQA_ERR_INVALID_ARG, "grad_scale_prepare: null pointer");
+  fvqa::grad_scale_prepare_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(gscale, target, gs_out, inv_k);
+  return fvqa::check_launch("grad_scale_prepare");
+}
+
+extern "C" int fvqa_scale_f32(float* x, const float* factor_dev, int64_t n, void* stream) {
+  FVQA_REQUIRE(x && factor_dev && n >= 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, FVQA_ERR_INVALID_ARG, "scale_f32: bad arguments");
+  if (n == 0) return FVQA_OK;
+  long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  fvqa::scale_f32_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, factor_dev, static_cast<long>(n));
+  return fvqa::check_launch("scale_f32");
 }
 
 extern "C" int fvqa_scatter_rows(const float* row_val, const int32_t* dst_index, float* dst, int rows, void* stream) {

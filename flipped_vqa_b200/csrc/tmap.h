@@ -4,7 +4,7 @@
 
 namespace fvqa {
 
-// 2-D bf16 row-major tensor [rows, cols] with leading dimension `ld` (elements), tiled in boxes of
+// 2-D h16 row-major tensor [rows, cols] with leading dimension `ld` (elements), tiled in boxes of
 // 64 columns (one 128-byte swizzle row) x box_rows rows, SWIZZLE_128B. Cached per (ptr, shape, box).
 // Requires fvqa_init(). Returns FVQA_OK or an error code (message via fvqa_last_error()).
 int get_tmap(const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out);

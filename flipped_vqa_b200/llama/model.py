@@ -27,7 +27,7 @@ from .. import ops
 from ..synthetic import AUDIO_DIM, audio_mode, ffn_hidden_dim
 from .tokenizer import Tokenizer
 
-BF16 = torch.bfloat16
+H16 = ops.H16
 
 
 @dataclass
@@ -195,7 +195,7 @@ class Transformer(nn.Module):
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
         self._device = torch.device(device)
-        dt = BF16
+        dt = H16
         d = params.dim
         self.hidden_dim = ffn_hidden_dim(d, params.multiple_of)
         self.feature_dim = 768                              # CLIP ViT-L/14 frame features
@@ -253,23 +253,23 @@ class Transformer(nn.Module):
 
     def repack(self):
         """(Re)build the packed / transposed frozen-weight layout from the named parameters and apply
-        the dtype contract of `llama_vqa.py:71-76` on the device (frozen bf16, trainables fp32)."""
+        the dtype contract of `llama_vqa.py:71-76` on the device (frozen h16 = the library's 16-bit operand format, trainables fp32)."""
         dev = self._device
         if dev.type != "cuda":
             raise RuntimeError("flipped_vqa_b200 runs only on a CUDA sm_100a device (no CPU path)")
         d, hid = self.params.dim, self.hidden_dim
         for name, p in self.named_parameters():
             trainable = any(s in name for s in ("gate", "adapter", "temporal_emb", "visual_proj"))
-            want = torch.float32 if (trainable or name.startswith("video_audio_cross_attn")) else BF16   # `.float()`, `model.py:227`
+            want = torch.float32 if (trainable or name.startswith("video_audio_cross_attn")) else H16   # `.float()`, `model.py:227`
             if p.dtype != want or p.device != dev:
                 p.data = p.data.to(device=dev, dtype=want)
         for blk in self.layers:
             at, ff = blk.attention, blk.feed_forward
-            if not (at.wq.weight.data_ptr() == blk._wqkv.data_ptr() and blk._wqkv.device == dev and blk._wqkv.dtype == BF16
+            if not (at.wq.weight.data_ptr() == blk._wqkv.data_ptr() and blk._wqkv.device == dev and blk._wqkv.dtype == H16
                     and at.wk.weight.data_ptr() == blk._wqkv[d:].data_ptr() and at.wv.weight.data_ptr() == blk._wqkv[2 * d:].data_ptr()):
                 blk._wqkv = torch.cat([at.wq.weight.data, at.wk.weight.data, at.wv.weight.data], 0).contiguous()
                 at.wq.weight.data, at.wk.weight.data, at.wv.weight.data = blk._wqkv[0:d], blk._wqkv[d:2 * d], blk._wqkv[2 * d:]
-            if not (ff.w1.weight.data_ptr() == blk._w13.data_ptr() and blk._w13.device == dev and blk._w13.dtype == BF16
+            if not (ff.w1.weight.data_ptr() == blk._w13.data_ptr() and blk._w13.device == dev and blk._w13.dtype == H16
                     and ff.w3.weight.data_ptr() == blk._w13[hid:].data_ptr()):
                 blk._w13 = torch.cat([ff.w1.weight.data, ff.w3.weight.data], 0).contiguous()
                 ff.w1.weight.data, ff.w3.weight.data = blk._w13[0:hid], blk._w13[hid:]

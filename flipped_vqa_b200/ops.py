@@ -10,7 +10,7 @@ import torch
 from . import _lib
 from ._lib import check as _check_rc, ptr, stream
 
-BF16 = torch.bfloat16
+H16 = _lib.H16
 
 # kernels launched through the C ABI since import (bench.py reports the count inside its timed region)
 LAUNCHES = 0
@@ -94,61 +94,61 @@ def _chk(t: torch.Tensor, dtype, name: str):
     assert t.is_cuda and t.dtype == dtype and t.is_contiguous(), f"{name}: need contiguous cuda {dtype}, got {t.dtype} {t.device} contiguous={t.is_contiguous()}"
 
 
-# ------------------------------------------------------------------ RMSNorm (fp32 residual stream in, bf16 GEMM operand out)
+# ------------------------------------------------------------------ RMSNorm (fp32 residual stream in, h16 GEMM operand out)
 F32 = torch.float32
 
 
 @_timed
 def rmsnorm_fwd(x, w, eps: float, y=None, rstd=None):
-    _chk(x, F32, "x"); _chk(w, BF16, "w")
+    _chk(x, F32, "x"); _chk(w, H16, "w")
     rows, dim = x.shape
-    y = torch.empty(rows, dim, dtype=BF16, device=x.device) if y is None else y
+    y = torch.empty(rows, dim, dtype=H16, device=x.device) if y is None else y
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if rstd is None else rstd
     check(_lib.lib().fvqa_rmsnorm_fwd(ptr(x), ptr(w), ptr(y), ptr(rstd), rows, dim, eps, stream()), "rmsnorm_fwd")
     return y, rstd
 
 
 @_timed
-def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None, dx_bf16=None):
-    """Returns (dx fp32, dx_bf16). dx = dres + rmsnorm'(x).dy"""
-    _chk(dy, BF16, "dy"); _chk(x, F32, "x")
+def rmsnorm_bwd(dy, x, w, rstd, dres=None, dx=None, dx_h16=None):
+    """Returns (dx fp32, dx_h16). dx = dres + rmsnorm'(x).dy"""
+    _chk(dy, H16, "dy"); _chk(x, F32, "x")
     rows, dim = x.shape
     dx = torch.empty(rows, dim, dtype=F32, device=x.device) if dx is None else dx
-    check(_lib.lib().fvqa_rmsnorm_bwd(ptr(dy), ptr(x), ptr(w), ptr(rstd), ptr(dres), ptr(dx), ptr(dx_bf16), rows, dim, stream()), "rmsnorm_bwd")
-    return dx, dx_bf16
+    check(_lib.lib().fvqa_rmsnorm_bwd(ptr(dy), ptr(x), ptr(w), ptr(rstd), ptr(dres), ptr(dx), ptr(dx_h16), rows, dim, stream()), "rmsnorm_bwd")
+    return dx, dx_h16
 
 
 @_timed
 def rmsnorm_gather_fwd(x, idx, w, eps: float, y=None, rstd=None):
     _chk(x, F32, "x"); _chk(idx, torch.int32, "idx")
     rows, dim = idx.numel(), x.shape[-1]
-    y = torch.empty(rows, dim, dtype=BF16, device=x.device) if y is None else y
+    y = torch.empty(rows, dim, dtype=H16, device=x.device) if y is None else y
     rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if rstd is None else rstd
     check(_lib.lib().fvqa_rmsnorm_gather_fwd(ptr(x), ptr(idx), ptr(w), ptr(y), ptr(rstd), rows, dim, eps, stream()), "rmsnorm_gather_fwd")
     return y, rstd
 
 
 @_timed
-def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dx_bf16=None):
+def rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dx_h16=None):
     rows, dim = idx.numel(), x.shape[-1]
-    check(_lib.lib().fvqa_rmsnorm_scatter_bwd(ptr(dy), ptr(x), ptr(idx), ptr(w), ptr(rstd), ptr(dx), ptr(dx_bf16), rows, dim, stream()), "rmsnorm_scatter_bwd")
+    check(_lib.lib().fvqa_rmsnorm_scatter_bwd(ptr(dy), ptr(x), ptr(idx), ptr(w), ptr(rstd), ptr(dx), ptr(dx_h16), rows, dim, stream()), "rmsnorm_scatter_bwd")
     return dx
 
 
 # ------------------------------------------------------------------ SwiGLU
 @_timed
 def swiglu_fwd(g, c=None):
-    _chk(g, BF16, "g")
+    _chk(g, H16, "g")
     rows, two_hid = g.shape
     hid = two_hid // 2
-    c = torch.empty(rows, hid, dtype=BF16, device=g.device) if c is None else c
+    c = torch.empty(rows, hid, dtype=H16, device=g.device) if c is None else c
     check(_lib.lib().fvqa_swiglu_fwd(ptr(g), ptr(c), rows, hid, stream()), "swiglu_fwd")
     return c
 
 
 @_timed
 def swiglu_bwd(dc, g, dg=None):
-    _chk(dc, BF16, "dc"); _chk(g, BF16, "g")
+    _chk(dc, H16, "dc"); _chk(g, H16, "g")
     rows, hid = dc.shape
     dg = torch.empty_like(g) if dg is None else dg
     check(_lib.lib().fvqa_swiglu_bwd(ptr(dc), ptr(g), ptr(dg), rows, hid, stream()), "swiglu_bwd")
@@ -160,22 +160,22 @@ def swiglu_bwd(dc, g, dg=None):
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
             out_fp32: bool = False, M: Optional[int] = None) -> torch.Tensor:
     """out[M,N] = a[M,K] @ b[N,K]^T (+ residual). a/b may be row-strided views (last dim contiguous)."""
-    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    assert a.dtype == H16 and b.dtype == H16 and a.stride(-1) == 1 and b.stride(-1) == 1
     Mfull, K = a.shape
     M = Mfull if M is None else M
     N, Kb = b.shape
     assert K == Kb, (a.shape, b.shape)
     if out is None:
-        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else BF16, device=a.device)
-    assert out.stride(-1) == 1 and out.dtype == (torch.float32 if out_fp32 else BF16)
+        out = torch.empty(M, N, dtype=torch.float32 if out_fp32 else H16, device=a.device)
+    assert out.stride(-1) == 1 and out.dtype == (torch.float32 if out_fp32 else H16)
     assert residual is None or (residual.dtype == out.dtype and residual.stride(-1) == 1)
     ldr = residual.stride(0) if residual is not None else 0
     tm = GEMM_TIMER
     if tm is not None and tm.active:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    check(_lib.lib().fvqa_gemm_bf16_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), ptr(residual), ldr,
-                                       M, N, K, 1 if out_fp32 else 0, stream()), "gemm_bf16_nt")
+    check(_lib.lib().fvqa_gemm_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), ptr(residual), ldr,
+                                       M, N, K, 1 if out_fp32 else 0, stream()), "gemm_h16_nt")
     if tm is not None and tm.active:
         e1.record()
         tm.records.append((e0, e1, 2.0 * M * N * K))
@@ -185,12 +185,12 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
 @_timed
 def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd: int, S: int, out: Optional[torch.Tensor] = None,
                  pos_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """QKV projection with RoPE applied to the q|k columns in the GEMM epilogue (bf16 out). Position of row r is
+    """QKV projection with RoPE applied to the q|k columns in the GEMM epilogue (h16 out). Position of row r is
     r % S, or pos_ids[r] (int32) for ragged / compacted token layouts."""
-    assert a.dtype == BF16 and b.dtype == BF16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    assert a.dtype == H16 and b.dtype == H16 and a.stride(-1) == 1 and b.stride(-1) == 1
     M, K = a.shape
     N = b.shape[0]
-    out = torch.empty(M, N, dtype=BF16, device=a.device) if out is None else out
+    out = torch.empty(M, N, dtype=H16, device=a.device) if out is None else out
     tm = GEMM_TIMER
     if tm is not None and tm.active:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -198,11 +198,11 @@ def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd:
     if pos_ids is not None:
         _chk(pos_ids, torch.int32, "pos_ids")
         assert pos_ids.numel() >= M
-        check(_lib.lib().fvqa_gemm_bf16_nt_rope_pos(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
-                                                    ptr(cos), ptr(sin), rope_cols, hd, ptr(pos_ids), stream()), "gemm_bf16_nt_rope_pos")
+        check(_lib.lib().fvqa_gemm_nt_rope_pos(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
+                                                    ptr(cos), ptr(sin), rope_cols, hd, ptr(pos_ids), stream()), "gemm_h16_nt_rope_pos")
     else:
-        check(_lib.lib().fvqa_gemm_bf16_nt_rope(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
-                                                ptr(cos), ptr(sin), rope_cols, hd, S, stream()), "gemm_bf16_nt_rope")
+        check(_lib.lib().fvqa_gemm_nt_rope(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K,
+                                                ptr(cos), ptr(sin), rope_cols, hd, S, stream()), "gemm_h16_nt_rope")
     if tm is not None and tm.active:
         e1.record()
         tm.records.append((e0, e1, 2.0 * M * N * K))
@@ -215,8 +215,8 @@ def gemm_swiglu_fwd(x: torch.Tensor, w13: torch.Tensor, g: Optional[torch.Tensor
     (`llama/model.py:142`). Falls back to GEMM + swiglu kernel when hid is not a multiple of 128. Returns (g, c)."""
     M, K = x.shape
     hid = w13.shape[0] // 2
-    g = torch.empty(M, 2 * hid, dtype=BF16, device=x.device) if g is None else g
-    c = torch.empty(M, hid, dtype=BF16, device=x.device) if c is None else c
+    g = torch.empty(M, 2 * hid, dtype=H16, device=x.device) if g is None else g
+    c = torch.empty(M, hid, dtype=H16, device=x.device) if c is None else c
     if hid % 128 != 0 or not FUSE_SWIGLU:
         gemm_nt(x, w13, out=g)
         swiglu_fwd(g, c)
@@ -238,7 +238,7 @@ def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Op
     """dg = swiglu'(g) . (dy @ W2t^T): backward through w2 and the SwiGLU in one GEMM (dc never materialised)."""
     M, K = dy.shape
     hid = w2t.shape[0]
-    dg = torch.empty(M, 2 * hid, dtype=BF16, device=dy.device) if dg is None else dg
+    dg = torch.empty(M, 2 * hid, dtype=H16, device=dy.device) if dg is None else dg
     if hid % 32 != 0 or not FUSE_SWIGLU:
         dc = gemm_nt(dy, w2t)
         return swiglu_bwd(dc, g, dg)
@@ -257,9 +257,9 @@ def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Op
 # ------------------------------------------------------------------ attention
 @_timed
 def attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F, out=None, lse=None):
-    _chk(qkv, BF16, "qkv"); _chk(vstart, torch.int32, "vstart")
-    assert akv.dtype == BF16 and akv.stride(-1) == 1
-    out = torch.empty(n_seq * S, H * hd, dtype=BF16, device=qkv.device) if out is None else out
+    _chk(qkv, H16, "qkv"); _chk(vstart, torch.int32, "vstart")
+    assert akv.dtype == H16 and akv.stride(-1) == 1
+    out = torch.empty(n_seq * S, H * hd, dtype=H16, device=qkv.device) if out is None else out
     lse = torch.empty(n_seq, H, S, dtype=torch.float32, device=qkv.device) if lse is None else lse
     check(_lib.lib().fvqa_attn_fwd(ptr(qkv), ptr(akv), akv.stride(0), ptr(cos), ptr(sin), ptr(gate1), ptr(gate2), ptr(vstart),
                                    ptr(out), ptr(lse), n_seq, S, H, hd, A, F, stream()), "attn_fwd")
@@ -348,7 +348,7 @@ def ce_fwd(logits, target, row_loss=None, row_lse=None):
 @_timed
 def ce_bwd(logits, target, row_lse, gscale, inv_count: float, dlogits=None):
     rows, V = target.numel(), logits.shape[1]
-    dlogits = torch.empty(rows, V, dtype=BF16, device=logits.device) if dlogits is None else dlogits
+    dlogits = torch.empty(rows, V, dtype=H16, device=logits.device) if dlogits is None else dlogits
     check(_lib.lib().fvqa_ce_bwd(ptr(logits), logits.stride(0), ptr(target), ptr(row_lse), ptr(gscale), inv_count, ptr(dlogits),
                                  dlogits.stride(0), rows, V, stream()), "ce_bwd")
     return dlogits
@@ -398,10 +398,27 @@ def option_score(token_loss: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 @_timed
-def f32_to_bf16(src, dst=None):
+def grad_scale_prepare(gscale: torch.Tensor, target: float):
+    """(gscale * k, 1 / k) with k = 2^round(log2(target / max|gscale|)) computed on the device (no host sync)."""
+    _chk(gscale, F32, "gscale")
+    assert gscale.numel() == 3
+    gs = torch.empty(3, dtype=F32, device=gscale.device)
+    inv_k = torch.empty(1, dtype=F32, device=gscale.device)
+    check(_lib.lib().fvqa_grad_scale_prepare(ptr(gscale), float(target), ptr(gs), ptr(inv_k), stream()), "grad_scale_prepare")
+    return gs, inv_k
+
+
+def scale_f32(x: torch.Tensor, factor: torch.Tensor) -> torch.Tensor:
+    """x *= factor[0] in place (factor: 1-element fp32 device tensor)."""
+    _chk(x, F32, "x"); _chk(factor, F32, "factor")
+    check(_lib.lib().fvqa_scale_f32(ptr(x), ptr(factor), x.numel(), stream()), "scale_f32")
+    return x
+
+
+def f32_to_h16(src, dst=None):
     _chk(src, torch.float32, "src")
-    dst = torch.empty(src.shape, dtype=BF16, device=src.device) if dst is None else dst
-    check(_lib.lib().fvqa_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream()), "f32_to_bf16")
+    dst = torch.empty(src.shape, dtype=H16, device=src.device) if dst is None else dst
+    check(_lib.lib().fvqa_f32_to_h16(ptr(src), ptr(dst), src.numel(), stream()), "f32_to_h16")
     return dst
 
 
@@ -458,11 +475,11 @@ def cross_attn_fwd(q, k, v, n_samples: int, frames: int, tokens: int):
 
 @_timed
 def gemm_skinny_grouped(a: torch.Tensor, b_ptrs: torch.Tensor, ldb: int, N: int, out: torch.Tensor) -> torch.Tensor:
-    """out[g] = a[g] @ B_g^T for every group in one launch. a [G, M<=16, K] bf16 contiguous; b_ptrs int64 device tensor of G
-    weight-block pointers ([N, K] bf16 each, leading dimension ldb); out [G, M, N] bf16 or fp32 contiguous."""
-    _chk(a, BF16, "a"); _chk(b_ptrs, torch.int64, "b_ptrs")
+    """out[g] = a[g] @ B_g^T for every group in one launch. a [G, M<=16, K] h16 contiguous; b_ptrs int64 device tensor of G
+    weight-block pointers ([N, K] h16 each, leading dimension ldb); out [G, M, N] h16 or fp32 contiguous."""
+    _chk(a, H16, "a"); _chk(b_ptrs, torch.int64, "b_ptrs")
     G, M, K = a.shape
-    assert out.is_contiguous() and tuple(out.shape) == (G, M, N) and out.dtype in (BF16, torch.float32) and b_ptrs.numel() >= G
+    assert out.is_contiguous() and tuple(out.shape) == (G, M, N) and out.dtype in (H16, torch.float32) and b_ptrs.numel() >= G
     check(_lib.lib().fvqa_gemm_skinny_grouped(ptr(a), M * K, K, ptr(b_ptrs), ldb, ptr(out), M * N, N, M, N, K, G,
                                               1 if out.dtype == torch.float32 else 0, stream()), "gemm_skinny_grouped")
     return out

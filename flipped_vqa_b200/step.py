@@ -18,7 +18,7 @@ import torch
 
 from . import ops
 
-BF16 = torch.bfloat16
+H16 = ops.H16
 I32 = torch.int32
 
 
@@ -342,6 +342,11 @@ class StepEngine:
         # Off by default: the default step computes the reference's row set (every position of every sequence).
         self.skip_pad_rows = False
         self.skip_pad_min_saving = 0.06
+        # fp16 operands: backward runs on upstream gradients normalised by ONE power of two so that the 16-bit gradient tensors sit
+        # mid-range for any caller-side loss scale / accum_iter (fvqa_grad_scale_prepare); the trainable gradients are multiplied by
+        # its exact inverse when they are final. 2^14: dlogits <= 2^14 / n_labelled, d hidden ~ O(1) (fp16 normal range 6e-5 .. 65504).
+        # bf16 operands have fp32's exponent range: no scaling (target 0).
+        self.grad_scale_target = 2.0 ** 14 if ops.H16 == torch.float16 else 0.0
 
     # -------------------------------------------------------------------------------- batch-independent prologue
     def adapter_kv(self, layers: List[LayerWeights], adapter_w):
@@ -350,12 +355,12 @@ class StepEngine:
         ~1 ms of work while the host flattens ids / labels and starts the H2D copy (instead of idling after the previous
         step's loss read). Same kernels and values as the in-loop computation."""
         A, d, L = self.A, self.d, len(layers)
-        adapter_bf16 = ops.f32_to_bf16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
+        adapter_h16 = ops.f32_to_h16(adapter_w)                                  # `adapter[i].half()`, `model.py:339`
         tables = self._weight_tables(layers)
         if tables is None:                                                          # small / odd dims: one skinny GEMM per layer
-            return [ops.gemm_nt(adapter_bf16[l * A:(l + 1) * A], w.wqkv[d:]) for l, w in enumerate(layers)]
-        akv_all = torch.empty(L, A, 2 * d, dtype=BF16, device=self.device)
-        ops.gemm_skinny_grouped(adapter_bf16.view(L, A, d), tables[0], d, 2 * d, akv_all)   # all layers, one launch (2.1 GB of Wk|Wv at 7B)
+            return [ops.gemm_nt(adapter_h16[l * A:(l + 1) * A], w.wqkv[d:]) for l, w in enumerate(layers)]
+        akv_all = torch.empty(L, A, 2 * d, dtype=H16, device=self.device)
+        ops.gemm_skinny_grouped(adapter_h16.view(L, A, d), tables[0], d, 2 * d, akv_all)   # all layers, one launch (2.1 GB of Wk|Wv at 7B)
         return [akv_all[l] for l in range(L)]
 
     def _weight_tables(self, layers: List[LayerWeights]):
@@ -395,11 +400,11 @@ class StepEngine:
             ce_full, q_full, live_rows, ce_live, q_live, n_live = (plan.ce_rows, plan.q_rows, plan.live_rows, plan.ce_rows_c,
                                                                    plan.q_rows_c, plan.n_live)
         akv_all = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)   # adapter K|V, no RoPE (`model.py:99-100`)
-        xn = torch.empty(R, d, dtype=BF16, device=dev)
-        c = torch.empty(R, hid, dtype=BF16, device=dev)
+        xn = torch.empty(R, d, dtype=H16, device=dev)
+        c = torch.empty(R, hid, dtype=H16, device=dev)
         qkv_b = o_b = g_b = None
-        qkv_c = torch.empty(R, 3 * d, dtype=BF16, device=dev) if compact else None
-        o_c = torch.empty(R, d, dtype=BF16, device=dev) if compact else None
+        qkv_c = torch.empty(R, 3 * d, dtype=H16, device=dev) if compact else None
+        o_c = torch.empty(R, d, dtype=H16, device=dev) if compact else None
         # The last layer's wo / FFN outputs are read only at the rows the losses use (labelled positions): run them on
         # those rows alone, exactly like the vocabulary projection (heads below). Everything upstream needs all rows (K/V).
         prune = self.prune_last_layer and 0 < n_live < R
@@ -504,14 +509,14 @@ class StepEngine:
         x = ops.gather_rows(x_full, plan.c2f)                                       # [Tc, d] fp32 residual stream, compact
         del x_full
         akv_all = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)
-        xn = torch.empty(Tc, d, dtype=BF16, device=dev)
-        qkv_c = torch.empty(Tc, 3 * d, dtype=BF16, device=dev)
-        qkv_f = torch.empty(plan.T, 3 * d, dtype=BF16, device=dev)
-        o_f = torch.empty(plan.T, d, dtype=BF16, device=dev)
+        xn = torch.empty(Tc, d, dtype=H16, device=dev)
+        qkv_c = torch.empty(Tc, 3 * d, dtype=H16, device=dev)
+        qkv_f = torch.empty(plan.T, 3 * d, dtype=H16, device=dev)
+        o_f = torch.empty(plan.T, d, dtype=H16, device=dev)
         lse = torch.empty(n_seq, H, S, dtype=torch.float32, device=dev)
-        o_c = torch.empty(Tc, d, dtype=BF16, device=dev)
-        g = torch.empty(Tc, 2 * hid, dtype=BF16, device=dev)
-        c = torch.empty(Tc, hid, dtype=BF16, device=dev)
+        o_c = torch.empty(Tc, d, dtype=H16, device=dev)
+        g = torch.empty(Tc, 2 * hid, dtype=H16, device=dev)
+        c = torch.empty(Tc, hid, dtype=H16, device=dev)
         prune = self.prune_last_layer and 0 < plan.n_live < Tc
         ce_idx = plan.ce_rows_c if prune else plan.ce_rows
         for l, w in enumerate(layers):
@@ -559,14 +564,18 @@ class StepEngine:
         Tr = plan.T_c if compact else T                       # rows of the row-wise tensors
         R = n_live if pruned else Tr                          # rows of the final hidden state that exist
         ce_idx, q_idx = (ce_live, q_live) if pruned else (ce_full, q_full)
-        # gradient of the residual stream: fp32 master + bf16 copy (A operand of the next dX GEMM)
+        # gradient of the residual stream: fp32 master + h16 copy (A operand of the next dX GEMM)
         dx = torch.zeros(R, d, dtype=torch.float32, device=dev)
-        dx_bf = torch.zeros(R, d, dtype=BF16, device=dev)
+        dx_h = torch.zeros(R, d, dtype=H16, device=dev)
         gidx = {"vqa": 0, "vaq": 1, "qav": 2}
+        inv_k = None
+        if self.grad_scale_target > 0:
+            gscale, inv_k = ops.grad_scale_prepare(gscale, self.grad_scale_target)
+        unscale = (lambda t: ops.scale_f32(t, inv_k)) if inv_k is not None else (lambda t: None)
         # --- heads backward
         if sv.ce is not None:
             ce = sv.ce
-            dlogits = torch.empty(plan.ce_total, self.V, dtype=BF16, device=dev)
+            dlogits = torch.empty(plan.ce_total, self.V, dtype=H16, device=dev)
             off = 0
             for k in plan.streams:
                 if k == "qav":
@@ -577,70 +586,72 @@ class StepEngine:
                                gscale[gidx[k]:gidx[k] + 1], 1.0 / n, dlogits=dlogits[off:off + n])
                 off += n
             dhn = ops.gemm_nt(dlogits, out_w_t)                                     # dH = dlogits . W_out
-            ops.rmsnorm_scatter_bwd(dhn, x_final, ce_idx, norm_w, ce["rstd"], dx, dx_bf)
+            ops.rmsnorm_scatter_bwd(dhn, x_final, ce_idx, norm_w, ce["rstd"], dx, dx_h)
         dvf_qav = None
         if sv.qav is not None:
             q = sv.qav
             dhnq, dvf_qav = ops.qav_loss_bwd(q["hn"], sv.vf32, plan.q_vid, plan.q_tgt, q["prob"], gscale[2:3],
                                              1.0 / plan.q_count, self.tau, plan.n_video, F)
-            ops.rmsnorm_scatter_bwd(dhnq, x_final, q_idx, norm_w, q["rstd"], dx, dx_bf)
+            ops.rmsnorm_scatter_bwd(dhnq, x_final, q_idx, norm_w, q["rstd"], dx, dx_h)
         # --- layers, last to first
         if self._attn_ws is None or self._attn_ws.numel() < ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A):
             self._attn_ws = torch.empty(ops.attn_bwd_ws_bytes(n_seq, S, H, hd, A), dtype=torch.uint8, device=dev)
-        dg = torch.empty(Tr, 2 * hid, dtype=BF16, device=dev)
-        dtmp = torch.empty(Tr, d, dtype=BF16, device=dev)
+        dg = torch.empty(Tr, 2 * hid, dtype=H16, device=dev)
+        dtmp = torch.empty(Tr, d, dtype=H16, device=dev)
         dh = torch.empty(Tr, d, dtype=torch.float32, device=dev)
-        dh_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
-        dqkv = torch.empty(T, 3 * d, dtype=BF16, device=dev)
+        dh_h = torch.empty(Tr, d, dtype=H16, device=dev)
+        dqkv = torch.empty(T, 3 * d, dtype=H16, device=dev)
         dakv = torch.empty(A, 2 * d, dtype=torch.float32, device=dev)
-        dakv_bf = torch.empty(A, 2 * d, dtype=BF16, device=dev)
+        dakv_h = torch.empty(A, 2 * d, dtype=H16, device=dev)
         tables, chunk = self._weight_tables(layers), max(1, self.adapter_grad_chunk)
-        dakv_bf_all = torch.empty(L, A, 2 * d, dtype=BF16, device=dev) if tables is not None else None
+        dakv_h_all = torch.empty(L, A, 2 * d, dtype=H16, device=dev) if tables is not None else None
         dx_next = torch.empty(Tr, d, dtype=torch.float32, device=dev)
-        dx_next_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
-        do_full = torch.empty(T, d, dtype=BF16, device=dev) if compact else None
-        dqkv_c = torch.empty(Tr, 3 * d, dtype=BF16, device=dev) if compact else None
+        dx_next_h = torch.empty(Tr, d, dtype=H16, device=dev)
+        do_full = torch.empty(T, d, dtype=H16, device=dev) if compact else None
+        dqkv_c = torch.empty(Tr, 3 * d, dtype=H16, device=dev) if compact else None
         for l in range(L - 1, -1, -1):
             w = layers[l]
             if ops.GEMM_TIMER is not None:
                 ops.GEMM_TIMER.active = l in self.sample_layers
             if pruned and l == L - 1:
                 # compact rows through the FFN and wo of the last layer, then scatter d(attn out) and dh back to all rows
-                dg_c = ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l])
+                dg_c = ops.gemm_swiglu_bwd(dx_h, w.w2_t, sv.g[l])
                 dtmp_c = ops.gemm_nt(dg_c, w.w13_t)
-                dh_c, dh_c_bf = ops.rmsnorm_bwd(dtmp_c, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx,
-                                                dx_bf16=torch.empty(R, d, dtype=BF16, device=dev))
-                do_c = ops.gemm_nt(dh_c_bf, w.wo_t)
+                dh_c, dh_c_h = ops.rmsnorm_bwd(dtmp_c, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx,
+                                                dx_h16=torch.empty(R, d, dtype=H16, device=dev))
+                do_c = ops.gemm_nt(dh_c_h, w.wo_t)
                 dtmp.zero_()
                 ops.scatter_row_vectors(do_c, live_rows, dtmp)
                 dh.zero_()
                 ops.scatter_row_vectors(dh_c, live_rows, dh)
                 dx = torch.empty(Tr, d, dtype=torch.float32, device=dev)          # full-size stream from here down
-                dx_bf = torch.empty(Tr, d, dtype=BF16, device=dev)
+                dx_h = torch.empty(Tr, d, dtype=H16, device=dev)
             else:
-                ops.gemm_swiglu_bwd(dx_bf, w.w2_t, sv.g[l], dg=dg)                 # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
+                ops.gemm_swiglu_bwd(dx_h, w.w2_t, sv.g[l], dg=dg)                 # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
                 ops.gemm_nt(dg, w.w13_t, out=dtmp)                                 # d(ffn_norm out) = [da|db] . [W1;W3]
-                ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_bf16=dh_bf)
-                ops.gemm_nt(dh_bf, w.wo_t, out=dtmp)                               # d(attn out) = dh . Wo
+                ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_h16=dh_h)
+                ops.gemm_nt(dh_h, w.wo_t, out=dtmp)                               # d(attn out) = dh . Wo
             # attention sees the full layout: d(attn out) of the rows that were never computed is zero
             dout = ops.expand_rows(dtmp, plan.f2c, dst=do_full) if compact else dtmp
             ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dout,
                          n_seq, S, H, hd, A, F, dqkv=dqkv, dakv=dakv, dgate1=grads.gate1[l], dgate2=grads.gate2[l], ws=self._attn_ws)
             dqkv_r = ops.gather_rows(dqkv, plan.c2f, dst=dqkv_c) if compact else dqkv
             ops.gemm_nt(dqkv_r, w.wqkv_t, out=dtmp)                                # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
-            ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next, dx_bf16=dx_next_bf)
+            ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next, dx_h16=dx_next_h)
             # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l): one grouped launch
             # per chunk of layers (their rows then become final together, which is what dp.GradSync reduces early)
             if tables is None:
-                ops.f32_to_bf16(dakv, dakv_bf)
-                ops.gemm_nt(dakv_bf, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
+                ops.f32_to_h16(dakv, dakv_h)
+                ops.gemm_nt(dakv_h, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
+                unscale(grads.adapter[l * A:(l + 1) * A])
             else:
-                ops.f32_to_bf16(dakv, dakv_bf_all[l])
+                ops.f32_to_h16(dakv, dakv_h_all[l])
                 if l % chunk == 0:
                     hi = min(l + chunk, L)
-                    ops.gemm_skinny_grouped(dakv_bf_all[l:hi], tables[1][l:hi], 3 * d, d, grads.adapter.view(L, A, d)[l:hi])
+                    ops.gemm_skinny_grouped(dakv_h_all[l:hi], tables[1][l:hi], 3 * d, d, grads.adapter.view(L, A, d)[l:hi])
+                    unscale(grads.adapter.view(L, A, d)[l:hi])                       # final rows of this chunk, before dp.GradSync reduces them
             dx, dx_next = dx_next, dx
-            dx_bf, dx_next_bf = dx_next_bf, dx_bf
+            dx_h, dx_next_h = dx_next_h, dx_h
             if on_layer_done is not None:
                 on_layer_done(l)
         if ops.GEMM_TIMER is not None:
@@ -652,6 +663,7 @@ class StepEngine:
         ops.video_grad_finish(dvf, dvf_qav, plan.n_video, F, dtemporal=grads.temporal)
         if grads.sizes["visual"]:                              # audio only: the projection is frozen (`model.py:209-210`)
             ops.visual_proj_bwd(dvf, plan.video, dwv=grads.visual)
+        unscale(grads.flat[grads.late_offset:])                # gates | visual_proj | temporal_emb: one contiguous tail
         return grads
 
 

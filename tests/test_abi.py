@@ -16,16 +16,21 @@ def lib_path():
 def test_library_exports_every_header_symbol(lib_path):
     syms = _lib.header_symbols()
     assert len(syms) >= 25
-    dll = ctypes.CDLL(lib_path)
-    missing = [s for s in syms if not hasattr(dll, s)]
-    assert not missing, missing
+    for variant in ("fp16", "bf16"):                 # both operand-format builds export the same ABI
+        dll = ctypes.CDLL(build.lib_path(variant))
+        missing = [s for s in syms if not hasattr(dll, s)]
+        assert not missing, (variant, missing)
+        assert dll.fvqa_operand_dtype() == {"fp16": 0, "bf16": 1}[variant]
     # and the ctypes binding declares a signature for each of them
     assert sorted(_lib._SIGNATURES) == syms
+    # the product boundary (fvqa.h) holds no test / tuning hook: those live in fvqa_debug.h
+    assert not [s for s in _lib.header_symbols(debug=False) if "debug" in s]
 
 
 def test_abi_version_and_load(lib_path):
     l = _lib.load()
-    assert l.fvqa_abi_version() == 1
+    assert l.fvqa_abi_version() == 2
+    assert l.fvqa_operand_dtype() == (0 if _lib.DTYPE_NAME == "fp16" else 1)
     assert isinstance(l.fvqa_last_error(), bytes)
     assert l.fvqa_attn_bwd_ws_bytes(24, 128, 32, 128, 10) > 0
 

@@ -5,6 +5,8 @@ import math
 import pytest
 import torch
 
+from flipped_vqa_b200 import _lib
+
 from tests.util_parity import GOLDEN, golden_inputs, make_args
 
 
@@ -43,7 +45,7 @@ def test_freeze_rule_matches_llama_vqa():
     for n, p in m.named_parameters():
         trainable = any(s in n for s in ("gate", "adapter", "temporal_emb", "visual_proj"))
         assert p.requires_grad == trainable, n
-        assert p.dtype == (torch.float32 if trainable else torch.bfloat16), n
+        assert p.dtype == (torch.float32 if trainable else _lib.H16), n
     assert float(m.layers[0].attention.gate1.abs().sum()) == 0.0                       # zero-init (model.py:84)
     assert torch.allclose(m.layers[0].attention.gate2, torch.full((1, 2, 1, 1), -3.5))  # -bias (model.py:85)
 

@@ -1,5 +1,6 @@
 """Parity of every CUDA kernel (called through the C ABI) against the oracle's PyTorch restatement
-of the same reference op, on seeded inputs. bf16 I/O, fp32 math: tolerances are stated per test."""
+of the same reference op, on seeded inputs. 16-bit I/O in the library's operand format H16 (fp16 by default, bf16 with
+FVQA_DTYPE=bf16), fp32 math: tolerances are stated per test (sized for the coarser of the two formats)."""
 import math
 
 import pytest
@@ -7,6 +8,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+from flipped_vqa_b200._lib import H16  # noqa: E402
 from oracle import llama_vqa_oracle as O  # noqa: E402  (checker only)
 
 
@@ -15,9 +17,9 @@ def relerr(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-def bf16_randn(*shape, std=1.0, seed=0):
+def h16_randn(*shape, std=1.0, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    return (torch.randn(*shape, device="cuda", generator=g) * std).to(torch.bfloat16)
+    return (torch.randn(*shape, device="cuda", generator=g) * std).to(H16)
 
 
 # ------------------------------------------------------------------ RMSNorm / SwiGLU
@@ -25,17 +27,17 @@ def bf16_randn(*shape, std=1.0, seed=0):
 def test_rmsnorm_fwd_bwd(fvqa_lib, rows, dim):
     """fp32 residual stream in, bf16 GEMM operand out; backward returns fp32 dx (+ bf16 copy)."""
     from flipped_vqa_b200 import ops
-    x = bf16_randn(rows, dim, seed=1).float() + 1e-3 * torch.randn(rows, dim, device="cuda")
-    w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(torch.bfloat16)
-    dy = bf16_randn(rows, dim, seed=2)
+    x = h16_randn(rows, dim, seed=1).float() + 1e-3 * torch.randn(rows, dim, device="cuda")
+    w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(H16)
+    dy = h16_randn(rows, dim, seed=2)
     res = torch.randn(rows, dim, device="cuda")
     y, rstd = ops.rmsnorm_fwd(x, w, 1e-6)
     xr = x.clone().requires_grad_(True)
     yr = O.rmsnorm(xr, w.float(), 1e-6)
     assert relerr(y, yr) < 3e-3                 # one bf16 rounding of the output
     (yr * dy.float()).sum().backward()
-    dxb = torch.empty(rows, dim, dtype=torch.bfloat16, device="cuda")
-    dx, _ = ops.rmsnorm_bwd(dy, x, w, rstd, dres=res, dx_bf16=dxb)
+    dxb = torch.empty(rows, dim, dtype=H16, device="cuda")
+    dx, _ = ops.rmsnorm_bwd(dy, x, w, rstd, dres=res, dx_h16=dxb)
     assert relerr(dx, xr.grad + res) < 1e-5
     assert relerr(dxb, xr.grad + res) < 3e-3
     dx2, _ = ops.rmsnorm_bwd(dy, x, w, rstd)
@@ -46,16 +48,16 @@ def test_rmsnorm_gather_scatter(fvqa_lib):
     from flipped_vqa_b200 import ops
     rows, dim = 300, 512
     x = torch.randn(rows, dim, device="cuda")
-    w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(dim, device="cuda")).to(H16)
     idx = torch.tensor([5, 17, -1, 299, 0, -1, 42], dtype=torch.int32, device="cuda")
     y, rstd = ops.rmsnorm_gather_fwd(x, idx, w, 1e-6)
     valid = idx >= 0
     yr = O.rmsnorm(x[idx[valid].long()], w.float(), 1e-6)
     assert relerr(y[valid], yr) < 3e-3
     assert float(y[~valid].float().abs().max()) == 0.0
-    dy = bf16_randn(idx.numel(), dim, seed=5)
+    dy = h16_randn(idx.numel(), dim, seed=5)
     dx = torch.zeros_like(x)
-    dxb = torch.zeros(rows, dim, dtype=torch.bfloat16, device="cuda")
+    dxb = torch.zeros(rows, dim, dtype=H16, device="cuda")
     ops.rmsnorm_scatter_bwd(dy, x, idx, w, rstd, dx, dxb)
     xr = x.clone().requires_grad_(True)
     (O.rmsnorm(xr[idx[valid].long()], w.float(), 1e-6) * dy[valid].float()).sum().backward()
@@ -66,8 +68,8 @@ def test_rmsnorm_gather_scatter(fvqa_lib):
 @pytest.mark.parametrize("rows,hid", [(5, 768), (1024, 11008)])
 def test_swiglu(fvqa_lib, rows, hid):
     from flipped_vqa_b200 import ops
-    g = bf16_randn(rows, 2 * hid, seed=6)
-    dc = bf16_randn(rows, hid, seed=7)
+    g = h16_randn(rows, 2 * hid, seed=6)
+    dc = h16_randn(rows, hid, seed=7)
     c = ops.swiglu_fwd(g)
     gr = g.float().requires_grad_(True)
     cr = O.swiglu(gr[:, :hid], gr[:, hid:])
@@ -87,14 +89,14 @@ GEMM_SHAPES = [
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_nt(fvqa_lib, M, N, K):
     from flipped_vqa_b200 import ops
-    a = bf16_randn(M, K, seed=10)
-    b = bf16_randn(N, K, std=0.05, seed=11)
+    a = h16_randn(M, K, seed=10)
+    b = h16_randn(N, K, std=0.05, seed=11)
     ref = a.float() @ b.float().t()
     c = ops.gemm_nt(a, b)
     assert relerr(c, ref) < 5e-3, f"bf16 out relerr {relerr(c, ref)}"
     c32 = ops.gemm_nt(a, b, out_fp32=True)
     assert relerr(c32, ref) < 2e-4, f"fp32 out relerr {relerr(c32, ref)}"
-    r = bf16_randn(M, N, seed=12)
+    r = h16_randn(M, N, seed=12)
     cr = ops.gemm_nt(a, b, residual=r)
     assert relerr(cr, ref + r.float()) < 5e-3
     r32 = torch.randn(M, N, device="cuda")            # fp32 residual stream (h = x + attn, out = h + ffn)
@@ -107,11 +109,11 @@ def test_gemm_skinny_grouped(fvqa_lib, G, M, N, K, f32):
     """One launch for the adapter projections of all layers: C_g = A_g B_g^T with the weight blocks B_g in separate
     allocations (device pointer table) and strided views (ldb > K, as the [Wk; Wv] rows of the packed Wqkv^T)."""
     from flipped_vqa_b200 import ops
-    a = bf16_randn(G * M, K, seed=70).view(G, M, K)
+    a = h16_randn(G * M, K, seed=70).view(G, M, K)
     ldb = K + 64
-    blocks = [bf16_randn(N, ldb, std=0.05, seed=71 + g) for g in range(G)]
+    blocks = [h16_randn(N, ldb, std=0.05, seed=71 + g) for g in range(G)]
     ptrs = torch.tensor([b.data_ptr() for b in blocks], dtype=torch.int64, device="cuda")
-    out = torch.full((G + 1, M, N), 7.0, device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    out = torch.full((G + 1, M, N), 7.0, device="cuda", dtype=torch.float32 if f32 else H16)
     ops.gemm_skinny_grouped(a, ptrs, ldb, N, out[:G])
     assert torch.all(out[G].float() == 7.0)
     for g in range(G):
@@ -128,8 +130,8 @@ def test_gemm_quad_cluster_multicast(fvqa_lib, M, N, K):
     from flipped_vqa_b200 import ops
     if fvqa_lib.fvqa_gemm_quad_clusters() <= 0:
         pytest.skip("no 4-CTA clusters on this device")
-    a = bf16_randn(M, K, seed=80)
-    b = bf16_randn(N, K, std=0.05, seed=81)
+    a = h16_randn(M, K, seed=80)
+    b = h16_randn(N, K, std=0.05, seed=81)
     r32 = torch.randn(M, N, device="cuda")
     prev = fvqa_lib.fvqa_gemm_debug_quad(0)
     try:
@@ -151,8 +153,8 @@ def test_gemm_pair_tile_widths(fvqa_lib, bn):
     on ragged shapes: M not a multiple of 256 (peer CTA partly / fully out of range), N not a multiple of bn."""
     from flipped_vqa_b200 import ops
     for (M, N, K) in [(200, 384, 128), (384, 1536, 256), (650, 1000, 192), (129, 72, 64)]:
-        a = bf16_randn(M, K, seed=20)
-        b = bf16_randn(N, K, std=0.05, seed=21)
+        a = h16_randn(M, K, seed=20)
+        b = h16_randn(N, K, std=0.05, seed=21)
         r32 = torch.randn(M, N, device="cuda")
         ref = a.float() @ b.float().t()
         prev = fvqa_lib.fvqa_gemm_debug_force_bn(bn)
@@ -170,8 +172,8 @@ def test_gemm_swiglu_fused_matches_unfused(fvqa_lib, M, hid, K):
     """SwiGLU fused into the W1|W3 GEMM epilogue (fwd) and into the W2^T GEMM epilogue (bwd) must be
     BIT-identical to GEMM + swiglu kernel (llama/model.py:142), and close to an fp32 restatement."""
     from flipped_vqa_b200 import ops
-    x = bf16_randn(M, K, seed=30)
-    w13 = bf16_randn(2 * hid, K, std=0.05, seed=31)
+    x = h16_randn(M, K, seed=30)
+    w13 = h16_randn(2 * hid, K, std=0.05, seed=31)
     g_ref = ops.gemm_nt(x, w13)
     c_ref = ops.swiglu_fwd(g_ref)
     g, c = ops.gemm_swiglu_fwd(x, w13)
@@ -179,8 +181,8 @@ def test_gemm_swiglu_fused_matches_unfused(fvqa_lib, M, hid, K):
     gf = x.float() @ w13.float().t()
     assert relerr(c, torch.nn.functional.silu(gf[:, :hid]) * gf[:, hid:]) < 1e-2
     d = 4 * K if K <= 256 else K
-    dy = bf16_randn(M, d, seed=32)
-    w2t = bf16_randn(hid, d, std=0.05, seed=33)
+    dy = h16_randn(M, d, seed=32)
+    w2t = h16_randn(hid, d, std=0.05, seed=33)
     dc_ref = ops.gemm_nt(dy, w2t)
     dg_ref = ops.swiglu_bwd(dc_ref, g_ref)
     dg = ops.gemm_swiglu_bwd(dy, w2t, g_ref)
@@ -193,8 +195,8 @@ def test_gemm_rope_epilogue(fvqa_lib, S, H, hd, B):
     apply_rope on the q|k parts (llama/model.py:61-67,89-96)."""
     from flipped_vqa_b200 import ops
     d = H * hd
-    x = bf16_randn(B * S, d, seed=17)
-    w = bf16_randn(3 * d, d, std=0.05, seed=18)
+    x = h16_randn(B * S, d, seed=17)
+    w = h16_randn(3 * d, d, std=0.05, seed=18)
     cos, sin = O.rope_table(hd, S)
     cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
     out = ops.gemm_nt_rope(x, w, cos, sin, 2 * d, hd, S)
@@ -206,13 +208,13 @@ def test_gemm_rope_epilogue(fvqa_lib, S, H, hd, B):
 
 
 def test_gemm_rope_epilogue_position_table(fvqa_lib):
-    """fvqa_gemm_bf16_nt_rope_pos: the row's position comes from an int32 table (ragged / compacted token layouts of
+    """fvqa_gemm_nt_rope_pos: the row's position comes from an int32 table (ragged / compacted token layouts of
     shared-prefix option scoring). Must be bit-identical to the row % S variant on the same (row, position) pairs."""
     from flipped_vqa_b200 import ops
     S, H, hd, B = 128, 4, 128, 3
     d = H * hd
-    x = bf16_randn(B * S, d, seed=27)
-    w = bf16_randn(3 * d, d, std=0.05, seed=28)
+    x = h16_randn(B * S, d, seed=27)
+    w = h16_randn(3 * d, d, std=0.05, seed=28)
     cos, sin = O.rope_table(hd, S)
     cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
     dense = ops.gemm_nt_rope(x, w, cos, sin, 2 * d, hd, S)
@@ -228,23 +230,23 @@ def test_gemm_strided_views(fvqa_lib):
     """Sub-blocks of larger matrices (used for Wk|Wv of the fused QKV weight and its transpose)."""
     from flipped_vqa_b200 import ops
     d = 256
-    a_full = bf16_randn(16, 2 * d, seed=13)
-    wT = bf16_randn(d, 3 * d, std=0.05, seed=14)          # [d, 3d] ; use columns d..3d  -> B[N=d, K=2d], ldb=3d
+    a_full = h16_randn(16, 2 * d, seed=13)
+    wT = h16_randn(d, 3 * d, std=0.05, seed=14)          # [d, 3d] ; use columns d..3d  -> B[N=d, K=2d], ldb=3d
     b = wT[:, d:]
     ref = a_full[:10].float() @ b.float().t()
     out = ops.gemm_nt(a_full, b, out_fp32=True, M=10)
     assert out.shape == (10, d)
     assert relerr(out, ref) < 2e-4
-    w = bf16_randn(3 * d, d, std=0.05, seed=15)           # rows d..3d of [3d, d]
-    x = bf16_randn(10, d, seed=16)
+    w = h16_randn(3 * d, d, std=0.05, seed=15)           # rows d..3d of [3d, d]
+    x = h16_randn(10, d, seed=16)
     out2 = ops.gemm_nt(x, w[d:])
     assert relerr(out2, x.float() @ w[d:].float().t()) < 5e-3
 
 
 def test_gemm_rejects_bad_shapes(fvqa_lib):
     from flipped_vqa_b200 import ops, _lib
-    a = bf16_randn(128, 72)
-    b = bf16_randn(128, 72)
+    a = h16_randn(128, 72)
+    b = h16_randn(128, 72)
     with pytest.raises(_lib.FvqaError):
         ops.gemm_nt(a, b)           # K not a multiple of 64
 
@@ -253,15 +255,15 @@ def test_gemm_rejects_bad_shapes(fvqa_lib):
 def _attn_case(n_seq, S, H, hd, A, F, vstarts, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
     D = H * hd
-    qkv = (torch.randn(n_seq * S, 3 * D, device="cuda", generator=g)).to(torch.bfloat16)
-    akv = (torch.randn(16, 2 * D, device="cuda", generator=g)).to(torch.bfloat16)
+    qkv = (torch.randn(n_seq * S, 3 * D, device="cuda", generator=g)).to(H16)
+    akv = (torch.randn(16, 2 * D, device="cuda", generator=g)).to(H16)
     akv[A:] = 0
     gate1 = torch.randn(H, device="cuda", generator=g) * 0.5
     gate2 = -3.5 + 0.1 * torch.randn(H, device="cuda", generator=g)
     cos, sin = O.rope_table(hd, S)
     cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
     vstart = torch.tensor(vstarts, dtype=torch.int32, device="cuda")
-    dout = (torch.randn(n_seq * S, D, device="cuda", generator=g)).to(torch.bfloat16)
+    dout = (torch.randn(n_seq * S, D, device="cuda", generator=g)).to(H16)
     return qkv, akv, gate1, gate2, cos, sin, vstart, dout
 
 
@@ -269,7 +271,7 @@ def _rotate_qk(qkv, cos, sin, n_seq, S, H, hd):
     x = qkv.float().view(n_seq, S, 3, H, hd)
     q = O.apply_rope(x[:, :, 0], cos, sin)
     k = O.apply_rope(x[:, :, 1], cos, sin)
-    return torch.stack([q, k, x[:, :, 2]], dim=2).reshape(n_seq * S, 3 * H * hd).to(torch.bfloat16).contiguous()
+    return torch.stack([q, k, x[:, :, 2]], dim=2).reshape(n_seq * S, 3 * H * hd).to(H16).contiguous()
 
 
 def _attn_ref(qkv, akv, gate1, gate2, cos, sin, vstarts, dout, n_seq, S, H, hd, A, F):
@@ -357,7 +359,7 @@ def test_visual_proj_and_h0(fvqa_lib):
     dvf_in = torch.randn(B * F, d, device="cuda", generator=g)
     dwv = ops.visual_proj_bwd(dvf_in, video)
     assert relerr(dwv, dvf_in.t() @ video) < 1e-5
-    emb = bf16_randn(V, d, seed=31)
+    emb = h16_randn(V, d, seed=31)
     n_seq = 3 * B
     ids = torch.randint(0, V, (n_seq, S), device="cuda", generator=g, dtype=torch.int32)
     labels = torch.zeros(n_seq, S, dtype=torch.int32, device="cuda")
@@ -369,7 +371,7 @@ def test_visual_proj_and_h0(fvqa_lib):
     seq_video = torch.tensor(list(range(B)) * 3, dtype=torch.int32, device="cuda")
     h0 = ops.build_h0_fwd(emb, ids, labels, vstart, seq_video, qav_index, vf, temporal, n_seq, S, F)
     # reference (llama/model.py:324-336)
-    video_feature = (vf.view(B, F, d) + temporal[None]).to(torch.bfloat16)
+    video_feature = (vf.view(B, F, d) + temporal[None]).to(H16)
     ref = emb[ids.long()].clone()
     ref[:2 * B, 12:12 + F] = video_feature.repeat(2, 1, 1)
     q = ref[2 * B:] * (~(labels[2 * B:] >= 0))[..., None]
@@ -418,7 +420,7 @@ def test_qav_loss(fvqa_lib):
     B, F, d, tau = 4, 10, 512, 100.0
     g = torch.Generator(device="cuda").manual_seed(41)
     rows = B * F + 3
-    hn = bf16_randn(rows, d, seed=42)
+    hn = h16_randn(rows, d, seed=42)
     vf = torch.randn(B * F, d, device="cuda", generator=g)
     row_video = torch.tensor([b for b in range(B) for _ in range(F)] + [-1, -1, -1], dtype=torch.int32, device="cuda")
     target = torch.tensor(list(range(F)) * B + [0, 0, 0], dtype=torch.int32, device="cuda")
@@ -473,13 +475,13 @@ def test_attention_writes_stay_in_bounds(fvqa_lib, n_seq, S, H):
     hd, A, F = 128, 10, 10
     D = H * hd
     qkv, akv, gate1, gate2, cos, sin, vstart, dout = _attn_case(n_seq, S, H, hd, A, F, [18] * n_seq, seed=40)
-    out_buf, out = _with_canary((n_seq * S, D), torch.bfloat16)
+    out_buf, out = _with_canary((n_seq * S, D), H16)
     lse_buf, lse = _with_canary((n_seq, H, S), torch.float32)
     ops.attn_fwd(qkv, akv, cos, sin, gate1, gate2, vstart, n_seq, S, H, hd, A, F, out=out, lse=lse)
     torch.cuda.synchronize()
     assert _canary_intact(out_buf, out.numel()) and _canary_intact(lse_buf, lse.numel())
     assert not bool((out == 7.0).all(dim=1).any()), "a row of the output was never written"
-    dq_buf, dqkv = _with_canary((n_seq * S, 3 * D), torch.bfloat16)
+    dq_buf, dqkv = _with_canary((n_seq * S, 3 * D), H16)
     dakv_buf, dakv = _with_canary((A, 2 * D), torch.float32)
     g1_buf, dg1 = _with_canary((H,), torch.float32)
     g2_buf, dg2 = _with_canary((H,), torch.float32)
@@ -497,19 +499,19 @@ def test_attention_writes_stay_in_bounds(fvqa_lib, n_seq, S, H):
 @pytest.mark.parametrize("M,N,K", [(200, 384, 128), (650, 1000, 192), (3072, 4096, 256)])
 def test_gemm_writes_stay_in_bounds(fvqa_lib, M, N, K):
     from flipped_vqa_b200 import ops
-    a = bf16_randn(M, K, seed=41)
-    b = bf16_randn(N, K, std=0.05, seed=42)
+    a = h16_randn(M, K, seed=41)
+    b = h16_randn(N, K, std=0.05, seed=42)
     for f32 in (False, True):
-        buf, c = _with_canary((M, N), torch.float32 if f32 else torch.bfloat16)
+        buf, c = _with_canary((M, N), torch.float32 if f32 else H16)
         ops.gemm_nt(a, b, out=c, out_fp32=f32)
         torch.cuda.synchronize()
         assert _canary_intact(buf, c.numel())
     if N % 256 == 0:
         hid = N // 2
-        gbuf, g = _with_canary((M, N), torch.bfloat16)
-        cbuf, c = _with_canary((M, hid), torch.bfloat16)
+        gbuf, g = _with_canary((M, N), H16)
+        cbuf, c = _with_canary((M, hid), H16)
         ops.gemm_swiglu_fwd(a, b, g=g, c=c)
-        dbuf, dg = _with_canary((M, N), torch.bfloat16)
-        ops.gemm_swiglu_bwd(a, bf16_randn(hid, K, std=0.05, seed=43), g, dg=dg)
+        dbuf, dg = _with_canary((M, N), H16)
+        ops.gemm_swiglu_bwd(a, h16_randn(hid, K, std=0.05, seed=43), g, dg=dg)
         torch.cuda.synchronize()
         assert _canary_intact(gbuf, g.numel()) and _canary_intact(cbuf, c.numel()) and _canary_intact(dbuf, dg.numel())

@@ -4,14 +4,15 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import ops, _lib
+from flipped_vqa_b200._lib import H16
 
 
 def case(n_seq, S, H, A=10, F=10, seed=0):
     hd = 128
     D = H * hd
     g = torch.Generator(device="cuda").manual_seed(seed)
-    qkv = torch.randn(n_seq * S, 3 * D, device="cuda", generator=g).to(torch.bfloat16)
-    akv = torch.randn(A, 2 * D, device="cuda", generator=g).to(torch.bfloat16)
+    qkv = torch.randn(n_seq * S, 3 * D, device="cuda", generator=g).to(H16)
+    akv = torch.randn(A, 2 * D, device="cuda", generator=g).to(H16)
     gate1 = torch.randn(H, device="cuda", generator=g) * 0.5
     gate2 = torch.full((H,), -3.5, device="cuda") + 0.1 * torch.randn(H, device="cuda", generator=g)
     ang = torch.outer(torch.arange(S).float(), 1.0 / (10000.0 ** (torch.arange(0, hd, 2).float() / hd)))
@@ -19,7 +20,7 @@ def case(n_seq, S, H, A=10, F=10, seed=0):
     cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
     vs = [min(18, max(S - 12, 0)) if i % 3 != 2 else -1 for i in range(n_seq)]
     vstart = torch.tensor(vs, dtype=torch.int32, device="cuda")
-    dout = torch.randn(n_seq * S, D, device="cuda", generator=g).to(torch.bfloat16)
+    dout = torch.randn(n_seq * S, D, device="cuda", generator=g).to(H16)
     return dict(qkv=qkv, akv=akv, gate1=gate1, gate2=gate2, cos=cos, sin=sin, vstart=vstart, dout=dout, n_seq=n_seq, S=S, H=H, hd=hd, A=A, F=F)
 
 

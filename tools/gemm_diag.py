@@ -7,6 +7,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import _lib, ops
+from flipped_vqa_b200._lib import H16
 
 
 def force(bn):
@@ -15,15 +16,15 @@ def force(bn):
 
 def check(M, N, K, bn, out_fp32=True, residual=False):
     torch.manual_seed(M + N + K)
-    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-    b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    a = torch.randn(M, K, device="cuda").to(H16)
+    b = (torch.randn(N, K, device="cuda") * 0.05).to(H16)
     ref = a.float() @ b.float().t()
     r = torch.randn(M, N, device="cuda") if residual else None
     if residual:
         ref = ref + r
     force(bn)
     try:
-        c = ops.gemm_nt(a, b, out_fp32=out_fp32, residual=(r if out_fp32 or r is None else r.to(torch.bfloat16)))
+        c = ops.gemm_nt(a, b, out_fp32=out_fp32, residual=(r if out_fp32 or r is None else r.to(H16)))
         torch.cuda.synchronize()
     finally:
         force(0)
@@ -63,9 +64,9 @@ def main():
         shapes = [(3072, 12288, 4096), (3072, 4096, 4096), (3072, 22016, 4096), (3072, 4096, 11008), (3072, 11008, 4096),
                   (3072, 4096, 22016), (3072, 4096, 12288), (3072, 5120, 5120), (3072, 5120, 13824), (2304, 4096, 11008), (1950, 4096, 11008)]
         for (M, N, K) in shapes:
-            a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-            b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
-            c = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+            a = torch.randn(M, K, device="cuda").to(H16)
+            b = (torch.randn(N, K, device="cuda") * 0.05).to(H16)
+            c = torch.empty(M, N, device="cuda", dtype=H16)
             fl = 2.0 * M * N * K
             res = []
             for bn in (0, -1, 256, 240, 224, 208, 192, 176, 144, 128):
@@ -81,8 +82,8 @@ def main():
 def skinny():
     d = 4096
     for (M, N, K, f32, ldb) in [(10, 2 * d, d, False, d), (10, d, 2 * d, True, 3 * d), (10, 2 * 5120, 5120, False, 5120)]:
-        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-        wfull = (torch.randn(N, ldb, device="cuda") * 0.05).to(torch.bfloat16)
+        a = torch.randn(M, K, device="cuda").to(H16)
+        wfull = (torch.randn(N, ldb, device="cuda") * 0.05).to(H16)
         b = wfull[:, ldb - K:]
         ref = a.float() @ b.float().t()
         res = {}

@@ -3,6 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import _lib, ops
+from flipped_vqa_b200._lib import H16
 from tools.gemm_step_shapes import timeit
 
 lib = _lib.lib()
@@ -11,8 +12,8 @@ shapes = [(256, 512, 64), (256, 512, 256), (512, 1024, 512), (700, 1536, 384), (
 if len(sys.argv) > 1 and sys.argv[1] == "small":
     shapes = shapes[:2]
 for (M, N, K) in shapes:
-    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-    b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    a = torch.randn(M, K, device="cuda").to(H16)
+    b = (torch.randn(N, K, device="cuda") * 0.05).to(H16)
     r = torch.randn(M, N, device="cuda")
     ref = a.float() @ b.float().t()
     lib.fvqa_gemm_debug_quad(0)
@@ -24,7 +25,7 @@ for (M, N, K) in shapes:
     print(f"{M}x{N}x{K}: quad relerr bf16 {e16:.2e} f32+res {e32:.2e}; identical to pair kernel: {torch.equal(p16, q16)} {torch.equal(p32, q32)}", flush=True)
     assert e16 < 5e-3 and e32 < 2e-4
     if M >= 2000:
-        c16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16); c32 = torch.empty(M, N, device="cuda")
+        c16 = torch.empty(M, N, device="cuda", dtype=H16); c32 = torch.empty(M, N, device="cuda")
         res = []
         for mode in (0, 2):
             lib.fvqa_gemm_debug_quad(mode)

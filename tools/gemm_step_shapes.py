@@ -4,8 +4,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import _lib, ops
+from flipped_vqa_b200._lib import H16
 
-BF = torch.bfloat16
+BF = H16
 
 
 def timeit(fn, n=30):

@@ -4,6 +4,7 @@ import os, sys, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import _lib, ops
+from flipped_vqa_b200._lib import H16
 import pynvml
 
 
@@ -46,9 +47,9 @@ def main():
     if len(sys.argv) > 1:
         shapes = shapes[:int(sys.argv[1])]
     for (M, N, K) in shapes:
-        a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-        b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
-        c = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        a = torch.randn(M, K, device="cuda").to(H16)
+        b = (torch.randn(N, K, device="cuda") * 0.05).to(H16)
+        c = torch.empty(M, N, device="cuda", dtype=H16)
         fl = 2.0 * M * N * K
         res = []
         for name, fn in [("pair", lambda: ops.gemm_nt(a, b, out=c)), ("cublas", lambda: torch.matmul(a, b.t(), out=c))]:

@@ -3,13 +3,14 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch, pynvml
 from flipped_vqa_b200 import _lib, ops
+from flipped_vqa_b200._lib import H16
 from gemm_sustained import sustained
 pynvml.nvmlInit()
 lib = _lib.lib()
 for (M, N, K) in [(3072, 4096, 22016), (3072, 4096, 12288), (3072, 4096, 11008), (3072, 22016, 4096)]:
-    a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
-    b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
-    c = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    a = torch.randn(M, K, device="cuda").to(H16)
+    b = (torch.randn(N, K, device="cuda") * 0.05).to(H16)
+    c = torch.empty(M, N, device="cuda", dtype=H16)
     out = []
     for on in (0, 1, 0, 1):
         lib.fvqa_gemm_debug_l2_hints(on)

@@ -32,12 +32,12 @@ def main(path, json_out=None):
     for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
         print(f"{v[1] / 1e3:10.3f} {v[0]:6d} {100 * v[1] / tot:5.1f}% {v[1] / v[0]:9.1f} {v[2] / v[0] / 1e6:15.1f}  {k}")
     print(f"{tot / 1e3:10.3f} ms in {sum(v[0] for v in agg.values())} launches (cold-cache, serialised: compare shares)")
-    gem = [v for k, v in agg.items() if k.startswith("fvqa::gemm_bf16_nt_pair_kernel") or k.startswith("gemm_bf16_nt_pair_kernel")]
+    gem = [v for k, v in agg.items() if k.startswith("fvqa::gemm_nt_pair_kernel") or k.startswith("gemm_nt_pair_kernel")]
     if gem and json_out:
         n = sum(v[0] for v in gem)
         out = {"avg_dram_bytes_per_launch": sum(v[2] for v in gem) / n, "launches": n,
                "avg_us_per_launch_under_ncu": sum(v[1] for v in gem) / n, "share_of_step_under_ncu": sum(v[1] for v in gem) / tot,
-               "note": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the gemm_bf16_nt_pair_kernel launches of one 7B NExT-QA "
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum averaged over the gemm_nt_pair_kernel launches of one 7B NExT-QA "
                        "step (ncu launch list, cold cache per launch)", "source": path}
         with open(json_out, "w") as f:
             json.dump(out, f, indent=1)

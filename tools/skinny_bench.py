@@ -3,17 +3,18 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from flipped_vqa_b200 import _lib, ops
+from flipped_vqa_b200._lib import H16
 from tools.gemm_step_shapes import timeit
 
 lib = _lib.lib()
 L, A, d = 32, 10, 4096
-w = [(torch.randn(3 * d, d, device="cuda") * 0.02).to(torch.bfloat16) for _ in range(L)]
+w = [(torch.randn(3 * d, d, device="cuda") * 0.02).to(H16) for _ in range(L)]
 wt = [x.t().contiguous() for x in w]
 kv = torch.tensor([x[d:].data_ptr() for x in w], dtype=torch.int64, device="cuda")
 kvt = torch.tensor([x[:, d:].data_ptr() for x in wt], dtype=torch.int64, device="cuda")
-a = torch.randn(L, A, d, device="cuda").to(torch.bfloat16)
-da = torch.randn(L, A, 2 * d, device="cuda").to(torch.bfloat16)
-out = torch.empty(L, A, 2 * d, device="cuda", dtype=torch.bfloat16)
+a = torch.randn(L, A, d, device="cuda").to(H16)
+da = torch.randn(L, A, 2 * d, device="cuda").to(H16)
+out = torch.empty(L, A, 2 * d, device="cuda", dtype=H16)
 g = torch.empty(L, A, d, device="cuda")
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 for nt in (0, 1, 2, 4):
