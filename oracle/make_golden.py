@@ -110,6 +110,73 @@ def run_reference_options(dtype, n_options=5):
     return {"token_losses": tok.float().numpy(), "prediction": pred.numpy()}
 
 
+# ------------------------------------------------------------------------------------------------
+# multi-step training trajectory through the reference's OWN loop
+# ------------------------------------------------------------------------------------------------
+TRAJ = dict(n_batches=8, accum_iter=2, epochs=2, lr=5e-3, min_lr=5e-4, warmup_epochs=1, weight_decay=0.14, batch_seed0=900)
+
+
+def trajectory_batches():
+    r = GOLDEN_RUN
+    return [synthetic_batch(r["bsz"], r["seqlen"], GOLDEN["vocab_size"], max_feats=r["max_feats"], seed=TRAJ["batch_seed0"] + i,
+                            video_start=r["video_start"], vaq_label_span=(5, 9)) for i in range(TRAJ["n_batches"])]
+
+
+def trajectory_args():
+    import argparse
+    return argparse.Namespace(accum_iter=TRAJ["accum_iter"], lr=TRAJ["lr"], min_lr=TRAJ["min_lr"], warmup_epochs=TRAJ["warmup_epochs"],
+                              epochs=TRAJ["epochs"], debug=False)
+
+
+def run_reference_trajectory(dtype=torch.float32):
+    """The UNMODIFIED `engine.train_one_epoch` (`engine.py:10-56`) + `util.misc.NativeScalerWithGradNormCount` (`util/misc.py:253-279`)
+    + `util.lr_sched.adjust_learning_rate` + AdamW(betas=(0.9, 0.95)) as `train.py:120-121` builds it (timm's weight-decay grouping
+    puts every trainable of this model - all >= 2-D, none named *.bias - into the decayed group) driving the reference model for
+    TRAJ['epochs'] epochs over the same 8 micro-batches (accum_iter 2 -> 4 optimizer steps per epoch). CPU run: the reference's
+    GradScaler disables itself without CUDA (scale 1) and `torch.cuda.synchronize` (`engine.py:43`) is stubbed."""
+    import importlib
+    params, sd, _ = golden_inputs()
+    mod = ref_shims.import_reference("model")
+    engine = importlib.import_module("engine")
+    misc = importlib.import_module("util.misc")
+    r = GOLDEN_RUN
+    model = ref_shims.build_reference_model(mod, GOLDEN, ref_shims.reference_args(max_feats=r["max_feats"], bias=r["bias"], tau=r["tau"]), sd, dtype)
+    trainables = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW([{"params": trainables, "weight_decay": TRAJ["weight_decay"]}], lr=TRAJ["lr"], betas=(0.9, 0.95))
+    step_losses = []
+
+    class Recorder(torch.nn.Module):                     # records what model(data) returned; the loop itself is the reference's
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, data):
+            out = self.inner(data)
+            step_losses.append([float(x.detach()) for x in out])
+            return out
+
+    wrapped = Recorder(model)
+    batches = trajectory_batches()
+    targs = trajectory_args()
+    out = {}
+    orig_sync = torch.cuda.synchronize
+    torch.cuda.synchronize = lambda *a, **k: None
+    try:
+        with ref_shims.patched_torch(dtype):
+            scaler = misc.NativeScalerWithGradNormCount()
+            for epoch in range(TRAJ["epochs"]):
+                stats = engine.train_one_epoch(wrapped, batches, opt, epoch, scaler, args=targs)
+                for k, v in stats.items():
+                    out[f"epoch{epoch}/stats/{k}"] = np.float64(v)
+                for n, p in model.named_parameters():
+                    if p.requires_grad:
+                        out[f"epoch{epoch}/param/{n}"] = p.detach().float().numpy().copy()
+    finally:
+        torch.cuda.synchronize = orig_sync
+    out["step_losses"] = np.array(step_losses, dtype=np.float64)          # [epochs * n_batches, 3]
+    return out
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -131,9 +198,12 @@ def main():
             au[f"{mode}/gold/{k}"] = v
         print(mode, "gold losses", au[f"{mode}/gold/loss"])
     np.savez_compressed(os.path.join(gdir, "train_audio_small.npz"), **au)
+    tj = run_reference_trajectory()
+    np.savez_compressed(os.path.join(gdir, "trajectory_small.npz"), **tj)
+    print("trajectory step losses (sum):", tj["step_losses"].sum(1))
     print("gold losses", tr["gold/loss"], "fp16 losses", tr["fp16/loss"])
     print("gold pred", op["gold/prediction"], "fp16 pred", op["fp16/prediction"])
-    for f in ("train_small.npz", "options_small.npz", "train_audio_small.npz"):
+    for f in ("train_small.npz", "options_small.npz", "train_audio_small.npz", "trajectory_small.npz"):
         print(f, os.path.getsize(os.path.join(gdir, f)), "bytes")
 
 
