@@ -10,9 +10,11 @@ One JSON line on stdout (rank 0). A "step" = forward + hand-written backward + g
   e2e   : same metric through the public API `model(data)` with HOST batch tensors: host planning,
           pinned H2D copy and a D2H read of the loss inside the timed region
   roofline     : tcgen05 GEMM launches sampled with CUDA events inside the timed region
-  cpu_baseline : the oracle (CPU port of the reference's step) on a bounded 7B-shaped slice
-`--impl reference` times that CPU port with all host threads (the reference itself is pure PyTorch
-and /root/reference does not exist on the GPU box).
+  cpu_baseline : the oracle (CPU port of the reference's step): one real full-depth step at a bounded batch
+  gpu_eager_baseline : the reference's op sequence in eager PyTorch on the same GPU (N = 1), outside the timed regions
+  dp_check / comm    : N > 1: hardware check that the reduced gradient is the rank mean; exposed NCCL wait and rank skew
+`--impl reference` times that CPU port with all host threads, every timed step a real full-depth step at
+a bounded batch (the reference itself is pure PyTorch and /root/reference does not exist on the GPU box).
 """
 from __future__ import annotations
 
@@ -147,96 +149,140 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_slice_seconds(cfg, n_layers, bsz, threads):
-    """fwd+bwd of the ORACLE (CPU port of the reference's step, fp32) on a 7B-shaped slice with
-    `n_layers` layers and batch `bsz`."""
-    from oracle import llama_vqa_oracle as O
-    from flipped_vqa_b200.synthetic import ffn_hidden_dim, synthetic_batch
-    torch.set_num_threads(threads)
-    d, V, H, S = cfg["dim"], cfg["vocab_size"], cfg["n_heads"], cfg["seqlen"]
-    hid = ffn_hidden_dim(d, cfg["multiple_of"])
-    g = torch.Generator().manual_seed(0)
-    r = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
-    sd = {"tok_embeddings.weight": r(V, d), "output.weight": r(V, d), "norm.weight": torch.ones(d),
-          "adapter_query.weight": r(ADAPTER_LEN * n_layers, d, std=1.0), "visual_proj.weight": r(d, 768, std=0.03),
-          "temporal_emb.weight": r(MAX_FEATS, d, std=1.0)}
-    for i in range(n_layers):
-        p = f"layers.{i}."
-        for nm in ("wq", "wk", "wv", "wo"):
-            sd[p + f"attention.{nm}.weight"] = r(d, d)
-        sd[p + "feed_forward.w1.weight"] = r(hid, d)
-        sd[p + "feed_forward.w2.weight"] = r(d, hid)
-        sd[p + "feed_forward.w3.weight"] = r(hid, d)
-        sd[p + "attention_norm.weight"] = torch.ones(d)
-        sd[p + "ffn_norm.weight"] = torch.ones(d)
-        sd[p + "attention.gate1"] = r(1, H, 1, 1, std=0.5)
-        sd[p + "attention.gate2"] = torch.full((1, H, 1, 1), -BIAS)
-    params = SimpleNamespace(dim=d, n_layers=n_layers, n_heads=H, vocab_size=V, norm_eps=1e-6, max_seq_len=S,
-                             adapter_len=ADAPTER_LEN, adapter_layer=n_layers)
-    st = O.prepare_state(sd)
-    data = synthetic_batch(bsz, S, V, max_feats=MAX_FEATS, seed=1)
-    t0 = time.perf_counter()
-    losses = O.forward_losses(st, params, data, max_feats=MAX_FEATS, tau=TAU)
-    sum(losses).backward()
-    return time.perf_counter() - t0
+class CpuOracleStep:
+    """The ORACLE (CPU port of the reference's step, `llama/model.py:250-365`, fp32, autograd) at FULL DEPTH on a bounded batch.
+    Timing only: every layer aliases ONE random layer's frozen weights (same shapes, FLOPs and bytes per layer; 0.8 GB instead of
+    27 GB of host memory and no minute-long random fill), trainables are per layer as in the model."""
+
+    def __init__(self, cfg, n_layers, threads):
+        from oracle import llama_vqa_oracle as O
+        from flipped_vqa_b200.synthetic import ffn_hidden_dim
+        torch.set_num_threads(threads)
+        self.O, self.cfg, self.L = O, cfg, n_layers
+        d, V, H, S = cfg["dim"], cfg["vocab_size"], cfg["n_heads"], cfg["seqlen"]
+        hid = ffn_hidden_dim(d, cfg["multiple_of"])
+        g = torch.Generator().manual_seed(0)
+        r = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+        sd = {"tok_embeddings.weight": r(V, d), "output.weight": r(V, d), "norm.weight": torch.ones(d),
+              "adapter_query.weight": r(ADAPTER_LEN * n_layers, d, std=1.0), "visual_proj.weight": r(d, 768, std=0.03),
+              "temporal_emb.weight": r(MAX_FEATS, d, std=1.0)}
+        shared = {"attention.wq.weight": r(d, d), "attention.wk.weight": r(d, d), "attention.wv.weight": r(d, d), "attention.wo.weight": r(d, d),
+                  "feed_forward.w1.weight": r(hid, d), "feed_forward.w2.weight": r(d, hid), "feed_forward.w3.weight": r(hid, d),
+                  "attention_norm.weight": torch.ones(d), "ffn_norm.weight": torch.ones(d)}
+        for i in range(n_layers):
+            p = f"layers.{i}."
+            for k, v in shared.items():
+                sd[p + k] = v
+            sd[p + "attention.gate1"] = r(1, H, 1, 1, std=0.5)
+            sd[p + "attention.gate2"] = torch.full((1, H, 1, 1), -BIAS)
+        self.params = SimpleNamespace(dim=d, n_layers=n_layers, n_heads=H, vocab_size=V, norm_eps=1e-6, max_seq_len=S,
+                                      adapter_len=ADAPTER_LEN, adapter_layer=n_layers)
+        self.st = O.prepare_state(sd)
+        self.names = O.trainable_names(self.st)
+
+    def step(self, bsz, seed=1):
+        from flipped_vqa_b200.synthetic import synthetic_batch
+        data = synthetic_batch(bsz, self.cfg["seqlen"], self.cfg["vocab_size"], max_feats=MAX_FEATS, seed=seed)
+        for n in self.names:
+            self.st[n].grad = None
+        t0 = time.perf_counter()
+        losses = self.O.forward_losses(self.st, self.params, data, max_feats=MAX_FEATS, tau=TAU)
+        sum(losses).backward()
+        return time.perf_counter() - t0
 
 
-def _extrapolate(t1, t2, L):
-    """1-layer and 2-layer slice times -> (full-depth step time, per-layer time, fixed time). The per-layer time is clamped to
-    at least 5 % of the 1-layer slice so that timing noise in t2 - t1 cannot collapse the extrapolation."""
-    t_layer = max(t2 - t1, 0.05 * t1)
-    t_fixed = max(t1 - t_layer, 0.0)
-    return t_fixed + L * t_layer, t_layer, t_fixed
+def _bounded_batch(cfg, threads, n_steps, budget_s):
+    """Largest batch in {B, B/2, ..., 1} whose `n_steps` full-depth CPU steps fit `budget_s`, estimated from a 2-layer probe at
+    batch 1 (a discarded cold call first). Returns (batch, probe seconds per layer per sample)."""
+    probe = CpuOracleStep(cfg, 2, threads)
+    probe.step(1)
+    t2 = probe.step(1)
+    per_layer = t2 / 2.0                                   # upper bound: the probe's fixed cost (heads, embedding) is folded in
+    B, L = cfg["bsz"], cfg["adapter_layer"]
+    b = B
+    while b > 1 and n_steps * b * L * per_layer > budget_s:
+        b //= 2
+    return b, per_layer
 
 
-def cpu_baseline(cfg, budget_s=25.0):
-    """Bounded CPU sample: 1-layer and 2-layer 7B-shaped slices (one untimed warm-up call, then the faster of two runs each)
-    -> per-layer and fixed cost -> extrapolated full-depth step time (clearly labelled)."""
+def cpu_baseline(cfg, budget_s=30.0):
+    """Bounded CPU sample for the `cpu_baseline` object: ONE real full-depth fwd+bwd of the oracle at a bounded batch (no layer
+    extrapolation), after a discarded 2-layer warm call."""
     threads = os.cpu_count() or 1
     B, L = cfg["bsz"], cfg["adapter_layer"]
-    t_warm = cpu_slice_seconds(cfg, 1, B, threads)                  # cold: thread pool, allocator
-    reps = 2 if t_warm * 7 < budget_s else 1
-    t1 = min(cpu_slice_seconds(cfg, 1, B, threads) for _ in range(reps))
-    t2 = min(cpu_slice_seconds(cfg, 2, B, threads) for _ in range(reps))
-    t_full, t_layer, t_fixed = _extrapolate(t1, t2, L)
-    return dict(value=B / t_full, unit="samples/s", cores=threads, kind="port",
-                sample=f"oracle fp32 fwd+bwd, {WORKLOAD_NAMES.get(cfg['name'], cfg['name'])} shapes, 1- and 2-layer slices (best of {reps}) -> "
-                       f"fixed + L x per-layer; extrapolated to {L} layers (t_layer={t_layer:.2f}s t_fixed={t_fixed:.2f}s)")
+    Bs, per_layer = _bounded_batch(cfg, threads, 1, budget_s)
+    t = CpuOracleStep(cfg, L, threads).step(Bs)
+    return dict(value=Bs / t, unit="samples/s", cores=threads, kind="port", extrapolated=False,
+                sample=f"oracle fp32 fwd+bwd (CPU port of llama/model.py step), {WORKLOAD_NAMES.get(cfg['name'], cfg['name'])} shapes, ALL {L} layers, "
+                       f"one step at batch {Bs} of {B} in {t:.1f} s (2-layer probe: {per_layer:.2f} s per layer per sample)")
 
 
 def run_reference_arm(a, guard):
-    """`--impl reference`: the reference's step is pure PyTorch with no native path; on this box it is represented by the
-    oracle port on the host cores. Each timed step = one 1-layer and one 2-layer 7B-shaped slice (forward + backward) at a
-    bounded batch; the medians over the K steps give the per-layer and fixed cost, extrapolated to the full depth."""
+    """`--impl reference`: the reference's step is pure PyTorch with no native path and /root/reference does not exist on the GPU
+    box; it is represented by the oracle port on the host cores. Every timed step is a REAL full-depth forward + backward (all
+    layers, three objective streams, heads) at a bounded batch chosen so that K + W steps end within minutes; value = that
+    batch / measured step time (nothing is extrapolated over layers). Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cfg = dict(CONFIGS[a.config], name=a.config)
     threads = os.cpu_count() or 1
     B, L = cfg["bsz"], cfg["adapter_layer"]
-    t_cold = cpu_slice_seconds(cfg, 1, B, threads)                  # cold call (thread pool, allocator): sizes the sample
-    Bs = B
-    while Bs > 1 and (a.steps + a.warmup) * 2.6 * t_cold * Bs / B > 170.0:   # keep the whole arm within minutes
-        Bs //= 2
-    for _ in range(max(a.warmup, 1)):
-        cpu_slice_seconds(cfg, 1, Bs, threads)
-    t1s, t2s = [], []
-    for _ in range(a.steps):
-        t1s.append(cpu_slice_seconds(cfg, 1, Bs, threads))
-        t2s.append(cpu_slice_seconds(cfg, 2, Bs, threads))
-    med = lambda v: sorted(v)[len(v) // 2]
-    t_full, t_layer, t_fixed = _extrapolate(med(t1s), med(t2s), L)
-    value = Bs / t_full
+    Bs, per_layer = _bounded_batch(cfg, threads, a.steps + a.warmup, 240.0)
+    model = CpuOracleStep(cfg, L, threads)
+    for i in range(a.warmup):
+        model.step(Bs, seed=i)
+    times = [model.step(Bs, seed=100 + i) for i in range(a.steps)]
+    t = sum(times) / len(times)
+    value = Bs / t
     line = {"impl": "reference", "metric": "7B NExT-QA train samples/s" if a.config == "7b-nextqa" else f"{a.config} train samples/s",
             "value": value, "unit": "samples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": t_full * 1e3 * (B / Bs), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD_NAMES[a.config]},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
-                             "sample": f"oracle (CPU port of llama/model.py step) fp32 fwd+bwd; each timed step = a 1-layer and a 2-layer "
-                                       f"7B-shaped slice at batch {Bs}; medians over {a.steps} steps -> fixed {t_fixed:.2f}s + {L} x "
-                                       f"{t_layer:.2f}s per layer"},
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "extrapolated": False,
+            "config": {"workload": WORKLOAD_NAMES[a.config], "batch_per_step": Bs, "config_batch": B, "layers": L,
+                       "note": "full depth, bounded batch: samples/s = batch_per_step / measured step time"},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "extrapolated": False,
+                             "sample": f"oracle (CPU port of llama/model.py step) fp32 fwd+bwd, all {L} layers, batch {Bs} of {B} per timed step; "
+                                       f"mean of {a.steps} steps = {t:.2f} s (min {min(times):.2f}, max {max(times):.2f})"},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     guard.emit(json.dumps(line))
+
+
+def gpu_eager_baseline(model, cfg, dev, steps=3):
+    """SURVEY 8(d) last row: the reference's op sequence (`llama/model.py:250-365`: three streams one after another, unfused
+    attention with materialised scores, full-vocabulary logits, autograd) in stock eager PyTorch on the SAME GPU, in the
+    library's operand dtype (fp16 = the reference's own), on the SAME weights as the product model (the oracle's state dict
+    aliases the model's parameters) + fused AdamW. Outside every timed region of the product; N = 1 only."""
+    from oracle import llama_vqa_oracle as O
+    from flipped_vqa_b200 import _lib
+    from flipped_vqa_b200.synthetic import synthetic_batch
+    sd = {n: p.detach() for n, p in model.state_dict().items()}
+    st = O.prepare_state(sd, frozen_dtype=_lib.H16, device=dev)
+    params = SimpleNamespace(dim=cfg["dim"], n_layers=cfg["n_layers"], n_heads=cfg["n_heads"], vocab_size=cfg["vocab_size"], norm_eps=1e-6,
+                             max_seq_len=cfg["seqlen"], adapter_len=ADAPTER_LEN, adapter_layer=cfg["adapter_layer"])
+    opt = torch.optim.AdamW([st[n] for n in O.trainable_names(st)], lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
+    batches = [synthetic_batch(cfg["bsz"], cfg["seqlen"], cfg["vocab_size"], max_feats=MAX_FEATS, seed=2000 + i) for i in range(2)]
+
+    def step(i):
+        losses = O.forward_losses(st, params, batches[i % 2], max_feats=MAX_FEATS, tau=TAU)
+        sum(losses).backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return losses
+
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": cfg["bsz"] / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms, "dtype": _lib.DTYPE_NAME, "steps": steps,
+            "what": "oracle = the reference's op sequence under autograd in eager PyTorch (cuBLAS / ATen kernels) + fused AdamW, same GPU, same "
+                    "weights and shapes, resident batch; not part of the product path"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -266,6 +312,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the end-to-end leg")
     ap.add_argument("--no-padfree", action="store_true", help="skip the extra padding-free leg")
     ap.add_argument("--sample-layers", type=int, default=2, help="layers whose GEMM launches are event-timed inside the timed region")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-the-same-GPU comparator leg (N = 1)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
@@ -323,6 +370,35 @@ def main():
         return loss.item()                                      # D2H read of the step's result
 
     step_ms = []        # per-step device times of the last timed() call on this rank (diagnostic: one-off stalls show up here)
+    rank_ms = []        # device time of the timed region on every rank (N > 1)
+
+    def dp_check():
+        """N > 1, un-timed: hardware proof that the data-parallel gradient is the rank MEAN (DDP semantics, `train.py:115-117`).
+        The same batch plan goes through backward twice on every rank - once with the exchange switched off (local gradient),
+        once through DataParallel (chunked NCCL all-reduces overlapped with backward) - then every rank all-gathers the local
+        flat buffers and compares its reduced buffer with their mean."""
+        net._attach()
+        sync = model.grad_sync
+        model.grad_sync = None
+        vqa, vaq, qav = model.forward_plan(plans[0])
+        (vqa + vaq + qav).backward()
+        local = model._grad_buffers.flat.clone()
+        model.grad_sync = sync
+        opt.zero_grad(set_to_none=True)
+        vqa, vaq, qav = net.forward_plan(plans[0])
+        (vqa + vaq + qav).backward()
+        reduced = model._grad_buffers.flat.clone()
+        opt.zero_grad(set_to_none=True)
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        mean = torch.stack(gathered).double().mean(0)
+        err = float((reduced.double() - mean).abs().max() / mean.abs().max())
+        distinct = float((gathered[0] - gathered[-1]).abs().max()) > 0          # ranks really hold different gradients
+        t = torch.tensor([err], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst = float(t.item())
+        return {"status": "ok" if (worst < 1e-5 and distinct) else "FAILED", "max_rel_err_over_ranks": worst, "ranks_hold_distinct_gradients": distinct,
+                "elements": int(local.numel()), "what": "post-all-reduce flat gradient vs mean of the all-gathered pre-reduce buffers"}
 
     def timed(fn, steps, sample_gemm=False):
         gc.collect()
@@ -352,21 +428,51 @@ def main():
         launches = ops.LAUNCHES - launches0
         clocks = sampler.stop()
         timer, ops.GEMM_TIMER = ops.GEMM_TIMER, None
+        rank_ms.clear()
         if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, clocks, (timer.summary() if timer is not None else None)
+            every = [torch.zeros(1, device=dev) for _ in range(world)]
+            dist.all_gather(every, torch.tensor([ms], device=dev))
+            rank_ms.extend(round(float(x.item()), 3) for x in every)
+            ms = max(rank_ms)
+        return ms, launches, clocks, timer
 
     L = cfg["adapter_layer"]
-    model._engine.sample_layers = tuple(sorted({0, L // 2} if a.sample_layers >= 2 else {L // 2})) if a.sample_layers > 0 else ()   # not the pruned last layer
+    chunk = model._engine.adapter_grad_chunk
+    quiet_layers = {0, L // 2} if a.sample_layers >= 2 else {L // 2}            # not the pruned last layer
+    # N > 1: the all-reduce of the adapter rows of layers [c, c + chunk) is issued after layer c's backward and runs on NCCL's
+    # stream while layer c - 1 is computed: sample such layers too, so SM contention from NCCL shows up in the GEMM numbers
+    overlap_layers = {c - 1 for c in range(chunk, L, chunk)} if world > 1 else set()
+    overlap_layers = set(sorted(overlap_layers)[-2:])
+    model._engine.sample_layers = tuple(sorted(quiet_layers | overlap_layers)) if a.sample_layers > 0 else ()
     ClockSampler._nvml(local)                                   # NVML set-up before the warm-up, not between warm-up and timing
+    dpc = dp_check() if world > 1 else None
     for i in range(a.warmup):
         step_resident(i)
-    ms, launches, clocks, gemm = timed(step_resident, a.steps, sample_gemm=a.sample_layers > 0)
+    if world > 1:
+        model.grad_sync.timing = []
+        msg0 = model.grad_sync.messages
+    ms, launches, clocks, gemm_timer = timed(step_resident, a.steps, sample_gemm=a.sample_layers > 0)
+    gemm = gemm_timer.summary(quiet_layers) if gemm_timer is not None else None
+    gemm_overlap = gemm_timer.summary(overlap_layers) if (gemm_timer is not None and overlap_layers) else None
     ms_per_step = ms / a.steps
     resident_step_ms = list(step_ms)
+    resident_rank_ms = list(rank_ms)
     value = world * B / (ms_per_step * 1e-3)
+    comm = None
+    if world > 1:
+        waits = [e0.elapsed_time(e1) for e0, e1 in model.grad_sync.timing]
+        model.grad_sync.timing = None
+        mine = torch.tensor([sum(waits) / max(len(waits), 1), max(waits) if waits else 0.0], device=dev)
+        every = [torch.zeros(2, device=dev) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_step = [x / a.steps for x in resident_rank_ms]
+        comm = {"comm_exposed_ms_per_step_by_rank": [round(float(x[0]), 4) for x in every],
+                "comm_exposed_ms_worst_step_by_rank": [round(float(x[1]), 4) for x in every],
+                "step_ms_by_rank": [round(x, 3) for x in per_rank_step], "rank_skew_ms_per_step": round(max(per_rank_step) - min(per_rank_step), 4),
+                "messages_per_step": (model.grad_sync.messages - msg0) / a.steps,
+                "what": "comm_exposed = CUDA-event time the compute stream spends in GradSync.finish() waiting for NCCL (late message + rank "
+                        "skew: a rank that finishes backward early waits here for the slowest one); step_ms_by_rank = each rank's own device "
+                        "time of the timed region / steps"}
 
     if a.no_e2e:
         ms_e, clocks_e = float("nan"), None
@@ -430,8 +536,22 @@ def main():
                                 "traffic": (tr["avg_dram_bytes_per_launch"] if tr else None),
                                 "traffic_note": (tr["note"] if tr else "no ncu capture for this config"),
                                 "launches_sampled": gemm["launches"], "avg_launch_ms": gemm["avg_ms"],
-                                "avg_flops_per_launch": gemm["avg_flops"], "sampled_layers": list(model._engine.sample_layers),
-                                "gemm_share_of_step": gemm["total_ms"] / len(model._engine.sample_layers) * L / (ms_per_step * a.steps)}
+                                "avg_flops_per_launch": gemm["avg_flops"], "sampled_layers": sorted(quiet_layers),
+                                "gemm_share_of_step": gemm["total_ms"] / len(quiet_layers) * L / (ms_per_step * a.steps)}
+            if gemm_overlap is not None:
+                line["roofline"]["overlapped_with_allreduce"] = {"sampled_layers": sorted(overlap_layers), "achieved": gemm_overlap["tflops"],
+                                                                 "avg_launch_ms": gemm_overlap["avg_ms"], "launches_sampled": gemm_overlap["launches"],
+                                                                 "vs_quiet_layers": gemm_overlap["tflops"] / gemm["tflops"]}
+        if dpc is not None:
+            line["dp_check"] = dpc
+        if comm is not None:
+            line["comm"] = comm
+        if world == 1 and not a.no_eager_baseline:
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(model, cfg, dev)
+                line["gpu_eager_baseline"]["speedup_of_this_repo"] = value / line["gpu_eager_baseline"]["value"]
+            except Exception as e:
+                line["gpu_eager_baseline"] = {"value": None, "unit": "samples/s", "what": f"failed: {e}"}
         if world == 1 and not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(cfg)

@@ -8,8 +8,12 @@ the hand-written backward, on NCCL's stream, overlapped with the remaining layer
     of `chunk_layers` layers while backward continues;
   * gates + visual_proj + temporal_emb are one contiguous tail of the flat buffer, final only after
     layer 0 -> one message at the end.
-Like the reference's DDP (no `no_sync()` under accum_iter, `engine.py:37-41`) the reduce runs on every
-micro-step; averaging per micro-step then accumulating equals accumulating then averaging.
+The reference's DDP reduces on EVERY micro-step (no `no_sync()` under accum_iter, `engine.py:37-41`). Here the reduce can be
+skipped on non-boundary micro-steps (`DataParallel.require_backward_grad_sync = False`, the attribute torch's DDP `no_sync()`
+toggles; `engine.train_one_epoch` sets it from `update_grad`): the local gradient of a skipped micro-step is remembered, and
+the boundary micro-step reduces (remembered + own) and returns mean(remembered + own) - remembered, so that `.grad`
+(= remembered + returned, accumulated by autograd) ends up as the rank mean of the accumulated gradient - the same value as
+averaging every micro-step (mean is linear), with 1/accum_iter of the messages.
 """
 from __future__ import annotations
 
@@ -28,6 +32,9 @@ class GradSync:
         self.chunk = max(1, chunk_layers)
         self.works: List = []
         self.messages = 0
+        self.enabled = True            # False: this micro-step's gradients stay local (accumulation, see module docstring)
+        self.acc = None                # sum of the local flat gradients of the skipped micro-steps since the last reduce
+        self.timing = None             # list -> (event before, event after) the stream-level wait on NCCL in finish() per step
 
     def _reduce(self, t: torch.Tensor):
         self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
@@ -53,21 +60,42 @@ class GradSync:
 
     def layer_done(self, l: int):
         """Called by the backward pass right after layer l's adapter gradient rows were written."""
-        if self.world == 1:
+        if self.world == 1 or not self.enabled:
             return
         if l % self.chunk == 0:                                   # layers [l, min(l+chunk, L)) are final
             hi = min(l + self.chunk, self.L)
-            self._reduce(self.gb.flat[l * self.A * self.d: hi * self.A * self.d])
+            lo_, hi_ = l * self.A * self.d, hi * self.A * self.d
+            if self.acc is not None:
+                self.gb.flat[lo_:hi_].add_(self.acc[lo_:hi_])
+            self._reduce(self.gb.flat[lo_:hi_])
 
     def finish(self):
         """Late message (gates, visual_proj, temporal_emb), wait for everything, turn the sum into a mean."""
         if self.world == 1:
             return
-        self._reduce(self.gb.flat[self.gb.late_offset:])
+        if not self.enabled:                                      # accumulate locally, no message
+            if self.acc is None:
+                self.acc = self.gb.flat.clone()
+            else:
+                self.acc.add_(self.gb.flat)
+            return
+        late = self.gb.late_offset
+        if self.acc is not None:
+            self.gb.flat[late:].add_(self.acc[late:])
+        self._reduce(self.gb.flat[late:])
+        if self.timing is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         for w in self.works:
             w.wait()                                              # stream-level wait for NCCL, not a host sync
+        if self.timing is not None:
+            e1.record()
+            self.timing.append((e0, e1))
         self.works = []
         self.gb.flat.mul_(1.0 / self.world)
+        if self.acc is not None:                                  # .grad already holds the skipped micro-steps' local gradients
+            self.gb.flat.sub_(self.acc)
+            self.acc = None
 
 
 class DataParallel(torch.nn.Module):
@@ -79,6 +107,7 @@ class DataParallel(torch.nn.Module):
         self.module = module
         self.group = group
         self.chunk_layers = chunk_layers
+        self.require_backward_grad_sync = True                  # same attribute as torch DDP (`no_sync()` clears it)
         if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
             for p in module.parameters():
                 if p.requires_grad:
@@ -92,6 +121,20 @@ class DataParallel(torch.nn.Module):
             m._engine.adapter_grad_chunk = self.chunk_layers    # adapter gradient rows become final in the chunks GradSync reduces
             if m._grad_buffers.flat.is_cuda:
                 m.grad_sync.warm_up()
+        m.grad_sync.enabled = bool(self.require_backward_grad_sync)
+
+    def no_sync(self):
+        """Context manager with torch DDP's semantics: backward passes inside it keep their gradients local."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self.require_backward_grad_sync = self.require_backward_grad_sync, False
+            try:
+                yield
+            finally:
+                self.require_backward_grad_sync = prev
+        return ctx()
 
     def forward(self, data, inference: bool = False):
         self._attach()

@@ -30,13 +30,15 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: to
     for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         if data_iter_step % accum_iter == 0:
             lr_sched.adjust_learning_rate(optimizer, data_iter_step / len(data_loader) + epoch, args)
+        update = (data_iter_step + 1) % accum_iter == 0
+        if hasattr(model, "require_backward_grad_sync"):      # dp.DataParallel: all-reduce only on the accumulation boundary
+            model.require_backward_grad_sync = update
         if isinstance(data, tuple):                  # dataloader.PlannedLoader: (batch dict, device-resident plan)
             data, plan = data
             vqa_loss, vaq_loss, qav_loss = model.forward_plan(plan)
         else:
             vqa_loss, vaq_loss, qav_loss = model(data)
         loss = vqa_loss + vaq_loss + qav_loss
-        update = (data_iter_step + 1) % accum_iter == 0
         # one D2H read for all four logged values (also the step's only host sync), BEFORE backward / the optimizer step as in
         # `engine.py:28-35`: a non-finite loss must never reach the trainables or the AdamW state
         vals = torch.stack([loss.detach().float().reshape(()), vqa_loss.detach().float().reshape(()),

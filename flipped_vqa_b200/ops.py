@@ -22,13 +22,15 @@ class GemmTimer:
 
     def __init__(self):
         self.active = False
-        self.records = []          # (start_event, end_event, flops)
+        self.tag = None            # set by the caller (step.py: the layer index) and stored with every record
+        self.records = []          # (start_event, end_event, flops, tag)
 
-    def summary(self):
-        if not self.records:
+    def summary(self, tags=None):
+        recs = [r for r in self.records if tags is None or r[3] in tags]
+        if not recs:
             return None
-        ms = [a.elapsed_time(b) for a, b, _ in self.records]
-        fl = [f for _, _, f in self.records]
+        ms = [a.elapsed_time(b) for a, b, _, _ in recs]
+        fl = [f for _, _, f, _ in recs]
         return dict(launches=len(ms), total_ms=sum(ms), total_flops=sum(fl), avg_ms=sum(ms) / len(ms),
                     avg_flops=sum(fl) / len(fl), tflops=sum(fl) / (sum(ms) * 1e-3) / 1e12)
 
@@ -178,7 +180,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
                                        M, N, K, 1 if out_fp32 else 0, stream()), "gemm_h16_nt")
     if tm is not None and tm.active:
         e1.record()
-        tm.records.append((e0, e1, 2.0 * M * N * K))
+        tm.records.append((e0, e1, 2.0 * M * N * K, tm.tag))
     return out
 
 
@@ -205,7 +207,7 @@ def gemm_nt_rope(a: torch.Tensor, b: torch.Tensor, cos, sin, rope_cols: int, hd:
                                                 ptr(cos), ptr(sin), rope_cols, hd, S, stream()), "gemm_h16_nt_rope")
     if tm is not None and tm.active:
         e1.record()
-        tm.records.append((e0, e1, 2.0 * M * N * K))
+        tm.records.append((e0, e1, 2.0 * M * N * K, tm.tag))
     return out
 
 
@@ -229,7 +231,7 @@ def gemm_swiglu_fwd(x: torch.Tensor, w13: torch.Tensor, g: Optional[torch.Tensor
                                           M, hid, K, stream()), "gemm_swiglu_fwd")
     if tm is not None and tm.active:
         e1.record()
-        tm.records.append((e0, e1, 2.0 * M * 2 * hid * K))
+        tm.records.append((e0, e1, 2.0 * M * 2 * hid * K, tm.tag))
     return g, c
 
 
@@ -250,7 +252,7 @@ def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Op
                                           M, hid, K, stream()), "gemm_swiglu_bwd")
     if tm is not None and tm.active:
         e1.record()
-        tm.records.append((e0, e1, 2.0 * M * hid * K))
+        tm.records.append((e0, e1, 2.0 * M * hid * K, tm.tag))
     return dg
 
 

@@ -411,7 +411,7 @@ class StepEngine:
         ce_idx, q_idx = (ce_live, q_live) if prune else (ce_full, q_full)
         for l, w in enumerate(layers):
             if ops.GEMM_TIMER is not None:
-                ops.GEMM_TIMER.active = l in self.sample_layers
+                ops.GEMM_TIMER.active, ops.GEMM_TIMER.tag = l in self.sample_layers, l
             _, rstd1 = ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
             # Wq|Wk|Wv in one GEMM, RoPE applied to q|k in its epilogue (`model.py:89,96`)
             if compact:
@@ -612,7 +612,7 @@ class StepEngine:
         for l in range(L - 1, -1, -1):
             w = layers[l]
             if ops.GEMM_TIMER is not None:
-                ops.GEMM_TIMER.active = l in self.sample_layers
+                ops.GEMM_TIMER.active, ops.GEMM_TIMER.tag = l in self.sample_layers, l
             if pruned and l == L - 1:
                 # compact rows through the FFN and wo of the last layer, then scatter d(attn out) and dh back to all rows
                 dg_c = ops.gemm_swiglu_bwd(dx_h, w.w2_t, sv.g[l])

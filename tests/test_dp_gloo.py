@@ -26,6 +26,57 @@ def _rank_grads(rank):
     return gb, torch.randn(gb.flat.numel(), generator=g)
 
 
+def _fill(gb, sync, vals):
+    """One backward pass as the hand-written step drives GradSync; returns what autograd would add to `.grad`."""
+    row = A * D
+    for l in range(L - 1, -1, -1):                           # backward order
+        gb.flat[l * row:(l + 1) * row] = vals[l * row:(l + 1) * row]
+        sync.layer_done(l)
+    gb.flat[gb.late_offset:] = vals[gb.late_offset:]          # gates, visual_proj, temporal_emb: final at the end
+    sync.finish()
+    return gb.flat.clone()
+
+
+def _accum_worker(rank, world, port, chunk, q):
+    """accum_iter = 3: two micro-steps with require_backward_grad_sync False, then the boundary micro-step."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from flipped_vqa_b200.dp import GradSync
+        gb, _ = _rank_grads(rank)
+        sync = GradSync(gb, L, A, D, chunk_layers=chunk)
+        grad = torch.zeros_like(gb.flat)                      # the parameters' .grad, accumulated by autograd
+        for micro in range(3):
+            g = torch.Generator().manual_seed(1000 * micro + rank)
+            sync.enabled = micro == 2
+            grad += _fill(gb, sync, torch.randn(gb.flat.numel(), generator=g))
+        q.put((rank, grad, sync.messages))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("chunk", [2, 8])
+def test_grad_sync_skips_non_boundary_micro_steps(chunk):
+    """with accum_iter > 1 only the boundary micro-step talks; .grad ends as the rank mean of the accumulated
+    gradient - what the reference's every-micro-step DDP reduce (`engine.py:37-41`) produces, with 1/accum_iter of the messages."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_accum_worker, args=(r, world, port, chunk, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n = got[0][1].numel()
+    expect = sum(torch.randn(n, generator=torch.Generator().manual_seed(1000 * m + r)) for m in range(3) for r in range(world)) / world
+    for rank, grad, messages in got:
+        assert torch.allclose(grad, expect, atol=1e-5), f"rank {rank}"
+        assert messages == -(-L // chunk) + 1                 # ONE round of messages for three micro-steps
+
+
 def _worker(rank, world, port, chunk, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
