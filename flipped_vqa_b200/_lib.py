@@ -65,6 +65,7 @@ _SIGNATURES = {
     "fvqa_build_h0_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fvqa_build_h0_bwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fvqa_video_grad_finish": [_p, _p, _p, _i, _i, _i, _p],
+    "fvqa_video_grad": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fvqa_ce_fwd": [_p, _i, _p, _p, _p, _i, _i, _p],
     "fvqa_ce_bwd": [_p, _i, _p, _p, _p, _f, _p, _i, _i, _i, _p],
     "fvqa_sum_scale": [_p, _i, _f, _p, _p],

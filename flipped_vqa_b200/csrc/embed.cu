@@ -5,44 +5,62 @@
 
 namespace fvqa {
 
-constexpr int VP_COLS = 8;      // output columns per CTA
 constexpr int VP_THREADS = 256;
+constexpr int LIN_COLS = 32;     // output columns per CTA (one per lane)
+constexpr int LIN_KC = 64;       // k-chunk staged in shared memory
+constexpr int LIN_ROWS = 128;    // rows per pass: warp w owns rows w, w + 8, ... (16 per warp)
 
-// vf32[r, c] = sum_k video[r, k] * wv[c, k] (+ bias[c]) (+ add[r, c])     fp32 Linear: model.py:322 (visual_proj, no bias);
-// also the frozen audio projections / cross-attention q,k,v of the audio-fusion variants (model.py:307-320, :148-163)
-__global__ void __launch_bounds__(VP_THREADS) visual_proj_fwd_kernel(const float* __restrict__ video,
-                                                                     const float* __restrict__ wv,
-                                                                     const float* __restrict__ bias, const float* __restrict__ add,
-                                                                     float* __restrict__ vf, int rows, int dim, int vdim) {
-  extern __shared__ float ws[];  // [VP_COLS][vdim]
-  const int c0 = blockIdx.x * VP_COLS;
-  for (int i = threadIdx.x; i < VP_COLS * vdim; i += VP_THREADS) {
-    const int j = i / vdim, k = i - j * vdim;
-    ws[i] = (c0 + j < dim) ? wv[static_cast<long>(c0 + j) * vdim + k] : 0.f;
-  }
-  __syncthreads();
+// y[r, c] = sum_k x[r, k] * w[c, k] (+ bias[c]) (+ add[r, c])     fp32 Linear: model.py:322 (visual_proj, no bias); also the frozen
+// audio projections / cross-attention q,k,v of the audio-fusion variants (model.py:307-320, :148-163).
+// CTA = 32 output columns x up to 128 rows; the k dimension goes through shared memory in chunks of 64: w tile transposed to
+// [k][c] (lane = column: conflict-free), x tile [row][k] read as float4 broadcasts; each lane keeps 16 row accumulators.
+// grid = (dim / 32, row passes): 128 CTAs at d = 4096 (was: 512 CTAs whose warps each reduced 8 columns per row with shuffles).
+__global__ void __launch_bounds__(VP_THREADS) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ bias, const float* __restrict__ add,
+                                                                float* __restrict__ y, int rows, int dim, int in_dim) {
+  __shared__ float wt[LIN_KC][LIN_COLS + 1];
+  __shared__ __align__(16) float xs[LIN_ROWS][LIN_KC];
+  const int c0 = blockIdx.x * LIN_COLS, r0 = blockIdx.y * LIN_ROWS;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < rows; r += VP_THREADS / 32) {
-    float acc[VP_COLS];
+  const int nrows = min(LIN_ROWS, rows - r0);
+  float acc[LIN_ROWS / 8];
 #pragma unroll
-    for (int j = 0; j < VP_COLS; ++j) acc[j] = 0.f;
-    const float* vrow = video + static_cast<long>(r) * vdim;
-    for (int k = lane; k < vdim; k += 32) {
-      const float v = __ldg(vrow + k);
-#pragma unroll
-      for (int j = 0; j < VP_COLS; ++j) acc[j] += v * ws[j * vdim + k];
+  for (int i = 0; i < LIN_ROWS / 8; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < in_dim; k0 += LIN_KC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < LIN_COLS * LIN_KC; i += VP_THREADS) {        // coalesced along k, transposed store (stride 33)
+      const int c = i / LIN_KC, k = i - c * LIN_KC;
+      wt[k][c] = (c0 + c < dim && k0 + k < in_dim) ? __ldg(w + static_cast<long>(c0 + c) * in_dim + k0 + k) : 0.f;
     }
+    for (int i = threadIdx.x; i < nrows * LIN_KC; i += VP_THREADS) {
+      const int r = i / LIN_KC, k = i - r * LIN_KC;
+      xs[r][k] = (k0 + k < in_dim) ? __ldg(x + static_cast<long>(r0 + r) * in_dim + k0 + k) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < LIN_KC; k += 4) {
+      const float w0 = wt[k][lane], w1 = wt[k + 1][lane], w2 = wt[k + 2][lane], w3 = wt[k + 3][lane];
 #pragma unroll
-    for (int j = 0; j < VP_COLS; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < VP_COLS; ++j)
-        if (c0 + j < dim) {
-          float o = acc[j];
-          if (bias != nullptr) o += bias[c0 + j];
-          if (add != nullptr) o += add[static_cast<long>(r) * dim + c0 + j];
-          vf[static_cast<long>(r) * dim + c0 + j] = o;
+      for (int i = 0; i < LIN_ROWS / 8; ++i) {
+        const int r = warp + 8 * i;
+        if (r < nrows) {                                                         // warp-uniform
+          const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k]);
+          acc[i] += xv.x * w0 + xv.y * w1 + xv.z * w2 + xv.w * w3;
         }
+      }
+    }
+  }
+  const int c = c0 + lane;
+  if (c < dim) {
+    const float bv = bias != nullptr ? bias[c] : 0.f;
+#pragma unroll
+    for (int i = 0; i < LIN_ROWS / 8; ++i) {
+      const int r = warp + 8 * i;
+      if (r < nrows) {
+        float o = acc[i] + bv;
+        if (add != nullptr) o += add[static_cast<long>(r0 + r) * dim + c];
+        y[static_cast<long>(r0 + r) * dim + c] = o;
+      }
     }
   }
 }
@@ -80,24 +98,44 @@ __global__ void __launch_bounds__(256) cross_attn_fwd_kernel(const float* __rest
   }
 }
 
-// dwv[c, k] = sum_r dvf[r, c] * video[r, k]
+// dwv[c, k] = sum_r dvf[r, c] * video[r, k]   (fp32 outer-product accumulation, fixed row order -> deterministic)
+// CTA = 32 c x 64 k output tile; rows go through shared memory in chunks of 64; thread = one k and 8 consecutive c
+// (x tile: conflict-free, d tile: float4 broadcasts). grid = (dim / 32, vdim / 64): 1536 CTAs at 4096 x 768 (was: 512 CTAs whose
+// threads walked all rows with 9 global loads per 8 FMAs, 122 us).
+constexpr int VPB_C = 32, VPB_K = 64, VPB_R = 64;
 __global__ void __launch_bounds__(VP_THREADS) visual_proj_bwd_kernel(const float* __restrict__ dvf,
                                                                      const float* __restrict__ video,
                                                                      float* __restrict__ dwv, int rows, int dim, int vdim) {
-  const int c0 = blockIdx.x * VP_COLS;
-  for (int k = threadIdx.x; k < vdim; k += VP_THREADS) {
-    float acc[VP_COLS];
+  __shared__ __align__(16) float ds[VPB_R][VPB_C];
+  __shared__ float vs[VPB_R][VPB_K];
+  const int c0 = blockIdx.x * VPB_C, k0 = blockIdx.y * VPB_K;
+  const int kk = threadIdx.x & (VPB_K - 1), cg = (threadIdx.x >> 6) * 8;        // 4 groups of 8 columns
+  float acc[8];
 #pragma unroll
-    for (int j = 0; j < VP_COLS; ++j) acc[j] = 0.f;
-    for (int r = 0; r < rows; ++r) {
-      const float v = __ldg(video + static_cast<long>(r) * vdim + k);
-#pragma unroll
-      for (int j = 0; j < VP_COLS; ++j)
-        if (c0 + j < dim) acc[j] += __ldg(dvf + static_cast<long>(r) * dim + c0 + j) * v;
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int r0 = 0; r0 < rows; r0 += VPB_R) {
+    const int n = min(VPB_R, rows - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n * VPB_C; i += VP_THREADS) {
+      const int r = i / VPB_C, c = i - r * VPB_C;
+      ds[r][c] = (c0 + c < dim) ? __ldg(dvf + static_cast<long>(r0 + r) * dim + c0 + c) : 0.f;
     }
+    for (int i = threadIdx.x; i < n * VPB_K; i += VP_THREADS) {
+      const int r = i / VPB_K, k = i - r * VPB_K;
+      vs[r][k] = (k0 + k < vdim) ? __ldg(video + static_cast<long>(r0 + r) * vdim + k0 + k) : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < n; ++r) {
+      const float v = vs[r][kk];
+      const float4 d0 = *reinterpret_cast<const float4*>(&ds[r][cg]), d1 = *reinterpret_cast<const float4*>(&ds[r][cg + 4]);
+      acc[0] += d0.x * v; acc[1] += d0.y * v; acc[2] += d0.z * v; acc[3] += d0.w * v;
+      acc[4] += d1.x * v; acc[5] += d1.y * v; acc[6] += d1.z * v; acc[7] += d1.w * v;
+    }
+  }
+  if (k0 + kk < vdim) {
 #pragma unroll
-    for (int j = 0; j < VP_COLS; ++j)
-      if (c0 + j < dim) dwv[static_cast<long>(c0 + j) * vdim + k] = acc[j];
+    for (int j = 0; j < 8; ++j)
+      if (c0 + cg + j < dim) dwv[static_cast<long>(c0 + cg + j) * vdim + k0 + kk] = acc[j];
   }
 }
 
@@ -194,23 +232,51 @@ __global__ void __launch_bounds__(256) video_grad_finish_kernel(float* __restric
   }
 }
 
+// build_h0_bwd + video_grad_finish in ONE full-grid launch: for frame f and a 256-column slab, walk the video samples b:
+//   g = sum over the sequences of sample b of dh0 at frame f's slot;  dtemporal[f] += g;  dvf[b, f] = g + dvf_qav[b, f].
+// grid (F, dim / 256) = 160 CTAs at d = 4096 (the two separate kernels ran on 80 and 10 CTAs: 56 + 61 us).
+__global__ void __launch_bounds__(256) video_grad_kernel(const float* __restrict__ dh0, const int32_t* __restrict__ vstart,
+                                                         const int32_t* __restrict__ seq_video, const int32_t* __restrict__ qav_index,
+                                                         const float* __restrict__ dvf_qav, float* __restrict__ dvf,
+                                                         float* __restrict__ dtemporal, int n_seq, int n_video, int S, int dim, int F) {
+  const int f = blockIdx.x, c = blockIdx.y * 256 + threadIdx.x;
+  if (c >= dim) return;
+  float tsum = 0.f;
+  for (int b = 0; b < n_video; ++b) {
+    float g = 0.f;
+    for (int n = 0; n < n_seq; ++n) {
+      if (seq_video[n] != b) continue;
+      const int vs = vstart[n];
+      const int pos = vs >= 0 ? vs + f : qav_index[b * F + f];
+      if (pos < 0 || pos >= S) continue;
+      g += __ldg(dh0 + (static_cast<long>(n) * S + pos) * dim + c);
+    }
+    tsum += g;
+    const long o = (static_cast<long>(b) * F + f) * dim + c;
+    dvf[o] = dvf_qav != nullptr ? g + dvf_qav[o] : g;
+  }
+  dtemporal[static_cast<long>(f) * dim + c] = tsum;
+}
+
 }  // namespace fvqa
 
 using namespace fvqa;
 
+extern "C" int fvqa_video_grad(const float* dh0, const int32_t* vstart, const int32_t* seq_video, const int32_t* qav_index,
+                               const float* dvf_qav, float* dvf, float* dtemporal, int n_seq, int n_video, int S, int dim, int max_feats,
+                               void* stream) {
+  if (max_feats <= 0 || dim <= 0) return FVQA_OK;
+  video_grad_kernel<<<dim3(max_feats, (dim + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dh0, vstart, seq_video, qav_index, dvf_qav, dvf, dtemporal, n_seq, n_video, S, dim, max_feats);
+  return check_launch("video_grad");
+}
+
 extern "C" int fvqa_linear_f32(const float* x, const float* w, const float* bias, const float* add, float* y, int rows, int dim,
                                int in_dim, void* stream) {
   if (rows <= 0) return FVQA_OK;
-  const size_t smem = static_cast<size_t>(VP_COLS) * in_dim * sizeof(float);
-  FVQA_REQUIRE(smem <= 96 * 1024, FVQA_ERR_UNSUPPORTED, "linear_f32: in_dim %d too large", in_dim);
-  static bool big_smem_enabled = false;       // 768 + 1024 concatenated features need 56 KB (> the 48 KB default)
-  if (smem > 48 * 1024 && !big_smem_enabled) {
-    const cudaError_t e = cudaFuncSetAttribute(visual_proj_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(visual_proj_fwd): %s", cudaGetErrorString(e));
-    big_smem_enabled = true;
-  }
-  visual_proj_fwd_kernel<<<(dim + VP_COLS - 1) / VP_COLS, VP_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(x, w, bias, add, y, rows,
-                                                                                                                dim, in_dim);
+  FVQA_REQUIRE(dim > 0 && in_dim > 0, FVQA_ERR_INVALID_ARG, "linear_f32: dim %d in_dim %d", dim, in_dim);
+  const dim3 grid((dim + LIN_COLS - 1) / LIN_COLS, (rows + LIN_ROWS - 1) / LIN_ROWS);
+  linear_f32_kernel<<<grid, VP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, add, y, rows, dim, in_dim);
   return check_launch("linear_f32");
 }
 
@@ -228,7 +294,9 @@ extern "C" int fvqa_cross_attn_fwd(const float* q, const float* k, const float* 
 }
 
 extern "C" int fvqa_visual_proj_bwd(const float* dvf, const float* video, float* dwv, int rows, int dim, int vdim, void* stream) {
-  visual_proj_bwd_kernel<<<(dim + VP_COLS - 1) / VP_COLS, VP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(dvf, video, dwv, rows, dim, vdim);
+  if (dim <= 0 || vdim <= 0) return FVQA_OK;
+  const dim3 grid((dim + VPB_C - 1) / VPB_C, (vdim + VPB_K - 1) / VPB_K);
+  visual_proj_bwd_kernel<<<grid, VP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(dvf, video, dwv, rows, dim, vdim);
   return check_launch("visual_proj_bwd");
 }
 

@@ -121,25 +121,50 @@ class PlannedLoader:
     def __iter__(self):
         q: "queue.Queue" = queue.Queue(maxsize=self.depth)
         stop = object()
+        cancel = threading.Event()
+        # weight packing (Transformer.repack) belongs to the consumer's thread: never let the worker trigger it concurrently
+        if hasattr(self.model, "_ensure_packed") and torch.cuda.is_available():
+            self.model._ensure_packed()
+
+        def put(item) -> bool:
+            """Blocking put that gives up when the consumer has gone away (early break, exception, sys.exit in the loop)."""
+            while not cancel.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def work():
             try:
                 for data in self.loader:
-                    q.put((data,) + self._plan(data))
+                    if cancel.is_set() or not put((data,) + self._plan(data)):
+                        return
             except BaseException as e:            # surface loader / planning errors in the consumer
-                q.put(e)
-            q.put(stop)
+                put(e)
+            put(stop)
 
-        threading.Thread(target=work, daemon=True).start()
-        while True:
-            item = q.get()
-            if item is stop:
-                return
-            if isinstance(item, BaseException):
-                raise item
-            data, plan, ev = item
-            if ev is not None:
-                cur = torch.cuda.current_stream()
-                cur.wait_event(ev)
-                plan.record_stream(cur)
-            yield data, plan
+        worker = threading.Thread(target=work, daemon=True)
+        worker.start()
+        try:
+            while True:
+                item = q.get()
+                if item is stop:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                data, plan, ev = item
+                if ev is not None:
+                    cur = torch.cuda.current_stream()
+                    cur.wait_event(ev)
+                    plan.record_stream(cur)
+                yield data, plan
+        finally:                                  # also runs when the consumer abandons the generator (GeneratorExit)
+            cancel.set()
+            while True:                           # release the pinned slots / device plans the worker had queued
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    break
+            worker.join(timeout=5.0)

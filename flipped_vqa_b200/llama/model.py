@@ -244,6 +244,9 @@ class Transformer(nn.Module):
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._pack_token = None                             # .to()/.cuda()/.half() replace parameter storage
+        dev = self.tok_embeddings.weight.device             # a model built on the CPU and moved with .cuda() runs on that device
+        if dev.type == "cuda":
+            self._device = dev
         return out
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
@@ -337,6 +340,10 @@ class Transformer(nn.Module):
         if mode == "concat":                                # `visual_proj(cat([video, audio]))`, `:310-311`
             d2["video"] = torch.cat([data["video"].float(), audio], dim=-1)
             return d2, (lambda plan: plan)
+        if mode == "sum" and Fa != F:                       # `:314` adds [B, Fa, d] to [B, F, d]: torch broadcasting needs Fa in {1, F}
+            if Fa != 1:
+                raise ValueError(f"audio_merge='sum': audio has {Fa} frames per sample, video features have {F} (need {F} or 1)")
+            audio, Fa = audio.expand(B, F, audio.shape[-1]), F
         audio_dev = audio.reshape(B * Fa, AUDIO_DIM).to(dev, non_blocking=True)
         if mode == "sum":                                   # `audio_proj(audio) + visual_proj(video)`, `:314`
 

@@ -336,6 +336,17 @@ def video_grad_finish(dvf, dvf_qav, n_video, F, dtemporal=None):
 
 # ------------------------------------------------------------------ heads
 @_timed
+def video_grad(dh0, vstart, seq_video, qav_index, dvf_qav, n_seq, n_video, S, F, dvf=None, dtemporal=None):
+    """build_h0_bwd + video_grad_finish in one launch: returns (dvf [n_video*F, d] incl. the QAV term, dtemporal [F, d])."""
+    dim = dh0.shape[-1]
+    dvf = torch.empty(n_video * F, dim, dtype=F32, device=dh0.device) if dvf is None else dvf
+    dtemporal = torch.empty(F, dim, dtype=F32, device=dh0.device) if dtemporal is None else dtemporal
+    check(_lib.lib().fvqa_video_grad(ptr(dh0), ptr(vstart), ptr(seq_video), ptr(qav_index), ptr(dvf_qav), ptr(dvf), ptr(dtemporal),
+                                     n_seq, n_video, S, dim, F, stream()), "video_grad")
+    return dvf, dtemporal
+
+
+@_timed
 def ce_fwd(logits, target, row_loss=None, row_lse=None):
     _chk(target, torch.int32, "target")
     assert logits.dtype == torch.float32 and logits.stride(-1) == 1

@@ -134,6 +134,9 @@ class BatchPlan:
         """The plan was copied on another stream (dataloader.PlannedLoader): tell the allocator who uses it."""
         self._dev.record_stream(stream)
         self.video.record_stream(stream)
+        extra = getattr(self, "vf_extra", None)           # audio 'sum' / 'attention': computed on the copy stream by Transformer._fuse_inputs
+        if extra is not None:
+            extra.record_stream(stream)
 
 
 class OptionPlan:
@@ -239,6 +242,9 @@ class OptionPlan:
     def record_stream(self, stream):
         self._dev.record_stream(stream)
         self.video.record_stream(stream)
+        extra = getattr(self, "vf_extra", None)
+        if extra is not None:
+            extra.record_stream(stream)
 
 
 class PinnedPool:
@@ -659,8 +665,7 @@ class StepEngine:
         # --- input side (`model.py:322-336` backward)
         if compact:
             dx = ops.expand_rows(dx, plan.f2c)                                     # [T, d] fp32, zero at the skipped rows
-        dvf = ops.build_h0_bwd(dx, plan.vstart, plan.seq_video, plan.qav_index, n_seq, plan.n_video, S, F)
-        ops.video_grad_finish(dvf, dvf_qav, plan.n_video, F, dtemporal=grads.temporal)
+        dvf, _ = ops.video_grad(dx, plan.vstart, plan.seq_video, plan.qav_index, dvf_qav, n_seq, plan.n_video, S, F, dtemporal=grads.temporal)
         if grads.sizes["visual"]:                              # audio only: the projection is frozen (`model.py:209-210`)
             ops.visual_proj_bwd(dvf, plan.video, dwv=grads.visual)
         unscale(grads.flat[grads.late_offset:])                # gates | visual_proj | temporal_emb: one contiguous tail

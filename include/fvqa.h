@@ -165,6 +165,12 @@ int fvqa_build_h0_bwd(const float* dh0, const int32_t* vstart, const int32_t* se
 int fvqa_video_grad_finish(float* dvf, const float* dvf_qav, float* dtemporal, int n_video, int dim,
                            int max_feats, void* stream);
 
+/* The two calls above in one full-grid launch: dvf[b, f] = (sum over the sequences of sample b of dh0 at frame f's slot) + dvf_qav[b, f]
+ * (dvf_qav may be NULL), dtemporal[f] = sum_b of the first term. Both outputs overwritten. */
+int fvqa_video_grad(const float* dh0, const int32_t* vstart, const int32_t* seq_video, const int32_t* qav_index,
+                    const float* dvf_qav, float* dvf, float* dtemporal, int n_seq, int n_video, int S, int dim,
+                    int max_feats, void* stream);
+
 /* ---- vocabulary cross-entropy over labelled rows (llama/model.py:348-356, ignore_index=0). -------
  * logits [rows, V] fp32 (row stride ld), target[rows] int32 (<0 = padding row).
  * row_loss[rows] = lse - logit[target] (0 for padding rows); row_lse saved for backward. */

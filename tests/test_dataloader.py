@@ -83,3 +83,40 @@ def test_planned_loader_feeds_plans_in_order():
         raise RuntimeError("loader failed")
     with pytest.raises(RuntimeError, match="loader failed"):
         list(D.PlannedLoader(boom(), model))
+
+
+def test_planned_loader_worker_stops_when_the_consumer_leaves():
+    """An abandoned iteration (`args.debug` break in `engine.py:52/81`, an exception, the non-finite-loss exit) must not leave a
+    worker thread blocked on a full queue holding pinned slots and device plans."""
+    import threading
+    import time
+    from flipped_vqa_b200.dataloader import PlannedLoader
+
+    class _Model:
+        _device = "cpu"
+
+        def plan_batch(self, d):
+            return ("plan", d)
+
+        def plan_options(self, d):
+            return ("options", d)
+
+    before = threading.active_count()
+    for i, (d, p) in enumerate(PlannedLoader(list(range(100)), _Model(), depth=2)):
+        assert p == ("plan", d)
+        if i == 3:
+            break
+    deadline = time.time() + 5
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() == before
+    assert [d for d, _ in PlannedLoader([1, 2, 3], _Model(), inference=True)] == [1, 2, 3]
+
+    class _Boom(list):
+        def __iter__(self):
+            yield 1
+            raise RuntimeError("loader failed")
+
+    import pytest
+    with pytest.raises(RuntimeError, match="loader failed"):
+        list(PlannedLoader(_Boom(), _Model()))

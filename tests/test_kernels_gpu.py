@@ -388,6 +388,32 @@ def test_visual_proj_and_h0(fvqa_lib):
     dtemp = ops.video_grad_finish(dvf, dq, B, F)
     assert relerr(dtemp, dvf_copy.view(B, F, d).sum(0)) < 1e-6
     assert relerr(dvf, dvf_copy + dq) < 1e-6
+    # the fused full-grid kernel the step uses = the two calls above
+    dvf2, dtemp2 = ops.video_grad(dh0, vstart, seq_video, qav_index, dq, n_seq, B, S, F)
+    assert torch.equal(dvf2, dvf) and torch.equal(dtemp2, dtemp)
+    dvf3, dtemp3 = ops.video_grad(dh0, vstart, seq_video, qav_index, None, n_seq, B, S, F)
+    assert torch.equal(dvf3, dvf_copy) and torch.equal(dtemp3, dtemp)
+
+
+@pytest.mark.parametrize("rows,dim,in_dim,bias,add", [(80, 4096, 768, False, False), (30, 256, 1792, True, True), (300, 520, 100, True, False),
+                                                      (1, 32, 1, False, True)])
+def test_linear_f32_shapes(fvqa_lib, rows, dim, in_dim, bias, add):
+    """fp32 Linear (visual_proj `model.py:322`, the audio-fusion projections `:307-320`, CrossAttentionModule q/k/v `:148-163`) and its
+    weight gradient on ragged shapes: row passes > 1, k tails, column tails, bias / additive term."""
+    from flipped_vqa_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + dim)
+    x = torch.randn(rows, in_dim, device="cuda", generator=g)
+    w = torch.randn(dim, in_dim, device="cuda", generator=g) / math.sqrt(in_dim)
+    b = torch.randn(dim, device="cuda", generator=g) if bias else None
+    a = torch.randn(rows, dim, device="cuda", generator=g) if add else None
+    buf = torch.full((rows + 2, dim), 7.0, device="cuda")
+    y = ops.linear_f32(x, w, bias=b, add=a, out=buf[1:rows + 1])
+    ref = x.double() @ w.double().t() + (b.double() if bias else 0) + (a.double() if add else 0)
+    assert relerr(y, ref.float()) < 1e-5
+    assert float((buf[0] - 7).abs().max()) == 0 and float((buf[-1] - 7).abs().max()) == 0
+    dy = torch.randn(rows, dim, device="cuda", generator=g)
+    dw = ops.visual_proj_bwd(dy, x)
+    assert relerr(dw, (dy.double().t() @ x.double()).float()) < 1e-5
 
 
 def test_ce_fwd_bwd(fvqa_lib):
