@@ -15,6 +15,7 @@ constexpr int LIN_ROWS = 128;    // rows per pass: warp w owns rows w, w + 8, ..
 // CTA = 32 output columns x up to 128 rows; the k dimension goes through shared memory in chunks of 64: w tile transposed to
 // [k][c] (lane = column: conflict-free), x tile [row][k] read as float4 broadcasts; each lane keeps 16 row accumulators.
 // grid = (dim / 32, row passes): 128 CTAs at d = 4096 (was: 512 CTAs whose warps each reduced 8 columns per row with shuffles).
+template <bool VEC>
 __global__ void __launch_bounds__(VP_THREADS) linear_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                 const float* __restrict__ bias, const float* __restrict__ add,
                                                                 float* __restrict__ y, int rows, int dim, int in_dim) {
@@ -26,17 +27,54 @@ __global__ void __launch_bounds__(VP_THREADS) linear_f32_kernel(const float* __r
   float acc[LIN_ROWS / 8];
 #pragma unroll
   for (int i = 0; i < LIN_ROWS / 8; ++i) acc[i] = 0.f;
+  // VEC (in_dim % 4 == 0, 16-byte aligned rows): the next chunk's global loads (2 + 8 float4 per thread) are in flight in
+  // registers while the current chunk is multiplied - with one CTA per SM nothing else hides the DRAM latency
+  constexpr int WV = LIN_COLS * LIN_KC / 4 / VP_THREADS, XV = LIN_ROWS * LIN_KC / 4 / VP_THREADS;
+  float4 wreg[WV], xreg[XV];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < WV; ++j) {
+      const int idx = threadIdx.x + j * VP_THREADS, c = idx / (LIN_KC / 4), k4 = idx % (LIN_KC / 4);
+      wreg[j] = (c0 + c < dim && k0 + 4 * k4 < in_dim) ? __ldg(reinterpret_cast<const float4*>(w + static_cast<long>(c0 + c) * in_dim + k0) + k4)
+                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < XV; ++j) {
+      const int idx = threadIdx.x + j * VP_THREADS, r = idx / (LIN_KC / 4), k4 = idx % (LIN_KC / 4);
+      xreg[j] = (r < nrows && k0 + 4 * k4 < in_dim) ? __ldg(reinterpret_cast<const float4*>(x + static_cast<long>(r0 + r) * in_dim + k0) + k4)
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto sstore = [&]() {
+#pragma unroll
+    for (int j = 0; j < WV; ++j) {
+      const int idx = threadIdx.x + j * VP_THREADS, c = idx / (LIN_KC / 4), k4 = idx % (LIN_KC / 4);
+      wt[4 * k4][c] = wreg[j].x; wt[4 * k4 + 1][c] = wreg[j].y; wt[4 * k4 + 2][c] = wreg[j].z; wt[4 * k4 + 3][c] = wreg[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < XV; ++j) {
+      const int idx = threadIdx.x + j * VP_THREADS, r = idx / (LIN_KC / 4), k4 = idx % (LIN_KC / 4);
+      *reinterpret_cast<float4*>(&xs[r][4 * k4]) = xreg[j];
+    }
+  };
+  if constexpr (VEC) gload(0);
   for (int k0 = 0; k0 < in_dim; k0 += LIN_KC) {
     __syncthreads();
-    for (int i = threadIdx.x; i < LIN_COLS * LIN_KC; i += VP_THREADS) {        // coalesced along k, transposed store (stride 33)
-      const int c = i / LIN_KC, k = i - c * LIN_KC;
-      wt[k][c] = (c0 + c < dim && k0 + k < in_dim) ? __ldg(w + static_cast<long>(c0 + c) * in_dim + k0 + k) : 0.f;
-    }
-    for (int i = threadIdx.x; i < nrows * LIN_KC; i += VP_THREADS) {
-      const int r = i / LIN_KC, k = i - r * LIN_KC;
-      xs[r][k] = (k0 + k < in_dim) ? __ldg(x + static_cast<long>(r0 + r) * in_dim + k0 + k) : 0.f;
+    if constexpr (VEC) {
+      sstore();
+    } else {
+      for (int i = threadIdx.x; i < LIN_COLS * LIN_KC; i += VP_THREADS) {        // coalesced along k, transposed store (stride 33)
+        const int c = i / LIN_KC, k = i - c * LIN_KC;
+        wt[k][c] = (c0 + c < dim && k0 + k < in_dim) ? __ldg(w + static_cast<long>(c0 + c) * in_dim + k0 + k) : 0.f;
+      }
+      for (int i = threadIdx.x; i < nrows * LIN_KC; i += VP_THREADS) {
+        const int r = i / LIN_KC, k = i - r * LIN_KC;
+        xs[r][k] = (k0 + k < in_dim) ? __ldg(x + static_cast<long>(r0 + r) * in_dim + k0 + k) : 0.f;
+      }
     }
     __syncthreads();
+    if constexpr (VEC)
+      if (k0 + LIN_KC < in_dim) gload(k0 + LIN_KC);
 #pragma unroll 4
     for (int k = 0; k < LIN_KC; k += 4) {
       const float w0 = wt[k][lane], w1 = wt[k + 1][lane], w2 = wt[k + 2][lane], w3 = wt[k + 3][lane];
@@ -276,7 +314,9 @@ extern "C" int fvqa_linear_f32(const float* x, const float* w, const float* bias
   if (rows <= 0) return FVQA_OK;
   FVQA_REQUIRE(dim > 0 && in_dim > 0, FVQA_ERR_INVALID_ARG, "linear_f32: dim %d in_dim %d", dim, in_dim);
   const dim3 grid((dim + LIN_COLS - 1) / LIN_COLS, (rows + LIN_ROWS - 1) / LIN_ROWS);
-  linear_f32_kernel<<<grid, VP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, add, y, rows, dim, in_dim);
+  const bool vec = in_dim % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0;
+  if (vec) linear_f32_kernel<true><<<grid, VP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, add, y, rows, dim, in_dim);
+  else linear_f32_kernel<false><<<grid, VP_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, add, y, rows, dim, in_dim);
   return check_launch("linear_f32");
 }
 
