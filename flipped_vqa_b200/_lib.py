@@ -72,6 +72,7 @@ _SIGNATURES = {
     "fvqa_qav_loss_fwd": [_p, _p, _p, _p, _f, _p, _p, _i, _i, _i, _p],
     "fvqa_qav_loss_bwd": [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _i, _i, _i, _i, _p],
     "fvqa_scatter_rows": [_p, _p, _p, _i, _p],
+    "fvqa_greedy_next": [_p, _i, _i, _p, _i, _p, _i, _p, _p, _i, _i, _p, _p, _i, _p],
     "fvqa_option_score": [_p, _p, _p, _i, _i, _i, _p],
     "fvqa_f32_to_h16": [_p, _p, _i64, _p],
     "fvqa_grad_scale_prepare": [_p, _f, _p, _p, _p],

@@ -268,6 +268,57 @@ extern "C" int fvqa_qav_loss_bwd(const fvqa_h16* hn, const float* vf32, const in
 }
 
 namespace fvqa {
+// Greedy decoding step of the generation evaluator (llama/model.py:429-467): for row b, tok = argmax_v logits[b, v] (lowest index
+// on ties, like torch.max), written to ids[b, pos[b] + 1] and out_tokens[b, step]; x_next[b, :] = tok_emb[tok, :] (fp32 residual
+// stream of the next decode step); margin[b] (optional) = best - second best logit. One CTA per row.
+__global__ void __launch_bounds__(256) greedy_next_kernel(const float* __restrict__ logits, int ld, int V, const h16* __restrict__ tok_emb,
+                                                          int dim, int32_t* __restrict__ ids, int S, const int32_t* __restrict__ pos,
+                                                          int32_t* __restrict__ out_tokens, int out_ld, int step, float* __restrict__ x_next,
+                                                          float* __restrict__ margin) {
+  __shared__ float bv[8], sv[8];
+  __shared__ int bi[8];
+  __shared__ int tok_s;
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* l = logits + static_cast<long>(b) * ld;
+  float best = -INFINITY, second = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += 256) {
+    const float x = l[v];
+    if (x > best || (x == best && v < arg)) { second = best; best = x; arg = v; }
+    else if (x > second) second = x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { second = fmaxf(best, os); best = ob; arg = oa; }
+    else second = fmaxf(second, ob);
+  }
+  if (lane == 0) { bv[warp] = best; sv[warp] = second; bi[warp] = arg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    best = bv[0]; second = sv[0]; arg = bi[0];
+    for (int w = 1; w < 8; ++w) {
+      if (bv[w] > best || (bv[w] == best && bi[w] < arg)) { second = fmaxf(best, sv[w]); best = bv[w]; arg = bi[w]; }
+      else second = fmaxf(second, bv[w]);
+    }
+    const int p = pos[b];
+    if (p + 1 < S) ids[static_cast<long>(b) * S + p + 1] = arg;
+    out_tokens[static_cast<long>(b) * out_ld + step] = arg;
+    if (margin != nullptr) margin[static_cast<long>(b) * out_ld + step] = best - second;
+    tok_s = arg;
+  }
+  __syncthreads();
+  const uint4* e = reinterpret_cast<const uint4*>(tok_emb + static_cast<long>(tok_s) * dim);
+  float4* o = reinterpret_cast<float4*>(x_next + static_cast<long>(b) * dim);
+  for (int v = threadIdx.x; v < (dim >> 3); v += 256) {
+    float f[8];
+    unpack8(__ldg(e + v), f);
+    o[2 * v] = make_float4(f[0], f[1], f[2], f[3]);
+    o[2 * v + 1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
 // One thread: k = 2^round(log2(target / max|g|)), gs_out = g * k, inv_k = 1 / k (see include/fvqa.h).
 __global__ void grad_scale_prepare_kernel(const float* __restrict__ g, float target, float* __restrict__ gs, float* __restrict__ inv_k) {
   const float m = fmaxf(fabsf(g[0]), fmaxf(fabsf(g[1]), fabsf(g[2])));
@@ -292,6 +343,16 @@ __global__ void scale_f32_kernel(float* __restrict__ x, const float* __restrict_
   for (long i = (n4 << 2) + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long>(gridDim.x) * blockDim.x) x[i] *= f;
 }
 }  // namespace fvqa
+
+extern "C" int fvqa_greedy_next(const float* logits, int ld, int V, const fvqa_h16* tok_emb, int dim, int32_t* ids, int S, const int32_t* pos,
+                                int32_t* out_tokens, int out_ld, int step, float* x_next, float* margin, int rows, void* stream) {
+  FVQA_REQUIRE(logits && tok_emb && ids && pos && out_tokens && x_next && dim % 8 == 0 && V > 0 && step >= 0 && step < out_ld,
+               FVQA_ERR_INVALID_ARG, "greedy_next: bad arguments (dim %d V %d step %d of %d)", dim, V, step, out_ld);
+  if (rows <= 0) return FVQA_OK;
+  fvqa::greedy_next_kernel<<<rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, V, reinterpret_cast<const fvqa::h16*>(tok_emb), dim,
+                                                                                 ids, S, pos, out_tokens, out_ld, step, x_next, margin);
+  return fvqa::check_launch("greedy_next");
+}
 
 extern "C" int fvqa_grad_scale_prepare(const float* gscale, float target, float* gs_out, float* inv_k, void* stream) {
   FVQA_REQUIRE(gscale && gs_out && inv_k, FVQA_ERR_INVALID_ARG, "grad_scale_prepare: null pointer");

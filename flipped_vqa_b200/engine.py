@@ -7,6 +7,7 @@ from __future__ import annotations
 
 import gc
 import math
+import os
 import sys
 from typing import Iterable
 
@@ -68,7 +69,8 @@ def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torc
     header = "Epoch: [{}]".format(epoch)
     print_freq = max(int(len(data_loader) / 4), 1)
     inner = model.module if hasattr(model, "module") else model
-    if getattr(args, "is_generation_task", False) and not hasattr(inner, "generate_answers"):
+    generation = bool(getattr(args, "is_generation_task", False))
+    if generation and not hasattr(inner, "generate_answers"):
         raise NotImplementedError("is_generation_task: this model has no generation evaluator (`engine.py:78-85,99-121`)")
     for data_iter_step, data in enumerate(metric_logger.log_every(data_loader, print_freq, header)):
         plan = None
@@ -76,6 +78,25 @@ def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torc
             data, plan = data
         answer = data["answer"]
         bsz = answer.shape[0]
+        if generation:                               # `engine.py:78-85,99-121`: greedy generation + nearest-option matching
+            with torch.no_grad():
+                most_similar, extracted_answers = inner.generate_answers(data)
+            if getattr(args, "output_dir", None):
+                out_dir = os.path.join(args.output_dir, "extracted_answers")
+                os.makedirs(out_dir, exist_ok=True)
+                misc.save_result(extracted_answers, out_dir, "extracted_answers_epoch%d" % epoch)
+            if getattr(args, "dataset", None) == "musicavqa":             # exact-prefix match against the first option's text
+                hits = torch.tensor([int(g["generated_answer"].startswith(c["options"][0])) for c, g in zip(data["text"], extracted_answers)],
+                                    dtype=torch.int32)
+            else:
+                hits = (answer.cpu() == most_similar.cpu())
+            acc = hits.sum().item() / bsz if bsz > 0 else 0
+            misc.log_qtype(data, hits, metric_logger, args)
+            metric_logger.update(lr=optimizer.param_groups[0]["lr"] if optimizer is not None else 0.0)
+            metric_logger.update(n=bsz, acc=acc)
+            if getattr(args, "debug", False):
+                break
+            continue
         with torch.no_grad():
             individual_losses = inner.inference_plan(plan) if plan is not None else model(data, inference=True)
             prediction = inner.predict_options(individual_losses)

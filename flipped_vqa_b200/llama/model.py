@@ -364,7 +364,8 @@ class Transformer(nn.Module):
 
     def forward(self, data, inference: bool = False):
         if inference:
-            return self.inference(data)
+            # HEAD `llama/model.py:251-252,367` generates and matches; the loss-based scorer is `model_my_original_mod.py` (`engine.py:78-93`)
+            return self.generate_answers(data) if getattr(self.args, "is_generation_task", False) else self.inference(data)
         self._ensure_packed()
         self._prefetch_adapter_kv()                         # GPU work that does not need the batch, enqueued before host planning
         return self.forward_plan(self.plan_batch(data))
@@ -429,6 +430,78 @@ class Transformer(nn.Module):
             return self._engine.forward_options(plan, *w, akv_pre=akv_pre)
         tok, _ = self._engine.forward(plan, *w, save=False, token_losses=True, akv_pre=akv_pre)
         return tok
+
+    # ------------------------------------------------------------------ generation evaluator (`llama/model.py:367-623`)
+    GENERATION_STEPS = 31                                   # `range(prefix - 1, prefix + 30)`, `model.py:433`
+    QUESTION_MARKER_ID = 894                                # hard-coded in `model.py:520`
+
+    @torch.no_grad()
+    def generate_answers(self, data, want_margin: bool = False):
+        """`Transformer.inference` of HEAD (`llama/model.py:367-546`): greedy-decode 31 tokens from `prefix_index - 1` on option
+        0's sequence of every sample, embed the generated answer (token-embedding mean up to the first EOS, restricted to the
+        positions of option 0's answer span) and every option's answer, and pick the option with the highest cosine similarity.
+        Returns (most_similar_indices [bsz] int64, extracted_answers: list of {'video_id', 'question', 'generated_answer'}), as
+        `engine.py:78-85,99-121` consumes them. Decoding is KV-cached (`StepEngine.generate`): every position is evaluated
+        once instead of 31 x bsz full-stack re-runs."""
+        self._ensure_packed()
+        self._prefetch_adapter_kv()
+        ids_all = data["text_id"]["vqa"]
+        bsz, n_options, S = ids_all.shape
+        d0 = dict(data)
+        d0["text_id"] = {"vqa": ids_all[:, 0:1].contiguous()}                 # `vqa_id = vqa_id[:, 0:1, :]`, `model.py:385-387`
+        d0["label"] = {"vqa": data["label"]["vqa"][:, 0:1].contiguous()}
+        plan = self.plan_batch(d0, inference=True)
+        self.last_plan = plan
+        trainables, n_run = self.trainable_parameters()
+        g1 = [p.data.view(-1) for p in trainables[3:3 + n_run]]
+        g2 = [p.data.view(-1) for p in trainables[3 + n_run:]]
+        prefix = [int(p) for p in data["prefix_index"]["vqa"]]
+        tokens, margin = self._engine.generate(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
+                                               self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data, g1, g2,
+                                               prefix, n_steps=self.GENERATION_STEPS, akv_pre=self._take_adapter_kv(), want_margin=want_margin)
+        vqa_id = plan.ids.view(bsz, S).long().cpu()                           # option 0's sequences with the generated tokens written in
+        self.last_generation = dict(tokens=tokens, margin=margin, ids=vqa_id)
+        # ---- cosine matching (`model.py:478-512,548-623`), token-embedding means in fp32 on the device
+        emb = self.tok_embeddings.weight.data
+        label0 = data["label"]["vqa"][:, 0, 1:]                               # `vqa_label[:, 1:]` of option 0
+        placeholder = label0 != 0                                             # positions of the answer span ([bsz, S-1])
+        choice_emb = []
+        for b in range(bsz):                                                  # extract_answers + embed_and_aggregate_answers
+            row0 = ids_all[b, 0].tolist()
+            start = row0.index(self.answer_token_id) + 5
+            answers = []
+            for o in range(n_options):
+                tail = ids_all[b, o, start:].tolist()
+                end = start + tail.index(self.eos_id) if self.eos_id in tail else S
+                answers.append(ids_all[b, o, start:end])
+            padded = torch.nn.utils.rnn.pad_sequence(answers, batch_first=True, padding_value=0).to(emb.device)
+            choice_emb.append(emb[padded].float().mean(dim=1))               # pad id 0 is embedded too, as in the reference
+        choice_emb = torch.stack(choice_emb)                                  # [bsz, n_options, d]
+        out_emb = []
+        for b in range(bsz):                                                  # filter_and_process_output_tokens + aggregate
+            toks = vqa_id[b, 1:][placeholder[b]]
+            eos = (toks == self.eos_id).nonzero(as_tuple=True)[0]
+            if eos.numel() > 0:
+                toks = toks[:eos[0]]
+            out_emb.append(emb[toks.to(emb.device)].float().mean(dim=0) if toks.numel() > 0 else torch.zeros(emb.shape[1], device=emb.device))
+        out_emb = torch.stack(out_emb)
+        sims = torch.bmm(torch.nn.functional.normalize(choice_emb, p=2, dim=2),
+                         torch.nn.functional.normalize(out_emb, p=2, dim=1).unsqueeze(-1)).squeeze(-1)          # find_most_similar
+        most_similar = sims.argmax(dim=1)
+        self.last_generation["similarities"] = sims
+        extracted = []
+        for b in range(bsz):                                                  # `model.py:514-544`
+            row = vqa_id[b].tolist()
+            q_start = row.index(self.QUESTION_MARKER_ID) + 2
+            q_end = row.index(self.answer_token_id)
+            a_tokens = row[q_end + 5:]
+            try:
+                a_end = a_tokens.index(self.eos_id)
+            except ValueError:
+                a_end = next((i for i, t in enumerate(a_tokens) if t == 0), len(a_tokens))
+            extracted.append({"video_id": data["vid"][b], "question": self.tokenizer.decode(row[q_start:q_end]),
+                              "generated_answer": self.tokenizer.decode(a_tokens[:a_end])})
+        return most_similar, extracted
 
     @staticmethod
     def predict_options(token_losses: torch.Tensor) -> torch.Tensor:

@@ -92,9 +92,9 @@ class Tokenizer(PromptBuilder):
 class SyntheticTokenizer:
     """Id-only stand-in (no text): vocabulary size plus the special ids the model stores."""
 
-    def __init__(self, n_words: int = 32000):
+    def __init__(self, n_words: int = 32000, a_token_id: int = 22550):
         self.n_words, self.bos_id, self.eos_id, self.pad_id = n_words, 1, 2, -1
-        self.v_token_id, self.q_token_id, self.a_token_id, self.nl_id = 15167, 16492, 22550, 13
+        self.v_token_id, self.q_token_id, self.a_token_id, self.nl_id = 15167, 16492, a_token_id, 13
 
     def decode(self, t):
         return ""

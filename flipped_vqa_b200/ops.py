@@ -411,6 +411,16 @@ def option_score(token_loss: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 @_timed
+@_timed
+def greedy_next(logits, tok_emb, ids, S: int, pos, out_tokens, step: int, x_next, margin=None):
+    """One greedy decoding step (see include/fvqa.h): argmax per row -> ids[b, pos[b] + 1] / out_tokens[b, step] / next embedding."""
+    _chk(logits, F32, "logits"); _chk(ids, torch.int32, "ids"); _chk(pos, torch.int32, "pos"); _chk(out_tokens, torch.int32, "out_tokens")
+    rows, V = logits.shape
+    check(_lib.lib().fvqa_greedy_next(ptr(logits), logits.stride(0), V, ptr(tok_emb), tok_emb.shape[1], ptr(ids), S, ptr(pos), ptr(out_tokens),
+                                      out_tokens.stride(0), step, ptr(x_next), ptr(margin), rows, stream()), "greedy_next")
+    return x_next
+
+
 def grad_scale_prepare(gscale: torch.Tensor, target: float):
     """(gscale * k, 1 / k) with k = 2^round(log2(target / max|gscale|)) computed on the device (no host sync)."""
     _chk(gscale, F32, "gscale")

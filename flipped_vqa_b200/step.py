@@ -550,6 +550,87 @@ class StepEngine:
         ops.scatter_rows(row_loss, plan.ce_dst, tl)
         return tl.view(plan.B, plan.n_opt, S - 1)
 
+    # -------------------------------------------------------------------------------- greedy generation, KV-cached
+    def generate(self, plan: BatchPlan, layers: List[LayerWeights], tok_emb, out_w, norm_w, adapter_w, visual_w, temporal_w,
+                 gate1: List[torch.Tensor], gate2: List[torch.Tensor], prefix_index: List[int], n_steps: int = 31, akv_pre=None,
+                 want_margin: bool = False):
+        """The generation evaluator's decoding loop (`llama/model.py:429-467`): for every sample, `n_steps` greedy steps starting at
+        position prefix - 1; step t reads the logits of position p = prefix - 1 + t and writes the arg-max token to position p + 1.
+
+        The reference re-runs the WHOLE layer stack over the whole sequence for every step of every sample (31 x bsz stack
+        evaluations). Under the causal mask the hidden state of position p only depends on tokens <= p, and those never change
+        once written, so this evaluates every position ONCE: one prefill over all sequences (the training forward's kernels; the
+        per-layer q|k|v buffers are kept as the K/V cache) and n_steps - 1 single-row decode steps for all samples together
+        (M = bsz rows through the GEMMs; the row's k|v is scattered into the cache and the fused attention kernel - adapter
+        branch, gate2 video bias, causal mask - runs over the cached layout).
+
+        `plan`: a dense inference plan of option 0's sequences (one per sample). Returns (tokens [bsz, n_steps] int32,
+        top-2 logit margins [bsz, n_steps] fp32 or None); plan.ids holds the sequences with the generated tokens written in."""
+        d, H, hd, hid, A, F, S = self.d, self.H, self.hd, self.hid, self.A, self.F, plan.S
+        B, T, dev = plan.n_seq, plan.T, self.device
+        assert len(prefix_index) == B
+        if min(prefix_index) < 1 or max(prefix_index) + n_steps - 1 > S - 1:
+            raise IndexError(f"generation needs 1 <= prefix_index and prefix_index + {n_steps - 1} <= {S - 1} (max_seq_len - 1); "
+                             f"got prefix_index in [{min(prefix_index)}, {max(prefix_index)}]")
+        L = len(layers)
+        # positions / cache rows of every step, known up front (decoding never stops early, `model.py:433`)
+        pos_host = torch.tensor([[p - 1 + t for p in prefix_index] for t in range(n_steps)], dtype=I32)
+        rows_host = pos_host + (torch.arange(B, dtype=I32) * S).view(1, B)
+        sched = torch.cat([pos_host.flatten(), rows_host.flatten()]).to(dev, non_blocking=True)
+        pos_all, rows_all = sched[: n_steps * B].view(n_steps, B), sched[n_steps * B:].view(n_steps, B)
+        tokens = torch.zeros(B, n_steps, dtype=I32, device=dev)
+        margin = torch.zeros(B, n_steps, dtype=torch.float32, device=dev) if want_margin else None
+        # ---- prefill: every sequence, all positions (option 0's original tokens; positions >= prefix are overwritten later)
+        vf32 = ops.linear_f32(plan.video, visual_w, add=getattr(plan, "vf_extra", None))
+        x = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w, B, S, F)
+        akv_all = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)
+        xn = torch.empty(T, d, dtype=H16, device=dev)
+        c = torch.empty(T, hid, dtype=H16, device=dev)
+        g = torch.empty(T, 2 * hid, dtype=H16, device=dev)
+        o = torch.empty(T, d, dtype=H16, device=dev)
+        lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
+        cache = []
+        for l, w in enumerate(layers):
+            ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
+            qkv = ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S)
+            cache.append(qkv)
+            ops.attn_fwd(qkv, akv_all[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, B, S, H, hd, A, F, out=o, lse=lse)
+            h = ops.gemm_nt(o, w.wo, residual=x, out_fp32=True)
+            ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
+            ops.gemm_swiglu_fwd(xn, w.w13, g=g, c=c)
+            x = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)
+        xs = torch.empty(B, d, dtype=torch.float32, device=dev)               # residual stream of the current decode rows
+        hn, _ = ops.rmsnorm_gather_fwd(x, rows_all[0], norm_w, self.eps)      # position prefix - 1 of every sample
+        logits = ops.gemm_nt(hn, out_w, out_fp32=True)
+        ops.greedy_next(logits, tok_emb, plan.ids, S, pos_all[0], tokens, 0, xs, margin)
+        del x, xn, c, g
+        # ---- decode: one row per sample and step
+        xn_s = torch.empty(B, d, dtype=H16, device=dev)
+        qkv_s = torch.empty(B, 3 * d, dtype=H16, device=dev)
+        o_s = torch.empty(B, d, dtype=H16, device=dev)
+        g_s = torch.empty(B, 2 * hid, dtype=H16, device=dev)
+        c_s = torch.empty(B, hid, dtype=H16, device=dev)
+        h_s = torch.empty(B, d, dtype=torch.float32, device=dev)
+        xs2 = torch.empty(B, d, dtype=torch.float32, device=dev)
+        for t in range(1, n_steps):
+            pos_t, rows_t = pos_all[t], rows_all[t]
+            for l, w in enumerate(layers):
+                ops.rmsnorm_fwd(xs, w.attn_norm, self.eps, y=xn_s)
+                ops.gemm_nt_rope(xn_s, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_s, pos_ids=pos_t)
+                ops.scatter_row_vectors(qkv_s, rows_t, cache[l])                # the new position's q | k | v into the cached layout
+                ops.attn_fwd(cache[l], akv_all[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, B, S, H, hd, A, F, out=o, lse=lse)
+                ops.gather_rows(o, rows_t, dst=o_s)
+                ops.gemm_nt(o_s, w.wo, residual=xs, out_fp32=True, out=h_s)
+                ops.rmsnorm_fwd(h_s, w.ffn_norm, self.eps, y=xn_s)
+                ops.gemm_nt(xn_s, w.w13, out=g_s)
+                ops.swiglu_fwd(g_s, c=c_s)
+                ops.gemm_nt(c_s, w.w2, residual=h_s, out_fp32=True, out=xs2)
+                xs, xs2 = xs2, xs
+            ops.rmsnorm_fwd(xs, norm_w, self.eps, y=xn_s)
+            ops.gemm_nt(xn_s, out_w, out_fp32=True, out=logits)
+            ops.greedy_next(logits, tok_emb, plan.ids, S, pos_t, tokens, t, xs, margin)
+        return tokens, margin
+
     # -------------------------------------------------------------------------------- backward
     def backward(self, sv: SavedStep, gscale: torch.Tensor, layers: List[LayerWeights], out_w_t, norm_w, gate1, gate2,
                  grads: "GradBuffers", on_layer_done=None):

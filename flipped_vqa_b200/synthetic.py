@@ -221,6 +221,54 @@ def synthetic_batch(bsz: int, seqlen: int, vocab: int, max_feats: int = 10, seed
     return data
 
 
+GEN_QUESTION_MARKER = 894        # the id `llama/model.py:520` searches for to locate the question
+
+
+def synthetic_generation_batch(bsz: int, seqlen: int, vocab: int, a_token_id: int, max_feats: int = 10, seed: int = 0,
+                               video_start: int = 12, n_options: int = 4, video_dim: int = 768) -> Dict:
+    """Validation batch for the generation evaluator (`llama/model.py:367-546`, `engine.py:78-85`): per sample `n_options` VQA
+    sequences  [BOS, instr..] | F video slots | nl | 894 x question.. | a_token + 4 tokens | answer_o .. EOS | pad(0)  that differ
+    only in the answer span; `prefix_index` = first answer position (= index(a_token) + 5, `model.py:551`); labels = answer span
+    incl. EOS, 0 elsewhere (`base_dataset.py:65-70`). Needs vocab > 894 and prefix + 30 <= seqlen - 1."""
+    assert vocab > GEN_QUESTION_MARKER and 2 < a_token_id < vocab and a_token_id != GEN_QUESTION_MARKER
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    F = max_feats
+
+    def rand_tokens(n):
+        t = torch.randint(3, vocab, (n,), generator=g)
+        bad = (t == GEN_QUESTION_MARKER) | (t == a_token_id) | (t == 13)
+        t[bad] = 7
+        return t
+
+    ids = torch.zeros(bsz, n_options, seqlen, dtype=torch.int64)
+    labels = torch.zeros(bsz, n_options, seqlen, dtype=torch.int64)
+    prefix = []
+    for b in range(bsz):
+        qlen = int(torch.randint(5, 10, (1,), generator=g))
+        head = torch.cat([torch.tensor([1]), rand_tokens(video_start - 1), torch.zeros(F, dtype=torch.int64), torch.tensor([13]),
+                          torch.tensor([GEN_QUESTION_MARKER]), rand_tokens(1 + qlen), torch.tensor([a_token_id]), rand_tokens(4)])
+        p = head.numel()
+        assert p + 30 <= seqlen - 1, "sequence too short for 31 generation steps"
+        prefix.append(p)
+        for o in range(n_options):
+            alen = int(torch.randint(1, 5, (1,), generator=g))
+            ans = torch.cat([rand_tokens(alen), torch.tensor([2])])
+            ids[b, o, :p] = head
+            ids[b, o, p:p + alen + 1] = ans
+            labels[b, o, p:p + alen + 1] = ans
+    return {
+        "video": torch.randn(bsz, F, video_dim, generator=g),
+        "text_id": {"vqa": ids}, "label": {"vqa": labels},
+        "video_start": {"vqa": [video_start] * bsz},
+        "prefix_index": {"vqa": prefix},
+        "answer": torch.randint(0, n_options, (bsz,), generator=g),
+        "qtype": torch.ones(bsz, dtype=torch.long),
+        "vid": [f"synthetic{b}" for b in range(bsz)], "qid": [f"q{b}" for b in range(bsz)],
+        "text": [{"options": [f"option{o}" for o in range(n_options)]} for _ in range(bsz)],
+    }
+
+
 class HashSentencePiece:
     """Deterministic stand-in for `SentencePieceProcessor.encode` (no `tokenizer.model` exists offline): words and
     punctuation marks hash to ids in [100, n_words); the pieces 'Video', 'Question', 'Answer' map to the ids the

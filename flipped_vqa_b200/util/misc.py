@@ -111,6 +111,41 @@ def save_on_master(*args, **kwargs):
         torch.save(*args, **kwargs)
 
 
+def save_result(result, result_dir, filename, is_json=True, is_list=True):
+    """`util/misc.py:570-610`: every rank writes `<filename>_rank<r>.{json,pth}`; after a barrier the main process merges all
+    ranks into `<filename>.{json,pth}` (the reference writes the merged JSON over the LAST rank's file and leaves the final path
+    empty - `:603` - here it goes to the path that is returned)."""
+    import json
+    ext = "json" if is_json else "pth"
+    part = os.path.join(result_dir, f"{filename}_rank{get_rank()}.{ext}")
+    final = os.path.join(result_dir, f"{filename}.{ext}")
+    if is_json:
+        with open(part, "w") as f:
+            json.dump(result, f, default=lambda o: o.tolist() if hasattr(o, "tolist") else str(o))
+    else:
+        torch.save(result, part)
+    if is_dist_avail_and_initialized():
+        dist.barrier()
+    if is_main_process():
+        merged = [] if is_list else {}
+        for r in range(get_world_size()):
+            path = os.path.join(result_dir, f"{filename}_rank{r}.{ext}")
+            res = json.load(open(path)) if is_json else torch.load(path, weights_only=False)
+            if is_list:
+                merged += res
+            else:
+                merged.update(res)
+        if is_json:
+            with open(final, "w") as f:
+                json.dump(merged, f)
+        else:
+            torch.save(merged, final)
+        print("result file saved to %s" % final)
+    if is_dist_avail_and_initialized():
+        dist.barrier()
+    return final
+
+
 def init_distributed_mode(args):
     """One process per GPU from torchrun's env (`util/misc.py:230-233`); NCCL over NVLink 5."""
     if "RANK" in os.environ and "WORLD_SIZE" in os.environ:

@@ -201,6 +201,14 @@ int fvqa_scatter_rows(const float* row_val, const int32_t* dst_index, float* dst
 int fvqa_option_score(const float* token_loss, int32_t* prediction, float* mean_loss, int n_items,
                       int n_opt, int len, void* stream);
 
+/* ---- greedy decoding step of the generation evaluator (llama/model.py:429-467: `pred = output[:, start_idx].max(1)[1]`, token
+ *      written to position start_idx + 1, its embedding fed back). Row b: tok = argmax_v logits[b, v] (lowest index on ties);
+ *      ids[b, pos[b] + 1] = tok (if in range); out_tokens[b, step] = tok; x_next[b, :] = tok_emb[tok, :] as fp32;
+ *      margin[b, step] (optional) = best - second-best logit. ids [rows, S] int32, pos [rows] int32, out_tokens / margin [rows, out_ld]. */
+int fvqa_greedy_next(const float* logits, int ld, int V, const fvqa_h16* tok_emb, int dim, int32_t* ids, int S,
+                     const int32_t* pos, int32_t* out_tokens, int out_ld, int step, float* x_next, float* margin, int rows,
+                     void* stream);
+
 /* ---- live-row pruning of the LAST layer: only the rows the losses read (labelled positions) go through
  *      its wo / FFN GEMMs, like the vocabulary projection (llama/model.py:347-356 never needs the other rows' outputs).
  *      dst[i, :] = src[idx[i], :]   and   dst[idx[i], :] = src[i, :]   for rows of row_bytes (multiple of 16); idx < 0 skipped. */

@@ -23,7 +23,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from flipped_vqa_b200.synthetic import synthetic_audio, synthetic_audio_state, synthetic_batch, synthetic_state_dict  # noqa: E402
+from flipped_vqa_b200.synthetic import (synthetic_audio, synthetic_audio_state, synthetic_batch, synthetic_generation_batch,  # noqa: E402
+                                        synthetic_state_dict)
 from oracle import ref_shims  # noqa: E402
 
 # The golden config: small enough for a <1 MB fixture, big enough for the CUDA path
@@ -177,6 +178,65 @@ def run_reference_trajectory(dtype=torch.float32):
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# generation evaluator (HEAD `llama/model.py:367-623`): greedy decoding + cosine matching
+# ------------------------------------------------------------------------------------------------
+GEN = dict(dim=128, n_layers=3, n_heads=2, vocab_size=1024, multiple_of=64, norm_eps=1e-6,
+           max_batch_size=32, max_seq_len=96, adapter_len=10, adapter_layer=2)
+GEN_RUN = dict(bsz=3, seqlen=96, n_options=4, max_feats=10, bias=3.5, tau=100.0, video_start=12, seed=23, a_token_id=900, logit_gain=12.0)   # seed: smallest arg-max margin of the reference run 0.017, similarity gaps > 0.13
+
+
+def generation_inputs():
+    """Weights: the usual synthetic state dict, with the output projection scaled by `logit_gain` so that the arg-max margins of
+    the random model sit well above 16-bit rounding noise (the fixture records the reference's own margins)."""
+    params = SimpleNamespace(**GEN)
+    r = GEN_RUN
+    sd = synthetic_state_dict(params, seed=r["seed"], max_feats=r["max_feats"], bias=r["bias"])
+    sd["output.weight"] = (sd["output.weight"] * r["logit_gain"]).to(torch.bfloat16).float()
+    data = synthetic_generation_batch(r["bsz"], r["seqlen"], GEN["vocab_size"], r["a_token_id"], max_feats=r["max_feats"], seed=r["seed"],
+                                      video_start=r["video_start"], n_options=r["n_options"])
+    return params, sd, data
+
+
+def run_reference_generation(dtype=torch.float32):
+    params, sd, data = generation_inputs()
+    mod = ref_shims.import_reference("model")
+    r = GEN_RUN
+    args = ref_shims.reference_args(max_feats=r["max_feats"], bias=r["bias"], tau=r["tau"])
+    args.is_generation_task = True
+    model = ref_shims.build_reference_model(mod, GEN, args, sd, dtype)
+    model.answer_token_id = r["a_token_id"]              # the stub tokenizer's id (22550) lies outside this small vocabulary
+    rec = {"logits": [], "final_ids": None, "sims": None}
+    hook = model.output.register_forward_hook(lambda m, i, o: rec["logits"].append(o.detach().float()))
+    orig_filter, orig_sim = model.filter_and_process_output_tokens, model.find_most_similar
+
+    def filt(tokens, mask):
+        rec["final_ids"] = tokens.detach().clone()
+        return orig_filter(tokens, mask)
+
+    def sim(out_emb, choice_emb):
+        res = orig_sim(out_emb, choice_emb)
+        rec["sims"] = res[1].detach().float()
+        return res
+    model.filter_and_process_output_tokens, model.find_most_similar = filt, sim
+    with ref_shims.patched_torch(dtype), torch.no_grad():
+        most_similar, extracted = model(data, inference=True)
+    hook.remove()
+    prefix, steps = data["prefix_index"]["vqa"], 31
+    assert len(rec["logits"]) == r["bsz"] * steps
+    margins = np.zeros((r["bsz"], steps))
+    tokens = np.zeros((r["bsz"], steps), dtype=np.int64)
+    for b in range(r["bsz"]):
+        for t in range(steps):
+            row = rec["logits"][b * steps + t][0, prefix[b] - 1 + t]
+            top = torch.topk(row, 2)
+            margins[b, t] = float(top.values[0] - top.values[1])
+            tokens[b, t] = int(top.indices[0])
+    return {"most_similar": most_similar.numpy(), "final_ids": rec["final_ids"].numpy(), "similarities": rec["sims"].numpy(),
+            "tokens": tokens, "margins": margins,
+            "generated_answer_lengths": np.array([len(e["generated_answer"]) for e in extracted])}
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -198,12 +258,15 @@ def main():
             au[f"{mode}/gold/{k}"] = v
         print(mode, "gold losses", au[f"{mode}/gold/loss"])
     np.savez_compressed(os.path.join(gdir, "train_audio_small.npz"), **au)
+    gen = run_reference_generation()
+    np.savez_compressed(os.path.join(gdir, "generation_small.npz"), **gen)
+    print("generation: most similar", gen["most_similar"], "min top-2 margin", gen["margins"].min(), "tokens[0,:8]", gen["tokens"][0, :8])
     tj = run_reference_trajectory()
     np.savez_compressed(os.path.join(gdir, "trajectory_small.npz"), **tj)
     print("trajectory step losses (sum):", tj["step_losses"].sum(1))
     print("gold losses", tr["gold/loss"], "fp16 losses", tr["fp16/loss"])
     print("gold pred", op["gold/prediction"], "fp16 pred", op["fp16/prediction"])
-    for f in ("train_small.npz", "options_small.npz", "train_audio_small.npz", "trajectory_small.npz"):
+    for f in ("train_small.npz", "options_small.npz", "train_audio_small.npz", "trajectory_small.npz", "generation_small.npz"):
         print(f, os.path.getsize(os.path.join(gdir, f)), "bytes")
 
 
