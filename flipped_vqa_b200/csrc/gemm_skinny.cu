@@ -26,13 +26,26 @@ constexpr int SK_THREADS = SK_WARPS * 32;
 
 }  // namespace
 
+// Optional epilogue of the single-group launch (the M = bsz rows of a KV-cached decode step, StepEngine.generate):
+// fp32 residual add (h = x + attn / out = h + ffn, llama/model.py:185-186) or RoPE of the q|k columns by each row's position
+// (llama/model.py:61-67), exactly what the tcgen05 GEMM's epilogues do for the M > 16 problems.
+struct SkinnyEpi {
+  const float* R = nullptr;          // [M, N] fp32 residual (OUT_F32 only)
+  int ldr = 0;
+  const float* cosT = nullptr;       // [positions, hd / 2]
+  const float* sinT = nullptr;
+  int rope_cols = 0, hd = 1, S = 1;
+  const int32_t* pos_ids = nullptr;  // position of row r (nullptr -> r % S)
+};
+
 // Grouped form (blockIdx.y = group g): A_g = A + g * strideA, C_g = C + g * strideC (elements), B_g = Bptrs[g] when a device
 // pointer table is given (the per-layer weight blocks live in separate allocations), else B. One launch then covers the
 // adapter projections of ALL layers (2.1 GB of weights at 7B) instead of 32 launches of 67 MB that are mostly ramp and tail.
 template <int NT, bool OUT_F32>
 __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const h16* __restrict__ A, long strideA, int lda,
                                                                  const h16* __restrict__ B, const h16* const* __restrict__ Bptrs, int ldb,
-                                                                 void* __restrict__ C, long strideC, int ldc, int M, int N, int K) {
+                                                                 void* __restrict__ C, long strideC, int ldc, int M, int N, int K,
+                                                                 const SkinnyEpi epi) {
   __shared__ float red[SK_WARPS][16][8 * NT + 1];
   {
     const int grp = blockIdx.y;
@@ -80,24 +93,41 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const h16* __re
     red[warp][g + 8][j * 8 + 2 * t + 1] = acc[j][3];
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 16 * 8 * NT; idx += SK_THREADS) {
-    const int r = idx / (8 * NT), cc = idx - r * (8 * NT);
-    if (r < M && n0 + cc < N) {
-      float s = 0.f;
+  // one thread per (row, column PAIR): a RoPE pair (2i, 2i + 1) never straddles threads (N is even: checked by the launcher)
+  for (int idx = threadIdx.x; idx < 16 * 4 * NT; idx += SK_THREADS) {
+    const int r = idx / (4 * NT), cc = 2 * (idx - r * (4 * NT));
+    const int col = n0 + cc;
+    if (r < M && col < N) {
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int w = 0; w < SK_WARPS; ++w) s += red[w][r][cc];
-      if constexpr (OUT_F32) reinterpret_cast<float*>(C)[static_cast<long>(r) * ldc + n0 + cc] = s;
-      else reinterpret_cast<h16*>(C)[static_cast<long>(r) * ldc + n0 + cc] = f2h(s);
+      for (int w = 0; w < SK_WARPS; ++w) { s0 += red[w][r][cc]; s1 += red[w][r][cc + 1]; }
+      if (epi.cosT != nullptr && col < epi.rope_cols) {
+        const int pos = epi.pos_ids != nullptr ? __ldg(epi.pos_ids + r) : r % epi.S;
+        const long ti = static_cast<long>(pos) * (epi.hd >> 1) + ((col % epi.hd) >> 1);
+        const float cv = __ldg(epi.cosT + ti), sv = __ldg(epi.sinT + ti);
+        const float a = s0, b = s1;
+        s0 = a * cv - b * sv;
+        s1 = a * sv + b * cv;
+      }
+      if constexpr (OUT_F32) {
+        float* o = reinterpret_cast<float*>(C) + static_cast<long>(r) * ldc + col;
+        if (epi.R != nullptr) { s0 += epi.R[static_cast<long>(r) * epi.ldr + col]; s1 += epi.R[static_cast<long>(r) * epi.ldr + col + 1]; }
+        o[0] = s0; o[1] = s1;
+      } else {
+        *reinterpret_cast<uint32_t*>(reinterpret_cast<h16*>(C) + static_cast<long>(r) * ldc + col) = pack_h16x2(s0, s1);
+      }
     }
   }
 }
 
+// R: fp32 residual is handled (out_fp32 launches); an h16 residual is not
 bool gemm_skinny_supported(int M, int K, const void* R) { return M <= 16 && R == nullptr && K % (SK_WARPS * 32) == 0; }
+bool gemm_skinny_shape_ok(int M, int N, int K) { return M <= 16 && K % (SK_WARPS * 32) == 0 && N % 2 == 0; }
 
 std::atomic<int> g_skinny_force_nt{0};   // tuning hook (fvqa_gemm_debug_skinny_nt): column blocks of 8 * nt per CTA; 0 = heuristic
 
-int gemm_skinny_grouped(const h16* A, long strideA, int lda, const h16* B, const h16* const* Bptrs, int ldb, void* C, long strideC,
-                        int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream) {
+static int skinny_launch(const h16* A, long strideA, int lda, const h16* B, const h16* const* Bptrs, int ldb, void* C, long strideC,
+                         int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, const SkinnyEpi& epi, cudaStream_t stream) {
   // 16 columns per CTA when that still gives every SM ~2 CTAs, else 8. (32 columns per CTA cost registers / resident CTAs:
   // measured 4.96 vs 5.38 TB/s on the 2.1 GB forward launch and 3.5 vs 4.3 TB/s on a backward chunk, tools/skinny_bench.py.)
   const long blocks16 = static_cast<long>(N / 16) * groups;
@@ -106,16 +136,31 @@ int gemm_skinny_grouped(const h16* A, long strideA, int lda, const h16* B, const
   const int cols = 8 * nt;
   const dim3 grid((N + cols - 1) / cols, groups);
 #define FVQA_SK(NT_)                                                                                                                \
-  if (out_fp32) gemm_skinny_kernel<NT_, true><<<grid, SK_THREADS, 0, stream>>>(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K); \
-  else gemm_skinny_kernel<NT_, false><<<grid, SK_THREADS, 0, stream>>>(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K);
+  if (out_fp32) gemm_skinny_kernel<NT_, true><<<grid, SK_THREADS, 0, stream>>>(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, epi); \
+  else gemm_skinny_kernel<NT_, false><<<grid, SK_THREADS, 0, stream>>>(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, epi);
   if (nt == 4) { FVQA_SK(4) } else if (nt == 2) { FVQA_SK(2) } else { FVQA_SK(1) }
 #undef FVQA_SK
   return check_launch("gemm_skinny");
 }
 
+int gemm_skinny_grouped(const h16* A, long strideA, int lda, const h16* B, const h16* const* Bptrs, int ldb, void* C, long strideC,
+                        int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream) {
+  return skinny_launch(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, groups, out_fp32, num_sms, SkinnyEpi{}, stream);
+}
+
 int gemm_skinny(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, int num_sms,
                 cudaStream_t stream) {
-  return gemm_skinny_grouped(A, 0, lda, B, nullptr, ldb, C, 0, ldc, M, N, K, 1, out_fp32, num_sms, stream);
+  return skinny_launch(A, 0, lda, B, nullptr, ldb, C, 0, ldc, M, N, K, 1, out_fp32, num_sms, SkinnyEpi{}, stream);
+}
+
+// + fp32 residual (out_fp32) or RoPE epilogue: the decode-step projections of the generation evaluator (M = bsz <= 16 rows)
+int gemm_skinny_epi(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, const float* R,
+                    int ldr, const float* cosT, const float* sinT, int rope_cols, int hd, int S, const int32_t* pos_ids, int num_sms,
+                    cudaStream_t stream) {
+  SkinnyEpi epi;
+  epi.R = R; epi.ldr = ldr; epi.cosT = cosT; epi.sinT = sinT; epi.rope_cols = rope_cols; epi.hd = hd > 0 ? hd : 1; epi.S = S > 0 ? S : 1;
+  epi.pos_ids = pos_ids;
+  return skinny_launch(A, 0, lda, B, nullptr, ldb, C, 0, ldc, M, N, K, 1, out_fp32, num_sms, epi, stream);
 }
 
 }  // namespace fvqa

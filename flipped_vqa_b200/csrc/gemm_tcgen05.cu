@@ -776,6 +776,10 @@ int gemm_skinny(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, 
                 cudaStream_t stream);
 int gemm_skinny_grouped(const h16* A, long strideA, int lda, const h16* B, const h16* const* Bptrs, int ldb, void* C, long strideC,
                         int ldc, int M, int N, int K, int groups, int out_fp32, int num_sms, cudaStream_t stream);
+bool gemm_skinny_shape_ok(int M, int N, int K);
+int gemm_skinny_epi(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, int M, int N, int K, int out_fp32, const float* R,
+                    int ldr, const float* cosT, const float* sinT, int rope_cols, int hd, int S, const int32_t* pos_ids, int num_sms,
+                    cudaStream_t stream);
 extern std::atomic<int> g_skinny_force_nt;
 
 // ---- CTA-pair path ---------------------------------------------------------------------------
@@ -910,6 +914,11 @@ extern "C" int fvqa_gemm_nt(const fvqa_h16* A, int lda, const fvqa_h16* B, int l
   const h16* b = reinterpret_cast<const h16*>(B);
   GemmEpi epi{R, ldr, nullptr, nullptr, 0, 0, 1, nullptr, 0, 0};
   if (g_force_bn == 0 && gemm_skinny_supported(M, K, R)) return gemm_skinny(a, lda, b, ldb, C, ldc, M, N, K, out_fp32, g_num_sms, s);
+  // M <= 16 with the fp32 residual stream (decode steps of the generation evaluator): HBM-bound weight streaming on every SM
+  // instead of N / 256 single-CTA tiles
+  if (g_force_bn == 0 && out_fp32 && R != nullptr && gemm_skinny_shape_ok(M, N, K))
+    return gemm_skinny_epi(a, lda, b, ldb, C, ldc, M, N, K, 1, reinterpret_cast<const float*>(R), ldr, nullptr, nullptr, 0, 0, 1, nullptr,
+                           g_num_sms, s);
   if (use_quad(M, N)) {
     return out_fp32 ? launch_gemm_quad<true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s) : launch_gemm_quad<false>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   }
@@ -952,6 +961,8 @@ static int gemm_rope_impl(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb
   const h16* a = reinterpret_cast<const h16*>(A);
   const h16* b = reinterpret_cast<const h16*>(B);
   GemmEpi epi{nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S, nullptr, 0, 0, pos_ids};
+  if (g_force_bn == 0 && gemm_skinny_shape_ok(M, N, K))
+    return gemm_skinny_epi(a, lda, b, ldb, C, ldc, M, N, K, 0, nullptr, 0, rope_cos, rope_sin, rope_cols, hd, S, pos_ids, g_num_sms, s);
   if (use_pair(M, N)) return launch_gemm_pair<false, EPI_ROPE>(a, lda, b, ldb, C, ldc, epi, M, N, K, pair_bn(M, N), s);
   if (prefer_bn128(M, N)) return launch_gemm<128, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);
   return launch_gemm<256, false, true>(a, lda, b, ldb, C, ldc, epi, M, N, K, s);

@@ -353,6 +353,8 @@ class StepEngine:
         # its exact inverse when they are final. 2^14: dlogits <= 2^14 / n_labelled, d hidden ~ O(1) (fp16 normal range 6e-5 .. 65504).
         # bf16 operands have fp32's exponent range: no scaling (target 0).
         self.grad_scale_target = 2.0 ** 14 if ops.H16 == torch.float16 else 0.0
+        self._gen_ws = None          # persistent workspace (+ captured decode graph) of StepEngine.generate
+        self.decode_graph = True     # generation evaluator: replay the single-row decode step as a CUDA graph (StepEngine.generate)
 
     # -------------------------------------------------------------------------------- batch-independent prologue
     def adapter_kv(self, layers: List[LayerWeights], adapter_w):
@@ -580,55 +582,90 @@ class StepEngine:
         pos_all, rows_all = sched[: n_steps * B].view(n_steps, B), sched[n_steps * B:].view(n_steps, B)
         tokens = torch.zeros(B, n_steps, dtype=I32, device=dev)
         margin = torch.zeros(B, n_steps, dtype=torch.float32, device=dev) if want_margin else None
+        # Persistent workspace per (batch, sequence length, depth): the decode step below is captured ONCE as a CUDA graph and replayed
+        # for every later step of every later batch, so every buffer it touches must keep its address across calls - the batch's ids /
+        # video_start / adapter K|V are copied in.
+        key = (B, S, L, bool(want_margin), tuple(w.wqkv.data_ptr() for w in layers[:2]), tok_emb.data_ptr(), gate1[0].data_ptr())
+        ws = self._gen_ws if self._gen_ws is not None and self._gen_ws["key"] == key else None
+        if ws is None:
+            e = lambda *shape, dt=H16: torch.empty(*shape, dtype=dt, device=dev)
+            f32 = torch.float32
+            ws = dict(key=key, graph=None, cache=[e(T, 3 * d) for _ in range(L)], o=e(T, d), lse=e(B, H, S, dt=f32), ids=e(T, dt=I32),
+                      vstart=e(B, dt=I32), akv=e(L, A, 2 * d), xs=e(B, d, dt=f32), xa=e(B, d, dt=f32), xb=e(B, d, dt=f32), h=e(B, d, dt=f32),
+                      xn=e(B, d), qkv=e(B, 3 * d), o_s=e(B, d), g=e(B, 2 * hid), c=e(B, hid), rstd=e(B, dt=f32), logits=e(B, self.V, dt=f32),
+                      pos=e(B, dt=I32), rows=e(B, dt=I32), tok=torch.zeros(B, 1, dtype=I32, device=dev),
+                      mar=(torch.zeros(B, 1, dtype=f32, device=dev) if want_margin else None))
+            self._gen_ws = ws
+        cache, o, lse, ids_w, vstart_w, xs, logits = ws["cache"], ws["o"], ws["lse"], ws["ids"], ws["vstart"], ws["xs"], ws["logits"]
+        ids_w.copy_(plan.ids)
+        vstart_w.copy_(plan.vstart)
+        akv_src = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)
+        for l in range(L):
+            ws["akv"][l].copy_(akv_src[l][:A])
+        akv_all = [ws["akv"][l] for l in range(L)]
         # ---- prefill: every sequence, all positions (option 0's original tokens; positions >= prefix are overwritten later)
         vf32 = ops.linear_f32(plan.video, visual_w, add=getattr(plan, "vf_extra", None))
-        x = ops.build_h0_fwd(tok_emb, plan.ids, plan.labels, plan.vstart, plan.seq_video, plan.qav_index, vf32, temporal_w, B, S, F)
-        akv_all = akv_pre if akv_pre is not None else self.adapter_kv(layers, adapter_w)
+        x = ops.build_h0_fwd(tok_emb, ids_w, plan.labels, vstart_w, plan.seq_video, plan.qav_index, vf32, temporal_w, B, S, F)
         xn = torch.empty(T, d, dtype=H16, device=dev)
         c = torch.empty(T, hid, dtype=H16, device=dev)
         g = torch.empty(T, 2 * hid, dtype=H16, device=dev)
-        o = torch.empty(T, d, dtype=H16, device=dev)
-        lse = torch.empty(B, H, S, dtype=torch.float32, device=dev)
-        cache = []
         for l, w in enumerate(layers):
             ops.rmsnorm_fwd(x, w.attn_norm, self.eps, y=xn)
-            qkv = ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S)
-            cache.append(qkv)
-            ops.attn_fwd(qkv, akv_all[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, B, S, H, hd, A, F, out=o, lse=lse)
+            ops.gemm_nt_rope(xn, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=cache[l])
+            ops.attn_fwd(cache[l], akv_all[l], self.cos, self.sin, gate1[l], gate2[l], vstart_w, B, S, H, hd, A, F, out=o, lse=lse)
             h = ops.gemm_nt(o, w.wo, residual=x, out_fp32=True)
             ops.rmsnorm_fwd(h, w.ffn_norm, self.eps, y=xn)
             ops.gemm_swiglu_fwd(xn, w.w13, g=g, c=c)
             x = ops.gemm_nt(c, w.w2, residual=h, out_fp32=True)
-        xs = torch.empty(B, d, dtype=torch.float32, device=dev)               # residual stream of the current decode rows
         hn, _ = ops.rmsnorm_gather_fwd(x, rows_all[0], norm_w, self.eps)      # position prefix - 1 of every sample
-        logits = ops.gemm_nt(hn, out_w, out_fp32=True)
-        ops.greedy_next(logits, tok_emb, plan.ids, S, pos_all[0], tokens, 0, xs, margin)
+        ops.gemm_nt(hn, out_w, out_fp32=True, out=logits)
+        ops.greedy_next(logits, tok_emb, ids_w, S, pos_all[0], tokens, 0, xs, margin)
         del x, xn, c, g
-        # ---- decode: one row per sample and step
-        xn_s = torch.empty(B, d, dtype=H16, device=dev)
-        qkv_s = torch.empty(B, 3 * d, dtype=H16, device=dev)
-        o_s = torch.empty(B, d, dtype=H16, device=dev)
-        g_s = torch.empty(B, 2 * hid, dtype=H16, device=dev)
-        c_s = torch.empty(B, hid, dtype=H16, device=dev)
-        h_s = torch.empty(B, d, dtype=torch.float32, device=dev)
-        xs2 = torch.empty(B, d, dtype=torch.float32, device=dev)
-        for t in range(1, n_steps):
-            pos_t, rows_t = pos_all[t], rows_all[t]
+        # ---- decode: one row per sample and step. The step is launch-bound (~10 small launches per layer around 13.5 GB of weight
+        # streaming): after one eager step it is captured in a CUDA graph (kept in the workspace) and replayed; positions / cache rows
+        # of the step are read from fixed device buffers that a copy refreshes between replays.
+        xn_s, qkv_s, o_s, g_s, c_s, h_s, xa, xb, rstd_s = (ws[k] for k in ("xn", "qkv", "o_s", "g", "c", "h", "xa", "xb", "rstd"))
+        pos_c, rows_c, tok_c, mar_c = ws["pos"], ws["rows"], ws["tok"], ws["mar"]
+
+        def decode_step():
+            """x (embedding of the last token) in `xs` -> logits of the current position -> next token / embedding back into `xs`."""
+            x_in, x_out = xs, xa
             for l, w in enumerate(layers):
-                ops.rmsnorm_fwd(xs, w.attn_norm, self.eps, y=xn_s)
-                ops.gemm_nt_rope(xn_s, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_s, pos_ids=pos_t)
-                ops.scatter_row_vectors(qkv_s, rows_t, cache[l])                # the new position's q | k | v into the cached layout
-                ops.attn_fwd(cache[l], akv_all[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, B, S, H, hd, A, F, out=o, lse=lse)
-                ops.gather_rows(o, rows_t, dst=o_s)
-                ops.gemm_nt(o_s, w.wo, residual=xs, out_fp32=True, out=h_s)
-                ops.rmsnorm_fwd(h_s, w.ffn_norm, self.eps, y=xn_s)
+                ops.rmsnorm_fwd(x_in, w.attn_norm, self.eps, y=xn_s, rstd=rstd_s)
+                ops.gemm_nt_rope(xn_s, w.wqkv, self.cos, self.sin, 2 * d, hd, S, out=qkv_s, pos_ids=pos_c)
+                ops.scatter_row_vectors(qkv_s, rows_c, cache[l])                # the new position's q | k | v into the cached layout
+                ops.attn_fwd(cache[l], akv_all[l], self.cos, self.sin, gate1[l], gate2[l], vstart_w, B, S, H, hd, A, F, out=o, lse=lse)
+                ops.gather_rows(o, rows_c, dst=o_s)
+                ops.gemm_nt(o_s, w.wo, residual=x_in, out_fp32=True, out=h_s)
+                ops.rmsnorm_fwd(h_s, w.ffn_norm, self.eps, y=xn_s, rstd=rstd_s)
                 ops.gemm_nt(xn_s, w.w13, out=g_s)
                 ops.swiglu_fwd(g_s, c=c_s)
-                ops.gemm_nt(c_s, w.w2, residual=h_s, out_fp32=True, out=xs2)
-                xs, xs2 = xs2, xs
-            ops.rmsnorm_fwd(xs, norm_w, self.eps, y=xn_s)
+                ops.gemm_nt(c_s, w.w2, residual=h_s, out_fp32=True, out=x_out)
+                x_in, x_out = x_out, (xb if x_out is xa else xa)
+            ops.rmsnorm_fwd(x_in, norm_w, self.eps, y=xn_s, rstd=rstd_s)
             ops.gemm_nt(xn_s, out_w, out_fp32=True, out=logits)
-            ops.greedy_next(logits, tok_emb, plan.ids, S, pos_t, tokens, t, xs, margin)
+            ops.greedy_next(logits, tok_emb, ids_w, S, pos_c, tok_c, 0, xs, mar_c)
+
+        for t in range(1, n_steps):
+            pos_c.copy_(pos_all[t])
+            rows_c.copy_(rows_all[t])
+            if self.decode_graph and ws["graph"] is not None:
+                ws["graph"].replay()
+            else:
+                decode_step()
+                if self.decode_graph and ws["graph"] is None and n_steps > 2:
+                    try:
+                        torch.cuda.synchronize()
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph):
+                            decode_step()
+                        ws["graph"] = graph
+                    except Exception:                                           # capture unsupported here: keep launching eagerly
+                        self.decode_graph = False
+            tokens[:, t].copy_(tok_c[:, 0])
+            if want_margin:
+                margin[:, t].copy_(mar_c[:, 0])
+        plan.ids.copy_(ids_w)                                                   # the sequences with the generated tokens written in
         return tokens, margin
 
     # -------------------------------------------------------------------------------- backward

@@ -38,6 +38,11 @@ def test_generation_matches_reference_golden(fvqa_lib):
     assert np.abs(gen["similarities"].cpu().numpy() - g["similarities"]).max() < 5e-3
     assert most_similar.cpu().tolist() == g["most_similar"].tolist()
     assert [e["video_id"] for e in extracted] == data["vid"] and all(set(e) == {"video_id", "question", "generated_answer"} for e in extracted)
+    # the decode step replayed as a CUDA graph (default) and launched eagerly give the same tokens
+    assert model._engine.decode_graph
+    model._engine.decode_graph = False
+    model(data, inference=True)
+    assert model.last_generation["tokens"].cpu().tolist() == g["tokens"].tolist()
 
 
 def test_kv_cached_decode_equals_full_rerun(fvqa_lib):

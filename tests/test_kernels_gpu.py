@@ -226,6 +226,40 @@ def test_gemm_rope_epilogue_position_table(fvqa_lib):
     assert torch.equal(out, dense[rows.cuda()])
 
 
+@pytest.mark.parametrize("M,H,hd,hid", [(8, 32, 128, 11008), (3, 2, 64, 256), (16, 4, 128, 768)])
+def test_decode_step_projections(fvqa_lib, M, H, hd, hid):
+    """The M = bsz <= 16 rows of a KV-cached decode step (StepEngine.generate) take the HBM-bound skinny kernel with the same
+    epilogues as the tcgen05 GEMM: RoPE by a per-row position table (QKV) and the fp32 residual add (wo, w2). Checked against
+    the tcgen05 kernels on the same inputs (debug hook: force the single-CTA tile) and against torch."""
+    from flipped_vqa_b200 import ops
+    d, S = H * hd, 128
+    x = h16_randn(M, d, seed=91)
+    wqkv = h16_randn(3 * d, d, std=0.05, seed=92)
+    w2 = h16_randn(d, hid, std=0.05, seed=93)
+    cact = h16_randn(M, hid, seed=94)
+    res = torch.randn(M, d, device="cuda")
+    cos, sin = O.rope_table(hd, 2 * S)
+    cos, sin = cos.cuda().contiguous(), sin.cuda().contiguous()
+    pos = torch.randint(0, S, (M,), dtype=torch.int32).cuda()
+    qkv = ops.gemm_nt_rope(x, wqkv, cos, sin, 2 * d, hd, S, pos_ids=pos)
+    y = ops.gemm_nt(cact, w2, residual=res, out_fp32=True)
+    prev = fvqa_lib.fvqa_gemm_debug_force_bn(-1)
+    try:
+        qkv_tc = ops.gemm_nt_rope(x, wqkv, cos, sin, 2 * d, hd, S, pos_ids=pos)
+        y_tc = ops.gemm_nt(cact, w2, residual=res, out_fp32=True)
+    finally:
+        fvqa_lib.fvqa_gemm_debug_force_bn(prev)
+    ref = (x.float() @ wqkv.float().t()).view(M, 1, 3, H, hd)
+    c, s_ = cos[pos.long()][:, None], sin[pos.long()][:, None]                       # [M, 1, hd/2]
+
+    def rot(t):                                                                      # t [M, 1, H, hd]
+        a, b = t[..., 0::2], t[..., 1::2]
+        return torch.stack((a * c[:, :, None] - b * s_[:, :, None], a * s_[:, :, None] + b * c[:, :, None]), dim=-1).flatten(3)
+    ref = torch.stack([rot(ref[:, :, 0]), rot(ref[:, :, 1]), ref[:, :, 2]], dim=2).reshape(M, 3 * d)
+    assert relerr(qkv, ref) < 5e-3 and relerr(qkv, qkv_tc) < 2e-3
+    assert relerr(y, cact.float() @ w2.float().t() + res) < 2e-4 and relerr(y, y_tc) < 1e-4
+
+
 def test_gemm_strided_views(fvqa_lib):
     """Sub-blocks of larger matrices (used for Wk|Wv of the fused QKV weight and its transpose)."""
     from flipped_vqa_b200 import ops
