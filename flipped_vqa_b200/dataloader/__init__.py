@@ -75,6 +75,54 @@ def encode_sample(tokenizer, text: Dict[str, str], answer: int, answer_mapping: 
                               {"vqa": vqa_vs, "vaq": vaq_vs}, max_seq_len, max_feats)
 
 
+def pad_text_ids_sub(seqs: Sequence[Sequence[int]], prefix_index: int, prefix_i: int, prefix_main: int, task: str, max_seq_len: int,
+                     max_feats: int, q_token_id: int, sub: bool = True):
+    """`TVQA._get_padding_id` (`dataloader/tvqa.py:75-108`): like `pad_text_ids`, but a sequence that overflows max_seq_len keeps
+    its head [0, prefix_i), its tail [prefix_main, end) and as much of the DIALOGUE [prefix_i, prefix_main) as still fits, instead
+    of losing its tail; prefix_index is then re-derived (vqa: S - 4, qav: S - F - 1, vaq: first 'Question' piece + 2 over all rows
+    padded so far). Without `sub`, or when the sample has no dialogue, overflow is a plain truncation. Returns (padded, prefix)."""
+    S = max_seq_len
+    out = torch.full((len(seqs), S), -1, dtype=torch.int64)
+    prefix = prefix_index
+    for i, s in enumerate(seqs):
+        t = torch.as_tensor(list(s), dtype=torch.int64)
+        if t.numel() <= S:
+            out[i, :t.numel()] = t
+            prefix = prefix_index
+        elif sub and prefix_i != prefix_main:
+            keep = S - (prefix_i + (t.numel() - prefix_main))                  # dialogue tokens that still fit
+            out[i, :prefix_i] = t[:prefix_i]
+            out[i, prefix_i:prefix_i + keep] = t[prefix_i:prefix_i + keep]
+            out[i, prefix_i + keep:] = t[prefix_main:]
+            if task == "vqa":
+                prefix = S - 4
+            elif task == "vaq":
+                prefix = int((out == q_token_id).nonzero(as_tuple=True)[1][0]) + 2
+            else:
+                prefix = S - max_feats - 1
+        else:
+            out[i] = t[:S]
+            prefix = prefix_index
+    return out, prefix
+
+
+def encode_sample_sub(tokenizer, text: Dict[str, str], answer: int, answer_mapping: Dict[int, str], split: str, max_seq_len: int,
+                      max_feats: int, sub: bool = True) -> Dict[str, Dict]:
+    """Prompt building + tensors for one `--sub` sample = `TVQA._get_text_token` (`dataloader/tvqa.py:110-160`; `vlep.py:104-154` is
+    the same code): dialogue prompts, dialogue-aware overflow handling, then the usual labels / masks / video indices."""
+    kw = dict(text=text, max_feats=max_feats, split=split, answer_mapping=answer_mapping, answer=answer)
+    vqa, vqa_p, vqa_vs, vqa_i, vqa_m = tokenizer.encode_dvqa(**kw)
+    vaq, vaq_p, vaq_vs, vaq_i, vaq_m = tokenizer.encode_dvaq(**kw)
+    qav, qav_p, qav_i, qav_m = tokenizer.encode_dqav(max_seq_len=max_seq_len, **kw)
+    padded, prefix = {}, {}
+    for task, seqs, p, pi, pm in (("vqa", vqa, vqa_p, vqa_i, vqa_m), ("vaq", vaq, vaq_p, vaq_i, vaq_m), ("qav", qav, qav_p, qav_i, qav_m)):
+        padded[task], prefix[task] = pad_text_ids_sub(seqs, p, pi, pm, task, max_seq_len, max_feats, tokenizer.q_token_id, sub)
+    ids = {t: [row.tolist() for row in padded[t]] for t in _TASKS}                      # already padded to S with -1
+    out = build_text_tensors(ids, prefix, {"vqa": vqa_vs, "vaq": vaq_vs}, max_seq_len, max_feats)
+    # `tvqa.py:139`: the qav frame labels are NOT clipped to the sequence there (prefix + F <= S holds by construction)
+    return out
+
+
 def batch_collate(batch: List[Dict]) -> Dict:
     """The batch dict of `dataloader/__init__.py:28-90`: per-task tensors stacked over samples, python lists for
     `video_start` / `prefix_index` / ids, optional `video` and `audio` (+ lengths)."""

@@ -5,7 +5,7 @@ The model itself only reads `n_words`, `eos_id`, `a_token_id`, `q_token_id` (`ll
 `tokenizer.model` this class wraps SentencePiece exactly like the reference; `SyntheticTokenizer` stands in when no
 tokenizer file exists (tests, benchmarks). The prompt builders live in `PromptBuilder`, which only needs an object
 with `.encode(str) -> List[int]` as `sp_model`, so they are testable without a SentencePiece model file. The subtitle
-(`--sub`) builders of TVQA (`tokenizer.py:213-302`) are not mirrored."""
+(`--sub`) builders of TVQA / VLEP (`encode_dvqa` / `encode_dvaq` / `encode_dqav`, `tokenizer.py:218-302`) are mirrored too."""
 from __future__ import annotations
 
 import os
@@ -65,6 +65,46 @@ class PromptBuilder:
                 for o in self._option_strings(split, answer_mapping, answer, options)]
         ref = seqs[0] if split == "train" else seqs[answer]
         return seqs, ref.index(self.v_token_id) + 2
+
+
+    # ---- dialogue (`--sub`) variants, `tokenizer.py:218-302`: the subtitle text d_text sits between the video block and the question
+    # (vqa / vaq) or between the instruction and the question (qav). They always append `answer_mapping[k]`, return the token spans
+    # of the dialogue (prefix_i = its first position, prefix_main = first position after it) so that the dataset can cut the
+    # dialogue when the sequence overflows max_seq_len (`dataloader/tvqa.py:75-108`), and locate prefix_index in sequence 0.
+    _INSTR_D = {"vqa": "Instruction: Predict the answer based on the dialogue, video and question.\n",
+                "vaq": "Instruction: Predict the question based on the dialogue, video and answer.\n",
+                "qav": "Instruction: Predict the video based on the dialogue, question and answer.\n"}
+
+    def _mapped(self, split, answer_mapping, answer):
+        return [answer_mapping[answer]] if split == "train" else list(answer_mapping.values())
+
+    def encode_dvqa(self, text=None, max_feats: int = 10, split: str = "train", answer_mapping=None, answer=None):
+        head = [self.bos_id] + self.sp_model.encode(self._INSTR_D["vqa"] + "Video:")
+        video_start = len(head)
+        prefix_i = video_start + max_feats + 1
+        dialogue = self.sp_model.encode(text["d_text"])
+        stem = text["q_text"] + text["o_text"] + text["a_text"]
+        seqs = [head + [-2] * max_feats + [self.nl_id] + dialogue + self.sp_model.encode(stem + v) + [self.eos_id]
+                for v in self._mapped(split, answer_mapping, answer)]
+        return seqs, len(seqs[0]) - 4, video_start, prefix_i, prefix_i + len(dialogue)
+
+    def encode_dvaq(self, text=None, max_feats: int = 10, split: str = "train", answer_mapping=None, answer=None):
+        head = [self.bos_id] + self.sp_model.encode(self._INSTR_D["vaq"] + "Video:")
+        video_start = len(head)
+        prefix_i = video_start + max_feats + 1
+        dialogue = self.sp_model.encode(text["d_text"])
+        stem, q = text["o_text"] + text["a_text"], text["q_text"].strip()
+        seqs = [head + [-2] * max_feats + [self.nl_id] + dialogue + self.sp_model.encode(stem + v + "\n" + q) + [self.eos_id]
+                for v in self._mapped(split, answer_mapping, answer)]
+        return seqs, seqs[0].index(self.q_token_id) + 2, video_start, prefix_i, prefix_i + len(dialogue)
+
+    def encode_dqav(self, text=None, max_feats: int = 10, max_seq_len: int = 128, split: str = "train", answer_mapping=None, answer=None):
+        head = [self.bos_id] + self.sp_model.encode(self._INSTR_D["qav"])
+        dialogue = self.sp_model.encode(text["d_text"])
+        stem = text["q_text"] + text["o_text"] + text["a_text"]
+        seqs = [head + dialogue + self.sp_model.encode(stem + v + "\n" + "Video:") + [-2] * max_feats + [self.eos_id]
+                for v in self._mapped(split, answer_mapping, answer)]
+        return seqs, len(seqs[0]) - max_feats - 1, len(head), len(head) + len(dialogue)
 
 
 class Tokenizer(PromptBuilder):

@@ -269,6 +269,25 @@ def synthetic_generation_batch(bsz: int, seqlen: int, vocab: int, a_token_id: in
     }
 
 
+def synthetic_dialogue_texts(n: int, n_options: int = 5, seed: int = 0, long_every: int = 2):
+    """TVQA-style prompt pieces with a subtitle dialogue (`dataloader/tvqa.py:36-58`): every `long_every`-th sample has a dialogue long
+    enough to overflow a 128-token sequence (the dialogue-aware truncation path), one sample has no dialogue at all."""
+    import random
+    rng = random.Random(seed)
+    words = ["sheldon", "door", "coffee", "why", "because", "leonard", "angry", "phone", "left", "room", "said", "never", "again", "ok"]
+    mapping = {i: f"({chr(65 + i)})" for i in range(n_options)}
+    out = []
+    for k in range(n):
+        question = " ".join(rng.choice(words) for _ in range(rng.randint(4, 9))).capitalize() + "?"
+        options = [" ".join(rng.choice(words) for _ in range(rng.randint(1, 4))) for _ in range(n_options)]
+        n_d = 0 if k == n - 1 else (rng.randint(120, 200) if k % long_every == 0 else rng.randint(5, 30))
+        d_text = ("Dialogue: " + " ".join(rng.choice(words) for _ in range(n_d)) + "\n") if n_d else ""
+        o_text = "Choices: \n" + "".join(f"{mapping[i]} {options[i]}\n" for i in range(n_options))
+        out.append(dict(text={"q_text": f"Question: {question}\n", "o_text": o_text, "a_text": "Answer: The answer is ", "d_text": d_text,
+                              "options": options}, answer=rng.randrange(n_options), options=options))
+    return out, mapping
+
+
 class HashSentencePiece:
     """Deterministic stand-in for `SentencePieceProcessor.encode` (no `tokenizer.model` exists offline): words and
     punctuation marks hash to ids in [100, n_words); the pieces 'Video', 'Question', 'Answer' map to the ids the

@@ -16,11 +16,12 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from flipped_vqa_b200.synthetic import hash_tokenizer, synthetic_qa_texts  # noqa: E402
+from flipped_vqa_b200.synthetic import hash_tokenizer, synthetic_dialogue_texts, synthetic_qa_texts  # noqa: E402
 
 REF = os.environ.get("FVQA_REFERENCE_ROOT", "/root/reference")
 CASES = [("train", False), ("val", False), ("train", True), ("val", True)]
 N, S, F = 3, 96, 10
+SUB_CASES, SUB_N, SUB_S = ("train", "val"), 4, 128
 
 
 def main():
@@ -56,6 +57,20 @@ def main():
         out[f"{k}/video_len"] = batch["video_len"].numpy()
         out[f"{k}/answer"] = batch["answer"].numpy()
         out[f"{k}/qtype"] = batch["qtype"].numpy()
+    # --sub (TVQA / VLEP): dialogue prompt builders + dialogue-aware overflow handling, `dataloader/tvqa.py:75-160`
+    tvqa = importlib.import_module("dataloader.tvqa")
+    for ci, split in enumerate(SUB_CASES):
+        tok = hash_tokenizer(ref_tok.Tokenizer)
+        ds = object.__new__(tvqa.TVQA)                       # no files: only the token path is exercised
+        ds.max_seq_len, ds.max_feats, ds.sub, ds.split, ds.tokenizer = SUB_S, F, True, split, tok
+        samples, mapping = synthetic_dialogue_texts(SUB_N, seed=40 + ci)
+        ds.answer_mapping = mapping
+        for i, smp in enumerate(samples):
+            text_id, label, video_start, video_index, label_mask = ds._get_text_token(smp["text"], smp["answer"])
+            for name, dct in (("text_id", text_id), ("label", label), ("video_index", video_index), ("label_mask", label_mask)):
+                for t in ("vqa", "vaq", "qav"):
+                    out[f"sub{ci}/{i}/{name}/{t}"] = dct[t].numpy()
+            out[f"sub{ci}/{i}/video_start"] = np.asarray([video_start[t] for t in ("vqa", "vaq", "qav")])
     path = os.path.join(ROOT, "tests", "golden", "collate_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, len(out), "arrays")

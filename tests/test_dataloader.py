@@ -120,3 +120,25 @@ def test_planned_loader_worker_stops_when_the_consumer_leaves():
     import pytest
     with pytest.raises(RuntimeError, match="loader failed"):
         list(PlannedLoader(_Boom(), _Model()))
+
+
+@pytest.mark.parametrize("ci,split", [(0, "train"), (1, "val")])
+def test_sub_dialogue_prompts_and_overflow_match_reference(ci, split):
+    """`--sub` (BASELINE.json configs[4]: TVQA with subtitles): `encode_dvqa / encode_dvaq / encode_dqav` (`llama/tokenizer.py:218-302`)
+    and the dialogue-aware overflow handling + labels of `TVQA._get_text_token` (`dataloader/tvqa.py:75-160`) against golden vectors
+    from the unmodified reference: samples with a short dialogue, a dialogue that overflows max_seq_len, and no dialogue."""
+    from flipped_vqa_b200.synthetic import synthetic_dialogue_texts
+    g = np.load(GOLDEN)
+    tok = hash_tokenizer(Tokenizer)
+    samples, mapping = synthetic_dialogue_texts(4, seed=40 + ci)
+    overflowed = 0
+    for i, smp in enumerate(samples):
+        t = D.encode_sample_sub(tok, smp["text"], smp["answer"], mapping, split, 128, F)
+        for name in ("text_id", "label", "video_index", "label_mask"):
+            for task in ("vqa", "vaq", "qav"):
+                ref = g[f"sub{ci}/{i}/{name}/{task}"]
+                got = t[name][task].numpy()
+                assert got.shape == ref.shape and got.dtype == ref.dtype and np.array_equal(got, ref), (i, name, task)
+        assert [t["video_start"][k] for k in ("vqa", "vaq", "qav")] == g[f"sub{ci}/{i}/video_start"].tolist()
+        overflowed += int(len(tok.encode_dvqa(text=smp["text"], max_feats=F, split=split, answer_mapping=mapping, answer=smp["answer"])[0][0]) > 128)
+    assert overflowed >= 1                       # the dialogue-cutting branch really ran
