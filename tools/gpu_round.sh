@@ -19,7 +19,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --log-file $OUT/launches_$TAG.csv $BENCH1 > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list exit $?"
 python tools/attn_bench.py > $OUT/attn_bench_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16|attn_|rmsnorm_bwd" -s 24 -c 6 \
+ncu --set full --clock-control none --import-source on -k regex:"gemm_nt|attn_|rmsnorm_bwd" -s 24 -c 6 \
     -f -o $OUT/prof_$TAG python tools/attn_bench.py > $OUT/ncu_full_$TAG.log 2>&1
 echo "ncu full exit $?"
 cat $OUT/attn_bench_$TAG.log
