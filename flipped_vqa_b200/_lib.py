@@ -54,6 +54,7 @@ _SIGNATURES = {
     "fvqa_gemm_debug_l2_hints": [_i],
     "fvqa_gemm_debug_mixed_a": [_i],
     "fvqa_attn_debug_use_tc": [_i],
+    "fvqa_debug_pdl": [_i],
     "fvqa_attn_uses_tc": [_i, _i, _i],
     "fvqa_attn_fwd": [_p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p],
     "fvqa_attn_bwd_ws_bytes": [_i, _i, _i, _i, _i],

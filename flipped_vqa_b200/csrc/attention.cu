@@ -748,6 +748,8 @@ __global__ void __launch_bounds__(256) attn_bwd_reduce_kernel(const float* __res
                                                               float* __restrict__ dgate1, float* __restrict__ dgate2, int n_seq,
                                                               int H, int hd, int A, int qtiles, int n_akv) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int h = blockIdx.x, a = blockIdx.y;
   const int D = H * hd;
   if (a < A) {
@@ -885,6 +887,7 @@ extern "C" int fvqa_attn_bwd(const fvqa_h16* qkv, const fvqa_h16* akv, int akv_l
   }
   rc = check_launch("attn_bwd_dkv");
   if (rc) return rc;
-  attn_bwd_reduce_kernel<<<dim3(H, A + 1), 256, 0, s>>>(p.ws_akv, p.ws_gate, gate1, dakv, dgate1, dgate2, n_seq, H, hd, A, p.qblocks, n_akv);
+  launch_k(attn_bwd_reduce_kernel, dim3(H, A + 1), dim3(256), 0, s, static_cast<const float*>(p.ws_akv), static_cast<const float*>(p.ws_gate), gate1, dakv,
+           dgate1, dgate2, n_seq, H, hd, A, p.qblocks, n_akv);
   return check_launch("attn_bwd_reduce");
 }

@@ -58,10 +58,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tmem_alloc(holder, 256);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + F_BAR + 32);
+  pdl_wait();                                          // set-up above overlaps the previous kernel's tail
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -281,10 +283,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tmem_alloc(holder, 512);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + B_BAR + 32);
+  pdl_wait();
   constexpr uint32_t T_S = 0, T_DP = 128, T_DV = 256, T_DK = 384, T_SA = 256, T_DPA = 272, T_DQ = 0, T_DKA = 128;
 
   auto kmaj = [&](int off, int blk, int ks) {
@@ -564,7 +568,7 @@ int attn_fwd_tc(const AttnParams& p, cudaStream_t stream) {
   const int D = p.H * 128;
   rc = get_tmap_seq(p.out, p.n_seq, p.S, D, D, 128, &to);
   if (rc) return rc;
-  attn_fwd_tc_kernel<<<dim3(p.H, p.n_seq), FW_THREADS, F_SMEM, stream>>>(tq, ta, to, p);
+  launch_k(attn_fwd_tc_kernel, dim3(p.H, p.n_seq), dim3(FW_THREADS), F_SMEM, stream, tq, ta, to, p);
   return check_launch("attn_fwd_tc");
 }
 
@@ -579,7 +583,7 @@ int attn_bwd_tc(const AttnParams& p, cudaStream_t stream) {
   if (rc) return rc;
   rc = get_tmap_seq(p.dqkv, p.n_seq, p.S, 3 * D, 3 * D, 128, &tg);
   if (rc) return rc;
-  attn_bwd_tc_kernel<<<dim3(p.H, p.n_seq), BW_THREADS, B_SMEM, stream>>>(tq, ta, td, tg, p);
+  launch_k(attn_bwd_tc_kernel, dim3(p.H, p.n_seq), dim3(BW_THREADS), B_SMEM, stream, tq, ta, td, tg, p);
   return check_launch("attn_bwd_tc");
 }
 

@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_fwd_kernel(
     const float* __restrict__ x, const int32_t* __restrict__ idx, const h16* __restrict__ w,
     h16* __restrict__ y, float* __restrict__ rstd_out, int dim, float eps) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int nvec = dim >> 3;
   long src = row;
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(NORM_THREADS) rmsnorm_bwd_kernel(
     const h16* __restrict__ w, const float* __restrict__ rstd_in, const float* __restrict__ dres,
     float* __restrict__ dx, h16* __restrict__ dx_h16, int dim) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const int nvec = dim >> 3;
   long src = row;
@@ -179,6 +183,8 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const h16* __restrict__
 }
 
 __global__ void f32_to_h16_kernel(const float* __restrict__ src, h16* __restrict__ dst, long n) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long>(gridDim.x) * blockDim.x)
     dst[i] = f2h(src[i]);
@@ -232,8 +238,8 @@ extern "C" int fvqa_rmsnorm_fwd(const float* x, const fvqa_h16* w, fvqa_h16* y, 
                "rmsnorm: dim %d must be a multiple of 8 and <= %d", dim, 8 * NORM_THREADS * NORM_MAXV);
   if (rows <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_fwd_kernel, dim);
-  kfn<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, nullptr, reinterpret_cast<const h16*>(w), reinterpret_cast<h16*>(y), rstd, dim, eps);
+  launch_k(kfn, dim3(rows), dim3(NORM_THREADS), 0, static_cast<cudaStream_t>(stream), x, static_cast<const int32_t*>(nullptr),
+           reinterpret_cast<const h16*>(w), reinterpret_cast<h16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_fwd");
 }
 
@@ -243,8 +249,8 @@ extern "C" int fvqa_rmsnorm_gather_fwd(const float* x, const int32_t* idx, const
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_gather: idx is null");
   if (rows_out <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_fwd_kernel, dim);
-  kfn<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, idx, reinterpret_cast<const h16*>(w), reinterpret_cast<h16*>(y), rstd, dim, eps);
+  launch_k(kfn, dim3(rows_out), dim3(NORM_THREADS), 0, static_cast<cudaStream_t>(stream), x, idx, reinterpret_cast<const h16*>(w),
+           reinterpret_cast<h16*>(y), rstd, dim, eps);
   return check_launch("rmsnorm_gather_fwd");
 }
 
@@ -253,9 +259,8 @@ extern "C" int fvqa_rmsnorm_bwd(const fvqa_h16* dy, const float* x, const fvqa_h
   FVQA_REQUIRE(dim % 8 == 0 && dim <= 8 * NORM_THREADS * NORM_MAXV, FVQA_ERR_UNSUPPORTED, "rmsnorm_bwd: bad dim %d", dim);
   if (rows <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_bwd_kernel, dim);
-  kfn<<<rows, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const h16*>(dy), x, nullptr, reinterpret_cast<const h16*>(w), rstd, dres, dx,
-      reinterpret_cast<h16*>(dx_h16), dim);
+  launch_k(kfn, dim3(rows), dim3(NORM_THREADS), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const h16*>(dy), x,
+           static_cast<const int32_t*>(nullptr), reinterpret_cast<const h16*>(w), rstd, dres, dx, reinterpret_cast<h16*>(dx_h16), dim);
   return check_launch("rmsnorm_bwd");
 }
 
@@ -265,9 +270,8 @@ extern "C" int fvqa_rmsnorm_scatter_bwd(const fvqa_h16* dy, const float* x, cons
   FVQA_REQUIRE(idx != nullptr, FVQA_ERR_INVALID_ARG, "rmsnorm_scatter_bwd: idx is null");
   if (rows_out <= 0) return FVQA_OK;
   auto kfn = FVQA_NORM_PICK(rmsnorm_bwd_kernel, dim);
-  kfn<<<rows_out, NORM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const h16*>(dy), x, idx, reinterpret_cast<const h16*>(w), rstd, nullptr, dx,
-      reinterpret_cast<h16*>(dx_h16), dim);
+  launch_k(kfn, dim3(rows_out), dim3(NORM_THREADS), 0, static_cast<cudaStream_t>(stream), reinterpret_cast<const h16*>(dy), x, idx,
+           reinterpret_cast<const h16*>(w), rstd, static_cast<const float*>(nullptr), dx, reinterpret_cast<h16*>(dx_h16), dim);
   return check_launch("rmsnorm_scatter_bwd");
 }
 
@@ -291,7 +295,8 @@ extern "C" int fvqa_swiglu_bwd(const fvqa_h16* dc, const fvqa_h16* g, fvqa_h16* 
 
 extern "C" int fvqa_f32_to_h16(const float* src, fvqa_h16* dst, int64_t n, void* stream) {
   if (n <= 0) return FVQA_OK;
-  f32_to_h16_kernel<<<elementwise_grid(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<h16*>(dst), n);
+  launch_k(f32_to_h16_kernel, dim3(elementwise_grid(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, reinterpret_cast<h16*>(dst),
+           static_cast<long>(n));
   return check_launch("f32_to_h16");
 }
 

@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(SK_THREADS) gemm_skinny_kernel(const h16* __re
                                                                  void* __restrict__ C, long strideC, int ldc, int M, int N, int K,
                                                                  const SkinnyEpi epi) {
   __shared__ float red[SK_WARPS][16][8 * NT + 1];
+  pdl_launch_dependents();
+  pdl_wait();
   {
     const int grp = blockIdx.y;
     A += grp * strideA;
@@ -136,8 +138,8 @@ static int skinny_launch(const h16* A, long strideA, int lda, const h16* B, cons
   const int cols = 8 * nt;
   const dim3 grid((N + cols - 1) / cols, groups);
 #define FVQA_SK(NT_)                                                                                                                \
-  if (out_fp32) gemm_skinny_kernel<NT_, true><<<grid, SK_THREADS, 0, stream>>>(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, epi); \
-  else gemm_skinny_kernel<NT_, false><<<grid, SK_THREADS, 0, stream>>>(A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, epi);
+  if (out_fp32) launch_k(gemm_skinny_kernel<NT_, true>, grid, dim3(SK_THREADS), 0, stream, A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, epi); \
+  else launch_k(gemm_skinny_kernel<NT_, false>, grid, dim3(SK_THREADS), 0, stream, A, strideA, lda, B, Bptrs, ldb, C, strideC, ldc, M, N, K, epi);
   if (nt == 4) { FVQA_SK(4) } else if (nt == 2) { FVQA_SK(2) } else { FVQA_SK(1) }
 #undef FVQA_SK
   return check_launch("gemm_skinny");

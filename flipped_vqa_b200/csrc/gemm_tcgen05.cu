@@ -158,10 +158,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     tmem_alloc(holder, Cfg::kTmemCols);
     tmem_relinquish();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -325,10 +327,12 @@ gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tmem_alloc_pair(holder, 512);
     tmem_relinquish_pair();
   }
+  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();               // barrier inits + TMEM allocation visible to both CTAs
   tc_fence_after();
   const uint32_t tmem_base = *holder_ptr;
+  pdl_wait();                       // everything above overlapped the previous kernel's tail; from here on global memory is touched
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -828,7 +832,8 @@ static int launch_gemm_pair(const h16* A, int lda, const h16* B, int ldb, void* 
   const int tiles_n = (EPI == EPI_SWIGLU_FWD) ? epi.hid / 128 : (N + bn - 1) / bn;
   const int tiles = ((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * tiles_n;
   const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
-  gemm_nt_pair_kernel<OUT_F32, EPI><<<2 * pairs, g_pair_threads.load(), smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, g_l2_hints | (g_mixed_a << 1));
+  launch_k(gemm_nt_pair_kernel<OUT_F32, EPI, false>, dim3(2 * pairs), dim3(g_pair_threads.load()), smem, stream, ta, tb, C, epi, M, N, K, ldc, bn, stages,
+           g_l2_hints | (g_mixed_a << 1));
   return check_launch("gemm_nt_pair");
 }
 
@@ -850,7 +855,7 @@ static int launch_gemm_quad(const h16* A, int lda, const h16* B, int ldb, void* 
   const int clusters = units < g_quad_clusters ? units : g_quad_clusters;
   // 384 threads = two epilogue warps per TMEM lane quadrant: neutral for the pair kernel, but with the multicast operand stream the
   // faster accumulator drain pays (K = 11008 burst 191.7 vs 199.0 us with four warps; in-step A/B -0.5 % vs 0.0 %)
-  gemm_nt_pair_kernel<OUT_F32, EPI_PLAIN, true><<<4 * clusters, PAIR_THREADS, smem, stream>>>(ta, tb, C, epi, M, N, K, ldc, bn, stages, 0);
+  launch_k(gemm_nt_pair_kernel<OUT_F32, EPI_PLAIN, true>, dim3(4 * clusters), dim3(PAIR_THREADS), smem, stream, ta, tb, C, epi, M, N, K, ldc, bn, stages, 0);
   return check_launch("gemm_nt_quad");
 }
 // Used when the pair schedule would end in a clearly partial wave and the cluster schedule does not (N = 4096 outputs of a

@@ -33,6 +33,11 @@ int fvqa_gemm_debug_l2_hints(int on);
  * Measured on B200: illegal instruction (tools/mixed_umma_probe.py) - which is why the operand format is per build. */
 int fvqa_gemm_debug_mixed_a(int on);
 
+/* Tuning hook: 1 (default) = the hot kernels (GEMMs, attention, norms) are launched with programmatic dependent launch, so the next
+ * kernel's prologue overlaps the previous kernel's last wave; 0 = ordinary stream-ordered launches. FVQA_PDL=0 in the environment sets
+ * 0 at fvqa_init(). Returns the previous setting. */
+int fvqa_debug_pdl(int on);
+
 /* Test hook: 0 forces the mma.sync kernels, 1 (default) lets S <= 128, hd = 128 take the tcgen05 path. */
 int fvqa_attn_debug_use_tc(int on);
 
