@@ -46,6 +46,8 @@ _SIGNATURES = {
     "fvqa_gemm_skinny_grouped": [_p, _i64, _i, _p, _i, _p, _i64, _i, _i, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_fwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_swiglu_bwd": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
+    "fvqa_gemm_nn": [_p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
+    "fvqa_gemm_swiglu_bwd_nn": [_p, _i, _p, _i, _p, _i, _p, _i, _i, _i, _i, _p],
     "fvqa_gemm_debug_force_bn": [_i],
     "fvqa_gemm_debug_skinny_nt": [_i],
     "fvqa_gemm_debug_quad": [_i],

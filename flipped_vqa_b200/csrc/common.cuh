@@ -385,6 +385,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                      // SWIZZLE_128B
   return d;
 }
+// MN-major, 128-byte swizzle (the operand's M/N dimension is the contiguous one): 64 MN-elements per 128-byte row, 8-row (K) groups
+// 1024 B apart (SBO), 64-element MN blocks `lbo_bytes` apart. This is what a TMA box [k rows][64 columns] of a row-major [K, N]
+// matrix looks like in shared memory: B of C = A . B without a transposed copy.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor: h16 x h16 -> fp32 (a/b format fields: 0 = fp16, 1 = bf16), A and B K-major, dense.
 __host__ __device__ constexpr uint32_t umma_idesc_h16(int m, int n) {
   return (1u << 4) | (FVQA_UMMA_FMT << 7) | (FVQA_UMMA_FMT << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);

@@ -276,7 +276,10 @@ __host__ __device__ constexpr int pair_stage_bytes(int bn) { return GEMM_BM * GE
 // what cuBLAS's 2x2-cluster kernels do on the N = 4096 shapes). A stage is free once BOTH pairs' MMAs have consumed it
 // (the partner pair writes into it), hence two arrivals on empty[s], committed to all four CTAs. Only 33 four-CTA
 // clusters fit the chip (132 of 148 SMs, profiles/r1_cluster_occupancy.txt).
-template <bool OUT_F32, int EPI, bool QUAD = false>
+// B_MN: B is given as a row-major [K, N] matrix (N contiguous) and read as an MN-major UMMA operand: C = A . B, i.e. the dX-only
+// backward dX = dY . W straight from the [out, in] weight the forward uses - no transposed weight copy (13.5 GB at 7B). Per k-block
+// each CTA TMA-loads (BN / 2) / 64 boxes of [64 k rows][64 columns] (same bytes as the K-major tile); BN must be a multiple of 128.
+template <bool OUT_F32, int EPI, bool QUAD = false, bool B_MN = false>
 __global__ void __cluster_dims__(QUAD ? 4 : 2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          void* __restrict__ Cout, const GemmEpi epi, int M, int N, int K, int ldc, int BN, int stages, int l2_hints) {
@@ -355,13 +358,21 @@ gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             constexpr uint32_t kHalf = (GEMM_BM / 2) * GEMM_BK * 2;
             tma_load_2d_pair_mc(sa + cq * kHalf, &tmap_a, lfull, kb * GEMM_BK, m0 + cq * (GEMM_BM / 2),
                                 static_cast<uint16_t>((1u << crank) | (1u << (crank ^ 2u))));
-            tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+            if constexpr (B_MN) {
+              for (int j = 0; j < (BN >> 7); ++j) tma_load_2d_pair(sb + j * 8192, &tmap_b, lfull, n0 + j * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+            }
           } else if (l2_hints & 1) {      // weights stream through once per wave; the activation operand is re-read by every tile column
             tma_load_2d_pair_hint(sa, &tmap_a, lfull, kb * GEMM_BK, m0, L2_EVICT_LAST);
             tma_load_2d_pair_hint(sb, &tmap_b, lfull, kb * GEMM_BK, n0, L2_EVICT_FIRST);
           } else {
             tma_load_2d_pair(sa, &tmap_a, lfull, kb * GEMM_BK, m0);
-            tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+            if constexpr (B_MN) {
+              for (int j = 0; j < (BN >> 7); ++j) tma_load_2d_pair(sb + j * 8192, &tmap_b, lfull, n0 + j * 64, kb * GEMM_BK);
+            } else {
+              tma_load_2d_pair(sb, &tmap_b, lfull, kb * GEMM_BK, n0);
+            }
           }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
@@ -371,7 +382,7 @@ gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
       // l2_hints bit 1 (probe, fvqa_debug_gemm_mixed_a): A is read in the OTHER 16-bit format than B (mixed fp16 x bf16 MMA)
-      const uint32_t idesc = umma_idesc_h16(2 * GEMM_BM, BN) ^ ((l2_hints & 2) ? (1u << 7) : 0u);
+      const uint32_t idesc = (umma_idesc_h16(2 * GEMM_BM, BN) ^ ((l2_hints & 2) ? (1u << 7) : 0u)) | (B_MN ? (1u << 16) : 0u);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -386,10 +397,11 @@ gemm_nt_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t sa = smem_base + stage * stage_bytes;
           const uint32_t sb = sa + GEMM_BM * GEMM_BK * 2;
           const uint64_t adesc = umma_desc_k_sw128(sa);
-          const uint64_t bdesc = umma_desc_k_sw128(sb);
+          const uint64_t bdesc = B_MN ? umma_desc_mn_sw128(sb, 8192) : umma_desc_k_sw128(sb);
 #pragma unroll
           for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-            umma_h16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+            // K-major: +16 elements = 32 B inside the swizzle row; MN-major: +16 k-rows of 128 B = 2048 B (16-byte units)
+            umma_h16_ss_pair(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(B_MN ? 128 * k : 2 * k), idesc,
                               (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit_pair_mask(empty_bar(stage), QUAD ? 0xF : 0x3);                       // QUAD: the partner pair writes into this stage too
@@ -687,6 +699,15 @@ int gemm_init() {
   FVQA_SET_PAIR(false, EPI_SWIGLU_FWD)
   FVQA_SET_PAIR(false, EPI_SWIGLU_BWD)
 #undef FVQA_SET_PAIR
+  {
+    auto k1 = gemm_nt_pair_kernel<false, EPI_PLAIN, false, true>;
+    auto k2 = gemm_nt_pair_kernel<false, EPI_SWIGLU_BWD, false, true>;
+    auto k3 = gemm_nt_pair_kernel<false, EPI_PLAIN, true, true>;
+    e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_LIMIT);
+    FVQA_REQUIRE(e == cudaSuccess, FVQA_ERR_CUDA, "cudaFuncSetAttribute(gemm nn): %s", cudaGetErrorString(e));
+  }
   // 2x2-cluster (QUAD) variants of the plain-epilogue kernel: opt-in shared memory, and how many 4-CTA clusters fit the chip
   {
     auto kq16 = gemm_nt_pair_kernel<false, EPI_PLAIN, true>;
@@ -835,6 +856,40 @@ static int launch_gemm_pair(const h16* A, int lda, const h16* B, int ldb, void* 
   launch_k(gemm_nt_pair_kernel<OUT_F32, EPI, false>, dim3(2 * pairs), dim3(g_pair_threads.load()), smem, stream, ta, tb, C, epi, M, N, K, ldc, bn, stages,
            g_l2_hints | (g_mixed_a << 1));
   return check_launch("gemm_nt_pair");
+}
+
+// C = A . B with B row-major [K, N] (see B_MN): h16 out, plain or SwiGLU-backward epilogue, BN = 256; the 2x2-cluster variant where
+// the pair schedule would end in a partial wave (same rule as the NT launcher).
+static bool use_quad(int M, int N);
+template <int EPI>
+static int launch_gemm_nn(const h16* A, int lda, const h16* B, int ldb, void* C, int ldc, const GemmEpi& epi, int M, int N, int K,
+                          cudaStream_t stream) {
+  constexpr int bn = 256;
+  const bool quad = (EPI == EPI_PLAIN) && use_quad(M, N);
+  CUtensorMap ta, tb;
+  int rc = get_tmap(A, M, K, lda, quad ? GEMM_BM / 2 : GEMM_BM, &ta);
+  if (rc) return rc;
+  rc = get_tmap(B, K, N, ldb, GEMM_BK, &tb);                     // boxes of [64 k rows][64 columns]
+  if (rc) return rc;
+  const int stage_bytes = pair_stage_bytes(bn);
+  int stages = (PAIR_SMEM_LIMIT - 1024 - PAIR_BAR_BYTES) / stage_bytes;
+  if (stages > PAIR_MAX_STAGES) stages = PAIR_MAX_STAGES;
+  const int smem = stages * stage_bytes + PAIR_BAR_BYTES + 1024;
+  const int tiles_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), tiles_n = (N + bn - 1) / bn;
+  if (quad) {
+    if constexpr (EPI == EPI_PLAIN) {
+      const int units = tiles_m * (N / (2 * bn));
+      const int clusters = units < g_quad_clusters ? units : g_quad_clusters;
+      launch_k(gemm_nt_pair_kernel<false, EPI_PLAIN, true, true>, dim3(4 * clusters), dim3(PAIR_THREADS), smem, stream, ta, tb, C, epi, M, N, K, ldc,
+               bn, stages, 0);
+      return check_launch("gemm_nn_quad");
+    }
+  }
+  const int tiles = tiles_m * tiles_n;
+  const int pairs = tiles < g_num_sms / 2 ? tiles : g_num_sms / 2;
+  launch_k(gemm_nt_pair_kernel<false, EPI, false, true>, dim3(2 * pairs), dim3(g_pair_threads.load()), smem, stream, ta, tb, C, epi, M, N, K, ldc, bn,
+           stages, 0);
+  return check_launch("gemm_nn_pair");
 }
 
 // 2x2-cluster multicast variant (plain epilogue, BN = 256, an even number of column tiles)
@@ -1044,6 +1099,36 @@ extern "C" int fvqa_gemm_swiglu_bwd(const fvqa_h16* dY, int ldy, const fvqa_h16*
   GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, const_cast<fvqa_h16*>(G), ldg, hid};
   return launch_gemm_pair<false, EPI_SWIGLU_BWD>(reinterpret_cast<const h16*>(dY), ldy, reinterpret_cast<const h16*>(W2t), ldw, dG, lddg, epi,
                                                  M, hid, K, 256, static_cast<cudaStream_t>(stream));
+}
+
+/* C[M,N] = A[M,K] . B[K,N] with B ROW-MAJOR [K, N] (leading dimension ldb >= N): the dX-only backward dX = dY . W read straight from
+ * the [out, in] weight of the forward pass (no transposed copy). h16 out. K % 64 == 0, N % 8 == 0. */
+extern "C" int fvqa_gemm_nn(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb, fvqa_h16* C, int ldc, int M, int N, int K, void* stream) {
+  FVQA_REQUIRE(g_encode != nullptr, FVQA_ERR_INVALID_ARG, "fvqa_init() has not been called");
+  FVQA_REQUIRE(M > 0 && N > 0 && K > 0, FVQA_ERR_INVALID_ARG, "gemm_nn: empty problem M=%d N=%d K=%d", M, N, K);
+  FVQA_REQUIRE(K % GEMM_BK == 0 && N % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldc % 8 == 0 && lda >= K && ldb >= N && ldc >= N,
+               FVQA_ERR_UNSUPPORTED, "gemm_nn: K=%d must be a multiple of 64, N / lda / ldb / ldc multiples of 8 (N=%d lda=%d ldb=%d ldc=%d)", K, N, lda,
+               ldb, ldc);
+  FVQA_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0, FVQA_ERR_INVALID_ARG,
+               "gemm_nn: pointers must be 16-byte aligned");
+  GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, nullptr, 0, 0};
+  return launch_gemm_nn<EPI_PLAIN>(reinterpret_cast<const h16*>(A), lda, reinterpret_cast<const h16*>(B), ldb, C, ldc, epi, M, N, K,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+/* fvqa_gemm_swiglu_bwd with W2 given as the forward's [K = d, hid] row-major weight instead of its transposed copy:
+ * dG[M, 2*hid] = swiglu'(G) applied to dc = dY[M,K] . W2[K, hid]. hid % 32 == 0. */
+extern "C" int fvqa_gemm_swiglu_bwd_nn(const fvqa_h16* dY, int ldy, const fvqa_h16* W2, int ldw, const fvqa_h16* G, int ldg, fvqa_h16* dG,
+                                       int lddg, int M, int hid, int K, void* stream) {
+  FVQA_REQUIRE(g_encode != nullptr, FVQA_ERR_INVALID_ARG, "fvqa_init() has not been called");
+  FVQA_REQUIRE(M > 0 && hid > 0 && K > 0 && K % GEMM_BK == 0 && hid % 32 == 0 && ldy % 8 == 0 && ldw % 8 == 0 && ldg % 8 == 0 && lddg % 8 == 0 &&
+                   ldy >= K && ldw >= hid && ldg >= 2 * hid && lddg >= 2 * hid && G != nullptr,
+               FVQA_ERR_UNSUPPORTED, "gemm_swiglu_bwd_nn: M=%d hid=%d K=%d ldy=%d ldw=%d ldg=%d lddg=%d", M, hid, K, ldy, ldw, ldg, lddg);
+  FVQA_REQUIRE(((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(G) | reinterpret_cast<uintptr_t>(dG)) & 15) == 0,
+               FVQA_ERR_INVALID_ARG, "gemm_swiglu_bwd_nn: pointers must be 16-byte aligned");
+  GemmEpi epi{nullptr, 0, nullptr, nullptr, 0, 0, 1, const_cast<fvqa_h16*>(G), ldg, hid};
+  return launch_gemm_nn<EPI_SWIGLU_BWD>(reinterpret_cast<const h16*>(dY), ldy, reinterpret_cast<const h16*>(W2), ldw, dG, lddg, epi, M, hid, K,
+                                        static_cast<cudaStream_t>(stream));
 }
 
 /* Tuning hook: 1 = TMA loads of the CTA-pair kernel carry L2 eviction hints (A evict_last, B evict_first). */

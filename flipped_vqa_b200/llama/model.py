@@ -16,6 +16,7 @@ There is no CPU path: calling forward without an sm_100 GPU raises.
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -161,7 +162,7 @@ class _StepFn(torch.autograd.Function):
         gb = model._grad_buffers
         sync = model.grad_sync
         model._engine.backward(sv, gscale, model._run_weights, model._output_t, model.norm.weight, ctx.gates[0], ctx.gates[1], gb,
-                               on_layer_done=(sync.layer_done if sync is not None else None))
+                               on_layer_done=(sync.layer_done if sync is not None else None), out_w=model.output.weight.data)
         if sync is not None:
             sync.finish()
         flat = gb.flat.clone()                              # autograd may keep what we return: never alias the work buffer
@@ -230,6 +231,9 @@ class Transformer(nn.Module):
         self.last_plan: Optional[BatchPlan] = None
         self._pinned: Optional[PinnedPool] = None
         self.share_option_prefix = True                     # validation: shared-prefix option scoring (step.OptionPlan)
+        # frozen weights held ONCE: the dX-only backward reads W [out, in] itself as an MN-major tcgen05 operand (ops.gemm_nn) instead of
+        # a load-time transposed copy (-13.5 GB at 7B, -26 GB at 13B, half the load time). False = the round-1 layout (A/B, tests).
+        self.weights_once = os.environ.get("FVQA_WEIGHTS_ONCE", "1") != "0"
         self._akv_pre = None                                # adapter K|V enqueued ahead of host planning (forward(data))
 
     # ------------------------------------------------------------------ weight layout
@@ -280,12 +284,16 @@ class Transformer(nn.Module):
             blk._w2 = ff.w2.weight.data
         run = []
         for blk in self.run_layers():
-            run.append(LayerWeights(
-                wqkv=blk._wqkv, wqkv_t=blk._wqkv.t().contiguous(), wo=blk._wo, wo_t=blk._wo.t().contiguous(),
-                w13=blk._w13, w13_t=blk._w13.t().contiguous(), w2=blk._w2, w2_t=blk._w2.t().contiguous(),
-                attn_norm=blk.attention_norm.weight.data, ffn_norm=blk.ffn_norm.weight.data))
+            lw = LayerWeights(wqkv=blk._wqkv, wo=blk._wo, w13=blk._w13, w2=blk._w2,
+                              attn_norm=blk.attention_norm.weight.data, ffn_norm=blk.ffn_norm.weight.data)
+            if self.weights_once:          # dX GEMMs read the forward weights as MN-major operands; only [Wk; Wv]^T is copied (adapter gradient)
+                lw.wkv_t = blk._wqkv[d:].t().contiguous()
+            else:                          # round-1 layout: a transposed copy of every frozen weight (2 x 13.5 GB at 7B)
+                lw.wqkv_t, lw.wo_t = blk._wqkv.t().contiguous(), blk._wo.t().contiguous()
+                lw.w13_t, lw.w2_t = blk._w13.t().contiguous(), blk._w2.t().contiguous()
+            run.append(lw)
         self._run_weights = run
-        self._output_t = self.output.weight.data.t().contiguous()
+        self._output_t = None if self.weights_once else self.output.weight.data.t().contiguous()
         self._audio_f32 = {"audio_proj": self.audio_proj.weight.data.float().contiguous()} if hasattr(self, "audio_proj") else {}
         if self._engine is None:
             self._engine = StepEngine(d, self.params.n_heads, hid, self.params.vocab_size, self.adapter_len, self.max_feats,

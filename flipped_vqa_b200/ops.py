@@ -236,14 +236,47 @@ def gemm_swiglu_fwd(x: torch.Tensor, w13: torch.Tensor, g: Optional[torch.Tensor
 
 
 @_timed
-def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Optional[torch.Tensor] = None):
-    """dg = swiglu'(g) . (dy @ W2t^T): backward through w2 and the SwiGLU in one GEMM (dc never materialised)."""
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = a[M,K] @ b[K,N] with b ROW-MAJOR [K, N] (a forward weight [out = K, in = N]): dX = dY . W without a transposed
+    weight copy (MN-major tcgen05 B operand). h16 in / out."""
+    assert a.dtype == H16 and b.dtype == H16 and a.stride(-1) == 1 and b.stride(-1) == 1
+    M, K = a.shape
+    Kb, N = b.shape
+    assert K == Kb, (a.shape, b.shape)
+    out = torch.empty(M, N, dtype=H16, device=a.device) if out is None else out
+    assert out.dtype == H16 and out.stride(-1) == 1
+    tm = GEMM_TIMER
+    if tm is not None and tm.active:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(_lib.lib().fvqa_gemm_nn(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out), out.stride(0), M, N, K, stream()), "gemm_nn")
+    if tm is not None and tm.active:
+        e1.record()
+        tm.records.append((e0, e1, 2.0 * M * N * K, tm.tag))
+    return out
+
+
+@_timed
+def gemm_swiglu_bwd(dy: torch.Tensor, w2t: torch.Tensor, g: torch.Tensor, dg: Optional[torch.Tensor] = None, nn: bool = False):
+    """dg = swiglu'(g) . (dy @ W2t^T): backward through w2 and the SwiGLU in one GEMM (dc never materialised).
+    nn=True: `w2t` is the forward weight W2 [d, hid] itself (row-major [K, N]) instead of its transposed copy [hid, d]."""
     M, K = dy.shape
-    hid = w2t.shape[0]
+    hid = w2t.shape[1] if nn else w2t.shape[0]
     dg = torch.empty(M, 2 * hid, dtype=H16, device=dy.device) if dg is None else dg
     if hid % 32 != 0 or not FUSE_SWIGLU:
-        dc = gemm_nt(dy, w2t)
+        dc = gemm_nn(dy, w2t) if nn else gemm_nt(dy, w2t)
         return swiglu_bwd(dc, g, dg)
+    if nn:
+        tm = GEMM_TIMER
+        if tm is not None and tm.active:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        check(_lib.lib().fvqa_gemm_swiglu_bwd_nn(ptr(dy), dy.stride(0), ptr(w2t), w2t.stride(0), ptr(g), g.stride(0), ptr(dg), dg.stride(0),
+                                                 M, hid, K, stream()), "gemm_swiglu_bwd_nn")
+        if tm is not None and tm.active:
+            e1.record()
+            tm.records.append((e0, e1, 2.0 * M * hid * K, tm.tag))
+        return dg
     tm = GEMM_TIMER
     if tm is not None and tm.active:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

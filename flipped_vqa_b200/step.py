@@ -287,16 +287,23 @@ def _cpu(t):
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class LayerWeights:
+    """Frozen weights of one layer. `*_t` are load-time transposed copies for the K-major dX GEMMs; with `weights_once` (default) only
+    `wkv_t` exists - the [Wk; Wv] block the skinny adapter-gradient GEMM streams - and the dX GEMMs read `wqkv` / `wo` / `w13` / `w2`
+    themselves as MN-major operands (`ops.gemm_nn`)."""
     wqkv: torch.Tensor      # [3d, d]   rows: Wq | Wk | Wv
-    wqkv_t: torch.Tensor    # [d, 3d]
     wo: torch.Tensor        # [d, d]
-    wo_t: torch.Tensor
     w13: torch.Tensor       # [2*hid, d] rows: W1 | W3
-    w13_t: torch.Tensor     # [d, 2*hid]
     w2: torch.Tensor        # [d, hid]
-    w2_t: torch.Tensor      # [hid, d]
     attn_norm: torch.Tensor
     ffn_norm: torch.Tensor
+    wkv_t: Optional[torch.Tensor] = None      # [d, 2d] = [Wk; Wv]^T (weights_once)
+    wqkv_t: Optional[torch.Tensor] = None     # [d, 3d]
+    wo_t: Optional[torch.Tensor] = None
+    w13_t: Optional[torch.Tensor] = None      # [d, 2*hid]
+    w2_t: Optional[torch.Tensor] = None       # [hid, d]
+
+    def kv_t(self, d: int) -> torch.Tensor:
+        return self.wkv_t if self.wkv_t is not None else self.wqkv_t[:, d:]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -376,12 +383,12 @@ class StepEngine:
         (None when the shape is outside its range). Cached per packed-weight list; the weights are frozen."""
         if self.A > 16 or self.d % 256 != 0 or not layers:
             return None
-        key = (id(layers), layers[0].wqkv.data_ptr(), layers[-1].wqkv_t.data_ptr())
+        d = self.d
+        key = (id(layers), layers[0].wqkv.data_ptr(), layers[-1].kv_t(d).data_ptr())
         if self._tables is None or self._tables[0] != key:
-            d = self.d
             kv = torch.tensor([w.wqkv[d:].data_ptr() for w in layers], dtype=torch.int64, device=self.device)
-            kv_t = torch.tensor([w.wqkv_t[:, d:].data_ptr() for w in layers], dtype=torch.int64, device=self.device)
-            self._tables = (key, (kv, kv_t))
+            kv_t = torch.tensor([w.kv_t(d).data_ptr() for w in layers], dtype=torch.int64, device=self.device)
+            self._tables = (key, (kv, kv_t, layers[0].kv_t(d).stride(0)))
         return self._tables[1]
 
     # -------------------------------------------------------------------------------- forward
@@ -670,7 +677,7 @@ class StepEngine:
 
     # -------------------------------------------------------------------------------- backward
     def backward(self, sv: SavedStep, gscale: torch.Tensor, layers: List[LayerWeights], out_w_t, norm_w, gate1, gate2,
-                 grads: "GradBuffers", on_layer_done=None):
+                 grads: "GradBuffers", on_layer_done=None, out_w=None):
         """gscale: fp32 device tensor [3] = upstream gradients of (vqa, vaq, qav) losses.
         Fills `grads` (fp32): adapter [L*A, d], gate1/gate2 [L, H], visual [d, vdim], temporal [F, d]."""
         plan = sv.plan
@@ -692,6 +699,12 @@ class StepEngine:
         dx = torch.zeros(R, d, dtype=torch.float32, device=dev)
         dx_h = torch.zeros(R, d, dtype=H16, device=dev)
         gidx = {"vqa": 0, "vaq": 1, "qav": 2}
+        # dX = dY . W: from the forward weight itself (MN-major operand) when no transposed copy exists (`weights_once`)
+        def dgemm(dy, w_fwd, w_t, out=None):
+            return ops.gemm_nt(dy, w_t, out=out) if w_t is not None else ops.gemm_nn(dy, w_fwd, out=out)
+
+        def dswiglu(dy, w, gsaved, dg=None):
+            return ops.gemm_swiglu_bwd(dy, w.w2_t, gsaved, dg=dg) if w.w2_t is not None else ops.gemm_swiglu_bwd(dy, w.w2, gsaved, dg=dg, nn=True)
         inv_k = None
         if self.grad_scale_target > 0:
             gscale, inv_k = ops.grad_scale_prepare(gscale, self.grad_scale_target)
@@ -709,7 +722,7 @@ class StepEngine:
                     ops.ce_bwd(ce["logits"][off:off + n], plan.ce_tgt[off:off + n], ce["row_lse"][off:off + n],
                                gscale[gidx[k]:gidx[k] + 1], 1.0 / n, dlogits=dlogits[off:off + n])
                 off += n
-            dhn = ops.gemm_nt(dlogits, out_w_t)                                     # dH = dlogits . W_out
+            dhn = dgemm(dlogits, out_w, out_w_t)                                    # dH = dlogits . W_out
             ops.rmsnorm_scatter_bwd(dhn, x_final, ce_idx, norm_w, ce["rstd"], dx, dx_h)
         dvf_qav = None
         if sv.qav is not None:
@@ -739,11 +752,11 @@ class StepEngine:
                 ops.GEMM_TIMER.active, ops.GEMM_TIMER.tag = l in self.sample_layers, l
             if pruned and l == L - 1:
                 # compact rows through the FFN and wo of the last layer, then scatter d(attn out) and dh back to all rows
-                dg_c = ops.gemm_swiglu_bwd(dx_h, w.w2_t, sv.g[l])
-                dtmp_c = ops.gemm_nt(dg_c, w.w13_t)
+                dg_c = dswiglu(dx_h, w, sv.g[l])
+                dtmp_c = dgemm(dg_c, w.w13, w.w13_t)
                 dh_c, dh_c_h = ops.rmsnorm_bwd(dtmp_c, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx,
                                                 dx_h16=torch.empty(R, d, dtype=H16, device=dev))
-                do_c = ops.gemm_nt(dh_c_h, w.wo_t)
+                do_c = dgemm(dh_c_h, w.wo, w.wo_t)
                 dtmp.zero_()
                 ops.scatter_row_vectors(do_c, live_rows, dtmp)
                 dh.zero_()
@@ -751,28 +764,28 @@ class StepEngine:
                 dx = torch.empty(Tr, d, dtype=torch.float32, device=dev)          # full-size stream from here down
                 dx_h = torch.empty(Tr, d, dtype=H16, device=dev)
             else:
-                ops.gemm_swiglu_bwd(dx_h, w.w2_t, sv.g[l], dg=dg)                 # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
-                ops.gemm_nt(dg, w.w13_t, out=dtmp)                                 # d(ffn_norm out) = [da|db] . [W1;W3]
+                dswiglu(dx_h, w, sv.g[l], dg=dg)                                   # d[a|b] = swiglu'(g) . (dout . W2), dc stays on chip
+                dgemm(dg, w.w13, w.w13_t, out=dtmp)                                # d(ffn_norm out) = [da|db] . [W1;W3]
                 ops.rmsnorm_bwd(dtmp, sv.h[l], w.ffn_norm, sv.rstd2[l], dres=dx, dx=dh, dx_h16=dh_h)
-                ops.gemm_nt(dh_h, w.wo_t, out=dtmp)                               # d(attn out) = dh . Wo
+                dgemm(dh_h, w.wo, w.wo_t, out=dtmp)                               # d(attn out) = dh . Wo
             # attention sees the full layout: d(attn out) of the rows that were never computed is zero
             dout = ops.expand_rows(dtmp, plan.f2c, dst=do_full) if compact else dtmp
             ops.attn_bwd(sv.qkv[l], sv.akv[l], self.cos, self.sin, gate1[l], gate2[l], plan.vstart, sv.o[l], sv.lse[l], dout,
                          n_seq, S, H, hd, A, F, dqkv=dqkv, dakv=dakv, dgate1=grads.gate1[l], dgate2=grads.gate2[l], ws=self._attn_ws)
             dqkv_r = ops.gather_rows(dqkv, plan.c2f, dst=dqkv_c) if compact else dqkv
-            ops.gemm_nt(dqkv_r, w.wqkv_t, out=dtmp)                                # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
+            dgemm(dqkv_r, w.wqkv, w.wqkv_t, out=dtmp)                              # d(attn_norm out) = dqkv . [Wq;Wk;Wv]
             ops.rmsnorm_bwd(dtmp, sv.x[l], w.attn_norm, sv.rstd1[l], dres=dh, dx=dx_next, dx_h16=dx_next_h)
             # d adapter_l = dK_a . Wk + dV_a . Wv   (fp32 out, straight into the gradient rows of layer l): one grouped launch
             # per chunk of layers (their rows then become final together, which is what dp.GradSync reduces early)
             if tables is None:
                 ops.f32_to_h16(dakv, dakv_h)
-                ops.gemm_nt(dakv_h, w.wqkv_t[:, d:], out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
+                ops.gemm_nt(dakv_h, w.kv_t(d), out=grads.adapter[l * A:(l + 1) * A], out_fp32=True)
                 unscale(grads.adapter[l * A:(l + 1) * A])
             else:
                 ops.f32_to_h16(dakv, dakv_h_all[l])
                 if l % chunk == 0:
                     hi = min(l + chunk, L)
-                    ops.gemm_skinny_grouped(dakv_h_all[l:hi], tables[1][l:hi], 3 * d, d, grads.adapter.view(L, A, d)[l:hi])
+                    ops.gemm_skinny_grouped(dakv_h_all[l:hi], tables[1][l:hi], tables[2], d, grads.adapter.view(L, A, d)[l:hi])
                     unscale(grads.adapter.view(L, A, d)[l:hi])                       # final rows of this chunk, before dp.GradSync reduces them
             dx, dx_next = dx_next, dx
             dx_h, dx_next_h = dx_next_h, dx_h

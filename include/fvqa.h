@@ -105,6 +105,15 @@ int fvqa_gemm_swiglu_bwd(const fvqa_h16* dY, int ldy, const fvqa_h16* W2t, int l
                          fvqa_h16* dG, int lddg, int M, int hid, int K, void* stream);
 
 
+/* dX-only backward WITHOUT transposed weight copies: C[M,N] = A[M,K] . B[K,N] with B the forward's row-major [out = K, in = N] weight
+ * (leading dimension ldb >= N), read as an MN-major tcgen05 operand; h16 in / out, fp32 accumulation, same tiles and k order as
+ * fvqa_gemm_nt on the transposed copy (bit-identical results). K % 64 == 0, N % 8 == 0. fvqa_gemm_swiglu_bwd_nn is
+ * fvqa_gemm_swiglu_bwd with W2 [K = d, hid] instead of W2t [hid, K]. */
+int fvqa_gemm_nn(const fvqa_h16* A, int lda, const fvqa_h16* B, int ldb, fvqa_h16* C, int ldc, int M, int N, int K,
+                 void* stream);
+int fvqa_gemm_swiglu_bwd_nn(const fvqa_h16* dY, int ldy, const fvqa_h16* W2, int ldw, const fvqa_h16* G, int ldg,
+                            fvqa_h16* dG, int lddg, int M, int hid, int K, void* stream);
+
 /* ---- fused attention (llama/model.py:61-67 RoPE, :87-126 attention incl. adapter branch). --------
  * qkv  [n_seq*S, 3*H*hd] h16 (q | k | v) with q,k ALREADY rotated (fvqa_gemm_nt_rope).
  * akv  [>=A rows, ld akv_ld] h16: adapter keys (cols 0..H*hd) | adapter values (cols H*hd..2*H*hd),

@@ -260,6 +260,39 @@ def test_decode_step_projections(fvqa_lib, M, H, hd, hid):
     assert relerr(y, cact.float() @ w2.float().t() + res) < 2e-4 and relerr(y, y_tc) < 1e-4
 
 
+@pytest.mark.parametrize("M,N,K", [(3072, 4096, 12288), (3072, 4096, 4096), (2304, 4096, 22016), (260, 4096, 4096), (180, 4096, 32000),
+                                   (700, 1536, 384), (129, 520, 128), (40, 264, 64)])
+def test_gemm_nn_equals_nt_on_transposed_copy(fvqa_lib, M, N, K):
+    """dX = dY . W from the forward's [out, in] weight (MN-major tcgen05 B operand, `fvqa_gemm_nn`) must be BIT-identical to the
+    K-major kernel on a transposed copy of W (same tiles, same k order) - incl. the 2x2-cluster variant on the N = 4096 shapes, ragged
+    M / N, and nothing written out of bounds."""
+    from flipped_vqa_b200 import ops
+    a = h16_randn(M, K, seed=101)
+    w = h16_randn(K, N, std=0.05, seed=102)                      # forward weight [out = K, in = N]
+    buf = torch.full((M + 2, N), 7.0, device="cuda", dtype=H16)
+    out = ops.gemm_nn(a, w, out=buf[1:M + 1])
+    prev = fvqa_lib.fvqa_gemm_debug_force_bn(256)                 # the NN kernel always uses 256-wide tiles
+    try:
+        ref = ops.gemm_nt(a, w.t().contiguous())
+    finally:
+        fvqa_lib.fvqa_gemm_debug_force_bn(prev)
+    assert relerr(out, a.float() @ w.float()) < 5e-3
+    assert torch.equal(out, ref) or relerr(out, ref) < 1e-6       # quad / pair scheduling differs for some shapes: same math
+    assert torch.all(buf[0].float() == 7.0) and torch.all(buf[M + 1].float() == 7.0)
+
+
+def test_gemm_swiglu_bwd_nn(fvqa_lib):
+    """SwiGLU backward through W2 read as [d, hid] (no transposed copy) == the K-major kernel on W2^T, bit for bit."""
+    from flipped_vqa_b200 import ops
+    M, d, hid = 700, 256, 768
+    dy = h16_randn(M, d, seed=111)
+    w2 = h16_randn(d, hid, std=0.05, seed=112)
+    g = h16_randn(M, 2 * hid, seed=113)
+    a = ops.gemm_swiglu_bwd(dy, w2, g, nn=True)
+    b = ops.gemm_swiglu_bwd(dy, w2.t().contiguous(), g)
+    assert torch.equal(a, b)
+
+
 def test_gemm_strided_views(fvqa_lib):
     """Sub-blocks of larger matrices (used for Wk|Wv of the fused QKV weight and its transpose)."""
     from flipped_vqa_b200 import ops

@@ -301,6 +301,29 @@ def test_last_layer_live_row_pruning_is_equivalent(fvqa_lib):
     assert torch.equal(tok[0], tok[1])
 
 
+def test_weights_held_once_equals_transposed_copies(fvqa_lib):
+    """`Transformer.weights_once` (default): the dX-only backward reads the forward weights as MN-major tcgen05 operands instead of
+    load-time transposed copies. Same tiles, same k order -> identical losses and gradients, half the frozen-weight memory."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=512, n_layers=3, n_heads=4, vocab_size=1024, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=128, adapter_len=10, adapter_layer=3)
+    args = make_args()
+    sd = synthetic_state_dict(SimpleNamespace(**pd), seed=81, max_feats=args.max_feats, bias=args.bias)
+    data = synthetic_batch(4, 128, 1024, max_feats=args.max_feats, seed=82)
+    res = []
+    for once in (True, False):
+        model = build_product_model(pd, sd, args)
+        model.weights_once = once
+        losses = _run_product(model, data)
+        lw = model._run_weights[0]
+        assert (lw.wqkv_t is None) == once and (lw.wkv_t is not None) == once and (model._output_t is None) == once
+        res.append((losses, product_grads(model)))
+    (l0, g0), (l1, g1) = res
+    assert l0 == l1
+    for n in g0:
+        assert rel_l2(g0[n], g1[n]) < 1e-6, n
+
+
 @pytest.mark.parametrize("dim,heads,S", [(256, 2, 128), (256, 4, 64), (256, 2, 200)])
 def test_shared_prefix_option_scoring_equals_dense(fvqa_lib, dim, heads, S):
     """Validation path: evaluating the option-invariant prefix once (step.OptionPlan,

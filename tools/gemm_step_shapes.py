@@ -49,6 +49,13 @@ def main():
         ("wot dX        N=4096  K=4096 ", lambda: ops.gemm_nt(x, wo, out=o16), 2. * T * d * d, (x, wo)),
         ("wqkvt dX      N=4096  K=12288", lambda: ops.gemm_nt(dqkv, wqkv_t, out=o16), 2. * T * d * 3 * d, (dqkv, wqkv_t)),
     ]
+    # the four dX GEMMs again, reading the FORWARD weight as an MN-major operand (no transposed copy: the product's default)
+    nn_cases = [
+        ("w2+swiglu' NN N=11008 K=4096 ", lambda: ops.gemm_swiglu_bwd(x, w2, g, dg=dgo, nn=True), 2. * T * hid * d),
+        ("w13 dX NN     N=4096  K=22016", lambda: ops.gemm_nn(dg, w13, out=o16), 2. * T * d * 2 * hid),
+        ("wo dX NN      N=4096  K=4096 ", lambda: ops.gemm_nn(x, wo, out=o16), 2. * T * d * d),
+        ("wqkv dX NN    N=4096  K=12288", lambda: ops.gemm_nn(dqkv, wqkv, out=o16), 2. * T * d * 3 * d),
+    ]
     tot = {"pair": 0.0, "cublas": 0.0}
     for name, fn, fl, (a, b) in cases:
         row = []
@@ -61,6 +68,12 @@ def main():
         row.append(f"cublas plain {us:6.1f} us {fl / us / 1e6:5.0f} TF/s")
         print(name, " | ".join(row), flush=True)
     print("layer total: " + " | ".join(f"{k}: {v:.0f} us" for k, v in tot.items()))
+    nn_tot = 0.0
+    for name, fn, fl in nn_cases:
+        us = timeit(fn)
+        nn_tot += us
+        print(name, f"pair kernel, MN-major B {us:6.1f} us {fl / us / 1e6:5.0f} TF/s", flush=True)
+    print(f"dX GEMMs without transposed copies: {nn_tot:.0f} us per layer")
 
 
 if __name__ == "__main__":
