@@ -98,7 +98,12 @@ def val_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: torc
                 break
             continue
         with torch.no_grad():
-            individual_losses = inner.inference_plan(plan) if plan is not None else model(data, inference=True)
+            if plan is not None:
+                individual_losses = inner.inference_plan(plan)
+            elif hasattr(inner, "inference"):        # the loss-based scorer even if the MODEL was built with is_generation_task set
+                individual_losses = inner.inference(data)
+            else:
+                individual_losses = model(data, inference=True)
             prediction = inner.predict_options(individual_losses)
         eval_exact_match = (answer.to(prediction.device) == prediction).cpu()
         acc = eval_exact_match.sum().item() / bsz
