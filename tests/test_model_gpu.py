@@ -208,6 +208,17 @@ def test_7b_nextqa_full_depth_vs_oracle(fvqa_lib):
     _full_depth_parity("7b-nextqa", 32, 8, 128)
 
 
+def test_7b_tvqa_full_depth_vs_oracle(fvqa_lib):
+    """BASELINE.json configs[4]: LLaMA-7B, all 32 layers, TVQA-shaped S=650 bs=1 (non-tile-multiple sequence, six key tiles)."""
+    _full_depth_parity("7b-tvqa", 32, 1, 650, full_length=True)
+
+
+def test_13b_nextqa_full_depth_vs_oracle(fvqa_lib):
+    """BASELINE.json configs[3]: LLaMA-13B (d 5120, 40 heads, hidden 13824), all 40 layers, S=128; batch 2 keeps the fp32 oracle's
+    autograd graph (and the 52 GB of fp32 weights beside the product's copy) inside one GPU."""
+    _full_depth_parity("13b-nextqa", 40, 2, 128, dim=5120, heads=40)
+
+
 def test_7b_dramaqa_full_depth_vs_oracle(fvqa_lib):
     """BASELINE.json configs[2]: LLaMA-7B, all 32 layers, DramaQA-shaped S=384, bs=2 (tiled long-sequence attention)."""
     _full_depth_parity("7b-dramaqa", 32, 2, 384)
