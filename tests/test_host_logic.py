@@ -291,3 +291,33 @@ def test_log_qtype_meters_match_reference_formulas():
     ml3 = misc.MetricLogger()
     misc.log_qtype(data, hit, ml3, argparse.Namespace(dataset="tvqa"))
     assert not ml3.meters
+
+
+def test_save_result_merges_rank_files(tmp_path):
+    """`util/misc.py:570-610`: per-rank result files merged by the main process (single process here: rank 0 only)."""
+    import json
+    from flipped_vqa_b200.util import misc
+    res = [{"video_id": "v0", "question": "q", "generated_answer": "a"}, {"video_id": "v1", "question": "q2", "generated_answer": "b"}]
+    final = misc.save_result(res, str(tmp_path), "extracted_answers_epoch0")
+    assert final.endswith("extracted_answers_epoch0.json")
+    assert json.load(open(final)) == res and json.load(open(tmp_path / "extracted_answers_epoch0_rank0.json")) == res
+    d = misc.save_result({"a": torch.tensor([1, 2])}, str(tmp_path), "blob", is_json=False, is_list=False)
+    assert torch.equal(torch.load(d, weights_only=False)["a"], torch.tensor([1, 2]))
+
+
+def test_generation_batch_layout():
+    """The synthetic validation batch of the generation evaluator follows the layout `llama/model.py:367-546` relies on:
+    prefix_index = index(answer token) + 5 = first answer position, labels = answer span incl. EOS, 31 steps fit the sequence."""
+    from flipped_vqa_b200.synthetic import GEN_QUESTION_MARKER, synthetic_generation_batch
+    d = synthetic_generation_batch(5, 96, 1024, a_token_id=900, seed=4, n_options=4)
+    ids, lab = d["text_id"]["vqa"], d["label"]["vqa"]
+    assert ids.shape == lab.shape == (5, 4, 96)
+    for b, p in enumerate(d["prefix_index"]["vqa"]):
+        row = ids[b, 0].tolist()
+        assert row.index(900) + 5 == p and GEN_QUESTION_MARKER in row[:p] and p + 30 <= 95
+        assert row[12:22] == [0] * 10                                         # video placeholders at video_start
+        for o in range(4):
+            assert torch.equal(ids[b, o, :p], ids[b, 0, :p])                  # options differ only in the answer span
+            span = (lab[b, o] != 0).nonzero().flatten().tolist()
+            assert span[0] == p and span == list(range(p, p + len(span))) and int(ids[b, o, span[-1]]) == 2   # ends with EOS
+            assert torch.equal(lab[b, o, span], ids[b, o, span])
