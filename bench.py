@@ -313,6 +313,7 @@ def main():
     ap.add_argument("--no-padfree", action="store_true", help="skip the extra padding-free leg")
     ap.add_argument("--sample-layers", type=int, default=2, help="layers whose GEMM launches are event-timed inside the timed region")
     ap.add_argument("--chunk-layers", type=int, default=8, help="N > 1: layers per early adapter-gradient all-reduce message (dp.GradSync)")
+    ap.add_argument("--chunk-ctas", type=int, default=0, help="N > 1: CTA cap of the NCCL communicator that carries the overlapped chunk messages (0 = one communicator)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-the-same-GPU comparator leg (N = 1)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
@@ -345,7 +346,7 @@ def main():
         for blk in model.layers:
             blk.attention.gate1.normal_(0, 0.5)
     model.repack()
-    net = DataParallel(model, chunk_layers=a.chunk_layers) if world > 1 else model
+    net = DataParallel(model, chunk_layers=a.chunk_layers, chunk_ctas=a.chunk_ctas) if world > 1 else model
     trainables = [p for p in model.parameters() if p.requires_grad]
     opt = torch.optim.AdamW(trainables, lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
 
@@ -513,7 +514,7 @@ def main():
             "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": _lib.DTYPE_NAME, "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAMES[a.config], "operands": f"{_lib.DTYPE_NAME} weights / activations / gradients (tcgen05 kind::f16, fp32 accumulate), fp32 residual stream and trainables", "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}", "allreduce_chunk_layers": (a.chunk_layers if world > 1 else None), "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
+            "config": {"workload": WORKLOAD_NAMES[a.config], "operands": f"{_lib.DTYPE_NAME} weights / activations / gradients (tcgen05 kind::f16, fp32 accumulate), fp32 residual stream and trainables", "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}", "allreduce_chunk_layers": (a.chunk_layers if world > 1 else None), "allreduce_chunk_ctas": (a.chunk_ctas if world > 1 else None), "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
                        "l2": "working set (2 x 13.5 GB frozen weights + 9 GB saved activations per step) >> 126 MB L2; no explicit flush",
                        "objectives": "vqa+vaq+qav", "optimizer": "AdamW(fused) on 4.5M trainables", "flops_per_step": step_flops,
                        "labelled_rows_per_step": n_lab,

@@ -24,10 +24,14 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, grad_buffers, n_layers_run: int, adapter_len: int, dim: int, group=None, chunk_layers: int = 8):
+    def __init__(self, grad_buffers, n_layers_run: int, adapter_len: int, dim: int, group=None, chunk_layers: int = 8, chunk_group=None):
         self.gb = grad_buffers
         self.L, self.A, self.d = n_layers_run, adapter_len, dim
         self.group = group
+        # communicator of the EARLY (overlapped) chunk messages; None = the same as the late message's. DataParallel passes a second NCCL
+        # communicator limited to a couple of CTAs: an overlapped all-reduce only has to finish before the end of backward, and every
+        # SM it holds is one the persistent GEMMs (sized for all 148) cannot use
+        self.chunk_group = chunk_group if chunk_group is not None else group
         self.world = dist.get_world_size(group)
         self.chunk = max(1, chunk_layers)
         self.works: List = []
@@ -36,8 +40,8 @@ class GradSync:
         self.acc = None                # sum of the local flat gradients of the skipped micro-steps since the last reduce
         self.timing = None             # list -> (event before, event after) the stream-level wait on NCCL in finish() per step
 
-    def _reduce(self, t: torch.Tensor):
-        self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+    def _reduce(self, t: torch.Tensor, group=None):
+        self.works.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group if group is not None else self.group, async_op=True))
         self.messages += 1
 
     def warm_up(self, rounds: int = 3):
@@ -52,7 +56,7 @@ class GradSync:
             for l in range(self.L - 1, -1, -1):
                 if l % self.chunk == 0:
                     hi = min(l + self.chunk, self.L)
-                    works.append(dist.all_reduce(scratch[l * self.A * self.d: hi * self.A * self.d], group=self.group, async_op=True))
+                    works.append(dist.all_reduce(scratch[l * self.A * self.d: hi * self.A * self.d], group=self.chunk_group, async_op=True))
             works.append(dist.all_reduce(scratch[self.gb.late_offset:], group=self.group, async_op=True))
             for w in works:
                 w.wait()
@@ -67,7 +71,7 @@ class GradSync:
             lo_, hi_ = l * self.A * self.d, hi * self.A * self.d
             if self.acc is not None:
                 self.gb.flat[lo_:hi_].add_(self.acc[lo_:hi_])
-            self._reduce(self.gb.flat[lo_:hi_])
+            self._reduce(self.gb.flat[lo_:hi_], self.chunk_group)
 
     def finish(self):
         """Late message (gates, visual_proj, temporal_emb), wait for everything, turn the sum into a mean."""
@@ -102,11 +106,22 @@ class DataParallel(torch.nn.Module):
     """`model = DataParallel(model)`; exposes `.module` like torch's DDP so `train.py:117`,
     `util/misc.py:297-317` keep working. Broadcasts the trainable parameters from rank 0 once (C2)."""
 
-    def __init__(self, module, group=None, chunk_layers: int = 8, broadcast: bool = True):
+    def __init__(self, module, group=None, chunk_layers: int = 8, broadcast: bool = True, chunk_ctas: int = 0):
         super().__init__()
         self.module = module
         self.group = group
         self.chunk_layers = chunk_layers
+        # optional second NCCL communicator for the overlapped chunk messages, capped at `chunk_ctas` CTAs (0 = default: use `group` for
+        # everything). Measured at 2 GPUs (profiles/r2_ab_chunk_ctas.txt): caps of 1 / 2 CTAs do not reduce the slow-down of the overlapped GEMMs.
+        self.chunk_group = None
+        if chunk_ctas > 0 and dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.max_ctas = int(chunk_ctas)
+                opts.config.min_ctas = 1
+                self.chunk_group = dist.new_group(ranks=(dist.get_process_group_ranks(group) if group is not None else None), pg_options=opts)
+            except Exception:                                 # older torch / NCCL without communicator config: one communicator
+                self.chunk_group = None
         self.require_backward_grad_sync = True                  # same attribute as torch DDP (`no_sync()` clears it)
         if broadcast and dist.is_initialized() and dist.get_world_size(group) > 1:
             for p in module.parameters():
@@ -117,7 +132,8 @@ class DataParallel(torch.nn.Module):
         m = self.module
         m._ensure_packed()
         if m.grad_sync is None or m.grad_sync.gb is not m._grad_buffers:
-            m.grad_sync = GradSync(m._grad_buffers, len(m.run_layers()), m.adapter_len, m.params.dim, self.group, self.chunk_layers)
+            m.grad_sync = GradSync(m._grad_buffers, len(m.run_layers()), m.adapter_len, m.params.dim, self.group, self.chunk_layers,
+                                   chunk_group=self.chunk_group)
             m._engine.adapter_grad_chunk = self.chunk_layers    # adapter gradient rows become final in the chunks GradSync reduces
             if m._grad_buffers.flat.is_cuda:
                 m.grad_sync.warm_up()
