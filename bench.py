@@ -95,7 +95,7 @@ def make_args():
 class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index: int, period: float = 0.1):
+    def __init__(self, index: int, period: float = 0.2):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.power, self.reasons = [], [], set()
@@ -115,6 +115,12 @@ class ClockSampler(threading.Thread):
                 import pynvml
                 pynvml.nvmlInit()
                 h = pynvml.nvmlDeviceGetHandleByIndex(index)
+                # every query the sampling thread will issue, once, before the warm-up: NVML initialises each lazily, and a first call
+                # landing inside the timed region stalls that rank's launches (one 150 ms step among 75 ms ones -> every rank waits)
+                pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                pynvml.nvmlDeviceGetPowerUsage(h)
+                (pynvml.nvmlDeviceGetCurrentClocksEventReasons if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons")
+                 else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons)(h)
                 ClockSampler._cache[index] = (pynvml, h, pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
             except Exception:
                 ClockSampler._cache[index] = (None, None, None)
