@@ -145,6 +145,55 @@ def test_objective_flags(fvqa_lib, vaq, qav):
     _compare_with_oracle(pd, dict(bsz=2, seqlen=64, video_start=12), make_args(vaq=vaq, qav=qav), seed=5)
 
 
+def test_edge_cases_vs_oracle(fvqa_lib):
+    """Edge inputs of `Transformer.forward` (`llama/model.py:250-365`) against the oracle: a batch of ONE sample; a sample whose VAQ
+    stream has no labelled token (it still contributes keys but no rows to the mean); a stream with NO labelled token in the whole
+    batch (`CrossEntropyLoss` mean over an empty set: NaN in the reference, NaN here); sequences of very different real lengths."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=96, adapter_len=10, adapter_layer=3)
+    args = make_args()
+    params = SimpleNamespace(**pd)
+    sd = synthetic_state_dict(params, seed=91, max_feats=args.max_feats, bias=args.bias)
+
+    def both(data):
+        model = build_product_model(pd, sd, args)
+        losses = _run_product(model, data)
+        ref_losses, ref_grads = _oracle_on_gpu(pd, sd, data, args)
+        return model, losses, ref_losses, ref_grads
+
+    # (1) a single sample
+    model, losses, ref_losses, ref_grads = both(synthetic_batch(1, 96, 512, max_feats=args.max_feats, seed=92))
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) / abs(b) < LOSS_RTOL
+    _check_grads(product_grads(model), ref_grads)
+    # (2) one sample without VAQ labels, one very short and one full-length sequence
+    data = synthetic_batch(4, 96, 512, max_feats=args.max_feats, seed=93)
+    data["label"]["vaq"][1] = 0
+    for k in ("vqa", "vaq"):
+        data["text_id"][k][2, :, 40:] = 0                     # a short sequence: everything after position 40 is padding
+        data["label"][k][2] = 0
+        data["label"][k][2, :, 36:40] = data["text_id"][k][2, :, 36:40]
+    model, losses, ref_losses, ref_grads = both(data)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) / abs(b) < LOSS_RTOL
+    _check_grads(product_grads(model), ref_grads)
+    # (3) no VAQ label in the whole batch: mean over an empty set
+    data = synthetic_batch(3, 96, 512, max_feats=args.max_feats, seed=94)
+    data["label"]["vaq"][:] = 0
+    model = build_product_model(pd, sd, args)
+    vqa, vaq, qav = model(data)
+    st = O.prepare_state(sd, frozen_dtype=torch.float32, device="cuda")
+    r_vqa, r_vaq, r_qav = O.forward_losses(st, params, data, max_feats=args.max_feats, tau=args.tau)
+    assert torch.isnan(r_vaq) and torch.isnan(vaq)
+    assert abs(float(vqa) - float(r_vqa)) / float(r_vqa) < LOSS_RTOL and abs(float(qav) - float(r_qav)) / float(r_qav) < LOSS_RTOL
+    (vqa + qav).backward()                                    # the empty stream must not poison the others' gradients
+    (r_vqa + r_qav).backward()
+    grads = product_grads(model)
+    assert all(torch.isfinite(g).all() for g in grads.values())
+    _check_grads(grads, {n: st[n].grad.detach().float().cpu() for n in O.trainable_names(st) if st[n].grad is not None})
+
+
 def test_7b_shaped_two_layer_slice_vs_oracle(fvqa_lib):
     """LLaMA-7B layer shapes (d 4096, 32 heads, hidden 11008, V 32000), B=8, S=128, 2 layers."""
     pd = dict(dim=4096, n_layers=2, n_heads=32, vocab_size=32000, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
