@@ -100,3 +100,47 @@ def rel_l2(a, b):
 
 def product_grads(model):
     return {n: p.grad.detach().float().cpu() for n, p in model.named_parameters() if p.requires_grad and p.grad is not None}
+
+
+def full_depth_argmax_report(items=256, layers=32, per=8, dim=4096, heads=32, seqlen=128):
+    """north_star's third criterion at FULL depth: loss-based option scoring (`llama/model_my_original_mod.py:375-377` +
+    `engine.py:88-93`) of the product vs the fp32 oracle (TF32 off) on the same random-init weights, `items` x 5 options. Returns
+    the agreement, the per-option normalised-loss error and the oracle's best-vs-runner-up margins (an item whose margin is below
+    the loss error can flip legitimately). Used by tests/test_model_gpu.py and tools/argmax_full_depth.py."""
+    from oracle import llama_vqa_oracle as O
+    from flipped_vqa_b200 import _lib
+    from flipped_vqa_b200.synthetic import synthetic_batch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pd = dict(dim=dim, n_layers=layers, n_heads=heads, vocab_size=32000, multiple_of=256, norm_eps=1e-6, max_batch_size=64,
+              max_seq_len=seqlen, adapter_len=10, adapter_layer=layers)
+    args = make_args()
+    sd = big_state_dict(pd, seed=0)
+    model = build_product_model(pd, sd, args)
+    st = O.prepare_state(sd, frozen_dtype=torch.float32, device="cuda", requires_grad=False)
+    del sd
+    agree = total = 0
+    errs, margins, flipped = [], [], []
+    for b in range(items // per):
+        data = synthetic_batch(per, seqlen, pd["vocab_size"], max_feats=args.max_feats, seed=1000 + b, n_options=5)
+        with torch.no_grad():
+            tok = model(data, inference=True)
+            pred = model.predict_options(tok).cpu()
+            ref_tok = O.option_token_losses(st, SimpleNamespace(**pd), data, max_feats=args.max_feats)
+        ref_pred = O.option_predict(ref_tok).cpu()
+        cnt = (ref_tok != 0).sum(-1).clamp(min=1)
+        score = (tok.float() * (ref_tok != 0)).sum(-1) / cnt                       # normalised loss per (item, option)
+        ref_score = ref_tok.sum(-1) / cnt
+        errs.append((score - ref_score).abs().max(-1).values.cpu())
+        top2 = ref_score.topk(2, dim=-1, largest=False).values
+        m = (top2[:, 1] - top2[:, 0]).cpu()
+        margins.append(m)
+        flipped += m[pred != ref_pred].tolist()
+        agree += int((pred == ref_pred).sum())
+        total += pred.numel()
+    errs, margins = torch.cat(errs), torch.cat(margins)
+    return {"task": "option-scoring argmax agreement at full depth", "operand_dtype": _lib.DTYPE_NAME, "dim": dim, "layers": layers,
+            "items": total, "options": 5, "seqlen": seqlen, "agree": agree, "agreement": agree / total,
+            "normalised_loss_abs_err_max": float(errs.max()), "normalised_loss_abs_err_median": float(errs.median()),
+            "oracle_margin_min": float(margins.min()), "oracle_margin_median": float(margins.median()),
+            "items_with_margin_below_2x_max_err": int((margins < 2 * errs.max()).sum()),
+            "oracle_margins_of_flipped_items": flipped}
