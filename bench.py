@@ -521,7 +521,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": _lib.DTYPE_NAME, "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[a.config], "operands": f"{_lib.DTYPE_NAME} weights / activations / gradients (tcgen05 kind::f16, fp32 accumulate), fp32 residual stream and trainables", "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}", "allreduce_chunk_layers": (a.chunk_layers if world > 1 else None), "allreduce_chunk_ctas": (a.chunk_ctas if world > 1 else None), "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
-                       "l2": "working set (2 x 13.5 GB frozen weights + 9 GB saved activations per step) >> 126 MB L2; no explicit flush",
+                       "l2": "working set (13.5 GB frozen weights read in both passes + 2.1 GB transposed Wk|Wv + 9 GB saved activations per step at 7B) >> 126 MB L2; no explicit flush",
                        "objectives": "vqa+vaq+qav", "optimizer": "AdamW(fused) on 4.5M trainables", "flops_per_step": step_flops,
                        "labelled_rows_per_step": n_lab,
                        "last_layer_live_rows": (n_live if model._engine.prune_last_layer else None),
