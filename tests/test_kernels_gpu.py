@@ -400,6 +400,18 @@ def _attention_fwd_bwd_case(n_seq, S, H, hd, vstarts, A, F):
     assert relerr(dg2, ref_dg2) < 2e-2, f"dgate2 {relerr(dg2, ref_dg2)} {dg2} {ref_dg2}"
 
 
+@pytest.mark.parametrize("A,F", [(1, 1), (4, 6), (7, 3), (16, 12)])
+@pytest.mark.parametrize("S,hd,use_tc", [(48, 64, 1), (128, 128, 1), (100, 128, 1), (200, 128, 1), (128, 128, 0)])
+def test_attention_adapter_len_and_max_feats(fvqa_lib, A, F, S, hd, use_tc):
+    """`--adapter_len` / `--max_feats` are command-line arguments of the reference (`train.py`), not constants: every attention path
+    (mma.sync, tcgen05 one tile / partial tile / tiled) with 1..16 adapter prompts and 1..12 video columns under the gate2 bias."""
+    prev = fvqa_lib.fvqa_attn_debug_use_tc(use_tc)
+    try:
+        _attention_fwd_bwd_case(2, S, 2, hd, [18, -1], A, F)
+    finally:
+        fvqa_lib.fvqa_attn_debug_use_tc(prev)
+
+
 @pytest.mark.parametrize("S", [128, 300])
 def test_attention_deterministic(fvqa_lib, S):
     from flipped_vqa_b200 import ops

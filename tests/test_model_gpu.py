@@ -145,6 +145,15 @@ def test_objective_flags(fvqa_lib, vaq, qav):
     _compare_with_oracle(pd, dict(bsz=2, seqlen=64, video_start=12), make_args(vaq=vaq, qav=qav), seed=5)
 
 
+@pytest.mark.parametrize("adapter_len,max_feats,dim,heads", [(4, 6, 256, 4), (16, 12, 256, 2), (1, 2, 256, 2), (7, 3, 512, 4)])
+def test_adapter_len_and_max_feats_vs_oracle(fvqa_lib, adapter_len, max_feats, dim, heads):
+    """`--adapter_len` and `--max_feats` other than 10 (`train.py` arguments; `llama/model.py:193,203,207`): prompt count of the adapter
+    softmax, number of video slots / temporal embeddings / QAV classes. head_dim 64 (mma.sync) and 128 (tcgen05)."""
+    pd = dict(dim=dim, n_layers=3, n_heads=heads, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=96, adapter_len=adapter_len, adapter_layer=2)
+    _compare_with_oracle(pd, dict(bsz=3, seqlen=96, video_start=14), make_args(max_feats=max_feats), seed=31)
+
+
 def test_edge_cases_vs_oracle(fvqa_lib):
     """Edge inputs of `Transformer.forward` (`llama/model.py:250-365`) against the oracle: a batch of ONE sample; a sample whose VAQ
     stream has no labelled token (it still contributes keys but no rows to the mean); a stream with NO labelled token in the whole
