@@ -404,8 +404,10 @@ class Transformer(nn.Module):
             losses, _ = self._engine.forward(plan, self._run_weights, self.tok_embeddings.weight.data, self.output.weight.data,
                                              self.norm.weight.data, trainables[0].data, trainables[1].data, trainables[2].data,
                                              g1, g2, save=False, akv_pre=akv_pre)
-        zero = lambda: torch.tensor([0], device=dev)        # disabled objectives, `model.py:302`
-        return losses["vqa"], losses.get("vaq", zero()), losses.get("qav", zero())
+        # disabled objectives return `torch.tensor([0]).cuda()` (`model.py:302`). Built on the device, and only when needed: a
+        # torch.tensor(list, device=cuda) is a pageable-memory H2D copy, i.e. a host sync on everything the step has enqueued so far
+        zero = lambda: torch.zeros(1, dtype=torch.int64, device=dev)
+        return losses["vqa"], (losses["vaq"] if "vaq" in losses else zero()), (losses["qav"] if "qav" in losses else zero())
 
     def plan_options(self, data) -> OptionPlan:
         """Host side of shared-prefix option scoring (`step.OptionPlan`) + its async H2D copy."""
