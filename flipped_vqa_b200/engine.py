@@ -40,15 +40,26 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: to
         else:
             vqa_loss, vaq_loss, qav_loss = model(data)
         loss = vqa_loss + vaq_loss + qav_loss
-        # one D2H read for all four logged values (also the step's only host sync), BEFORE backward / the optimizer step as in
-        # `engine.py:28-35`: a non-finite loss must never reach the trainables or the AdamW state
-        vals = torch.stack([loss.detach().float().reshape(()), vqa_loss.detach().float().reshape(()),
-                            vaq_loss.detach().float().reshape(()), qav_loss.detach().float().reshape(())]).tolist()
+        stacked = torch.stack([loss.detach().float().reshape(()), vqa_loss.detach().float().reshape(()),
+                               vaq_loss.detach().float().reshape(()), qav_loss.detach().float().reshape(())])
+        vals = []
+
+        def read_and_check():
+            # one D2H read for all four logged values (the step's only host sync). A non-finite loss must never reach the
+            # trainables or the AdamW state (`engine.py:28-35` exits before backward): the read happens before the optimizer
+            # is touched - with our scaler AFTER backward has been enqueued, so the host waits for the forward pass while
+            # the GPU is already running backward instead of idling until the host has launched it
+            vals.extend(stacked.tolist())
+            if not math.isfinite(vals[0]):
+                print("Loss is {}, stopping training".format(vals[0]))
+                sys.exit(1)
+
+        if getattr(loss_scaler, "accepts_before_step", False):
+            loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update, before_step=read_and_check)
+        else:                                        # any other scaler with the reference's signature: check first, like the reference
+            read_and_check()
+            loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update)
         loss_value = vals[0]
-        if not math.isfinite(loss_value):
-            print("Loss is {}, stopping training".format(loss_value))
-            sys.exit(1)
-        loss_scaler(loss / accum_iter, optimizer, parameters=model.parameters(), update_grad=update)
         if update:
             optimizer.zero_grad()
         metric_logger.update(loss=loss_value, vqa_loss=vals[1], vaq_loss=vals[2], qav_loss=vals[3])

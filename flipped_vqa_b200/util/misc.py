@@ -172,8 +172,14 @@ class NativeScalerWithGradNormCount:
     def __init__(self, enabled: bool = False):
         self._scaler = torch.amp.GradScaler("cuda", enabled=enabled)
 
-    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):
+    accepts_before_step = True     # engine.train_one_epoch: this scaler can run the finite-loss check between backward and the update
+
+    def __call__(self, loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True, before_step=None):
+        """`before_step` (optional callable) runs after backward has been ENQUEUED and before anything touches the optimizer:
+        the place for a host-side read of the loss (it then waits for the forward pass while the GPU is already in backward)."""
         self._scaler.scale(loss).backward(create_graph=create_graph)
+        if before_step is not None:
+            before_step()
         if update_grad:
             self._scaler.unscale_(optimizer)
             if clip_grad is not None:

@@ -124,3 +124,44 @@ def test_product_training_trajectory_matches_reference(fvqa_lib):
         assert cos > 0.98, (n, cos)
         assert abs(float(d_got.norm() / d_ref.norm()) - 1.0) < 0.05, n
         assert rel_l2(snap[(e, n)], ref_p) < 1e-2, n
+
+
+@pytest.mark.parametrize("reference_style_scaler", [False, True])
+def test_non_finite_loss_exits_before_the_optimizer_is_touched(reference_style_scaler):
+    """`engine.py:33-35`: 'Loss is nan, stopping training' + sys.exit(1), and the non-finite loss never reaches the trainables or the
+    AdamW state - with our scaler (check between backward and the update) and with any scaler that only has the reference's
+    signature (check before backward, like the reference)."""
+    from flipped_vqa_b200 import engine
+    from flipped_vqa_b200.util import misc
+
+    class _NaNOnSecondStep(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(4))
+            self.calls = 0
+
+        def forward(self, data):
+            self.calls += 1
+            base = (self.w * self.w).sum()
+            bad = base * float("nan") if self.calls == 2 else base
+            return bad, base.detach() * 0 + 1.0, base.detach() * 0 + 2.0
+
+    model = _NaNOnSecondStep()
+    opt = torch.optim.AdamW(model.parameters(), lr=0.1)
+    ours = misc.NativeScalerWithGradNormCount()
+    steps = []
+
+    def ref_style(loss, optimizer, clip_grad=None, parameters=None, create_graph=False, update_grad=True):   # `util/misc.py:259-273`
+        steps.append("scaler")
+        return ours(loss, optimizer, clip_grad=clip_grad, parameters=parameters, create_graph=create_graph, update_grad=update_grad)
+
+    args = argparse.Namespace(accum_iter=1, lr=0.1, min_lr=0.0, warmup_epochs=0, epochs=1, debug=False)
+    with pytest.raises(SystemExit) as ex:
+        engine.train_one_epoch(model, [{}, {}, {}], opt, 0, ref_style if reference_style_scaler else ours, args=args)
+    assert ex.value.code == 1
+    assert model.calls == 2
+    assert torch.isfinite(model.w).all()                              # the NaN step never reached the parameters ...
+    st = opt.state[model.w]
+    assert int(st["step"]) == 1 and torch.isfinite(st["exp_avg"]).all() and torch.isfinite(st["exp_avg_sq"]).all()   # ... nor AdamW's moments
+    if reference_style_scaler:
+        assert steps == ["scaler"]                                    # second call never happened: the check ran before backward

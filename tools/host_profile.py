@@ -14,7 +14,7 @@ from flipped_vqa_b200.synthetic import synthetic_batch
 
 def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "7b-nextqa"
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 5
     cfg = dict(B.CONFIGS[name], name=name)
     dev = torch.device("cuda", 0)
     params = ModelArgs(dim=cfg["dim"], n_layers=cfg["n_layers"], n_heads=cfg["n_heads"], vocab_size=cfg["vocab_size"], multiple_of=cfg["multiple_of"],
@@ -27,10 +27,24 @@ def main():
     opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.95), weight_decay=0.05, fused=True)
     plans = [model.plan_batch(synthetic_batch(cfg["bsz"], cfg["seqlen"], cfg["vocab_size"], max_feats=B.MAX_FEATS, seed=i)) for i in range(2)]
 
+    e2e = "--e2e" in sys.argv                    # through model(data) with host tensors + a loss read, like bench.py's e2e leg
+    batches = [synthetic_batch(cfg["bsz"], cfg["seqlen"], cfg["vocab_size"], max_feats=B.MAX_FEATS, seed=i) for i in range(2)]
+
     def step(i):
-        vqa, vaq, qav = model.forward_plan(plans[i % 2])
-        (vqa + vaq + qav).backward()
+        vqa, vaq, qav = model(batches[i % 2]) if e2e else model.forward_plan(plans[i % 2])
+        loss = vqa + vaq + qav
+        loss.backward()
         opt.step(); opt.zero_grad(set_to_none=True)
+        if e2e:
+            loss.item()
+
+    if "--val" in sys.argv:                      # validation: loss-based option scoring through model(data, inference=True) + predict_options
+        vb = [synthetic_batch(cfg["bsz"], cfg["seqlen"], cfg["vocab_size"], max_feats=B.MAX_FEATS, seed=i, n_options=5) for i in range(2)]
+
+        def step(i):                             # noqa: F811
+            with torch.no_grad():
+                tok = model(vb[i % 2], inference=True)
+                return model.predict_options(tok).cpu()
 
     for i in range(3):
         step(i)
