@@ -66,6 +66,7 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: to
         metric_logger.update(lr=optimizer.param_groups[0]["lr"])
         if getattr(args, "debug", False):
             break
+    gc.unfreeze()                                    # back into the collector's generations until the next epoch freezes again
     metric_logger.synchronize_between_processes()
     print("Averaged stats:", metric_logger)
     return {k: meter.global_avg for k, meter in metric_logger.meters.items()}
