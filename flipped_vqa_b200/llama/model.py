@@ -235,6 +235,9 @@ class Transformer(nn.Module):
         # a load-time transposed copy (-13.5 GB at 7B, -26 GB at 13B, half the load time). False = the round-1 layout (A/B, tests).
         self.weights_once = os.environ.get("FVQA_WEIGHTS_ONCE", "1") != "0"
         self._akv_pre = None                                # adapter K|V enqueued ahead of host planning (forward(data))
+        # False (default) = the reference: video_start of SAMPLE 0 places the video span and the gate2 bias block of every sample
+        # (`model.py:264`); True = every sample's own value (the kernels take one video_start per sequence)
+        self.per_sample_video_start = False
 
     # ------------------------------------------------------------------ weight layout
     def run_layers(self):
@@ -327,7 +330,8 @@ class Transformer(nn.Module):
         streams = ["vqa"] if inference else self.streams()
         data, post = self._fuse_inputs(data)
         compact = self._engine is not None and self._engine.skip_pad_rows        # padding-free row maps only when they are used
-        return post(BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned, compact=compact).to_device(self._device))
+        return post(BatchPlan(data, streams, self.max_feats, inference=inference, pool=self._pinned, compact=compact,
+                              per_sample_video_start=self.per_sample_video_start).to_device(self._device))
 
     def _fuse_inputs(self, data):
         """The input-fusion branches of `model.py:306-322` reduced to what the step kernels see: a feature matrix
@@ -414,7 +418,8 @@ class Transformer(nn.Module):
         if self._pinned is None:
             self._pinned = PinnedPool()
         data, post = self._fuse_inputs(data)
-        return post(OptionPlan(data, self.max_feats, pool=self._pinned).to_device(self._device))
+        return post(OptionPlan(data, self.max_feats, pool=self._pinned,
+                               per_sample_video_start=self.per_sample_video_start).to_device(self._device))
 
     @torch.no_grad()
     def inference(self, data):

@@ -30,7 +30,7 @@ class BatchPlan:
     pinned int32 buffer (one H2D copy) plus the fp32 video features."""
 
     def __init__(self, data: Dict, streams: List[str], max_feats: int, inference: bool = False, pool: "PinnedPool" = None,
-                 compact: bool = True):
+                 compact: bool = True, per_sample_video_start: bool = False):
         F = max_feats
         ids = {k: _cpu(data["text_id"][k]) for k in streams}
         lab = {k: _cpu(data["label"][k]) for k in streams}
@@ -45,9 +45,17 @@ class BatchPlan:
         labels_all = torch.zeros(self.n_seq, S, dtype=I32)
         vstart = torch.empty(self.n_seq, dtype=I32)
         seq_video = (torch.arange(per) // n_opt).repeat(len(streams)).to(I32)
-        # the reference reads video_start of sample 0 only (`llama/model.py:264`)
+        # the reference reads video_start of sample 0 only (`llama/model.py:264`); the kernels take one value per sequence, so
+        # `per_sample_video_start` (opt-in) gives every sample its own video span / gate2 column block
         for si, k in enumerate(streams):
-            vstart[si * per:(si + 1) * per] = -1 if k == "qav" else int(data["video_start"][k][0])
+            if k == "qav":
+                vstart[si * per:(si + 1) * per] = -1
+            elif per_sample_video_start:
+                vs_b = torch.as_tensor([int(v) for v in data["video_start"][k]], dtype=I32)
+                assert vs_b.numel() == B, f"video_start[{k}] has {vs_b.numel()} entries for a batch of {B}"
+                vstart[si * per:(si + 1) * per] = vs_b.repeat_interleave(n_opt)
+            else:
+                vstart[si * per:(si + 1) * per] = int(data["video_start"][k][0])
         qav_index = torch.zeros(B, F, dtype=I32)
         self.ce_counts: Dict[str, int] = {}
         ce_rows, ce_tgt, ce_dst = [], [], []
@@ -157,7 +165,7 @@ class OptionPlan:
       f2c[n_seq * S]    compact row holding full row's values, -1 for rows past E_b (never read: causal)
     """
 
-    def __init__(self, data: Dict, max_feats: int, pool: "PinnedPool" = None):
+    def __init__(self, data: Dict, max_feats: int, pool: "PinnedPool" = None, per_sample_video_start: bool = False):
         ids = _cpu(data["text_id"]["vqa"]).long()
         lab = _cpu(data["label"]["vqa"]).long()
         B, n_opt, S = ids.shape
@@ -200,8 +208,12 @@ class OptionPlan:
         live = torch.unique(ce_rows, sorted=True)                             # last layer: wo / FFN on these only
         self.n_live = int(live.numel())
         ce_rows_c = torch.searchsorted(live, ce_rows)
-        vs = int(data["video_start"]["vqa"][0])                               # sample 0's, `model_my_original_mod.py:264`
-        vstart = torch.full((self.n_seq,), vs, dtype=I32)
+        if per_sample_video_start:                                            # opt-in, see BatchPlan
+            vstart = torch.as_tensor([int(v) for v in data["video_start"]["vqa"]], dtype=I32).repeat_interleave(n_opt)
+            assert vstart.numel() == self.n_seq
+        else:
+            vs = int(data["video_start"]["vqa"][0])                           # sample 0's, `model_my_original_mod.py:264`
+            vstart = torch.full((self.n_seq,), vs, dtype=I32)
         seq_video = (torch.arange(self.n_seq) // n_opt).to(I32)
         parts = [ids.reshape(-1), torch.zeros(self.T, dtype=I32), vstart, seq_video, torch.zeros(B * F, dtype=I32),
                  pos_ids, c2f, f2c, ce_rows, ce_tgt, ce_dst, live, ce_rows_c]

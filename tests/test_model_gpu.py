@@ -154,6 +154,65 @@ def test_adapter_len_and_max_feats_vs_oracle(fvqa_lib, adapter_len, max_feats, d
     _compare_with_oracle(pd, dict(bsz=3, seqlen=96, video_start=14), make_args(max_feats=max_feats), seed=31)
 
 
+def _cat_batches(parts):
+    """Concatenate single-sample batch dicts (dataloader/__init__.py:28-90 layout) along the sample axis."""
+    out = {}
+    for k, v in parts[0].items():
+        if isinstance(v, torch.Tensor):
+            out[k] = torch.cat([p[k] for p in parts], 0)
+        elif isinstance(v, dict):
+            out[k] = {kk: (torch.cat([p[k][kk] for p in parts], 0) if isinstance(vv, torch.Tensor) else sum((list(p[k][kk]) for p in parts), []))
+                      for kk, vv in v.items()}
+        else:
+            out[k] = sum((list(p[k]) for p in parts), [])
+    return out
+
+
+def test_per_sample_video_start(fvqa_lib):
+    """the reference places the video span and the gate2 bias block of EVERY sample at sample 0's video_start
+    (`llama/model.py:264`); `Transformer.per_sample_video_start = True` uses each sample's own value. Checked against the oracle
+    run sample by sample (each with its own video_start) and recombined with the batch's token-count weights (CE is a mean over
+    all labelled tokens of the batch, `model.py:233-235`), losses and gradients; and that the default still is sample 0's."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=96, adapter_len=10, adapter_layer=3)
+    args = make_args()
+    params = SimpleNamespace(**pd)
+    sd = synthetic_state_dict(params, seed=61, max_feats=args.max_feats, bias=args.bias)
+    singles = [synthetic_batch(1, 96, 512, max_feats=args.max_feats, seed=70 + i, video_start=vs) for i, vs in enumerate((12, 20, 16))]
+    data = _cat_batches(singles)
+    assert data["video_start"]["vqa"] == [12, 20, 16]
+    model = build_product_model(pd, sd, args)
+    model.per_sample_video_start = True
+    losses = _run_product(model, data)
+    grads = product_grads(model)
+    # oracle: one sample at a time, weights = labelled tokens of the sample / labelled tokens of the batch, per objective
+    st = O.prepare_state(sd, frozen_dtype=torch.float32, device="cuda")
+    counts = [[float((d["label"]["vqa"][:, :, 1:] != 0).sum()), float((d["label"]["vaq"][:, :, 1:] != 0).sum()),
+               float((d["label"]["qav"][:, :, 1:] >= 0).sum())] for d in singles]
+    tot = [sum(c[k] for c in counts) for k in range(3)]
+    ref = [0.0, 0.0, 0.0]
+    total = 0
+    for d, c in zip(singles, counts):
+        ls = O.forward_losses(st, params, d, max_feats=args.max_feats, tau=args.tau, vaq=True, qav=True)
+        for k in range(3):
+            total = total + ls[k] * (c[k] / tot[k])
+            ref[k] += float(ls[k].detach()) * c[k] / tot[k]
+    total.backward()
+    ref_grads = {n: st[n].grad.detach().float().cpu() for n in O.trainable_names(st) if st[n].grad is not None}
+    for name, a, b in zip(("vqa", "vaq", "qav"), losses, ref):
+        assert abs(a - b) / abs(b) < LOSS_RTOL, f"{name} loss {a} vs per-sample oracle {b}"
+    assert set(grads) == set(ref_grads)
+    _check_grads(grads, ref_grads)
+    # default: the reference's sample-0 rule (the batch-level oracle implements exactly that) - and it differs from the above
+    model2 = build_product_model(pd, sd, args)
+    l0 = _run_product(model2, data)
+    ref0, _ = _oracle_on_gpu(pd, sd, data, args)
+    for a, b in zip(l0, ref0):
+        assert abs(a - b) / abs(b) < LOSS_RTOL
+    assert abs(l0[0] - losses[0]) / abs(losses[0]) > 1e-4 or abs(l0[1] - losses[1]) / abs(losses[1]) > 1e-4
+
+
 def test_edge_cases_vs_oracle(fvqa_lib):
     """Edge inputs of `Transformer.forward` (`llama/model.py:250-365`) against the oracle: a batch of ONE sample; a sample whose VAQ
     stream has no labelled token (it still contributes keys but no rows to the mean); a stream with NO labelled token in the whole
