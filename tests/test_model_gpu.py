@@ -154,6 +154,39 @@ def test_adapter_len_and_max_feats_vs_oracle(fvqa_lib, adapter_len, max_feats, d
     _compare_with_oracle(pd, dict(bsz=3, seqlen=96, video_start=14), make_args(max_feats=max_feats), seed=31)
 
 
+def test_training_step_enqueues_without_host_sync(fvqa_lib):
+    """The step must never wait for the GPU on the host: `model(data)` (host planning + pinned H2D), backward and the fused AdamW
+    update run under torch's sync debug mode 'error', which raises on any implicit synchronisation (a pageable-memory copy, .item(),
+    a blocking allocation ...). Round 2 found one by profiling (a torch.tensor([0], device=cuda) per forward_plan call)."""
+    from flipped_vqa_b200.synthetic import synthetic_batch, synthetic_state_dict
+    pd = dict(dim=256, n_layers=3, n_heads=2, vocab_size=512, multiple_of=256, norm_eps=1e-6, max_batch_size=32,
+              max_seq_len=96, adapter_len=10, adapter_layer=3)
+    for vaq, qav in ((True, True), (False, False)):            # the disabled-objective placeholders are on the path too
+        args = make_args(vaq=vaq, qav=qav)
+        sd = synthetic_state_dict(SimpleNamespace(**pd), seed=77, max_feats=args.max_feats, bias=args.bias)
+        model = build_product_model(pd, sd, args)
+        opt = torch.optim.AdamW([p for p in model.parameters() if p.requires_grad], lr=1e-3, fused=True)
+        batches = [synthetic_batch(4, 96, 512, max_feats=args.max_feats, seed=80 + i) for i in range(3)]
+
+        def step(i):
+            vqa, vaq_l, qav_l = model(batches[i])
+            (vqa + vaq_l + qav_l).backward()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+
+        step(0)                                                 # set-up (packing, workspace, NCCL-free): may synchronise
+        torch.cuda.synchronize()
+        prev = torch.cuda.get_sync_debug_mode()
+        torch.cuda.set_sync_debug_mode("error")
+        try:
+            step(1)
+            step(2)
+        finally:
+            torch.cuda.set_sync_debug_mode(prev)
+        torch.cuda.synchronize()
+        assert all(torch.isfinite(p).all() for p in model.parameters() if p.requires_grad)
+
+
 def _cat_batches(parts):
     """Concatenate single-sample batch dicts (dataloader/__init__.py:28-90 layout) along the sample axis."""
     out = {}
