@@ -176,15 +176,22 @@ def test_training_step_enqueues_without_host_sync(fvqa_lib):
 
         step(0)                                                 # set-up (packing, workspace, NCCL-free): may synchronise
         torch.cuda.synchronize()
+        val = [synthetic_batch(4, 96, 512, max_feats=args.max_feats, seed=90 + i, n_options=5) for i in range(2)]
+        with torch.no_grad():
+            model.predict_options(model(val[0], inference=True))    # set-up of the validation path
+        torch.cuda.synchronize()
         prev = torch.cuda.get_sync_debug_mode()
         torch.cuda.set_sync_debug_mode("error")
         try:
             step(1)
             step(2)
+            with torch.no_grad():                               # validation: shared-prefix option scoring up to the device-side argmin
+                pred = model.predict_options(model(val[1], inference=True))
         finally:
             torch.cuda.set_sync_debug_mode(prev)
         torch.cuda.synchronize()
         assert all(torch.isfinite(p).all() for p in model.parameters() if p.requires_grad)
+        assert pred.shape == (4,)
 
 
 def _cat_batches(parts):
