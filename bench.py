@@ -490,6 +490,21 @@ def main():
         ms_e, _, clocks_e, _ = timed(step_e2e, a.steps)
     e2e_value = world * B / (ms_e / a.steps * 1e-3)
 
+    # Host side: wall-clock time to ENQUEUE one resident step with an empty GPU queue (no sync inside; N = 1 only: at N > 1 the
+    # ranks would have to stay in lock-step for the NCCL calls). Outside every timed region.
+    host = None
+    if world == 1:
+        import time as _time
+        ts = []
+        for i in range(5):
+            torch.cuda.synchronize()
+            t0 = _time.perf_counter()
+            step_resident(i)
+            ts.append((_time.perf_counter() - t0) * 1e3)
+        torch.cuda.synchronize()
+        host = {"enqueue_ms_per_step": round(sorted(ts)[len(ts) // 2], 2), "launches_per_step": launches / a.steps,
+                "what": "median host wall-clock time of forward_plan + backward + AdamW with an empty GPU queue and no synchronisation"}
+
     # Extra leg (not the headline): the opt-in padding-free row set (StepEngine.skip_pad_rows) on the same resident batches
     padfree = None
     if not a.no_padfree:
@@ -517,7 +532,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "7B NExT-QA train samples/s" if a.config == "7b-nextqa" else f"{a.config} train samples/s",
-            "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "host": host,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": _lib.DTYPE_NAME, "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[a.config], "operands": f"{_lib.DTYPE_NAME} weights / activations / gradients (tcgen05 kind::f16, fp32 accumulate), fp32 residual stream and trainables", "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}", "allreduce_chunk_layers": (a.chunk_layers if world > 1 else None), "allreduce_chunk_ctas": (a.chunk_ctas if world > 1 else None), "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
