@@ -12,6 +12,8 @@ One JSON line on stdout (rank 0). A "step" = forward + hand-written backward + g
   roofline     : tcgen05 GEMM launches sampled with CUDA events inside the timed region
   cpu_baseline : the oracle (CPU port of the reference's step): one real full-depth step at a bounded batch
   gpu_eager_baseline : the reference's op sequence in eager PyTorch on the same GPU (N = 1), outside the timed regions
+  alt_build    : the same resident-batch measurement with the other operand build (bf16 when the default fp16 library is loaded), child
+                 process on the same GPU (N = 1)
   dp_check / comm    : N > 1: hardware check that the reduced gradient is the rank mean; exposed NCCL wait and rank skew
 `--impl reference` times that CPU port with all host threads, every timed step a real full-depth step at
 a bounded batch (the reference itself is pure PyTorch and /root/reference does not exist on the GPU box).
@@ -254,6 +256,30 @@ def run_reference_arm(a, guard):
     guard.emit(json.dumps(line))
 
 
+def alt_build_leg(a):
+    """The same resident-batch measurement with the OTHER operand build of the library (FVQA_DTYPE: bf16 when this process loaded
+    fp16 and vice versa), in a child process on the same GPU right after this one's legs: the operand format is a property of
+    the build, north_star names bf16, the default build is fp16 because that is the one that meets the gradient
+    tolerance at full depth. Not the headline; outside every timed region of this process."""
+    import subprocess
+    from flipped_vqa_b200 import _lib
+    other = "bf16" if _lib.DTYPE_NAME == "fp16" else "fp16"
+    cmd = [sys.executable, os.path.abspath(__file__), "--config", a.config, "--steps", str(a.steps), "--warmup", str(a.warmup),
+           "--no-e2e", "--no-padfree", "--no-cpu-baseline", "--no-eager-baseline", "--no-alt-build"]
+    try:
+        torch.cuda.empty_cache()
+        r = subprocess.run(cmd, env={**os.environ, "FVQA_DTYPE": other}, capture_output=True, text=True, timeout=600)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        d = json.loads(lines[-1])
+        return {"dtype": d["dtype"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                "tensor_util": d["tensor_util"]["value"], "gemm_tflops_in_step": d["roofline"]["achieved"], "gemm_frac_of_sustained_peak": d["roofline"]["frac"],
+                "clocks": d["clocks"],
+                "what": f"python bench.py with FVQA_DTYPE={other} (lib{'fvqa_bf16' if other == 'bf16' else 'fvqa'}.so), same GPU, same config / steps / warm-up, "
+                        "resident batch; gradient parity of this build at full depth: DESIGN.md 5"}
+    except Exception as e:          # informative leg: never lose the headline numbers over it
+        return {"dtype": other, "value": None, "what": f"failed: {e}"}
+
+
 def gpu_eager_baseline(model, cfg, dev, steps=3):
     """SURVEY 8(d) last row: the reference's op sequence (`llama/model.py:250-365`: three streams one after another, unfused
     attention with materialised scores, full-vocabulary logits, autograd) in stock eager PyTorch on the SAME GPU, in the
@@ -321,6 +347,7 @@ def main():
     ap.add_argument("--chunk-layers", type=int, default=8, help="N > 1: layers per early adapter-gradient all-reduce message (dp.GradSync)")
     ap.add_argument("--chunk-ctas", type=int, default=0, help="N > 1: CTA cap of the NCCL communicator that carries the overlapped chunk messages (0 = one communicator)")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-the-same-GPU comparator leg (N = 1)")
+    ap.add_argument("--no-alt-build", action="store_true", help="skip the leg that runs the OTHER operand build (bf16 when this is fp16) on the same GPU (N = 1)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
@@ -575,6 +602,8 @@ def main():
                 line["gpu_eager_baseline"]["speedup_of_this_repo"] = value / line["gpu_eager_baseline"]["value"]
             except Exception as e:
                 line["gpu_eager_baseline"] = {"value": None, "unit": "samples/s", "what": f"failed: {e}"}
+        if world == 1 and not a.no_alt_build and not a.no_e2e:      # (--no-e2e = profiling runs: no child processes under ncu)
+            line["alt_build"] = alt_build_leg(a)
         if world == 1 and not a.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(cfg)
