@@ -268,7 +268,7 @@ def alt_build_leg(a):
            "--no-e2e", "--no-padfree", "--no-cpu-baseline", "--no-eager-baseline", "--no-alt-build"]
     try:
         torch.cuda.empty_cache()
-        r = subprocess.run(cmd, env={**os.environ, "FVQA_DTYPE": other}, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, env={**os.environ, "FVQA_DTYPE": other}, capture_output=True, text=True, timeout=240)
         lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
         d = json.loads(lines[-1])
         return {"dtype": d["dtype"], "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
