@@ -105,6 +105,23 @@ def test_batch_plan_rows_and_targets():
     assert torch.equal(ql.flatten()[qrows + 1], arr["q_tgt"].long())
 
 
+def test_plans_video_start_rule():
+    """Default: sample 0's video_start for every sample of the batch (`llama/model.py:264`); `per_sample_video_start=True`: each
+    sample's own, repeated over its options; the QAV stream never has one (-1). Host-side arrays only (no GPU)."""
+    from flipped_vqa_b200.step import BatchPlan, OptionPlan
+    from flipped_vqa_b200.synthetic import synthetic_batch
+    data = synthetic_batch(3, 64, 256, seed=9, video_start=12, n_options=2)
+    data["video_start"] = {"vqa": [12, 15, 9], "vaq": [11, 14, 8], "qav": data["video_start"]["qav"]}
+    vstart = lambda plan: plan.host_ints[plan._slices[2][0]:plan._slices[2][0] + plan._slices[2][1]].tolist()
+    assert vstart(BatchPlan(data, ["vqa", "vaq", "qav"], 10)) == [12] * 6 + [11] * 6 + [-1] * 6
+    assert vstart(BatchPlan(data, ["vqa", "vaq", "qav"], 10, per_sample_video_start=True)) == \
+        [12, 12, 15, 15, 9, 9] + [11, 11, 14, 14, 8, 8] + [-1] * 6
+    assert OptionPlan(data, 10).host("vstart").tolist() == [12] * 6
+    assert OptionPlan(data, 10, per_sample_video_start=True).host("vstart").tolist() == [12, 12, 15, 15, 9, 9]
+    with pytest.raises(AssertionError):
+        BatchPlan(dict(data, video_start={"vqa": [12, 15], "vaq": [11, 14], "qav": [0, 0]}), ["vqa"], 10, per_sample_video_start=True)
+
+
 def test_batch_plan_padding_free_rows():
     """BatchPlan's compact row set: every sequence keeps exactly the rows [0, last loss-relevant position]; the loss row
     lists re-indexed into it point at the same (sequence, position) pairs."""
