@@ -532,6 +532,28 @@ def main():
         host = {"enqueue_ms_per_step": round(sorted(ts)[len(ts) // 2], 2), "launches_per_step": launches / a.steps,
                 "what": "median host wall-clock time of forward_plan + backward + AdamW with an empty GPU queue and no synchronisation"}
 
+    # HBM-bound kernels (north_star: achieved GB/s of the norm / attention kernels against the HBM roofline): CUDA events around
+    # every C-ABI call of three extra resident steps (outside every timed region; N = 1). Algorithmic bytes per launch;
+    # event time includes the launch gap in front of the kernel, so these are lower bounds of the kernels' own rates.
+    hbm_kernels = None
+    if world == 1 and not a.no_e2e:
+        ops.OP_TIMER = ops.OpTimer()
+        for i in range(3):
+            step_resident(i)
+        torch.cuda.synchronize()
+        agg, ops.OP_TIMER = ops.OP_TIMER.summary(), None
+        T_all, dm = 3 * B * S, cfg["dim"]
+        per_launch = {"rmsnorm_fwd": T_all * dm * 6.0, "rmsnorm_bwd": T_all * dm * 16.0, "attn_fwd": T_all * dm * 8.0, "attn_bwd": T_all * dm * 16.0}
+        hbm_peak = measured_peaks()["hbm_gbs"]
+        hbm_kernels = {"peak_gbs": hbm_peak, "what": "algorithmic bytes per launch / in-step CUDA-event time per launch (events include the launch gap); "
+                                                     "rmsnorm fwd 6d, bwd 16d, attention fwd 8d, bwd 16d bytes per token"}
+        for name, nbytes in per_launch.items():
+            if name in agg and agg[name][0] > 0:
+                us = agg[name][1] / agg[name][0] * 1e3
+                # the pruned last layer runs its second norm on a handful of rows: the per-launch average is slightly optimistic in bytes
+                hbm_kernels[name] = {"avg_us": round(us, 1), "gbs": round(nbytes / (us * 1e-6) / 1e9, 0), "frac": round(nbytes / (us * 1e-6) / 1e9 / hbm_peak, 3),
+                                     "launches_per_step": agg[name][0] / 3}
+
     # Extra leg (not the headline): the opt-in padding-free row set (StepEngine.skip_pad_rows) on the same resident batches
     padfree = None
     if not a.no_padfree:
@@ -559,7 +581,7 @@ def main():
     if rank == 0:
         line = {
             "metric": "7B NExT-QA train samples/s" if a.config == "7b-nextqa" else f"{a.config} train samples/s",
-            "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "host": host,
+            "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "host": host, "hbm_kernels": hbm_kernels,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": _lib.DTYPE_NAME, "data": "synthetic",
             "config": {"workload": WORKLOAD_NAMES[a.config], "operands": f"{_lib.DTYPE_NAME} weights / activations / gradients (tcgen05 kind::f16, fp32 accumulate), fp32 residual stream and trainables", "global_batch": world * B, "seq_len": S, "parallelism": f"dp{world}", "allreduce_chunk_layers": (a.chunk_layers if world > 1 else None), "allreduce_chunk_ctas": (a.chunk_ctas if world > 1 else None), "nccl_env": {k: v for k, v in os.environ.items() if k.startswith("NCCL_")},
